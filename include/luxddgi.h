@@ -1,0 +1,278 @@
+/*
+ * luxddgi.h — C ABI of the B200-native DDGI probe-update engine (libluxddgi.so).
+ *
+ * This is the drop-in boundary for the SDF-traced branch of the Maple renderer's DDGI pass
+ * (flwmxd/LuxGI).  The reference has no C ABI; its "operator API" for this path is the three IoC
+ * systems registered by ddgi::registerDDGI (Engine/DDGI/DDGIRenderer.cpp:1016-1037):
+ *
+ *     trace_rays::system     DDGIRenderer.cpp:215-331   -> lux_ddgi_trace_rays
+ *     probe_update::system   DDGIRenderer.cpp:345-414   -> lux_ddgi_probe_update
+ *     border_update::system  DDGIRenderer.cpp:416-465   -> lux_ddgi_border_update
+ *     end_frame::system      DDGIRenderer.cpp:333-343   -> lux_ddgi_end_frame
+ *     ddgi::on_game_start    DDGIRenderer.cpp:563-690   -> lux_ddgi_uniform_from_volume + lux_ddgi_create
+ *     ddgi::on_game_end      DDGIRenderer.cpp:692-714   -> lux_ddgi_destroy
+ *
+ * Every struct below is byte-identical to the GLSL block / host twin it cites, so a maintainer can pass the
+ * engine's own uniform blocks and SSBO contents through unchanged.
+ *
+ * Plain C: pointers and sizes only.  All functions return LUX_OK (0) or a negative LuxStatus; none of them
+ * aborts.  lux_ddgi_last_error() returns a thread-local description of the last failure.
+ * A context is bound to one CUDA device and one stream; calls on one context are not thread-safe
+ * (the reference runs its systems sequentially on the render thread, IoC/SystemBuilder.h:202-208).
+ */
+#ifndef LUXDDGI_H
+#define LUXDDGI_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LUXDDGI_VERSION 0x00010000
+
+#if defined(__GNUC__)
+#define LUX_API __attribute__((visibility("default")))
+#else
+#define LUX_API
+#endif
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Status codes
+ * ------------------------------------------------------------------------------------------------------ */
+typedef enum LuxStatus {
+    LUX_OK                 = 0,
+    LUX_ERR_INVALID_ARG    = -1, /* null pointer, bad size, inconsistent uniform                           */
+    LUX_ERR_NOT_READY      = -2, /* stage called before its inputs were set                                */
+    LUX_ERR_CUDA           = -3, /* a CUDA runtime call failed; text in lux_ddgi_last_error()              */
+    LUX_ERR_NO_DEVICE      = -4, /* no usable sm_100 device: the engine has NO CPU fallback, it fails here */
+    LUX_ERR_OUT_OF_MEMORY  = -5,
+    LUX_ERR_UNSUPPORTED    = -6
+} LuxStatus;
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Constants of the pass (Engine/DDGI/DDGIRenderer.h:17-18, Shaders/SDF/SDFCommon.glsl:8-10,
+ * Shaders/SDF/AtlasCommon.glsl:5-6, Shaders/DDGI/ProbeUpdate.glsl:7)
+ * ------------------------------------------------------------------------------------------------------ */
+#define LUX_IRRADIANCE_OCT_SIZE                 8      /* interior texels per probe side, irradiance      */
+#define LUX_DEPTH_OCT_SIZE                      16     /* interior texels per probe side, depth           */
+#define LUX_GLOBAL_SDF_WORLD_SIZE               60000.0f
+#define LUX_GLOBAL_SDF_RASTERIZE_CHUNK_SIZE     32
+#define LUX_GLOBAL_SDF_RASTERIZE_CHUNK_MARGIN   4
+#define LUX_GLOBAL_SDF_MAX_STEPS                250
+#define LUX_SURFACE_ATLAS_CHUNKS_RESOLUTION     40
+#define LUX_SURFACE_ATLAS_TILE_NORMAL_THRESHOLD 0.05f
+#define LUX_MAX_CASCADES                        4
+
+/* ---------------------------------------------------------------------------------------------------------
+ * a1. DDGIUniform — probe-volume parameter block, `scalar` layout, 96 bytes.
+ *     Shaders/DDGI/DDGICommon.glsl:11-31; host twin Engine/DDGI/DDGIRenderer.h:22-42.
+ * ------------------------------------------------------------------------------------------------------ */
+typedef struct LuxDDGIUniform {
+    float   startPosition[4];          /* @0   world position of probe (0,0,0); w unused                  */
+    float   step[4];                   /* @16  probe spacing per axis; w unused                           */
+    int32_t probeCounts[4];            /* @32  X, Y, Z probes; w unused                                   */
+    float   maxDistance;               /* @48  depth clamp = 1.5 * probeDistance                          */
+    float   sharpness;                 /* @52  depth weight exponent (host twin: depthSharpness)          */
+    float   hysteresis;                /* @56                                                             */
+    float   normalBias;                /* @60  consumer only                                              */
+    float   ddgiGamma;                 /* @64                                                             */
+    int32_t irradianceProbeSideLength; /* @68  must be 8                                                  */
+    int32_t irradianceTextureWidth;    /* @72  10*X*Y + 2                                                 */
+    int32_t irradianceTextureHeight;   /* @76  10*Z + 2                                                   */
+    int32_t depthProbeSideLength;      /* @80  must be 16                                                 */
+    int32_t depthTextureWidth;         /* @84  18*X*Y + 2                                                 */
+    int32_t depthTextureHeight;        /* @88  18*Z + 2                                                   */
+    int32_t raysPerProbe;              /* @92                                                             */
+} LuxDDGIUniform;
+
+/* IrradianceVolume — the serialised user-facing component (Engine/DDGI/DDGIRenderer.h:44-66). */
+typedef struct LuxIrradianceVolume {
+    float   probeDistance;   /* 1.5  */
+    int32_t infiniteBounce;  /* 1    */
+    int32_t raysPerProbe;    /* 256  */
+    float   hysteresis;      /* 0.98 */
+    float   intensity;       /* 1.0  */
+    float   normalBias;      /* 0.1  */
+    float   depthSharpness;  /* 50   */
+    float   ddgiGamma;       /* 5    */
+} LuxIrradianceVolume;
+
+/* ---------------------------------------------------------------------------------------------------------
+ * a2. Trace push constants, 80 bytes (Shaders/DDGI/GISDFRays.comp:53-60; host DDGIRenderer.cpp:111-118).
+ *     Only the upper-left 3x3 of randomOrientation (column-major) is used by the SDF path.
+ * ------------------------------------------------------------------------------------------------------ */
+typedef struct LuxTracePushConstants {
+    float    randomOrientation[16]; /* column-major mat4: element (row r, col c) = m[c*4 + r]              */
+    uint32_t numFrames;             /* declared, unused by GISDFRays.comp                                  */
+    uint32_t infiniteBounces;       /* declared, unused by GISDFRays.comp                                  */
+    int32_t  numLights;             /* declared, unused by GISDFRays.comp                                  */
+    float    intensity;             /* declared, unused by GISDFRays.comp                                  */
+} LuxTracePushConstants;
+
+/* ---------------------------------------------------------------------------------------------------------
+ * a5. GlobalSDFData, std140, 96 bytes (Shaders/SDF/GlobalSDFData.glsl:4-12; host GlobalDistanceField.h:19-27).
+ *     SDF texture: R16F, [z][y][x] with x in [0, resolution*cascadesCount) — cascade c occupies
+ *     x in [c*res, (c+1)*res); value = world distance / (2*cascadePosDistance[c].w) clamped to [-1,1].
+ *     Mip texture: same with resolution/4 per axis.  Both sampled trilinear, clamp-to-edge
+ *     (GlobalDistanceField.cpp:615,621).
+ * ------------------------------------------------------------------------------------------------------ */
+typedef struct LuxGlobalSDFData {
+    float    cascadePosDistance[LUX_MAX_CASCADES][4]; /* @0   centre.xyz, half-extent.w                  */
+    float    cascadeVoxelSize[4];                     /* @64                                              */
+    uint32_t cascadesCount;                           /* @80                                              */
+    float    resolution;                              /* @84  voxels per cascade axis (float, as in GLSL) */
+    float    nearPlane;                               /* @88  unused on this path                         */
+    float    farPlane;                                /* @92  unused on this path                         */
+} LuxGlobalSDFData;
+
+/* ---------------------------------------------------------------------------------------------------------
+ * a6. Surface-cache records (Shaders/SDF/AtlasCommon.glsl:8-32; host GlobalSurfaceAtlas.cpp:59-73,
+ *     SurfaceAtlasTile.h:117-125).
+ * ------------------------------------------------------------------------------------------------------ */
+typedef struct LuxGlobalSurfaceAtlasData { /* 32 bytes */
+    float    cameraPos[3];           /* @0  unused by sampling                                            */
+    float    chunkSize;              /* @12 world size of one of the 40^3 culling chunks                  */
+    uint32_t culledObjectsCapacity;  /* @16                                                               */
+    uint32_t resolution;             /* @20 atlas side in texels                                          */
+    uint32_t objectsCount;           /* @24                                                               */
+    uint32_t padding;                /* @28                                                               */
+} LuxGlobalSurfaceAtlasData;
+
+typedef struct LuxObjectBuffer { /* std430, 128 bytes */
+    float    objectBounds[4];  /* @0   bounding sphere centre.xyz, radius.w                               */
+    uint32_t tileOffset[6];    /* @16  index into tiles[]; 0 = no tile                                    */
+    int32_t  padding[2];       /* @40                                                                     */
+    float    transform[16];    /* @48  column-major OBB local->world                                      */
+    float    extends[4];       /* @112 OBB half extents xyz, 1                                            */
+} LuxObjectBuffer;
+
+typedef struct LuxTileBuffer { /* std430, 96 bytes */
+    float extends[4];      /* @0   (tile x, tile y, width-1, height-1) / atlas resolution                 */
+    float transform[16];   /* @16  column-major tile view rotation (translation zeroed)                   */
+    float objectBounds[4]; /* @80  view-space bounds size xyz, 0                                          */
+} LuxTileBuffer;
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Engine-side types
+ * ------------------------------------------------------------------------------------------------------ */
+typedef struct LuxDDGIContext LuxDDGIContext; /* opaque */
+
+typedef enum LuxMemKind {
+    LUX_MEM_HOST   = 0, /* pointer is host memory; the engine copies it to the device                      */
+    LUX_MEM_DEVICE = 1  /* pointer is device memory on the context's device; the engine BORROWS it         */
+} LuxMemKind;
+
+enum {
+    LUX_DDGI_FLAG_NONE          = 0,
+    LUX_DDGI_FLAG_STAGE_TIMERS  = 1u << 0, /* record CUDA events around every stage (lux_ddgi_get_stage_ms)  */
+    LUX_DDGI_FLAG_UNFUSED_BORDER= 1u << 1, /* probe_update writes interiors only; border_update does borders */
+    LUX_DDGI_FLAG_SDF_TEXTURE   = 1u << 2  /* read the SDF through layered texture-object gathers            */
+};
+
+typedef struct LuxDDGICreateInfo {
+    int32_t  device;  /* CUDA device ordinal                                                              */
+    int32_t  rank;    /* z-slab shard owned by this context, 0 <= rank < world                            */
+    int32_t  world;   /* number of z-slab shards (1 = whole volume); must divide probeCounts.z            */
+    uint32_t flags;   /* LUX_DDGI_FLAG_*                                                                  */
+    void*    stream;  /* cudaStream_t to run on, or NULL for an engine-owned stream                       */
+} LuxDDGICreateInfo;
+
+typedef enum LuxBufferId {
+    LUX_BUF_RADIANCE            = 0, /* RGBA16F [probe_count(shard)][raysPerProbe]: rgb, 0                */
+    LUX_BUF_DIRECTION_DISTANCE  = 1, /* RGBA16F [probe_count(shard)][raysPerProbe]: dir.xyz, hit distance */
+    LUX_BUF_IRRADIANCE          = 2, /* RGBA16F [10Z+2][10XY+2], the atlas most recently written          */
+    LUX_BUF_DEPTH               = 3, /* RG16F   [18Z+2][18XY+2], the atlas most recently written          */
+    LUX_BUF_IRRADIANCE_PREV     = 4, /* the other half of the ping-pong pair                              */
+    LUX_BUF_DEPTH_PREV          = 5
+} LuxBufferId;
+
+typedef struct LuxDDGIState {
+    int32_t  frames;          /* frames completed (DDGIPipelineInternal::frames)                          */
+    int32_t  pingPong;        /* DDGIPipelineInternal::pingPong                                           */
+    int32_t  probeBegin;      /* first probe id of this shard                                             */
+    int32_t  probeCount;      /* probes in this shard                                                     */
+    int32_t  irradianceRowBegin, irradianceRowCount; /* atlas rows owned by this shard (all-gather unit)  */
+    int32_t  depthRowBegin, depthRowCount;
+    uint64_t kernelLaunches;  /* kernels launched by this context since creation                          */
+} LuxDDGIState;
+
+typedef struct LuxStageTimes { /* milliseconds of the last lux_ddgi_update, needs FLAG_STAGE_TIMERS */
+    float setup_ms, trace_ms, blend_ms, border_ms, total_ms;
+} LuxStageTimes;
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Entry points
+ * ------------------------------------------------------------------------------------------------------ */
+LUX_API uint32_t    lux_ddgi_version(void);
+LUX_API const char* lux_ddgi_last_error(void);
+
+/* Grid derivation of ddgi::on_game_start (DDGIRenderer.cpp:663-682) and delegates::uniformChanged (:975-1013):
+ * probeCounts = ivec3(sceneLength / probeDistance) + 2, start = aabb.min, step = probeDistance,
+ * maxDistance = 1.5 * probeDistance, atlas sizes.  Unlike the reference (SURVEY finding 8) raysPerProbe IS copied. */
+LUX_API int lux_ddgi_uniform_from_volume(const LuxIrradianceVolume* volume, const float aabbMin[3], const float aabbMax[3],
+                                 LuxDDGIUniform* out);
+/* Atlas sizing of init::initializeProbeGrid (DDGIRenderer.cpp:181-191): fills side lengths + texture sizes. */
+LUX_API int lux_ddgi_uniform_finalize(LuxDDGIUniform* uniform);
+
+/* Allocates ray buffers and the 2x2 ping-pong atlases (zero-filled), DDGIRenderer.cpp:163-211. */
+LUX_API int lux_ddgi_create(const LuxDDGIUniform* uniform, const LuxDDGICreateInfo* info, LuxDDGIContext** out);
+LUX_API int lux_ddgi_destroy(LuxDDGIContext* ctx);
+
+/* Runtime-editable fields only (hysteresis, sharpness, gamma, maxDistance, normalBias, start, step);
+ * probeCounts / raysPerProbe changes need a new context (the reference rebuilds its textures too, :505-561). */
+LUX_API int lux_ddgi_set_uniform(LuxDDGIContext* ctx, const LuxDDGIUniform* uniform);
+
+/* uGlobalSDF / uGlobalMipSDF + UniformBufferObject.sdfData (DDGIRenderer.cpp:304-305,314). fp16 texels. */
+LUX_API int lux_ddgi_set_global_sdf(LuxDDGIContext* ctx, const LuxGlobalSDFData* data,
+                            const void* sdfR16F, const void* mipR16F, LuxMemKind kind);
+
+/* SDFAtlasChunkBuffer, SDFCullObjectBuffer, SDFObjectBuffer, SDFAtlasTileBuffer, uSurfaceAtlasTex (RGBA16F,
+ * linear/repeat), uSurfaceAtlasDepth (D32F, clamp), UniformBufferObject.data (DDGIRenderer.cpp:306-313).
+ * chunks has 40^3 entries. */
+LUX_API int lux_ddgi_set_surface_atlas(LuxDDGIContext* ctx, const LuxGlobalSurfaceAtlasData* data,
+                               const uint32_t* chunks, const uint32_t* cullObjects, size_t cullObjectsCount,
+                               const LuxObjectBuffer* objects, size_t objectsCount,
+                               const LuxTileBuffer* tiles, size_t tilesCount,
+                               const void* lightCacheRGBA16F, const float* depthD32F, LuxMemKind kind);
+/* Per-frame relight: replaces the light-cache texels only (same resolution). */
+LUX_API int lux_ddgi_update_surface_light_cache(LuxDDGIContext* ctx, const void* lightCacheRGBA16F, LuxMemKind kind);
+
+/* uSkybox: 6 faces (+X,-X,+Y,-Y,+Z,-Z) of faceSize^2 RGBA16F texels.  Default = the reference's 1x1 black
+ * fallback cube (DDGIRenderer.cpp:308). */
+LUX_API int lux_ddgi_set_skybox(LuxDDGIContext* ctx, int32_t faceSize, const void* facesRGBA16F, LuxMemKind kind);
+
+/* The three stages + frame bookkeeping, in the order RenderGraph.cpp:98-114 runs them. */
+LUX_API int lux_ddgi_trace_rays(LuxDDGIContext* ctx, const LuxTracePushConstants* pushConsts);
+LUX_API int lux_ddgi_probe_update(LuxDDGIContext* ctx);  /* blend both atlases; borders fused unless UNFUSED_BORDER */
+LUX_API int lux_ddgi_border_update(LuxDDGIContext* ctx); /* idempotent; a no-op cost-wise when borders were fused   */
+LUX_API int lux_ddgi_end_frame(LuxDDGIContext* ctx);     /* pingPong ^= 1; frames++                                 */
+
+/* trace_rays + probe_update (+ border_update if unfused) + end_frame with rotation `orientation`
+ * (column-major mat4, as pushed at DDGIRenderer.cpp:271-272).  Asynchronous on the context's stream. */
+LUX_API int lux_ddgi_update(LuxDDGIContext* ctx, const float orientation[16]);
+
+LUX_API int lux_ddgi_synchronize(LuxDDGIContext* ctx);
+
+/* Outputs.  Device pointers stay valid until destroy; `bytes` may be NULL. */
+LUX_API int lux_ddgi_get_buffer(LuxDDGIContext* ctx, LuxBufferId id, void** devicePtr, size_t* bytes);
+LUX_API int lux_ddgi_download(LuxDDGIContext* ctx, LuxBufferId id, void* host, size_t bytes);
+/* Same, without the trailing synchronize: `pinnedHost` must be page-locked; order with lux_ddgi_synchronize. */
+LUX_API int lux_ddgi_download_async(LuxDDGIContext* ctx, LuxBufferId id, void* pinnedHost, size_t bytes);
+/* Overwrite the ray buffers (this shard's rows) — what probe_update consumes is whatever these hold, exactly as the
+ * reference's blend reads the iRadiance / iDirectionDistance images (ProbeUpdate.glsl:53-64).  Lets a host (or a test)
+ * run the blend stage on rays produced elsewhere. */
+LUX_API int lux_ddgi_set_ray_buffers(LuxDDGIContext* ctx, const void* radianceRGBA16F, const void* directionDistanceRGBA16F,
+                             LuxMemKind kind);
+/* Checkpoint/resume of the probe state (the reference never saves it): load both atlases + counters. */
+LUX_API int lux_ddgi_restore(LuxDDGIContext* ctx, const void* irradianceRGBA16F, const void* depthRG16F,
+                     int32_t frames, int32_t pingPong);
+
+LUX_API int lux_ddgi_get_state(LuxDDGIContext* ctx, LuxDDGIState* out);
+LUX_API int lux_ddgi_get_stage_ms(LuxDDGIContext* ctx, LuxStageTimes* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LUXDDGI_H */

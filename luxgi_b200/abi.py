@@ -1,0 +1,187 @@
+"""ctypes mirrors of the POD structs in include/luxddgi.h.
+
+Field-for-field twins of the reference's GLSL blocks (see the header for file:line citations):
+DDGIUniform (Shaders/DDGI/DDGICommon.glsl:11-31), GlobalSDFData (Shaders/SDF/GlobalSDFData.glsl:4-12),
+GlobalSurfaceAtlasData / ObjectBuffer / TileBuffer (Shaders/SDF/AtlasCommon.glsl:8-32), trace push constants
+(Shaders/DDGI/GISDFRays.comp:53-60).  Sizes are asserted at import time.
+"""
+import ctypes as C
+
+IRRADIANCE_OCT_SIZE = 8
+DEPTH_OCT_SIZE = 16
+GLOBAL_SDF_WORLD_SIZE = 60000.0
+CHUNKS_RESOLUTION = 40
+
+
+class DDGIUniform(C.Structure):
+    _fields_ = [
+        ("startPosition", C.c_float * 4),
+        ("step", C.c_float * 4),
+        ("probeCounts", C.c_int32 * 4),
+        ("maxDistance", C.c_float),
+        ("sharpness", C.c_float),
+        ("hysteresis", C.c_float),
+        ("normalBias", C.c_float),
+        ("ddgiGamma", C.c_float),
+        ("irradianceProbeSideLength", C.c_int32),
+        ("irradianceTextureWidth", C.c_int32),
+        ("irradianceTextureHeight", C.c_int32),
+        ("depthProbeSideLength", C.c_int32),
+        ("depthTextureWidth", C.c_int32),
+        ("depthTextureHeight", C.c_int32),
+        ("raysPerProbe", C.c_int32),
+    ]
+
+
+class IrradianceVolume(C.Structure):
+    _fields_ = [
+        ("probeDistance", C.c_float),
+        ("infiniteBounce", C.c_int32),
+        ("raysPerProbe", C.c_int32),
+        ("hysteresis", C.c_float),
+        ("intensity", C.c_float),
+        ("normalBias", C.c_float),
+        ("depthSharpness", C.c_float),
+        ("ddgiGamma", C.c_float),
+    ]
+
+
+class TracePushConstants(C.Structure):
+    _fields_ = [
+        ("randomOrientation", C.c_float * 16),
+        ("numFrames", C.c_uint32),
+        ("infiniteBounces", C.c_uint32),
+        ("numLights", C.c_int32),
+        ("intensity", C.c_float),
+    ]
+
+
+class GlobalSDFData(C.Structure):
+    _fields_ = [
+        ("cascadePosDistance", (C.c_float * 4) * 4),
+        ("cascadeVoxelSize", C.c_float * 4),
+        ("cascadesCount", C.c_uint32),
+        ("resolution", C.c_float),
+        ("nearPlane", C.c_float),
+        ("farPlane", C.c_float),
+    ]
+
+
+class GlobalSurfaceAtlasData(C.Structure):
+    _fields_ = [
+        ("cameraPos", C.c_float * 3),
+        ("chunkSize", C.c_float),
+        ("culledObjectsCapacity", C.c_uint32),
+        ("resolution", C.c_uint32),
+        ("objectsCount", C.c_uint32),
+        ("padding", C.c_uint32),
+    ]
+
+
+class ObjectBuffer(C.Structure):
+    _fields_ = [
+        ("objectBounds", C.c_float * 4),
+        ("tileOffset", C.c_uint32 * 6),
+        ("padding", C.c_int32 * 2),
+        ("transform", C.c_float * 16),
+        ("extends", C.c_float * 4),
+    ]
+
+
+class TileBuffer(C.Structure):
+    _fields_ = [
+        ("extends", C.c_float * 4),
+        ("transform", C.c_float * 16),
+        ("objectBounds", C.c_float * 4),
+    ]
+
+
+class CreateInfo(C.Structure):
+    _fields_ = [
+        ("device", C.c_int32),
+        ("rank", C.c_int32),
+        ("world", C.c_int32),
+        ("flags", C.c_uint32),
+        ("stream", C.c_void_p),
+    ]
+
+
+class State(C.Structure):
+    _fields_ = [
+        ("frames", C.c_int32),
+        ("pingPong", C.c_int32),
+        ("probeBegin", C.c_int32),
+        ("probeCount", C.c_int32),
+        ("irradianceRowBegin", C.c_int32),
+        ("irradianceRowCount", C.c_int32),
+        ("depthRowBegin", C.c_int32),
+        ("depthRowCount", C.c_int32),
+        ("kernelLaunches", C.c_uint64),
+    ]
+
+
+class StageTimes(C.Structure):
+    _fields_ = [
+        ("setup_ms", C.c_float),
+        ("trace_ms", C.c_float),
+        ("blend_ms", C.c_float),
+        ("border_ms", C.c_float),
+        ("total_ms", C.c_float),
+    ]
+
+
+SIZES = {
+    DDGIUniform: 96,
+    TracePushConstants: 80,
+    GlobalSDFData: 96,
+    GlobalSurfaceAtlasData: 32,
+    ObjectBuffer: 128,
+    TileBuffer: 96,
+}
+for _t, _n in SIZES.items():
+    assert C.sizeof(_t) == _n, (_t.__name__, C.sizeof(_t), _n)
+
+# numpy structured dtypes for bulk construction of the SSBO contents
+import numpy as np  # noqa: E402
+
+OBJECT_DTYPE = np.dtype(
+    [("objectBounds", "<f4", 4), ("tileOffset", "<u4", 6), ("padding", "<i4", 2), ("transform", "<f4", 16), ("extends", "<f4", 4)]
+)
+TILE_DTYPE = np.dtype([("extends", "<f4", 4), ("transform", "<f4", 16), ("objectBounds", "<f4", 4)])
+assert OBJECT_DTYPE.itemsize == 128 and TILE_DTYPE.itemsize == 96
+
+# LuxStatus / flags / buffer ids (include/luxddgi.h)
+LUX_OK = 0
+MEM_HOST, MEM_DEVICE = 0, 1
+FLAG_STAGE_TIMERS = 1 << 0
+FLAG_UNFUSED_BORDER = 1 << 1
+FLAG_SDF_TEXTURE = 1 << 2
+BUF_RADIANCE, BUF_DIRECTION_DISTANCE, BUF_IRRADIANCE, BUF_DEPTH, BUF_IRRADIANCE_PREV, BUF_DEPTH_PREV = range(6)
+
+
+def make_uniform(start, step, counts, rays, max_distance=None, sharpness=50.0, hysteresis=0.98, normal_bias=1.0, gamma=5.0):
+    """DDGIUniform with the atlas sizing of init::initializeProbeGrid (DDGIRenderer.cpp:181-191).
+
+    max_distance defaults to 1.5 * min(step) (DDGIRenderer.cpp:674 with a per-axis step)."""
+    u = DDGIUniform()
+    u.startPosition[:] = [float(start[0]), float(start[1]), float(start[2]), 1.0]
+    u.step[:] = [float(step[0]), float(step[1]), float(step[2]), 0.0]
+    u.probeCounts[:] = [int(counts[0]), int(counts[1]), int(counts[2]), 1]
+    u.maxDistance = float(max_distance if max_distance is not None else 1.5 * min(step))
+    u.sharpness = sharpness
+    u.hysteresis = hysteresis
+    u.normalBias = normal_bias
+    u.ddgiGamma = gamma
+    u.irradianceProbeSideLength = IRRADIANCE_OCT_SIZE
+    u.depthProbeSideLength = DEPTH_OCT_SIZE
+    xy = int(counts[0]) * int(counts[1])
+    u.irradianceTextureWidth = (IRRADIANCE_OCT_SIZE + 2) * xy + 2
+    u.irradianceTextureHeight = (IRRADIANCE_OCT_SIZE + 2) * int(counts[2]) + 2
+    u.depthTextureWidth = (DEPTH_OCT_SIZE + 2) * xy + 2
+    u.depthTextureHeight = (DEPTH_OCT_SIZE + 2) * int(counts[2]) + 2
+    u.raysPerProbe = int(rays)
+    return u
+
+
+def probe_count(u):
+    return u.probeCounts[0] * u.probeCounts[1] * u.probeCounts[2]

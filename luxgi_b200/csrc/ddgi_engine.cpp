@@ -1,0 +1,792 @@
+// ddgi_engine.cpp — C++ host side of libluxddgi.so: the B200 replacement for the SDF-traced branch of the Maple
+// renderer's DDGI pass, behind the C ABI declared in include/luxddgi.h.
+//
+// The host layer mirrors the reference's systems one to one (Code/Maple/src/Engine/DDGI/DDGIRenderer.cpp):
+//   lux::ddgi::init::initializeProbeGrid   :163-211   atlas sizing, ray buffers, 2x2 ping-pong atlases
+//   lux::ddgi::trace_rays::system          :215-331   (SDF branch :302-328)
+//   lux::ddgi::probe_update::system        :345-414
+//   lux::ddgi::border_update::system       :416-465
+//   lux::ddgi::end_frame::system           :333-343
+// There is no CPU fallback: creation fails with LUX_ERR_NO_DEVICE when no sm_100-class GPU is usable.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "ddgi_kernels.h"
+
+namespace {
+
+thread_local std::string g_lastError;
+
+int fail(int code, const char* fmt, ...)
+{
+    char    buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_lastError = buf;
+    return code;
+}
+
+#define LUX_CUDA(expr)                                                                                          \
+    do                                                                                                          \
+    {                                                                                                           \
+        cudaError_t e__ = (expr);                                                                               \
+        if (e__ != cudaSuccess)                                                                                 \
+            return fail(e__ == cudaErrorMemoryAllocation ? LUX_ERR_OUT_OF_MEMORY : LUX_ERR_CUDA, "%s: %s (%s:%d)", #expr, \
+                        cudaGetErrorString(e__), __FILE__, __LINE__);                                           \
+    } while (0)
+
+struct DeviceBuffer
+{
+    void*  ptr      = nullptr;
+    size_t bytes    = 0;
+    bool   borrowed = false;
+
+    void release()
+    {
+        if (ptr && !borrowed)
+            cudaFree(ptr);
+        ptr      = nullptr;
+        bytes    = 0;
+        borrowed = false;
+    }
+};
+
+} // namespace
+
+// The opaque context = the reference's per-entity components for this pass:
+// DDGIUniform + DDGIPipelineInternal (DDGIRenderer.cpp:85-97) + the bound inputs of RaytracePass.sdfDescriptor.
+struct LuxDDGIContext
+{
+    int          device    = 0;
+    cudaStream_t stream    = nullptr;
+    bool         ownStream = false;
+    uint32_t     flags     = 0;
+    int          rank = 0, world = 1;
+
+    LuxDDGIUniform uniform{};
+    int            totalProbes = 0, probeBegin = 0, probeCount = 0;
+    int            raysPadded  = 0;
+
+    // DDGIPipelineInternal
+    DeviceBuffer radiance, directionDepth;
+    DeviceBuffer irradiance[2], depth[2];
+    int32_t      frames      = 0;
+    int32_t      pingPong    = 0;
+    int32_t      lastWritten = 1; // index of the atlas pair most recently written ("current")
+    bool         raysValid   = false;
+
+    // per-frame tables
+    DeviceBuffer dirs, wIrr, wDepth, scaleIrr, scaleDepth;
+
+    // uGlobalSDF / uGlobalMipSDF / sdfData
+    bool             hasSdf = false;
+    LuxGlobalSDFData sdfData{};
+    DeviceBuffer     sdf, mip;
+
+    // surface cache
+    bool                      hasAtlas = false;
+    LuxGlobalSurfaceAtlasData atlasData{};
+    DeviceBuffer              chunks, cull, objects, objectInverse, tiles, light, atlasDepth;
+
+    // sky
+    int          skyFace = 0;
+    DeviceBuffer sky;
+
+    // timers
+    cudaEvent_t   ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool          timed = false;
+    uint64_t      launches = 0;
+};
+
+namespace lux {
+namespace ddgi {
+
+static int upload(LuxDDGIContext& c, DeviceBuffer& dst, const void* src, size_t bytes, LuxMemKind kind)
+{
+    if (kind == LUX_MEM_DEVICE)
+    {
+        dst.release();
+        dst.ptr      = const_cast<void*>(src);
+        dst.bytes    = bytes;
+        dst.borrowed = true;
+        return LUX_OK;
+    }
+    if (dst.borrowed || dst.bytes != bytes)
+    {
+        dst.release();
+        LUX_CUDA(cudaMalloc(&dst.ptr, bytes ? bytes : 1));
+        dst.bytes = bytes;
+    }
+    if (bytes)
+        LUX_CUDA(cudaMemcpyAsync(dst.ptr, src, bytes, cudaMemcpyHostToDevice, c.stream));
+    return LUX_OK;
+}
+
+static int allocZero(LuxDDGIContext& c, DeviceBuffer& dst, size_t bytes)
+{
+    dst.release();
+    LUX_CUDA(cudaMalloc(&dst.ptr, bytes ? bytes : 1));
+    dst.bytes = bytes;
+    LUX_CUDA(cudaMemsetAsync(dst.ptr, 0, bytes, c.stream));
+    return LUX_OK;
+}
+
+namespace init {
+
+// Atlas sizing, DDGIRenderer.cpp:181-191
+static void atlasSizes(LuxDDGIUniform& u)
+{
+    u.irradianceProbeSideLength = LUX_IRRADIANCE_OCT_SIZE;
+    u.depthProbeSideLength      = LUX_DEPTH_OCT_SIZE;
+    const int xy                = u.probeCounts[0] * u.probeCounts[1];
+    u.irradianceTextureWidth    = (LUX_IRRADIANCE_OCT_SIZE + 2) * xy + 2;
+    u.irradianceTextureHeight   = (LUX_IRRADIANCE_OCT_SIZE + 2) * u.probeCounts[2] + 2;
+    u.depthTextureWidth         = (LUX_DEPTH_OCT_SIZE + 2) * xy + 2;
+    u.depthTextureHeight        = (LUX_DEPTH_OCT_SIZE + 2) * u.probeCounts[2] + 2;
+}
+
+static int validate(const LuxDDGIUniform& u)
+{
+    if (u.probeCounts[0] <= 0 || u.probeCounts[1] <= 0 || u.probeCounts[2] <= 0)
+        return fail(LUX_ERR_INVALID_ARG, "probeCounts must be positive (%d,%d,%d)", u.probeCounts[0], u.probeCounts[1], u.probeCounts[2]);
+    if ((long long)u.probeCounts[0] * u.probeCounts[1] * u.probeCounts[2] > (1ll << 30))
+        return fail(LUX_ERR_INVALID_ARG, "too many probes");
+    if (u.raysPerProbe <= 0 || u.raysPerProbe > 65535)
+        return fail(LUX_ERR_INVALID_ARG, "raysPerProbe %d out of range", u.raysPerProbe);
+    if (u.irradianceProbeSideLength != LUX_IRRADIANCE_OCT_SIZE || u.depthProbeSideLength != LUX_DEPTH_OCT_SIZE)
+        return fail(LUX_ERR_UNSUPPORTED, "probe side lengths must be %d / %d", LUX_IRRADIANCE_OCT_SIZE, LUX_DEPTH_OCT_SIZE);
+    LuxDDGIUniform t = u;
+    atlasSizes(t);
+    if (t.irradianceTextureWidth != u.irradianceTextureWidth || t.irradianceTextureHeight != u.irradianceTextureHeight ||
+        t.depthTextureWidth != u.depthTextureWidth || t.depthTextureHeight != u.depthTextureHeight)
+        return fail(LUX_ERR_INVALID_ARG, "atlas sizes in DDGIUniform do not match probeCounts (call lux_ddgi_uniform_finalize)");
+    if (!(u.ddgiGamma > 0.0f))
+        return fail(LUX_ERR_INVALID_ARG, "ddgiGamma must be positive");
+    return LUX_OK;
+}
+
+// init::initializeProbeGrid, DDGIRenderer.cpp:163-211.  The reference caps probes at int16 max (:169); this engine does not.
+static int initializeProbeGrid(LuxDDGIContext& c)
+{
+    const LuxDDGIUniform& u = c.uniform;
+    const size_t rayBytes   = (size_t)c.probeCount * u.raysPerProbe * 8; // RGBA16F
+    int rc;
+    if ((rc = allocZero(c, c.radiance, rayBytes)) != LUX_OK) return rc;
+    if ((rc = allocZero(c, c.directionDepth, rayBytes)) != LUX_OK) return rc;
+    const size_t irrBytes   = (size_t)u.irradianceTextureWidth * u.irradianceTextureHeight * 8; // RGBA16F
+    const size_t depthBytes = (size_t)u.depthTextureWidth * u.depthTextureHeight * 4;           // RG16F
+    for (int i = 0; i < 2; i++)
+    {
+        if ((rc = allocZero(c, c.irradiance[i], irrBytes)) != LUX_OK) return rc;
+        if ((rc = allocZero(c, c.depth[i], depthBytes)) != LUX_OK) return rc;
+    }
+    c.raysPadded = (u.raysPerProbe + 31) / 32 * 32;
+    if ((rc = allocZero(c, c.dirs, (size_t)u.raysPerProbe * sizeof(float4))) != LUX_OK) return rc;
+    if ((rc = allocZero(c, c.wIrr, (size_t)c.raysPadded * 64 * sizeof(float))) != LUX_OK) return rc;
+    if ((rc = allocZero(c, c.wDepth, (size_t)c.raysPadded * 256 * sizeof(float))) != LUX_OK) return rc;
+    if ((rc = allocZero(c, c.scaleIrr, 64 * sizeof(float))) != LUX_OK) return rc;
+    if ((rc = allocZero(c, c.scaleDepth, 256 * sizeof(float))) != LUX_OK) return rc;
+    c.frames      = 0;
+    c.pingPong    = 0;
+    c.lastWritten = 1;
+    c.raysValid   = false;
+    return LUX_OK;
+}
+
+} // namespace init
+
+static void mark(LuxDDGIContext& c, int i)
+{
+    if (c.flags & LUX_DDGI_FLAG_STAGE_TIMERS)
+        cudaEventRecord(c.ev[i], c.stream);
+}
+
+namespace trace_rays {
+
+// trace_rays::system, SDF branch (DDGIRenderer.cpp:235-240, 302-328)
+static int system(LuxDDGIContext& c, const LuxTracePushConstants& push)
+{
+    if (!c.hasSdf)
+        return fail(LUX_ERR_NOT_READY, "trace_rays: no global SDF bound (lux_ddgi_set_global_sdf)");
+    const LuxDDGIUniform& u = c.uniform;
+
+    mark(c, 0);
+    launch_ray_dirs(push.randomOrientation, u.raysPerProbe, (float4*)c.dirs.ptr, c.stream);
+    c.launches += 1;
+    mark(c, 1);
+
+    TraceParams p{};
+    for (int i = 0; i < 3; i++)
+    {
+        p.start[i] = u.startPosition[i];
+        p.step[i]  = u.step[i];
+    }
+    p.countX       = u.probeCounts[0];
+    p.countY       = u.probeCounts[1];
+    p.raysPerProbe = u.raysPerProbe;
+    p.probeBegin   = c.probeBegin;
+    p.probeCount   = c.probeCount;
+    p.sdf          = c.sdfData;
+    p.tex          = (const uint16_t*)c.sdf.ptr;
+    p.mip          = (const uint16_t*)c.mip.ptr;
+    p.res          = (int)c.sdfData.resolution;
+    p.mipRes       = p.res / 4;
+    p.cascades     = (int)c.sdfData.cascadesCount;
+    p.texObj = p.mipObj = 0;
+    p.hasAtlas     = c.hasAtlas ? 1 : 0;
+    if (c.hasAtlas)
+    {
+        p.chunkSize     = c.atlasData.chunkSize;
+        p.atlasRes      = c.atlasData.resolution;
+        p.objectsCount  = c.atlasData.objectsCount;
+        p.chunks        = (const uint32_t*)c.chunks.ptr;
+        p.cull          = (const uint32_t*)c.cull.ptr;
+        p.objects       = (const LuxObjectBuffer*)c.objects.ptr;
+        p.objectInverse = (const float*)c.objectInverse.ptr;
+        p.tiles         = (const LuxTileBuffer*)c.tiles.ptr;
+        p.light         = (const uint2*)c.light.ptr;
+        p.depth         = (const float*)c.atlasDepth.ptr;
+    }
+    p.skyFace  = c.skyFace;
+    p.sky      = (const uint2*)c.sky.ptr;
+    p.dirs     = (const float4*)c.dirs.ptr;
+    p.radiance = (uint2*)c.radiance.ptr;
+    p.dirDist  = (uint2*)c.directionDepth.ptr;
+    p.steps    = nullptr;
+    launch_trace(p, false, c.stream);
+    c.launches += 1;
+    mark(c, 2);
+    LUX_CUDA(cudaGetLastError());
+    c.raysValid = true;
+    return LUX_OK;
+}
+
+} // namespace trace_rays
+
+namespace probe_update {
+
+// probe_update::system (DDGIRenderer.cpp:377-413): writeIdx = 1 - pingPong, firstFrame = (frames == 0)
+static int system(LuxDDGIContext& c)
+{
+    if (!c.raysValid)
+        return fail(LUX_ERR_NOT_READY, "probe_update: ray buffers are empty (call lux_ddgi_trace_rays or lux_ddgi_set_ray_buffers)");
+    const LuxDDGIUniform& u = c.uniform;
+    const int writeIdx = 1 - c.pingPong;
+
+    launch_blend_weights((const uint2*)c.directionDepth.ptr, u.raysPerProbe, c.raysPadded, u.sharpness, (float*)c.wIrr.ptr,
+                         (float*)c.wDepth.ptr, (float*)c.scaleIrr.ptr, (float*)c.scaleDepth.ptr, c.stream);
+    c.launches += 2;
+
+    BlendParams p{};
+    p.probeBegin   = c.probeBegin;
+    p.probeCount   = c.probeCount;
+    p.raysPerProbe = u.raysPerProbe;
+    p.raysPadded   = c.raysPadded;
+    p.probesPerRow = u.probeCounts[0] * u.probeCounts[1];
+    p.irrWidth     = u.irradianceTextureWidth;
+    p.depthWidth   = u.depthTextureWidth;
+    p.hysteresis   = u.hysteresis;
+    p.invGamma     = 1.0f / u.ddgiGamma; // ProbeUpdate.glsl:141
+    p.maxDistance  = u.maxDistance;
+    p.firstFrame   = (c.frames == 0) ? 1 : 0; // DDGIRenderer.cpp:362
+    p.fuseBorder   = (c.flags & LUX_DDGI_FLAG_UNFUSED_BORDER) ? 0 : 1;
+    p.radiance     = (const uint2*)c.radiance.ptr;
+    p.dirDist      = (const uint2*)c.directionDepth.ptr;
+    p.wIrr         = (const float*)c.wIrr.ptr;
+    p.wDepth       = (const float*)c.wDepth.ptr;
+    p.scaleIrr     = (const float*)c.scaleIrr.ptr;
+    p.scaleDepth   = (const float*)c.scaleDepth.ptr;
+    p.prevIrr      = (const uint2*)c.irradiance[c.pingPong].ptr;
+    p.outIrr       = (uint2*)c.irradiance[writeIdx].ptr;
+    p.prevDepth    = (const uint32_t*)c.depth[c.pingPong].ptr;
+    p.outDepth     = (uint32_t*)c.depth[writeIdx].ptr;
+    launch_blend_irradiance(p, c.stream);
+    launch_blend_depth(p, c.stream);
+    c.launches += 2;
+    mark(c, 3);
+    LUX_CUDA(cudaGetLastError());
+    c.lastWritten = writeIdx;
+    return LUX_OK;
+}
+
+} // namespace probe_update
+
+namespace border_update {
+
+// border_update::system (DDGIRenderer.cpp:441-464): in place on tex[1 - pingPong]
+static int system(LuxDDGIContext& c)
+{
+    const LuxDDGIUniform& u = c.uniform;
+    const int writeIdx = 1 - c.pingPong;
+    launch_border((uint2*)c.irradiance[writeIdx].ptr, u.irradianceTextureWidth, (uint32_t*)c.depth[writeIdx].ptr, u.depthTextureWidth,
+                  u.probeCounts[0] * u.probeCounts[1], c.probeBegin, c.probeCount, c.stream);
+    c.launches += 2;
+    LUX_CUDA(cudaGetLastError());
+    return LUX_OK;
+}
+
+} // namespace border_update
+
+namespace end_frame {
+
+// end_frame::system (DDGIRenderer.cpp:333-343)
+static int system(LuxDDGIContext& c)
+{
+    c.pingPong = 1 - c.pingPong;
+    c.frames++;
+    return LUX_OK;
+}
+
+} // namespace end_frame
+
+} // namespace ddgi
+} // namespace lux
+
+using namespace lux::ddgi;
+
+#define CHECK_CTX(ctx)                                                  \
+    do                                                                  \
+    {                                                                   \
+        if (!(ctx))                                                     \
+            return fail(LUX_ERR_INVALID_ARG, "null context");           \
+        LUX_CUDA(cudaSetDevice((ctx)->device));                         \
+    } while (0)
+
+extern "C" {
+
+uint32_t lux_ddgi_version(void) { return LUXDDGI_VERSION; }
+
+const char* lux_ddgi_last_error(void) { return g_lastError.c_str(); }
+
+int lux_ddgi_uniform_finalize(LuxDDGIUniform* u)
+{
+    if (!u)
+        return fail(LUX_ERR_INVALID_ARG, "null uniform");
+    init::atlasSizes(*u);
+    return LUX_OK;
+}
+
+int lux_ddgi_uniform_from_volume(const LuxIrradianceVolume* v, const float aabbMin[3], const float aabbMax[3], LuxDDGIUniform* out)
+{
+    if (!v || !aabbMin || !aabbMax || !out)
+        return fail(LUX_ERR_INVALID_ARG, "null argument");
+    if (!(v->probeDistance > 0.0f))
+        return fail(LUX_ERR_INVALID_ARG, "probeDistance must be positive");
+    LuxDDGIUniform u{};
+    for (int i = 0; i < 3; i++)
+    {
+        float sceneLength  = aabbMax[i] - aabbMin[i];
+        u.probeCounts[i]   = (int)(sceneLength / v->probeDistance) + 2; // DDGIRenderer.cpp:669 "Add 2 more probes to fully cover scene"
+        u.startPosition[i] = aabbMin[i];
+        u.step[i]          = v->probeDistance;
+    }
+    u.probeCounts[3]   = 1;
+    u.startPosition[3] = 1.0f;
+    u.step[3]          = v->probeDistance;
+    u.maxDistance      = v->probeDistance * 1.5f; // :674
+    u.sharpness        = v->depthSharpness;
+    u.hysteresis       = v->hysteresis;
+    u.normalBias       = v->normalBias;
+    u.ddgiGamma        = v->ddgiGamma;
+    u.raysPerProbe     = v->raysPerProbe; // the reference forgets this copy (SURVEY finding 8); the engine does not
+    init::atlasSizes(u);
+    *out = u;
+    return LUX_OK;
+}
+
+int lux_ddgi_create(const LuxDDGIUniform* uniform, const LuxDDGICreateInfo* info, LuxDDGIContext** out)
+{
+    if (!uniform || !out)
+        return fail(LUX_ERR_INVALID_ARG, "null argument");
+    *out = nullptr;
+    int rc = init::validate(*uniform);
+    if (rc != LUX_OK)
+        return rc;
+    LuxDDGICreateInfo ci{};
+    if (info)
+        ci = *info;
+    if (ci.world <= 0)
+        ci.world = 1;
+    if (ci.rank < 0 || ci.rank >= ci.world)
+        return fail(LUX_ERR_INVALID_ARG, "rank %d outside world %d", ci.rank, ci.world);
+    if (uniform->probeCounts[2] % ci.world != 0)
+        return fail(LUX_ERR_INVALID_ARG, "world %d must divide probeCounts.z %d (z-slab sharding)", ci.world, uniform->probeCounts[2]);
+
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0)
+        return fail(LUX_ERR_NO_DEVICE, "no CUDA device available (%s); the engine has no CPU fallback", cudaGetErrorString(e));
+    if (ci.device < 0 || ci.device >= ndev)
+        return fail(LUX_ERR_INVALID_ARG, "device %d out of range (%d devices)", ci.device, ndev);
+    cudaDeviceProp prop{};
+    LUX_CUDA(cudaGetDeviceProperties(&prop, ci.device));
+    if (prop.major != 10)
+        return fail(LUX_ERR_NO_DEVICE, "device %d is sm_%d%d; this build contains sm_100a code only", ci.device, prop.major, prop.minor);
+    LUX_CUDA(cudaSetDevice(ci.device));
+
+    LuxDDGIContext* c = new (std::nothrow) LuxDDGIContext();
+    if (!c)
+        return fail(LUX_ERR_OUT_OF_MEMORY, "host allocation failed");
+    c->device  = ci.device;
+    c->flags   = ci.flags;
+    c->rank    = ci.rank;
+    c->world   = ci.world;
+    c->uniform = *uniform;
+    c->totalProbes = uniform->probeCounts[0] * uniform->probeCounts[1] * uniform->probeCounts[2];
+    c->probeCount  = c->totalProbes / ci.world;
+    c->probeBegin  = c->probeCount * ci.rank;
+    if (ci.stream)
+        c->stream = (cudaStream_t)ci.stream;
+    else
+    {
+        cudaError_t se = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+        if (se != cudaSuccess)
+        {
+            delete c;
+            return fail(LUX_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(se));
+        }
+        c->ownStream = true;
+    }
+    for (auto& ev : c->ev)
+        cudaEventCreate(&ev);
+    rc = init::initializeProbeGrid(*c);
+    if (rc != LUX_OK)
+    {
+        lux_ddgi_destroy(c);
+        return rc;
+    }
+    // default sky: the reference's 1x1 black fallback cube (DDGIRenderer.cpp:308)
+    c->skyFace = 0;
+    *out = c;
+    return LUX_OK;
+}
+
+int lux_ddgi_destroy(LuxDDGIContext* c)
+{
+    if (!c)
+        return LUX_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    DeviceBuffer* all[] = {&c->radiance, &c->directionDepth, &c->irradiance[0], &c->irradiance[1], &c->depth[0], &c->depth[1],
+                           &c->dirs, &c->wIrr, &c->wDepth, &c->scaleIrr, &c->scaleDepth, &c->sdf, &c->mip, &c->chunks, &c->cull,
+                           &c->objects, &c->objectInverse, &c->tiles, &c->light, &c->atlasDepth, &c->sky};
+    for (DeviceBuffer* b : all)
+        b->release();
+    for (auto& ev : c->ev)
+        if (ev)
+            cudaEventDestroy(ev);
+    if (c->ownStream)
+        cudaStreamDestroy(c->stream);
+    delete c;
+    return LUX_OK;
+}
+
+int lux_ddgi_set_uniform(LuxDDGIContext* c, const LuxDDGIUniform* u)
+{
+    CHECK_CTX(c);
+    if (!u)
+        return fail(LUX_ERR_INVALID_ARG, "null uniform");
+    for (int i = 0; i < 3; i++)
+        if (u->probeCounts[i] != c->uniform.probeCounts[i])
+            return fail(LUX_ERR_UNSUPPORTED, "probeCounts changed; create a new context");
+    if (u->raysPerProbe != c->uniform.raysPerProbe)
+        return fail(LUX_ERR_UNSUPPORTED, "raysPerProbe changed; create a new context");
+    int rc = init::validate(*u);
+    if (rc != LUX_OK)
+        return rc;
+    c->uniform = *u;
+    return LUX_OK;
+}
+
+int lux_ddgi_set_global_sdf(LuxDDGIContext* c, const LuxGlobalSDFData* data, const void* sdf, const void* mip, LuxMemKind kind)
+{
+    CHECK_CTX(c);
+    if (!data || !sdf || !mip)
+        return fail(LUX_ERR_INVALID_ARG, "null argument");
+    if (data->cascadesCount < 1 || data->cascadesCount > LUX_MAX_CASCADES)
+        return fail(LUX_ERR_INVALID_ARG, "cascadesCount %u out of range", data->cascadesCount);
+    const int res = (int)data->resolution;
+    if (res < 4 || (float)res != data->resolution || res % 4 != 0)
+        return fail(LUX_ERR_INVALID_ARG, "resolution %g must be a positive multiple of 4", data->resolution);
+    const size_t n    = (size_t)res * res * res * data->cascadesCount;
+    const size_t mres = res / 4;
+    const size_t nm   = mres * mres * mres * data->cascadesCount;
+    int rc;
+    if ((rc = upload(*c, c->sdf, sdf, n * 2, kind)) != LUX_OK) return rc;
+    if ((rc = upload(*c, c->mip, mip, nm * 2, kind)) != LUX_OK) return rc;
+    if (kind == LUX_MEM_HOST)
+        LUX_CUDA(cudaStreamSynchronize(c->stream)); // the caller may free its buffers on return
+    c->sdfData = *data;
+    c->hasSdf  = true;
+    return LUX_OK;
+}
+
+int lux_ddgi_set_surface_atlas(LuxDDGIContext* c, const LuxGlobalSurfaceAtlasData* data, const uint32_t* chunks,
+                               const uint32_t* cullObjects, size_t cullObjectsCount, const LuxObjectBuffer* objects, size_t objectsCount,
+                               const LuxTileBuffer* tiles, size_t tilesCount, const void* light, const float* depth, LuxMemKind kind)
+{
+    CHECK_CTX(c);
+    if (!data)
+    {
+        c->hasAtlas = false; // unbind: hits return zero radiance
+        return LUX_OK;
+    }
+    if (!chunks || !cullObjects || !objects || !tiles || !light || !depth)
+        return fail(LUX_ERR_INVALID_ARG, "null surface-cache buffer");
+    if (data->resolution == 0 || !(data->chunkSize > 0.0f))
+        return fail(LUX_ERR_INVALID_ARG, "bad GlobalSurfaceAtlasData (resolution %u, chunkSize %g)", data->resolution, data->chunkSize);
+    if (data->objectsCount > objectsCount)
+        return fail(LUX_ERR_INVALID_ARG, "objectsCount %u exceeds the object buffer (%zu)", data->objectsCount, objectsCount);
+    const size_t nchunks = (size_t)LUX_SURFACE_ATLAS_CHUNKS_RESOLUTION * LUX_SURFACE_ATLAS_CHUNKS_RESOLUTION * LUX_SURFACE_ATLAS_CHUNKS_RESOLUTION;
+    const size_t texels  = (size_t)data->resolution * data->resolution;
+    int rc;
+    if ((rc = upload(*c, c->chunks, chunks, nchunks * 4, kind)) != LUX_OK) return rc;
+    if ((rc = upload(*c, c->cull, cullObjects, cullObjectsCount * 4, kind)) != LUX_OK) return rc;
+    if ((rc = upload(*c, c->objects, objects, objectsCount * sizeof(LuxObjectBuffer), kind)) != LUX_OK) return rc;
+    if ((rc = upload(*c, c->tiles, tiles, tilesCount * sizeof(LuxTileBuffer), kind)) != LUX_OK) return rc;
+    if ((rc = upload(*c, c->light, light, texels * 8, kind)) != LUX_OK) return rc;
+    if ((rc = upload(*c, c->atlasDepth, depth, texels * 4, kind)) != LUX_OK) return rc;
+    if (c->objectInverse.bytes != objectsCount * 64)
+    {
+        c->objectInverse.release();
+        LUX_CUDA(cudaMalloc(&c->objectInverse.ptr, objectsCount ? objectsCount * 64 : 1));
+        c->objectInverse.bytes = objectsCount * 64;
+    }
+    lux::launch_object_inverse((const LuxObjectBuffer*)c->objects.ptr, (int)objectsCount, (float*)c->objectInverse.ptr, c->stream);
+    c->launches += objectsCount ? 1 : 0;
+    LUX_CUDA(cudaGetLastError());
+    if (kind == LUX_MEM_HOST)
+        LUX_CUDA(cudaStreamSynchronize(c->stream));
+    c->atlasData = *data;
+    c->hasAtlas  = true;
+    return LUX_OK;
+}
+
+int lux_ddgi_update_surface_light_cache(LuxDDGIContext* c, const void* light, LuxMemKind kind)
+{
+    CHECK_CTX(c);
+    if (!c->hasAtlas)
+        return fail(LUX_ERR_NOT_READY, "no surface cache bound");
+    if (!light)
+        return fail(LUX_ERR_INVALID_ARG, "null light cache");
+    const size_t texels = (size_t)c->atlasData.resolution * c->atlasData.resolution;
+    if (kind == LUX_MEM_DEVICE)
+        return upload(*c, c->light, light, texels * 8, kind);
+    if (c->light.borrowed)
+        return fail(LUX_ERR_UNSUPPORTED, "light cache is a borrowed device buffer; update it in place");
+    LUX_CUDA(cudaMemcpyAsync(c->light.ptr, light, texels * 8, cudaMemcpyHostToDevice, c->stream)); // async for pinned sources
+    return LUX_OK;
+}
+
+int lux_ddgi_set_skybox(LuxDDGIContext* c, int32_t faceSize, const void* faces, LuxMemKind kind)
+{
+    CHECK_CTX(c);
+    if (faceSize <= 0 || !faces)
+    {
+        c->skyFace = 0;
+        c->sky.release();
+        return LUX_OK;
+    }
+    int rc = upload(*c, c->sky, faces, (size_t)6 * faceSize * faceSize * 8, kind);
+    if (rc != LUX_OK)
+        return rc;
+    if (kind == LUX_MEM_HOST)
+        LUX_CUDA(cudaStreamSynchronize(c->stream));
+    c->skyFace = faceSize;
+    return LUX_OK;
+}
+
+int lux_ddgi_set_ray_buffers(LuxDDGIContext* c, const void* radiance, const void* directionDistance, LuxMemKind kind)
+{
+    CHECK_CTX(c);
+    if (!radiance || !directionDistance)
+        return fail(LUX_ERR_INVALID_ARG, "null ray buffer");
+    const size_t bytes = (size_t)c->probeCount * c->uniform.raysPerProbe * 8;
+    cudaMemcpyKind k = kind == LUX_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    LUX_CUDA(cudaMemcpyAsync(c->radiance.ptr, radiance, bytes, k, c->stream));
+    LUX_CUDA(cudaMemcpyAsync(c->directionDepth.ptr, directionDistance, bytes, k, c->stream));
+    LUX_CUDA(cudaStreamSynchronize(c->stream));
+    c->raysValid = true;
+    return LUX_OK;
+}
+
+int lux_ddgi_trace_rays(LuxDDGIContext* c, const LuxTracePushConstants* push)
+{
+    CHECK_CTX(c);
+    if (!push)
+        return fail(LUX_ERR_INVALID_ARG, "null push constants");
+    return trace_rays::system(*c, *push);
+}
+
+int lux_ddgi_probe_update(LuxDDGIContext* c)
+{
+    CHECK_CTX(c);
+    return probe_update::system(*c);
+}
+
+int lux_ddgi_border_update(LuxDDGIContext* c)
+{
+    CHECK_CTX(c);
+    return border_update::system(*c);
+}
+
+int lux_ddgi_end_frame(LuxDDGIContext* c)
+{
+    CHECK_CTX(c);
+    return end_frame::system(*c);
+}
+
+int lux_ddgi_update(LuxDDGIContext* c, const float orientation[16])
+{
+    CHECK_CTX(c);
+    if (!orientation)
+        return fail(LUX_ERR_INVALID_ARG, "null orientation");
+    LuxTracePushConstants push{};
+    std::memcpy(push.randomOrientation, orientation, sizeof(float) * 16);
+    push.numFrames       = (uint32_t)c->frames;
+    push.infiniteBounces = c->frames != 0 ? 1u : 0u; // DDGIRenderer.cpp:263
+    push.numLights       = 0;
+    push.intensity       = 1.0f;
+    int rc = trace_rays::system(*c, push);
+    if (rc != LUX_OK)
+        return rc;
+    rc = probe_update::system(*c);
+    if (rc != LUX_OK)
+        return rc;
+    if (c->flags & LUX_DDGI_FLAG_UNFUSED_BORDER)
+    {
+        rc = border_update::system(*c);
+        if (rc != LUX_OK)
+            return rc;
+    }
+    mark(*c, 4);
+    c->timed = (c->flags & LUX_DDGI_FLAG_STAGE_TIMERS) != 0;
+    return end_frame::system(*c);
+}
+
+int lux_ddgi_synchronize(LuxDDGIContext* c)
+{
+    CHECK_CTX(c);
+    LUX_CUDA(cudaStreamSynchronize(c->stream));
+    return LUX_OK;
+}
+
+static int bufferOf(LuxDDGIContext* c, LuxBufferId id, DeviceBuffer** out)
+{
+    switch (id)
+    {
+    case LUX_BUF_RADIANCE: *out = &c->radiance; break;
+    case LUX_BUF_DIRECTION_DISTANCE: *out = &c->directionDepth; break;
+    case LUX_BUF_IRRADIANCE: *out = &c->irradiance[c->lastWritten]; break;
+    case LUX_BUF_DEPTH: *out = &c->depth[c->lastWritten]; break;
+    case LUX_BUF_IRRADIANCE_PREV: *out = &c->irradiance[1 - c->lastWritten]; break;
+    case LUX_BUF_DEPTH_PREV: *out = &c->depth[1 - c->lastWritten]; break;
+    default: return fail(LUX_ERR_INVALID_ARG, "unknown buffer id %d", (int)id);
+    }
+    return LUX_OK;
+}
+
+int lux_ddgi_get_buffer(LuxDDGIContext* c, LuxBufferId id, void** devicePtr, size_t* bytes)
+{
+    CHECK_CTX(c);
+    if (!devicePtr)
+        return fail(LUX_ERR_INVALID_ARG, "null output pointer");
+    DeviceBuffer* b = nullptr;
+    int rc = bufferOf(c, id, &b);
+    if (rc != LUX_OK)
+        return rc;
+    *devicePtr = b->ptr;
+    if (bytes)
+        *bytes = b->bytes;
+    return LUX_OK;
+}
+
+int lux_ddgi_download(LuxDDGIContext* c, LuxBufferId id, void* host, size_t bytes)
+{
+    CHECK_CTX(c);
+    if (!host)
+        return fail(LUX_ERR_INVALID_ARG, "null host pointer");
+    DeviceBuffer* b = nullptr;
+    int rc = bufferOf(c, id, &b);
+    if (rc != LUX_OK)
+        return rc;
+    if (bytes != b->bytes)
+        return fail(LUX_ERR_INVALID_ARG, "size mismatch: buffer holds %zu bytes, caller passed %zu", b->bytes, bytes);
+    LUX_CUDA(cudaMemcpyAsync(host, b->ptr, bytes, cudaMemcpyDeviceToHost, c->stream));
+    LUX_CUDA(cudaStreamSynchronize(c->stream));
+    return LUX_OK;
+}
+
+int lux_ddgi_download_async(LuxDDGIContext* c, LuxBufferId id, void* pinnedHost, size_t bytes)
+{
+    CHECK_CTX(c);
+    if (!pinnedHost)
+        return fail(LUX_ERR_INVALID_ARG, "null host pointer");
+    DeviceBuffer* b = nullptr;
+    int rc = bufferOf(c, id, &b);
+    if (rc != LUX_OK)
+        return rc;
+    if (bytes != b->bytes)
+        return fail(LUX_ERR_INVALID_ARG, "size mismatch: buffer holds %zu bytes, caller passed %zu", b->bytes, bytes);
+    LUX_CUDA(cudaMemcpyAsync(pinnedHost, b->ptr, bytes, cudaMemcpyDeviceToHost, c->stream));
+    return LUX_OK;
+}
+
+int lux_ddgi_restore(LuxDDGIContext* c, const void* irradiance, const void* depth, int32_t frames, int32_t pingPong)
+{
+    CHECK_CTX(c);
+    if (!irradiance || !depth || frames < 0 || (pingPong != 0 && pingPong != 1))
+        return fail(LUX_ERR_INVALID_ARG, "bad restore arguments");
+    // "current" after `frames` frames is tex[pingPong] (the pair the next frame reads as prev)
+    LUX_CUDA(cudaMemcpyAsync(c->irradiance[pingPong].ptr, irradiance, c->irradiance[pingPong].bytes, cudaMemcpyHostToDevice, c->stream));
+    LUX_CUDA(cudaMemcpyAsync(c->depth[pingPong].ptr, depth, c->depth[pingPong].bytes, cudaMemcpyHostToDevice, c->stream));
+    LUX_CUDA(cudaStreamSynchronize(c->stream));
+    c->frames      = frames;
+    c->pingPong    = pingPong;
+    c->lastWritten = pingPong;
+    return LUX_OK;
+}
+
+int lux_ddgi_get_state(LuxDDGIContext* c, LuxDDGIState* out)
+{
+    if (!c || !out)
+        return fail(LUX_ERR_INVALID_ARG, "null argument");
+    const int xy     = c->uniform.probeCounts[0] * c->uniform.probeCounts[1];
+    const int zBegin = c->probeBegin / xy, zCount = c->probeCount / xy;
+    out->frames             = c->frames;
+    out->pingPong           = c->pingPong;
+    out->probeBegin         = c->probeBegin;
+    out->probeCount         = c->probeCount;
+    out->irradianceRowBegin = 1 + zBegin * (LUX_IRRADIANCE_OCT_SIZE + 2);
+    out->irradianceRowCount = zCount * (LUX_IRRADIANCE_OCT_SIZE + 2);
+    out->depthRowBegin      = 1 + zBegin * (LUX_DEPTH_OCT_SIZE + 2);
+    out->depthRowCount      = zCount * (LUX_DEPTH_OCT_SIZE + 2);
+    out->kernelLaunches     = c->launches;
+    return LUX_OK;
+}
+
+int lux_ddgi_get_stage_ms(LuxDDGIContext* c, LuxStageTimes* out)
+{
+    CHECK_CTX(c);
+    if (!out)
+        return fail(LUX_ERR_INVALID_ARG, "null argument");
+    if (!c->timed)
+        return fail(LUX_ERR_NOT_READY, "no timed update yet (create with LUX_DDGI_FLAG_STAGE_TIMERS and call lux_ddgi_update)");
+    LUX_CUDA(cudaEventSynchronize(c->ev[4]));
+    cudaEventElapsedTime(&out->setup_ms, c->ev[0], c->ev[1]);
+    cudaEventElapsedTime(&out->trace_ms, c->ev[1], c->ev[2]);
+    cudaEventElapsedTime(&out->blend_ms, c->ev[2], c->ev[3]);
+    cudaEventElapsedTime(&out->border_ms, c->ev[3], c->ev[4]);
+    cudaEventElapsedTime(&out->total_ms, c->ev[0], c->ev[4]);
+    return LUX_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,900 @@
+// ddgi_kernels.cu — sm_100a kernels of the DDGI probe update: per-frame setup, SDF sphere trace with surface-cache
+// radiance, irradiance / depth blend with hysteresis and fused border, standalone border.
+//
+// What each kernel replaces in the reference (paths relative to Code/Maple/src/):
+//   ray_dirs_kernel          Shaders/DDGI/GISDFRays.comp:73 + DDGICommon.glsl:42-52 (hoisted: directions depend on rayId only)
+//   blend_weights_kernel     Shaders/DDGI/ProbeUpdate.glsl:83-91 (hoisted: weights depend on (texel, rayId) only, SURVEY finding 5)
+//   trace_kernel             Shaders/DDGI/GISDFRays.comp:63-128, Shaders/SDF/SDFCommon.glsl:64-199, Shaders/SDF/AtlasCommon.glsl:40-157
+//   blend_irradiance_kernel  Shaders/DDGI/ProbeUpdate.glsl:105-152 (+ BorderUpdate.glsl fused in the epilogue)
+//   blend_depth_kernel       same with DEPTHPROBE_UPDATE
+//   border_kernel            Shaders/DDGI/BorderUpdate.glsl:136-156
+//
+// Compiled with -fmad=false; see ddgi_math.cuh for the numerics contract.
+#include "ddgi_kernels.h"
+#include "ddgi_math.cuh"
+
+namespace lux {
+
+struct RotationArg { float m[16]; };
+
+// =====================================================================================================================
+// Per-frame setup
+// =====================================================================================================================
+
+// DDGICommon.glsl:42-52 with the constants glslang folded into the shipped GISDFRays.comp.spv.
+__device__ __forceinline__ f3 spherical_fibonacci(float i, float raysPerProbe)
+{
+    const float PHI_M1 = 0.61803400516510009765625f;
+    const float TWO_PI = 6.283185482025146484375f;
+    float ab       = i * PHI_M1;
+    float phi      = TWO_PI * (ab - floorf(ab));
+    float cosTheta = 1.0f - (2.0f * i + 1.0f) * __fdiv_rn(1.0f, raysPerProbe);
+    float sinTheta = __fsqrt_rn(gclamp(1.0f - cosTheta * cosTheta, 0.0f, 1.0f));
+    return {cos_rn(phi) * sinTheta, sin_rn(phi) * sinTheta, cosTheta};
+}
+
+__global__ void ray_dirs_kernel(const RotationArg rot, int R, float4* __restrict__ dirs)
+{
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R)
+        return;
+    f3 d = normalize3(mat3_mul(rot.m, spherical_fibonacci((float)r, (float)R)));
+    dirs[r] = make_float4(d.x, d.y, d.z, 0.0f);
+}
+
+__device__ __forceinline__ float sign_not_zero(float k) { return (k >= 0.0f) ? 1.0f : -1.0f; }
+
+// DDGICommon.glsl:74-92 for interior texel (i, j) of a probe with `side` texels per side
+__device__ __forceinline__ f3 texel_direction(int i, int j, int side)
+{
+    float s  = __fdiv_rn(2.0f, (float)side);
+    float ox = ((float)i + 0.5f) * s - 1.0f;
+    float oy = ((float)j + 0.5f) * s - 1.0f;
+    f3    v  = {ox, oy, (1.0f - fabsf(ox)) - fabsf(oy)};
+    if (v.z < 0.0f)
+    {
+        float nx = (1.0f - fabsf(v.y)) * sign_not_zero(v.x);
+        float ny = (1.0f - fabsf(v.x)) * sign_not_zero(v.y);
+        v.x = nx;
+        v.y = ny;
+    }
+    return normalize3(v);
+}
+
+// One thread per (texel, ray).  Texels 0..63 are irradiance texels, 64..319 depth texels.
+// Ray directions are read back from row 0 of the direction/distance buffer, i.e. already quantised to fp16 exactly as
+// the reference's blend sees them (texelFetch of an RGBA16F image, ProbeUpdate.glsl:59).
+// Weights below the reference's gate (ProbeUpdate.glsl:93, w >= 1e-8) are stored as exact zeros.
+__global__ void blend_weights_kernel(const uint2* __restrict__ dirsHalf, int R, int Rpad, float sharpness,
+                                     float* __restrict__ wIrr, float* __restrict__ wDepth)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x; // texel 0..319
+    int r = blockIdx.y;
+    if (t >= 320)
+        return;
+    const float FLT_EPS = 0.00000001f;
+    float       w       = 0.0f;
+    if (r < R)
+    {
+        uint2 dh = dirsHalf[r];
+        f3    rd = {h2f_bits((uint16_t)(dh.x & 0xffffu)), h2f_bits((uint16_t)(dh.x >> 16)), h2f_bits((uint16_t)(dh.y & 0xffffu))};
+        if (t < 64)
+        {
+            f3 td = texel_direction(t & 7, t >> 3, 8);
+            w     = gmax(0.0f, dot3(td, rd));
+        }
+        else
+        {
+            int u  = t - 64;
+            f3  td = texel_direction(u & 15, u >> 4, 16);
+            w      = pow_rn(gmax(0.0f, dot3(td, rd)), sharpness);
+        }
+        if (!(w >= FLT_EPS))
+            w = 0.0f;
+    }
+    if (t < 64)
+        wIrr[(size_t)r * 64 + t] = w;
+    else
+        wDepth[(size_t)r * 256 + (t - 64)] = w;
+}
+
+// Sequential sum over rays in ray order (the reference's accumulation order), then 1/(2*sum) (ProbeUpdate.glsl:133-134).
+__global__ void blend_scales_kernel(const float* __restrict__ wIrr, const float* __restrict__ wDepth, int R,
+                                    float* __restrict__ scaleIrr, float* __restrict__ scaleDepth)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= 320)
+        return;
+    const float FLT_EPS = 0.00000001f;
+    float       total   = 0.0f;
+    if (t < 64)
+        for (int r = 0; r < R; r++)
+            total += wIrr[(size_t)r * 64 + t];
+    else
+        for (int r = 0; r < R; r++)
+            total += wDepth[(size_t)r * 256 + (t - 64)];
+    float s = (total > FLT_EPS) ? __fdiv_rn(1.0f, 2.0f * total) : 1.0f;
+    if (t < 64)
+        scaleIrr[t] = s;
+    else
+        scaleDepth[t - 64] = s;
+}
+
+// inverse(object.transform) (AtlasCommon.glsl:133), hoisted to upload time.  Cofactor expansion fixed by the contract.
+__global__ void object_inverse_kernel(const LuxObjectBuffer* __restrict__ objects, int count, float* __restrict__ inv)
+{
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count)
+        return;
+    const float* m = objects[k].transform;
+    float*       o = inv + (size_t)k * 16;
+#define A(r, c) m[(c)*4 + (r)]
+#define B(r, c) o[(c)*4 + (r)]
+    float s0 = A(0, 0) * A(1, 1) - A(1, 0) * A(0, 1);
+    float s1 = A(0, 0) * A(1, 2) - A(1, 0) * A(0, 2);
+    float s2 = A(0, 0) * A(1, 3) - A(1, 0) * A(0, 3);
+    float s3 = A(0, 1) * A(1, 2) - A(1, 1) * A(0, 2);
+    float s4 = A(0, 1) * A(1, 3) - A(1, 1) * A(0, 3);
+    float s5 = A(0, 2) * A(1, 3) - A(1, 2) * A(0, 3);
+    float c5 = A(2, 2) * A(3, 3) - A(3, 2) * A(2, 3);
+    float c4 = A(2, 1) * A(3, 3) - A(3, 1) * A(2, 3);
+    float c3 = A(2, 1) * A(3, 2) - A(3, 1) * A(2, 2);
+    float c2 = A(2, 0) * A(3, 3) - A(3, 0) * A(2, 3);
+    float c1 = A(2, 0) * A(3, 2) - A(3, 0) * A(2, 2);
+    float c0 = A(2, 0) * A(3, 1) - A(3, 0) * A(2, 1);
+    float det = ((((s0 * c5 - s1 * c4) + s2 * c3) + s3 * c2) - s4 * c1) + s5 * c0;
+    float id  = __fdiv_rn(1.0f, det);
+    B(0, 0) = ((A(1, 1) * c5 - A(1, 2) * c4) + A(1, 3) * c3) * id;
+    B(0, 1) = ((-A(0, 1) * c5 + A(0, 2) * c4) - A(0, 3) * c3) * id;
+    B(0, 2) = ((A(3, 1) * s5 - A(3, 2) * s4) + A(3, 3) * s3) * id;
+    B(0, 3) = ((-A(2, 1) * s5 + A(2, 2) * s4) - A(2, 3) * s3) * id;
+    B(1, 0) = ((-A(1, 0) * c5 + A(1, 2) * c2) - A(1, 3) * c1) * id;
+    B(1, 1) = ((A(0, 0) * c5 - A(0, 2) * c2) + A(0, 3) * c1) * id;
+    B(1, 2) = ((-A(3, 0) * s5 + A(3, 2) * s2) - A(3, 3) * s1) * id;
+    B(1, 3) = ((A(2, 0) * s5 - A(2, 2) * s2) + A(2, 3) * s1) * id;
+    B(2, 0) = ((A(1, 0) * c4 - A(1, 1) * c2) + A(1, 3) * c0) * id;
+    B(2, 1) = ((-A(0, 0) * c4 + A(0, 1) * c2) - A(0, 3) * c0) * id;
+    B(2, 2) = ((A(3, 0) * s4 - A(3, 1) * s2) + A(3, 3) * s0) * id;
+    B(2, 3) = ((-A(2, 0) * s4 + A(2, 1) * s2) - A(2, 3) * s0) * id;
+    B(3, 0) = ((-A(1, 0) * c3 + A(1, 1) * c1) - A(1, 2) * c0) * id;
+    B(3, 1) = ((A(0, 0) * c3 - A(0, 1) * c1) + A(0, 2) * c0) * id;
+    B(3, 2) = ((-A(3, 0) * s3 + A(3, 1) * s1) - A(3, 2) * s0) * id;
+    B(3, 3) = ((A(2, 0) * s3 - A(2, 1) * s1) + A(2, 2) * s0) * id;
+#undef A
+#undef B
+}
+
+// =====================================================================================================================
+// Trace
+// =====================================================================================================================
+
+struct SdfVolume
+{
+    const uint16_t* d;
+    int             w, h, dep;
+};
+
+__device__ __forceinline__ float ld_h(const uint16_t* p) { return h2f_bits(__ldg(p)); }
+__device__ __forceinline__ float lerp1(float a, float b, float t) { return a + t * (b - a); }
+
+// texture(sampler3D, uvw).r: trilinear, clamp-to-edge, LOD 0.  Explicit fp16 loads, fp32 nested lerp x -> y -> z.
+__device__ __forceinline__ float sample3D(const SdfVolume& t, float u, float v, float w)
+{
+    float x = u * (float)t.w - 0.5f, y = v * (float)t.h - 0.5f, z = w * (float)t.dep - 0.5f;
+    float fx = floorf(x), fy = floorf(y), fz = floorf(z);
+    float ax = x - fx, ay = y - fy, az = z - fz;
+    int   ix = (int)fx, iy = (int)fy, iz = (int)fz;
+    int   x0 = iclamp(ix, 0, t.w - 1), x1 = iclamp(ix + 1, 0, t.w - 1);
+    int   y0 = iclamp(iy, 0, t.h - 1), y1 = iclamp(iy + 1, 0, t.h - 1);
+    int   z0 = iclamp(iz, 0, t.dep - 1), z1 = iclamp(iz + 1, 0, t.dep - 1);
+    const uint16_t* r00 = t.d + ((size_t)z0 * t.h + y0) * t.w;
+    const uint16_t* r10 = t.d + ((size_t)z0 * t.h + y1) * t.w;
+    const uint16_t* r01 = t.d + ((size_t)z1 * t.h + y0) * t.w;
+    const uint16_t* r11 = t.d + ((size_t)z1 * t.h + y1) * t.w;
+    float v000 = ld_h(r00 + x0), v100 = ld_h(r00 + x1);
+    float v010 = ld_h(r10 + x0), v110 = ld_h(r10 + x1);
+    float v001 = ld_h(r01 + x0), v101 = ld_h(r01 + x1);
+    float v011 = ld_h(r11 + x0), v111 = ld_h(r11 + x1);
+    float c00 = lerp1(v000, v100, ax);
+    float c10 = lerp1(v010, v110, ax);
+    float c01 = lerp1(v001, v101, ax);
+    float c11 = lerp1(v011, v111, ax);
+    float c0  = lerp1(c00, c10, ay);
+    float c1  = lerp1(c01, c11, ay);
+    return lerp1(c0, c1, az);
+}
+
+struct Hit
+{
+    f3       normal;
+    float    time;
+    uint32_t cascade;
+    uint32_t steps;
+    float    sdf;
+};
+
+// SDFCommon.glsl:84-95
+__device__ __forceinline__ void line_hit_aabb(f3 s, f3 e, f3 bmin, f3 bmax, float& nearT, float& farT)
+{
+    f3 inv   = {__fdiv_rn(1.0f, e.x - s.x), __fdiv_rn(1.0f, e.y - s.y), __fdiv_rn(1.0f, e.z - s.z)};
+    f3 enter = (bmin - s) * inv;
+    f3 exit_ = (bmax - s) * inv;
+    f3 mn    = {gmin(enter.x, exit_.x), gmin(enter.y, exit_.y), gmin(enter.z, exit_.z)};
+    f3 mx    = {gmax(enter.x, exit_.x), gmax(enter.y, exit_.y), gmax(enter.z, exit_.z)};
+    nearT    = gclamp(gmax(mn.x, gmax(mn.y, mn.z)), 0.0f, 1.0f);
+    farT     = gclamp(gmin(mx.x, gmin(mx.y, mx.z)), 0.0f, 1.0f);
+}
+
+// SDFCommon.glsl:98-194 (tracyGlobalSDF) with minDistance 0, stepScale 1, needsHitNormal true, start bias 0
+__device__ __forceinline__ Hit trace_global_sdf(const TraceParams& P, f3 origin, f3 dir, float maxDistance)
+{
+    const LuxGlobalSDFData& data = P.sdf;
+    Hit hit;
+    hit.steps   = 0;
+    hit.time    = -1.0f;
+    hit.normal  = {0.0f, 0.0f, 0.0f};
+    hit.cascade = 0;
+    hit.sdf     = 0.0f;
+
+    const float stepScale = 1.0f, cascadeTraceStartBias = 0.0f;
+    float traceMaxDistance    = gmin(maxDistance, data.cascadePosDistance[data.cascadesCount - 1][3] * 2.0f);
+    float chunkSizeDistance   = __fdiv_rn((float)LUX_GLOBAL_SDF_RASTERIZE_CHUNK_SIZE, data.resolution);
+    float chunkMarginDistance = __fdiv_rn((float)LUX_GLOBAL_SDF_RASTERIZE_CHUNK_MARGIN, data.resolution);
+    float nextIntersectionStart = 0.0f;
+    f3    traceEnd        = origin + dir * traceMaxDistance;
+    float cascadesCountF  = (float)data.cascadesCount;
+    SdfVolume tex = {P.tex, P.res * P.cascades, P.res, P.res};
+    SdfVolume mip = {P.mip, P.mipRes * P.cascades, P.mipRes, P.mipRes};
+
+    for (uint32_t cascade = 0; cascade < data.cascadesCount && hit.time < 0.0f; cascade++)
+    {
+        f3    c         = {data.cascadePosDistance[cascade][0], data.cascadePosDistance[cascade][1], data.cascadePosDistance[cascade][2]};
+        float cd        = data.cascadePosDistance[cascade][3];
+        float voxelSize = data.cascadeVoxelSize[cascade];
+        float voxelHalf = voxelSize * 0.5f;
+        f3    worldPosition = origin + dir * (voxelSize * cascadeTraceStartBias);
+        f3    ext = {cd, cd, cd};
+
+        float nearT, farT;
+        line_hit_aabb(worldPosition, traceEnd, c - ext, c + ext, nearT, farT);
+        nearT *= traceMaxDistance;
+        farT *= traceMaxDistance;
+        nearT = gmax(nearT, nextIntersectionStart);
+
+        float stepTime = nearT;
+        if (nearT >= farT)
+            stepTime = farT;
+        else
+            nextIntersectionStart = farT;
+
+        float    cascadeMaxDistance = cd * 2.0f;
+        uint32_t step = 0;
+        for (; step < LUX_GLOBAL_SDF_MAX_STEPS && stepTime < farT; step++)
+        {
+            f3 stepPosition = worldPosition + dir * stepTime;
+            f3 pc           = stepPosition - c;
+            f3 cuv = {gclamp(__fdiv_rn(pc.x, cascadeMaxDistance) + 0.5f, 0.0f, 1.0f),
+                      gclamp(__fdiv_rn(pc.y, cascadeMaxDistance) + 0.5f, 0.0f, 1.0f),
+                      gclamp(__fdiv_rn(pc.z, cascadeMaxDistance) + 0.5f, 0.0f, 1.0f)};
+            f3 uvw = {__fdiv_rn((float)cascade + cuv.x, cascadesCountF), cuv.y, cuv.z};
+
+            float stepDistance = sample3D(mip, uvw.x, uvw.y, uvw.z);
+            if (stepDistance < chunkSizeDistance)
+            {
+                float stepDistanceTex = sample3D(tex, uvw.x, uvw.y, uvw.z);
+                if (stepDistanceTex < chunkMarginDistance * 2.0f)
+                    stepDistance = stepDistanceTex;
+            }
+            else
+                stepDistance = chunkSizeDistance;
+
+            stepDistance *= cascadeMaxDistance;
+
+            float minSurfaceThickness = voxelHalf * gclamp(__fdiv_rn(stepTime, voxelSize), 0.0f, 1.0f);
+            if (stepDistance < minSurfaceThickness)
+            {
+                hit.time    = gmax((stepTime + stepDistance) - minSurfaceThickness, 0.0f);
+                hit.cascade = cascade;
+                hit.sdf     = stepDistance;
+                float o  = __fdiv_rn(1.0f, data.resolution);
+                float xp = sample3D(tex, uvw.x + o, uvw.y, uvw.z);
+                float xn = sample3D(tex, uvw.x - o, uvw.y, uvw.z);
+                float yp = sample3D(tex, uvw.x, uvw.y + o, uvw.z);
+                float yn = sample3D(tex, uvw.x, uvw.y - o, uvw.z);
+                float zp = sample3D(tex, uvw.x, uvw.y, uvw.z + o);
+                float zn = sample3D(tex, uvw.x, uvw.y, uvw.z - o);
+                hit.normal = normalize3({xp - xn, yp - yn, zp - zn});
+                break;
+            }
+            stepTime += gmax(stepDistance * stepScale, voxelSize);
+        }
+        hit.steps += step;
+    }
+    return hit;
+}
+
+__device__ __forceinline__ void gather_coords(float u, float v, int W, int H, bool repeat, int& i0, int& i1, int& j0, int& j1)
+{
+    int a = (int)floorf(u * (float)W - 0.5f);
+    int b = (int)floorf(v * (float)H - 0.5f);
+    if (repeat)
+    {
+        i0 = ((a % W) + W) % W; i1 = (((a + 1) % W) + W) % W;
+        j0 = ((b % H) + H) % H; j1 = (((b + 1) % H) + H) % H;
+    }
+    else
+    {
+        i0 = iclamp(a, 0, W - 1); i1 = iclamp(a + 1, 0, W - 1);
+        j0 = iclamp(b, 0, H - 1); j1 = iclamp(b + 1, 0, H - 1);
+    }
+}
+
+__device__ __forceinline__ f4 unpack_rgba16f(uint2 t)
+{
+    return {h2f_bits((uint16_t)(t.x & 0xffffu)), h2f_bits((uint16_t)(t.x >> 16)), h2f_bits((uint16_t)(t.y & 0xffffu)),
+            h2f_bits((uint16_t)(t.y >> 16))};
+}
+
+// AtlasCommon.glsl:58-112: one tile of one object
+__device__ __forceinline__ f4 sample_atlas_tile(const TraceParams& P, const LuxTileBuffer* __restrict__ tile, f3 localPosition,
+                                                f3 normal, float surfaceThreshold)
+{
+    float tm[16];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+    {
+        float4 c = __ldg(reinterpret_cast<const float4*>(tile->transform) + i);
+        tm[i * 4 + 0] = c.x; tm[i * 4 + 1] = c.y; tm[i * 4 + 2] = c.z; tm[i * 4 + 3] = c.w;
+    }
+    f3 nt = normalize3(mat4_mul_point(tm, normal, 1.0f));
+    float normalWeight = gclamp(nt.z, 0.0f, 1.0f);
+    normalWeight = __fdiv_rn(normalWeight - LUX_SURFACE_ATLAS_TILE_NORMAL_THRESHOLD, 1.0f - LUX_SURFACE_ATLAS_TILE_NORMAL_THRESHOLD);
+    if (normalWeight <= 0.0f)
+        return {0.0f, 0.0f, 0.0f, 0.0f};
+
+    float4 ext = __ldg(reinterpret_cast<const float4*>(tile->extends));
+    float4 ob  = __ldg(reinterpret_cast<const float4*>(tile->objectBounds));
+    f3     tp  = mat4_mul_point(tm, localPosition, 1.0f);
+    float  tileDepth = __fdiv_rn(tp.z, ob.z);
+    float  tu = gclamp(__fdiv_rn(tp.x, ob.x) + 0.5f, 0.0f, 1.0f);
+    float  tv = gclamp(__fdiv_rn(tp.y, ob.y) + 0.5f, 0.0f, 1.0f);
+    float  au = tu * ext.z + ext.x, av = tv * ext.w + ext.y;
+    float  res = (float)P.atlasRes;
+    float  fx = gfract(au * res + 0.5f), fy = gfract(av * res + 0.5f);
+    f4     bw = {(1.0f - fx) * fy, fx * fy, fx * (1.0f - fy), (1.0f - fx) * (1.0f - fy)};
+
+    int R = (int)P.atlasRes, i0, i1, j0, j1;
+    gather_coords(au, av, R, R, false, i0, i1, j0, j1);
+    float z4[4] = {__ldg(P.depth + (size_t)j1 * R + i0), __ldg(P.depth + (size_t)j1 * R + i1), __ldg(P.depth + (size_t)j0 * R + i1),
+                   __ldg(P.depth + (size_t)j0 * R + i0)};
+    float depthThreshold = __fdiv_rn(2.0f * surfaceThreshold, ob.z);
+    float vis[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+    {
+        vis[i] = 1.0f - gclamp(__fdiv_rn(fabsf(tileDepth - z4[i]) - depthThreshold, 0.5f * depthThreshold), 0.0f, 1.0f);
+        if (z4[i] >= 1.0f)
+            vis[i] = 0.0f;
+    }
+    f4    visv = {vis[0], vis[1], vis[2], vis[3]};
+    float sampleWeight = dot4(visv, bw);
+    sampleWeight *= normalWeight;
+    if (sampleWeight <= 0.0f)
+        return {0.0f, 0.0f, 0.0f, 0.0f};
+
+    bw = {bw.x * visv.x, bw.y * visv.y, bw.z * visv.z, bw.w * visv.w};
+    gather_coords(au, av, R, R, true, i0, i1, j0, j1);
+    f4 t0 = unpack_rgba16f(__ldg(P.light + (size_t)j1 * R + i0));
+    f4 t1 = unpack_rgba16f(__ldg(P.light + (size_t)j1 * R + i1));
+    f4 t2 = unpack_rgba16f(__ldg(P.light + (size_t)j0 * R + i1));
+    f4 t3 = unpack_rgba16f(__ldg(P.light + (size_t)j0 * R + i0));
+    float cr = dot4({t0.x, t1.x, t2.x, t3.x}, bw);
+    float cg = dot4({t0.y, t1.y, t2.y, t3.y}, bw);
+    float cb = dot4({t0.z, t1.z, t2.z, t3.z}, bw);
+    return {cr * sampleWeight, cg * sampleWeight, cb * sampleWeight, sampleWeight};
+}
+
+// AtlasCommon.glsl:115-157 (sampleGlobalSurfaceAtlas, debug = false)
+__device__ __forceinline__ f4 sample_global_surface_atlas(const TraceParams& P, f3 worldPosition, f3 worldNormal, float surfaceThreshold)
+{
+    f4 result = {0.0f, 0.0f, 0.0f, 0.0f};
+    if (!P.hasAtlas)
+        return result;
+    const float half = (float)LUX_SURFACE_ATLAS_CHUNKS_RESOLUTION * 0.5f;
+    const int   N    = LUX_SURFACE_ATLAS_CHUNKS_RESOLUTION;
+    int cx = iclamp((int)floorf(__fdiv_rn(worldPosition.x, P.chunkSize) + half), 0, N - 1);
+    int cy = iclamp((int)floorf(__fdiv_rn(worldPosition.y, P.chunkSize) + half), 0, N - 1);
+    int cz = iclamp((int)floorf(__fdiv_rn(worldPosition.z, P.chunkSize) + half), 0, N - 1);
+    uint32_t objectsStart = __ldg(P.chunks + (cz * N * N + cy * N + cx));
+    if (objectsStart == 0)
+        return result;
+    uint32_t objectsCount = __ldg(P.cull + objectsStart);
+    if (objectsCount > P.objectsCount)
+        return result;
+    objectsStart++;
+    for (uint32_t k = 0; k < objectsCount; k++)
+    {
+        uint32_t               objectAddress = __ldg(P.cull + objectsStart++);
+        const LuxObjectBuffer* object        = P.objects + objectAddress;
+        float4                 ob            = __ldg(reinterpret_cast<const float4*>(object->objectBounds));
+        f3                     bc            = {ob.x, ob.y, ob.z};
+        if (length3(bc - worldPosition) > ob.w)
+            continue;
+        float wl[16];
+        const float4* invp = reinterpret_cast<const float4*>(P.objectInverse + (size_t)objectAddress * 16);
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+        {
+            float4 c = __ldg(invp + i);
+            wl[i * 4 + 0] = c.x; wl[i * 4 + 1] = c.y; wl[i * 4 + 2] = c.z; wl[i * 4 + 3] = c.w;
+        }
+        f3     localPosition = mat4_mul_point(wl, worldPosition, 1.0f);
+        float4 ex            = __ldg(reinterpret_cast<const float4*>(object->extends));
+        if (fabsf(localPosition.x) > ex.x + surfaceThreshold || fabsf(localPosition.y) > ex.y + surfaceThreshold ||
+            fabsf(localPosition.z) > ex.z + surfaceThreshold)
+            continue;
+        f3 normal = normalize3(mat3_mul(wl, worldNormal));
+#pragma unroll 1
+        for (int i = 0; i < 6; i++)
+        {
+            uint32_t tileOffset = __ldg(object->tileOffset + i);
+            if (tileOffset != 0)
+            {
+                f4 s = sample_atlas_tile(P, P.tiles + tileOffset, localPosition, normal, surfaceThreshold);
+                result.x += s.x; result.y += s.y; result.z += s.z; result.w += s.w;
+            }
+        }
+    }
+    float d = gmax(result.w, 0.0001f);
+    result.x = __fdiv_rn(result.x, d);
+    result.y = __fdiv_rn(result.y, d);
+    result.z = __fdiv_rn(result.z, d);
+    return result;
+}
+
+// texture(samplerCube, dir).rgb: Vulkan face selection, bilinear inside the face, clamp at the face edge
+__device__ __forceinline__ f3 sample_sky(const TraceParams& P, f3 d)
+{
+    if (P.sky == nullptr || P.skyFace <= 0)
+        return {0.0f, 0.0f, 0.0f};
+    float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+    int   face;
+    float sc, tc, ma;
+    if (az >= ax && az >= ay) { face = d.z >= 0.0f ? 4 : 5; sc = d.z >= 0.0f ? d.x : -d.x; tc = -d.y; ma = az; }
+    else if (ay >= ax)        { face = d.y >= 0.0f ? 2 : 3; sc = d.x; tc = d.y >= 0.0f ? d.z : -d.z; ma = ay; }
+    else                      { face = d.x >= 0.0f ? 0 : 1; sc = d.x >= 0.0f ? -d.z : d.z; tc = -d.y; ma = ax; }
+    float u = 0.5f * __fdiv_rn(sc, ma) + 0.5f, v = 0.5f * __fdiv_rn(tc, ma) + 0.5f;
+    int   N = P.skyFace;
+    float x = u * (float)N - 0.5f, y = v * (float)N - 0.5f;
+    float fx = floorf(x), fy = floorf(y);
+    float axw = x - fx, ayw = y - fy;
+    int   x0 = iclamp((int)fx, 0, N - 1), x1 = iclamp((int)fx + 1, 0, N - 1);
+    int   y0 = iclamp((int)fy, 0, N - 1), y1 = iclamp((int)fy + 1, 0, N - 1);
+    const uint2* base = P.sky + (size_t)face * N * N;
+    f4 t00 = unpack_rgba16f(__ldg(base + (size_t)y0 * N + x0)), t10 = unpack_rgba16f(__ldg(base + (size_t)y0 * N + x1));
+    f4 t01 = unpack_rgba16f(__ldg(base + (size_t)y1 * N + x0)), t11 = unpack_rgba16f(__ldg(base + (size_t)y1 * N + x1));
+    f3 out;
+    out.x = lerp1(lerp1(t00.x, t10.x, axw), lerp1(t01.x, t11.x, axw), ayw);
+    out.y = lerp1(lerp1(t00.y, t10.y, axw), lerp1(t01.y, t11.y, axw), ayw);
+    out.z = lerp1(lerp1(t00.z, t10.z, axw), lerp1(t01.z, t11.z, axw), ayw);
+    return out;
+}
+
+// Thread (x = probe lane, y = ray in group).  A warp holds 32 consecutive probes tracing the SAME ray direction:
+// parallel rays from a row of probes stay spatially coherent (adjacent SDF rows, same surface-cache objects) and
+// terminate after similar step counts, unlike the 32 divergent directions of one probe.
+constexpr int TRACE_RAYS_PER_BLOCK = 8;
+
+__global__ void __launch_bounds__(32 * TRACE_RAYS_PER_BLOCK) trace_kernel(const __grid_constant__ TraceParams P)
+{
+    __shared__ uint2 sRad[32][TRACE_RAYS_PER_BLOCK + 1];
+    __shared__ uint2 sDir[32][TRACE_RAYS_PER_BLOCK + 1];
+
+    const int lane       = threadIdx.x;
+    const int rayInGroup = threadIdx.y;
+    const int rayId      = blockIdx.x * TRACE_RAYS_PER_BLOCK + rayInGroup;
+    const int probeLocal = blockIdx.y * 32 + lane;
+    const bool active    = (rayId < P.raysPerProbe) && (probeLocal < P.probeCount);
+
+    if (active)
+    {
+        const int probeId = P.probeBegin + probeLocal;
+        // probeLocation, DDGICommon.glsl:101-114
+        int cx = probeId % P.countX;
+        int cy = (probeId % (P.countX * P.countY)) / P.countX;
+        int cz = probeId / (P.countX * P.countY);
+        f3  rayOrigin = {P.step[0] * (float)cx + P.start[0], P.step[1] * (float)cy + P.start[1], P.step[2] * (float)cz + P.start[2]};
+        float4 d4 = __ldg(P.dirs + rayId);
+        f3     direction = {d4.x, d4.y, d4.z};
+
+        Hit hit = trace_global_sdf(P, rayOrigin, direction, LUX_GLOBAL_SDF_WORLD_SIZE);
+
+        f4 radiance = {0.0f, 0.0f, 0.0f, 0.0f};
+        if (hit.time >= 0.0f)
+        {
+            if (hit.sdf <= 0.0f && hit.time <= P.sdf.cascadeVoxelSize[0])
+                radiance = {0.0f, 0.0f, 0.0f, LUX_GLOBAL_SDF_WORLD_SIZE};
+            else
+            {
+                f3    hitPosition      = rayOrigin + direction * hit.time;
+                float surfaceThreshold = P.sdf.cascadeVoxelSize[hit.cascade] * 1.05f;
+                f4    sc = sample_global_surface_atlas(P, hitPosition, hit.normal, surfaceThreshold);
+                radiance   = {sc.x, sc.y, sc.z, hit.time};
+                radiance.w = gmax(radiance.w + P.sdf.cascadeVoxelSize[hit.cascade] * 0.5f, 0.0f);
+            }
+        }
+        else
+        {
+            f3 s     = sample_sky(P, direction);
+            radiance = {s.x, s.y, s.z, LUX_GLOBAL_SDF_WORLD_SIZE};
+        }
+        uint32_t r0 = f2h_bits(radiance.x), r1 = f2h_bits(radiance.y), r2 = f2h_bits(radiance.z);
+        uint32_t d0 = f2h_bits(direction.x), d1 = f2h_bits(direction.y), d2 = f2h_bits(direction.z), d3 = f2h_bits(radiance.w);
+        sRad[lane][rayInGroup] = make_uint2(r0 | (r1 << 16), r2); // alpha = 0
+        sDir[lane][rayInGroup] = make_uint2(d0 | (d1 << 16), d2 | (d3 << 16));
+        if (P.steps)
+            P.steps[(size_t)probeLocal * P.raysPerProbe + rayId] = (uint16_t)hit.steps;
+    }
+    __syncthreads();
+    // transposed write-out: consecutive threads -> consecutive rays of one probe (64 contiguous bytes per probe)
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    const int pl  = tid / TRACE_RAYS_PER_BLOCK, rl = tid % TRACE_RAYS_PER_BLOCK;
+    const int ray = blockIdx.x * TRACE_RAYS_PER_BLOCK + rl, probe = blockIdx.y * 32 + pl;
+    if (ray < P.raysPerProbe && probe < P.probeCount)
+    {
+        size_t o = (size_t)probe * P.raysPerProbe + ray;
+        P.radiance[o] = sRad[pl][rl];
+        P.dirDist[o]  = sDir[pl][rl];
+    }
+}
+
+// =====================================================================================================================
+// Blend (+ fused border)
+// =====================================================================================================================
+//
+// Because the weights are probe independent the blend is   Out[(probe,channel)][texel] = sum_r Val[(probe,channel)][r] * W[r][texel]
+// i.e. a small-N SGEMM.  It is evaluated on the FP32 pipe with one FFMA per (value, weight) pair and each accumulator
+// walks r = 0..R-1 in order, which is exactly the reference's sequential loop (ProbeUpdate.glsl:68-102) with the
+// gated weights stored as zeros.  Register tile 8 (rows) x 8 (texels) per thread; A = values staged in shared memory
+// as [row][k] (+1 pad), B = weights staged as [k][texel].
+
+constexpr int KC = 32; // rays per shared-memory chunk
+
+// mirrored border stores for interior texel (i, j) of a probe whose ring origin is (bx, by)  (BorderUpdate.glsl:25-133)
+template <typename T>
+__device__ __forceinline__ void store_with_border(T* __restrict__ img, int W, int bx, int by, int side, int i, int j, T v, bool border)
+{
+    const int x = i + 1, y = j + 1;
+    img[(size_t)(by + y) * W + (bx + x)] = v;
+    if (!border)
+        return;
+    if (y == 1)    img[(size_t)(by + 0) * W + (bx + side + 1 - x)] = v;
+    if (y == side) img[(size_t)(by + side + 1) * W + (bx + side + 1 - x)] = v;
+    if (x == 1)    img[(size_t)(by + side + 1 - y) * W + (bx + 0)] = v;
+    if (x == side) img[(size_t)(by + side + 1 - y) * W + (bx + side + 1)] = v;
+    if (x == side && y == side) img[(size_t)(by + 0) * W + (bx + 0)] = v;
+    if (x == 1 && y == side)    img[(size_t)(by + 0) * W + (bx + side + 1)] = v;
+    if (x == side && y == 1)    img[(size_t)(by + side + 1) * W + (bx + 0)] = v;
+    if (x == 1 && y == 1)       img[(size_t)(by + side + 1) * W + (bx + side + 1)] = v;
+}
+
+// Irradiance: PB probes per block, rows m = p*3 + channel (M = 3*PB), N = 64 texels.
+template <int PB>
+__global__ void __launch_bounds__((3 * PB / 8) * 8) blend_irradiance_kernel(const __grid_constant__ BlendParams P)
+{
+    constexpr int M = 3 * PB, N = 64, NT = (M / 8) * 8;
+    extern __shared__ __align__(16) float smem[];
+    float* As = smem;                  // [M][KC+1]
+    float* Bs = smem + M * (KC + 1);   // [KC][N]
+    float* Cs = smem;                  // epilogue overlay [M][N]
+
+    const int tid  = threadIdx.x;
+    const int ng   = tid & 7;  // texel group: texels ng*8 .. ng*8+7
+    const int mg   = tid >> 3; // row group: rows mg*8 .. mg*8+7
+    const int probe0 = blockIdx.x * PB; // shard-local index of the block's first probe
+    const int R = P.raysPerProbe;
+
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+            acc[i][j] = 0.0f;
+
+    for (int k0 = 0; k0 < P.raysPadded; k0 += KC)
+    {
+        // A: radiance texels -> fp32 rows.  Consecutive threads read consecutive rays of one probe (coalesced) and write
+        // consecutive k of one row (conflict-free).
+        for (int idx = tid; idx < PB * KC; idx += NT)
+        {
+            int p = idx / KC, k = idx % KC;
+            int probe = probe0 + p, ray = k0 + k;
+            uint2 t = make_uint2(0u, 0u);
+            if (probe < P.probeCount && ray < R)
+                t = __ldg(P.radiance + (size_t)probe * R + ray);
+            As[(p * 3 + 0) * (KC + 1) + k] = h2f_bits((uint16_t)(t.x & 0xffffu));
+            As[(p * 3 + 1) * (KC + 1) + k] = h2f_bits((uint16_t)(t.x >> 16));
+            As[(p * 3 + 2) * (KC + 1) + k] = h2f_bits((uint16_t)(t.y & 0xffffu));
+        }
+        // B: weights chunk [KC][64] is contiguous in global memory
+        {
+            const float4* src = reinterpret_cast<const float4*>(P.wIrr + (size_t)k0 * N);
+            float4*       dst = reinterpret_cast<float4*>(Bs);
+            for (int idx = tid; idx < KC * N / 4; idx += NT)
+                dst[idx] = __ldg(src + idx);
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int k = 0; k < KC; k++)
+        {
+            float a[8], b[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+                a[i] = As[(mg * 8 + i) * (KC + 1) + k];
+            float4 b0 = *reinterpret_cast<const float4*>(Bs + k * N + ng * 8);
+            float4 b1 = *reinterpret_cast<const float4*>(Bs + k * N + ng * 8 + 4);
+            b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    acc[i][j] = __fmaf_rn(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+
+    // epilogue: accumulators -> Cs[row][texel]
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+    {
+        float4* dst = reinterpret_cast<float4*>(Cs + (mg * 8 + i) * N + ng * 8);
+        dst[0] = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        dst[1] = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+    }
+    __syncthreads();
+
+    const uint32_t one = 0x3c00u; // fp16 1.0 (alpha, ProbeUpdate.glsl:150)
+    for (int idx = tid; idx < PB * N; idx += NT)
+    {
+        int p = idx / N, t = idx % N;
+        int probeLocal = probe0 + p;
+        if (probeLocal >= P.probeCount)
+            continue;
+        int   probe = P.probeBegin + probeLocal;
+        float s = __ldg(P.scaleIrr + t);
+        float r = Cs[(p * 3 + 0) * N + t] * s, g = Cs[(p * 3 + 1) * N + t] * s, b = Cs[(p * 3 + 2) * N + t] * s;
+        r = pow_rn(r, P.invGamma);
+        g = pow_rn(g, P.invGamma);
+        b = pow_rn(b, P.invGamma);
+        int i = t & 7, j = t >> 3;
+        int bx = (probe % P.probesPerRow) * 10 + 1, by = (probe / P.probesPerRow) * 10 + 1;
+        if (!P.firstFrame)
+        {
+            f4 prev = unpack_rgba16f(__ldg(P.prevIrr + (size_t)(by + j + 1) * P.irrWidth + (bx + i + 1)));
+            r = mixh(r, prev.x, P.hysteresis);
+            g = mixh(g, prev.y, P.hysteresis);
+            b = mixh(b, prev.z, P.hysteresis);
+        }
+        uint2 o = make_uint2((uint32_t)f2h_bits(r) | ((uint32_t)f2h_bits(g) << 16), (uint32_t)f2h_bits(b) | (one << 16));
+        store_with_border<uint2>(P.outIrr, P.irrWidth, bx, by, 8, i, j, o, P.fuseBorder != 0);
+    }
+}
+
+// Depth: PB probes per block, rows m = p*2 + {d, d*d} (M = 2*PB), N = 256 texels; thread tile 8 rows x 8 texels.
+template <int PB>
+__global__ void __launch_bounds__((2 * PB / 8) * 32) blend_depth_kernel(const __grid_constant__ BlendParams P)
+{
+    constexpr int M = 2 * PB, N = 256, NT = (M / 8) * 32;
+    extern __shared__ __align__(16) float smem[];
+    constexpr int MS = M + 4;    // padded row stride of As (keeps float4 alignment, spreads banks for the k-major stores)
+    float* As = smem;            // [KC][MS] (k-major: all lanes of a warp read the same 8 rows -> broadcast)
+    float* Bs = smem + KC * MS;  // [KC][N]
+    float* Cs = smem;            // epilogue overlay [M][N]
+
+    const int tid  = threadIdx.x;
+    const int ng   = tid & 31; // texel group
+    const int mg   = tid >> 5; // row group (one per warp)
+    const int probe0 = blockIdx.x * PB;
+    const int R = P.raysPerProbe;
+
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+            acc[i][j] = 0.0f;
+
+    for (int k0 = 0; k0 < P.raysPadded; k0 += KC)
+    {
+        for (int idx = tid; idx < PB * KC; idx += NT)
+        {
+            int p = idx / KC, k = idx % KC; // consecutive threads -> consecutive rays of one probe (coalesced)
+            int probe = probe0 + p, ray = k0 + k;
+            float d = 0.0f;
+            if (probe < P.probeCount && ray < R)
+            {
+                uint2 t = __ldg(P.dirDist + (size_t)probe * R + ray);
+                d = gmin(P.maxDistance, h2f_bits((uint16_t)(t.y >> 16)) - 0.01f); // ProbeUpdate.glsl:75
+                if (d == -1.0f)
+                    d = P.maxDistance;
+            }
+            *reinterpret_cast<float2*>(As + k * MS + p * 2) = make_float2(d, d * d);
+        }
+        {
+            const float4* src = reinterpret_cast<const float4*>(P.wDepth + (size_t)k0 * N);
+            float4*       dst = reinterpret_cast<float4*>(Bs);
+            for (int idx = tid; idx < KC * N / 4; idx += NT)
+                dst[idx] = __ldg(src + idx);
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int k = 0; k < KC; k++)
+        {
+            float a[8], b[8];
+            float4 a0 = *reinterpret_cast<const float4*>(As + k * MS + mg * 8);
+            float4 a1 = *reinterpret_cast<const float4*>(As + k * MS + mg * 8 + 4);
+            a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+            float4 b0 = *reinterpret_cast<const float4*>(Bs + k * N + ng * 8);
+            float4 b1 = *reinterpret_cast<const float4*>(Bs + k * N + ng * 8 + 4);
+            b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+#pragma unroll
+                for (int j = 0; j < 8; j++)
+                    acc[i][j] = __fmaf_rn(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+    {
+        float4* dst = reinterpret_cast<float4*>(Cs + (mg * 8 + i) * N + ng * 8);
+        dst[0] = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        dst[1] = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+    }
+    __syncthreads();
+
+    for (int idx = tid; idx < PB * N; idx += NT)
+    {
+        int p = idx / N, t = idx % N;
+        int probeLocal = probe0 + p;
+        if (probeLocal >= P.probeCount)
+            continue;
+        int   probe = P.probeBegin + probeLocal;
+        float s = __ldg(P.scaleDepth + t);
+        float r = Cs[(p * 2 + 0) * N + t] * s, g = Cs[(p * 2 + 1) * N + t] * s;
+        int i = t & 15, j = t >> 4;
+        int bx = (probe % P.probesPerRow) * 18 + 1, by = (probe / P.probesPerRow) * 18 + 1;
+        if (!P.firstFrame)
+        {
+            uint32_t pv = __ldg(P.prevDepth + (size_t)(by + j + 1) * P.depthWidth + (bx + i + 1));
+            r = mixh(r, h2f_bits((uint16_t)(pv & 0xffffu)), P.hysteresis);
+            g = mixh(g, h2f_bits((uint16_t)(pv >> 16)), P.hysteresis);
+        }
+        uint32_t o = (uint32_t)f2h_bits(r) | ((uint32_t)f2h_bits(g) << 16);
+        store_with_border<uint32_t>(P.outDepth, P.depthWidth, bx, by, 16, i, j, o, P.fuseBorder != 0);
+    }
+}
+
+// Standalone border pass (BorderUpdate.glsl:136-156): one warp-sized group of threads per probe and atlas.
+template <typename T, int SIDE>
+__global__ void border_kernel(T* __restrict__ img, int W, int probesPerRow, int probeBegin, int probeCount)
+{
+    constexpr int NB = 4 * SIDE + 4; // 36 / 68 copies
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    int p = idx / NB, e = idx % NB;
+    if (p >= probeCount)
+        return;
+    int probe = probeBegin + p;
+    int bx = (probe % probesPerRow) * (SIDE + 2) + 1, by = (probe / probesPerRow) * (SIDE + 2) + 1;
+    int sx, sy, dx, dy;
+    if (e < SIDE)            { int x = e + 1;            sx = SIDE + 1 - x; sy = 1;    dx = x; dy = 0; }
+    else if (e < 2 * SIDE)   { int x = e - SIDE + 1;     sx = SIDE + 1 - x; sy = SIDE; dx = x; dy = SIDE + 1; }
+    else if (e < 3 * SIDE)   { int y = e - 2 * SIDE + 1; sx = 1;    sy = SIDE + 1 - y; dx = 0;        dy = y; }
+    else if (e < 4 * SIDE)   { int y = e - 3 * SIDE + 1; sx = SIDE; sy = SIDE + 1 - y; dx = SIDE + 1; dy = y; }
+    else if (e == 4 * SIDE)     { sx = SIDE; sy = SIDE; dx = 0;        dy = 0; }
+    else if (e == 4 * SIDE + 1) { sx = 1;    sy = SIDE; dx = SIDE + 1; dy = 0; }
+    else if (e == 4 * SIDE + 2) { sx = SIDE; sy = 1;    dx = 0;        dy = SIDE + 1; }
+    else                        { sx = 1;    sy = 1;    dx = SIDE + 1; dy = SIDE + 1; }
+    img[(size_t)(by + dy) * W + (bx + dx)] = img[(size_t)(by + sy) * W + (bx + sx)];
+}
+
+// =====================================================================================================================
+// Launchers
+// =====================================================================================================================
+
+void launch_ray_dirs(const float* rot16Host, int R, float4* dirs, cudaStream_t s)
+{
+    RotationArg rot;
+    for (int i = 0; i < 16; i++)
+        rot.m[i] = rot16Host[i];
+    ray_dirs_kernel<<<(R + 127) / 128, 128, 0, s>>>(rot, R, dirs);
+}
+
+void launch_blend_weights(const uint2* dirsHalf, int R, int Rpad, float sharpness, float* wIrr, float* wDepth, float* scaleIrr,
+                          float* scaleDepth, cudaStream_t s)
+{
+    blend_weights_kernel<<<dim3(5, Rpad), 64, 0, s>>>(dirsHalf, R, Rpad, sharpness, wIrr, wDepth);
+    blend_scales_kernel<<<5, 64, 0, s>>>(wIrr, wDepth, R, scaleIrr, scaleDepth);
+}
+
+void launch_object_inverse(const LuxObjectBuffer* objects, int count, float* inv, cudaStream_t s)
+{
+    if (count > 0)
+        object_inverse_kernel<<<(count + 127) / 128, 128, 0, s>>>(objects, count, inv);
+}
+
+void launch_trace(const TraceParams& p, bool /*useTexture*/, cudaStream_t s)
+{
+    dim3 block(32, TRACE_RAYS_PER_BLOCK);
+    dim3 grid((p.raysPerProbe + TRACE_RAYS_PER_BLOCK - 1) / TRACE_RAYS_PER_BLOCK, (p.probeCount + 31) / 32);
+    trace_kernel<<<grid, block, 0, s>>>(p);
+}
+
+template <int PB>
+static void launch_blend_irradiance_t(const BlendParams& p, cudaStream_t s)
+{
+    constexpr int M = 3 * PB, NT = (M / 8) * 8;
+    size_t main = (size_t)(M * (KC + 1) + KC * 64) * sizeof(float), epi = (size_t)M * 64 * sizeof(float);
+    size_t smem = main > epi ? main : epi;
+    static bool attr = false;
+    if (!attr)
+    {
+        cudaFuncSetAttribute(blend_irradiance_kernel<PB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr = true;
+    }
+    blend_irradiance_kernel<PB><<<(p.probeCount + PB - 1) / PB, NT, smem, s>>>(p);
+}
+
+void launch_blend_irradiance(const BlendParams& p, cudaStream_t s)
+{
+    if (p.probeCount >= 64 * 148)
+        launch_blend_irradiance_t<64>(p, s);
+    else
+        launch_blend_irradiance_t<16>(p, s);
+}
+
+template <int PB>
+static void launch_blend_depth_t(const BlendParams& p, cudaStream_t s)
+{
+    constexpr int M = 2 * PB, NT = (M / 8) * 32;
+    size_t main = (size_t)(KC * (M + 4) + KC * 256) * sizeof(float), epi = (size_t)M * 256 * sizeof(float);
+    size_t smem = main > epi ? main : epi;
+    static bool attr = false;
+    if (!attr)
+    {
+        cudaFuncSetAttribute(blend_depth_kernel<PB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr = true;
+    }
+    blend_depth_kernel<PB><<<(p.probeCount + PB - 1) / PB, NT, smem, s>>>(p);
+}
+
+void launch_blend_depth(const BlendParams& p, cudaStream_t s)
+{
+    if (p.probeCount >= 32 * 148)
+        launch_blend_depth_t<32>(p, s);
+    else
+        launch_blend_depth_t<8>(p, s);
+}
+
+void launch_border(uint2* irr, int irrWidth, uint32_t* depth, int depthWidth, int probesPerRow, int probeBegin, int probeCount,
+                   cudaStream_t s)
+{
+    if (probeCount <= 0)
+        return;
+    if (irr)
+    {
+        long long n = (long long)probeCount * 36;
+        border_kernel<uint2, 8><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(irr, irrWidth, probesPerRow, probeBegin, probeCount);
+    }
+    if (depth)
+    {
+        long long n = (long long)probeCount * 68;
+        border_kernel<uint32_t, 16><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(depth, depthWidth, probesPerRow, probeBegin, probeCount);
+    }
+}
+
+int kernels_per_update(bool fusedBorder) { return fusedBorder ? 6 : 8; } // dirs, trace, weights, scales, 2 blends (+2 borders)
+
+} // namespace lux

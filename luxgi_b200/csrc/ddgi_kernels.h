@@ -1,0 +1,81 @@
+// ddgi_kernels.h — launch interface between the C++ host (ddgi_engine.cpp) and the sm_100a kernels (ddgi_kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/luxddgi.h"
+
+namespace lux {
+
+// Everything the trace kernel reads, passed as one __grid_constant__ parameter block.
+struct TraceParams
+{
+    // probe volume (DDGIUniform)
+    float start[3];
+    float step[3];
+    int   countX, countY;
+    int   raysPerProbe;
+    int   probeBegin, probeCount; // z-slab shard: probes [probeBegin, probeBegin + probeCount)
+    // global SDF
+    LuxGlobalSDFData sdf;
+    const uint16_t*  tex; // R16F [res][res][res*cascades]
+    const uint16_t*  mip; // R16F [res/4][res/4][res/4*cascades]
+    int              res, mipRes, cascades;
+    cudaTextureObject_t texObj, mipObj; // optional layered-2D texture objects (LUX_DDGI_FLAG_SDF_TEXTURE)
+    // surface cache
+    int                    hasAtlas;
+    float                  chunkSize;
+    uint32_t               atlasRes, objectsCount;
+    const uint32_t*        chunks;
+    const uint32_t*        cull;
+    const LuxObjectBuffer* objects;
+    const float*           objectInverse; // [objects][16], inverse(object.transform) precomputed at upload
+    const LuxTileBuffer*   tiles;
+    const uint2*           light; // RGBA16F
+    const float*           depth; // D32F
+    // sky
+    int          skyFace;
+    const uint2* sky; // [6][n][n] RGBA16F or null
+    // rays
+    const float4* dirs;     // [R] normalize(mat3(rot) * sphericalFibonacci(r, R))
+    uint2*        radiance; // [probeCount][R] RGBA16F
+    uint2*        dirDist;  // [probeCount][R] RGBA16F
+    uint16_t*     steps;    // optional [probeCount][R] march-step counts (debug / roofline counters)
+};
+
+struct BlendParams
+{
+    int   probeBegin, probeCount;
+    int   raysPerProbe, raysPadded; // raysPadded = round_up(R, 32): weight rows beyond R are zero
+    int   probesPerRow;             // X*Y
+    int   irrWidth, depthWidth;     // atlas widths in texels
+    float hysteresis, invGamma, maxDistance;
+    int   firstFrame;
+    int   fuseBorder;
+    const uint2* radiance; // [probeCount][R]
+    const uint2* dirDist;  // [probeCount][R]
+    const float* wIrr;     // [raysPadded][64]   gated weights, probe independent
+    const float* wDepth;   // [raysPadded][256]
+    const float* scaleIrr; // [64]  1/(2*sum w) or 1
+    const float* scaleDepth; // [256]
+    const uint2* prevIrr;  // RGBA16F atlas
+    uint2*       outIrr;
+    const uint32_t* prevDepth; // RG16F atlas
+    uint32_t*       outDepth;
+};
+
+// per-frame setup: ray directions and the probe-independent blend weights
+void launch_ray_dirs(const float* rot16Host, int raysPerProbe, float4* dirs, cudaStream_t s); // rotation travels as a kernel argument
+void launch_blend_weights(const uint2* dirDistRow0, int raysPerProbe, int raysPadded, float sharpness, float* wIrr, float* wDepth,
+                          float* scaleIrr, float* scaleDepth, cudaStream_t s);
+void launch_object_inverse(const LuxObjectBuffer* objects, int count, float* inv, cudaStream_t s);
+
+void launch_trace(const TraceParams& p, bool useTexture, cudaStream_t s);
+void launch_blend_irradiance(const BlendParams& p, cudaStream_t s);
+void launch_blend_depth(const BlendParams& p, cudaStream_t s);
+void launch_border(uint2* irr, int irrWidth, uint32_t* depth, int depthWidth, int probesPerRow, int probeBegin, int probeCount,
+                   cudaStream_t s);
+
+int kernels_per_update(bool fusedBorder);
+
+} // namespace lux

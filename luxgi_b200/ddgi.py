@@ -1,0 +1,309 @@
+"""Python host binding of libluxddgi.so (ctypes over the C ABI in include/luxddgi.h).
+
+The class mirrors the reference's pass interface (Code/Maple/src/Engine/DDGI/DDGIRenderer.cpp): a `DDGIPipeline` owns
+what `DDGIPipelineInternal` owns (ray buffers, 2x2 ping-pong atlases, frames, pingPong) and exposes the systems under
+their reference names — trace_rays, probe_update, border_update, end_frame — plus `update` (= the whole pass).
+
+There is NO CPU path here: if the library or a B200 is missing, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+
+_LIB = None
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libluxddgi.so")
+
+EXPORTS = [
+    "lux_ddgi_version", "lux_ddgi_last_error", "lux_ddgi_uniform_from_volume", "lux_ddgi_uniform_finalize", "lux_ddgi_create",
+    "lux_ddgi_destroy", "lux_ddgi_set_uniform", "lux_ddgi_set_global_sdf", "lux_ddgi_set_surface_atlas",
+    "lux_ddgi_update_surface_light_cache", "lux_ddgi_set_skybox", "lux_ddgi_trace_rays", "lux_ddgi_probe_update",
+    "lux_ddgi_border_update", "lux_ddgi_end_frame", "lux_ddgi_update", "lux_ddgi_synchronize", "lux_ddgi_get_buffer",
+    "lux_ddgi_download", "lux_ddgi_download_async", "lux_ddgi_set_ray_buffers", "lux_ddgi_restore", "lux_ddgi_get_state",
+    "lux_ddgi_get_stage_ms",
+]
+
+
+class LuxError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libluxddgi error {code}: {msg}")
+        self.code = code
+
+
+def load():
+    """dlopen libluxddgi.so.  Raises if it has not been built (python -m luxgi_b200.build)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(_LIB_PATH):
+        raise RuntimeError(f"{_LIB_PATH} is missing: build it with `python -m luxgi_b200.build` (there is no CPU fallback)")
+    L = C.CDLL(_LIB_PATH)
+    vp, i32, u32, sz = C.c_void_p, C.c_int32, C.c_uint32, C.c_size_t
+    L.lux_ddgi_version.restype = u32
+    L.lux_ddgi_last_error.restype = C.c_char_p
+    sig = {
+        "lux_ddgi_uniform_from_volume": [C.POINTER(abi.IrradianceVolume), C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(abi.DDGIUniform)],
+        "lux_ddgi_uniform_finalize": [C.POINTER(abi.DDGIUniform)],
+        "lux_ddgi_create": [C.POINTER(abi.DDGIUniform), C.POINTER(abi.CreateInfo), C.POINTER(vp)],
+        "lux_ddgi_destroy": [vp],
+        "lux_ddgi_set_uniform": [vp, C.POINTER(abi.DDGIUniform)],
+        "lux_ddgi_set_global_sdf": [vp, C.POINTER(abi.GlobalSDFData), vp, vp, i32],
+        "lux_ddgi_set_surface_atlas": [vp, C.POINTER(abi.GlobalSurfaceAtlasData), vp, vp, sz, vp, sz, vp, sz, vp, vp, i32],
+        "lux_ddgi_update_surface_light_cache": [vp, vp, i32],
+        "lux_ddgi_set_skybox": [vp, i32, vp, i32],
+        "lux_ddgi_trace_rays": [vp, C.POINTER(abi.TracePushConstants)],
+        "lux_ddgi_probe_update": [vp],
+        "lux_ddgi_border_update": [vp],
+        "lux_ddgi_end_frame": [vp],
+        "lux_ddgi_update": [vp, C.POINTER(C.c_float)],
+        "lux_ddgi_synchronize": [vp],
+        "lux_ddgi_get_buffer": [vp, i32, C.POINTER(vp), C.POINTER(sz)],
+        "lux_ddgi_download": [vp, i32, vp, sz],
+        "lux_ddgi_download_async": [vp, i32, vp, sz],
+        "lux_ddgi_set_ray_buffers": [vp, vp, vp, i32],
+        "lux_ddgi_restore": [vp, vp, vp, i32, i32],
+        "lux_ddgi_get_state": [vp, C.POINTER(abi.State)],
+        "lux_ddgi_get_stage_ms": [vp, C.POINTER(abi.StageTimes)],
+    }
+    for name, argtypes in sig.items():
+        fn = getattr(L, name)
+        fn.argtypes = argtypes
+        fn.restype = C.c_int
+    _LIB = L
+    return L
+
+
+def _check(rc):
+    if rc != abi.LUX_OK:
+        raise LuxError(rc, load().lux_ddgi_last_error().decode("utf-8", "replace"))
+
+
+def _host_ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _as_host(t, dtype=None):
+    """numpy array or CPU torch tensor -> contiguous numpy array (fp16 kept as is)."""
+    if hasattr(t, "detach"):
+        t = t.detach().contiguous().numpy()
+    a = np.ascontiguousarray(t)
+    if dtype is not None and a.dtype != dtype:
+        a = a.astype(dtype)
+    return a
+
+
+def _is_cuda_tensor(t):
+    return hasattr(t, "is_cuda") and t.is_cuda
+
+
+def _mem(t):
+    """-> (pointer, kind, keepalive)"""
+    if _is_cuda_tensor(t):
+        t = t.contiguous()
+        return C.c_void_p(t.data_ptr()), abi.MEM_DEVICE, t
+    a = _as_host(t)
+    return _host_ptr(a), abi.MEM_HOST, a
+
+
+def uniform_from_volume(volume: abi.IrradianceVolume, aabb_min, aabb_max) -> abi.DDGIUniform:
+    """ddgi::on_game_start grid derivation (DDGIRenderer.cpp:663-682)."""
+    u = abi.DDGIUniform()
+    mn = (C.c_float * 3)(*[float(v) for v in aabb_min])
+    mx = (C.c_float * 3)(*[float(v) for v in aabb_max])
+    _check(load().lux_ddgi_uniform_from_volume(C.byref(volume), mn, mx, C.byref(u)))
+    return u
+
+
+class DeviceView:
+    """Zero-copy view of an engine buffer for torch (`torch.as_tensor(view, device='cuda')`) via __cuda_array_interface__."""
+
+    def __init__(self, ptr, shape, typestr, owner):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 3, "strides": None}
+        self._owner = owner
+
+
+class DDGIPipeline:
+    """One probe volume (or one z-slab shard of it) on one GPU."""
+
+    def __init__(self, uniform: abi.DDGIUniform, device=0, rank=0, world=1, flags=0, stream=None):
+        self._lib = load()
+        self.uniform = uniform
+        self._keep = []
+        info = abi.CreateInfo(int(device), int(rank), int(world), int(flags), C.c_void_p(stream) if stream else None)
+        h = C.c_void_p()
+        _check(self._lib.lux_ddgi_create(C.byref(uniform), C.byref(info), C.byref(h)))
+        self._h = h
+        self.rays = uniform.raysPerProbe
+        st = self.state()
+        self.probe_begin, self.probe_count = st.probeBegin, st.probeCount
+
+    # ---- lifetime -------------------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.lux_ddgi_destroy(self._h)
+            self._h = None
+            self._keep = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ---- inputs (what trace_rays::system binds, DDGIRenderer.cpp:304-316) -------------------------------------
+    def set_global_sdf(self, sdf_data: abi.GlobalSDFData, sdf, mip):
+        ps, ks, k1 = _mem(sdf)
+        pm, km, k2 = _mem(mip)
+        if ks != km:
+            raise ValueError("sdf and mip must both be host or both be device arrays")
+        _check(self._lib.lux_ddgi_set_global_sdf(self._h, C.byref(sdf_data), ps, pm, ks))
+        if ks == abi.MEM_DEVICE:
+            self._keep += [k1, k2]
+
+    def set_surface_atlas(self, atlas_data, chunks, cull, objects, tiles, light, depth):
+        if atlas_data is None:
+            _check(self._lib.lux_ddgi_set_surface_atlas(self._h, None, None, None, 0, None, 0, None, 0, None, None, 0))
+            return
+        dev = _is_cuda_tensor(light)
+        if dev:
+            import torch
+
+            to_dev = lambda a: torch.as_tensor(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).to(light.device)
+            tens = [to_dev(chunks), to_dev(cull), to_dev(objects), to_dev(tiles), light.contiguous(), depth.contiguous()]
+            ptrs = [C.c_void_p(t.data_ptr()) for t in tens]
+            kind = abi.MEM_DEVICE
+            self._keep += tens
+        else:
+            arrs = [_as_host(chunks, np.uint32), _as_host(cull, np.uint32), _as_host(objects), _as_host(tiles), _as_host(light),
+                    _as_host(depth, np.float32)]
+            ptrs = [_host_ptr(a) for a in arrs]
+            kind = abi.MEM_HOST
+        _check(self._lib.lux_ddgi_set_surface_atlas(self._h, C.byref(atlas_data), ptrs[0], ptrs[1], len(cull), ptrs[2], len(objects),
+                                                     ptrs[3], len(tiles), ptrs[4], ptrs[5], kind))
+
+    def update_surface_light_cache(self, light):
+        p, k, keep = _mem(light)
+        _check(self._lib.lux_ddgi_update_surface_light_cache(self._h, p, k))
+        if k == abi.MEM_DEVICE:
+            self._keep.append(keep)
+
+    def update_surface_light_cache_ptr(self, host_ptr):
+        _check(self._lib.lux_ddgi_update_surface_light_cache(self._h, C.c_void_p(host_ptr), abi.MEM_HOST))
+
+    def set_skybox(self, face_size, faces):
+        if not face_size or faces is None:
+            _check(self._lib.lux_ddgi_set_skybox(self._h, 0, None, 0))
+            return
+        p, k, keep = _mem(faces)
+        _check(self._lib.lux_ddgi_set_skybox(self._h, int(face_size), p, k))
+        if k == abi.MEM_DEVICE:
+            self._keep.append(keep)
+
+    def set_scene(self, scene):
+        """Bind every input of a luxgi_b200.scenes.Scene."""
+        self.set_global_sdf(scene.sdf_data, scene.sdf, scene.mip)
+        if scene.atlas_data is not None:
+            self.set_surface_atlas(scene.atlas_data, scene.chunks, scene.cull, scene.objects, scene.tiles, scene.light, scene.depth)
+        self.set_skybox(scene.sky_face, scene.sky)
+
+    def set_uniform(self, uniform):
+        _check(self._lib.lux_ddgi_set_uniform(self._h, C.byref(uniform)))
+        self.uniform = uniform
+
+    def set_ray_buffers(self, radiance, direction_distance):
+        pr, kr, _ = _mem(radiance)
+        pd, kd, _ = _mem(direction_distance)
+        assert kr == kd
+        _check(self._lib.lux_ddgi_set_ray_buffers(self._h, pr, pd, kr))
+
+    # ---- the systems, in RenderGraph order (RenderGraph.cpp:98-114) ----------------------------------------------
+    def trace_rays(self, orientation, num_frames=0):
+        pc = abi.TracePushConstants()
+        pc.randomOrientation[:] = [float(v) for v in np.asarray(orientation, dtype=np.float32).reshape(16)]
+        pc.numFrames = num_frames
+        pc.infiniteBounces = 1 if num_frames else 0
+        pc.intensity = 1.0
+        _check(self._lib.lux_ddgi_trace_rays(self._h, C.byref(pc)))
+
+    def probe_update(self):
+        _check(self._lib.lux_ddgi_probe_update(self._h))
+
+    def border_update(self):
+        _check(self._lib.lux_ddgi_border_update(self._h))
+
+    def end_frame(self):
+        _check(self._lib.lux_ddgi_end_frame(self._h))
+
+    def update(self, orientation):
+        rot = np.ascontiguousarray(orientation, dtype=np.float32).reshape(16)
+        _check(self._lib.lux_ddgi_update(self._h, rot.ctypes.data_as(C.POINTER(C.c_float))))
+
+    def synchronize(self):
+        _check(self._lib.lux_ddgi_synchronize(self._h))
+
+    # ---- outputs -------------------------------------------------------------------------------------------------
+    def state(self) -> abi.State:
+        st = abi.State()
+        _check(self._lib.lux_ddgi_get_state(self._h, C.byref(st)))
+        return st
+
+    def stage_ms(self) -> abi.StageTimes:
+        t = abi.StageTimes()
+        _check(self._lib.lux_ddgi_get_stage_ms(self._h, C.byref(t)))
+        return t
+
+    def _shape(self, buf):
+        u = self.uniform
+        if buf in (abi.BUF_RADIANCE, abi.BUF_DIRECTION_DISTANCE):
+            return (self.probe_count, self.rays, 4)
+        if buf in (abi.BUF_IRRADIANCE, abi.BUF_IRRADIANCE_PREV):
+            return (u.irradianceTextureHeight, u.irradianceTextureWidth, 4)
+        return (u.depthTextureHeight, u.depthTextureWidth, 2)
+
+    def buffer_ptr(self, buf):
+        p, n = C.c_void_p(), C.c_size_t()
+        _check(self._lib.lux_ddgi_get_buffer(self._h, buf, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def device_view(self, buf) -> DeviceView:
+        p, _ = self.buffer_ptr(buf)
+        return DeviceView(p, self._shape(buf), "<f2", self)
+
+    def download(self, buf) -> np.ndarray:
+        """uint16 (fp16 bit patterns) array of the buffer's natural shape."""
+        out = np.empty(self._shape(buf), dtype=np.uint16)
+        _check(self._lib.lux_ddgi_download(self._h, buf, _host_ptr(out), out.nbytes))
+        return out
+
+    def download_async_ptr(self, buf, host_ptr, nbytes):
+        _check(self._lib.lux_ddgi_download_async(self._h, buf, C.c_void_p(host_ptr), nbytes))
+
+    def restore(self, irradiance, depth, frames, ping_pong):
+        a, b = _as_host(irradiance), _as_host(depth)
+        _check(self._lib.lux_ddgi_restore(self._h, _host_ptr(a), _host_ptr(b), int(frames), int(ping_pong)))
+
+    @property
+    def radiance(self):
+        return self.download(abi.BUF_RADIANCE)
+
+    @property
+    def direction_distance(self):
+        return self.download(abi.BUF_DIRECTION_DISTANCE)
+
+    @property
+    def irradiance(self):
+        return self.download(abi.BUF_IRRADIANCE)
+
+    @property
+    def depth(self):
+        return self.download(abi.BUF_DEPTH)

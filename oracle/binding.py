@@ -1,0 +1,192 @@
+"""ctypes binding of oracle/libddgi_oracle.so — TEST INFRASTRUCTURE.
+
+Import this only from tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs.
+The product package (luxgi_b200) never imports it.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from luxgi_b200 import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libddgi_oracle.so")
+_lib = None
+
+
+class SceneDesc(C.Structure):
+    _fields_ = [
+        ("ddgi", C.POINTER(abi.DDGIUniform)),
+        ("sdfData", C.POINTER(abi.GlobalSDFData)),
+        ("sdf", C.c_void_p),
+        ("mip", C.c_void_p),
+        ("atlasData", C.POINTER(abi.GlobalSurfaceAtlasData)),
+        ("chunks", C.c_void_p),
+        ("cull", C.c_void_p),
+        ("objects", C.c_void_p),
+        ("tiles", C.c_void_p),
+        ("light", C.c_void_p),
+        ("depth", C.c_void_p),
+        ("skyFace", C.c_int32),
+        ("sky", C.c_void_p),
+    ]
+
+
+class Counters(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("mipTaps", "texTaps", "hits", "tileSamples", "steps", "objectsVisited")]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+def build(force=False):
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(os.path.join(_HERE, "ddgi_oracle.cpp")):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "all"])
+    return _LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            build()
+        L = C.CDLL(_LIB_PATH)
+        L.oracle_threads.restype = C.c_int
+        L.oracle_f2h.restype = C.c_uint16
+        L.oracle_f2h.argtypes = [C.c_float]
+        L.oracle_h2f.restype = C.c_float
+        L.oracle_h2f.argtypes = [C.c_uint16]
+        L.oracle_sample3d.restype = C.c_float
+        L.oracle_sample3d.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float]
+        L.oracle_trace.restype = C.c_int
+        L.oracle_trace.argtypes = [C.POINTER(SceneDesc), C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.POINTER(Counters)]
+        L.oracle_blend.restype = C.c_int
+        L.oracle_blend.argtypes = [C.POINTER(abi.DDGIUniform), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.oracle_border.restype = C.c_int
+        L.oracle_border.argtypes = [C.POINTER(abi.DDGIUniform), C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.oracle_border_offsets.restype = C.c_int
+        L.oracle_border_offsets.argtypes = [C.c_int, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _np(t, dtype=None):
+    """torch tensor / numpy array -> contiguous numpy (fp16 viewed as uint16)."""
+    if t is None:
+        return None
+    if hasattr(t, "detach"):
+        t = t.detach().cpu().contiguous().numpy()
+    a = np.ascontiguousarray(t)
+    if a.dtype == np.float16:
+        a = a.view(np.uint16)
+    if dtype is not None and a.dtype != dtype:
+        a = a.astype(dtype)
+    return a
+
+
+class OracleScene:
+    """Host copies of a luxgi_b200.scenes.Scene in the layout the oracle reads."""
+
+    def __init__(self, scene):
+        self.scene = scene
+        self.uniform = scene.uniform
+        self.sdf = _np(scene.sdf)
+        self.mip = _np(scene.mip)
+        self.chunks = _np(scene.chunks)
+        self.cull = _np(scene.cull)
+        self.objects = _np(scene.objects)
+        self.tiles = _np(scene.tiles)
+        self.light = _np(scene.light)
+        self.depth = _np(scene.depth)
+        self.sky = _np(scene.sky)
+        d = SceneDesc()
+        d.ddgi = C.pointer(scene.uniform)
+        d.sdfData = C.pointer(scene.sdf_data)
+        d.sdf, d.mip = _ptr(self.sdf), _ptr(self.mip)
+        if scene.atlas_data is not None:
+            d.atlasData = C.pointer(scene.atlas_data)
+            d.chunks, d.cull, d.objects, d.tiles = _ptr(self.chunks), _ptr(self.cull), _ptr(self.objects), _ptr(self.tiles)
+            d.light, d.depth = _ptr(self.light), _ptr(self.depth)
+        d.skyFace = scene.sky_face
+        d.sky = _ptr(self.sky)
+        self.desc = d
+
+    def trace(self, rot16, probe_begin=0, count=None, probe_ids=None, want_steps=False):
+        """Returns (radiance u16 [n][R][4], dirDist u16 [n][R][4], steps u16 [n][R] | None, counters dict)."""
+        R = self.uniform.raysPerProbe
+        ids = None
+        if probe_ids is not None:
+            ids = np.ascontiguousarray(probe_ids, dtype=np.int32)
+            count = len(ids)
+        elif count is None:
+            count = abi.probe_count(self.uniform) - probe_begin
+        rad = np.zeros((count, R, 4), dtype=np.uint16)
+        dd = np.zeros((count, R, 4), dtype=np.uint16)
+        steps = np.zeros((count, R), dtype=np.uint16) if want_steps else None
+        rot = np.ascontiguousarray(rot16, dtype=np.float32)
+        cn = Counters()
+        rc = lib().oracle_trace(C.byref(self.desc), _ptr(rot), probe_begin, count, _ptr(ids), _ptr(rad), _ptr(dd), _ptr(steps), C.byref(cn))
+        assert rc == 0, rc
+        return rad, dd, steps, cn.as_dict()
+
+
+def new_atlases(u):
+    irr = np.zeros((u.irradianceTextureHeight, u.irradianceTextureWidth, 4), dtype=np.uint16)
+    dep = np.zeros((u.depthTextureHeight, u.depthTextureWidth, 2), dtype=np.uint16)
+    return irr, dep
+
+
+def blend(u, rad, dd, prev_irr, prev_dep, out_irr, out_dep, first_frame, probe_begin=0, count=None, ray_row_offset=0, naive=False):
+    if count is None:
+        count = rad.shape[0]
+    rc = lib().oracle_blend(C.byref(u), _ptr(rad), _ptr(dd), ray_row_offset, _ptr(prev_irr), _ptr(prev_dep), _ptr(out_irr),
+                            _ptr(out_dep), int(bool(first_frame)), probe_begin, count, int(bool(naive)))
+    assert rc == 0, rc
+
+
+def border(u, irr, dep, probe_begin=0, count=None):
+    if count is None:
+        count = abi.probe_count(u)
+    rc = lib().oracle_border(C.byref(u), _ptr(irr), _ptr(dep), probe_begin, count)
+    assert rc == 0, rc
+
+
+class OraclePipeline:
+    """The reference's frame protocol (DDGIRenderer.cpp:333-343,390-395) driven through the oracle."""
+
+    def __init__(self, scene, probe_begin=0, count=None):
+        self.os = scene if isinstance(scene, OracleScene) else OracleScene(scene)
+        self.u = self.os.uniform
+        self.irr = [new_atlases(self.u)[0] for _ in range(2)]
+        self.dep = [new_atlases(self.u)[1] for _ in range(2)]
+        self.frames = 0
+        self.ping = 0
+        self.probe_begin = probe_begin
+        self.count = abi.probe_count(self.u) - probe_begin if count is None else count
+        self.rad = self.dd = None
+        self.counters = None
+
+    def update(self, rot16, naive=False):
+        self.rad, self.dd, _, self.counters = self.os.trace(rot16, self.probe_begin, self.count)
+        w = 1 - self.ping
+        blend(self.u, self.rad, self.dd, self.irr[self.ping], self.dep[self.ping], self.irr[w], self.dep[w], self.frames == 0,
+              self.probe_begin, self.count, ray_row_offset=self.probe_begin, naive=naive)
+        border(self.u, self.irr[w], self.dep[w], self.probe_begin, self.count)
+        self.ping = 1 - self.ping
+        self.frames += 1
+
+    @property
+    def irradiance(self):
+        return self.irr[self.ping]
+
+    @property
+    def depth(self):
+        return self.dep[self.ping]

@@ -1,0 +1,958 @@
+// ddgi_oracle.cpp — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+//
+// CPU restatement of the reference's SDF-traced DDGI probe update (flwmxd/LuxGI, Maple engine) used as the
+// parity oracle and as the timed CPU baseline.  Only tests/, __graft_entry__.smoke() and bench.py's
+// cpu_baseline / --impl reference legs may load this library; libluxddgi.so never does.
+//
+// PARITY PINNING: the reference ships no tests, golden vectors or KATs for this path, and
+// its shaders cannot be executed by any toolchain in this image.  What pins this restatement:
+//   * the reference's own border offset tables (BorderUpdate.glsl:25-133), extracted to
+//     tests/golden/border_offsets.json and compared entry by entry;
+//   * golden vectors produced by executing the reference's SHIPPED SPIR-V binaries
+//     (Assets/shaders/spv/DDGI/*.comp.spv) with the interpreter in oracle/spirv/ (see tests/golden/README.md);
+//   * closed-form known-answer tests (tests/test_oracle_kat.py).
+// Anything not covered by those is "parity unpinned" and says so in DESIGN.md.
+//
+// Every function cites the reference file:line it follows (paths relative to Code/Maple/src/).
+//
+// NUMERICS CONTRACT (shared with the CUDA engine by specification, not by code — see DESIGN.md §4):
+//   * every +,-,*,/,sqrt is IEEE-754 binary32 round-to-nearest-even, evaluated in source order; no contraction
+//     (built with -ffp-contract=off) except where fmaf() is written explicitly (blend accumulation, mix);
+//   * GLSL min/max/clamp are select-based: min(x,y) = y<x ? y : x, max(x,y) = x<y ? y : x;
+//   * sin, cos, pow are evaluated in binary64 and rounded once to binary32;
+//   * normalize(v) = v * (1 / sqrt((v.x*v.x + v.y*v.y) + v.z*v.z));
+//   * textures: fp16 texels decoded exactly, fp32 filter weights, nested lerp x→y→z, lerp(a,b,t) = a + t*(b-a);
+//   * imageStore to *16F formats rounds to nearest even (overflow → inf).
+//
+// Build: see oracle/Makefile (g++ -O2 -ffp-contract=off -fopenmp -shared).
+
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#include "../include/luxddgi.h" // POD layouts of the boundary only (no product code)
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------------------
+// binary16 <-> binary32 (Vulkan image load/store conversion for R16F/RG16F/RGBA16F, VulkanHelper.cpp:1113-1130)
+// ---------------------------------------------------------------------------------------------------------
+inline float h2f(uint16_t h)
+{
+    uint32_t sign = (uint32_t)(h & 0x8000u) << 16;
+    uint32_t exp  = (h >> 10) & 0x1fu;
+    uint32_t man  = h & 0x3ffu;
+    uint32_t bits;
+    if (exp == 0)
+    {
+        if (man == 0)
+            bits = sign;
+        else
+        { // subnormal: value = man * 2^-24
+            float    f = (float)man * 5.9604644775390625e-08f;
+            uint32_t b;
+            std::memcpy(&b, &f, 4);
+            bits = b | sign;
+        }
+    }
+    else if (exp == 31)
+        bits = sign | 0x7f800000u | (man << 13);
+    else
+        bits = sign | ((exp + 112u) << 23) | (man << 13);
+    float out;
+    std::memcpy(&out, &bits, 4);
+    return out;
+}
+
+inline uint16_t f2h(float f)
+{
+    uint32_t x;
+    std::memcpy(&x, &f, 4);
+    uint16_t sign = (uint16_t)((x >> 16) & 0x8000u);
+    x &= 0x7fffffffu;
+    if (x > 0x7f800000u)
+        return 0x7fffu; // NaN (canonical, as cvt.rn.f16.f32)
+    if (x >= 0x477ff000u)
+        return sign | 0x7c00u; // >= 65520 rounds to inf
+    if (x < 0x38800000u)
+    { // below 2^-14: half subnormal, integer mantissa = RNE(|f| * 2^24)
+        float a;
+        std::memcpy(&a, &x, 4);
+        uint32_t m = (uint32_t)std::lrintf(a * 16777216.0f); // exact scaling, RNE under the default mode
+        return sign | (uint16_t)m;                           // m == 1024 is the smallest normal, same bits
+    }
+    uint32_t man = x & 0x7fffffu;
+    uint32_t e   = (x >> 23) - 112u;
+    uint32_t h   = (e << 10) | (man >> 13);
+    uint32_t rem = man & 0x1fffu;
+    if (rem > 0x1000u || (rem == 0x1000u && (h & 1u)))
+        h++;
+    return sign | (uint16_t)h;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// GLSL built-ins under the numerics contract
+// ---------------------------------------------------------------------------------------------------------
+struct vec2 { float x, y; };
+struct vec3 { float x, y, z; };
+struct vec4 { float x, y, z, w; };
+
+inline float gmin(float x, float y) { return (y < x) ? y : x; }
+inline float gmax(float x, float y) { return (x < y) ? y : x; }
+inline float gclamp(float x, float lo, float hi) { return gmin(gmax(x, lo), hi); }
+inline int   iclamp(int x, int lo, int hi) { return x < lo ? lo : (x > hi ? hi : x); }
+inline float gfract(float x) { return x - std::floor(x); }
+
+inline vec3 add(vec3 a, vec3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+inline vec3 sub(vec3 a, vec3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline vec3 mul(vec3 a, float s) { return {a.x * s, a.y * s, a.z * s}; }
+inline vec3 mul(vec3 a, vec3 b) { return {a.x * b.x, a.y * b.y, a.z * b.z}; }
+inline float dot3(vec3 a, vec3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+inline float dot4(vec4 a, vec4 b) { return ((a.x * b.x + a.y * b.y) + a.z * b.z) + a.w * b.w; }
+inline vec3 normalize3(vec3 v)
+{
+    float inv = 1.0f / std::sqrt(dot3(v, v));
+    return {v.x * inv, v.y * inv, v.z * inv};
+}
+inline float length3(vec3 v) { return std::sqrt(dot3(v, v)); }
+inline float sin_rn(float x) { return (float)std::sin((double)x); }
+inline float cos_rn(float x) { return (float)std::cos((double)x); }
+inline float pow_rn(float x, float y) { return (float)std::pow((double)x, (double)y); }
+
+// column-major mat4 m[c*4+r] times (v,1) / times (v, w)
+inline vec3 mat4_mul_point(const float* m, vec3 v, float w)
+{
+    vec3 r;
+    r.x = ((m[0] * v.x + m[4] * v.y) + m[8] * v.z) + m[12] * w;
+    r.y = ((m[1] * v.x + m[5] * v.y) + m[9] * v.z) + m[13] * w;
+    r.z = ((m[2] * v.x + m[6] * v.y) + m[10] * v.z) + m[14] * w;
+    return r;
+}
+inline vec3 mat3_mul(const float* m, vec3 v) // upper-left 3x3 of a column-major mat4
+{
+    vec3 r;
+    r.x = (m[0] * v.x + m[4] * v.y) + m[8] * v.z;
+    r.y = (m[1] * v.x + m[5] * v.y) + m[9] * v.z;
+    r.z = (m[2] * v.x + m[6] * v.y) + m[10] * v.z;
+    return r;
+}
+
+// inverse(mat4) — GLSL leaves the algorithm to the implementation; the contract fixes it to the cofactor
+// expansion over 2x2 sub-determinants below (used at AtlasCommon.glsl:133).
+void inverse4(const float* m, float* o)
+{
+#define A(r, c) m[(c)*4 + (r)]
+    float s0 = A(0, 0) * A(1, 1) - A(1, 0) * A(0, 1);
+    float s1 = A(0, 0) * A(1, 2) - A(1, 0) * A(0, 2);
+    float s2 = A(0, 0) * A(1, 3) - A(1, 0) * A(0, 3);
+    float s3 = A(0, 1) * A(1, 2) - A(1, 1) * A(0, 2);
+    float s4 = A(0, 1) * A(1, 3) - A(1, 1) * A(0, 3);
+    float s5 = A(0, 2) * A(1, 3) - A(1, 2) * A(0, 3);
+    float c5 = A(2, 2) * A(3, 3) - A(3, 2) * A(2, 3);
+    float c4 = A(2, 1) * A(3, 3) - A(3, 1) * A(2, 3);
+    float c3 = A(2, 1) * A(3, 2) - A(3, 1) * A(2, 2);
+    float c2 = A(2, 0) * A(3, 3) - A(3, 0) * A(2, 3);
+    float c1 = A(2, 0) * A(3, 2) - A(3, 0) * A(2, 2);
+    float c0 = A(2, 0) * A(3, 1) - A(3, 0) * A(2, 1);
+    float det = ((((s0 * c5 - s1 * c4) + s2 * c3) + s3 * c2) - s4 * c1) + s5 * c0;
+    float inv = 1.0f / det;
+#define B(r, c) o[(c)*4 + (r)]
+    B(0, 0) = ((A(1, 1) * c5 - A(1, 2) * c4) + A(1, 3) * c3) * inv;
+    B(0, 1) = ((-A(0, 1) * c5 + A(0, 2) * c4) - A(0, 3) * c3) * inv;
+    B(0, 2) = ((A(3, 1) * s5 - A(3, 2) * s4) + A(3, 3) * s3) * inv;
+    B(0, 3) = ((-A(2, 1) * s5 + A(2, 2) * s4) - A(2, 3) * s3) * inv;
+    B(1, 0) = ((-A(1, 0) * c5 + A(1, 2) * c2) - A(1, 3) * c1) * inv;
+    B(1, 1) = ((A(0, 0) * c5 - A(0, 2) * c2) + A(0, 3) * c1) * inv;
+    B(1, 2) = ((-A(3, 0) * s5 + A(3, 2) * s2) - A(3, 3) * s1) * inv;
+    B(1, 3) = ((A(2, 0) * s5 - A(2, 2) * s2) + A(2, 3) * s1) * inv;
+    B(2, 0) = ((A(1, 0) * c4 - A(1, 1) * c2) + A(1, 3) * c0) * inv;
+    B(2, 1) = ((-A(0, 0) * c4 + A(0, 1) * c2) - A(0, 3) * c0) * inv;
+    B(2, 2) = ((A(3, 0) * s4 - A(3, 1) * s2) + A(3, 3) * s0) * inv;
+    B(2, 3) = ((-A(2, 0) * s4 + A(2, 1) * s2) - A(2, 3) * s0) * inv;
+    B(3, 0) = ((-A(1, 0) * c3 + A(1, 1) * c1) - A(1, 2) * c0) * inv;
+    B(3, 1) = ((A(0, 0) * c3 - A(0, 1) * c1) + A(0, 2) * c0) * inv;
+    B(3, 2) = ((-A(3, 0) * s3 + A(3, 1) * s1) - A(3, 2) * s0) * inv;
+    B(3, 3) = ((A(2, 0) * s3 - A(2, 1) * s1) + A(2, 2) * s0) * inv;
+#undef A
+#undef B
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Software texture units
+// ---------------------------------------------------------------------------------------------------------
+struct Tex3D // R16F, [z][y][x], linear filter, clamp-to-edge (GlobalDistanceField.cpp:615,621)
+{
+    const uint16_t* data;
+    int             w, h, d;
+    inline float texel(int x, int y, int z) const { return h2f(data[((size_t)z * h + y) * w + x]); }
+};
+
+inline float lerp1(float a, float b, float t) { return a + t * (b - a); }
+
+// texture(sampler3D, uvw).r at LOD 0
+float sample3D(const Tex3D& t, float u, float v, float w, uint64_t* taps)
+{
+    float x = u * (float)t.w - 0.5f, y = v * (float)t.h - 0.5f, z = w * (float)t.d - 0.5f;
+    float fx = std::floor(x), fy = std::floor(y), fz = std::floor(z);
+    float ax = x - fx, ay = y - fy, az = z - fz;
+    int   ix = (int)fx, iy = (int)fy, iz = (int)fz;
+    int   x0 = iclamp(ix, 0, t.w - 1), x1 = iclamp(ix + 1, 0, t.w - 1);
+    int   y0 = iclamp(iy, 0, t.h - 1), y1 = iclamp(iy + 1, 0, t.h - 1);
+    int   z0 = iclamp(iz, 0, t.d - 1), z1 = iclamp(iz + 1, 0, t.d - 1);
+    float c00 = lerp1(t.texel(x0, y0, z0), t.texel(x1, y0, z0), ax);
+    float c10 = lerp1(t.texel(x0, y1, z0), t.texel(x1, y1, z0), ax);
+    float c01 = lerp1(t.texel(x0, y0, z1), t.texel(x1, y0, z1), ax);
+    float c11 = lerp1(t.texel(x0, y1, z1), t.texel(x1, y1, z1), ax);
+    float c0  = lerp1(c00, c10, ay);
+    float c1  = lerp1(c01, c11, ay);
+    if (taps)
+        ++*taps;
+    return lerp1(c0, c1, az);
+}
+
+// textureGather footprint: i0 = floor(u*W - 0.5), order (i0,j1),(i1,j1),(i1,j0),(i0,j0) (Vulkan spec §16.9)
+struct GatherCoords { int i0, i1, j0, j1; };
+inline GatherCoords gatherCoords(float u, float v, int W, int H, bool repeat)
+{
+    int i0 = (int)std::floor(u * (float)W - 0.5f);
+    int j0 = (int)std::floor(v * (float)H - 0.5f);
+    int i1 = i0 + 1, j1 = j0 + 1;
+    GatherCoords g;
+    if (repeat)
+    {
+        g.i0 = ((i0 % W) + W) % W; g.i1 = ((i1 % W) + W) % W;
+        g.j0 = ((j0 % H) + H) % H; g.j1 = ((j1 % H) + H) % H;
+    }
+    else
+    {
+        g.i0 = iclamp(i0, 0, W - 1); g.i1 = iclamp(i1, 0, W - 1);
+        g.j0 = iclamp(j0, 0, H - 1); g.j1 = iclamp(j1, 0, H - 1);
+    }
+    return g;
+}
+
+struct Scene
+{
+    LuxDDGIUniform             ddgi;
+    LuxGlobalSDFData           sdfData;
+    Tex3D                      tex, mip;
+    bool                       hasAtlas;
+    LuxGlobalSurfaceAtlasData  atlasData;
+    const uint32_t*            chunks;
+    const uint32_t*            cull;
+    const LuxObjectBuffer*     objects;
+    const LuxTileBuffer*       tiles;
+    const uint16_t*            light; // RGBA16F res^2, linear/repeat (GlobalSurfaceAtlas.cpp:411, Definitions.h:152-159)
+    const float*               depth; // D32F res^2, linear/clamp (VulkanTexture.cpp:643-668)
+    int                        skyFace;
+    const uint16_t*            sky; // 6 faces RGBA16F, or null = black 1x1 fallback (DDGIRenderer.cpp:308)
+};
+
+struct Counters
+{
+    uint64_t mipTaps = 0, texTaps = 0, hits = 0, tileSamples = 0, steps = 0, objectsVisited = 0;
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// DDGICommon.glsl
+// ---------------------------------------------------------------------------------------------------------
+// DDGICommon.glsl:42-52.  Constants as folded by glslang in the shipped GISDFRays.comp.spv.
+vec3 sphericalFibonacci(float i, float raysPerProbe)
+{
+    const float PHI_M1 = 0.61803400516510009765625f;
+    const float TWO_PI = 6.283185482025146484375f;
+    float       ab       = i * PHI_M1;
+    float       phi      = TWO_PI * (ab - std::floor(ab));
+    float       cosTheta = 1.0f - (2.0f * i + 1.0f) * (1.0f / raysPerProbe);
+    float       sinTheta = std::sqrt(gclamp(1.0f - cosTheta * cosTheta, 0.0f, 1.0f));
+    return {cos_rn(phi) * sinTheta, sin_rn(phi) * sinTheta, cosTheta};
+}
+
+inline float signNotZero(float k) { return (k >= 0.0f) ? 1.0f : -1.0f; } // DDGICommon.glsl:55-58
+
+// DDGICommon.glsl:74-82
+vec3 octDecode(vec2 o)
+{
+    vec3 v = {o.x, o.y, (1.0f - std::fabs(o.x)) - std::fabs(o.y)};
+    if (v.z < 0.0f)
+    {
+        float nx = (1.0f - std::fabs(v.y)) * signNotZero(v.x);
+        float ny = (1.0f - std::fabs(v.x)) * signNotZero(v.y);
+        v.x = nx;
+        v.y = ny;
+    }
+    return normalize3(v);
+}
+
+// DDGICommon.glsl:85-92 with fragCoord = probe base + 2 + (i,j): (fragCoord-2) % (side+2) = (i,j)
+vec2 normalizedOctCoordLocal(int i, int j, int side)
+{
+    float s = 2.0f / (float)side;
+    return {((float)i + 0.5f) * s - 1.0f, ((float)j + 0.5f) * s - 1.0f};
+}
+
+// DDGICommon.glsl:101-114
+vec3 probeLocation(const LuxDDGIUniform& d, int index)
+{
+    int X = d.probeCounts[0], Y = d.probeCounts[1];
+    int cx = index % X;
+    int cy = (index % (X * Y)) / X;
+    int cz = index / (X * Y);
+    return {d.step[0] * (float)cx + d.startPosition[0], d.step[1] * (float)cy + d.startPosition[1],
+            d.step[2] * (float)cz + d.startPosition[2]};
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// SDFCommon.glsl
+// ---------------------------------------------------------------------------------------------------------
+struct Hit // GlobalSDFHit.glsl:4-11
+{
+    vec3     hitNormal;
+    float    hitTime;
+    uint32_t hitCascade;
+    uint32_t stepsCount;
+    float    hitSDF;
+};
+
+// SDFCommon.glsl:84-95
+vec2 lineHitAABB(vec3 s, vec3 e, vec3 bmin, vec3 bmax)
+{
+    vec3 inv   = {1.0f / (e.x - s.x), 1.0f / (e.y - s.y), 1.0f / (e.z - s.z)};
+    vec3 enter = mul(sub(bmin, s), inv);
+    vec3 exit_ = mul(sub(bmax, s), inv);
+    vec3 mn    = {gmin(enter.x, exit_.x), gmin(enter.y, exit_.y), gmin(enter.z, exit_.z)};
+    vec3 mx    = {gmax(enter.x, exit_.x), gmax(enter.y, exit_.y), gmax(enter.z, exit_.z)};
+    vec2 r;
+    r.x = gmax(mn.x, gmax(mn.y, mn.z));
+    r.y = gmin(mx.x, gmin(mx.y, mx.z));
+    r.x = gclamp(r.x, 0.0f, 1.0f);
+    r.y = gclamp(r.y, 0.0f, 1.0f);
+    return r;
+}
+
+// SDFCommon.glsl:98-194, with trace = {origin, dir, minDistance 0, maxDistance, stepScale, needsHitNormal true}
+Hit tracyGlobalSDF(const Scene& sc, vec3 origin, vec3 dir, float maxDistance, float stepScale,
+                   float cascadeTraceStartBias, Counters& cn)
+{
+    const LuxGlobalSDFData& data = sc.sdfData;
+    Hit                     hit;
+    hit.stepsCount = 0;
+    hit.hitTime    = -1.0f;
+    hit.hitNormal  = {0, 0, 0};
+    hit.hitCascade = 0;
+    hit.hitSDF     = 0.0f;
+
+    float traceMaxDistance    = gmin(maxDistance, data.cascadePosDistance[data.cascadesCount - 1][3] * 2.0f);
+    float chunkSizeDistance   = (float)LUX_GLOBAL_SDF_RASTERIZE_CHUNK_SIZE / data.resolution;
+    float chunkMarginDistance = (float)LUX_GLOBAL_SDF_RASTERIZE_CHUNK_MARGIN / data.resolution;
+    float nextIntersectionStart = 0.0f;
+    vec3  traceEndPosition      = add(origin, mul(dir, traceMaxDistance));
+    float cascadesCountF        = (float)data.cascadesCount;
+
+    for (uint32_t cascade = 0; cascade < data.cascadesCount && hit.hitTime < 0.0f; cascade++)
+    {
+        const float* cpd       = data.cascadePosDistance[cascade];
+        float        voxelSize = data.cascadeVoxelSize[cascade];
+        float        voxelHalf = voxelSize * 0.5f;
+        vec3         worldPosition = add(origin, mul(dir, voxelSize * cascadeTraceStartBias));
+
+        vec3 c    = {cpd[0], cpd[1], cpd[2]};
+        vec3 ext  = {cpd[3], cpd[3], cpd[3]};
+        vec2 isec = lineHitAABB(worldPosition, traceEndPosition, sub(c, ext), add(c, ext));
+        isec.x *= traceMaxDistance;
+        isec.y *= traceMaxDistance;
+        isec.x = gmax(isec.x, nextIntersectionStart);
+
+        float stepTime = isec.x;
+        if (isec.x >= isec.y)
+            stepTime = isec.y;
+        else
+            nextIntersectionStart = isec.y;
+
+        uint32_t step = 0;
+        for (; step < LUX_GLOBAL_SDF_MAX_STEPS && stepTime < isec.y; step++)
+        {
+            vec3 stepPosition = add(worldPosition, mul(dir, stepTime));
+
+            // getGlobalSDFCascadeUV, SDFCommon.glsl:64-71
+            vec3  posInCascade       = sub(stepPosition, c);
+            float cascadeMaxDistance = cpd[3] * 2.0f;
+            vec3  cascadeUV = {gclamp(posInCascade.x / cascadeMaxDistance + 0.5f, 0.0f, 1.0f),
+                               gclamp(posInCascade.y / cascadeMaxDistance + 0.5f, 0.0f, 1.0f),
+                               gclamp(posInCascade.z / cascadeMaxDistance + 0.5f, 0.0f, 1.0f)};
+            vec3  textureUV = {((float)cascade + cascadeUV.x) / cascadesCountF, cascadeUV.y, cascadeUV.z};
+
+            float stepDistance = sample3D(sc.mip, textureUV.x, textureUV.y, textureUV.z, &cn.mipTaps);
+            if (stepDistance < chunkSizeDistance)
+            {
+                float stepDistanceTex = sample3D(sc.tex, textureUV.x, textureUV.y, textureUV.z, &cn.texTaps);
+                if (stepDistanceTex < chunkMarginDistance * 2.0f)
+                    stepDistance = stepDistanceTex;
+            }
+            else
+                stepDistance = chunkSizeDistance;
+
+            stepDistance *= cascadeMaxDistance;
+
+            float minSurfaceThickness = voxelHalf * gclamp(stepTime / voxelSize, 0.0f, 1.0f);
+            if (stepDistance < minSurfaceThickness)
+            {
+                hit.hitTime    = gmax((stepTime + stepDistance) - minSurfaceThickness, 0.0f);
+                hit.hitCascade = cascade;
+                hit.hitSDF     = stepDistance;
+                float texelOffset = 1.0f / data.resolution;
+                float xp = sample3D(sc.tex, textureUV.x + texelOffset, textureUV.y, textureUV.z, &cn.texTaps);
+                float xn = sample3D(sc.tex, textureUV.x - texelOffset, textureUV.y, textureUV.z, &cn.texTaps);
+                float yp = sample3D(sc.tex, textureUV.x, textureUV.y + texelOffset, textureUV.z, &cn.texTaps);
+                float yn = sample3D(sc.tex, textureUV.x, textureUV.y - texelOffset, textureUV.z, &cn.texTaps);
+                float zp = sample3D(sc.tex, textureUV.x, textureUV.y, textureUV.z + texelOffset, &cn.texTaps);
+                float zn = sample3D(sc.tex, textureUV.x, textureUV.y, textureUV.z - texelOffset, &cn.texTaps);
+                hit.hitNormal = normalize3({xp - xn, yp - yn, zp - zn});
+                break;
+            }
+            stepTime += gmax(stepDistance * stepScale, voxelSize);
+        }
+        hit.stepsCount += step;
+    }
+    cn.steps += hit.stepsCount;
+    return hit;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// AtlasCommon.glsl
+// ---------------------------------------------------------------------------------------------------------
+// AtlasCommon.glsl:58-97 (tile sampling) + :100-112 (normal weight)
+vec4 sampleGlobalSurfaceAtlasTile(const Scene& sc, const LuxTileBuffer& tile, vec3 localPosition, vec3 normal,
+                                  float surfaceThreshold, Counters& cn)
+{
+    // :104-110
+    vec3 nt = mat4_mul_point(tile.transform, normal, 1.0f);
+    nt      = normalize3(nt);
+    float normalWeight = gclamp(nt.z, 0.0f, 1.0f);
+    normalWeight = (normalWeight - LUX_SURFACE_ATLAS_TILE_NORMAL_THRESHOLD) / (1.0f - LUX_SURFACE_ATLAS_TILE_NORMAL_THRESHOLD);
+    if (normalWeight <= 0.0f)
+        return {0, 0, 0, 0};
+
+    cn.tileSamples++;
+    // :62-67
+    vec3  tp        = mat4_mul_point(tile.transform, localPosition, 1.0f);
+    float tileDepth = tp.z / tile.objectBounds[2];
+    vec2  tileUV    = {gclamp(tp.x / tile.objectBounds[0] + 0.5f, 0.0f, 1.0f),
+                       gclamp(tp.y / tile.objectBounds[1] + 0.5f, 0.0f, 1.0f)};
+    vec2  atlasUV   = {tileUV.x * tile.extends[2] + tile.extends[0], tileUV.y * tile.extends[3] + tile.extends[1]};
+    // :68-74
+    float res = (float)sc.atlasData.resolution;
+    vec2  f   = {gfract(atlasUV.x * res + 0.5f), gfract(atlasUV.y * res + 0.5f)};
+    vec4  bw  = {(1.0f - f.x) * f.y, f.x * f.y, f.x * (1.0f - f.y), (1.0f - f.x) * (1.0f - f.y)};
+    // :76-84
+    int          R  = (int)sc.atlasData.resolution;
+    GatherCoords gd = gatherCoords(atlasUV.x, atlasUV.y, R, R, false);
+    float        z4[4] = {sc.depth[(size_t)gd.j1 * R + gd.i0], sc.depth[(size_t)gd.j1 * R + gd.i1],
+                          sc.depth[(size_t)gd.j0 * R + gd.i1], sc.depth[(size_t)gd.j0 * R + gd.i0]};
+    float depthThreshold = 2.0f * surfaceThreshold / tile.objectBounds[2];
+    float vis[4];
+    for (int i = 0; i < 4; i++)
+    {
+        vis[i] = 1.0f - gclamp((std::fabs(tileDepth - z4[i]) - depthThreshold) / (0.5f * depthThreshold), 0.0f, 1.0f);
+        if (z4[i] >= 1.0f)
+            vis[i] = 0.0f;
+    }
+    vec4 visv = {vis[0], vis[1], vis[2], vis[3]};
+    // :86-91
+    float sampleWeight = dot4(visv, bw);
+    sampleWeight *= normalWeight;
+    if (sampleWeight <= 0.0f)
+        return {0, 0, 0, 0};
+    // :93-96 (sampleGlobalSurfaceAtlasTex :50-56)
+    bw = {bw.x * visv.x, bw.y * visv.y, bw.z * visv.z, bw.w * visv.w};
+    GatherCoords gc = gatherCoords(atlasUV.x, atlasUV.y, R, R, true);
+    const uint16_t* t0 = sc.light + ((size_t)gc.j1 * R + gc.i0) * 4;
+    const uint16_t* t1 = sc.light + ((size_t)gc.j1 * R + gc.i1) * 4;
+    const uint16_t* t2 = sc.light + ((size_t)gc.j0 * R + gc.i1) * 4;
+    const uint16_t* t3 = sc.light + ((size_t)gc.j0 * R + gc.i0) * 4;
+    vec3 col;
+    col.x = dot4({h2f(t0[0]), h2f(t1[0]), h2f(t2[0]), h2f(t3[0])}, bw);
+    col.y = dot4({h2f(t0[1]), h2f(t1[1]), h2f(t2[1]), h2f(t3[1])}, bw);
+    col.z = dot4({h2f(t0[2]), h2f(t1[2]), h2f(t2[2]), h2f(t3[2])}, bw);
+    return {col.x * sampleWeight, col.y * sampleWeight, col.z * sampleWeight, sampleWeight};
+}
+
+// AtlasCommon.glsl:115-157 (macro sampleGlobalSurfaceAtlas, debug = false)
+vec4 sampleGlobalSurfaceAtlas(const Scene& sc, vec3 worldPosition, vec3 worldNormal, float surfaceThreshold, Counters& cn)
+{
+    vec4 result = {0, 0, 0, 0};
+    if (!sc.hasAtlas)
+        return result;
+    const LuxGlobalSurfaceAtlasData& data = sc.atlasData;
+    const float half = (float)LUX_SURFACE_ATLAS_CHUNKS_RESOLUTION * 0.5f;
+    int cx = iclamp((int)std::floor(worldPosition.x / data.chunkSize + half), 0, LUX_SURFACE_ATLAS_CHUNKS_RESOLUTION - 1);
+    int cy = iclamp((int)std::floor(worldPosition.y / data.chunkSize + half), 0, LUX_SURFACE_ATLAS_CHUNKS_RESOLUTION - 1);
+    int cz = iclamp((int)std::floor(worldPosition.z / data.chunkSize + half), 0, LUX_SURFACE_ATLAS_CHUNKS_RESOLUTION - 1);
+    uint32_t chunkAddress = (uint32_t)(cz * LUX_SURFACE_ATLAS_CHUNKS_RESOLUTION * LUX_SURFACE_ATLAS_CHUNKS_RESOLUTION +
+                                       cy * LUX_SURFACE_ATLAS_CHUNKS_RESOLUTION + cx); // flattenId :40-48
+    uint32_t objectsStart = sc.chunks[chunkAddress];
+    if (objectsStart == 0)
+        return result;
+    uint32_t objectsCount = sc.cull[objectsStart];
+    if (objectsCount > data.objectsCount)
+        return result;
+    objectsStart++;
+    for (uint32_t k = 0; k < objectsCount; k++)
+    {
+        uint32_t               objectAddress = sc.cull[objectsStart++];
+        const LuxObjectBuffer& object        = sc.objects[objectAddress];
+        cn.objectsVisited++;
+        vec3 bc = {object.objectBounds[0], object.objectBounds[1], object.objectBounds[2]};
+        if (length3(sub(bc, worldPosition)) > object.objectBounds[3])
+            continue;
+        float worldToLocal[16];
+        inverse4(object.transform, worldToLocal);
+        vec3 localPosition = mat4_mul_point(worldToLocal, worldPosition, 1.0f);
+        vec3 localExtents  = {object.extends[0] + surfaceThreshold, object.extends[1] + surfaceThreshold,
+                              object.extends[2] + surfaceThreshold};
+        if (std::fabs(localPosition.x) > localExtents.x || std::fabs(localPosition.y) > localExtents.y ||
+            std::fabs(localPosition.z) > localExtents.z)
+            continue;
+        vec3 normal = normalize3(mat3_mul(worldToLocal, worldNormal));
+        for (int i = 0; i < 6; i++)
+        {
+            uint32_t tileOffset = object.tileOffset[i];
+            if (tileOffset != 0)
+            {
+                vec4 s = sampleGlobalSurfaceAtlasTile(sc, sc.tiles[tileOffset], localPosition, normal, surfaceThreshold, cn);
+                result.x += s.x; result.y += s.y; result.z += s.z; result.w += s.w;
+            }
+        }
+    }
+    float d = gmax(result.w, 0.0001f);
+    result.x /= d; result.y /= d; result.z /= d;
+    return result;
+}
+
+// texture(samplerCube, dir).rgb — Vulkan cube face selection (spec §16.5.4), bilinear inside the face,
+// clamp at face edges.  The reference binds a 1x1 fallback cube when the scene has no skybox.
+vec3 sampleSky(const Scene& sc, vec3 d)
+{
+    if (!sc.sky || sc.skyFace <= 0)
+        return {0, 0, 0};
+    float ax = std::fabs(d.x), ay = std::fabs(d.y), az = std::fabs(d.z);
+    int   face;
+    float sc_, tc, ma;
+    if (az >= ax && az >= ay) { face = d.z >= 0 ? 4 : 5; sc_ = d.z >= 0 ? d.x : -d.x; tc = -d.y; ma = az; }
+    else if (ay >= ax)        { face = d.y >= 0 ? 2 : 3; sc_ = d.x; tc = d.y >= 0 ? d.z : -d.z; ma = ay; }
+    else                      { face = d.x >= 0 ? 0 : 1; sc_ = d.x >= 0 ? -d.z : d.z; tc = -d.y; ma = ax; }
+    float u = 0.5f * (sc_ / ma) + 0.5f, v = 0.5f * (tc / ma) + 0.5f;
+    int   N = sc.skyFace;
+    float x = u * (float)N - 0.5f, y = v * (float)N - 0.5f;
+    float fx = std::floor(x), fy = std::floor(y);
+    float axw = x - fx, ayw = y - fy;
+    int   x0 = iclamp((int)fx, 0, N - 1), x1 = iclamp((int)fx + 1, 0, N - 1);
+    int   y0 = iclamp((int)fy, 0, N - 1), y1 = iclamp((int)fy + 1, 0, N - 1);
+    const uint16_t* base = sc.sky + (size_t)face * N * N * 4;
+    float out[3];
+    for (int ch = 0; ch < 3; ch++)
+    {
+        float a = lerp1(h2f(base[((size_t)y0 * N + x0) * 4 + ch]), h2f(base[((size_t)y0 * N + x1) * 4 + ch]), axw);
+        float b = lerp1(h2f(base[((size_t)y1 * N + x0) * 4 + ch]), h2f(base[((size_t)y1 * N + x1) * 4 + ch]), axw);
+        out[ch] = lerp1(a, b, ayw);
+    }
+    return {out[0], out[1], out[2]};
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// GISDFRays.comp:63-128 — one probe ray
+// ---------------------------------------------------------------------------------------------------------
+void traceOneRay(const Scene& sc, const float* rot, int rayId, int probeId, uint16_t* radianceOut, uint16_t* dirDistOut,
+                 uint16_t* stepsOut, Counters& cn)
+{
+    const LuxDDGIUniform& ddgi = sc.ddgi;
+    vec3 rayOrigin = probeLocation(ddgi, probeId);
+    vec3 direction = normalize3(mat3_mul(rot, sphericalFibonacci((float)rayId, (float)ddgi.raysPerProbe)));
+
+    Hit hit = tracyGlobalSDF(sc, rayOrigin, direction, LUX_GLOBAL_SDF_WORLD_SIZE, 1.0f, 0.0f, cn);
+
+    vec4 radiance = {0, 0, 0, 0};
+    if (hit.hitTime >= 0.0f) // isHit, SDFCommon.glsl:73-76
+    {
+        cn.hits++;
+        if (hit.hitSDF <= 0.0f && hit.hitTime <= sc.sdfData.cascadeVoxelSize[0])
+            radiance = {0, 0, 0, LUX_GLOBAL_SDF_WORLD_SIZE};
+        else
+        {
+            vec3  hitPosition      = add(rayOrigin, mul(direction, hit.hitTime)); // getHitPosition :78-81
+            float surfaceThreshold = sc.sdfData.cascadeVoxelSize[hit.hitCascade] * 1.05f; // :196-199
+            vec4  surfaceColor     = sampleGlobalSurfaceAtlas(sc, hitPosition, hit.hitNormal, surfaceThreshold, cn);
+            radiance   = {surfaceColor.x, surfaceColor.y, surfaceColor.z, hit.hitTime};
+            radiance.w = gmax(radiance.w + sc.sdfData.cascadeVoxelSize[hit.hitCascade] * 0.5f, 0.0f);
+        }
+    }
+    else
+    {
+        vec3 s   = sampleSky(sc, direction);
+        radiance = {s.x, s.y, s.z, LUX_GLOBAL_SDF_WORLD_SIZE};
+    }
+    radianceOut[0] = f2h(radiance.x); radianceOut[1] = f2h(radiance.y); radianceOut[2] = f2h(radiance.z); radianceOut[3] = f2h(0.0f);
+    dirDistOut[0] = f2h(direction.x); dirDistOut[1] = f2h(direction.y); dirDistOut[2] = f2h(direction.z); dirDistOut[3] = f2h(radiance.w);
+    if (stepsOut)
+        *stepsOut = (uint16_t)hit.stepsCount;
+}
+
+const float FLT_EPS = 0.00000001f; // ProbeUpdate.glsl:51
+
+inline float mixh(float x, float y, float a) { return std::fmaf(y, a, x * (1.0f - a)); } // mix(), contract form
+
+// ---------------------------------------------------------------------------------------------------------
+// ProbeUpdate.glsl:66-152 for one interior texel of one probe.  `naive` keeps octDecode/pow inside the ray loop
+// exactly as written; the hoisted form (weights precomputed per (texel, ray)) is bit-identical because both
+// are pure functions of (texel, fp16 ray direction).
+// ---------------------------------------------------------------------------------------------------------
+struct BlendArgs
+{
+    const LuxDDGIUniform* ddgi;
+    const uint16_t*       radiance; // [nprobes][R][4]
+    const uint16_t*       dirDist;  // [nprobes][R][4]
+    int                   rayRowOffset; // probe id of row 0 of the ray buffers
+    const uint16_t*       prevIrr;
+    const uint16_t*       prevDepth;
+    uint16_t*             outIrr;
+    uint16_t*             outDepth;
+    int                   firstFrame;
+};
+
+void blendIrradianceTexel(const BlendArgs& a, int probe, int i, int j, const float* wRow /*nullable: hoisted weights [R]*/)
+{
+    const LuxDDGIUniform& d = *a.ddgi;
+    const int side = d.irradianceProbeSideLength, S = side + 2, W = d.irradianceTextureWidth;
+    const int perRow = (W - 2) / S;
+    const int px = probe % perRow, py = probe / perRow;
+    const int cx = 2 + px * S + i, cy = 2 + py * S + j; // ProbeUpdate.glsl:107
+    const int R = d.raysPerProbe;
+    const uint16_t* rad = a.radiance + (size_t)(probe - a.rayRowOffset) * R * 4;
+    const uint16_t* dd  = a.dirDist + (size_t)(probe - a.rayRowOffset) * R * 4;
+
+    float rx = 0, ry = 0, rz = 0, total = 0;
+    for (int r = 0; r < R; r++)
+    {
+        float weight;
+        if (wRow)
+            weight = wRow[r];
+        else
+        {
+            vec3 rayDirection   = {h2f(dd[r * 4 + 0]), h2f(dd[r * 4 + 1]), h2f(dd[r * 4 + 2])};
+            vec3 texelDirection = octDecode(normalizedOctCoordLocal(i, j, side));
+            weight              = gmax(0.0f, dot3(texelDirection, rayDirection));
+        }
+        if (weight >= FLT_EPS)
+        {
+            rx = std::fmaf(h2f(rad[r * 4 + 0]), weight, rx);
+            ry = std::fmaf(h2f(rad[r * 4 + 1]), weight, ry);
+            rz = std::fmaf(h2f(rad[r * 4 + 2]), weight, rz);
+            total += weight;
+        }
+    }
+    if (total > FLT_EPS)
+    {
+        float s = 1.0f / (2.0f * total);
+        rx *= s; ry *= s; rz *= s;
+    }
+    float ig = 1.0f / d.ddgiGamma;
+    rx = pow_rn(rx, ig); ry = pow_rn(ry, ig); rz = pow_rn(rz, ig);
+    size_t o = ((size_t)cy * W + cx) * 4;
+    if (!a.firstFrame)
+    {
+        rx = mixh(rx, h2f(a.prevIrr[o + 0]), d.hysteresis);
+        ry = mixh(ry, h2f(a.prevIrr[o + 1]), d.hysteresis);
+        rz = mixh(rz, h2f(a.prevIrr[o + 2]), d.hysteresis);
+    }
+    a.outIrr[o + 0] = f2h(rx); a.outIrr[o + 1] = f2h(ry); a.outIrr[o + 2] = f2h(rz); a.outIrr[o + 3] = f2h(1.0f);
+}
+
+void blendDepthTexel(const BlendArgs& a, int probe, int i, int j, const float* wRow)
+{
+    const LuxDDGIUniform& d = *a.ddgi;
+    const int side = d.depthProbeSideLength, S = side + 2, W = d.depthTextureWidth;
+    const int perRow = (W - 2) / S;
+    const int px = probe % perRow, py = probe / perRow;
+    const int cx = 2 + px * S + i, cy = 2 + py * S + j;
+    const int R = d.raysPerProbe;
+    const uint16_t* dd = a.dirDist + (size_t)(probe - a.rayRowOffset) * R * 4;
+
+    float rx = 0, ry = 0, total = 0;
+    for (int r = 0; r < R; r++)
+    {
+        float rayProbeDistance = gmin(d.maxDistance, h2f(dd[r * 4 + 3]) - 0.01f);
+        if (rayProbeDistance == -1.0f)
+            rayProbeDistance = d.maxDistance;
+        float weight;
+        if (wRow)
+            weight = wRow[r];
+        else
+        {
+            vec3 rayDirection   = {h2f(dd[r * 4 + 0]), h2f(dd[r * 4 + 1]), h2f(dd[r * 4 + 2])};
+            vec3 texelDirection = octDecode(normalizedOctCoordLocal(i, j, side));
+            weight              = pow_rn(gmax(0.0f, dot3(texelDirection, rayDirection)), d.sharpness);
+        }
+        if (weight >= FLT_EPS)
+        {
+            rx = std::fmaf(rayProbeDistance, weight, rx);
+            ry = std::fmaf(rayProbeDistance * rayProbeDistance, weight, ry);
+            total += weight;
+        }
+    }
+    if (total > FLT_EPS)
+    {
+        float s = 1.0f / (2.0f * total);
+        rx *= s; ry *= s;
+    }
+    size_t o = ((size_t)cy * W + cx) * 2;
+    if (!a.firstFrame)
+    {
+        rx = mixh(rx, h2f(a.prevDepth[o + 0]), d.hysteresis);
+        ry = mixh(ry, h2f(a.prevDepth[o + 1]), d.hysteresis);
+    }
+    a.outDepth[o + 0] = f2h(rx); a.outDepth[o + 1] = f2h(ry);
+}
+
+// BorderUpdate.glsl:25-133,136-156 — the offset tables reduce to this mirror rule (checked entry by entry
+// against tests/golden/border_offsets.json): for x,y in 1..side (coordinates relative to the probe's ring origin)
+//   (x,0) <- (side+1-x, 1)   (x,side+1) <- (side+1-x, side)   (0,y) <- (1, side+1-y)   (side+1,y) <- (side, side+1-y)
+//   corners: (0,0)<-(side,side) (side+1,0)<-(1,side) (0,side+1)<-(side,1) (side+1,side+1)<-(1,1)
+void borderProbe(uint16_t* img, int W, int channels, int side, int probe)
+{
+    const int S = side + 2, perRow = (W - 2) / S;
+    const int bx = (probe % perRow) * S + 1, by = (probe / perRow) * S + 1; // BorderUpdate.glsl:150
+    auto cp = [&](int sx, int sy, int dx, int dy) {
+        std::memcpy(img + ((size_t)(by + dy) * W + (bx + dx)) * channels, img + ((size_t)(by + sy) * W + (bx + sx)) * channels,
+                    sizeof(uint16_t) * channels);
+    };
+    for (int x = 1; x <= side; x++)
+    {
+        cp(side + 1 - x, 1, x, 0);
+        cp(side + 1 - x, side, x, side + 1);
+    }
+    for (int y = 1; y <= side; y++)
+    {
+        cp(1, side + 1 - y, 0, y);
+        cp(side, side + 1 - y, side + 1, y);
+    }
+    cp(side, side, 0, 0);
+    cp(1, side, side + 1, 0);
+    cp(side, 1, 0, side + 1);
+    cp(1, 1, side + 1, side + 1);
+}
+
+} // namespace
+
+// ---------------------------------------------------------------------------------------------------------
+// C interface for ctypes (tests / bench only)
+// ---------------------------------------------------------------------------------------------------------
+extern "C" {
+
+struct OracleSceneDesc
+{
+    const LuxDDGIUniform*            ddgi;
+    const LuxGlobalSDFData*          sdfData;
+    const uint16_t*                  sdf;
+    const uint16_t*                  mip;
+    const LuxGlobalSurfaceAtlasData* atlasData; // null = no surface cache (radiance 0 on hit)
+    const uint32_t*                  chunks;
+    const uint32_t*                  cull;
+    const LuxObjectBuffer*           objects;
+    const LuxTileBuffer*             tiles;
+    const uint16_t*                  light;
+    const float*                     depth;
+    int32_t                          skyFace;
+    const uint16_t*                  sky;
+};
+
+struct OracleCounters
+{
+    uint64_t mipTaps, texTaps, hits, tileSamples, steps, objectsVisited;
+};
+
+int oracle_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+void oracle_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0)
+        omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
+uint16_t oracle_f2h(float f) { return f2h(f); }
+float    oracle_h2f(uint16_t h) { return h2f(h); }
+
+void oracle_spherical_fibonacci(int i, int R, const float* rot, float* out3)
+{
+    vec3 v = sphericalFibonacci((float)i, (float)R);
+    if (rot)
+        v = normalize3(mat3_mul(rot, v));
+    out3[0] = v.x; out3[1] = v.y; out3[2] = v.z;
+}
+
+void oracle_oct_decode(int i, int j, int side, float* out3)
+{
+    vec3 v = octDecode(normalizedOctCoordLocal(i, j, side));
+    out3[0] = v.x; out3[1] = v.y; out3[2] = v.z;
+}
+
+void oracle_probe_location(const LuxDDGIUniform* d, int index, float* out3)
+{
+    vec3 v = probeLocation(*d, index);
+    out3[0] = v.x; out3[1] = v.y; out3[2] = v.z;
+}
+
+void oracle_inverse4(const float* m, float* o) { inverse4(m, o); }
+
+float oracle_sample3d(const uint16_t* data, int w, int h, int d, float u, float v, float ww)
+{
+    Tex3D t{data, w, h, d};
+    return sample3D(t, u, v, ww, nullptr);
+}
+
+// Trace `count` probes.  probeIds == null: probes probeBegin .. probeBegin+count-1; else the listed ids.
+// Output row k (of `count`) holds probe k's R rays.  stepsOut (nullable) [count][R] u16.
+int oracle_trace(const OracleSceneDesc* s, const float* rot16, int probeBegin, int count, const int32_t* probeIds,
+                 uint16_t* radiance, uint16_t* dirDist, uint16_t* stepsOut, OracleCounters* counters)
+{
+    if (!s || !s->ddgi || !s->sdfData || !s->sdf || !s->mip || !rot16 || !radiance || !dirDist)
+        return -1;
+    Scene sc;
+    sc.ddgi    = *s->ddgi;
+    sc.sdfData = *s->sdfData;
+    int res    = (int)s->sdfData->resolution;
+    int casc   = (int)s->sdfData->cascadesCount;
+    sc.tex     = Tex3D{s->sdf, res * casc, res, res};
+    sc.mip     = Tex3D{s->mip, (res / 4) * casc, res / 4, res / 4};
+    sc.hasAtlas = s->atlasData != nullptr;
+    if (sc.hasAtlas)
+        sc.atlasData = *s->atlasData;
+    sc.chunks = s->chunks; sc.cull = s->cull; sc.objects = s->objects; sc.tiles = s->tiles;
+    sc.light = s->light; sc.depth = s->depth;
+    sc.skyFace = s->skyFace; sc.sky = s->sky;
+    const int R = sc.ddgi.raysPerProbe;
+
+    Counters total;
+#pragma omp parallel
+    {
+        Counters cn;
+#pragma omp for schedule(dynamic, 1)
+        for (int k = 0; k < count; k++)
+        {
+            int probe = probeIds ? probeIds[k] : probeBegin + k;
+            for (int r = 0; r < R; r++)
+            {
+                size_t o = ((size_t)k * R + r);
+                traceOneRay(sc, rot16, r, probe, radiance + o * 4, dirDist + o * 4, stepsOut ? stepsOut + o : nullptr, cn);
+            }
+        }
+#pragma omp critical
+        {
+            total.mipTaps += cn.mipTaps; total.texTaps += cn.texTaps; total.hits += cn.hits;
+            total.tileSamples += cn.tileSamples; total.steps += cn.steps; total.objectsVisited += cn.objectsVisited;
+        }
+    }
+    if (counters)
+    {
+        counters->mipTaps = total.mipTaps; counters->texTaps = total.texTaps; counters->hits = total.hits;
+        counters->tileSamples = total.tileSamples; counters->steps = total.steps; counters->objectsVisited = total.objectsVisited;
+    }
+    return 0;
+}
+
+// Blend probes [probeBegin, probeBegin+count).  Ray buffers hold rows for probes rayRowOffset...
+// naive != 0: literal per-(texel, ray) evaluation as in the shader (this is the timed CPU baseline);
+// naive == 0: weights hoisted per (texel, ray) once (bit-identical; see test_oracle_kat.py).
+int oracle_blend(const LuxDDGIUniform* ddgi, const uint16_t* radiance, const uint16_t* dirDist, int rayRowOffset,
+                 const uint16_t* prevIrr, const uint16_t* prevDepth, uint16_t* outIrr, uint16_t* outDepth, int firstFrame,
+                 int probeBegin, int count, int naive)
+{
+    if (!ddgi || !radiance || !dirDist || !outIrr || !outDepth)
+        return -1;
+    if (!firstFrame && (!prevIrr || !prevDepth))
+        return -1;
+    BlendArgs a{ddgi, radiance, dirDist, rayRowOffset, prevIrr, prevDepth, outIrr, outDepth, firstFrame};
+    const int R = ddgi->raysPerProbe, si = ddgi->irradianceProbeSideLength, sd = ddgi->depthProbeSideLength;
+
+    std::vector<float> wi, wd;
+    if (!naive && count > 0)
+    {
+        // Ray directions are probe-independent (GISDFRays.comp:73): take them from the first probe's row.
+        const uint16_t* dd = dirDist + (size_t)(probeBegin - rayRowOffset) * R * 4;
+        wi.resize((size_t)si * si * R);
+        wd.resize((size_t)sd * sd * R);
+        for (int j = 0; j < si; j++)
+            for (int i = 0; i < si; i++)
+            {
+                vec3 t = octDecode(normalizedOctCoordLocal(i, j, si));
+                for (int r = 0; r < R; r++)
+                    wi[((size_t)j * si + i) * R + r] = gmax(0.0f, dot3(t, {h2f(dd[r * 4]), h2f(dd[r * 4 + 1]), h2f(dd[r * 4 + 2])}));
+            }
+#pragma omp parallel for schedule(static)
+        for (int j = 0; j < sd; j++)
+            for (int i = 0; i < sd; i++)
+            {
+                vec3 t = octDecode(normalizedOctCoordLocal(i, j, sd));
+                for (int r = 0; r < R; r++)
+                    wd[((size_t)j * sd + i) * R + r] =
+                        pow_rn(gmax(0.0f, dot3(t, {h2f(dd[r * 4]), h2f(dd[r * 4 + 1]), h2f(dd[r * 4 + 2])})), ddgi->sharpness);
+            }
+    }
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int k = 0; k < count; k++)
+    {
+        int probe = probeBegin + k;
+        for (int j = 0; j < si; j++)
+            for (int i = 0; i < si; i++)
+                blendIrradianceTexel(a, probe, i, j, naive ? nullptr : &wi[((size_t)j * si + i) * R]);
+        for (int j = 0; j < sd; j++)
+            for (int i = 0; i < sd; i++)
+                blendDepthTexel(a, probe, i, j, naive ? nullptr : &wd[((size_t)j * sd + i) * R]);
+    }
+    return 0;
+}
+
+int oracle_border(const LuxDDGIUniform* ddgi, uint16_t* irr, uint16_t* depth, int probeBegin, int count)
+{
+    if (!ddgi)
+        return -1;
+#pragma omp parallel for schedule(static)
+    for (int k = 0; k < count; k++)
+    {
+        if (irr)
+            borderProbe(irr, ddgi->irradianceTextureWidth, 4, ddgi->irradianceProbeSideLength, probeBegin + k);
+        if (depth)
+            borderProbe(depth, ddgi->depthTextureWidth, 2, ddgi->depthProbeSideLength, probeBegin + k);
+    }
+    return 0;
+}
+
+// Border copy list of one probe in ring-relative coordinates: out[n][4] = (srcx, srcy, dstx, dsty); returns n.
+int oracle_border_offsets(int side, int32_t* out)
+{
+    int n = 0;
+    auto push = [&](int sx, int sy, int dx, int dy) { out[n * 4] = sx; out[n * 4 + 1] = sy; out[n * 4 + 2] = dx; out[n * 4 + 3] = dy; n++; };
+    for (int x = 1; x <= side; x++) push(side + 1 - x, 1, x, 0);
+    for (int x = 1; x <= side; x++) push(side + 1 - x, side, x, side + 1);
+    for (int y = 1; y <= side; y++) push(1, side + 1 - y, 0, y);
+    for (int y = 1; y <= side; y++) push(side, side + 1 - y, side + 1, y);
+    push(side, side, 0, 0); push(1, side, side + 1, 0); push(side, 1, 0, side + 1); push(1, 1, side + 1, side + 1);
+    return n;
+}
+
+} // extern "C"
