@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""bench.py — SDF probe rays/s and ms per DDGI volume update (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4|c5|c1|city128] [--impl lux|reference]
+
+One "step" = one DDGI volume update (trace + blend + border [+ all-gather of the updated atlases at N > 1]) of the
+named workload.  N > 1 is launched by torchrun (one rank per GPU); the probe volume is sharded into z-slabs, the SDF
+and the surface cache are replicated, the updated atlas rows are exchanged with one in-place NCCL all-gather per atlas
+per step.  Total work is fixed as N grows => "scaling": "strong".
+
+Printed keys beyond the base contract:
+  ms_per_update          the second half of the BASELINE metric
+  stage_ms               setup / trace / blend of the last timed step (CUDA events on the engine's stream)
+  roofline               dominant kernel (trace): algorithmic HBM bytes per launch / measured launch time vs measured HBM peak
+  roofline_blend         the same for the blend stage (HBM bytes and FP32 FMA rate)
+  cpu_baseline           the CPU oracle (a port of the reference shaders) timed on this box's host cores on a bounded sample
+  e2e                    the same metric through the C ABI with HOST buffers: per step the light cache is uploaded from pinned
+                         memory and both updated atlases are read back into pinned memory
+
+--impl reference times the reference's algorithm on the host CPU (the oracle port; the reference's own shaders cannot run
+here: no Vulkan/glslang in the image) on a bounded probe sample per step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "sdf_probe_rays_per_s"
+UNIT = "rays/s"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def workload_desc(name, sc):
+    u = sc.uniform
+    return {"workload": f"{name}: {sc.name} SDF {int(sc.sdf_data.resolution)}^3 fp16, {u.probeCounts[0]}x{u.probeCounts[1]}x{u.probeCounts[2]} probes, "
+                        f"{u.raysPerProbe} rays/probe",
+            "probes": sc.probes, "rays_per_probe": u.raysPerProbe, "sdf_res": int(sc.sdf_data.resolution),
+            "surface_atlas_res": int(sc.atlas_data.resolution) if sc.atlas_data is not None else 0}
+
+
+def algorithmic_bytes(sc, probes):
+    """SURVEY §8d.  Trace: two RGBA16F stores per ray + SDF + mip read once + both surface atlases once (upper bound).
+    Blend+border: ray buffers read once + previous interiors + new interiors and borders."""
+    R = sc.uniform.raysPerProbe
+    atlas = (int(sc.atlas_data.resolution) ** 2) * (8 + 4) if sc.atlas_data is not None else 0
+    trace = 16 * probes * R + sc.sdf_bytes() + atlas
+    blend = 16 * probes * R + probes * (64 * 8 + 256 * 4) + probes * (100 * 8 + 324 * 4)
+    return trace, blend
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle on host cores
+# ----------------------------------------------------------------------------------------------------------------------
+def oracle_sample_ids(sc, n):
+    P = sc.probes
+    n = min(n, P)
+    return (np.arange(n, dtype=np.int64) * P // n).astype(np.int32)  # stratified over the whole volume
+
+
+def time_oracle(sc, rot, sample_probes, steps, warmup):
+    """One step = trace + literal (naive) blend + border of `sample_probes` stratified probes on all host threads."""
+    from oracle import binding as ob
+
+    osc = ob.OracleScene(sc)
+    ids = oracle_sample_ids(sc, sample_probes)
+    n = len(ids)
+    R = sc.uniform.raysPerProbe
+    # blend timing runs on a compact n-probe volume with the same rays per probe (its cost is independent of probe position)
+    from luxgi_b200 import abi
+
+    side = 1
+    while side * side < n:
+        side *= 2
+    ub = abi.make_uniform((0, 0, 0), (1, 1, 1), (side, max(1, n // side), 1), R, max_distance=sc.uniform.maxDistance,
+                          sharpness=sc.uniform.sharpness, hysteresis=sc.uniform.hysteresis, gamma=sc.uniform.ddgiGamma)
+    nb = abi.probe_count(ub)
+    irr = [ob.new_atlases(ub)[0] for _ in range(2)]
+    dep = [ob.new_atlases(ub)[1] for _ in range(2)]
+    times, t_trace, t_blend = [], 0.0, 0.0
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        rad, dd, _, counters = osc.trace(rot, probe_ids=ids)
+        t1 = time.perf_counter()
+        ob.blend(ub, rad[:nb], dd[:nb], irr[0], dep[0], irr[1], dep[1], first_frame=(it == 0), naive=True)
+        ob.border(ub, irr[1], dep[1])
+        t2 = time.perf_counter()
+        irr.reverse(); dep.reverse()
+        if it >= warmup:
+            times.append(t2 - t0); t_trace += t1 - t0; t_blend += t2 - t1
+    total = sum(times)
+    return {"rays_per_s": n * R * len(times) / total, "sec_per_step": total / len(times), "trace_frac": t_trace / total,
+            "sample_probes": int(n), "rays": int(n * R), "threads": ob.lib().oracle_threads(), "counters": counters}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+
+    from luxgi_b200 import scenes
+
+    dev = "cuda" if torch.cuda.is_available() else "cpu"  # the fixture generator may use the GPU; the timed code is CPU only
+    sc = scenes.build(args.workload, device=dev)
+    rot = scenes.frame_rotation(0)
+    sample = args.reference_probes
+    r = time_oracle(sc, rot, sample, args.steps, args.warmup)
+    full_ms = sc.probes * sc.uniform.raysPerProbe / r["rays_per_s"] * 1e3
+    line = {"impl": "reference", "metric": METRIC, "value": r["rays_per_s"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": r["sec_per_step"] * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_desc(args.workload, sc),
+            "ms_per_update_extrapolated": full_ms,
+            "cpu_baseline": {"value": r["rays_per_s"], "unit": UNIT, "cores": r["threads"], "kind": "port",
+                             "sample": f"{r['sample_probes']} stratified probes x {sc.uniform.raysPerProbe} rays per step "
+                                       f"(trace + literal blend + border), OpenMP over probes; trace share {r['trace_frac']:.2f}"},
+            "e2e": {"value": r["rays_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------------------------
+def run_lux(args):
+    import torch
+    import torch.distributed as dist
+
+    from luxgi_b200 import abi, ddgi, scenes
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the engine has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus or world == 1, (world, args.gpus)
+
+    sc = scenes.build(args.workload, device=dev)
+    u = sc.uniform
+    if u.probeCounts[2] % world:
+        raise SystemExit(f"{world} GPUs do not divide Z={u.probeCounts[2]}")
+    stream = torch.cuda.Stream(device=dev)
+    flags = abi.FLAG_STAGE_TIMERS
+    pipe = ddgi.DDGIPipeline(u, device=local, rank=rank, world=world, flags=flags, stream=stream.cuda_stream)
+    pipe.set_scene(sc)
+    st = pipe.state()
+    P, R = sc.probes, u.raysPerProbe
+    rot_cache = {}
+
+    def rot_of(f):
+        if f not in rot_cache:
+            rot_cache[f] = scenes.frame_rotation(f)
+        return rot_cache[f]
+
+    views = {}
+
+    def atlas_rows(buf, row_begin, rows_total):
+        ptr, _ = pipe.buffer_ptr(buf)
+        if (buf, ptr) not in views:
+            t = torch.as_tensor(pipe.device_view(buf), device=dev)
+            views[(buf, ptr)] = t
+        t = views[(buf, ptr)]
+        return t[1:1 + rows_total].reshape(-1), t[row_begin:row_begin + rows_total // world].reshape(-1)
+
+    def step(f):
+        pipe.update(rot_of(f))
+        if world > 1:  # one in-place all-gather per atlas: own slab rows -> every rank's full atlas
+            with torch.cuda.stream(stream):
+                full, mine = atlas_rows(abi.BUF_IRRADIANCE, st.irradianceRowBegin, st.irradianceRowCount * world)
+                dist.all_gather_into_tensor(full, mine)
+                full, mine = atlas_rows(abi.BUF_DEPTH, st.depthRowBegin, st.depthRowCount * world)
+                dist.all_gather_into_tensor(full, mine)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-resident timing -----------------------------------------------------------------------------------
+    f = 0
+    for _ in range(args.warmup):
+        step(f); f += 1
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = pipe.state().kernelLaunches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stage = {"setup": 0.0, "trace": 0.0, "blend": 0.0}
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        step(f); f += 1
+        if args.stage_every_step:
+            pipe.synchronize()
+            t = pipe.stage_ms()
+            stage["setup"] += t.setup_ms; stage["trace"] += t.trace_ms; stage["blend"] += t.blend_ms
+    with torch.cuda.stream(stream):
+        e1.record(stream)
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    ms_total = e0.elapsed_time(e1)
+    if not args.stage_every_step:
+        t = pipe.stage_ms()
+        stage = {"setup": t.setup_ms * args.steps, "trace": t.trace_ms * args.steps, "blend": t.blend_ms * args.steps}
+    launches = pipe.state().kernelLaunches - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    tm = torch.tensor([ms_total, stage["trace"], stage["blend"], stage["setup"]], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    ms_total, trace_ms, blend_ms, setup_ms = [float(x) for x in tm.tolist()]
+    ms_per_step = ms_total / args.steps
+    value = P * R * args.steps / (ms_total * 1e-3)
+
+    # ---- end to end through the C ABI with host buffers --------------------------------------------------------------
+    light_bytes = int(sc.atlas_data.resolution) ** 2 * 8
+    pin_light = torch.empty(light_bytes, dtype=torch.uint8).pin_memory()
+    pin_light.copy_(sc.light.reshape(-1).view(torch.uint8).cpu())
+    irr_row_bytes, dep_row_bytes = u.irradianceTextureWidth * 8, u.depthTextureWidth * 4
+    pin_irr = torch.empty(st.irradianceRowCount * irr_row_bytes, dtype=torch.uint8).pin_memory()
+    pin_dep = torch.empty(st.depthRowCount * dep_row_bytes, dtype=torch.uint8).pin_memory()
+    def e2e_step(f):
+        pipe.update_surface_light_cache_ptr(pin_light.data_ptr())  # H2D of this frame's light cache through the C ABI
+        step(f)
+        pipe.download_rows_async_ptr(abi.BUF_IRRADIANCE, st.irradianceRowBegin, st.irradianceRowCount, pin_irr.data_ptr())
+        pipe.download_rows_async_ptr(abi.BUF_DEPTH, st.depthRowBegin, st.depthRowCount, pin_dep.data_ptr())
+        pipe.synchronize()  # the caller consumes the atlases on the host every frame
+
+    for _ in range(max(1, args.warmup // 2)):
+        e2e_step(f); f += 1
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step(f); f += 1
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te.item())
+    e2e_value = P * R * args.steps / e2e_s
+
+    if rank == 0:
+        peaks, peak_kind = measured_peaks()
+        hbm = float(peaks["hbm_gbs"])
+        probes_rank = st.probeCount
+        tb, bb = algorithmic_bytes(sc, probes_rank)
+        trace_launch_ms = trace_ms / args.steps
+        blend_launch_ms = blend_ms / args.steps
+        ach = tb / (trace_launch_ms * 1e-3) / 1e9
+        achb = bb / (blend_launch_ms * 1e-3) / 1e9
+        fma = probes_rank * R * 704 / (blend_launch_ms * 1e-3) / 1e12  # dense (value, weight) FMAs per second, T FMA/s
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "ms_per_update": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": dict(workload_desc(args.workload, sc), parallelism=f"zslab{world}", l2_policy="inputs larger than L2 (no flush)",
+                           sharding="probe z-slabs, SDF + surface cache replicated, in-place NCCL all-gather of atlas rows per step"),
+            "stage_ms": {"setup": setup_ms / args.steps, "trace": trace_launch_ms, "blend_border": blend_launch_ms,
+                         "other_incl_allgather": ms_per_step - (setup_ms + trace_ms + blend_ms) / args.steps},
+            "trace_rays_per_s": probes_rank * world * R / (trace_launch_ms * 1e-3),
+            "roofline": {"bound": "hbm", "kernel": "trace_kernel", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+                         "traffic": None, "peak_source": peak_kind, "algorithmic_bytes_per_launch": tb},
+            "roofline_blend": {"bound": "hbm", "kernel": "blend_irradiance_kernel+blend_depth_kernel", "achieved": achb, "peak": hbm,
+                               "unit": "GB/s", "frac": achb / hbm, "algorithmic_bytes_per_launch": bb, "fp32_tfma_per_s": fma},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_update": e2e_s / args.steps * 1e3,
+                    "h2d_bytes_per_step": light_bytes + 64, "d2h_bytes_per_step": int(pin_irr.numel() + pin_dep.numel()),
+                    "note": "per rank: light cache H2D from pinned memory, own atlas rows D2H into pinned memory, host sync every step"},
+            "gpu_launches": int(launches),
+            "wall_s_timed_region": t_wall,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            r = time_oracle(sc, rot_of(0), args.cpu_probes, 1, 0)
+            line["cpu_baseline"] = {"value": r["rays_per_s"], "unit": UNIT, "cores": r["threads"], "kind": "port",
+                                    "sample": f"{r['sample_probes']} stratified probes x {R} rays, 1 update (trace + literal blend + border), "
+                                              f"{r['sec_per_step']:.1f} s; trace share {r['trace_frac']:.2f}",
+                                    "counters_per_ray": {k: v / r["rays"] for k, v in r["counters"].items()}}
+        print(json.dumps(line), flush=True)
+    pipe.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="c4")
+    ap.add_argument("--impl", default="lux", choices=["lux", "reference"])
+    ap.add_argument("--cpu-probes", type=int, default=4096)
+    ap.add_argument("--reference-probes", type=int, default=4096)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--stage-every-step", action="store_true", help="sync + read stage timers every step (perturbs the total)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_lux(args)
+
+
+if __name__ == "__main__":
+    main()

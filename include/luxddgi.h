@@ -260,6 +260,8 @@ LUX_API int lux_ddgi_get_buffer(LuxDDGIContext* ctx, LuxBufferId id, void** devi
 LUX_API int lux_ddgi_download(LuxDDGIContext* ctx, LuxBufferId id, void* host, size_t bytes);
 /* Same, without the trailing synchronize: `pinnedHost` must be page-locked; order with lux_ddgi_synchronize. */
 LUX_API int lux_ddgi_download_async(LuxDDGIContext* ctx, LuxBufferId id, void* pinnedHost, size_t bytes);
+/* Rows [rowBegin, rowBegin + rowCount) of an atlas (e.g. the shard's own rows from lux_ddgi_get_state) into pinned memory. */
+LUX_API int lux_ddgi_download_rows_async(LuxDDGIContext* ctx, LuxBufferId id, int32_t rowBegin, int32_t rowCount, void* pinnedHost);
 /* Overwrite the ray buffers (this shard's rows) — what probe_update consumes is whatever these hold, exactly as the
  * reference's blend reads the iRadiance / iDirectionDistance images (ProbeUpdate.glsl:53-64).  Lets a host (or a test)
  * run the blend stage on rays produced elsewhere. */

@@ -578,12 +578,7 @@ int lux_ddgi_update_surface_light_cache(LuxDDGIContext* c, const void* light, Lu
     if (!light)
         return fail(LUX_ERR_INVALID_ARG, "null light cache");
     const size_t texels = (size_t)c->atlasData.resolution * c->atlasData.resolution;
-    if (kind == LUX_MEM_DEVICE)
-        return upload(*c, c->light, light, texels * 8, kind);
-    if (c->light.borrowed)
-        return fail(LUX_ERR_UNSUPPORTED, "light cache is a borrowed device buffer; update it in place");
-    LUX_CUDA(cudaMemcpyAsync(c->light.ptr, light, texels * 8, cudaMemcpyHostToDevice, c->stream)); // async for pinned sources
-    return LUX_OK;
+    return upload(*c, c->light, light, texels * 8, kind); // HOST: async copy on the context's stream (pinned sources overlap)
 }
 
 int lux_ddgi_set_skybox(LuxDDGIContext* c, int32_t faceSize, const void* faces, LuxMemKind kind)
@@ -737,6 +732,35 @@ int lux_ddgi_download_async(LuxDDGIContext* c, LuxBufferId id, void* pinnedHost,
     if (bytes != b->bytes)
         return fail(LUX_ERR_INVALID_ARG, "size mismatch: buffer holds %zu bytes, caller passed %zu", b->bytes, bytes);
     LUX_CUDA(cudaMemcpyAsync(pinnedHost, b->ptr, bytes, cudaMemcpyDeviceToHost, c->stream));
+    return LUX_OK;
+}
+
+int lux_ddgi_download_rows_async(LuxDDGIContext* c, LuxBufferId id, int32_t rowBegin, int32_t rowCount, void* pinnedHost)
+{
+    CHECK_CTX(c);
+    if (!pinnedHost)
+        return fail(LUX_ERR_INVALID_ARG, "null host pointer");
+    DeviceBuffer* b = nullptr;
+    int rc = bufferOf(c, id, &b);
+    if (rc != LUX_OK)
+        return rc;
+    size_t rowBytes;
+    int    rows;
+    if (id == LUX_BUF_IRRADIANCE || id == LUX_BUF_IRRADIANCE_PREV)
+    {
+        rowBytes = (size_t)c->uniform.irradianceTextureWidth * 8;
+        rows     = c->uniform.irradianceTextureHeight;
+    }
+    else if (id == LUX_BUF_DEPTH || id == LUX_BUF_DEPTH_PREV)
+    {
+        rowBytes = (size_t)c->uniform.depthTextureWidth * 4;
+        rows     = c->uniform.depthTextureHeight;
+    }
+    else
+        return fail(LUX_ERR_INVALID_ARG, "row download is for atlases only");
+    if (rowBegin < 0 || rowCount < 0 || rowBegin + rowCount > rows)
+        return fail(LUX_ERR_INVALID_ARG, "rows [%d,%d) outside the atlas (%d rows)", rowBegin, rowBegin + rowCount, rows);
+    LUX_CUDA(cudaMemcpyAsync(pinnedHost, (const char*)b->ptr + rowBegin * rowBytes, rowCount * rowBytes, cudaMemcpyDeviceToHost, c->stream));
     return LUX_OK;
 }
 

@@ -23,7 +23,7 @@ EXPORTS = [
     "lux_ddgi_destroy", "lux_ddgi_set_uniform", "lux_ddgi_set_global_sdf", "lux_ddgi_set_surface_atlas",
     "lux_ddgi_update_surface_light_cache", "lux_ddgi_set_skybox", "lux_ddgi_trace_rays", "lux_ddgi_probe_update",
     "lux_ddgi_border_update", "lux_ddgi_end_frame", "lux_ddgi_update", "lux_ddgi_synchronize", "lux_ddgi_get_buffer",
-    "lux_ddgi_download", "lux_ddgi_download_async", "lux_ddgi_set_ray_buffers", "lux_ddgi_restore", "lux_ddgi_get_state",
+    "lux_ddgi_download", "lux_ddgi_download_async", "lux_ddgi_download_rows_async", "lux_ddgi_set_ray_buffers", "lux_ddgi_restore", "lux_ddgi_get_state",
     "lux_ddgi_get_stage_ms",
 ]
 
@@ -64,6 +64,7 @@ def load():
         "lux_ddgi_get_buffer": [vp, i32, C.POINTER(vp), C.POINTER(sz)],
         "lux_ddgi_download": [vp, i32, vp, sz],
         "lux_ddgi_download_async": [vp, i32, vp, sz],
+        "lux_ddgi_download_rows_async": [vp, i32, i32, i32, vp],
         "lux_ddgi_set_ray_buffers": [vp, vp, vp, i32],
         "lux_ddgi_restore": [vp, vp, vp, i32, i32],
         "lux_ddgi_get_state": [vp, C.POINTER(abi.State)],
@@ -287,6 +288,9 @@ class DDGIPipeline:
 
     def download_async_ptr(self, buf, host_ptr, nbytes):
         _check(self._lib.lux_ddgi_download_async(self._h, buf, C.c_void_p(host_ptr), nbytes))
+
+    def download_rows_async_ptr(self, buf, row_begin, row_count, host_ptr):
+        _check(self._lib.lux_ddgi_download_rows_async(self._h, buf, int(row_begin), int(row_count), C.c_void_p(host_ptr)))
 
     def restore(self, irradiance, depth, frames, ping_pong):
         a, b = _as_host(irradiance), _as_host(depth)

@@ -493,8 +493,8 @@ CONFIGS = {
     "c4": (city_scene, dict(res=512, lots=48, counts=(64, 16, 64), rays=512, atlas_res=4096)),
     "c5": (city_scene, dict(res=1024, lots=96, counts=(128, 32, 128), rays=1024, atlas_res=8192)),
     # reduced cities for tests
-    "city64": (city_scene, dict(res=64, lots=6, counts=(8, 4, 8), rays=64, atlas_res=256)),
-    "city128": (city_scene, dict(res=128, lots=12, counts=(16, 8, 16), rays=128, atlas_res=512)),
+    "city64": (city_scene, dict(res=64, lots=6, counts=(8, 4, 8), rays=64, atlas_res=512)),
+    "city128": (city_scene, dict(res=128, lots=12, counts=(16, 8, 16), rays=128, atlas_res=1024)),
 }
 
 

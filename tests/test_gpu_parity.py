@@ -86,9 +86,10 @@ def test_staged_systems_and_unfused_border_equal_fused(oracle):
     a = run_engine(sc, rots)
     b = run_engine(sc, rots, flags=abi.FLAG_UNFUSED_BORDER, staged=True)
     c = run_engine(sc, rots, staged=True)  # fused borders + the (idempotent) standalone border pass
+    ai, ad = a.irradiance, a.depth
     for p in (a, b, c):
         assert_atlases_match(p, orc)
-        assert np.array_equal(p.irradiance, a.irradiance) and np.array_equal(p.depth, a.depth)
+        assert np.array_equal(p.irradiance, ai) and np.array_equal(p.depth, ad)
         p.close()
 
 
