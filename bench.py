@@ -210,7 +210,7 @@ def run_lux(args):
     if u.probeCounts[2] % world:
         raise SystemExit(f"{world} GPUs do not divide Z={u.probeCounts[2]}")
     stream = torch.cuda.Stream(device=dev)
-    flags = abi.FLAG_STAGE_TIMERS
+    flags = abi.FLAG_STAGE_TIMERS | {"wavefront": 0, "texture": abi.FLAG_SDF_TEXTURE, "simple": abi.FLAG_TRACE_SIMPLE}[args.trace]
     pipe = ddgi.DDGIPipeline(u, device=local, rank=rank, world=world, flags=flags, stream=stream.cuda_stream)
     pipe.set_scene(sc)
     st = pipe.state()
@@ -284,34 +284,38 @@ def run_lux(args):
     ms_per_step = ms_total / args.steps
     value = P * R * args.steps / (ms_total * 1e-3)
 
-    # ---- end to end through the C ABI with host buffers --------------------------------------------------------------
-    light_bytes = int(sc.atlas_data.resolution) ** 2 * 8
-    pin_light = torch.empty(light_bytes, dtype=torch.uint8).pin_memory()
-    pin_light.copy_(sc.light.reshape(-1).view(torch.uint8).cpu())
-    irr_row_bytes, dep_row_bytes = u.irradianceTextureWidth * 8, u.depthTextureWidth * 4
-    pin_irr = torch.empty(st.irradianceRowCount * irr_row_bytes, dtype=torch.uint8).pin_memory()
-    pin_dep = torch.empty(st.depthRowCount * dep_row_bytes, dtype=torch.uint8).pin_memory()
-    def e2e_step(f):
-        pipe.update_surface_light_cache_ptr(pin_light.data_ptr())  # H2D of this frame's light cache through the C ABI
-        step(f)
-        pipe.download_rows_async_ptr(abi.BUF_IRRADIANCE, st.irradianceRowBegin, st.irradianceRowCount, pin_irr.data_ptr())
-        pipe.download_rows_async_ptr(abi.BUF_DEPTH, st.depthRowBegin, st.depthRowCount, pin_dep.data_ptr())
-        pipe.synchronize()  # the caller consumes the atlases on the host every frame
+    e2e_value, e2e_s, light_bytes, d2h_bytes = None, None, 0, 0
+    if not args.no_e2e:
+        # ---- end to end through the C ABI with host buffers --------------------------------------------------------------
+        light_bytes = int(sc.atlas_data.resolution) ** 2 * 8
+        pin_light = torch.empty(light_bytes, dtype=torch.uint8).pin_memory()
+        pin_light.copy_(sc.light.reshape(-1).view(torch.uint8).cpu())
+        irr_row_bytes, dep_row_bytes = u.irradianceTextureWidth * 8, u.depthTextureWidth * 4
+        pin_irr = torch.empty(st.irradianceRowCount * irr_row_bytes, dtype=torch.uint8).pin_memory()
+        pin_dep = torch.empty(st.depthRowCount * dep_row_bytes, dtype=torch.uint8).pin_memory()
+        def e2e_step(f):
+            pipe.update_surface_light_cache_ptr(pin_light.data_ptr())  # H2D of this frame's light cache through the C ABI
+            step(f)
+            pipe.download_rows_async_ptr(abi.BUF_IRRADIANCE, st.irradianceRowBegin, st.irradianceRowCount, pin_irr.data_ptr())
+            pipe.download_rows_async_ptr(abi.BUF_DEPTH, st.depthRowBegin, st.depthRowCount, pin_dep.data_ptr())
+            pipe.synchronize()  # the caller consumes the atlases on the host every frame
 
-    for _ in range(max(1, args.warmup // 2)):
-        e2e_step(f); f += 1
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step(f); f += 1
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_s = float(te.item())
-    e2e_value = P * R * args.steps / e2e_s
+        for _ in range(max(1, args.warmup // 2)):
+            e2e_step(f); f += 1
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step(f); f += 1
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_s = float(te.item())
+        e2e_value = P * R * args.steps / e2e_s
 
+
+        d2h_bytes = int(pin_irr.numel() + pin_dep.numel())
     if rank == 0:
         peaks, peak_kind = measured_peaks()
         hbm = float(peaks["hbm_gbs"])
@@ -336,8 +340,8 @@ def run_lux(args):
             "roofline_blend": {"bound": "hbm", "kernel": "blend_irradiance_kernel+blend_depth_kernel", "achieved": achb, "peak": hbm,
                                "unit": "GB/s", "frac": achb / hbm, "algorithmic_bytes_per_launch": bb, "fp32_tfma_per_s": fma},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_update": e2e_s / args.steps * 1e3,
-                    "h2d_bytes_per_step": light_bytes + 64, "d2h_bytes_per_step": int(pin_irr.numel() + pin_dep.numel()),
+            "e2e": None if e2e_value is None else {"value": e2e_value, "unit": UNIT, "ms_per_update": e2e_s / args.steps * 1e3,
+                    "h2d_bytes_per_step": light_bytes + 64, "d2h_bytes_per_step": d2h_bytes,
                     "note": "per rank: light cache H2D from pinned memory, own atlas rows D2H into pinned memory, host sync every step"},
             "gpu_launches": int(launches),
             "wall_s_timed_region": t_wall,
@@ -364,6 +368,8 @@ def main():
     ap.add_argument("--cpu-probes", type=int, default=4096)
     ap.add_argument("--reference-probes", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--trace", default="wavefront", choices=["wavefront", "texture", "simple"], help="trace kernel variant")
+    ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--stage-every-step", action="store_true", help="sync + read stage timers every step (perturbs the total)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -85,11 +85,14 @@ struct LuxDDGIContext
 
     // per-frame tables
     DeviceBuffer dirs, wIrr, wDepth, scaleIrr, scaleDepth;
+    DeviceBuffer origins, records, meta, chunkCounter; // wavefront trace scratch
 
     // uGlobalSDF / uGlobalMipSDF / sdfData
     bool             hasSdf = false;
     LuxGlobalSDFData sdfData{};
     DeviceBuffer     sdf, mip;
+    cudaArray_t         sdfArray = nullptr, mipArray = nullptr;
+    cudaTextureObject_t sdfTex = 0, mipTex = 0;
 
     // surface cache
     bool                      hasAtlas = false;
@@ -136,6 +139,40 @@ static int allocZero(LuxDDGIContext& c, DeviceBuffer& dst, size_t bytes)
     LUX_CUDA(cudaMalloc(&dst.ptr, bytes ? bytes : 1));
     dst.bytes = bytes;
     LUX_CUDA(cudaMemsetAsync(dst.ptr, 0, bytes, c.stream));
+    return LUX_OK;
+}
+
+static void releaseSdfTextures(LuxDDGIContext& c)
+{
+    if (c.sdfTex) cudaDestroyTextureObject(c.sdfTex);
+    if (c.mipTex) cudaDestroyTextureObject(c.mipTex);
+    if (c.sdfArray) cudaFreeArray(c.sdfArray);
+    if (c.mipArray) cudaFreeArray(c.mipArray);
+    c.sdfTex = c.mipTex = 0;
+    c.sdfArray = c.mipArray = nullptr;
+}
+
+// R16F volume [d][h][w] in linear device memory -> layered 2-D cudaArray (one layer per z) + texture object:
+// unnormalised coordinates, clamp addressing, point sampling (only tld4 gathers are issued against it).
+static int makeLayeredTexture(LuxDDGIContext& c, const void* dev, int w, int h, int d, cudaArray_t* arr, cudaTextureObject_t* tex)
+{
+    cudaChannelFormatDesc desc = cudaCreateChannelDescHalf();
+    LUX_CUDA(cudaMalloc3DArray(arr, &desc, make_cudaExtent((size_t)w, (size_t)h, (size_t)d), cudaArrayLayered));
+    cudaMemcpy3DParms cp{};
+    cp.srcPtr   = make_cudaPitchedPtr(const_cast<void*>(dev), (size_t)w * 2, (size_t)w, (size_t)h);
+    cp.dstArray = *arr;
+    cp.extent   = make_cudaExtent((size_t)w, (size_t)h, (size_t)d);
+    cp.kind     = cudaMemcpyDeviceToDevice;
+    LUX_CUDA(cudaMemcpy3DAsync(&cp, c.stream));
+    cudaResourceDesc rd{};
+    rd.resType         = cudaResourceTypeArray;
+    rd.res.array.array = *arr;
+    cudaTextureDesc td{};
+    td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+    td.filterMode       = cudaFilterModePoint;
+    td.readMode         = cudaReadModeElementType;
+    td.normalizedCoords = 0;
+    LUX_CUDA(cudaCreateTextureObject(tex, &rd, &td, nullptr));
     return LUX_OK;
 }
 
@@ -194,6 +231,14 @@ static int initializeProbeGrid(LuxDDGIContext& c)
     if ((rc = allocZero(c, c.wDepth, (size_t)c.raysPadded * 256 * sizeof(float))) != LUX_OK) return rc;
     if ((rc = allocZero(c, c.scaleIrr, 64 * sizeof(float))) != LUX_OK) return rc;
     if ((rc = allocZero(c, c.scaleDepth, 256 * sizeof(float))) != LUX_OK) return rc;
+    if ((rc = allocZero(c, c.origins, (size_t)c.probeCount * sizeof(float4))) != LUX_OK) return rc;
+    if ((rc = allocZero(c, c.chunkCounter, 64)) != LUX_OK) return rc;
+    if (!(c.flags & LUX_DDGI_FLAG_TRACE_SIMPLE))
+    {
+        const size_t nrec = lux::trace_record_count(c.probeCount, u.raysPerProbe);
+        if ((rc = allocZero(c, c.records, nrec * sizeof(float4))) != LUX_OK) return rc;
+        if ((rc = allocZero(c, c.meta, nrec * sizeof(uint32_t))) != LUX_OK) return rc;
+    }
     c.frames      = 0;
     c.pingPong    = 0;
     c.lastWritten = 1;
@@ -202,6 +247,33 @@ static int initializeProbeGrid(LuxDDGIContext& c)
 }
 
 } // namespace init
+
+static void fillVolume(const LuxDDGIContext& c, lux::TraceParams& p)
+{
+    const LuxDDGIUniform& u = c.uniform;
+    for (int i = 0; i < 3; i++)
+    {
+        p.start[i] = u.startPosition[i];
+        p.step[i]  = u.step[i];
+    }
+    p.countX       = u.probeCounts[0];
+    p.countY       = u.probeCounts[1];
+    p.raysPerProbe = u.raysPerProbe;
+    p.probeBegin   = c.probeBegin;
+    p.probeCount   = c.probeCount;
+    p.origins      = (const float4*)c.origins.ptr;
+}
+
+// probe positions only change with the uniform: computed once per (re)configuration
+static int updateOrigins(LuxDDGIContext& c)
+{
+    lux::TraceParams p{};
+    fillVolume(c, p);
+    lux::launch_probe_origins(p, c.stream);
+    c.launches += 1;
+    LUX_CUDA(cudaGetLastError());
+    return LUX_OK;
+}
 
 static void mark(LuxDDGIContext& c, int i)
 {
@@ -224,23 +296,15 @@ static int system(LuxDDGIContext& c, const LuxTracePushConstants& push)
     mark(c, 1);
 
     TraceParams p{};
-    for (int i = 0; i < 3; i++)
-    {
-        p.start[i] = u.startPosition[i];
-        p.step[i]  = u.step[i];
-    }
-    p.countX       = u.probeCounts[0];
-    p.countY       = u.probeCounts[1];
-    p.raysPerProbe = u.raysPerProbe;
-    p.probeBegin   = c.probeBegin;
-    p.probeCount   = c.probeCount;
+    fillVolume(c, p);
     p.sdf          = c.sdfData;
     p.tex          = (const uint16_t*)c.sdf.ptr;
     p.mip          = (const uint16_t*)c.mip.ptr;
     p.res          = (int)c.sdfData.resolution;
     p.mipRes       = p.res / 4;
     p.cascades     = (int)c.sdfData.cascadesCount;
-    p.texObj = p.mipObj = 0;
+    p.texObj       = c.sdfTex;
+    p.mipObj       = c.mipTex;
     p.hasAtlas     = c.hasAtlas ? 1 : 0;
     if (c.hasAtlas)
     {
@@ -261,8 +325,10 @@ static int system(LuxDDGIContext& c, const LuxTracePushConstants& push)
     p.radiance = (uint2*)c.radiance.ptr;
     p.dirDist  = (uint2*)c.directionDepth.ptr;
     p.steps    = nullptr;
-    launch_trace(p, false, c.stream);
-    c.launches += 1;
+    p.records  = (float4*)c.records.ptr;
+    p.meta     = (uint32_t*)c.meta.ptr;
+    const int variant = (c.flags & LUX_DDGI_FLAG_TRACE_SIMPLE) ? 0 : (c.sdfTex ? 2 : 1);
+    c.launches += launch_trace(p, variant, (unsigned int*)c.chunkCounter.ptr, c.stream);
     mark(c, 2);
     LUX_CUDA(cudaGetLastError());
     c.raysValid = true;
@@ -458,6 +524,8 @@ int lux_ddgi_create(const LuxDDGIUniform* uniform, const LuxDDGICreateInfo* info
     for (auto& ev : c->ev)
         cudaEventCreate(&ev);
     rc = init::initializeProbeGrid(*c);
+    if (rc == LUX_OK)
+        rc = updateOrigins(*c);
     if (rc != LUX_OK)
     {
         lux_ddgi_destroy(c);
@@ -476,10 +544,11 @@ int lux_ddgi_destroy(LuxDDGIContext* c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     DeviceBuffer* all[] = {&c->radiance, &c->directionDepth, &c->irradiance[0], &c->irradiance[1], &c->depth[0], &c->depth[1],
-                           &c->dirs, &c->wIrr, &c->wDepth, &c->scaleIrr, &c->scaleDepth, &c->sdf, &c->mip, &c->chunks, &c->cull,
+                           &c->dirs, &c->wIrr, &c->wDepth, &c->scaleIrr, &c->scaleDepth, &c->origins, &c->records, &c->meta, &c->chunkCounter, &c->sdf, &c->mip, &c->chunks, &c->cull,
                            &c->objects, &c->objectInverse, &c->tiles, &c->light, &c->atlasDepth, &c->sky};
     for (DeviceBuffer* b : all)
         b->release();
+    releaseSdfTextures(*c);
     for (auto& ev : c->ev)
         if (ev)
             cudaEventDestroy(ev);
@@ -503,7 +572,7 @@ int lux_ddgi_set_uniform(LuxDDGIContext* c, const LuxDDGIUniform* u)
     if (rc != LUX_OK)
         return rc;
     c->uniform = *u;
-    return LUX_OK;
+    return updateOrigins(*c);
 }
 
 int lux_ddgi_set_global_sdf(LuxDDGIContext* c, const LuxGlobalSDFData* data, const void* sdf, const void* mip, LuxMemKind kind)
@@ -522,6 +591,15 @@ int lux_ddgi_set_global_sdf(LuxDDGIContext* c, const LuxGlobalSDFData* data, con
     int rc;
     if ((rc = upload(*c, c->sdf, sdf, n * 2, kind)) != LUX_OK) return rc;
     if ((rc = upload(*c, c->mip, mip, nm * 2, kind)) != LUX_OK) return rc;
+    releaseSdfTextures(*c);
+    if ((c->flags & LUX_DDGI_FLAG_SDF_TEXTURE) && !(c->flags & LUX_DDGI_FLAG_TRACE_SIMPLE))
+    {
+        const int w = res * (int)data->cascadesCount, mw = (int)mres * (int)data->cascadesCount;
+        if (res > 2048)
+            return fail(LUX_ERR_UNSUPPORTED, "layered SDF textures support at most 2048 z-slices");
+        if ((rc = makeLayeredTexture(*c, c->sdf.ptr, w, res, res, &c->sdfArray, &c->sdfTex)) != LUX_OK) return rc;
+        if ((rc = makeLayeredTexture(*c, c->mip.ptr, mw, (int)mres, (int)mres, &c->mipArray, &c->mipTex)) != LUX_OK) return rc;
+    }
     if (kind == LUX_MEM_HOST)
         LUX_CUDA(cudaStreamSynchronize(c->stream)); // the caller may free its buffers on return
     c->sdfData = *data;

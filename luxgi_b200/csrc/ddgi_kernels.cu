@@ -549,6 +549,491 @@ __global__ void __launch_bounds__(32 * TRACE_RAYS_PER_BLOCK) trace_kernel(const 
 }
 
 // =====================================================================================================================
+// Trace, wavefront form
+// =====================================================================================================================
+//
+// Same arithmetic as trace_kernel, restructured for SIMT convergence (ncu on the simple kernel, C4: 7 of 32 lanes
+// active on average; 11/32 in the march loop, 2/32 in the surface-cache loops — profiles/r1_v1_*):
+//   * a warp owns a pool of 32 probes x TW_RAYS_PER_UNIT directions and its lanes REFILL from the pool as their rays
+//     terminate, so the march loop always runs (almost) full; lanes that refill together take adjacent probes with the
+//     same direction, which keeps their SDF taps on neighbouring rows;
+//   * hits are not shaded where they occur: they go to a per-warp shared-memory queue and are shaded 32 at a time;
+//   * surface-cache sampling first SCANS the chunk's object list for candidates and then loops over candidates and
+//     tiles, so the expensive tile code is entered by all lanes together.  Tile contributions are accumulated in the
+//     reference's (object, tile) order; skipped terms are exact zeros, so the sums are bit-identical.
+
+constexpr int TW_RAYS_PER_UNIT = 16;
+constexpr int TW_MAX_CAND      = 8;
+constexpr int CAND_STRIDE      = 256; // candidate scratch is [TW_MAX_CAND][256 threads]: conflict-free per lane
+
+template <bool TEX>
+struct SdfSampler;
+
+template <>
+struct SdfSampler<false>
+{
+    SdfVolume tex, mip;
+    __device__ __forceinline__ SdfSampler(const TraceParams& P)
+        : tex{P.tex, P.res * P.cascades, P.res, P.res}, mip{P.mip, P.mipRes * P.cascades, P.mipRes, P.mipRes} {}
+    __device__ __forceinline__ float sampleTex(float u, float v, float w) const { return sample3D(tex, u, v, w); }
+    __device__ __forceinline__ float sampleMip(float u, float v, float w) const { return sample3D(mip, u, v, w); }
+};
+
+// tld4 on a layered 2-D texture: the four texels of the bilinear footprint at (x, y) of `layer`, as
+// .x=(i0,j1) .y=(i1,j1) .z=(i1,j0) .w=(i0,j0).  Coordinates are unnormalised; clamp addressing.
+__device__ __forceinline__ float4 gather_layer(cudaTextureObject_t tex, float x, float y, int layer)
+{
+    float4 r;
+    asm("tld4.r.a2d.v4.f32.f32 {%0, %1, %2, %3}, [%4, {%5, %6, %7, %7}];"
+        : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+        : "l"(tex), "r"(layer), "f"(x), "f"(y));
+    return r;
+}
+
+// Trilinear tap through two layered gathers: the texture unit does addressing, clamping and fp16 decode, the lerps
+// stay in fp32 ALU with the oracle's weights (hardware filtering would quantise them to 8 bits).
+__device__ __forceinline__ float sample3D_tex(cudaTextureObject_t obj, int W, int H, int D, float u, float v, float w)
+{
+    float x = u * (float)W - 0.5f, y = v * (float)H - 0.5f, z = w * (float)D - 0.5f;
+    float fx = floorf(x), fy = floorf(y), fz = floorf(z);
+    float ax = x - fx, ay = y - fy, az = z - fz;
+    int   iz = (int)fz;
+    int   z0 = iclamp(iz, 0, D - 1), z1 = iclamp(iz + 1, 0, D - 1);
+    // the corner shared by texels (ix, ix+1) x (iy, iy+1): an exact coordinate, so the footprint is unambiguous
+    float gx = fx + 1.0f, gy = fy + 1.0f;
+    float4 a = gather_layer(obj, gx, gy, z0);
+    float4 b = gather_layer(obj, gx, gy, z1);
+    float c00 = lerp1(a.w, a.z, ax);
+    float c10 = lerp1(a.x, a.y, ax);
+    float c01 = lerp1(b.w, b.z, ax);
+    float c11 = lerp1(b.x, b.y, ax);
+    float c0  = lerp1(c00, c10, ay);
+    float c1  = lerp1(c01, c11, ay);
+    return lerp1(c0, c1, az);
+}
+
+template <>
+struct SdfSampler<true>
+{
+    cudaTextureObject_t tex, mip;
+    int                 tw, th, mw, mh;
+    __device__ __forceinline__ SdfSampler(const TraceParams& P)
+        : tex(P.texObj), mip(P.mipObj), tw(P.res * P.cascades), th(P.res), mw(P.mipRes * P.cascades), mh(P.mipRes) {}
+    __device__ __forceinline__ float sampleTex(float u, float v, float w) const { return sample3D_tex(tex, tw, th, th, u, v, w); }
+    __device__ __forceinline__ float sampleMip(float u, float v, float w) const { return sample3D_tex(mip, mw, mh, mh, u, v, w); }
+};
+
+// One tile of one candidate object, split in two: the normal weight (cheap, rejects most tiles) ...
+__device__ __forceinline__ float tile_normal_weight(const LuxTileBuffer* __restrict__ tile, f3 normal, float* tm)
+{
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+    {
+        float4 c = __ldg(reinterpret_cast<const float4*>(tile->transform) + i);
+        tm[i * 4 + 0] = c.x; tm[i * 4 + 1] = c.y; tm[i * 4 + 2] = c.z; tm[i * 4 + 3] = c.w;
+    }
+    f3    nt = normalize3(mat4_mul_point(tm, normal, 1.0f));
+    float nw = gclamp(nt.z, 0.0f, 1.0f);
+    return __fdiv_rn(nw - LUX_SURFACE_ATLAS_TILE_NORMAL_THRESHOLD, 1.0f - LUX_SURFACE_ATLAS_TILE_NORMAL_THRESHOLD);
+}
+
+// ... and the depth-tested bilinear sample (AtlasCommon.glsl:62-96)
+__device__ __forceinline__ f4 tile_sample(const TraceParams& P, const LuxTileBuffer* __restrict__ tile, const float* tm,
+                                          f3 localPosition, float normalWeight, float surfaceThreshold)
+{
+    float4 ext = __ldg(reinterpret_cast<const float4*>(tile->extends));
+    float4 ob  = __ldg(reinterpret_cast<const float4*>(tile->objectBounds));
+    f3     tp  = mat4_mul_point(tm, localPosition, 1.0f);
+    float  tileDepth = __fdiv_rn(tp.z, ob.z);
+    float  tu = gclamp(__fdiv_rn(tp.x, ob.x) + 0.5f, 0.0f, 1.0f);
+    float  tv = gclamp(__fdiv_rn(tp.y, ob.y) + 0.5f, 0.0f, 1.0f);
+    float  au = tu * ext.z + ext.x, av = tv * ext.w + ext.y;
+    float  res = (float)P.atlasRes;
+    float  fx = gfract(au * res + 0.5f), fy = gfract(av * res + 0.5f);
+    f4     bw = {(1.0f - fx) * fy, fx * fy, fx * (1.0f - fy), (1.0f - fx) * (1.0f - fy)};
+
+    int R = (int)P.atlasRes, i0, i1, j0, j1;
+    gather_coords(au, av, R, R, false, i0, i1, j0, j1);
+    float z4[4] = {__ldg(P.depth + (size_t)j1 * R + i0), __ldg(P.depth + (size_t)j1 * R + i1), __ldg(P.depth + (size_t)j0 * R + i1),
+                   __ldg(P.depth + (size_t)j0 * R + i0)};
+    float depthThreshold = __fdiv_rn(2.0f * surfaceThreshold, ob.z);
+    float vis[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+    {
+        vis[i] = 1.0f - gclamp(__fdiv_rn(fabsf(tileDepth - z4[i]) - depthThreshold, 0.5f * depthThreshold), 0.0f, 1.0f);
+        if (z4[i] >= 1.0f)
+            vis[i] = 0.0f;
+    }
+    f4    visv = {vis[0], vis[1], vis[2], vis[3]};
+    float sampleWeight = dot4(visv, bw);
+    sampleWeight *= normalWeight;
+    if (sampleWeight <= 0.0f)
+        return {0.0f, 0.0f, 0.0f, 0.0f};
+    bw = {bw.x * visv.x, bw.y * visv.y, bw.z * visv.z, bw.w * visv.w};
+    gather_coords(au, av, R, R, true, i0, i1, j0, j1);
+    f4 t0 = unpack_rgba16f(__ldg(P.light + (size_t)j1 * R + i0));
+    f4 t1 = unpack_rgba16f(__ldg(P.light + (size_t)j1 * R + i1));
+    f4 t2 = unpack_rgba16f(__ldg(P.light + (size_t)j0 * R + i1));
+    f4 t3 = unpack_rgba16f(__ldg(P.light + (size_t)j0 * R + i0));
+    float cr = dot4({t0.x, t1.x, t2.x, t3.x}, bw);
+    float cg = dot4({t0.y, t1.y, t2.y, t3.y}, bw);
+    float cb = dot4({t0.z, t1.z, t2.z, t3.z}, bw);
+    return {cr * sampleWeight, cg * sampleWeight, cb * sampleWeight, sampleWeight};
+}
+
+__device__ __forceinline__ void load_object_inverse(const TraceParams& P, uint32_t objectAddress, float* wl)
+{
+    const float4* invp = reinterpret_cast<const float4*>(P.objectInverse + (size_t)objectAddress * 16);
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+    {
+        float4 c = __ldg(invp + i);
+        wl[i * 4 + 0] = c.x; wl[i * 4 + 1] = c.y; wl[i * 4 + 2] = c.z; wl[i * 4 + 3] = c.w;
+    }
+}
+
+// AtlasCommon.glsl:115-157 in scan-then-shade form.  `cand` is this lane's candidate scratch in shared memory.
+__device__ __forceinline__ f4 sample_global_surface_atlas_2p(const TraceParams& P, f3 worldPosition, f3 worldNormal,
+                                                             float surfaceThreshold, uint32_t* cand)
+{
+    f4 result = {0.0f, 0.0f, 0.0f, 0.0f};
+    if (!P.hasAtlas)
+        return result;
+    const float half = (float)LUX_SURFACE_ATLAS_CHUNKS_RESOLUTION * 0.5f;
+    const int   N    = LUX_SURFACE_ATLAS_CHUNKS_RESOLUTION;
+    int cx = iclamp((int)floorf(__fdiv_rn(worldPosition.x, P.chunkSize) + half), 0, N - 1);
+    int cy = iclamp((int)floorf(__fdiv_rn(worldPosition.y, P.chunkSize) + half), 0, N - 1);
+    int cz = iclamp((int)floorf(__fdiv_rn(worldPosition.z, P.chunkSize) + half), 0, N - 1);
+    uint32_t objectsStart = __ldg(P.chunks + (cz * N * N + cy * N + cx));
+    if (objectsStart == 0)
+        return result;
+    uint32_t objectsCount = __ldg(P.cull + objectsStart);
+    if (objectsCount > P.objectsCount)
+        return result;
+    objectsStart++;
+    uint32_t k = 0;
+    while (k < objectsCount)
+    {
+        // ---- scan: bounding sphere + OBB tests only, in list order ----
+        int nc = 0;
+        while (k < objectsCount && nc < TW_MAX_CAND)
+        {
+            uint32_t objectAddress = __ldg(P.cull + objectsStart + k);
+            k++;
+            const LuxObjectBuffer* object = P.objects + objectAddress;
+            float4 ob = __ldg(reinterpret_cast<const float4*>(object->objectBounds));
+            f3     bc = {ob.x, ob.y, ob.z};
+            if (length3(bc - worldPosition) > ob.w)
+                continue;
+            float wl[16];
+            load_object_inverse(P, objectAddress, wl);
+            f3     lp = mat4_mul_point(wl, worldPosition, 1.0f);
+            float4 ex = __ldg(reinterpret_cast<const float4*>(object->extends));
+            if (fabsf(lp.x) > ex.x + surfaceThreshold || fabsf(lp.y) > ex.y + surfaceThreshold || fabsf(lp.z) > ex.z + surfaceThreshold)
+                continue;
+            cand[(nc++) * CAND_STRIDE] = objectAddress;
+        }
+        // ---- shade the candidates, tiles in order ----
+        for (int c = 0; c < nc; c++)
+        {
+            uint32_t objectAddress = cand[c * CAND_STRIDE];
+            const LuxObjectBuffer* object = P.objects + objectAddress;
+            float wl[16];
+            load_object_inverse(P, objectAddress, wl);
+            f3 localPosition = mat4_mul_point(wl, worldPosition, 1.0f);
+            f3 normal        = normalize3(mat3_mul(wl, worldNormal));
+#pragma unroll 1
+            for (int i = 0; i < 6; i++)
+            {
+                uint32_t tileOffset = __ldg(object->tileOffset + i);
+                if (tileOffset == 0)
+                    continue;
+                float tm[16];
+                const LuxTileBuffer* tile = P.tiles + tileOffset;
+                float nw = tile_normal_weight(tile, normal, tm);
+                if (nw <= 0.0f)
+                    continue;
+                f4 s = tile_sample(P, tile, tm, localPosition, nw, surfaceThreshold);
+                result.x += s.x; result.y += s.y; result.z += s.z; result.w += s.w;
+            }
+        }
+    }
+    float d = gmax(result.w, 0.0001f);
+    result.x = __fdiv_rn(result.x, d);
+    result.y = __fdiv_rn(result.y, d);
+    result.z = __fdiv_rn(result.z, d);
+    return result;
+}
+
+__device__ __forceinline__ f3 probe_origin(const TraceParams& P, int probeId)
+{
+    int cx = probeId % P.countX;
+    int cy = (probeId % (P.countX * P.countY)) / P.countX;
+    int cz = probeId / (P.countX * P.countY);
+    return {P.step[0] * (float)cx + P.start[0], P.step[1] * (float)cy + P.start[1], P.step[2] * (float)cz + P.start[2]};
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Stage 1 of the wavefront trace: MARCH.  Persistent warps pull chunks of rays from a global counter; lanes refill
+// from the warp's pool in batches (so ray setup also runs on many lanes) and every loop iteration is one sphere-trace
+// step for all active lanes.  A finished ray leaves a 20-byte record (hit time, hit uvw, cascade, kind, steps);
+// nothing is shaded here, which keeps the register count low and the occupancy high.
+//
+// Ray index g enumerates [probeGroup][rayGroup][rayInUnit (16)][probeLane (32)], so lanes that refill together take
+// adjacent probes with the same direction.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int MARCH_WARPS       = 8;
+constexpr int MARCH_CHUNK_UNITS = 2;                                       // units (32 probes x 16 rays) per pool fetch
+constexpr int UNIT_RAYS         = 32 * TW_RAYS_PER_UNIT;                   // 512
+constexpr int MARCH_REFILL_MIN  = 8;                                       // refill when this many lanes are idle
+
+enum RayKind : uint32_t { RAY_MISS = 0, RAY_INSIDE = 1, RAY_HIT = 2 };
+
+template <bool TEX>
+__global__ void __launch_bounds__(32 * MARCH_WARPS, 3) march_kernel(const __grid_constant__ TraceParams P, int numChunks, int rayGroups,
+                                                                    unsigned int* __restrict__ chunkCounter)
+{
+    const int      lane = threadIdx.x & 31;
+    const unsigned FULL = 0xffffffffu;
+    const SdfSampler<TEX> sdf(P);
+    const LuxGlobalSDFData& data = P.sdf;
+
+    const float traceMaxDistance    = gmin(LUX_GLOBAL_SDF_WORLD_SIZE, data.cascadePosDistance[data.cascadesCount - 1][3] * 2.0f);
+    const float chunkSizeDistance   = __fdiv_rn((float)LUX_GLOBAL_SDF_RASTERIZE_CHUNK_SIZE, data.resolution);
+    const float chunkMarginDistance = __fdiv_rn((float)LUX_GLOBAL_SDF_RASTERIZE_CHUNK_MARGIN, data.resolution);
+    const float cascadesCountF      = (float)data.cascadesCount;
+
+    long long poolNext = 0, poolEnd = 0; // warp-uniform
+    bool      exhausted = false;
+
+    // per-lane ray state
+    bool      active = false;
+    long long g = 0;
+    f3        origin = {0, 0, 0}, dir = {0, 0, 0}, traceEnd = {0, 0, 0}, cc = {0, 0, 0};
+    uint32_t  cascade = 0, step = 0, totalSteps = 0;
+    float     stepTime = 0.0f, farT = 0.0f, nextIntersectionStart = 0.0f, cd = 0.0f, voxelSize = 0.0f;
+
+    auto begin_cascade = [&]() {
+        cc        = {data.cascadePosDistance[cascade][0], data.cascadePosDistance[cascade][1], data.cascadePosDistance[cascade][2]};
+        cd        = data.cascadePosDistance[cascade][3];
+        voxelSize = data.cascadeVoxelSize[cascade];
+        f3    worldPosition = origin + dir * (voxelSize * 0.0f); // cascadeTraceStartBias = 0
+        f3    ext = {cd, cd, cd};
+        float nearT, fT;
+        line_hit_aabb(worldPosition, traceEnd, cc - ext, cc + ext, nearT, fT);
+        nearT *= traceMaxDistance;
+        fT *= traceMaxDistance;
+        nearT    = gmax(nearT, nextIntersectionStart);
+        stepTime = nearT;
+        if (nearT >= fT)
+            stepTime = fT;
+        else
+            nextIntersectionStart = fT;
+        farT = fT;
+        step = 0;
+    };
+    auto finish = [&](uint32_t kind, float hitTime, f3 uvw) {
+        P.records[g] = make_float4(hitTime, uvw.x, uvw.y, uvw.z);
+        P.meta[g]    = cascade | (kind << 2) | (totalSteps << 4);
+        active       = false;
+    };
+
+    while (true)
+    {
+        // ---- refill idle lanes, in batches ----
+        unsigned idle = __ballot_sync(FULL, !active);
+        if (idle && (__popc(idle) >= MARCH_REFILL_MIN || idle == FULL) && !exhausted)
+        {
+            if (poolNext >= poolEnd)
+            { // fetch the next chunk of rays
+                unsigned int c = 0;
+                if (lane == 0)
+                    c = atomicAdd(chunkCounter, 1u);
+                c = __shfl_sync(FULL, c, 0);
+                if ((int)c >= numChunks)
+                    exhausted = true;
+                else
+                {
+                    poolNext = (long long)c * (MARCH_CHUNK_UNITS * UNIT_RAYS);
+                    poolEnd  = poolNext + MARCH_CHUNK_UNITS * UNIT_RAYS;
+                }
+            }
+            if (!exhausted)
+            {
+                const long long base = poolNext;
+                const int avail = (int)min((long long)__popc(idle), poolEnd - poolNext);
+                poolNext += avail;
+                const int rank = __popc(idle & ((1u << lane) - 1u));
+                if (!active && rank < avail)
+                {
+                    g = base + rank;
+                    const long long unit = g / UNIT_RAYS;
+                    const int rem = (int)(g % UNIT_RAYS);
+                    const int probeLocal = (int)(unit / rayGroups) * 32 + (rem & 31);
+                    const int rayId      = (int)(unit % rayGroups) * TW_RAYS_PER_UNIT + (rem >> 5);
+                    if (probeLocal < P.probeCount && rayId < P.raysPerProbe)
+                    {
+                        float4 o4 = __ldg(P.origins + probeLocal);
+                        float4 d4 = __ldg(P.dirs + rayId);
+                        origin    = {o4.x, o4.y, o4.z};
+                        dir       = {d4.x, d4.y, d4.z};
+                        traceEnd  = origin + dir * traceMaxDistance;
+                        cascade   = 0;
+                        totalSteps = 0;
+                        nextIntersectionStart = 0.0f;
+                        begin_cascade();
+                        active = true;
+                    }
+                }
+            }
+        }
+        if (!__any_sync(FULL, active))
+        {
+            if (exhausted)
+                break;
+            continue;
+        }
+
+        // ---- one march iteration for every active lane (SDFCommon.glsl:143-190) ----
+        if (active)
+        {
+            if (!(step < LUX_GLOBAL_SDF_MAX_STEPS && stepTime < farT))
+            {
+                totalSteps += step;
+                if (cascade + 1 < data.cascadesCount)
+                {
+                    cascade++;
+                    begin_cascade();
+                }
+                else
+                    finish(RAY_MISS, -1.0f, {0.0f, 0.0f, 0.0f});
+            }
+            else
+            {
+                f3 stepPosition = origin + dir * stepTime;
+                f3 pc           = stepPosition - cc;
+                float cascadeMaxDistance = cd * 2.0f;
+                f3 cuv = {gclamp(__fdiv_rn(pc.x, cascadeMaxDistance) + 0.5f, 0.0f, 1.0f),
+                          gclamp(__fdiv_rn(pc.y, cascadeMaxDistance) + 0.5f, 0.0f, 1.0f),
+                          gclamp(__fdiv_rn(pc.z, cascadeMaxDistance) + 0.5f, 0.0f, 1.0f)};
+                f3 uvw = {__fdiv_rn((float)cascade + cuv.x, cascadesCountF), cuv.y, cuv.z};
+                float stepDistance = sdf.sampleMip(uvw.x, uvw.y, uvw.z);
+                if (stepDistance < chunkSizeDistance)
+                {
+                    float stepDistanceTex = sdf.sampleTex(uvw.x, uvw.y, uvw.z);
+                    if (stepDistanceTex < chunkMarginDistance * 2.0f)
+                        stepDistance = stepDistanceTex;
+                }
+                else
+                    stepDistance = chunkSizeDistance;
+                stepDistance *= cascadeMaxDistance;
+                float voxelHalf = voxelSize * 0.5f;
+                float minSurfaceThickness = voxelHalf * gclamp(__fdiv_rn(stepTime, voxelSize), 0.0f, 1.0f);
+                if (stepDistance < minSurfaceThickness)
+                {
+                    float hitTime = gmax((stepTime + stepDistance) - minSurfaceThickness, 0.0f);
+                    totalSteps += step;
+                    // probe inside geometry (GISDFRays.comp:93-96) needs neither normal nor surface cache
+                    bool inside = (stepDistance <= 0.0f && hitTime <= data.cascadeVoxelSize[0]);
+                    finish(inside ? RAY_INSIDE : RAY_HIT, hitTime, uvw);
+                }
+                else
+                {
+                    stepTime += gmax(stepDistance * 1.0f, voxelSize);
+                    step++;
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Stage 2: SHADE.  One thread per ray record, in the same [32 probes] x [8 rays] tiling as the simple kernel, so a warp
+// holds hits of parallel rays from adjacent probes (same building face, same culling chunk most of the time).
+// Misses take the sky, inside-geometry rays are black, hits get their normal (six taps) and surface-cache radiance.
+// ---------------------------------------------------------------------------------------------------------------------
+template <bool TEX>
+__global__ void __launch_bounds__(256) shade_kernel(const __grid_constant__ TraceParams P, int rayGroups)
+{
+    __shared__ uint2    sRad[32][TRACE_RAYS_PER_BLOCK + 1];
+    __shared__ uint2    sDir[32][TRACE_RAYS_PER_BLOCK + 1];
+    __shared__ uint32_t sCand[TW_MAX_CAND][CAND_STRIDE];
+
+    const int lane = threadIdx.x & 31, sub = threadIdx.x >> 5; // sub = ray within the block's 8
+    // block b covers half a unit: unit = b / 2, rays (b & 1) * 8 .. + 8 of the unit's 16
+    const long long unit = blockIdx.x >> 1;
+    const int rayInUnit  = ((blockIdx.x & 1) << 3) + sub;
+    const long long g    = unit * UNIT_RAYS + rayInUnit * 32 + lane;
+    const int probeLocal = (int)(unit / rayGroups) * 32 + lane;
+    const int rayId      = (int)(unit % rayGroups) * TW_RAYS_PER_UNIT + rayInUnit;
+    const bool valid     = probeLocal < P.probeCount && rayId < P.raysPerProbe;
+    const SdfSampler<TEX> sdf(P);
+    const LuxGlobalSDFData& data = P.sdf;
+
+    if (valid)
+    {
+        const float4   rec  = __ldg(P.records + g);
+        const uint32_t meta = __ldg(P.meta + g);
+        const uint32_t hc = meta & 3u, kind = (meta >> 2) & 3u;
+        float4 d4 = __ldg(P.dirs + rayId);
+        f3     d  = {d4.x, d4.y, d4.z};
+        f4     radiance;
+        if (kind == RAY_HIT)
+        {
+            float4 o4 = __ldg(P.origins + probeLocal);
+            f3     o  = {o4.x, o4.y, o4.z};
+            const float texelOffset = __fdiv_rn(1.0f, data.resolution);
+            float xp = sdf.sampleTex(rec.y + texelOffset, rec.z, rec.w);
+            float xn = sdf.sampleTex(rec.y - texelOffset, rec.z, rec.w);
+            float yp = sdf.sampleTex(rec.y, rec.z + texelOffset, rec.w);
+            float yn = sdf.sampleTex(rec.y, rec.z - texelOffset, rec.w);
+            float zp = sdf.sampleTex(rec.y, rec.z, rec.w + texelOffset);
+            float zn = sdf.sampleTex(rec.y, rec.z, rec.w - texelOffset);
+            f3    normal = normalize3({xp - xn, yp - yn, zp - zn});
+            f3    hitPosition      = o + d * rec.x;
+            float surfaceThreshold = data.cascadeVoxelSize[hc] * 1.05f;
+            f4    sc = sample_global_surface_atlas_2p(P, hitPosition, normal, surfaceThreshold, &sCand[0][threadIdx.x]);
+            radiance   = {sc.x, sc.y, sc.z, rec.x};
+            radiance.w = gmax(radiance.w + data.cascadeVoxelSize[hc] * 0.5f, 0.0f);
+        }
+        else if (kind == RAY_INSIDE)
+            radiance = {0.0f, 0.0f, 0.0f, LUX_GLOBAL_SDF_WORLD_SIZE};
+        else
+        {
+            f3 s     = sample_sky(P, d);
+            radiance = {s.x, s.y, s.z, LUX_GLOBAL_SDF_WORLD_SIZE};
+        }
+        uint32_t r0 = f2h_bits(radiance.x), r1 = f2h_bits(radiance.y), r2 = f2h_bits(radiance.z);
+        uint32_t d0 = f2h_bits(d.x), d1 = f2h_bits(d.y), d2 = f2h_bits(d.z), d3 = f2h_bits(radiance.w);
+        sRad[lane][sub] = make_uint2(r0 | (r1 << 16), r2);
+        sDir[lane][sub] = make_uint2(d0 | (d1 << 16), d2 | (d3 << 16));
+        if (P.steps)
+            P.steps[(size_t)probeLocal * P.raysPerProbe + rayId] = (uint16_t)(meta >> 4);
+    }
+    __syncthreads();
+    // transposed write-out: 8 consecutive rays (64 bytes) per probe
+    const int pl = threadIdx.x / TRACE_RAYS_PER_BLOCK, rl = threadIdx.x % TRACE_RAYS_PER_BLOCK;
+    const int oProbe = (int)(unit / rayGroups) * 32 + pl;
+    const int oRay   = (int)(unit % rayGroups) * TW_RAYS_PER_UNIT + ((blockIdx.x & 1) << 3) + rl;
+    if (oProbe < P.probeCount && oRay < P.raysPerProbe)
+    {
+        size_t o = (size_t)oProbe * P.raysPerProbe + oRay;
+        P.radiance[o] = sRad[pl][rl];
+        P.dirDist[o]  = sDir[pl][rl];
+    }
+}
+
+__global__ void probe_origins_kernel(const TraceParams P, float4* __restrict__ origins)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.probeCount)
+        return;
+    f3 o = probe_origin(P, P.probeBegin + i);
+    origins[i] = make_float4(o.x, o.y, o.z, 0.0f);
+}
+
+// =====================================================================================================================
 // Blend (+ fused border)
 // =====================================================================================================================
 //
@@ -825,11 +1310,49 @@ void launch_object_inverse(const LuxObjectBuffer* objects, int count, float* inv
         object_inverse_kernel<<<(count + 127) / 128, 128, 0, s>>>(objects, count, inv);
 }
 
-void launch_trace(const TraceParams& p, bool /*useTexture*/, cudaStream_t s)
+size_t trace_record_count(int probeCount, int raysPerProbe)
 {
-    dim3 block(32, TRACE_RAYS_PER_BLOCK);
-    dim3 grid((p.raysPerProbe + TRACE_RAYS_PER_BLOCK - 1) / TRACE_RAYS_PER_BLOCK, (p.probeCount + 31) / 32);
-    trace_kernel<<<grid, block, 0, s>>>(p);
+    const long long rayGroups   = (raysPerProbe + TW_RAYS_PER_UNIT - 1) / TW_RAYS_PER_UNIT;
+    const long long probeGroups = (probeCount + 31) / 32;
+    const long long units       = rayGroups * probeGroups;
+    const long long chunks      = (units + MARCH_CHUNK_UNITS - 1) / MARCH_CHUNK_UNITS;
+    return (size_t)(chunks * MARCH_CHUNK_UNITS * UNIT_RAYS);
+}
+
+void launch_probe_origins(const TraceParams& p, cudaStream_t s)
+{
+    probe_origins_kernel<<<(p.probeCount + 255) / 256, 256, 0, s>>>(p, const_cast<float4*>(p.origins));
+}
+
+int launch_trace(const TraceParams& p, int variant, unsigned int* chunkCounter, cudaStream_t s)
+{
+    if (variant == 0)
+    {
+        dim3 block(32, TRACE_RAYS_PER_BLOCK);
+        dim3 grid((p.raysPerProbe + TRACE_RAYS_PER_BLOCK - 1) / TRACE_RAYS_PER_BLOCK, (p.probeCount + 31) / 32);
+        trace_kernel<<<grid, block, 0, s>>>(p);
+        return 1;
+    }
+    const int rayGroups   = (p.raysPerProbe + TW_RAYS_PER_UNIT - 1) / TW_RAYS_PER_UNIT;
+    const int probeGroups = (p.probeCount + 31) / 32;
+    const long long units = (long long)rayGroups * probeGroups;
+    const int chunks      = (int)((units + MARCH_CHUNK_UNITS - 1) / MARCH_CHUNK_UNITS);
+    cudaMemsetAsync(chunkCounter, 0, sizeof(unsigned int), s);
+    long long blocks = ((long long)chunks + MARCH_WARPS - 1) / MARCH_WARPS;
+    const long long persistent = 148ll * 3; // one resident generation: 3 blocks of 8 warps per SM
+    if (blocks > persistent)
+        blocks = persistent;
+    if (variant == 2)
+    {
+        march_kernel<true><<<(unsigned)blocks, 32 * MARCH_WARPS, 0, s>>>(p, chunks, rayGroups, chunkCounter);
+        shade_kernel<true><<<(unsigned)(units * 2), 256, 0, s>>>(p, rayGroups);
+    }
+    else
+    {
+        march_kernel<false><<<(unsigned)blocks, 32 * MARCH_WARPS, 0, s>>>(p, chunks, rayGroups, chunkCounter);
+        shade_kernel<false><<<(unsigned)(units * 2), 256, 0, s>>>(p, rayGroups);
+    }
+    return 2;
 }
 
 template <int PB>
@@ -895,6 +1418,6 @@ void launch_border(uint2* irr, int irrWidth, uint32_t* depth, int depthWidth, in
     }
 }
 
-int kernels_per_update(bool fusedBorder) { return fusedBorder ? 6 : 8; } // dirs, trace, weights, scales, 2 blends (+2 borders)
+
 
 } // namespace lux

@@ -38,6 +38,9 @@ struct TraceParams
     const uint2* sky; // [6][n][n] RGBA16F or null
     // rays
     const float4* dirs;     // [R] normalize(mat3(rot) * sphericalFibonacci(r, R))
+    const float4* origins;  // [probeCount] probeLocation of this shard's probes
+    float4*       records;  // wavefront trace: per ray (hitTime, hit u, v, w), indexed [probeGroup][rayGroup][16][32]
+    uint32_t*     meta;     // wavefront trace: cascade | kind << 2 | steps << 4
     uint2*        radiance; // [probeCount][R] RGBA16F
     uint2*        dirDist;  // [probeCount][R] RGBA16F
     uint16_t*     steps;    // optional [probeCount][R] march-step counts (debug / roofline counters)
@@ -70,12 +73,15 @@ void launch_blend_weights(const uint2* dirDistRow0, int raysPerProbe, int raysPa
                           float* scaleIrr, float* scaleDepth, cudaStream_t s);
 void launch_object_inverse(const LuxObjectBuffer* objects, int count, float* inv, cudaStream_t s);
 
-void launch_trace(const TraceParams& p, bool useTexture, cudaStream_t s);
+// variant 0: one thread per ray (simple); 1: wavefront (march + shade), explicit fp16 loads; 2: wavefront, layered-texture
+// gathers.  Returns the number of kernels launched.
+int    launch_trace(const TraceParams& p, int variant, unsigned int* chunkCounter, cudaStream_t s);
+size_t trace_record_count(int probeCount, int raysPerProbe);
+void   launch_probe_origins(const TraceParams& p, cudaStream_t s);
 void launch_blend_irradiance(const BlendParams& p, cudaStream_t s);
 void launch_blend_depth(const BlendParams& p, cudaStream_t s);
 void launch_border(uint2* irr, int irrWidth, uint32_t* depth, int depthWidth, int probesPerRow, int probeBegin, int probeCount,
                    cudaStream_t s);
 
-int kernels_per_update(bool fusedBorder);
 
 } // namespace lux

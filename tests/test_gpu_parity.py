@@ -204,3 +204,33 @@ def test_restore_resumes_bit_identically():
     assert np.array_equal(c.irradiance, a.irradiance) and np.array_equal(c.depth, a.depth)
     for p in (a, b, c):
         p.close()
+
+
+@pytest.mark.parametrize("flags,name", [(0, "wavefront+loads"), (abi.FLAG_SDF_TEXTURE, "wavefront+tld4"), (abi.FLAG_TRACE_SIMPLE, "simple")])
+@pytest.mark.parametrize("cfg", ["c1", "city64"])
+def test_trace_variants_match_oracle(oracle, flags, name, cfg):
+    """Every trace kernel variant (thread-per-ray, wavefront with explicit loads, wavefront with texture gathers)
+    must reproduce the oracle's ray buffers bit for bit."""
+    sc = scenes.build(cfg)
+    rots = [scenes.frame_rotation(f) for f in range(2)]
+    orc = oracle.OraclePipeline(sc)
+    for r in rots:
+        orc.update(r)
+    pipe = run_engine(sc, rots, flags=flags)
+    assert_rays_match(pipe, orc)
+    assert_atlases_match(pipe, orc)
+    pipe.close()
+
+
+def test_ragged_sizes(oracle):
+    """Probe count not a multiple of 32, rays not a multiple of 16/32, non-cubic grid."""
+    sc = scenes.cornell_scene(res=32, counts=(3, 5, 2), rays=50, atlas_res=256)
+    rots = [scenes.frame_rotation(f) for f in range(2)]
+    orc = oracle.OraclePipeline(sc)
+    for r in rots:
+        orc.update(r)
+    for flags in (0, abi.FLAG_SDF_TEXTURE, abi.FLAG_TRACE_SIMPLE):
+        pipe = run_engine(sc, rots, flags=flags)
+        assert_rays_match(pipe, orc)
+        assert_atlases_match(pipe, orc)
+        pipe.close()
