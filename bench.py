@@ -210,7 +210,7 @@ def run_lux(args):
     if u.probeCounts[2] % world:
         raise SystemExit(f"{world} GPUs do not divide Z={u.probeCounts[2]}")
     stream = torch.cuda.Stream(device=dev)
-    flags = abi.FLAG_STAGE_TIMERS | {"wavefront": 0, "texture": abi.FLAG_SDF_TEXTURE, "simple": abi.FLAG_TRACE_SIMPLE}[args.trace]
+    flags = abi.FLAG_STAGE_TIMERS | {"texture": 0, "loads": abi.FLAG_SDF_LOADS, "simple": abi.FLAG_TRACE_SIMPLE}[args.trace]
     pipe = ddgi.DDGIPipeline(u, device=local, rank=rank, world=world, flags=flags, stream=stream.cuda_stream)
     pipe.set_scene(sc)
     st = pipe.state()
@@ -368,7 +368,8 @@ def main():
     ap.add_argument("--cpu-probes", type=int, default=4096)
     ap.add_argument("--reference-probes", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--trace", default="wavefront", choices=["wavefront", "texture", "simple"], help="trace kernel variant")
+    ap.add_argument("--trace", default="texture", choices=["texture", "loads", "simple"],
+                    help="SDF read path / trace kernel variant: wavefront + tld4 gathers (default), wavefront + fp16 loads, thread-per-ray")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--stage-every-step", action="store_true", help="sync + read stage timers every step (perturbs the total)")
     args = ap.parse_args()

@@ -168,9 +168,10 @@ enum {
     LUX_DDGI_FLAG_NONE          = 0,
     LUX_DDGI_FLAG_STAGE_TIMERS  = 1u << 0, /* record CUDA events around every stage (lux_ddgi_get_stage_ms)  */
     LUX_DDGI_FLAG_UNFUSED_BORDER= 1u << 1, /* probe_update writes interiors only; border_update does borders */
-    LUX_DDGI_FLAG_SDF_TEXTURE   = 1u << 2, /* read the SDF through layered texture-object gathers (tld4)     */
-    LUX_DDGI_FLAG_SDF_LOADS     = 1u << 3, /* read the SDF with explicit fp16 global loads                   */
-    LUX_DDGI_FLAG_TRACE_SIMPLE  = 1u << 4  /* one-thread-per-ray trace kernel (no wavefront scheduling), for A/B */
+    LUX_DDGI_FLAG_SDF_TEXTURE   = 1u << 2, /* require the layered-texture gather (tld4) SDF path (the default) */
+    LUX_DDGI_FLAG_SDF_LOADS     = 1u << 3, /* read the SDF with explicit fp16 global loads instead             */
+    LUX_DDGI_FLAG_TRACE_SIMPLE  = 1u << 4, /* one-thread-per-ray trace kernel (no wavefront scheduling), for A/B */
+    LUX_DDGI_FLAG_NO_PREFILTER  = 1u << 5  /* walk the full per-chunk object lists (no sub-cell candidate masks), for A/B */
 };
 
 typedef struct LuxDDGICreateInfo {

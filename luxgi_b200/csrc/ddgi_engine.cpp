@@ -97,7 +97,8 @@ struct LuxDDGIContext
     // surface cache
     bool                      hasAtlas = false;
     LuxGlobalSurfaceAtlasData atlasData{};
-    DeviceBuffer              chunks, cull, objects, objectInverse, tiles, light, atlasDepth;
+    DeviceBuffer              chunks, cull, objects, objectInverse, tiles, light, atlasDepth, chunkMasks;
+    bool                      masksDirty = true;
 
     // sky
     int          skyFace = 0;
@@ -290,6 +291,25 @@ static int system(LuxDDGIContext& c, const LuxTracePushConstants& push)
         return fail(LUX_ERR_NOT_READY, "trace_rays: no global SDF bound (lux_ddgi_set_global_sdf)");
     const LuxDDGIUniform& u = c.uniform;
 
+    if (c.hasAtlas && c.masksDirty && !(c.flags & LUX_DDGI_FLAG_NO_PREFILTER))
+    { // surface-cache prefilter: depends on the object lists and on the largest surfaceThreshold (1.05 * voxel)
+        float vmax = 0.0f;
+        for (uint32_t i = 0; i < c.sdfData.cascadesCount; i++)
+            vmax = std::fmax(vmax, c.sdfData.cascadeVoxelSize[i]);
+        const size_t bytes = (size_t)64000 * 64 * sizeof(unsigned long long);
+        if (c.chunkMasks.bytes != bytes)
+        {
+            c.chunkMasks.release();
+            LUX_CUDA(cudaMalloc(&c.chunkMasks.ptr, bytes));
+            c.chunkMasks.bytes = bytes;
+        }
+        launch_chunk_masks((const uint32_t*)c.chunks.ptr, (const uint32_t*)c.cull.ptr, (const LuxObjectBuffer*)c.objects.ptr,
+                           (const float*)c.objectInverse.ptr, c.atlasData.objectsCount, c.atlasData.chunkSize, 1.05f * vmax * 1.001f,
+                           (unsigned long long*)c.chunkMasks.ptr, c.stream);
+        c.launches += 1;
+        LUX_CUDA(cudaGetLastError());
+        c.masksDirty = false;
+    }
     mark(c, 0);
     launch_ray_dirs(push.randomOrientation, u.raysPerProbe, (float4*)c.dirs.ptr, c.stream);
     c.launches += 1;
@@ -315,6 +335,7 @@ static int system(LuxDDGIContext& c, const LuxTracePushConstants& push)
         p.cull          = (const uint32_t*)c.cull.ptr;
         p.objects       = (const LuxObjectBuffer*)c.objects.ptr;
         p.objectInverse = (const float*)c.objectInverse.ptr;
+        p.chunkMasks    = (c.flags & LUX_DDGI_FLAG_NO_PREFILTER) ? nullptr : (const unsigned long long*)c.chunkMasks.ptr;
         p.tiles         = (const LuxTileBuffer*)c.tiles.ptr;
         p.light         = (const uint2*)c.light.ptr;
         p.depth         = (const float*)c.atlasDepth.ptr;
@@ -545,7 +566,7 @@ int lux_ddgi_destroy(LuxDDGIContext* c)
     cudaStreamSynchronize(c->stream);
     DeviceBuffer* all[] = {&c->radiance, &c->directionDepth, &c->irradiance[0], &c->irradiance[1], &c->depth[0], &c->depth[1],
                            &c->dirs, &c->wIrr, &c->wDepth, &c->scaleIrr, &c->scaleDepth, &c->origins, &c->records, &c->meta, &c->chunkCounter, &c->sdf, &c->mip, &c->chunks, &c->cull,
-                           &c->objects, &c->objectInverse, &c->tiles, &c->light, &c->atlasDepth, &c->sky};
+                           &c->objects, &c->objectInverse, &c->chunkMasks, &c->tiles, &c->light, &c->atlasDepth, &c->sky};
     for (DeviceBuffer* b : all)
         b->release();
     releaseSdfTextures(*c);
@@ -592,18 +613,22 @@ int lux_ddgi_set_global_sdf(LuxDDGIContext* c, const LuxGlobalSDFData* data, con
     if ((rc = upload(*c, c->sdf, sdf, n * 2, kind)) != LUX_OK) return rc;
     if ((rc = upload(*c, c->mip, mip, nm * 2, kind)) != LUX_OK) return rc;
     releaseSdfTextures(*c);
-    if ((c->flags & LUX_DDGI_FLAG_SDF_TEXTURE) && !(c->flags & LUX_DDGI_FLAG_TRACE_SIMPLE))
+    // Default SDF path = layered-texture gathers (chosen by ncu, profiles/r1_*): falls back to explicit loads when asked to
+    // (LUX_DDGI_FLAG_SDF_LOADS), for the simple kernel, or when the volume has more z-slices than a layered array allows.
+    const bool wantTex = !(c->flags & (LUX_DDGI_FLAG_SDF_LOADS | LUX_DDGI_FLAG_TRACE_SIMPLE)) && res <= 2048;
+    if ((c->flags & LUX_DDGI_FLAG_SDF_TEXTURE) && res > 2048)
+        return fail(LUX_ERR_UNSUPPORTED, "layered SDF textures support at most 2048 z-slices");
+    if (wantTex)
     {
         const int w = res * (int)data->cascadesCount, mw = (int)mres * (int)data->cascadesCount;
-        if (res > 2048)
-            return fail(LUX_ERR_UNSUPPORTED, "layered SDF textures support at most 2048 z-slices");
         if ((rc = makeLayeredTexture(*c, c->sdf.ptr, w, res, res, &c->sdfArray, &c->sdfTex)) != LUX_OK) return rc;
         if ((rc = makeLayeredTexture(*c, c->mip.ptr, mw, (int)mres, (int)mres, &c->mipArray, &c->mipTex)) != LUX_OK) return rc;
     }
     if (kind == LUX_MEM_HOST)
         LUX_CUDA(cudaStreamSynchronize(c->stream)); // the caller may free its buffers on return
-    c->sdfData = *data;
-    c->hasSdf  = true;
+    c->sdfData    = *data;
+    c->hasSdf     = true;
+    c->masksDirty = true;
     return LUX_OK;
 }
 
@@ -643,8 +668,9 @@ int lux_ddgi_set_surface_atlas(LuxDDGIContext* c, const LuxGlobalSurfaceAtlasDat
     LUX_CUDA(cudaGetLastError());
     if (kind == LUX_MEM_HOST)
         LUX_CUDA(cudaStreamSynchronize(c->stream));
-    c->atlasData = *data;
-    c->hasAtlas  = true;
+    c->atlasData  = *data;
+    c->hasAtlas   = true;
+    c->masksDirty = true;
     return LUX_OK;
 }
 

@@ -164,6 +164,73 @@ __global__ void object_inverse_kernel(const LuxObjectBuffer* __restrict__ object
 #undef B
 }
 
+// Prefilter for the surface-cache object loop (AtlasCommon.glsl:125-139), built once per surface-cache upload.
+// One block per culling chunk, one thread per quarter-chunk sub-cell (4x4x4): bit j of the thread's 64-bit mask stays
+// set iff list entry j could pass BOTH the bounding-sphere test and the OBB-extent test for SOME point of the sub-cell
+// (expanded by eps; sub-cells on the outer faces of the 40^3 grid are unbounded because chunk coordinates are clamped).
+// thrMax = 1.05 * the largest cascade voxel size, the largest surfaceThreshold the trace can pass.
+__global__ void chunk_masks_kernel(const uint32_t* __restrict__ chunks, const uint32_t* __restrict__ cull,
+                                   const LuxObjectBuffer* __restrict__ objects, const float* __restrict__ objectInverse,
+                                   uint32_t objectsCountLimit, float chunkSize, float thrMax, unsigned long long* __restrict__ masks)
+{
+    const int N = LUX_SURFACE_ATLAS_CHUNKS_RESOLUTION;
+    const int chunk = blockIdx.x, sub = threadIdx.x;
+    const int cx = chunk % N, cy = (chunk / N) % N, cz = chunk / (N * N);
+    const int sx = sub & 3, sy = (sub >> 2) & 3, sz = sub >> 4;
+    unsigned long long mask = 0ull;
+    uint32_t start = chunks[chunk];
+    if (start != 0)
+    {
+        uint32_t count = cull[start];
+        if (count <= objectsCountLimit)
+        {
+            const float BIG = 1e18f, eps = 1e-3f * chunkSize, cell = chunkSize * 0.25f;
+            int   ci[3] = {cx, cy, cz}, si[3] = {sx, sy, sz};
+            float bc[3], hb[3];
+            for (int a = 0; a < 3; a++)
+            {
+                float lo = ((float)ci[a] - 0.5f * (float)N) * chunkSize + (float)si[a] * cell;
+                float hi = lo + cell;
+                bc[a] = 0.5f * (lo + hi);
+                hb[a] = 0.5f * cell + eps;
+                if ((ci[a] == 0 && si[a] == 0) || (ci[a] == N - 1 && si[a] == 3))
+                    hb[a] = BIG; // clamped chunk coordinate: the cell is unbounded outwards (inwards too, harmlessly)
+            }
+            uint32_t n = count < 64u ? count : 64u;
+            for (uint32_t j = 0; j < n; j++)
+            {
+                uint32_t     obj = cull[start + 1 + j];
+                const float* ob  = objects[obj].objectBounds;
+                float d2 = 0.0f;
+                for (int a = 0; a < 3; a++)
+                {
+                    float d = fabsf(ob[a] - bc[a]) - hb[a];
+                    d = d > 0.0f ? d : 0.0f;
+                    d2 += d * d;
+                }
+                float r = ob[3] + eps;
+                bool keep = d2 <= r * r;
+                if (keep)
+                {
+                    const float* W  = objectInverse + (size_t)obj * 16;
+                    const float* ex = objects[obj].extends;
+                    for (int i = 0; i < 3 && keep; i++)
+                    {
+                        float c = W[0 + i] * bc[0] + W[4 + i] * bc[1] + W[8 + i] * bc[2] + W[12 + i];
+                        float rr = fabsf(W[0 + i]) * hb[0] + fabsf(W[4 + i]) * hb[1] + fabsf(W[8 + i]) * hb[2];
+                        rr += 1e-4f * (fabsf(c) + rr) + eps; // slack for fp32 rounding of the exact test
+                        if (fabsf(c) - rr > ex[i] + thrMax)
+                            keep = false;
+                    }
+                }
+                if (keep)
+                    mask |= 1ull << j;
+            }
+        }
+    }
+    masks[(size_t)chunk * 64 + sub] = mask;
+}
+
 // =====================================================================================================================
 // Trace
 // =====================================================================================================================
@@ -712,6 +779,17 @@ __device__ __forceinline__ f4 sample_global_surface_atlas_2p(const TraceParams& 
     if (objectsCount > P.objectsCount)
         return result;
     objectsStart++;
+    // Conservative prefilter (chunk_masks_kernel): bit j of the sub-cell mask is clear only if list entry j < 64 cannot pass
+    // the sphere or the OBB test anywhere in this quarter-chunk cell, so skipping it never changes the result.
+    unsigned long long mask = ~0ull;
+    if (P.chunkMasks)
+    {
+        const float q = __fdiv_rn(4.0f, P.chunkSize);
+        int sx = iclamp((int)floorf((worldPosition.x - ((float)cx - half) * P.chunkSize) * q), 0, 3);
+        int sy = iclamp((int)floorf((worldPosition.y - ((float)cy - half) * P.chunkSize) * q), 0, 3);
+        int sz = iclamp((int)floorf((worldPosition.z - ((float)cz - half) * P.chunkSize) * q), 0, 3);
+        mask = __ldg(P.chunkMasks + (size_t)(cz * N * N + cy * N + cx) * 64 + (sz * 16 + sy * 4 + sx));
+    }
     uint32_t k = 0;
     while (k < objectsCount)
     {
@@ -719,6 +797,18 @@ __device__ __forceinline__ f4 sample_global_surface_atlas_2p(const TraceParams& 
         int nc = 0;
         while (k < objectsCount && nc < TW_MAX_CAND)
         {
+            if (k < 64)
+            { // jump to the next list position the prefilter kept
+                unsigned long long rest = mask >> k;
+                if (rest == 0ull)
+                {
+                    k = 64;
+                    continue;
+                }
+                k += __ffsll((long long)rest) - 1;
+                if (k >= objectsCount)
+                    break;
+            }
             uint32_t objectAddress = __ldg(P.cull + objectsStart + k);
             k++;
             const LuxObjectBuffer* object = P.objects + objectAddress;
@@ -1308,6 +1398,13 @@ void launch_object_inverse(const LuxObjectBuffer* objects, int count, float* inv
 {
     if (count > 0)
         object_inverse_kernel<<<(count + 127) / 128, 128, 0, s>>>(objects, count, inv);
+}
+
+void launch_chunk_masks(const uint32_t* chunks, const uint32_t* cull, const LuxObjectBuffer* objects, const float* objectInverse,
+                        uint32_t objectsCount, float chunkSize, float thrMax, unsigned long long* masks, cudaStream_t s)
+{
+    const int N = LUX_SURFACE_ATLAS_CHUNKS_RESOLUTION;
+    chunk_masks_kernel<<<N * N * N, 64, 0, s>>>(chunks, cull, objects, objectInverse, objectsCount, chunkSize, thrMax, masks);
 }
 
 size_t trace_record_count(int probeCount, int raysPerProbe)

@@ -30,6 +30,7 @@ struct TraceParams
     const uint32_t*        cull;
     const LuxObjectBuffer* objects;
     const float*           objectInverse; // [objects][16], inverse(object.transform) precomputed at upload
+    const unsigned long long* chunkMasks; // [40^3][64] conservative per-sub-cell candidate masks, or null
     const LuxTileBuffer*   tiles;
     const uint2*           light; // RGBA16F
     const float*           depth; // D32F
@@ -71,6 +72,8 @@ struct BlendParams
 void launch_ray_dirs(const float* rot16Host, int raysPerProbe, float4* dirs, cudaStream_t s); // rotation travels as a kernel argument
 void launch_blend_weights(const uint2* dirDistRow0, int raysPerProbe, int raysPadded, float sharpness, float* wIrr, float* wDepth,
                           float* scaleIrr, float* scaleDepth, cudaStream_t s);
+void launch_chunk_masks(const uint32_t* chunks, const uint32_t* cull, const LuxObjectBuffer* objects, const float* objectInverse,
+                        uint32_t objectsCount, float chunkSize, float thrMax, unsigned long long* masks, cudaStream_t s);
 void launch_object_inverse(const LuxObjectBuffer* objects, int count, float* inv, cudaStream_t s);
 
 // variant 0: one thread per ray (simple); 1: wavefront (march + shade), explicit fp16 loads; 2: wavefront, layered-texture

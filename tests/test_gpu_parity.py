@@ -206,7 +206,8 @@ def test_restore_resumes_bit_identically():
         p.close()
 
 
-@pytest.mark.parametrize("flags,name", [(0, "wavefront+loads"), (abi.FLAG_SDF_TEXTURE, "wavefront+tld4"), (abi.FLAG_TRACE_SIMPLE, "simple")])
+@pytest.mark.parametrize("flags,name", [(0, "wavefront+tld4"), (abi.FLAG_SDF_LOADS, "wavefront+loads"), (abi.FLAG_TRACE_SIMPLE, "simple"),
+                                        (abi.FLAG_NO_PREFILTER, "wavefront, full object lists")])
 @pytest.mark.parametrize("cfg", ["c1", "city64"])
 def test_trace_variants_match_oracle(oracle, flags, name, cfg):
     """Every trace kernel variant (thread-per-ray, wavefront with explicit loads, wavefront with texture gathers)
@@ -229,7 +230,7 @@ def test_ragged_sizes(oracle):
     orc = oracle.OraclePipeline(sc)
     for r in rots:
         orc.update(r)
-    for flags in (0, abi.FLAG_SDF_TEXTURE, abi.FLAG_TRACE_SIMPLE):
+    for flags in (0, abi.FLAG_SDF_LOADS, abi.FLAG_TRACE_SIMPLE):
         pipe = run_engine(sc, rots, flags=flags)
         assert_rays_match(pipe, orc)
         assert_atlases_match(pipe, orc)
