@@ -658,7 +658,7 @@ __device__ __forceinline__ float4 gather_layer(cudaTextureObject_t tex, float x,
 }
 
 // Trilinear tap through two layered gathers: the texture unit does addressing, clamping and fp16 decode, the lerps
-// stay in fp32 ALU with the oracle's weights (hardware filtering would quantise them to 8 bits).
+// stay in fp32 ALU with full-precision weights (hardware filtering would quantise them to 8 bits).
 __device__ __forceinline__ float sample3D_tex(cudaTextureObject_t obj, int W, int H, int D, float u, float v, float w)
 {
     float x = u * (float)W - 0.5f, y = v * (float)H - 0.5f, z = w * (float)D - 0.5f;
