@@ -275,6 +275,9 @@ LUX_API int lux_ddgi_restore(LuxDDGIContext* ctx, const void* irradianceRGBA16F,
                      int32_t frames, int32_t pingPong);
 
 LUX_API int lux_ddgi_get_state(LuxDDGIContext* ctx, LuxDDGIState* out);
+/* z-slab layout of shard `rank` of `world` without a context (pure host arithmetic, usable on a machine with no GPU):
+ * fills probeBegin/Count and the atlas row ranges of `out`; the other fields are zero. */
+LUX_API int lux_ddgi_shard_layout(const LuxDDGIUniform* uniform, int32_t rank, int32_t world, LuxDDGIState* out);
 LUX_API int lux_ddgi_get_stage_ms(LuxDDGIContext* ctx, LuxStageTimes* out);
 
 #ifdef __cplusplus

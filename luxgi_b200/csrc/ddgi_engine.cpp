@@ -439,6 +439,19 @@ static int system(LuxDDGIContext& c)
 
 using namespace lux::ddgi;
 
+static void shardLayout(const LuxDDGIUniform& u, int rank, int world, LuxDDGIState* out)
+{
+    const int xy     = u.probeCounts[0] * u.probeCounts[1];
+    const int zCount = u.probeCounts[2] / world, zBegin = zCount * rank;
+    out->probeBegin         = zBegin * xy;
+    out->probeCount         = zCount * xy;
+    out->irradianceRowBegin = 1 + zBegin * (LUX_IRRADIANCE_OCT_SIZE + 2);
+    out->irradianceRowCount = zCount * (LUX_IRRADIANCE_OCT_SIZE + 2);
+    out->depthRowBegin      = 1 + zBegin * (LUX_DEPTH_OCT_SIZE + 2);
+    out->depthRowCount      = zCount * (LUX_DEPTH_OCT_SIZE + 2);
+}
+
+
 #define CHECK_CTX(ctx)                                                  \
     do                                                                  \
     {                                                                   \
@@ -528,8 +541,12 @@ int lux_ddgi_create(const LuxDDGIUniform* uniform, const LuxDDGICreateInfo* info
     c->world   = ci.world;
     c->uniform = *uniform;
     c->totalProbes = uniform->probeCounts[0] * uniform->probeCounts[1] * uniform->probeCounts[2];
-    c->probeCount  = c->totalProbes / ci.world;
-    c->probeBegin  = c->probeCount * ci.rank;
+    {
+        LuxDDGIState lay{};
+        shardLayout(*uniform, ci.rank, ci.world, &lay);
+        c->probeCount = lay.probeCount;
+        c->probeBegin = lay.probeBegin;
+    }
     if (ci.stream)
         c->stream = (cudaStream_t)ci.stream;
     else
@@ -883,21 +900,28 @@ int lux_ddgi_restore(LuxDDGIContext* c, const void* irradiance, const void* dept
     return LUX_OK;
 }
 
+int lux_ddgi_shard_layout(const LuxDDGIUniform* u, int32_t rank, int32_t world, LuxDDGIState* out)
+{
+    if (!u || !out)
+        return fail(LUX_ERR_INVALID_ARG, "null argument");
+    if (world <= 0 || rank < 0 || rank >= world)
+        return fail(LUX_ERR_INVALID_ARG, "rank %d outside world %d", rank, world);
+    if (u->probeCounts[2] <= 0 || u->probeCounts[2] % world != 0)
+        return fail(LUX_ERR_INVALID_ARG, "world %d must divide probeCounts.z %d (z-slab sharding)", world, u->probeCounts[2]);
+    *out = LuxDDGIState{};
+    shardLayout(*u, rank, world, out);
+    return LUX_OK;
+}
+
 int lux_ddgi_get_state(LuxDDGIContext* c, LuxDDGIState* out)
 {
     if (!c || !out)
         return fail(LUX_ERR_INVALID_ARG, "null argument");
-    const int xy     = c->uniform.probeCounts[0] * c->uniform.probeCounts[1];
-    const int zBegin = c->probeBegin / xy, zCount = c->probeCount / xy;
-    out->frames             = c->frames;
-    out->pingPong           = c->pingPong;
-    out->probeBegin         = c->probeBegin;
-    out->probeCount         = c->probeCount;
-    out->irradianceRowBegin = 1 + zBegin * (LUX_IRRADIANCE_OCT_SIZE + 2);
-    out->irradianceRowCount = zCount * (LUX_IRRADIANCE_OCT_SIZE + 2);
-    out->depthRowBegin      = 1 + zBegin * (LUX_DEPTH_OCT_SIZE + 2);
-    out->depthRowCount      = zCount * (LUX_DEPTH_OCT_SIZE + 2);
-    out->kernelLaunches     = c->launches;
+    *out = LuxDDGIState{};
+    shardLayout(c->uniform, c->rank, c->world, out);
+    out->frames         = c->frames;
+    out->pingPong       = c->pingPong;
+    out->kernelLaunches = c->launches;
     return LUX_OK;
 }
 

@@ -23,7 +23,7 @@ EXPORTS = [
     "lux_ddgi_destroy", "lux_ddgi_set_uniform", "lux_ddgi_set_global_sdf", "lux_ddgi_set_surface_atlas",
     "lux_ddgi_update_surface_light_cache", "lux_ddgi_set_skybox", "lux_ddgi_trace_rays", "lux_ddgi_probe_update",
     "lux_ddgi_border_update", "lux_ddgi_end_frame", "lux_ddgi_update", "lux_ddgi_synchronize", "lux_ddgi_get_buffer",
-    "lux_ddgi_download", "lux_ddgi_download_async", "lux_ddgi_download_rows_async", "lux_ddgi_set_ray_buffers", "lux_ddgi_restore", "lux_ddgi_get_state",
+    "lux_ddgi_download", "lux_ddgi_download_async", "lux_ddgi_download_rows_async", "lux_ddgi_set_ray_buffers", "lux_ddgi_restore", "lux_ddgi_get_state", "lux_ddgi_shard_layout",
     "lux_ddgi_get_stage_ms",
 ]
 
@@ -68,6 +68,7 @@ def load():
         "lux_ddgi_set_ray_buffers": [vp, vp, vp, i32],
         "lux_ddgi_restore": [vp, vp, vp, i32, i32],
         "lux_ddgi_get_state": [vp, C.POINTER(abi.State)],
+        "lux_ddgi_shard_layout": [C.POINTER(abi.DDGIUniform), i32, i32, C.POINTER(abi.State)],
         "lux_ddgi_get_stage_ms": [vp, C.POINTER(abi.StageTimes)],
     }
     for name, argtypes in sig.items():
@@ -117,6 +118,13 @@ def uniform_from_volume(volume: abi.IrradianceVolume, aabb_min, aabb_max) -> abi
     mx = (C.c_float * 3)(*[float(v) for v in aabb_max])
     _check(load().lux_ddgi_uniform_from_volume(C.byref(volume), mn, mx, C.byref(u)))
     return u
+
+
+def shard_layout(uniform: abi.DDGIUniform, rank: int, world: int) -> abi.State:
+    """z-slab probe range and atlas row ranges of one shard (host arithmetic only; works without a GPU)."""
+    st = abi.State()
+    _check(load().lux_ddgi_shard_layout(C.byref(uniform), int(rank), int(world), C.byref(st)))
+    return st
 
 
 class DeviceView:
