@@ -235,3 +235,29 @@ def test_ragged_sizes(oracle):
         assert_rays_match(pipe, orc)
         assert_atlases_match(pipe, orc)
         pipe.close()
+
+
+def test_64_frame_convergence_shipped_scene_parameters(oracle):
+    """north_star: converged irradiance over 64 frames within tolerance.  Probe-volume parameters of the shipped
+    dark-room-emissive.scene (hysteresis 0.98, gamma 0.85, sharpness 50, 256 rays) on the Cornell SDF, 16x8x16
+    probes as in BASELINE configs[1]; every frame re-quantises the feedback to fp16, so any drift would accumulate."""
+    sc = scenes.cornell_scene(res=64, counts=(16, 8, 16), rays=256, atlas_res=512, hysteresis=0.98, gamma=0.85)
+    orc = oracle.OraclePipeline(sc)
+    pipe = ddgi.DDGIPipeline(sc.uniform)
+    pipe.set_scene(sc)
+    prev = None
+    deltas = []
+    for f in range(64):
+        rot = scenes.frame_rotation(f)
+        orc.update(rot)
+        pipe.update(rot)
+        if f in (0, 7, 31, 63):
+            assert_atlases_match(pipe, orc)
+        cur = f16(pipe.irradiance)[..., :3]
+        if prev is not None:
+            deltas.append(float(np.abs(cur - prev).mean()))
+        prev = cur
+    assert_rays_match(pipe, orc)
+    assert np.mean(deltas[-8:]) < 0.5 * np.mean(deltas[:8])  # the temporal filter is converging, not oscillating
+    assert pipe.state().frames == 64
+    pipe.close()
