@@ -152,6 +152,11 @@ def blend(u, rad, dd, prev_irr, prev_dep, out_irr, out_dep, first_frame, probe_b
     assert rc == 0, rc
 
 
+def set_unfused(on):
+    """Literal two-rounding blend arithmetic of the shipped SPIR-V instead of the contract's explicit FMAs."""
+    lib().oracle_set_unfused(int(bool(on)))
+
+
 def border(u, irr, dep, probe_begin=0, count=None):
     if count is None:
         count = abi.probe_count(u)
