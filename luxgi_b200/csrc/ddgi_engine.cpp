@@ -106,6 +106,10 @@ struct LuxDDGIContext
 
     // timers
     cudaEvent_t   ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    // copy engine overlap: host<->device transfers run on their own stream, ordered against the kernels by events
+    cudaStream_t  copyStream = nullptr;
+    cudaEvent_t   evLightReady = nullptr, evShadeDone = nullptr, evIrrDone = nullptr, evDepthDone = nullptr, evCopyDone = nullptr;
+    bool          lightPending = false;
     bool          timed = false;
     uint64_t      launches = 0;
 };
@@ -349,7 +353,9 @@ static int system(LuxDDGIContext& c, const LuxTracePushConstants& push)
     p.records  = (float4*)c.records.ptr;
     p.meta     = (uint32_t*)c.meta.ptr;
     const int variant = (c.flags & LUX_DDGI_FLAG_TRACE_SIMPLE) ? 0 : (c.sdfTex ? 2 : 1);
-    c.launches += launch_trace(p, variant, (unsigned int*)c.chunkCounter.ptr, c.stream);
+    c.launches += launch_trace(p, variant, (unsigned int*)c.chunkCounter.ptr, c.stream, c.lightPending ? c.evLightReady : nullptr);
+    c.lightPending = false;
+    cudaEventRecord(c.evShadeDone, c.stream);
     mark(c, 2);
     LUX_CUDA(cudaGetLastError());
     c.raysValid = true;
@@ -395,8 +401,11 @@ static int system(LuxDDGIContext& c)
     p.outIrr       = (uint2*)c.irradiance[writeIdx].ptr;
     p.prevDepth    = (const uint32_t*)c.depth[c.pingPong].ptr;
     p.outDepth     = (uint32_t*)c.depth[writeIdx].ptr;
+    cudaStreamWaitEvent(c.stream, c.evCopyDone, 0); // row downloads of earlier frames must have left the atlases
     launch_blend_irradiance(p, c.stream);
+    cudaEventRecord(c.evIrrDone, c.stream);
     launch_blend_depth(p, c.stream);
+    cudaEventRecord(c.evDepthDone, c.stream);
     c.launches += 2;
     mark(c, 3);
     LUX_CUDA(cudaGetLastError());
@@ -561,6 +570,9 @@ int lux_ddgi_create(const LuxDDGIUniform* uniform, const LuxDDGICreateInfo* info
     }
     for (auto& ev : c->ev)
         cudaEventCreate(&ev);
+    cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking);
+    for (cudaEvent_t* e : {&c->evLightReady, &c->evShadeDone, &c->evIrrDone, &c->evDepthDone, &c->evCopyDone})
+        cudaEventCreateWithFlags(e, cudaEventDisableTiming);
     rc = init::initializeProbeGrid(*c);
     if (rc == LUX_OK)
         rc = updateOrigins(*c);
@@ -581,6 +593,8 @@ int lux_ddgi_destroy(LuxDDGIContext* c)
         return LUX_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    if (c->copyStream)
+        cudaStreamSynchronize(c->copyStream);
     DeviceBuffer* all[] = {&c->radiance, &c->directionDepth, &c->irradiance[0], &c->irradiance[1], &c->depth[0], &c->depth[1],
                            &c->dirs, &c->wIrr, &c->wDepth, &c->scaleIrr, &c->scaleDepth, &c->origins, &c->records, &c->meta, &c->chunkCounter, &c->sdf, &c->mip, &c->chunks, &c->cull,
                            &c->objects, &c->objectInverse, &c->chunkMasks, &c->tiles, &c->light, &c->atlasDepth, &c->sky};
@@ -590,6 +604,11 @@ int lux_ddgi_destroy(LuxDDGIContext* c)
     for (auto& ev : c->ev)
         if (ev)
             cudaEventDestroy(ev);
+    for (cudaEvent_t e : {c->evLightReady, c->evShadeDone, c->evIrrDone, c->evDepthDone, c->evCopyDone})
+        if (e)
+            cudaEventDestroy(e);
+    if (c->copyStream)
+        cudaStreamDestroy(c->copyStream);
     if (c->ownStream)
         cudaStreamDestroy(c->stream);
     delete c;
@@ -699,7 +718,21 @@ int lux_ddgi_update_surface_light_cache(LuxDDGIContext* c, const void* light, Lu
     if (!light)
         return fail(LUX_ERR_INVALID_ARG, "null light cache");
     const size_t texels = (size_t)c->atlasData.resolution * c->atlasData.resolution;
-    return upload(*c, c->light, light, texels * 8, kind); // HOST: async copy on the context's stream (pinned sources overlap)
+    if (kind == LUX_MEM_DEVICE)
+        return upload(*c, c->light, light, texels * 8, kind);
+    if (c->light.borrowed || c->light.bytes != texels * 8)
+    {
+        c->light.release();
+        LUX_CUDA(cudaMalloc(&c->light.ptr, texels * 8));
+        c->light.bytes = texels * 8;
+    }
+    // Copy-engine overlap: the upload runs on the copy stream once the previous frame's shade kernel (the only reader) is
+    // done, and only the NEXT shade kernel waits for it — the march of that frame overlaps the transfer.
+    LUX_CUDA(cudaStreamWaitEvent(c->copyStream, c->evShadeDone, 0));
+    LUX_CUDA(cudaMemcpyAsync(c->light.ptr, light, texels * 8, cudaMemcpyHostToDevice, c->copyStream));
+    LUX_CUDA(cudaEventRecord(c->evLightReady, c->copyStream));
+    c->lightPending = true;
+    return LUX_OK;
 }
 
 int lux_ddgi_set_skybox(LuxDDGIContext* c, int32_t faceSize, const void* faces, LuxMemKind kind)
@@ -792,6 +825,7 @@ int lux_ddgi_synchronize(LuxDDGIContext* c)
 {
     CHECK_CTX(c);
     LUX_CUDA(cudaStreamSynchronize(c->stream));
+    LUX_CUDA(cudaStreamSynchronize(c->copyStream));
     return LUX_OK;
 }
 
@@ -881,7 +915,11 @@ int lux_ddgi_download_rows_async(LuxDDGIContext* c, LuxBufferId id, int32_t rowB
         return fail(LUX_ERR_INVALID_ARG, "row download is for atlases only");
     if (rowBegin < 0 || rowCount < 0 || rowBegin + rowCount > rows)
         return fail(LUX_ERR_INVALID_ARG, "rows [%d,%d) outside the atlas (%d rows)", rowBegin, rowBegin + rowCount, rows);
-    LUX_CUDA(cudaMemcpyAsync(pinnedHost, (const char*)b->ptr + rowBegin * rowBytes, rowCount * rowBytes, cudaMemcpyDeviceToHost, c->stream));
+    // on the copy stream, as soon as the blend kernel that produced this atlas has finished
+    const bool isIrr = (id == LUX_BUF_IRRADIANCE || id == LUX_BUF_IRRADIANCE_PREV);
+    LUX_CUDA(cudaStreamWaitEvent(c->copyStream, isIrr ? c->evIrrDone : c->evDepthDone, 0));
+    LUX_CUDA(cudaMemcpyAsync(pinnedHost, (const char*)b->ptr + rowBegin * rowBytes, rowCount * rowBytes, cudaMemcpyDeviceToHost, c->copyStream));
+    LUX_CUDA(cudaEventRecord(c->evCopyDone, c->copyStream));
     return LUX_OK;
 }
 

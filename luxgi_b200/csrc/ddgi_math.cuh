@@ -60,6 +60,24 @@ __device__ __forceinline__ f3 mat3_mul(const float* __restrict__ m, f3 v)
 __device__ __forceinline__ float h2f_bits(uint16_t h) { return __half2float(__ushort_as_half(h)); }
 __device__ __forceinline__ uint16_t f2h_bits(float f) { return __half_as_ushort(__float2half_rn(f)); }
 
+// x / d for a divisor that is reused many times.  When d is a normal power of two, x * (1/d) is the correctly rounded
+// quotient too (pure exponent shift), so the IEEE division (~17 SASS instructions) can be replaced by one multiply
+// without changing a single bit; any other divisor keeps the true division.
+struct ExactDivisor
+{
+    float d, inv;
+    bool  pow2;
+    __device__ __forceinline__ ExactDivisor() : d(1.0f), inv(1.0f), pow2(true) {}
+    __device__ __forceinline__ explicit ExactDivisor(float v) : d(v)
+    {
+        uint32_t b = __float_as_uint(v);
+        uint32_t e = (b >> 23) & 0xffu;
+        pow2 = ((b & 0x7fffffu) == 0u) && e > 2u && e < 252u; // normal power of two whose reciprocal is normal as well
+        inv  = pow2 ? __fdiv_rn(1.0f, v) : 0.0f;
+    }
+    __device__ __forceinline__ float div(float x) const { return pow2 ? x * inv : __fdiv_rn(x, d); }
+};
+
 // mix(x, y, a) in the contract's form: fma(y, a, x*(1-a))
 __device__ __forceinline__ float mixh(float x, float y, float a) { return __fmaf_rn(y, a, x * (1.0f - a)); }
 
