@@ -232,14 +232,31 @@ def run_lux(args):
         t = views[(buf, ptr)]
         return t[1:1 + rows_total].reshape(-1), t[row_begin:row_begin + rows_total // world].reshape(-1)
 
+    ag_stream = torch.cuda.Stream(device=dev) if world > 1 else None
+    ag_done = []
+
     def step(f):
+        """One volume update.  At N > 1 the all-gather of the atlases written by step f runs on its own stream and overlaps the
+        trace of step f+1 (the trace never reads the atlases); step f+2 is the first to overwrite the rows it sends from, so
+        that step waits for it."""
+        if world > 1 and not args.sync_allgather and len(ag_done) >= 2:
+            stream.wait_event(ag_done[-2])
         pipe.update(rot_of(f))
         if world > 1:  # one in-place all-gather per atlas (SURVEY §8e): own slab rows -> every rank's full atlas
-            with torch.cuda.stream(stream):
+            side = stream if args.sync_allgather else ag_stream
+            if side is not stream:
+                ev = torch.cuda.Event()
+                ev.record(stream)
+                side.wait_event(ev)
+            with torch.cuda.stream(side):
                 full, mine = atlas_rows(abi.BUF_IRRADIANCE, st.irradianceRowBegin, st.irradianceRowCount * world)
                 dist.all_gather_into_tensor(full, mine)
                 full, mine = atlas_rows(abi.BUF_DEPTH, st.depthRowBegin, st.depthRowCount * world)
                 dist.all_gather_into_tensor(full, mine)
+                done = torch.cuda.Event()
+                done.record(side)
+            ag_done.append(done)
+            del ag_done[:-2]
 
     def barrier():
         torch.cuda.synchronize()
@@ -331,7 +348,8 @@ def run_lux(args):
             "ms_per_step": ms_per_step, "ms_per_update": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": dict(workload_desc(args.workload, sc), parallelism=f"zslab{world}", l2_policy="inputs larger than L2 (no flush)",
-                           sharding="probe z-slabs, SDF + surface cache replicated, in-place NCCL all-gather of atlas rows per step"),
+                           sharding="probe z-slabs, SDF + surface cache replicated, in-place NCCL all-gather of atlas rows per step"
+                           + ("" if world == 1 else (" (on the compute stream)" if args.sync_allgather else " overlapped with the next step's trace"))),
             "stage_ms": {"setup": setup_ms / args.steps, "trace": trace_launch_ms, "blend_border": blend_launch_ms,
                          "other_incl_allgather": ms_per_step - (setup_ms + trace_ms + blend_ms) / args.steps},
             "trace_rays_per_s": probes_rank * world * R / (trace_launch_ms * 1e-3),
@@ -371,6 +389,7 @@ def main():
     ap.add_argument("--trace", default="texture", choices=["texture", "loads", "simple"],
                     help="SDF read path / trace kernel variant: wavefront + tld4 gathers (default), wavefront + fp16 loads, thread-per-ray")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--sync-allgather", action="store_true", help="all-gather on the compute stream (no overlap with the next trace)")
     ap.add_argument("--stage-every-step", action="store_true", help="sync + read stage timers every step (perturbs the total)")
     args = ap.parse_args()
     if args.impl == "reference":
