@@ -211,7 +211,8 @@ def run_lux(args):
         raise SystemExit(f"{world} GPUs do not divide Z={u.probeCounts[2]}")
     stream = torch.cuda.Stream(device=dev)
     flags = abi.FLAG_STAGE_TIMERS | {"texture": 0, "loads": abi.FLAG_SDF_LOADS, "simple": abi.FLAG_TRACE_SIMPLE}[args.trace]
-    pipe = ddgi.DDGIPipeline(u, device=local, rank=rank, world=world, flags=flags, stream=stream.cuda_stream)
+    shard_rank, shard_world = (rank, world) if args.emulate_shard is None else tuple(int(x) for x in args.emulate_shard.split('/'))
+    pipe = ddgi.DDGIPipeline(u, device=local, rank=shard_rank, world=shard_world, flags=flags, stream=stream.cuda_stream)
     pipe.set_scene(sc)
     st = pipe.state()
     P, R = sc.probes, u.raysPerProbe
@@ -295,11 +296,16 @@ def run_lux(args):
     launches = pipe.state().kernelLaunches - launches0
     clocks = sampler.stop() if rank == 0 else None
     tm = torch.tensor([ms_total, stage["trace"], stage["blend"], stage["setup"]], device=dev, dtype=torch.float64)
+    per_rank = None
     if world > 1:
+        allr = [torch.zeros_like(tm) for _ in range(world)]
+        dist.all_gather(allr, tm)
+        per_rank = [[round(float(x) / args.steps, 4) for x in t.tolist()[1:3]] for t in allr]
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
     ms_total, trace_ms, blend_ms, setup_ms = [float(x) for x in tm.tolist()]
     ms_per_step = ms_total / args.steps
-    value = P * R * args.steps / (ms_total * 1e-3)
+    P_timed = st.probeCount * world  # == P unless --emulate-shard
+    value = P_timed * R * args.steps / (ms_total * 1e-3)
 
     e2e_value, e2e_s, light_bytes, d2h_bytes = None, None, 0, 0
     if not args.no_e2e:
@@ -353,6 +359,7 @@ def run_lux(args):
             "stage_ms": {"setup": setup_ms / args.steps, "trace": trace_launch_ms, "blend_border": blend_launch_ms,
                          "other_incl_allgather": ms_per_step - (setup_ms + trace_ms + blend_ms) / args.steps},
             "trace_rays_per_s": probes_rank * world * R / (trace_launch_ms * 1e-3),
+            "per_rank_trace_blend_ms": per_rank,
             "roofline": {"bound": "hbm", "kernel": "trace_kernel", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
                          "traffic": None, "peak_source": peak_kind, "algorithmic_bytes_per_launch": tb},
             "roofline_blend": {"bound": "hbm", "kernel": "blend_irradiance_kernel+blend_depth_kernel", "achieved": achb, "peak": hbm,
@@ -389,6 +396,7 @@ def main():
     ap.add_argument("--trace", default="texture", choices=["texture", "loads", "simple"],
                     help="SDF read path / trace kernel variant: wavefront + tld4 gathers (default), wavefront + fp16 loads, thread-per-ray")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--emulate-shard", default=None, help="r/w: run shard r of w on one GPU without any collective (profiling aid)")
     ap.add_argument("--sync-allgather", action="store_true", help="all-gather on the compute stream (no overlap with the next trace)")
     ap.add_argument("--stage-every-step", action="store_true", help="sync + read stage timers every step (perturbs the total)")
     args = ap.parse_args()

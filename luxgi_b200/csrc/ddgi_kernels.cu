@@ -890,7 +890,8 @@ constexpr int MARCH_WARPS       = 8;
 #ifndef SHADE_BLOCKS_PER_SM
 #define SHADE_BLOCKS_PER_SM 4
 #endif
-constexpr int MARCH_CHUNK_UNITS = 2;                                       // units (32 probes x 16 rays) per pool fetch
+constexpr int MARCH_CHUNK_RAYS  = 256;                                     // rays per pool fetch (8 directions x 32 probes): small, so
+                                                                           // that shards with few rays per warp still balance
 constexpr int UNIT_RAYS         = 32 * TW_RAYS_PER_UNIT;                   // 512
 constexpr int MARCH_REFILL_MIN  = 8;                                       // refill when this many lanes are idle
 
@@ -965,8 +966,8 @@ __global__ void __launch_bounds__(32 * MARCH_WARPS, MARCH_BLOCKS_PER_SM) march_k
                     exhausted = true;
                 else
                 {
-                    poolNext = (long long)c * (MARCH_CHUNK_UNITS * UNIT_RAYS);
-                    poolEnd  = poolNext + MARCH_CHUNK_UNITS * UNIT_RAYS;
+                    poolNext = (long long)c * MARCH_CHUNK_RAYS;
+                    poolEnd  = poolNext + MARCH_CHUNK_RAYS;
                 }
             }
             if (!exhausted)
@@ -1435,8 +1436,7 @@ size_t trace_record_count(int probeCount, int raysPerProbe)
     const long long rayGroups   = (raysPerProbe + TW_RAYS_PER_UNIT - 1) / TW_RAYS_PER_UNIT;
     const long long probeGroups = (probeCount + 31) / 32;
     const long long units       = rayGroups * probeGroups;
-    const long long chunks      = (units + MARCH_CHUNK_UNITS - 1) / MARCH_CHUNK_UNITS;
-    return (size_t)(chunks * MARCH_CHUNK_UNITS * UNIT_RAYS);
+    return (size_t)(units * UNIT_RAYS);
 }
 
 void launch_probe_origins(const TraceParams& p, cudaStream_t s)
@@ -1458,7 +1458,7 @@ int launch_trace(const TraceParams& p, int variant, unsigned int* chunkCounter, 
     const int rayGroups   = (p.raysPerProbe + TW_RAYS_PER_UNIT - 1) / TW_RAYS_PER_UNIT;
     const int probeGroups = (p.probeCount + 31) / 32;
     const long long units = (long long)rayGroups * probeGroups;
-    const int chunks      = (int)((units + MARCH_CHUNK_UNITS - 1) / MARCH_CHUNK_UNITS);
+    const int chunks      = (int)(units * (UNIT_RAYS / MARCH_CHUNK_RAYS));
     cudaMemsetAsync(chunkCounter, 0, sizeof(unsigned int), s);
     long long blocks = ((long long)chunks + MARCH_WARPS - 1) / MARCH_WARPS;
     const long long persistent = 148ll * MARCH_BLOCKS_PER_SM; // one resident generation of 8-warp blocks per SM
@@ -1498,7 +1498,7 @@ static void launch_blend_irradiance_t(const BlendParams& p, cudaStream_t s)
 
 void launch_blend_irradiance(const BlendParams& p, cudaStream_t s)
 {
-    if (p.probeCount >= 64 * 148)
+    if (p.probeCount >= 64 * 64) // measured: the 64-probe tile wins as soon as it yields ~half a wave of blocks
         launch_blend_irradiance_t<64>(p, s);
     else
         launch_blend_irradiance_t<16>(p, s);
@@ -1521,7 +1521,7 @@ static void launch_blend_depth_t(const BlendParams& p, cudaStream_t s)
 
 void launch_blend_depth(const BlendParams& p, cudaStream_t s)
 {
-    if (p.probeCount >= 32 * 148)
+    if (p.probeCount >= 32 * 64)
         launch_blend_depth_t<32>(p, s);
     else
         launch_blend_depth_t<8>(p, s);
