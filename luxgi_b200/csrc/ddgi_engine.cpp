@@ -84,7 +84,7 @@ struct LuxDDGIContext
     bool         raysValid   = false;
 
     // per-frame tables
-    DeviceBuffer dirs, wIrr, wDepth, scaleIrr, scaleDepth;
+    DeviceBuffer dirs, wIrr, wDepth, scaleIrr, scaleDepth, nzIrr, nzDepth;
     DeviceBuffer origins, records, meta, chunkCounter; // wavefront trace scratch
 
     // uGlobalSDF / uGlobalMipSDF / sdfData
@@ -236,6 +236,8 @@ static int initializeProbeGrid(LuxDDGIContext& c)
     if ((rc = allocZero(c, c.wDepth, (size_t)c.raysPadded * 256 * sizeof(float))) != LUX_OK) return rc;
     if ((rc = allocZero(c, c.scaleIrr, 64 * sizeof(float))) != LUX_OK) return rc;
     if ((rc = allocZero(c, c.scaleDepth, 256 * sizeof(float))) != LUX_OK) return rc;
+    if ((rc = allocZero(c, c.nzIrr, (size_t)c.raysPadded * sizeof(uint32_t))) != LUX_OK) return rc;
+    if ((rc = allocZero(c, c.nzDepth, (size_t)c.raysPadded * sizeof(uint32_t))) != LUX_OK) return rc;
     if ((rc = allocZero(c, c.origins, (size_t)c.probeCount * sizeof(float4))) != LUX_OK) return rc;
     if ((rc = allocZero(c, c.chunkCounter, 64)) != LUX_OK) return rc;
     if (!(c.flags & LUX_DDGI_FLAG_TRACE_SIMPLE))
@@ -374,9 +376,9 @@ static int system(LuxDDGIContext& c)
     const LuxDDGIUniform& u = c.uniform;
     const int writeIdx = 1 - c.pingPong;
 
-    launch_blend_weights((const uint2*)c.directionDepth.ptr, u.raysPerProbe, c.raysPadded, u.sharpness, (float*)c.wIrr.ptr,
-                         (float*)c.wDepth.ptr, (float*)c.scaleIrr.ptr, (float*)c.scaleDepth.ptr, c.stream);
-    c.launches += 2;
+    c.launches += launch_blend_weights((const uint2*)c.directionDepth.ptr, u.raysPerProbe, c.raysPadded, u.sharpness, (float*)c.wIrr.ptr,
+                                       (float*)c.wDepth.ptr, (float*)c.scaleIrr.ptr, (float*)c.scaleDepth.ptr, (uint32_t*)c.nzIrr.ptr,
+                                       (uint32_t*)c.nzDepth.ptr, c.stream);
 
     BlendParams p{};
     p.probeBegin   = c.probeBegin;
@@ -397,6 +399,8 @@ static int system(LuxDDGIContext& c)
     p.wDepth       = (const float*)c.wDepth.ptr;
     p.scaleIrr     = (const float*)c.scaleIrr.ptr;
     p.scaleDepth   = (const float*)c.scaleDepth.ptr;
+    p.nzIrr        = (const uint32_t*)c.nzIrr.ptr;
+    p.nzDepth      = (const uint32_t*)c.nzDepth.ptr;
     p.prevIrr      = (const uint2*)c.irradiance[c.pingPong].ptr;
     p.outIrr       = (uint2*)c.irradiance[writeIdx].ptr;
     p.prevDepth    = (const uint32_t*)c.depth[c.pingPong].ptr;
@@ -596,7 +600,7 @@ int lux_ddgi_destroy(LuxDDGIContext* c)
     if (c->copyStream)
         cudaStreamSynchronize(c->copyStream);
     DeviceBuffer* all[] = {&c->radiance, &c->directionDepth, &c->irradiance[0], &c->irradiance[1], &c->depth[0], &c->depth[1],
-                           &c->dirs, &c->wIrr, &c->wDepth, &c->scaleIrr, &c->scaleDepth, &c->origins, &c->records, &c->meta, &c->chunkCounter, &c->sdf, &c->mip, &c->chunks, &c->cull,
+                           &c->dirs, &c->wIrr, &c->wDepth, &c->scaleIrr, &c->scaleDepth, &c->nzIrr, &c->nzDepth, &c->origins, &c->records, &c->meta, &c->chunkCounter, &c->sdf, &c->mip, &c->chunks, &c->cull,
                            &c->objects, &c->objectInverse, &c->chunkMasks, &c->tiles, &c->light, &c->atlasDepth, &c->sky};
     for (DeviceBuffer* b : all)
         b->release();

@@ -10,6 +10,8 @@
 //   border_kernel            Shaders/DDGI/BorderUpdate.glsl:136-156
 //
 // Compiled with -fmad=false; see ddgi_math.cuh for the numerics contract.
+#include <cstdlib>
+
 #include "ddgi_kernels.h"
 #include "ddgi_math.cuh"
 
@@ -43,6 +45,18 @@ __global__ void ray_dirs_kernel(const RotationArg rot, int R, float4* __restrict
 }
 
 __device__ __forceinline__ float sign_not_zero(float k) { return (k >= 0.0f) ? 1.0f : -1.0f; }
+
+// Column order of the depth weight matrix: column n = block*8 + (j%2)*4 + (i%4) with block = (j/2)*4 + i/4, i.e. the 16x16
+// octahedral map is cut into 4x2-texel blocks.  A block spans ~13 degrees, so "all 8 weights of this ray are zero" holds
+// for ~3/4 of the (ray, block) pairs (depth weights vanish beyond 46 degrees); rows of the map, in contrast, wind across a
+// whole great arc and are almost always live.  Only the ORDER OF COLUMNS changes: each texel still sums its rays in order.
+__device__ __forceinline__ int depth_column_of_texel(int i, int j) { return (((j >> 1) << 2) + (i >> 2)) * 8 + ((j & 1) << 2) + (i & 3); }
+__device__ __forceinline__ void depth_texel_of_column(int n, int& i, int& j)
+{
+    int block = n >> 3, w = n & 7;
+    i = ((block & 3) << 2) + (w & 3);
+    j = ((block >> 2) << 1) + (w >> 2);
+}
 
 // DDGICommon.glsl:74-92 for interior texel (i, j) of a probe with `side` texels per side
 __device__ __forceinline__ f3 texel_direction(int i, int j, int side)
@@ -95,10 +109,36 @@ __global__ void blend_weights_kernel(const uint2* __restrict__ dirsHalf, int R, 
     if (t < 64)
         wIrr[(size_t)r * 64 + t] = w;
     else
-        wDepth[(size_t)r * 256 + (t - 64)] = w;
+        wDepth[(size_t)r * 256 + depth_column_of_texel((t - 64) & 15, (t - 64) >> 4)] = w;
 }
 
 // Sequential sum over rays in ray order (the reference's accumulation order), then 1/(2*sum) (ProbeUpdate.glsl:133-134).
+// Per ray, which groups of 8 consecutive texels carry any non-zero weight (bit g): lets the blend skip exact zeros.
+__global__ void blend_nonzero_kernel(const float* __restrict__ wIrr, const float* __restrict__ wDepth, int Rpad,
+                                     uint32_t* __restrict__ nzIrr, uint32_t* __restrict__ nzDepth)
+{
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= Rpad)
+        return;
+    uint32_t zi = 0, zd = 0;
+    for (int g = 0; g < 8; g++)
+    {
+        bool any = false;
+        for (int j = 0; j < 8; j++)
+            any |= wIrr[(size_t)r * 64 + g * 8 + j] != 0.0f;
+        zi |= (any ? 1u : 0u) << g;
+    }
+    for (int g = 0; g < 32; g++)
+    {
+        bool any = false;
+        for (int j = 0; j < 8; j++)
+            any |= wDepth[(size_t)r * 256 + g * 8 + j] != 0.0f;
+        zd |= (any ? 1u : 0u) << g;
+    }
+    nzIrr[r]   = zi;
+    nzDepth[r] = zd;
+}
+
 __global__ void blend_scales_kernel(const float* __restrict__ wIrr, const float* __restrict__ wDepth, int R,
                                     float* __restrict__ scaleIrr, float* __restrict__ scaleDepth)
 {
@@ -112,7 +152,7 @@ __global__ void blend_scales_kernel(const float* __restrict__ wIrr, const float*
             total += wIrr[(size_t)r * 64 + t];
     else
         for (int r = 0; r < R; r++)
-            total += wDepth[(size_t)r * 256 + (t - 64)];
+            total += wDepth[(size_t)r * 256 + depth_column_of_texel((t - 64) & 15, (t - 64) >> 4)];
     float s = (total > FLT_EPS) ? __fdiv_rn(1.0f, 2.0f * total) : 1.0f;
     if (t < 64)
         scaleIrr[t] = s;
@@ -1157,7 +1197,7 @@ __global__ void probe_origins_kernel(const TraceParams P, float4* __restrict__ o
 // gated weights stored as zeros.  Register tile 8 (rows) x 8 (texels) per thread; A = values staged in shared memory
 // as [row][k] (+1 pad), B = weights staged as [k][texel].
 
-constexpr int KC = 32; // rays per shared-memory chunk
+constexpr int KC = 32; // rays per shared-memory chunk (== warp size: the per-chunk live-ray mask is one ballot)
 
 // mirrored border stores for interior texel (i, j) of a probe whose ring origin is (bx, by)  (BorderUpdate.glsl:25-133)
 template <typename T>
@@ -1177,76 +1217,145 @@ __device__ __forceinline__ void store_with_border(T* __restrict__ img, int W, in
     if (x == 1 && y == 1)       img[(size_t)(by + side + 1) * W + (bx + side + 1)] = v;
 }
 
-// Irradiance: PB probes per block, rows m = p*3 + channel (M = 3*PB), N = 64 texels.
-template <int PB>
-__global__ void __launch_bounds__((3 * PB / 8) * 8) blend_irradiance_kernel(const __grid_constant__ BlendParams P)
+// cp.async (LDGSTS) helpers: global -> shared without a register round trip, completion tracked per thread group.
+__device__ __forceinline__ void cp_async_16(void* smemDst, const void* gsrc)
 {
-    constexpr int M = 3 * PB, N = 64, NT = (M / 8) * 8;
-    extern __shared__ __align__(16) float smem[];
-    float* As = smem;                  // [M][KC+1]
-    float* Bs = smem + M * (KC + 1);   // [KC][N]
-    float* Cs = smem;                  // epilogue overlay [M][N]
+    unsigned s = (unsigned)__cvta_generic_to_shared(smemDst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_8_zfill(void* smemDst, const void* gsrc, bool valid)
+{
+    unsigned s = (unsigned)__cvta_generic_to_shared(smemDst);
+    int      n = valid ? 8 : 0; // src-size 0: the 8 destination bytes are zero-filled, nothing is read
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(s), "l"(gsrc), "r"(n));
+}
+__device__ __forceinline__ void cp_async_4(void* smemDst, const void* gsrc)
+{
+    unsigned s = (unsigned)__cvta_generic_to_shared(smemDst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-    const int tid  = threadIdx.x;
-    const int ng   = tid & 7;  // texel group: texels ng*8 .. ng*8+7
-    const int mg   = tid >> 3; // row group: rows mg*8 .. mg*8+7
-    const int probe0 = blockIdx.x * PB; // shard-local index of the block's first probe
+// Load TR consecutive floats (TR in {2,3,4,6}) from shared memory with the widest aligned vectors.
+template <int TR>
+__device__ __forceinline__ void lds_row(const float* __restrict__ p, float* a)
+{
+    if constexpr (TR == 4)
+    {
+        float4 v = *reinterpret_cast<const float4*>(p);
+        a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w;
+    }
+    else if constexpr (TR % 2 == 0)
+    {
+#pragma unroll
+        for (int i = 0; i < TR / 2; i++)
+        {
+            float2 v = *reinterpret_cast<const float2*>(p + 2 * i);
+            a[2 * i] = v.x; a[2 * i + 1] = v.y;
+        }
+    }
+    else
+    {
+#pragma unroll
+        for (int i = 0; i < TR; i++)
+            a[i] = p[i];
+    }
+}
+
+// Blend tiling, second form (profiles/r1_*: the 8x8 tiles reached 28 % / 44 % of the FP32 peak and did all the work on
+// weights that are exact zeros).  Now a WARP owns one group of 8 texels and its 32 lanes own 32 disjoint row groups
+// (rows = (probe, channel)), so "all 8 weights of this ray are zero" is a warp-uniform condition and the ray is skipped
+// for that warp: depth weights pow(cos, 50) are zero below the 1e-8 gate on ~85 % of the sphere, irradiance weights
+// max(0, cos) on half of it.  Skipped terms are exact zeros, so every accumulator still sees the reference's sum in ray
+// order.  A fragments are lane-contiguous (conflict-free), B fragments are warp broadcasts.
+
+// Irradiance: PB probes per block, rows m = p*3 + channel (M = 3*PB), 8 warps = the 8 rows of the 8x8 octahedral map.
+template <int PB>
+__global__ void __launch_bounds__(256) blend_irradiance_kernel(const __grid_constant__ BlendParams P)
+{
+    constexpr int M = 3 * PB, MS = M + 2, N = 64, NT = 256, TR = M / 32;
+    static_assert(M % 32 == 0, "rows must split evenly over 32 lanes");
+    extern __shared__ __align__(16) float smem[];
+    // double-buffered by cp.async: raw fp16 ray texels + weights + zero masks of chunk c+1 arrive while chunk c is computed
+    float*    As  = smem;                                   // [KC][MS] fp32 values of the current chunk
+    float*    Bs  = As + KC * MS;                           // [2][KC][N]
+    uint2*    Raw = reinterpret_cast<uint2*>(Bs + 2 * KC * N); // [2][PB][KC] RGBA16F texels
+    uint32_t* Zs  = reinterpret_cast<uint32_t*>(Raw + 2 * PB * KC); // [2][KC] bit g = texel group g has a non-zero weight
+    float*    Cs  = smem;                                   // epilogue overlay [M][N]
+
+    const int tid = threadIdx.x, lane = tid & 31, grp = tid >> 5;
+    const int probe0 = blockIdx.x * PB;
     const int R = P.raysPerProbe;
 
-    float acc[8][8];
+    float acc[TR][8];
 #pragma unroll
-    for (int i = 0; i < 8; i++)
+    for (int i = 0; i < TR; i++)
 #pragma unroll
         for (int j = 0; j < 8; j++)
             acc[i][j] = 0.0f;
 
-    for (int k0 = 0; k0 < P.raysPadded; k0 += KC)
-    {
-        // A: radiance texels -> fp32 rows.  Consecutive threads read consecutive rays of one probe (coalesced) and write
-        // consecutive k of one row (conflict-free).
+    auto prefetch = [&](int k0, int st) {
         for (int idx = tid; idx < PB * KC; idx += NT)
         {
-            int p = idx / KC, k = idx % KC;
-            int probe = probe0 + p, ray = k0 + k;
-            uint2 t = make_uint2(0u, 0u);
-            if (probe < P.probeCount && ray < R)
-                t = __ldg(P.radiance + (size_t)probe * R + ray);
-            As[(p * 3 + 0) * (KC + 1) + k] = h2f_bits((uint16_t)(t.x & 0xffffu));
-            As[(p * 3 + 1) * (KC + 1) + k] = h2f_bits((uint16_t)(t.x >> 16));
-            As[(p * 3 + 2) * (KC + 1) + k] = h2f_bits((uint16_t)(t.y & 0xffffu));
+            int  p = idx / KC, k = idx % KC; // consecutive threads -> consecutive rays of one probe (coalesced)
+            int  probe = probe0 + p, ray = k0 + k;
+            bool ok = probe < P.probeCount && ray < R;
+            cp_async_8_zfill(Raw + (st * PB + p) * KC + k, P.radiance + (ok ? (size_t)probe * R + ray : 0), ok);
         }
-        // B: weights chunk [KC][64] is contiguous in global memory
+        const float* src = P.wIrr + (size_t)k0 * N;
+        for (int idx = tid; idx < KC * N / 4; idx += NT)
+            cp_async_16(Bs + st * KC * N + idx * 4, src + idx * 4);
+        if (tid < KC)
+            cp_async_4(Zs + st * KC + tid, P.nzIrr + k0 + tid);
+        cp_async_commit();
+    };
+
+    const int nChunks = P.raysPadded / KC;
+    prefetch(0, 0);
+    for (int c = 0; c < nChunks; c++)
+    {
+        const int st = c & 1;
+        cp_async_wait_all();
+        __syncthreads(); // chunk c landed; everybody is done computing chunk c-1
+        for (int idx = tid; idx < PB * KC; idx += NT)
         {
-            const float4* src = reinterpret_cast<const float4*>(P.wIrr + (size_t)k0 * N);
-            float4*       dst = reinterpret_cast<float4*>(Bs);
-            for (int idx = tid; idx < KC * N / 4; idx += NT)
-                dst[idx] = __ldg(src + idx);
+            int   p = idx / KC, k = idx % KC;
+            uint2 t = Raw[(st * PB + p) * KC + k];
+            float* dst = As + k * MS + p * 3;
+            dst[0] = h2f_bits((uint16_t)(t.x & 0xffffu));
+            dst[1] = h2f_bits((uint16_t)(t.x >> 16));
+            dst[2] = h2f_bits((uint16_t)(t.y & 0xffffu));
         }
+        if (c + 1 < nChunks)
+            prefetch((c + 1) * KC, st ^ 1);
         __syncthreads();
-#pragma unroll 4
-        for (int k = 0; k < KC; k++)
+        const float*    B = Bs + st * KC * N;
+        const uint32_t* Z = Zs + st * KC;
+        // rays of this chunk with a non-zero weight for the warp's texel group (KC == 32: one ballot), visited in ray order
+        uint32_t live = __ballot_sync(0xffffffffu, (Z[lane] >> grp) & 1u);
+        while (live)
         {
-            float a[8], b[8];
-#pragma unroll
-            for (int i = 0; i < 8; i++)
-                a[i] = As[(mg * 8 + i) * (KC + 1) + k];
-            float4 b0 = *reinterpret_cast<const float4*>(Bs + k * N + ng * 8);
-            float4 b1 = *reinterpret_cast<const float4*>(Bs + k * N + ng * 8 + 4);
+            const int k = __ffs(live) - 1;
+            live &= live - 1;
+            float a[TR], b[8];
+            lds_row<TR>(As + k * MS + lane * TR, a);
+            float4 b0 = *reinterpret_cast<const float4*>(B + k * N + grp * 8);
+            float4 b1 = *reinterpret_cast<const float4*>(B + k * N + grp * 8 + 4);
             b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
 #pragma unroll
-            for (int i = 0; i < 8; i++)
+            for (int i = 0; i < TR; i++)
 #pragma unroll
                 for (int j = 0; j < 8; j++)
                     acc[i][j] = __fmaf_rn(a[i], b[j], acc[i][j]);
         }
-        __syncthreads();
     }
+    __syncthreads(); // before the epilogue overlays the staging buffers
 
-    // epilogue: accumulators -> Cs[row][texel]
 #pragma unroll
-    for (int i = 0; i < 8; i++)
+    for (int i = 0; i < TR; i++)
     {
-        float4* dst = reinterpret_cast<float4*>(Cs + (mg * 8 + i) * N + ng * 8);
+        float4* dst = reinterpret_cast<float4*>(Cs + (lane * TR + i) * N + grp * 8);
         dst[0] = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
         dst[1] = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
     }
@@ -1279,79 +1388,109 @@ __global__ void __launch_bounds__((3 * PB / 8) * 8) blend_irradiance_kernel(cons
     }
 }
 
-// Depth: PB probes per block, rows m = p*2 + {d, d*d} (M = 2*PB), N = 256 texels; thread tile 8 rows x 8 texels.
+// Depth: PB probes per block, rows m = p*2 + {d, d*d} (M = 2*PB), 16 warps x 2 texel groups x 8 texels = 256 texels.
 template <int PB>
-__global__ void __launch_bounds__((2 * PB / 8) * 32) blend_depth_kernel(const __grid_constant__ BlendParams P)
+__global__ void __launch_bounds__(512) blend_depth_kernel(const __grid_constant__ BlendParams P)
 {
-    constexpr int M = 2 * PB, N = 256, NT = (M / 8) * 32;
+    constexpr int M = 2 * PB, MS = M + 4, N = 256, NT = 512, TR = M / 32;
+    static_assert(M % 32 == 0, "rows must split evenly over 32 lanes");
     extern __shared__ __align__(16) float smem[];
-    constexpr int MS = M + 4;    // padded row stride of As (keeps float4 alignment, spreads banks for the k-major stores)
-    float* As = smem;            // [KC][MS] (k-major: all lanes of a warp read the same 8 rows -> broadcast)
-    float* Bs = smem + KC * MS;  // [KC][N]
-    float* Cs = smem;            // epilogue overlay [M][N]
+    float*    As  = smem;                                   // [KC][MS] (d, d*d) of the current chunk
+    float*    Bs  = As + KC * MS;                           // [2][KC][N]
+    uint2*    Raw = reinterpret_cast<uint2*>(Bs + 2 * KC * N); // [2][PB][KC] direction/distance texels
+    uint32_t* Zs  = reinterpret_cast<uint32_t*>(Raw + 2 * PB * KC); // [2][KC]
+    float*    Cs  = smem;                                   // epilogue overlay [M][N]
 
-    const int tid  = threadIdx.x;
-    const int ng   = tid & 31; // texel group
-    const int mg   = tid >> 5; // row group (one per warp)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int probe0 = blockIdx.x * PB;
     const int R = P.raysPerProbe;
 
-    float acc[8][8];
+    float acc[2][TR][8];
 #pragma unroll
-    for (int i = 0; i < 8; i++)
+    for (int g = 0; g < 2; g++)
 #pragma unroll
-        for (int j = 0; j < 8; j++)
-            acc[i][j] = 0.0f;
+        for (int i = 0; i < TR; i++)
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                acc[g][i][j] = 0.0f;
 
-    for (int k0 = 0; k0 < P.raysPadded; k0 += KC)
-    {
+    auto prefetch = [&](int k0, int st) {
         for (int idx = tid; idx < PB * KC; idx += NT)
         {
-            int p = idx / KC, k = idx % KC; // consecutive threads -> consecutive rays of one probe (coalesced)
-            int probe = probe0 + p, ray = k0 + k;
+            int  p = idx / KC, k = idx % KC;
+            int  probe = probe0 + p, ray = k0 + k;
+            bool ok = probe < P.probeCount && ray < R;
+            cp_async_8_zfill(Raw + (st * PB + p) * KC + k, P.dirDist + (ok ? (size_t)probe * R + ray : 0), ok);
+        }
+        const float* src = P.wDepth + (size_t)k0 * N;
+        for (int idx = tid; idx < KC * N / 4; idx += NT)
+            cp_async_16(Bs + st * KC * N + idx * 4, src + idx * 4);
+        if (tid < KC)
+            cp_async_4(Zs + st * KC + tid, P.nzDepth + k0 + tid);
+        cp_async_commit();
+    };
+
+    const int nChunks = P.raysPadded / KC;
+    prefetch(0, 0);
+    for (int c = 0; c < nChunks; c++)
+    {
+        const int st = c & 1, k0 = c * KC;
+        cp_async_wait_all();
+        __syncthreads();
+        for (int idx = tid; idx < PB * KC; idx += NT)
+        {
+            int   p = idx / KC, k = idx % KC;
             float d = 0.0f;
-            if (probe < P.probeCount && ray < R)
+            if (probe0 + p < P.probeCount && k0 + k < R)
             {
-                uint2 t = __ldg(P.dirDist + (size_t)probe * R + ray);
+                uint2 t = Raw[(st * PB + p) * KC + k];
                 d = gmin(P.maxDistance, h2f_bits((uint16_t)(t.y >> 16)) - 0.01f); // ProbeUpdate.glsl:75
                 if (d == -1.0f)
                     d = P.maxDistance;
             }
             *reinterpret_cast<float2*>(As + k * MS + p * 2) = make_float2(d, d * d);
         }
-        {
-            const float4* src = reinterpret_cast<const float4*>(P.wDepth + (size_t)k0 * N);
-            float4*       dst = reinterpret_cast<float4*>(Bs);
-            for (int idx = tid; idx < KC * N / 4; idx += NT)
-                dst[idx] = __ldg(src + idx);
-        }
+        if (c + 1 < nChunks)
+            prefetch((c + 1) * KC, st ^ 1);
         __syncthreads();
-#pragma unroll 4
-        for (int k = 0; k < KC; k++)
+        const float*    B = Bs + st * KC * N;
+        const uint32_t* Z = Zs + st * KC;
+        uint32_t live = __ballot_sync(0xffffffffu, ((Z[lane] >> (warp * 2)) & 3u) != 0u);
+        while (live)
         {
-            float a[8], b[8];
-            float4 a0 = *reinterpret_cast<const float4*>(As + k * MS + mg * 8);
-            float4 a1 = *reinterpret_cast<const float4*>(As + k * MS + mg * 8 + 4);
-            a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
-            float4 b0 = *reinterpret_cast<const float4*>(Bs + k * N + ng * 8);
-            float4 b1 = *reinterpret_cast<const float4*>(Bs + k * N + ng * 8 + 4);
-            b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+            const int k = __ffs(live) - 1;
+            live &= live - 1;
+            const uint32_t z = (Z[k] >> (warp * 2)) & 3u;
+            float a[TR];
+            lds_row<TR>(As + k * MS + lane * TR, a);
 #pragma unroll
-            for (int i = 0; i < 8; i++)
+            for (int g = 0; g < 2; g++)
+            {
+                if (!((z >> g) & 1u))
+                    continue;
+                float  b[8];
+                float4 b0 = *reinterpret_cast<const float4*>(B + k * N + (warp * 2 + g) * 8);
+                float4 b1 = *reinterpret_cast<const float4*>(B + k * N + (warp * 2 + g) * 8 + 4);
+                b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
 #pragma unroll
-                for (int j = 0; j < 8; j++)
-                    acc[i][j] = __fmaf_rn(a[i], b[j], acc[i][j]);
+                for (int i = 0; i < TR; i++)
+#pragma unroll
+                    for (int j = 0; j < 8; j++)
+                        acc[g][i][j] = __fmaf_rn(a[i], b[j], acc[g][i][j]);
+            }
         }
-        __syncthreads();
     }
+    __syncthreads();
 
 #pragma unroll
-    for (int i = 0; i < 8; i++)
-    {
-        float4* dst = reinterpret_cast<float4*>(Cs + (mg * 8 + i) * N + ng * 8);
-        dst[0] = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-        dst[1] = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
-    }
+    for (int g = 0; g < 2; g++)
+#pragma unroll
+        for (int i = 0; i < TR; i++)
+        {
+            float4* dst = reinterpret_cast<float4*>(Cs + (lane * TR + i) * N + (warp * 2 + g) * 8);
+            dst[0] = make_float4(acc[g][i][0], acc[g][i][1], acc[g][i][2], acc[g][i][3]);
+            dst[1] = make_float4(acc[g][i][4], acc[g][i][5], acc[g][i][6], acc[g][i][7]);
+        }
     __syncthreads();
 
     for (int idx = tid; idx < PB * N; idx += NT)
@@ -1361,9 +1500,10 @@ __global__ void __launch_bounds__((2 * PB / 8) * 32) blend_depth_kernel(const __
         if (probeLocal >= P.probeCount)
             continue;
         int   probe = P.probeBegin + probeLocal;
-        float s = __ldg(P.scaleDepth + t);
+        int i, j; // column t of the weight matrix -> texel (i, j)
+        depth_texel_of_column(t, i, j);
+        float s = __ldg(P.scaleDepth + (j * 16 + i));
         float r = Cs[(p * 2 + 0) * N + t] * s, g = Cs[(p * 2 + 1) * N + t] * s;
-        int i = t & 15, j = t >> 4;
         int bx = (probe % P.probesPerRow) * 18 + 1, by = (probe / P.probesPerRow) * 18 + 1;
         if (!P.firstFrame)
         {
@@ -1374,6 +1514,136 @@ __global__ void __launch_bounds__((2 * PB / 8) * 32) blend_depth_kernel(const __
         uint32_t o = (uint32_t)f2h_bits(r) | ((uint32_t)f2h_bits(g) << 16);
         store_with_border<uint32_t>(P.outDepth, P.depthWidth, bx, by, 16, i, j, o, P.fuseBorder != 0);
     }
+}
+
+// Depth, resident form (used whenever the probes' distances fit in shared memory: R <= ~780 at 64 probes per block,
+// <= ~1560 at 32).  ncu on the chunked kernel showed the sparsity win being eaten by the per-chunk block barriers: within a
+// 32-ray chunk some warp always owns a fully live texel row, so every chunk costs its densest warp.  Here the block loads
+// the distances of ALL rays once, synchronises once, and then each warp walks its own live-ray list over the whole ray
+// range without any further block-wide barrier; weights come straight from L1/L2 (one broadcast float4 pair per texel
+// group, prefetched one live ray ahead).  Lane l owns probes l and l+32 (conflict-free column reads of D[p][R+1]).
+template <int PB>
+__global__ void __launch_bounds__(512) blend_depth_resident_kernel(const __grid_constant__ BlendParams P)
+{
+    constexpr int N = 256, NT = 512, NP = PB / 32, M = 2 * PB; // NP probes per lane
+    extern __shared__ __align__(16) float smem[];
+    const int R = P.raysPerProbe, RS = P.raysPadded + 1; // odd row stride: column reads hit 32 distinct banks
+    float* D  = smem;  // [PB][RS] d = min(maxDistance, dist - 0.01)
+    float* Cs = smem;  // epilogue overlay [M][N]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int probe0 = blockIdx.x * PB;
+
+    for (int idx = tid; idx < PB * P.raysPadded; idx += NT)
+    {
+        int   p = idx / P.raysPadded, k = idx % P.raysPadded; // consecutive threads -> consecutive rays (coalesced, conflict-free)
+        float d = 0.0f;
+        if (probe0 + p < P.probeCount && k < R)
+        {
+            uint2 t = __ldg(P.dirDist + (size_t)(probe0 + p) * R + k);
+            d = gmin(P.maxDistance, h2f_bits((uint16_t)(t.y >> 16)) - 0.01f); // ProbeUpdate.glsl:75
+            if (d == -1.0f)
+                d = P.maxDistance;
+        }
+        D[p * RS + k] = d;
+    }
+    __syncthreads();
+
+    float acc[2][2 * NP][8];
+#pragma unroll
+    for (int g = 0; g < 2; g++)
+#pragma unroll
+        for (int i = 0; i < 2 * NP; i++)
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                acc[g][i][j] = 0.0f;
+
+    const float4* W4 = reinterpret_cast<const float4*>(P.wDepth) + warp * 4; // this warp's 16 weights of ray k: W4[k*64 .. +3]
+    float4 w[4], wn[4];
+    for (int k0 = 0; k0 < P.raysPadded; k0 += 32)
+    {
+        const uint32_t zl   = (__ldg(P.nzDepth + k0 + lane) >> (warp * 2)) & 3u;
+        uint32_t       live = __ballot_sync(0xffffffffu, zl != 0u);
+        if (!live)
+            continue;
+        int k = k0 + __ffs(live) - 1;
+        live &= live - 1;
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+            w[q] = __ldg(W4 + (size_t)k * 64 + q);
+        while (true)
+        {
+            int kn = -1;
+            if (live)
+            { // prefetch the next live ray's weights while this one is accumulated
+                kn = k0 + __ffs(live) - 1;
+                live &= live - 1;
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    wn[q] = __ldg(W4 + (size_t)kn * 64 + q);
+            }
+            float a[2 * NP];
+#pragma unroll
+            for (int i = 0; i < NP; i++)
+            {
+                float d      = D[(lane + 32 * i) * RS + k];
+                a[2 * i]     = d;
+                a[2 * i + 1] = d * d;
+            }
+            const float b[2][8] = {{w[0].x, w[0].y, w[0].z, w[0].w, w[1].x, w[1].y, w[1].z, w[1].w},
+                                   {w[2].x, w[2].y, w[2].z, w[2].w, w[3].x, w[3].y, w[3].z, w[3].w}};
+            // the warp's two blocks are horizontal neighbours (an 8x2-texel patch): mostly live together, so no per-block branch
+#pragma unroll
+            for (int g = 0; g < 2; g++)
+#pragma unroll
+                for (int i = 0; i < 2 * NP; i++)
+#pragma unroll
+                    for (int j = 0; j < 8; j++)
+                        acc[g][i][j] = __fmaf_rn(a[i], b[g][j], acc[g][i][j]);
+            if (kn < 0)
+                break;
+            k = kn;
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+                w[q] = wn[q];
+        }
+    }
+    __syncthreads(); // every warp is done reading D before the epilogue overlays it
+
+#pragma unroll
+    for (int g = 0; g < 2; g++)
+#pragma unroll
+        for (int i = 0; i < 2 * NP; i++)
+        {
+            const int row = (lane + 32 * (i >> 1)) * 2 + (i & 1); // m = probe*2 + {d, d*d}
+            float4* dst = reinterpret_cast<float4*>(Cs + row * N + (warp * 2 + g) * 8);
+            dst[0] = make_float4(acc[g][i][0], acc[g][i][1], acc[g][i][2], acc[g][i][3]);
+            dst[1] = make_float4(acc[g][i][4], acc[g][i][5], acc[g][i][6], acc[g][i][7]);
+        }
+    __syncthreads();
+
+    for (int idx = tid; idx < PB * N; idx += NT)
+    {
+        int p = idx / N, t = idx % N;
+        int probeLocal = probe0 + p;
+        if (probeLocal >= P.probeCount)
+            continue;
+        int   probe = P.probeBegin + probeLocal;
+        int i, j; // column t of the weight matrix -> texel (i, j)
+        depth_texel_of_column(t, i, j);
+        float s = __ldg(P.scaleDepth + (j * 16 + i));
+        float r = Cs[(p * 2 + 0) * N + t] * s, g = Cs[(p * 2 + 1) * N + t] * s;
+        int bx = (probe % P.probesPerRow) * 18 + 1, by = (probe / P.probesPerRow) * 18 + 1;
+        if (!P.firstFrame)
+        {
+            uint32_t pv = __ldg(P.prevDepth + (size_t)(by + j + 1) * P.depthWidth + (bx + i + 1));
+            r = mixh(r, h2f_bits((uint16_t)(pv & 0xffffu)), P.hysteresis);
+            g = mixh(g, h2f_bits((uint16_t)(pv >> 16)), P.hysteresis);
+        }
+        uint32_t o = (uint32_t)f2h_bits(r) | ((uint32_t)f2h_bits(g) << 16);
+        store_with_border<uint32_t>(P.outDepth, P.depthWidth, bx, by, 16, i, j, o, P.fuseBorder != 0);
+    }
+    (void)M;
 }
 
 // Standalone border pass (BorderUpdate.glsl:136-156): one warp-sized group of threads per probe and atlas.
@@ -1411,11 +1681,13 @@ void launch_ray_dirs(const float* rot16Host, int R, float4* dirs, cudaStream_t s
     ray_dirs_kernel<<<(R + 127) / 128, 128, 0, s>>>(rot, R, dirs);
 }
 
-void launch_blend_weights(const uint2* dirsHalf, int R, int Rpad, float sharpness, float* wIrr, float* wDepth, float* scaleIrr,
-                          float* scaleDepth, cudaStream_t s)
+int launch_blend_weights(const uint2* dirsHalf, int R, int Rpad, float sharpness, float* wIrr, float* wDepth, float* scaleIrr,
+                         float* scaleDepth, uint32_t* nzIrr, uint32_t* nzDepth, cudaStream_t s)
 {
     blend_weights_kernel<<<dim3(5, Rpad), 64, 0, s>>>(dirsHalf, R, Rpad, sharpness, wIrr, wDepth);
     blend_scales_kernel<<<5, 64, 0, s>>>(wIrr, wDepth, R, scaleIrr, scaleDepth);
+    blend_nonzero_kernel<<<(Rpad + 63) / 64, 64, 0, s>>>(wIrr, wDepth, Rpad, nzIrr, nzDepth);
+    return 3;
 }
 
 void launch_object_inverse(const LuxObjectBuffer* objects, int count, float* inv, cudaStream_t s)
@@ -1484,8 +1756,9 @@ int launch_trace(const TraceParams& p, int variant, unsigned int* chunkCounter, 
 template <int PB>
 static void launch_blend_irradiance_t(const BlendParams& p, cudaStream_t s)
 {
-    constexpr int M = 3 * PB, NT = (M / 8) * 8;
-    size_t main = (size_t)(M * (KC + 1) + KC * 64) * sizeof(float), epi = (size_t)M * 64 * sizeof(float);
+    constexpr int M = 3 * PB;
+    size_t main = (size_t)(KC * (M + 2) + 2 * KC * 64 + 2 * KC) * sizeof(float) + (size_t)2 * PB * KC * sizeof(uint2);
+    size_t epi  = (size_t)M * 64 * sizeof(float);
     size_t smem = main > epi ? main : epi;
     static bool attr = false;
     if (!attr)
@@ -1493,22 +1766,23 @@ static void launch_blend_irradiance_t(const BlendParams& p, cudaStream_t s)
         cudaFuncSetAttribute(blend_irradiance_kernel<PB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr = true;
     }
-    blend_irradiance_kernel<PB><<<(p.probeCount + PB - 1) / PB, NT, smem, s>>>(p);
+    blend_irradiance_kernel<PB><<<(p.probeCount + PB - 1) / PB, 256, smem, s>>>(p);
 }
 
 void launch_blend_irradiance(const BlendParams& p, cudaStream_t s)
 {
-    if (p.probeCount >= 64 * 64) // measured: the 64-probe tile wins as soon as it yields ~half a wave of blocks
+    if (p.probeCount >= 64 * 64)
         launch_blend_irradiance_t<64>(p, s);
     else
-        launch_blend_irradiance_t<16>(p, s);
+        launch_blend_irradiance_t<32>(p, s);
 }
 
 template <int PB>
 static void launch_blend_depth_t(const BlendParams& p, cudaStream_t s)
 {
-    constexpr int M = 2 * PB, NT = (M / 8) * 32;
-    size_t main = (size_t)(KC * (M + 4) + KC * 256) * sizeof(float), epi = (size_t)M * 256 * sizeof(float);
+    constexpr int M = 2 * PB;
+    size_t main = (size_t)(KC * (M + 4) + 2 * KC * 256 + 2 * KC) * sizeof(float) + (size_t)2 * PB * KC * sizeof(uint2);
+    size_t epi  = (size_t)M * 256 * sizeof(float);
     size_t smem = main > epi ? main : epi;
     static bool attr = false;
     if (!attr)
@@ -1516,15 +1790,37 @@ static void launch_blend_depth_t(const BlendParams& p, cudaStream_t s)
         cudaFuncSetAttribute(blend_depth_kernel<PB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr = true;
     }
-    blend_depth_kernel<PB><<<(p.probeCount + PB - 1) / PB, NT, smem, s>>>(p);
+    blend_depth_kernel<PB><<<(p.probeCount + PB - 1) / PB, 512, smem, s>>>(p);
+}
+
+template <int PB>
+static bool launch_blend_depth_resident_t(const BlendParams& p, cudaStream_t s)
+{
+    size_t main = (size_t)PB * (p.raysPadded + 1) * sizeof(float), epi = (size_t)2 * PB * 256 * sizeof(float);
+    size_t smem = main > epi ? main : epi;
+    if (smem > 200 * 1024)
+        return false;
+    static size_t attr = 0;
+    if (smem > attr)
+    {
+        cudaFuncSetAttribute(blend_depth_resident_kernel<PB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
+        attr = 200 * 1024;
+    }
+    blend_depth_resident_kernel<PB><<<(p.probeCount + PB - 1) / PB, 512, smem, s>>>(p);
+    return true;
 }
 
 void launch_blend_depth(const BlendParams& p, cudaStream_t s)
 {
-    if (p.probeCount >= 32 * 64)
-        launch_blend_depth_t<32>(p, s);
+    static const bool resident = getenv("LUX_DEPTH_RESIDENT") != nullptr;
+    if (resident && p.probeCount >= 64 * 64 && launch_blend_depth_resident_t<64>(p, s))
+        return;
+    if (resident && p.probeCount >= 32 * 64 && launch_blend_depth_resident_t<32>(p, s))
+        return;
+    if (p.probeCount >= 64 * 64)
+        launch_blend_depth_t<64>(p, s);
     else
-        launch_blend_depth_t<8>(p, s);
+        launch_blend_depth_t<16>(p, s);
 }
 
 void launch_border(uint2* irr, int irrWidth, uint32_t* depth, int depthWidth, int probesPerRow, int probeBegin, int probeCount,

@@ -62,6 +62,8 @@ struct BlendParams
     const float* wDepth;   // [raysPadded][256]
     const float* scaleIrr; // [64]  1/(2*sum w) or 1
     const float* scaleDepth; // [256]
+    const uint32_t* nzIrr;   // [raysPadded] bit g: texel group g (8 consecutive texels) has a non-zero weight for this ray
+    const uint32_t* nzDepth; // [raysPadded]
     const uint2* prevIrr;  // RGBA16F atlas
     uint2*       outIrr;
     const uint32_t* prevDepth; // RG16F atlas
@@ -70,8 +72,8 @@ struct BlendParams
 
 // per-frame setup: ray directions and the probe-independent blend weights
 void launch_ray_dirs(const float* rot16Host, int raysPerProbe, float4* dirs, cudaStream_t s); // rotation travels as a kernel argument
-void launch_blend_weights(const uint2* dirDistRow0, int raysPerProbe, int raysPadded, float sharpness, float* wIrr, float* wDepth,
-                          float* scaleIrr, float* scaleDepth, cudaStream_t s);
+int  launch_blend_weights(const uint2* dirDistRow0, int raysPerProbe, int raysPadded, float sharpness, float* wIrr, float* wDepth,
+                          float* scaleIrr, float* scaleDepth, uint32_t* nzIrr, uint32_t* nzDepth, cudaStream_t s);
 void launch_chunk_masks(const uint32_t* chunks, const uint32_t* cull, const LuxObjectBuffer* objects, const float* objectInverse,
                         uint32_t objectsCount, float chunkSize, float thrMax, unsigned long long* masks, cudaStream_t s);
 void launch_object_inverse(const LuxObjectBuffer* objects, int count, float* inv, cudaStream_t s);

@@ -262,3 +262,16 @@ def test_64_frame_convergence_shipped_scene_parameters(oracle):
     assert np.mean(deltas[-8:]) <= np.mean(deltas[:8]) and np.mean(deltas[-8:]) < 0.01 * float(cur.mean())
     assert pipe.state().frames == 64
     pipe.close()
+
+
+def test_large_probe_count_big_tile_kernels(oracle):
+    """4096 probes: the 64-probe blend tiles (irradiance<64>, resident depth<64>) and many march chunks per warp."""
+    sc = scenes.cornell_scene(res=32, counts=(16, 16, 16), rays=96, atlas_res=256)
+    rots = [scenes.frame_rotation(f) for f in range(2)]
+    orc = oracle.OraclePipeline(sc)
+    for r in rots:
+        orc.update(r)
+    pipe = run_engine(sc, rots)
+    assert_rays_match(pipe, orc)
+    assert_atlases_match(pipe, orc)
+    pipe.close()
