@@ -106,13 +106,28 @@ def workload_desc(name, sc):
 
 
 def algorithmic_bytes(sc, probes):
-    """SURVEY §8d.  Trace: two RGBA16F stores per ray + SDF + mip read once + both surface atlases once (upper bound).
-    Blend+border: ray buffers read once + previous interiors + new interiors and borders."""
+    """Compulsory HBM bytes per launch.
+    trace (whole stage): two RGBA16F stores per ray + SDF + mip read once + both surface atlases once (upper bound);
+    march: SDF + mip read once + one 20-byte record written per ray;   shade: record read + two RGBA16F stores per ray + SDF once
+    (normal taps) + both surface atlases once;   blend+border: ray buffers read once + previous interiors + new interiors and borders."""
     R = sc.uniform.raysPerProbe
     atlas = (int(sc.atlas_data.resolution) ** 2) * (8 + 4) if sc.atlas_data is not None else 0
-    trace = 16 * probes * R + sc.sdf_bytes() + atlas
-    blend = 16 * probes * R + probes * (64 * 8 + 256 * 4) + probes * (100 * 8 + 324 * 4)
-    return trace, blend
+    sdf = sc.sdf.numel() * 2
+    return {"trace": 16 * probes * R + sc.sdf_bytes() + atlas,
+            "march": 20 * probes * R + sc.sdf_bytes(),
+            "shade": (20 + 16) * probes * R + sdf + atlas,
+            "blend": 16 * probes * R + probes * (64 * 8 + 256 * 4) + probes * (100 * 8 + 324 * 4)}
+
+
+def measured_traffic(workload, world):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/),
+    valid only for the configuration they were taken on."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        t = json.load(open(p))
+        return t.get(f"{workload}@{world}", {})
+    except Exception:
+        return {}
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -275,7 +290,7 @@ def run_lux(args):
         sampler.start()
     launches0 = pipe.state().kernelLaunches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    stage = {"setup": 0.0, "trace": 0.0, "blend": 0.0}
+    stage = {"setup": 0.0, "trace": 0.0, "blend": 0.0, "march": 0.0, "shade": 0.0}
     with torch.cuda.stream(stream):
         e0.record(stream)
     t_wall0 = time.perf_counter()
@@ -285,6 +300,7 @@ def run_lux(args):
             pipe.synchronize()
             t = pipe.stage_ms()
             stage["setup"] += t.setup_ms; stage["trace"] += t.trace_ms; stage["blend"] += t.blend_ms
+            stage["march"] += t.march_ms; stage["shade"] += t.shade_ms
     with torch.cuda.stream(stream):
         e1.record(stream)
     barrier()
@@ -292,17 +308,18 @@ def run_lux(args):
     ms_total = e0.elapsed_time(e1)
     if not args.stage_every_step:
         t = pipe.stage_ms()
-        stage = {"setup": t.setup_ms * args.steps, "trace": t.trace_ms * args.steps, "blend": t.blend_ms * args.steps}
+        stage = {"setup": t.setup_ms * args.steps, "trace": t.trace_ms * args.steps, "blend": t.blend_ms * args.steps,
+                 "march": t.march_ms * args.steps, "shade": t.shade_ms * args.steps}
     launches = pipe.state().kernelLaunches - launches0
     clocks = sampler.stop() if rank == 0 else None
-    tm = torch.tensor([ms_total, stage["trace"], stage["blend"], stage["setup"]], device=dev, dtype=torch.float64)
+    tm = torch.tensor([ms_total, stage["trace"], stage["blend"], stage["setup"], stage["march"], stage["shade"]], device=dev, dtype=torch.float64)
     per_rank = None
     if world > 1:
         allr = [torch.zeros_like(tm) for _ in range(world)]
         dist.all_gather(allr, tm)
         per_rank = [[round(float(x) / args.steps, 4) for x in t.tolist()[1:3]] for t in allr]
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-    ms_total, trace_ms, blend_ms, setup_ms = [float(x) for x in tm.tolist()]
+    ms_total, trace_ms, blend_ms, setup_ms, march_ms, shade_ms = [float(x) for x in tm.tolist()]
     ms_per_step = ms_total / args.steps
     P_timed = st.probeCount * world  # == P unless --emulate-shard
     value = P_timed * R * args.steps / (ms_total * 1e-3)
@@ -343,12 +360,25 @@ def run_lux(args):
         peaks, peak_kind = measured_peaks()
         hbm = float(peaks["hbm_gbs"])
         probes_rank = st.probeCount
-        tb, bb = algorithmic_bytes(sc, probes_rank)
+        stages_b = algorithmic_bytes(sc, probes_rank)
+        march_launch_ms, shade_launch_ms = march_ms / args.steps, shade_ms / args.steps
         trace_launch_ms = trace_ms / args.steps
         blend_launch_ms = blend_ms / args.steps
-        ach = tb / (trace_launch_ms * 1e-3) / 1e9
-        achb = bb / (blend_launch_ms * 1e-3) / 1e9
-        fma = probes_rank * R * 704 / (blend_launch_ms * 1e-3) / 1e12  # dense (value, weight) FMAs per second, T FMA/s
+        traffic = measured_traffic(args.workload, world)
+
+        def roof(kernel, nbytes, ms):
+            a = nbytes / (ms * 1e-3) / 1e9 if ms > 0 else None
+            return {"bound": "hbm", "kernel": kernel, "achieved": a, "peak": hbm, "unit": "GB/s", "frac": (a / hbm) if a else None,
+                    "traffic": traffic.get(kernel), "peak_source": peak_kind, "algorithmic_bytes_per_launch": nbytes, "ms_per_launch": ms}
+
+        dominant = "march_kernel" if march_launch_ms >= shade_launch_ms else "shade_kernel"
+        if march_launch_ms == 0.0:  # --trace simple: one kernel
+            dominant = "trace_kernel"
+        roofs = {"march_kernel": roof("march_kernel", stages_b["march"], march_launch_ms),
+                 "shade_kernel": roof("shade_kernel", stages_b["shade"], shade_launch_ms),
+                 "trace_kernel": roof("trace_kernel", stages_b["trace"], trace_launch_ms),
+                 "blend": roof("blend_irradiance_kernel+blend_depth_kernel", stages_b["blend"], blend_launch_ms)}
+        roofs["blend"]["fp32_tfma_per_s_dense_equivalent"] = probes_rank * R * 704 / (blend_launch_ms * 1e-3) / 1e12
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "ms_per_update": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -356,14 +386,13 @@ def run_lux(args):
             "config": dict(workload_desc(args.workload, sc), parallelism=f"zslab{world}", l2_policy="inputs larger than L2 (no flush)",
                            sharding="probe z-slabs, SDF + surface cache replicated, in-place NCCL all-gather of atlas rows per step"
                            + ("" if world == 1 else (" (on the compute stream)" if args.sync_allgather else " overlapped with the next step's trace"))),
-            "stage_ms": {"setup": setup_ms / args.steps, "trace": trace_launch_ms, "blend_border": blend_launch_ms,
+            "stage_ms": {"setup": setup_ms / args.steps, "trace": trace_launch_ms, "march": march_launch_ms, "shade": shade_launch_ms,
+                         "blend_border": blend_launch_ms,
                          "other_incl_allgather": ms_per_step - (setup_ms + trace_ms + blend_ms) / args.steps},
             "trace_rays_per_s": probes_rank * world * R / (trace_launch_ms * 1e-3),
             "per_rank_trace_blend_ms": per_rank,
-            "roofline": {"bound": "hbm", "kernel": "trace_kernel", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
-                         "traffic": None, "peak_source": peak_kind, "algorithmic_bytes_per_launch": tb},
-            "roofline_blend": {"bound": "hbm", "kernel": "blend_irradiance_kernel+blend_depth_kernel", "achieved": achb, "peak": hbm,
-                               "unit": "GB/s", "frac": achb / hbm, "algorithmic_bytes_per_launch": bb, "fp32_tfma_per_s": fma},
+            "roofline": roofs[dominant],
+            "roofline_stages": {k: v for k, v in roofs.items() if k != dominant and v["ms_per_launch"] > 0},
             "clocks": clocks,
             "e2e": None if e2e_value is None else {"value": e2e_value, "unit": UNIT, "ms_per_update": e2e_s / args.steps * 1e3,
                     "h2d_bytes_per_step": light_bytes + 64, "d2h_bytes_per_step": d2h_bytes,

@@ -203,6 +203,7 @@ typedef struct LuxDDGIState {
 
 typedef struct LuxStageTimes { /* milliseconds of the last lux_ddgi_update, needs FLAG_STAGE_TIMERS */
     float setup_ms, trace_ms, blend_ms, border_ms, total_ms;
+    float march_ms, shade_ms; /* the two kernels of the wavefront trace (0 for the simple kernel) */
 } LuxStageTimes;
 
 /* ---------------------------------------------------------------------------------------------------------

@@ -127,6 +127,8 @@ class StageTimes(C.Structure):
         ("blend_ms", C.c_float),
         ("border_ms", C.c_float),
         ("total_ms", C.c_float),
+        ("march_ms", C.c_float),
+        ("shade_ms", C.c_float),
     ]
 
 

@@ -355,7 +355,8 @@ static int system(LuxDDGIContext& c, const LuxTracePushConstants& push)
     p.records  = (float4*)c.records.ptr;
     p.meta     = (uint32_t*)c.meta.ptr;
     const int variant = (c.flags & LUX_DDGI_FLAG_TRACE_SIMPLE) ? 0 : (c.sdfTex ? 2 : 1);
-    c.launches += launch_trace(p, variant, (unsigned int*)c.chunkCounter.ptr, c.stream, c.lightPending ? c.evLightReady : nullptr);
+    c.launches += launch_trace(p, variant, (unsigned int*)c.chunkCounter.ptr, c.stream, c.lightPending ? c.evLightReady : nullptr,
+                               (c.flags & LUX_DDGI_FLAG_STAGE_TIMERS) ? c.ev[5] : nullptr);
     c.lightPending = false;
     cudaEventRecord(c.evShadeDone, c.stream);
     mark(c, 2);
@@ -980,6 +981,12 @@ int lux_ddgi_get_stage_ms(LuxDDGIContext* c, LuxStageTimes* out)
     cudaEventElapsedTime(&out->blend_ms, c->ev[2], c->ev[3]);
     cudaEventElapsedTime(&out->border_ms, c->ev[3], c->ev[4]);
     cudaEventElapsedTime(&out->total_ms, c->ev[0], c->ev[4]);
+    out->march_ms = out->shade_ms = 0.0f;
+    if (!(c->flags & LUX_DDGI_FLAG_TRACE_SIMPLE))
+    {
+        cudaEventElapsedTime(&out->march_ms, c->ev[1], c->ev[5]);
+        cudaEventElapsedTime(&out->shade_ms, c->ev[5], c->ev[2]);
+    }
     return LUX_OK;
 }
 

@@ -1716,7 +1716,7 @@ void launch_probe_origins(const TraceParams& p, cudaStream_t s)
     probe_origins_kernel<<<(p.probeCount + 255) / 256, 256, 0, s>>>(p, const_cast<float4*>(p.origins));
 }
 
-int launch_trace(const TraceParams& p, int variant, unsigned int* chunkCounter, cudaStream_t s, cudaEvent_t beforeShade)
+int launch_trace(const TraceParams& p, int variant, unsigned int* chunkCounter, cudaStream_t s, cudaEvent_t beforeShade, cudaEvent_t afterMarch)
 {
     if (variant == 0)
     {
@@ -1739,6 +1739,8 @@ int launch_trace(const TraceParams& p, int variant, unsigned int* chunkCounter, 
     if (variant == 2)
     {
         march_kernel<true><<<(unsigned)blocks, 32 * MARCH_WARPS, 0, s>>>(p, chunks, rayGroups, chunkCounter);
+        if (afterMarch)
+            cudaEventRecord(afterMarch, s);
         if (beforeShade) // the march never reads the surface cache: a pending light-cache upload only gates the shade
             cudaStreamWaitEvent(s, beforeShade, 0);
         shade_kernel<true><<<(unsigned)(units * 2), 256, 0, s>>>(p, rayGroups);
@@ -1746,6 +1748,8 @@ int launch_trace(const TraceParams& p, int variant, unsigned int* chunkCounter, 
     else
     {
         march_kernel<false><<<(unsigned)blocks, 32 * MARCH_WARPS, 0, s>>>(p, chunks, rayGroups, chunkCounter);
+        if (afterMarch)
+            cudaEventRecord(afterMarch, s);
         if (beforeShade)
             cudaStreamWaitEvent(s, beforeShade, 0);
         shade_kernel<false><<<(unsigned)(units * 2), 256, 0, s>>>(p, rayGroups);

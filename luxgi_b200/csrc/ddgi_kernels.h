@@ -81,7 +81,9 @@ void launch_object_inverse(const LuxObjectBuffer* objects, int count, float* inv
 // variant 0: one thread per ray (simple); 1: wavefront (march + shade), explicit fp16 loads; 2: wavefront, layered-texture
 // gathers.  Returns the number of kernels launched.
 // `beforeShade` (nullable): event the stream waits on before the first kernel that reads the surface cache.
-int    launch_trace(const TraceParams& p, int variant, unsigned int* chunkCounter, cudaStream_t s, cudaEvent_t beforeShade);
+// `afterMarch` (nullable): recorded between the march and the shade kernel (stage timers).
+int    launch_trace(const TraceParams& p, int variant, unsigned int* chunkCounter, cudaStream_t s, cudaEvent_t beforeShade,
+                    cudaEvent_t afterMarch);
 size_t trace_record_count(int probeCount, int raysPerProbe);
 void   launch_probe_origins(const TraceParams& p, cudaStream_t s);
 void launch_blend_irradiance(const BlendParams& p, cudaStream_t s);

@@ -66,6 +66,11 @@ def lib():
         L.oracle_blend.restype = C.c_int
         L.oracle_blend.argtypes = [C.POINTER(abi.DDGIUniform), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.oracle_blend_ids.restype = C.c_int
+        L.oracle_blend_ids.argtypes = [C.POINTER(abi.DDGIUniform), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.oracle_border_ids.restype = C.c_int
+        L.oracle_border_ids.argtypes = [C.POINTER(abi.DDGIUniform), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.oracle_border.restype = C.c_int
         L.oracle_border.argtypes = [C.POINTER(abi.DDGIUniform), C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.oracle_border_offsets.restype = C.c_int
@@ -149,6 +154,16 @@ def blend(u, rad, dd, prev_irr, prev_dep, out_irr, out_dep, first_frame, probe_b
         count = rad.shape[0]
     rc = lib().oracle_blend(C.byref(u), _ptr(rad), _ptr(dd), ray_row_offset, _ptr(prev_irr), _ptr(prev_dep), _ptr(out_irr),
                             _ptr(out_dep), int(bool(first_frame)), probe_begin, count, int(bool(naive)))
+    assert rc == 0, rc
+
+
+def blend_ids(u, rad, dd, prev_irr, prev_dep, out_irr, out_dep, first_frame, probe_ids, naive=False):
+    """Blend + border of a probe list: row k of rad/dd belongs to probe probe_ids[k]."""
+    ids = np.ascontiguousarray(probe_ids, dtype=np.int32)
+    rc = lib().oracle_blend_ids(C.byref(u), _ptr(rad), _ptr(dd), 0, _ptr(prev_irr), _ptr(prev_dep), _ptr(out_irr), _ptr(out_dep),
+                                int(bool(first_frame)), 0, len(ids), _ptr(ids), int(bool(naive)))
+    assert rc == 0, rc
+    rc = lib().oracle_border_ids(C.byref(u), _ptr(out_irr), _ptr(out_dep), _ptr(ids), len(ids))
     assert rc == 0, rc
 
 

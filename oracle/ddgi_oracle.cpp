@@ -882,25 +882,25 @@ int oracle_trace(const OracleSceneDesc* s, const float* rot16, int probeBegin, i
     return 0;
 }
 
-// Blend probes [probeBegin, probeBegin+count).  Ray buffers hold rows for probes rayRowOffset...
+// Blend probes [probeBegin, probeBegin+count), or, when probeIds != null, the listed probes: ray-buffer row k then belongs to
+// probe probeIds[k] (stratified subsamples of large volumes).  Otherwise the ray buffers hold rows for probes rayRowOffset...
 // naive != 0: literal per-(texel, ray) evaluation as in the shader (this is the timed CPU baseline);
 // naive == 0: weights hoisted per (texel, ray) once (bit-identical; see test_oracle_kat.py).
-int oracle_blend(const LuxDDGIUniform* ddgi, const uint16_t* radiance, const uint16_t* dirDist, int rayRowOffset,
-                 const uint16_t* prevIrr, const uint16_t* prevDepth, uint16_t* outIrr, uint16_t* outDepth, int firstFrame,
-                 int probeBegin, int count, int naive)
+int oracle_blend_ids(const LuxDDGIUniform* ddgi, const uint16_t* radiance, const uint16_t* dirDist, int rayRowOffset,
+                     const uint16_t* prevIrr, const uint16_t* prevDepth, uint16_t* outIrr, uint16_t* outDepth, int firstFrame,
+                     int probeBegin, int count, const int32_t* probeIds, int naive)
 {
     if (!ddgi || !radiance || !dirDist || !outIrr || !outDepth)
         return -1;
     if (!firstFrame && (!prevIrr || !prevDepth))
         return -1;
-    BlendArgs a{ddgi, radiance, dirDist, rayRowOffset, prevIrr, prevDepth, outIrr, outDepth, firstFrame};
     const int R = ddgi->raysPerProbe, si = ddgi->irradianceProbeSideLength, sd = ddgi->depthProbeSideLength;
 
     std::vector<float> wi, wd;
     if (!naive && count > 0)
     {
-        // Ray directions are probe-independent (GISDFRays.comp:73): take them from the first probe's row.
-        const uint16_t* dd = dirDist + (size_t)(probeBegin - rayRowOffset) * R * 4;
+        // Ray directions are probe-independent (GISDFRays.comp:73): take them from the first row.
+        const uint16_t* dd = probeIds ? dirDist : dirDist + (size_t)(probeBegin - rayRowOffset) * R * 4;
         wi.resize((size_t)si * si * R);
         wd.resize((size_t)sd * sd * R);
         for (int j = 0; j < si; j++)
@@ -923,13 +923,37 @@ int oracle_blend(const LuxDDGIUniform* ddgi, const uint16_t* radiance, const uin
 #pragma omp parallel for schedule(dynamic, 1)
     for (int k = 0; k < count; k++)
     {
-        int probe = probeBegin + k;
+        int probe = probeIds ? probeIds[k] : probeBegin + k;
+        // with a probe list, row k of the ray buffers is probe probeIds[k]: express that through a per-probe row offset
+        BlendArgs a{ddgi, radiance, dirDist, probeIds ? probe - k : rayRowOffset, prevIrr, prevDepth, outIrr, outDepth, firstFrame};
         for (int j = 0; j < si; j++)
             for (int i = 0; i < si; i++)
                 blendIrradianceTexel(a, probe, i, j, naive ? nullptr : &wi[((size_t)j * si + i) * R]);
         for (int j = 0; j < sd; j++)
             for (int i = 0; i < sd; i++)
                 blendDepthTexel(a, probe, i, j, naive ? nullptr : &wd[((size_t)j * sd + i) * R]);
+    }
+    return 0;
+}
+
+int oracle_blend(const LuxDDGIUniform* ddgi, const uint16_t* radiance, const uint16_t* dirDist, int rayRowOffset,
+                 const uint16_t* prevIrr, const uint16_t* prevDepth, uint16_t* outIrr, uint16_t* outDepth, int firstFrame,
+                 int probeBegin, int count, int naive)
+{
+    return oracle_blend_ids(ddgi, radiance, dirDist, rayRowOffset, prevIrr, prevDepth, outIrr, outDepth, firstFrame, probeBegin, count,
+                            nullptr, naive);
+}
+
+int oracle_border_ids(const LuxDDGIUniform* ddgi, uint16_t* irr, uint16_t* depth, const int32_t* probeIds, int count)
+{
+    if (!ddgi || !probeIds)
+        return -1;
+    for (int k = 0; k < count; k++)
+    {
+        if (irr)
+            borderProbe(irr, ddgi->irradianceTextureWidth, 4, ddgi->irradianceProbeSideLength, probeIds[k]);
+        if (depth)
+            borderProbe(depth, ddgi->depthTextureWidth, 2, ddgi->depthProbeSideLength, probeIds[k]);
     }
     return 0;
 }

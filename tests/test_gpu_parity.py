@@ -275,3 +275,51 @@ def test_large_probe_count_big_tile_kernels(oracle):
     assert_rays_match(pipe, orc)
     assert_atlases_match(pipe, orc)
     pipe.close()
+
+
+def probe_tiles(atlas, u, ids, side):
+    S = side + 2
+    per_row = u.probeCounts[0] * u.probeCounts[1]
+    return np.stack([atlas[1 + (p // per_row) * S: 1 + (p // per_row) * S + S, 1 + (p % per_row) * S: 1 + (p % per_row) * S + S] for p in ids])
+
+
+@pytest.mark.parametrize("cfg,sample", [("c4", 4096)])
+def test_full_size_config_on_a_stratified_probe_subsample(oracle, cfg, sample):
+    """BASELINE configs[3] at FULL size (city 512^3, 64x16x64 probes, 512 rays, 33.5 M rays per update) on the GPU; the oracle
+    replays a stratified subsample of probes from the same device-generated inputs, two frames (the second
+    through the hysteresis branch).  Rays and the subsample's atlas tiles (interior + border) must match bit for bit."""
+    import torch
+
+    sc = scenes.build(cfg, device="cuda")
+    u = sc.uniform
+    P = sc.probes
+    ids = (np.arange(sample, dtype=np.int64) * P // sample).astype(np.int32)
+    osc = oracle.OracleScene(sc)  # host copies of the device-generated inputs
+    pipe = ddgi.DDGIPipeline(u)
+    pipe.set_scene(sc)
+    irr = [oracle.new_atlases(u)[0] for _ in range(2)]
+    dep = [oracle.new_atlases(u)[1] for _ in range(2)]
+    for f in range(2):
+        rot = scenes.frame_rotation(f)
+        pipe.update(rot)
+        rad, dd, _, _ = osc.trace(rot, probe_ids=ids)
+        grad, gdd = pipe.radiance[ids], pipe.direction_distance[ids]
+        assert np.array_equal(gdd, dd), f"frame {f}: direction/distance differ on {(gdd != dd).sum()} values"
+        assert np.array_equal(grad, rad), f"frame {f}: radiance differs on {(grad != rad).sum()} values"
+        oracle.blend_ids(u, rad, dd, irr[f % 2], dep[f % 2], irr[1 - f % 2], dep[1 - f % 2], first_frame=(f == 0), probe_ids=ids)
+        for name, got, want, side in (("irradiance", pipe.irradiance, irr[1 - f % 2], 8), ("depth", pipe.depth, dep[1 - f % 2], 16)):
+            rep = compare_atlas(name, probe_tiles(got, u, ids, side), probe_tiles(want, u, ids, side))
+            print(cfg, f, rep)
+            assert rep["out_of_tolerance"] == 0 and rep["mismatched_bits"] == 0, rep
+    # size-independent properties on the FULL atlases: border idempotence and the mirror rule on every probe
+    full_i, full_d = pipe.irradiance, pipe.depth
+    pipe.border_update()
+    pipe.synchronize()
+    assert np.array_equal(pipe.irradiance, full_i) and np.array_equal(pipe.depth, full_d)
+    t = full_i[1:-1, 1:-1].reshape(u.probeCounts[2], 10, -1, 10, 4).transpose(0, 2, 1, 3, 4)  # [z][xy][10][10][4]
+    assert np.array_equal(t[:, :, 0, 1:-1], t[:, :, 1, 1:-1][:, :, ::-1]) and np.array_equal(t[:, :, 1:-1, 0], t[:, :, 1:-1, 1][:, :, ::-1])
+    assert np.array_equal(t[:, :, 0, 0], t[:, :, -2, -2]) and np.array_equal(t[:, :, -1, -1], t[:, :, 1, 1])
+    assert np.isfinite(f16(full_i)).all() and np.isfinite(f16(full_d)).all()
+    pipe.close()
+    del sc
+    torch.cuda.empty_cache()
