@@ -275,6 +275,17 @@ LUX_API int lux_ddgi_set_ray_buffers(LuxDDGIContext* ctx, const void* radianceRG
 LUX_API int lux_ddgi_restore(LuxDDGIContext* ctx, const void* irradianceRGBA16F, const void* depthRG16F,
                      int32_t frames, int32_t pingPong);
 
+/* ---- consumer side (the step after the path) ----
+ * sampleIrradiance() of Shaders/DDGI/DDGICommon.glsl:163-233 against the atlases most recently written, for `count` points:
+ * P, N, Wo and out are [count][3] floats.  Both atlas taps are bilinear through the 1-texel borders (linear / repeat sampler). */
+LUX_API int lux_ddgi_sample_irradiance(LuxDDGIContext* ctx, int32_t count, const float* P, const float* N, const float* Wo, float* out,
+                                       LuxMemKind kind);
+/* sample_probe::system (DDGIRenderer.cpp:467-503) = Shaders/DDGI/SampleProbe.comp: per pixel of a width x height G-buffer
+ * (depth D32F [h][w]; normals RGBA32F [h][w][4] with xy = octahedral normal, GBuffer.cpp:17) reconstruct the world position with
+ * viewProjInv (column-major), sample the probe volume and write RGBA32F [h][w][4] (the INDIRECT_LIGHTING target, GBuffer.cpp:24). */
+LUX_API int lux_ddgi_sample_probe(LuxDDGIContext* ctx, int32_t width, int32_t height, const float* depthD32F, const float* normalsRGBA32F,
+                                  const float cameraPosition[4], const float viewProjInv[16], float* outRGBA32F, LuxMemKind kind);
+
 LUX_API int lux_ddgi_get_state(LuxDDGIContext* ctx, LuxDDGIState* out);
 /* z-slab layout of shard `rank` of `world` without a context (pure host arithmetic, usable on a machine with no GPU):
  * fills probeBegin/Count and the atlas row ranges of `out`; the other fields are zero. */

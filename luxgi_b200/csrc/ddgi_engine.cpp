@@ -968,6 +968,84 @@ int lux_ddgi_get_state(LuxDDGIContext* c, LuxDDGIState* out)
     return LUX_OK;
 }
 
+// ---- consumer side: the step after the path (sample_probe::system, DDGIRenderer.cpp:467-503; SampleProbe.comp) ----
+static int stageToDevice(LuxDDGIContext* c, const void* src, size_t bytes, LuxMemKind kind, void** dev, bool* owned)
+{
+    *owned = false;
+    if (kind == LUX_MEM_DEVICE)
+    {
+        *dev = const_cast<void*>(src);
+        return LUX_OK;
+    }
+    LUX_CUDA(cudaMalloc(dev, bytes ? bytes : 1));
+    *owned = true;
+    LUX_CUDA(cudaMemcpyAsync(*dev, src, bytes, cudaMemcpyHostToDevice, c->stream));
+    return LUX_OK;
+}
+
+int lux_ddgi_sample_irradiance(LuxDDGIContext* c, int32_t count, const float* P, const float* N, const float* Wo, float* out, LuxMemKind kind)
+{
+    CHECK_CTX(c);
+    if (count < 0 || !P || !N || !Wo || !out)
+        return fail(LUX_ERR_INVALID_ARG, "bad sample_irradiance arguments");
+    if (c->frames == 0)
+        return fail(LUX_ERR_NOT_READY, "no atlas has been written yet");
+    const size_t bytes = (size_t)count * 3 * sizeof(float);
+    void *dP, *dN, *dW, *dO;
+    bool  oP, oN, oW, oO;
+    int   rc;
+    if ((rc = stageToDevice(c, P, bytes, kind, &dP, &oP)) != LUX_OK) return rc;
+    if ((rc = stageToDevice(c, N, bytes, kind, &dN, &oN)) != LUX_OK) return rc;
+    if ((rc = stageToDevice(c, Wo, bytes, kind, &dW, &oW)) != LUX_OK) return rc;
+    if (kind == LUX_MEM_DEVICE) { dO = out; oO = false; }
+    else { LUX_CUDA(cudaMalloc(&dO, bytes ? bytes : 1)); oO = true; }
+    lux::launch_sample_irradiance(c->uniform, c->irradiance[c->lastWritten].ptr, c->depth[c->lastWritten].ptr, count, (const float*)dP,
+                                  (const float*)dN, (const float*)dW, (float*)dO, c->stream);
+    c->launches += count > 0 ? 1 : 0;
+    LUX_CUDA(cudaGetLastError());
+    if (oO)
+    {
+        LUX_CUDA(cudaMemcpyAsync(out, dO, bytes, cudaMemcpyDeviceToHost, c->stream));
+        LUX_CUDA(cudaStreamSynchronize(c->stream));
+        cudaFree(dO);
+    }
+    if (oP) cudaFree(dP);
+    if (oN) cudaFree(dN);
+    if (oW) cudaFree(dW);
+    return LUX_OK;
+}
+
+int lux_ddgi_sample_probe(LuxDDGIContext* c, int32_t width, int32_t height, const float* depthD32F, const float* normalsRGBA32F,
+                          const float cameraPosition[4], const float viewProjInv[16], float* outRGBA32F, LuxMemKind kind)
+{
+    CHECK_CTX(c);
+    if (width <= 0 || height <= 0 || !depthD32F || !normalsRGBA32F || !cameraPosition || !viewProjInv || !outRGBA32F)
+        return fail(LUX_ERR_INVALID_ARG, "bad sample_probe arguments");
+    if (c->frames == 0)
+        return fail(LUX_ERR_NOT_READY, "no atlas has been written yet");
+    const size_t px = (size_t)width * height;
+    void *dD, *dN, *dO;
+    bool  oD, oN, oO;
+    int   rc;
+    if ((rc = stageToDevice(c, depthD32F, px * 4, kind, &dD, &oD)) != LUX_OK) return rc;
+    if ((rc = stageToDevice(c, normalsRGBA32F, px * 16, kind, &dN, &oN)) != LUX_OK) return rc;
+    if (kind == LUX_MEM_DEVICE) { dO = outRGBA32F; oO = false; }
+    else { LUX_CUDA(cudaMalloc(&dO, px * 16)); oO = true; }
+    lux::launch_sample_probe(c->uniform, c->irradiance[c->lastWritten].ptr, c->depth[c->lastWritten].ptr, width, height, (const float*)dD,
+                             (const float*)dN, cameraPosition, viewProjInv, (float*)dO, c->stream);
+    c->launches += 1;
+    LUX_CUDA(cudaGetLastError());
+    if (oO)
+    {
+        LUX_CUDA(cudaMemcpyAsync(outRGBA32F, dO, px * 16, cudaMemcpyDeviceToHost, c->stream));
+        LUX_CUDA(cudaStreamSynchronize(c->stream));
+        cudaFree(dO);
+    }
+    if (oD) cudaFree(dD);
+    if (oN) cudaFree(dN);
+    return LUX_OK;
+}
+
 int lux_ddgi_get_stage_ms(LuxDDGIContext* c, LuxStageTimes* out)
 {
     CHECK_CTX(c);

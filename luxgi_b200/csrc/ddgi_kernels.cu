@@ -1681,6 +1681,207 @@ __global__ void border_kernel(T* __restrict__ img, int W, int probesPerRow, int 
 }
 
 // =====================================================================================================================
+// Consumer ("next" row f2): sampleIrradiance (DDGICommon.glsl:163-233) and SampleProbe.comp
+// =====================================================================================================================
+
+struct AtlasView
+{
+    const uint16_t* d;
+    int             w, h, c;
+};
+
+__device__ __forceinline__ int wrapi(int i, int n) { return ((i % n) + n) % n; }
+
+// textureLod(sampler2D, uv, 0): bilinear, repeat wrap, fp16 texels, fp32 weights
+__device__ __forceinline__ void sample_atlas(const AtlasView& t, float u, float v, float* out)
+{
+    float x = u * (float)t.w - 0.5f, y = v * (float)t.h - 0.5f;
+    float fx = floorf(x), fy = floorf(y);
+    float ax = x - fx, ay = y - fy;
+    int   x0 = wrapi((int)fx, t.w), x1 = wrapi((int)fx + 1, t.w), y0 = wrapi((int)fy, t.h), y1 = wrapi((int)fy + 1, t.h);
+    for (int k = 0; k < t.c; k++)
+    {
+        float a = lerp1(ld_h(t.d + ((size_t)y0 * t.w + x0) * t.c + k), ld_h(t.d + ((size_t)y0 * t.w + x1) * t.c + k), ax);
+        float b = lerp1(ld_h(t.d + ((size_t)y1 * t.w + x0) * t.c + k), ld_h(t.d + ((size_t)y1 * t.w + x1) * t.c + k), ax);
+        out[k]  = lerp1(a, b, ay);
+    }
+}
+
+__device__ __forceinline__ void oct_encode(f3 v, float& ox, float& oy)
+{
+    float l1  = (fabsf(v.x) + fabsf(v.y)) + fabsf(v.z);
+    float inv = __fdiv_rn(1.0f, l1);
+    ox = v.x * inv;
+    oy = v.y * inv;
+    if (v.z < 0.0f)
+    {
+        float qx = (1.0f - fabsf(oy)) * sign_not_zero(ox), qy = (1.0f - fabsf(ox)) * sign_not_zero(oy);
+        ox = qx;
+        oy = qy;
+    }
+}
+
+// DDGICommon.glsl:141-158
+__device__ __forceinline__ void texture_coord_from_direction(f3 dir, int probeIndex, int width, int height, int side, float& u, float& v)
+{
+    float ox, oy;
+    oct_encode(normalize3(dir), ox, oy);
+    float zx = (ox + 1.0f) * 0.5f, zy = (oy + 1.0f) * 0.5f;
+    float withBorder = (float)side + 2.0f;
+    float tx = __fdiv_rn(zx * (float)side, (float)width), ty = __fdiv_rn(zy * (float)side, (float)height);
+    int   perRow = (width - 2) / (int)withBorder;
+    float fi = (float)probeIndex, fp = (float)perRow;
+    float modv = fi - fp * floorf(__fdiv_rn(fi, fp));
+    float px = modv * withBorder + 2.0f, py = (float)(probeIndex / perRow) * withBorder + 2.0f;
+    u = __fdiv_rn(px, (float)width) + tx;
+    v = __fdiv_rn(py, (float)height) + ty;
+}
+
+__device__ f3 sample_irradiance(const LuxDDGIUniform& ddgi, f3 P, f3 N, f3 Wo, const AtlasView& irr, const AtlasView& dep)
+{
+    int   bg[3], cnt[3] = {ddgi.probeCounts[0], ddgi.probeCounts[1], ddgi.probeCounts[2]};
+    float Pv[3] = {P.x, P.y, P.z};
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+        bg[a] = iclamp((int)__fdiv_rn(Pv[a] - ddgi.startPosition[a], ddgi.step[a]), 0, cnt[a] - 1);
+    f3 base = {ddgi.step[0] * (float)bg[0] + ddgi.startPosition[0], ddgi.step[1] * (float)bg[1] + ddgi.startPosition[1],
+               ddgi.step[2] * (float)bg[2] + ddgi.startPosition[2]};
+    f3    sum = {0.0f, 0.0f, 0.0f};
+    float sumWeight = 0.0f;
+    float al[3] = {gclamp(__fdiv_rn(P.x - base.x, ddgi.step[0]), 0.0f, 1.0f), gclamp(__fdiv_rn(P.y - base.y, ddgi.step[1]), 0.0f, 1.0f),
+                   gclamp(__fdiv_rn(P.z - base.z, ddgi.step[2]), 0.0f, 1.0f)};
+#pragma unroll 1
+    for (int i = 0; i < 8; ++i)
+    {
+        int off[3] = {i & 1, (i >> 1) & 1, (i >> 2) & 1}, pg[3];
+        float tri[3];
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+        {
+            pg[a]  = iclamp(bg[a] + off[a], 0, cnt[a] - 1);
+            tri[a] = (1.0f - al[a]) * (1.0f - (float)off[a]) + al[a] * (float)off[a];
+        }
+        f3 probePos = {ddgi.step[0] * (float)pg[0] + ddgi.startPosition[0], ddgi.step[1] * (float)pg[1] + ddgi.startPosition[1],
+                       ddgi.step[2] * (float)pg[2] + ddgi.startPosition[2]};
+        float weight = 1.0f;
+        f3    dirToProbe = normalize3(probePos - P);
+        float bf = gmax(0.0001f, (dot3(dirToProbe, N) + 1.0f) * 0.5f);
+        weight *= bf * bf + 0.2f;
+        int probeIdx = pg[0] + pg[1] * cnt[0] + pg[2] * cnt[0] * cnt[1];
+
+        f3    vBias        = (N + Wo * 3.0f) * ddgi.normalBias;
+        f3    probeToPoint = (P - probePos) + vBias;
+        f3    dir          = normalize3({-probeToPoint.x, -probeToPoint.y, -probeToPoint.z});
+        float u, v, tmp[4];
+        texture_coord_from_direction({-dir.x, -dir.y, -dir.z}, probeIdx, ddgi.depthTextureWidth, ddgi.depthTextureHeight, ddgi.depthProbeSideLength, u, v);
+        float dist = length3(probeToPoint);
+        sample_atlas(dep, u, v, tmp);
+        float mean = tmp[0];
+        float variance = fabsf(tmp[0] * tmp[0] - tmp[1]);
+        float dm = gmax(dist - mean, 0.0f);
+        float cheb = __fdiv_rn(variance, variance + dm * dm);
+        cheb = gmax(cheb * cheb * cheb, 0.0f);
+        weight *= (dist <= mean) ? 1.0f : cheb;
+        weight = gmax(0.000001f, weight);
+
+        texture_coord_from_direction(normalize3(N), probeIdx, ddgi.irradianceTextureWidth, ddgi.irradianceTextureHeight, ddgi.irradianceProbeSideLength, u, v);
+        sample_atlas(irr, u, v, tmp);
+        float e = ddgi.ddgiGamma * 0.5f;
+        f3    pi = {pow_rn(tmp[0], e), pow_rn(tmp[1], e), pow_rn(tmp[2], e)};
+        const float crush = 0.2f;
+        if (weight < crush)
+            weight *= weight * weight * __fdiv_rn(1.0f, crush * crush);
+        weight *= tri[0] * tri[1] * tri[2];
+        sum = sum + pi * weight;
+        sumWeight += weight;
+    }
+    f3 net = {__fdiv_rn(sum.x, sumWeight), __fdiv_rn(sum.y, sumWeight), __fdiv_rn(sum.z, sumWeight)};
+    net    = net * net;
+    return net * 6.283185482025146484375f;
+}
+
+__global__ void sample_irradiance_kernel(const __grid_constant__ LuxDDGIUniform ddgi, const uint16_t* __restrict__ irr,
+                                         const uint16_t* __restrict__ dep, int count, const float* __restrict__ P, const float* __restrict__ N,
+                                         const float* __restrict__ Wo, float* __restrict__ out)
+{
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count)
+        return;
+    AtlasView ai{irr, ddgi.irradianceTextureWidth, ddgi.irradianceTextureHeight, 4}, ad{dep, ddgi.depthTextureWidth, ddgi.depthTextureHeight, 2};
+    f3 r = sample_irradiance(ddgi, {P[3 * k], P[3 * k + 1], P[3 * k + 2]}, {N[3 * k], N[3 * k + 1], N[3 * k + 2]},
+                             {Wo[3 * k], Wo[3 * k + 1], Wo[3 * k + 2]}, ai, ad);
+    out[3 * k] = r.x; out[3 * k + 1] = r.y; out[3 * k + 2] = r.z;
+}
+
+struct SampleProbeArgs
+{
+    LuxDDGIUniform ddgi;
+    float          cameraPosition[4];
+    float          viewProjInv[16];
+    int            width, height;
+};
+
+// SampleProbe.comp:36-60
+__global__ void sample_probe_kernel(const __grid_constant__ SampleProbeArgs A, const uint16_t* __restrict__ irr, const uint16_t* __restrict__ dep,
+                                    const float* __restrict__ gDepth, const float4* __restrict__ gNormal, float4* __restrict__ out)
+{
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= A.width || y >= A.height)
+        return;
+    size_t o = (size_t)y * A.width + x;
+    float  d = __ldg(gDepth + o);
+    if (d == 1.0f)
+    {
+        out[o] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        return;
+    }
+    float tx = __fdiv_rn((float)x + 0.5f, (float)A.width), ty = __fdiv_rn((float)y + 0.5f, (float)A.height);
+    float sx = tx * 2.0f - 1.0f, sy = ty * 2.0f - 1.0f;
+    const float* m = A.viewProjInv;
+    float wx = ((m[0] * sx + m[4] * sy) + m[8] * d) + m[12] * 1.0f;
+    float wy = ((m[1] * sx + m[5] * sy) + m[9] * d) + m[13] * 1.0f;
+    float wz = ((m[2] * sx + m[6] * sy) + m[10] * d) + m[14] * 1.0f;
+    float ww = ((m[3] * sx + m[7] * sy) + m[11] * d) + m[15] * 1.0f;
+    f3 Pw = {__fdiv_rn(wx, ww), __fdiv_rn(wy, ww), __fdiv_rn(wz, ww)};
+    float4 n4 = __ldg(gNormal + o);
+    // octohedralToDirection, Common/Math.glsl:27-33
+    f3 v = {n4.x, n4.y, (1.0f - fabsf(n4.x)) - fabsf(n4.y)};
+    if (v.z < 0.0f)
+    {
+        float s0 = (v.x >= 0.0f ? 1.0f : 0.0f) * 2.0f - 1.0f, s1 = (v.y >= 0.0f ? 1.0f : 0.0f) * 2.0f - 1.0f;
+        float nx = (1.0f - fabsf(v.y)) * s0, ny = (1.0f - fabsf(v.x)) * s1;
+        v.x = nx;
+        v.y = ny;
+    }
+    f3 Nn = normalize3(v);
+    f3 cam = {A.cameraPosition[0], A.cameraPosition[1], A.cameraPosition[2]};
+    f3 Wo = normalize3(cam - Pw);
+    AtlasView ai{irr, A.ddgi.irradianceTextureWidth, A.ddgi.irradianceTextureHeight, 4}, ad{dep, A.ddgi.depthTextureWidth, A.ddgi.depthTextureHeight, 2};
+    f3 r = sample_irradiance(A.ddgi, Pw, Nn, Wo, ai, ad);
+    out[o] = make_float4(r.x, r.y, r.z, 1.0f);
+}
+
+void launch_sample_irradiance(const LuxDDGIUniform& ddgi, const void* irr, const void* dep, int count, const float* P, const float* N,
+                              const float* Wo, float* out, cudaStream_t s)
+{
+    if (count > 0)
+        sample_irradiance_kernel<<<(count + 127) / 128, 128, 0, s>>>(ddgi, (const uint16_t*)irr, (const uint16_t*)dep, count, P, N, Wo, out);
+}
+
+void launch_sample_probe(const LuxDDGIUniform& ddgi, const void* irr, const void* dep, int width, int height, const float* gDepth,
+                         const float* gNormal, const float* cameraPosition, const float* viewProjInv, float* out, cudaStream_t s)
+{
+    SampleProbeArgs a;
+    a.ddgi = ddgi;
+    for (int i = 0; i < 4; i++) a.cameraPosition[i] = cameraPosition[i];
+    for (int i = 0; i < 16; i++) a.viewProjInv[i] = viewProjInv[i];
+    a.width = width;
+    a.height = height;
+    dim3 block(32, 8), grid((width + 31) / 32, (height + 7) / 8);
+    sample_probe_kernel<<<grid, block, 0, s>>>(a, (const uint16_t*)irr, (const uint16_t*)dep, gDepth, (const float4*)gNormal, (float4*)out);
+}
+
+// =====================================================================================================================
 // Launchers
 // =====================================================================================================================
 

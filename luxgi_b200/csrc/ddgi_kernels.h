@@ -92,4 +92,10 @@ void launch_border(uint2* irr, int irrWidth, uint32_t* depth, int depthWidth, in
                    cudaStream_t s);
 
 
+// consumer side
+void launch_sample_irradiance(const LuxDDGIUniform& ddgi, const void* irr, const void* dep, int count, const float* P, const float* N,
+                              const float* Wo, float* out, cudaStream_t s);
+void launch_sample_probe(const LuxDDGIUniform& ddgi, const void* irr, const void* dep, int width, int height, const float* gDepth,
+                         const float* gNormal, const float* cameraPosition, const float* viewProjInv, float* out, cudaStream_t s);
+
 } // namespace lux

@@ -24,7 +24,7 @@ EXPORTS = [
     "lux_ddgi_update_surface_light_cache", "lux_ddgi_set_skybox", "lux_ddgi_trace_rays", "lux_ddgi_probe_update",
     "lux_ddgi_border_update", "lux_ddgi_end_frame", "lux_ddgi_update", "lux_ddgi_synchronize", "lux_ddgi_get_buffer",
     "lux_ddgi_download", "lux_ddgi_download_async", "lux_ddgi_download_rows_async", "lux_ddgi_set_ray_buffers", "lux_ddgi_restore", "lux_ddgi_get_state", "lux_ddgi_shard_layout",
-    "lux_ddgi_get_stage_ms",
+    "lux_ddgi_get_stage_ms", "lux_ddgi_sample_irradiance", "lux_ddgi_sample_probe",
 ]
 
 
@@ -70,6 +70,8 @@ def load():
         "lux_ddgi_get_state": [vp, C.POINTER(abi.State)],
         "lux_ddgi_shard_layout": [C.POINTER(abi.DDGIUniform), i32, i32, C.POINTER(abi.State)],
         "lux_ddgi_get_stage_ms": [vp, C.POINTER(abi.StageTimes)],
+        "lux_ddgi_sample_irradiance": [vp, i32, vp, vp, vp, vp, i32],
+        "lux_ddgi_sample_probe": [vp, i32, i32, vp, vp, vp, vp, vp, i32],
     }
     for name, argtypes in sig.items():
         fn = getattr(L, name)
@@ -303,6 +305,24 @@ class DDGIPipeline:
     def restore(self, irradiance, depth, frames, ping_pong):
         a, b = _as_host(irradiance), _as_host(depth)
         _check(self._lib.lux_ddgi_restore(self._h, _host_ptr(a), _host_ptr(b), int(frames), int(ping_pong)))
+
+    # ---- consumer side (SampleProbe.comp / sampleIrradiance) --------------------------------------------------------
+    def sample_irradiance(self, P, N, Wo) -> np.ndarray:
+        P, N, Wo = (np.ascontiguousarray(a, dtype=np.float32).reshape(-1, 3) for a in (P, N, Wo))
+        out = np.empty_like(P)
+        _check(self._lib.lux_ddgi_sample_irradiance(self._h, len(P), _host_ptr(P), _host_ptr(N), _host_ptr(Wo), _host_ptr(out), abi.MEM_HOST))
+        return out
+
+    def sample_probe(self, depth, normals, camera_position, view_proj_inv) -> np.ndarray:
+        depth = np.ascontiguousarray(depth, dtype=np.float32)
+        normals = np.ascontiguousarray(normals, dtype=np.float32)
+        h, w = depth.shape
+        cam = np.ascontiguousarray(camera_position, dtype=np.float32).reshape(4)
+        vpi = np.ascontiguousarray(view_proj_inv, dtype=np.float32).reshape(16)
+        out = np.empty((h, w, 4), dtype=np.float32)
+        _check(self._lib.lux_ddgi_sample_probe(self._h, w, h, _host_ptr(depth), _host_ptr(normals), _host_ptr(cam), _host_ptr(vpi), _host_ptr(out),
+                                               abi.MEM_HOST))
+        return out
 
     @property
     def radiance(self):

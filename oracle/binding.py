@@ -167,6 +167,32 @@ def blend_ids(u, rad, dd, prev_irr, prev_dep, out_irr, out_dep, first_frame, pro
     assert rc == 0, rc
 
 
+def sample_irradiance(u, irr, dep, P, N, Wo):
+    P, N, Wo = (np.ascontiguousarray(a, dtype=np.float32).reshape(-1, 3) for a in (P, N, Wo))
+    out = np.empty_like(P)
+    L = lib()
+    L.oracle_sample_irradiance.restype = C.c_int
+    L.oracle_sample_irradiance.argtypes = [C.POINTER(abi.DDGIUniform), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    rc = L.oracle_sample_irradiance(C.byref(u), _ptr(irr), _ptr(dep), len(P), _ptr(P), _ptr(N), _ptr(Wo), _ptr(out))
+    assert rc == 0, rc
+    return out
+
+
+def sample_probe(u, irr, dep, g_depth, g_normal, camera_position, view_proj_inv):
+    g_depth = np.ascontiguousarray(g_depth, dtype=np.float32)
+    g_normal = np.ascontiguousarray(g_normal, dtype=np.float32)
+    h, w = g_depth.shape
+    cam = np.ascontiguousarray(camera_position, dtype=np.float32).reshape(4)
+    vpi = np.ascontiguousarray(view_proj_inv, dtype=np.float32).reshape(16)
+    out = np.empty((h, w, 4), dtype=np.float32)
+    L = lib()
+    L.oracle_sample_probe.restype = C.c_int
+    L.oracle_sample_probe.argtypes = [C.POINTER(abi.DDGIUniform), C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    rc = L.oracle_sample_probe(C.byref(u), _ptr(irr), _ptr(dep), w, h, _ptr(g_depth), _ptr(g_normal), _ptr(cam), _ptr(vpi), _ptr(out))
+    assert rc == 0, rc
+    return out
+
+
 def set_unfused(on):
     """Literal two-rounding blend arithmetic of the shipped SPIR-V instead of the contract's explicit FMAs."""
     lib().oracle_set_unfused(int(bool(on)))

@@ -751,6 +751,140 @@ void borderProbe(uint16_t* img, int W, int channels, int side, int probe)
     cp(1, 1, side + 1, side + 1);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Consumer side ("next" row f2): sampleIrradiance + SampleProbe.comp
+// ---------------------------------------------------------------------------------------------------------
+// textureLod(sampler2D, uv, 0) on an fp16 atlas: bilinear, REPEAT wrap (default Texture2D sampler, RHI/Definitions.h:152-159)
+struct Atlas2D
+{
+    const uint16_t* d;
+    int             w, h, c;
+};
+
+inline int wrapi(int i, int n) { return ((i % n) + n) % n; }
+
+void sampleAtlas(const Atlas2D& t, float u, float v, float* out)
+{
+    float x = u * (float)t.w - 0.5f, y = v * (float)t.h - 0.5f;
+    float fx = std::floor(x), fy = std::floor(y);
+    float ax = x - fx, ay = y - fy;
+    int   x0 = wrapi((int)fx, t.w), x1 = wrapi((int)fx + 1, t.w), y0 = wrapi((int)fy, t.h), y1 = wrapi((int)fy + 1, t.h);
+    for (int k = 0; k < t.c; k++)
+    {
+        float a = lerp1(h2f(t.d[((size_t)y0 * t.w + x0) * t.c + k]), h2f(t.d[((size_t)y0 * t.w + x1) * t.c + k]), ax);
+        float b = lerp1(h2f(t.d[((size_t)y1 * t.w + x0) * t.c + k]), h2f(t.d[((size_t)y1 * t.w + x1) * t.c + k]), ax);
+        out[k]  = lerp1(a, b, ay);
+    }
+}
+
+// DDGICommon.glsl:60-72
+inline vec2 octEncode(vec3 v)
+{
+    float l1norm = (std::fabs(v.x) + std::fabs(v.y)) + std::fabs(v.z);
+    float inv    = 1.0f / l1norm;
+    vec2  r      = {v.x * inv, v.y * inv};
+    if (v.z < 0.0f)
+    {
+        vec2 q = {(1.0f - std::fabs(r.y)) * signNotZero(r.x), (1.0f - std::fabs(r.x)) * signNotZero(r.y)};
+        r      = q;
+    }
+    return r;
+}
+
+// DDGICommon.glsl:141-158
+inline vec2 textureCoordFromDirection(vec3 dir, int probeIndex, int width, int height, int probeSideLength)
+{
+    vec2  oc  = octEncode(normalize3(dir));
+    vec2  o01 = {(oc.x + 1.0f) * 0.5f, (oc.y + 1.0f) * 0.5f};
+    float probeWithBorderSide = (float)probeSideLength + 2.0f;
+    vec2  octTex = {(o01.x * (float)probeSideLength) / (float)width, (o01.y * (float)probeSideLength) / (float)height};
+    int   probesPerRow = (width - 2) / (int)probeWithBorderSide;
+    float fi = (float)probeIndex, fp = (float)probesPerRow;
+    float modv = fi - fp * std::floor(fi / fp); // mod(probeIndex, probesPerRow) on floats
+    vec2  topLeft = {modv * probeWithBorderSide + 2.0f, (float)(probeIndex / probesPerRow) * probeWithBorderSide + 2.0f};
+    vec2  topLeftN = {topLeft.x / (float)width, topLeft.y / (float)height};
+    return {topLeftN.x + octTex.x, topLeftN.y + octTex.y};
+}
+
+inline float square1(float v) { return v * v; }
+
+// DDGICommon.glsl:163-233
+vec3 sampleIrradiance(const LuxDDGIUniform& ddgi, vec3 P, vec3 N, vec3 Wo, const Atlas2D& irr, const Atlas2D& dep)
+{
+    int   bg[3], cnt[3] = {ddgi.probeCounts[0], ddgi.probeCounts[1], ddgi.probeCounts[2]};
+    float Pv[3] = {P.x, P.y, P.z};
+    for (int a = 0; a < 3; a++) // baseGridCoord :124-127: clamp(ivec3((X - start) / step), 0, counts - 1)
+        bg[a] = iclamp((int)((Pv[a] - ddgi.startPosition[a]) / ddgi.step[a]), 0, cnt[a] - 1);
+    vec3 baseProbePos = {ddgi.step[0] * (float)bg[0] + ddgi.startPosition[0], ddgi.step[1] * (float)bg[1] + ddgi.startPosition[1],
+                         ddgi.step[2] * (float)bg[2] + ddgi.startPosition[2]};
+    vec3 sumIrradiance = {0, 0, 0};
+    float sumWeight = 0.0f;
+    vec3 alpha = {gclamp((P.x - baseProbePos.x) / ddgi.step[0], 0.0f, 1.0f), gclamp((P.y - baseProbePos.y) / ddgi.step[1], 0.0f, 1.0f),
+                  gclamp((P.z - baseProbePos.z) / ddgi.step[2], 0.0f, 1.0f)};
+    for (int i = 0; i < 8; ++i)
+    {
+        int  off[3] = {i & 1, (i >> 1) & 1, (i >> 2) & 1};
+        int  pg[3];
+        for (int a = 0; a < 3; a++)
+            pg[a] = iclamp(bg[a] + off[a], 0, cnt[a] - 1);
+        vec3 probePos = {ddgi.step[0] * (float)pg[0] + ddgi.startPosition[0], ddgi.step[1] * (float)pg[1] + ddgi.startPosition[1],
+                         ddgi.step[2] * (float)pg[2] + ddgi.startPosition[2]};
+        // mix(1 - alpha, alpha, offset) = x*(1-a) + y*a with a in {0, 1}
+        float al[3] = {alpha.x, alpha.y, alpha.z}, tri[3];
+        for (int a = 0; a < 3; a++)
+            tri[a] = (1.0f - al[a]) * (1.0f - (float)off[a]) + al[a] * (float)off[a];
+        float weight = 1.0f;
+        vec3  dirToProbe = normalize3(sub(probePos, P));
+        weight *= square1(gmax(0.0001f, (dot3(dirToProbe, N) + 1.0f) * 0.5f)) + 0.2f;
+        int probeIdx = pg[0] + pg[1] * cnt[0] + pg[2] * cnt[0] * cnt[1];
+
+        vec3  vBias        = mul(add(N, mul(Wo, 3.0f)), ddgi.normalBias);
+        vec3  probeToPoint = add(sub(P, probePos), vBias);
+        vec3  dir          = normalize3({-probeToPoint.x, -probeToPoint.y, -probeToPoint.z});
+        vec2  tc           = textureCoordFromDirection({-dir.x, -dir.y, -dir.z}, probeIdx, ddgi.depthTextureWidth, ddgi.depthTextureHeight,
+                                                       ddgi.depthProbeSideLength);
+        float dist = length3(probeToPoint);
+        float tmp[4];
+        sampleAtlas(dep, tc.x, tc.y, tmp);
+        float mean     = tmp[0];
+        float variance = std::fabs(square1(tmp[0]) - tmp[1]);
+        float cheb     = variance / (variance + square1(gmax(dist - mean, 0.0f)));
+        cheb           = gmax(cheb * cheb * cheb, 0.0f);
+        weight *= (dist <= mean) ? 1.0f : cheb;
+        weight = gmax(0.000001f, weight);
+
+        tc = textureCoordFromDirection(normalize3(N), probeIdx, ddgi.irradianceTextureWidth, ddgi.irradianceTextureHeight,
+                                       ddgi.irradianceProbeSideLength);
+        sampleAtlas(irr, tc.x, tc.y, tmp);
+        float e = ddgi.ddgiGamma * 0.5f;
+        vec3  probeIrradiance = {pow_rn(tmp[0], e), pow_rn(tmp[1], e), pow_rn(tmp[2], e)};
+        const float crushThreshold = 0.2f;
+        if (weight < crushThreshold)
+            weight *= weight * weight * (1.0f / square1(crushThreshold));
+        weight *= tri[0] * tri[1] * tri[2];
+        sumIrradiance = add(sumIrradiance, mul(probeIrradiance, weight));
+        sumWeight += weight;
+    }
+    vec3 net = {sumIrradiance.x / sumWeight, sumIrradiance.y / sumWeight, sumIrradiance.z / sumWeight};
+    net      = mul(net, net);
+    const float TWO_PI_F = 6.283185482025146484375f; // 2 * PI folded to float
+    return mul(net, TWO_PI_F);
+}
+
+// Common/Math.glsl:27-33
+inline vec3 octohedralToDirection(vec2 e)
+{
+    vec3 v = {e.x, e.y, (1.0f - std::fabs(e.x)) - std::fabs(e.y)};
+    if (v.z < 0.0f)
+    {
+        float sx = (v.x >= 0.0f ? 1.0f : 0.0f) * 2.0f - 1.0f, sy = (v.y >= 0.0f ? 1.0f : 0.0f) * 2.0f - 1.0f; // step(0, v) * 2 - 1
+        float nx = (1.0f - std::fabs(v.y)) * sx, ny = (1.0f - std::fabs(v.x)) * sy;
+        v.x = nx;
+        v.y = ny;
+    }
+    return normalize3(v);
+}
+
 } // namespace
 
 // ---------------------------------------------------------------------------------------------------------
@@ -970,6 +1104,61 @@ int oracle_border(const LuxDDGIUniform* ddgi, uint16_t* irr, uint16_t* depth, in
         if (depth)
             borderProbe(depth, ddgi->depthTextureWidth, 2, ddgi->depthProbeSideLength, probeBegin + k);
     }
+    return 0;
+}
+
+// sampleIrradiance (DDGICommon.glsl:163-233) for `count` points; P, N, Wo, out are [count][3] floats.
+int oracle_sample_irradiance(const LuxDDGIUniform* ddgi, const uint16_t* irr, const uint16_t* depth, int count, const float* P, const float* N,
+                             const float* Wo, float* out)
+{
+    if (!ddgi || !irr || !depth || !P || !N || !Wo || !out)
+        return -1;
+    Atlas2D ai{irr, ddgi->irradianceTextureWidth, ddgi->irradianceTextureHeight, 4};
+    Atlas2D ad{depth, ddgi->depthTextureWidth, ddgi->depthTextureHeight, 2};
+#pragma omp parallel for schedule(static)
+    for (int k = 0; k < count; k++)
+    {
+        vec3 r = sampleIrradiance(*ddgi, {P[3 * k], P[3 * k + 1], P[3 * k + 2]}, {N[3 * k], N[3 * k + 1], N[3 * k + 2]},
+                                  {Wo[3 * k], Wo[3 * k + 1], Wo[3 * k + 2]}, ai, ad);
+        out[3 * k] = r.x; out[3 * k + 1] = r.y; out[3 * k + 2] = r.z;
+    }
+    return 0;
+}
+
+// SampleProbe.comp:36-60 over a width x height G-buffer: depth [h][w] (D32F), normals [h][w][4] (RGBA32F, xy = octahedral normal),
+// cameraPosition[4], viewProjInv (column-major mat4); out [h][w][4] floats (the INDIRECT_LIGHTING target is RGBA32F, GBuffer.cpp:24).
+int oracle_sample_probe(const LuxDDGIUniform* ddgi, const uint16_t* irr, const uint16_t* depthAtlas, int width, int height,
+                        const float* gDepth, const float* gNormal, const float* cameraPosition, const float* viewProjInv, float* out)
+{
+    if (!ddgi || !irr || !depthAtlas || !gDepth || !gNormal || !cameraPosition || !viewProjInv || !out)
+        return -1;
+    Atlas2D ai{irr, ddgi->irradianceTextureWidth, ddgi->irradianceTextureHeight, 4};
+    Atlas2D ad{depthAtlas, ddgi->depthTextureWidth, ddgi->depthTextureHeight, 2};
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < height; y++)
+        for (int x = 0; x < width; x++)
+        {
+            size_t o = (size_t)y * width + x;
+            float  d = gDepth[o];
+            if (d == 1.0f)
+            {
+                out[4 * o] = out[4 * o + 1] = out[4 * o + 2] = out[4 * o + 3] = 0.0f;
+                continue;
+            }
+            // texCoord = (coord + 0.5) / size; worldPositionFromDepth (Common/Math.glsl:35-42)
+            float tx = ((float)x + 0.5f) / (float)width, ty = ((float)y + 0.5f) / (float)height;
+            float sx = tx * 2.0f - 1.0f, sy = ty * 2.0f - 1.0f;
+            const float* m = viewProjInv;
+            float wx = ((m[0] * sx + m[4] * sy) + m[8] * d) + m[12] * 1.0f;
+            float wy = ((m[1] * sx + m[5] * sy) + m[9] * d) + m[13] * 1.0f;
+            float wz = ((m[2] * sx + m[6] * sy) + m[10] * d) + m[14] * 1.0f;
+            float ww = ((m[3] * sx + m[7] * sy) + m[11] * d) + m[15] * 1.0f;
+            vec3  Pw = {wx / ww, wy / ww, wz / ww};
+            vec3  Nn = octohedralToDirection({gNormal[4 * o], gNormal[4 * o + 1]});
+            vec3  Wo = normalize3(sub({cameraPosition[0], cameraPosition[1], cameraPosition[2]}, Pw));
+            vec3  r  = sampleIrradiance(*ddgi, Pw, Nn, Wo, ai, ad);
+            out[4 * o] = r.x; out[4 * o + 1] = r.y; out[4 * o + 2] = r.z; out[4 * o + 3] = 1.0f;
+        }
     return 0;
 }
 

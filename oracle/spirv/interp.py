@@ -32,7 +32,7 @@ OP = {
     57: "FunctionCall", 59: "Variable", 61: "Load", 62: "Store", 65: "AccessChain", 66: "InBoundsAccessChain", 71: "Decorate",
     72: "MemberDecorate", 79: "VectorShuffle", 80: "CompositeConstruct", 81: "CompositeExtract", 82: "CompositeInsert",
     83: "CopyObject", 88: "ImageSampleExplicitLod", 95: "ImageFetch", 96: "ImageGather", 98: "ImageRead", 99: "ImageWrite",
-    100: "Image", 110: "ConvertFToS", 109: "ConvertFToU", 111: "ConvertSToF", 112: "ConvertUToF", 124: "Bitcast", 126: "SNegate",
+    100: "Image", 103: "ImageQuerySizeLod", 110: "ConvertFToS", 109: "ConvertFToU", 111: "ConvertSToF", 112: "ConvertUToF", 124: "Bitcast", 126: "SNegate",
     127: "FNegate", 128: "IAdd", 129: "FAdd", 130: "ISub", 131: "FSub", 132: "IMul", 133: "FMul", 134: "UDiv", 135: "SDiv",
     136: "FDiv", 137: "UMod", 138: "SRem", 139: "SMod", 141: "FMod", 142: "VectorTimesScalar", 143: "MatrixTimesScalar",
     144: "VectorTimesMatrix", 145: "MatrixTimesVector", 146: "MatrixTimesMatrix", 148: "Dot", 154: "Any", 155: "All",
@@ -45,7 +45,7 @@ OP = {
     250: "BranchConditional", 252: "Kill", 253: "Return", 254: "ReturnValue", 255: "Unreachable", 400: "CopyLogical",
 }
 GLSL = {4: "FAbs", 8: "Floor", 10: "Fract", 13: "Sin", 14: "Cos", 26: "Pow", 31: "Sqrt", 32: "InverseSqrt", 34: "MatrixInverse",
-        37: "FMin", 38: "UMin", 39: "SMin", 40: "FMax", 41: "UMax", 42: "SMax", 43: "FClamp", 44: "UClamp", 45: "SClamp", 46: "FMix",
+        37: "FMin", 38: "UMin", 39: "SMin", 40: "FMax", 41: "UMax", 42: "SMax", 43: "FClamp", 44: "UClamp", 45: "SClamp", 46: "FMix", 48: "Step",
         66: "Length", 67: "Distance", 69: "Normalize"}
 DEC_BUILTIN, DEC_BINDING, DEC_SET = 11, 33, 34
 BUILTIN = {24: "NumWorkgroups", 25: "WorkgroupSize", 26: "WorkgroupId", 27: "LocalInvocationId", 28: "GlobalInvocationId", 29: "LocalInvocationIndex"}
@@ -137,9 +137,27 @@ class Texture2D:
         return [g(i0, j1), g(i1, j1), g(i1, j0), g(i0, j0)]
 
     def fetch(self, c):
-        px = self.d[s32(c[1]), s32(c[0])]
+        y, x = s32(c[1]), s32(c[0])
+        if not (0 <= y < self.H and 0 <= x < self.W):  # out-of-bounds texelFetch: robust-buffer-access style zeros
+            return [F(0), F(0), F(0), F(0)]
+        px = self.d[y, x]
         out = [F(px[k]) if k < self.C else F(0) for k in range(3)]
         out.append(F(px[3]) if self.C > 3 else F(1))
+        return out
+
+    def sample(self, c):
+        """textureLod(sampler2D, uv, 0): bilinear with fp32 weights, nested lerp x then y."""
+        x = F(F(c[0] * F(self.W)) - F(0.5)); y = F(F(c[1] * F(self.H)) - F(0.5))
+        fx, fy = F(math.floor(x)), F(math.floor(y))
+        ax, ay = F(x - fx), F(y - fy)
+        x0, x1, y0, y1 = self._wrap(int(fx), self.W), self._wrap(int(fx) + 1, self.W), self._wrap(int(fy), self.H), self._wrap(int(fy) + 1, self.H)
+        out = []
+        for k in range(4):
+            if k < self.C:
+                t = lambda xx, yy: F(self.d[yy, xx, k])
+                out.append(lerp(lerp(t(x0, y0), t(x1, y0), ax), lerp(t(x0, y1), t(x1, y1), ax), ay))
+            else:
+                out.append(F(0) if k < 3 else F(1))
         return out
 
 
@@ -424,6 +442,7 @@ class Invocation:
         if name == "ISub": return vec(lambda p, q: (p - q) & M32, x(2), x(3))
         if name == "IMul": return vec(lambda p, q: (p * q) & M32, x(2), x(3))
         if name == "SDiv": return vec(sdiv, x(2), x(3))
+        if name == "FMod": return vec(lambda p, q: F(p - F(q * F(math.floor(F(np.divide(p, q)))))), x(2), x(3))
         if name == "UDiv": return vec(lambda p, q: (p // q) & M32, x(2), x(3))
         if name == "SMod": return vec(lambda p, q: (s32(p) % s32(q)) & M32, x(2), x(3))  # sign follows the divisor, like Python
         if name == "UMod": return vec(lambda p, q: (p % q) & M32, x(2), x(3))
@@ -447,6 +466,7 @@ class Invocation:
                 acc = F(acc + F(p[k] * q[k]))
             return acc
         if name == "ShiftRightLogical": return vec(lambda p, q: (p & M32) >> (q & 31), x(2), x(3))
+        if name == "ShiftRightArithmetic": return vec(lambda p, q: (s32(p) >> (q & 31)) & M32, x(2), x(3))
         if name == "ShiftLeftLogical": return vec(lambda p, q: (p << (q & 31)) & M32, x(2), x(3))
         if name == "BitwiseXor": return vec(lambda p, q: (p ^ q) & M32, x(2), x(3))
         if name == "BitwiseOr": return vec(lambda p, q: (p | q) & M32, x(2), x(3))
@@ -508,6 +528,7 @@ class Invocation:
         if name == "ImageSampleExplicitLod": return x(2).sample(x(3))
         if name == "ImageGather": return x(2).gather(x(3), s32(x(4)))
         if name == "ImageFetch": return x(2).fetch(x(3))
+        if name == "ImageQuerySizeLod": return [x(2).W, x(2).H]
         if name == "ImageRead": return x(2).read(x(3))
         if name == "ExtInst": return self.ext(GLSL.get(a[3]), [V(k) for k in a[4:]], a[3])
         raise NotImplementedError(name)
@@ -527,6 +548,7 @@ class Invocation:
                 except (ValueError, OverflowError):
                     return F(np.nan)
             return vec(pw, o[0], o[1])
+        if op == "Step": return vec(lambda edge, p: F(0.0) if p < edge else F(1.0), o[0], o[1])
         if op == "FMin": return vec(gmin, o[0], o[1])
         if op == "FMax": return vec(gmax, o[0], o[1])
         if op == "FClamp": return vec(gclamp, o[0], o[1], o[2])

@@ -323,3 +323,37 @@ def test_full_size_config_on_a_stratified_probe_subsample(oracle, cfg, sample):
     pipe.close()
     del sc
     torch.cuda.empty_cache()
+
+
+def test_consumer_sample_irradiance_and_sample_probe(oracle):
+    """The step after the path: sampleIrradiance / SampleProbe.comp read the just-written atlases with
+    bilinear taps through the 1-texel borders — so this also proves the border + outer-pad layout end to end."""
+    import os
+
+    sc = scenes.build("c1")
+    sc.uniform.normalBias = 0.1
+    rots = [scenes.frame_rotation(f) for f in range(3)]
+    orc = oracle.OraclePipeline(sc)
+    for r in rots:
+        orc.update(r)
+    pipe = run_engine(sc, rots)
+    rng = np.random.default_rng(3)
+    n = 4096
+    P = rng.uniform(-4.8, 4.8, (n, 3)).astype(np.float32)
+    P[:64] = rng.uniform(-9, 9, (64, 3))  # outside the probe grid: base cell clamps
+    N = rng.standard_normal((n, 3)).astype(np.float32)
+    N /= np.linalg.norm(N, axis=1, keepdims=True)
+    Wo = rng.standard_normal((n, 3)).astype(np.float32)
+    Wo /= np.linalg.norm(Wo, axis=1, keepdims=True)
+    want = oracle.sample_irradiance(sc.uniform, orc.irradiance, orc.depth, P, N, Wo)
+    got = pipe.sample_irradiance(P, N, Wo)
+    assert np.isfinite(want).all() and want.mean() > 0.01
+    assert np.allclose(got, want, rtol=1e-3, atol=1e-4)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), f"{(got != want).sum()} of {got.size} values differ"
+    # the shipped-SPIR-V golden G-buffer through the engine's SampleProbe kernel (atlases = the engine's own)
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "spirv_golden_consumer.npz"))
+    want = oracle.sample_probe(sc.uniform, orc.irradiance, orc.depth, g["g_depth"], g["g_normal"], g["camera"], g["view_proj_inv"])
+    got = pipe.sample_probe(g["g_depth"], g["g_normal"], g["camera"], g["view_proj_inv"])
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), f"max abs diff {np.abs(got - want).max()}"
+    assert (got[0, :3] == 0).all()  # depth == 1 pixels are cleared
+    pipe.close()

@@ -87,3 +87,15 @@ def test_hoisted_blend_equals_golden_too(oracle, golden):
         assert np.array_equal(irr, g["f1_irradiance_interior"]) and np.array_equal(dep, g["f1_depth_interior"])
     finally:
         oracle.set_unfused(False)
+
+
+def test_sample_probe_matches_shipped_spirv(oracle):
+    """Consumer row: the oracle's SampleProbe / sampleIrradiance restatement against the image written by the
+    reference's shipped SampleProbe.comp.spv (tests/golden/make_spirv_golden_consumer.py).  Bit for bit: every operation of
+    this shader is either pinned by the binary or fixed by the numerics contract (pow through binary64, bilinear atlas taps)."""
+    g = np.load(os.path.join(os.path.dirname(PATH), "spirv_golden_consumer.npz"))
+    u = abi.DDGIUniform.from_buffer_copy(g["uniform"].tobytes())
+    got = oracle.sample_probe(u, g["irradiance"], g["depth_atlas"], g["g_depth"], g["g_normal"], g["camera"], g["view_proj_inv"])
+    want = g["out"]
+    assert (want[..., 3] > 0).sum() > 150 and np.isfinite(want).all()
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), f"max abs diff {np.abs(got - want).max()}"
