@@ -286,6 +286,16 @@ LUX_API int lux_ddgi_sample_irradiance(LuxDDGIContext* ctx, int32_t count, const
 LUX_API int lux_ddgi_sample_probe(LuxDDGIContext* ctx, int32_t width, int32_t height, const float* depthD32F, const float* normalsRGBA32F,
                                   const float cameraPosition[4], const float viewProjInv[16], float* outRGBA32F, LuxMemKind kind);
 
+/* Infinite-bounce feedback: surface::indirect_light::system (GlobalSurfaceAtlas.cpp:1004-1085) =
+ * Shaders/SDF/SDFAtlasIndirectLight.frag:44-67, additive into the RGBA16F light cache.  For each listed atlas texel t:
+ *   light[t].rgb = fp16( base[t].rgb + intensity * (min(albedo,0.9) - min(albedo,0.9)*metallic)/PI * sampleIrradiance(P, N, normalize(cameraPos-P)) )
+ * `baseLightRGBA16F` (full atlas; emissive + direct light, i.e. the cache after CopyEmissive + SDFDeferredLight) may be NULL to
+ * add onto the current contents.  The rasterisation of tiles into texel lists stays with the caller. */
+LUX_API int lux_ddgi_indirect_light(LuxDDGIContext* ctx, const void* baseLightRGBA16F, int32_t count, const uint32_t* texelIndex,
+                                    const float* worldPos, const float* normal, const float* albedo, const float* metallic, float intensity,
+                                    const float cameraPos[3], LuxMemKind kind);
+LUX_API int lux_ddgi_get_surface_light_cache(LuxDDGIContext* ctx, void** devicePtr, size_t* bytes);
+
 LUX_API int lux_ddgi_get_state(LuxDDGIContext* ctx, LuxDDGIState* out);
 /* z-slab layout of shard `rank` of `world` without a context (pure host arithmetic, usable on a machine with no GPU):
  * fills probeBegin/Count and the atlas row ranges of `out`; the other fields are zero. */

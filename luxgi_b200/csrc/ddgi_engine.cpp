@@ -1046,6 +1046,65 @@ int lux_ddgi_sample_probe(LuxDDGIContext* c, int32_t width, int32_t height, cons
     return LUX_OK;
 }
 
+int lux_ddgi_indirect_light(LuxDDGIContext* c, const void* baseLightRGBA16F, int32_t count, const uint32_t* texelIndex, const float* worldPos,
+                            const float* normal, const float* albedo, const float* metallic, float intensity, const float cameraPos[3],
+                            LuxMemKind kind)
+{
+    CHECK_CTX(c);
+    if (!c->hasAtlas)
+        return fail(LUX_ERR_NOT_READY, "no surface cache bound");
+    if (c->frames == 0)
+        return fail(LUX_ERR_NOT_READY, "no atlas has been written yet");
+    if (count < 0 || !texelIndex || !worldPos || !normal || !albedo || !metallic || !cameraPos)
+        return fail(LUX_ERR_INVALID_ARG, "bad indirect_light arguments");
+    const size_t texels = (size_t)c->atlasData.resolution * c->atlasData.resolution;
+    if (c->light.borrowed)
+    { // never write into a caller-owned buffer: take a private copy first
+        void* own = nullptr;
+        LUX_CUDA(cudaMalloc(&own, texels * 8));
+        LUX_CUDA(cudaMemcpyAsync(own, c->light.ptr, texels * 8, cudaMemcpyDeviceToDevice, c->stream));
+        c->light.ptr      = own;
+        c->light.borrowed = false;
+        c->light.bytes    = texels * 8;
+    }
+    void *dB = nullptr, *dT, *dP, *dN, *dA, *dM;
+    bool  oB = false, oT, oP, oN, oA, oM;
+    int   rc;
+    if (baseLightRGBA16F && (rc = stageToDevice(c, baseLightRGBA16F, texels * 8, kind, &dB, &oB)) != LUX_OK) return rc;
+    if ((rc = stageToDevice(c, texelIndex, (size_t)count * 4, kind, &dT, &oT)) != LUX_OK) return rc;
+    if ((rc = stageToDevice(c, worldPos, (size_t)count * 12, kind, &dP, &oP)) != LUX_OK) return rc;
+    if ((rc = stageToDevice(c, normal, (size_t)count * 12, kind, &dN, &oN)) != LUX_OK) return rc;
+    if ((rc = stageToDevice(c, albedo, (size_t)count * 12, kind, &dA, &oA)) != LUX_OK) return rc;
+    if ((rc = stageToDevice(c, metallic, (size_t)count * 4, kind, &dM, &oM)) != LUX_OK) return rc;
+    if (dB) // light = base everywhere, then the listed texels receive base + indirect
+        LUX_CUDA(cudaMemcpyAsync(c->light.ptr, dB, texels * 8, cudaMemcpyDeviceToDevice, c->stream));
+    lux::launch_indirect_light(c->uniform, c->irradiance[c->lastWritten].ptr, c->depth[c->lastWritten].ptr, c->light.ptr, dB, count,
+                               (const uint32_t*)dT, (const float*)dP, (const float*)dN, (const float*)dA, (const float*)dM, intensity, cameraPos,
+                               c->stream);
+    c->launches += count > 0 ? 1 : 0;
+    LUX_CUDA(cudaGetLastError());
+    if (oB || oT || oP || oN || oA || oM)
+        LUX_CUDA(cudaStreamSynchronize(c->stream));
+    if (oB) cudaFree(dB);
+    if (oT) cudaFree(dT);
+    if (oP) cudaFree(dP);
+    if (oN) cudaFree(dN);
+    if (oA) cudaFree(dA);
+    if (oM) cudaFree(dM);
+    return LUX_OK;
+}
+
+int lux_ddgi_get_surface_light_cache(LuxDDGIContext* c, void** devicePtr, size_t* bytes)
+{
+    CHECK_CTX(c);
+    if (!c->hasAtlas || !devicePtr)
+        return fail(LUX_ERR_NOT_READY, "no surface cache bound");
+    *devicePtr = c->light.ptr;
+    if (bytes)
+        *bytes = c->light.bytes;
+    return LUX_OK;
+}
+
 int lux_ddgi_get_stage_ms(LuxDDGIContext* c, LuxStageTimes* out)
 {
     CHECK_CTX(c);

@@ -1861,6 +1861,47 @@ __global__ void sample_probe_kernel(const __grid_constant__ SampleProbeArgs A, c
     out[o] = make_float4(r.x, r.y, r.z, 1.0f);
 }
 
+// SDFAtlasIndirectLight.frag:44-67 + additive blend into the RGBA16F light cache, for a list of atlas texels
+__global__ void indirect_light_kernel(const __grid_constant__ LuxDDGIUniform ddgi, const uint16_t* __restrict__ irr, const uint16_t* __restrict__ dep,
+                                      uint2* __restrict__ light, const uint2* __restrict__ base, int count, const uint32_t* __restrict__ texel,
+                                      const float* __restrict__ P, const float* __restrict__ N, const float* __restrict__ albedo,
+                                      const float* __restrict__ metallic, float intensity, float camX, float camY, float camZ)
+{
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count)
+        return;
+    AtlasView ai{irr, ddgi.irradianceTextureWidth, ddgi.irradianceTextureHeight, 4}, ad{dep, ddgi.depthTextureWidth, ddgi.depthTextureHeight, 2};
+    f3 Pw = {P[3 * k], P[3 * k + 1], P[3 * k + 2]}, Nn = {N[3 * k], N[3 * k + 1], N[3 * k + 2]};
+    f3 cam = {camX, camY, camZ};
+    f3 Wo = normalize3(cam - Pw);
+    f3 E  = sample_irradiance(ddgi, Pw, Nn, Wo, ai, ad);
+    const float PI_F = 3.1415926535897932384626433832795f;
+    float m = metallic[k];
+    float Ev[3] = {E.x, E.y, E.z}, outv[3];
+    uint32_t idx = texel[k];
+    uint2 b = base ? base[idx] : light[idx];
+    f4 dst = unpack_rgba16f(b);
+    float dv[3] = {dst.x, dst.y, dst.z};
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+    {
+        float a       = gmin(albedo[3 * k + c], 0.9f);
+        float diffuse = __fdiv_rn(a - a * m, PI_F);
+        outv[c]       = dv[c] + (intensity * diffuse) * Ev[c];
+    }
+    uint32_t h0 = f2h_bits(outv[0]), h1 = f2h_bits(outv[1]), h2 = f2h_bits(outv[2]);
+    light[idx] = make_uint2(h0 | (h1 << 16), h2 | (b.y & 0xffff0000u));
+}
+
+void launch_indirect_light(const LuxDDGIUniform& ddgi, const void* irr, const void* dep, void* light, const void* base, int count,
+                           const uint32_t* texel, const float* P, const float* N, const float* albedo, const float* metallic, float intensity,
+                           const float* cameraPos, cudaStream_t s)
+{
+    if (count > 0)
+        indirect_light_kernel<<<(count + 127) / 128, 128, 0, s>>>(ddgi, (const uint16_t*)irr, (const uint16_t*)dep, (uint2*)light, (const uint2*)base, count,
+                                                                  texel, P, N, albedo, metallic, intensity, cameraPos[0], cameraPos[1], cameraPos[2]);
+}
+
 void launch_sample_irradiance(const LuxDDGIUniform& ddgi, const void* irr, const void* dep, int count, const float* P, const float* N,
                               const float* Wo, float* out, cudaStream_t s)
 {

@@ -97,5 +97,8 @@ void launch_sample_irradiance(const LuxDDGIUniform& ddgi, const void* irr, const
                               const float* Wo, float* out, cudaStream_t s);
 void launch_sample_probe(const LuxDDGIUniform& ddgi, const void* irr, const void* dep, int width, int height, const float* gDepth,
                          const float* gNormal, const float* cameraPosition, const float* viewProjInv, float* out, cudaStream_t s);
+void launch_indirect_light(const LuxDDGIUniform& ddgi, const void* irr, const void* dep, void* light, const void* base, int count,
+                           const uint32_t* texel, const float* P, const float* N, const float* albedo, const float* metallic, float intensity,
+                           const float* cameraPos, cudaStream_t s);
 
 } // namespace lux

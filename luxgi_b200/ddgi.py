@@ -24,7 +24,8 @@ EXPORTS = [
     "lux_ddgi_update_surface_light_cache", "lux_ddgi_set_skybox", "lux_ddgi_trace_rays", "lux_ddgi_probe_update",
     "lux_ddgi_border_update", "lux_ddgi_end_frame", "lux_ddgi_update", "lux_ddgi_synchronize", "lux_ddgi_get_buffer",
     "lux_ddgi_download", "lux_ddgi_download_async", "lux_ddgi_download_rows_async", "lux_ddgi_set_ray_buffers", "lux_ddgi_restore", "lux_ddgi_get_state", "lux_ddgi_shard_layout",
-    "lux_ddgi_get_stage_ms", "lux_ddgi_sample_irradiance", "lux_ddgi_sample_probe",
+    "lux_ddgi_get_stage_ms", "lux_ddgi_sample_irradiance", "lux_ddgi_sample_probe", "lux_ddgi_indirect_light",
+    "lux_ddgi_get_surface_light_cache",
 ]
 
 
@@ -72,6 +73,8 @@ def load():
         "lux_ddgi_get_stage_ms": [vp, C.POINTER(abi.StageTimes)],
         "lux_ddgi_sample_irradiance": [vp, i32, vp, vp, vp, vp, i32],
         "lux_ddgi_sample_probe": [vp, i32, i32, vp, vp, vp, vp, vp, i32],
+        "lux_ddgi_indirect_light": [vp, vp, i32, vp, vp, vp, vp, vp, C.c_float, vp, i32],
+        "lux_ddgi_get_surface_light_cache": [vp, C.POINTER(vp), C.POINTER(sz)],
     }
     for name, argtypes in sig.items():
         fn = getattr(L, name)
@@ -323,6 +326,26 @@ class DDGIPipeline:
         _check(self._lib.lux_ddgi_sample_probe(self._h, w, h, _host_ptr(depth), _host_ptr(normals), _host_ptr(cam), _host_ptr(vpi), _host_ptr(out),
                                                abi.MEM_HOST))
         return out
+
+    def indirect_light(self, base_light, texel, P, N, albedo, metallic, intensity, camera_pos):
+        """Infinite-bounce refresh of the surface light cache (SDFAtlasIndirectLight.frag) for a list of atlas texels."""
+        texel = np.ascontiguousarray(texel, dtype=np.uint32)
+        P, N, albedo = (np.ascontiguousarray(a, dtype=np.float32).reshape(-1, 3) for a in (P, N, albedo))
+        metallic = np.ascontiguousarray(metallic, dtype=np.float32)
+        cam = np.ascontiguousarray(camera_pos, dtype=np.float32).reshape(3)
+        base = None if base_light is None else _as_host(base_light)
+        _check(self._lib.lux_ddgi_indirect_light(self._h, None if base is None else _host_ptr(base), len(texel), _host_ptr(texel), _host_ptr(P),
+                                                 _host_ptr(N), _host_ptr(albedo), _host_ptr(metallic), float(intensity), _host_ptr(cam), abi.MEM_HOST))
+
+    def surface_light_cache(self) -> np.ndarray:
+        p, n = C.c_void_p(), C.c_size_t()
+        _check(self._lib.lux_ddgi_get_surface_light_cache(self._h, C.byref(p), C.byref(n)))
+        import torch
+
+        res = int(round((n.value // 8) ** 0.5))
+        view = DeviceView(p.value, (res, res, 4), "<f2", self)
+        self.synchronize()
+        return torch.as_tensor(view, device="cuda").cpu().numpy().view(np.uint16)
 
     @property
     def radiance(self):

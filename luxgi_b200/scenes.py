@@ -210,7 +210,7 @@ def _box_rotation(rot_y: float) -> np.ndarray:
     return np.array([[cs, 0, sn], [0, 1, 0], [-sn, 0, cs]])  # local -> world
 
 
-def build_surface_cache(boxes, atlas_res: int, cell: int, chunk_size: float, shade_fn, device="cpu", margin: int = 1):
+def build_surface_cache(boxes, atlas_res: int, cell: int, chunk_size: float, shade_fn, device="cpu", margin: int = 1, gbuffer: dict = None):
     """Objects/tiles/chunk lists + light and depth atlases for a list of BoxObject.
 
     Each object gets 6 tiles (one per face) of (cell - 2*margin)^2 texels laid out on a regular grid of `cell`-texel cells.
@@ -286,6 +286,11 @@ def build_surface_cache(boxes, atlas_res: int, cell: int, chunk_size: float, sha
         light[ys, xs, :3] = rgb.to(torch.float16)
         light[ys, xs, 3] = 1.0
         depth[ys, xs] = 0.5  # tileDepth of the captured face (tp.z / bounds.z = +1/2), SURVEY A.3
+        if gbuffer is not None:  # per-texel surface G-buffer (what SDFDeferredColor.frag captures), for the bounce refresh
+            gbuffer.setdefault("texel", []).append((ys * atlas_res + xs).reshape(-1).cpu())
+            gbuffer.setdefault("pos", []).append(wp.reshape(-1, 3).cpu())
+            gbuffer.setdefault("normal", []).append(wn.reshape(-1, 3).cpu())
+            gbuffer.setdefault("object", []).append(oi[:, None, None].expand(wp.shape[:3]).reshape(-1).cpu())
 
     # ---- chunk lists, SDFCulling.comp:36-101 ----
     NC = abi.CHUNKS_RESOLUTION
@@ -317,6 +322,9 @@ def build_surface_cache(boxes, atlas_res: int, cell: int, chunk_size: float, sha
     cull[0] = len(cull)
     cull = np.asarray(cull, dtype=np.uint32)
 
+    if gbuffer is not None:
+        for k in ("texel", "pos", "normal", "object"):
+            gbuffer[k] = torch.cat(gbuffer[k]).numpy()
     data = abi.GlobalSurfaceAtlasData()
     data.cameraPos[:] = [0.0, 0.0, 0.0]
     data.chunkSize = chunk_size
@@ -381,9 +389,14 @@ def cornell_scene(res: int = 64, counts=(8, 8, 8), rays: int = 64, atlas_res: in
             return torch.where(panel[:, None], torch.full_like(rgb, 15.0), rgb)
 
         cell = atlas_res // 8
+        gb = {}
         (sc.atlas_data, sc.chunks, sc.cull, sc.objects, sc.tiles, sc.light, sc.depth) = build_surface_cache(
-            boxes, atlas_res, cell, 2.0 * D / abi.CHUNKS_RESOLUTION, shade, device=device)
-    sc.meta = {"D": D, "res": res, "voxel": 2 * D / res}
+            boxes, atlas_res, cell, 2.0 * D / abi.CHUNKS_RESOLUTION, shade, device=device, gbuffer=gb)
+        alb = np.asarray([b.albedo for b in boxes], dtype=np.float32)
+        gb["albedo"] = alb[gb["object"]]
+        gb["metallic"] = np.zeros(len(gb["texel"]), dtype=np.float32)
+        sc.meta["gbuffer"] = gb
+    sc.meta.update({"D": D, "res": res, "voxel": 2 * D / res})
     return sc
 
 

@@ -193,6 +193,20 @@ def sample_probe(u, irr, dep, g_depth, g_normal, camera_position, view_proj_inv)
     return out
 
 
+def indirect_light(u, irr, dep, light, base, texel, P, N, albedo, metallic, intensity, camera_pos):
+    """In-place indirect-light refresh of `light` (uint16 RGBA16F atlas) for the listed texels."""
+    texel = np.ascontiguousarray(texel, dtype=np.uint32)
+    P, N, albedo = (np.ascontiguousarray(a, dtype=np.float32).reshape(-1, 3) for a in (P, N, albedo))
+    metallic = np.ascontiguousarray(metallic, dtype=np.float32)
+    cam = np.ascontiguousarray(camera_pos, dtype=np.float32).reshape(3)
+    L = lib()
+    L.oracle_indirect_light.restype = C.c_int
+    L.oracle_indirect_light.argtypes = [C.POINTER(abi.DDGIUniform)] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 5 + [C.c_float, C.c_void_p]
+    rc = L.oracle_indirect_light(C.byref(u), _ptr(irr), _ptr(dep), _ptr(light), _ptr(base), len(texel), _ptr(texel), _ptr(P), _ptr(N), _ptr(albedo),
+                                 _ptr(metallic), float(intensity), _ptr(cam))
+    assert rc == 0, rc
+
+
 def set_unfused(on):
     """Literal two-rounding blend arithmetic of the shipped SPIR-V instead of the contract's explicit FMAs."""
     lib().oracle_set_unfused(int(bool(on)))

@@ -1162,6 +1162,41 @@ int oracle_sample_probe(const LuxDDGIUniform* ddgi, const uint16_t* irr, const u
     return 0;
 }
 
+// Indirect-light refresh of the surface light cache ("next" row f1): for each listed atlas texel
+//   light.rgb = fp16( base.rgb + intensity * (min(albedo, 0.9) - min(albedo, 0.9) * metallic) / PI * sampleIrradiance(P, N, Wo) )
+// with Wo = normalize(cameraPos - P)  (Shaders/SDF/SDFAtlasIndirectLight.frag:44-67; additive blend into the RGBA16F light cache,
+// GlobalSurfaceAtlas.cpp:1004-1085).  `light` is updated in place; base == null means "add to the current contents".
+int oracle_indirect_light(const LuxDDGIUniform* ddgi, const uint16_t* irr, const uint16_t* depth, uint16_t* light, const uint16_t* base, int count,
+                          const uint32_t* texel, const float* P, const float* N, const float* albedo, const float* metallic, float intensity,
+                          const float* cameraPos)
+{
+    if (!ddgi || !irr || !depth || !light || !texel || !P || !N || !albedo || !metallic || !cameraPos)
+        return -1;
+    Atlas2D ai{irr, ddgi->irradianceTextureWidth, ddgi->irradianceTextureHeight, 4};
+    Atlas2D ad{depth, ddgi->depthTextureWidth, ddgi->depthTextureHeight, 2};
+    const float PI_F = 3.1415926535897932384626433832795f;
+#pragma omp parallel for schedule(static)
+    for (int k = 0; k < count; k++)
+    {
+        vec3 Pw = {P[3 * k], P[3 * k + 1], P[3 * k + 2]}, Nn = {N[3 * k], N[3 * k + 1], N[3 * k + 2]};
+        vec3 Wo = normalize3(sub({cameraPos[0], cameraPos[1], cameraPos[2]}, Pw));
+        vec3 E  = sampleIrradiance(*ddgi, Pw, Nn, Wo, ai, ad);
+        float Ev[3] = {E.x, E.y, E.z};
+        size_t o = (size_t)texel[k] * 4;
+        for (int c = 0; c < 3; c++)
+        {
+            float a       = gmin(albedo[3 * k + c], 0.9f);
+            float diffuse = (a - a * metallic[k]) / PI_F;
+            float out     = (intensity * diffuse) * Ev[c];
+            float dst     = h2f(base ? base[o + c] : light[o + c]);
+            light[o + c]  = f2h(dst + out);
+        }
+        if (base)
+            light[o + 3] = base[o + 3];
+    }
+    return 0;
+}
+
 // Border copy list of one probe in ring-relative coordinates: out[n][4] = (srcx, srcy, dstx, dsty); returns n.
 int oracle_border_offsets(int side, int32_t* out)
 {

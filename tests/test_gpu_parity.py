@@ -357,3 +357,35 @@ def test_consumer_sample_irradiance_and_sample_probe(oracle):
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), f"max abs diff {np.abs(got - want).max()}"
     assert (got[0, :3] == 0).all()  # depth == 1 pixels are cleared
     pipe.close()
+
+
+def test_infinite_bounce_refresh_closes_the_loop(oracle):
+    """BASELINE configs[2] in miniature: every 16 frames the surface light cache is rebuilt as
+    emissive + direct + intensity * (albedo_0.9 - albedo*metal)/pi * sampleIrradiance(previous atlases) and the trace then
+    sees the brighter cache.  Engine (lux_ddgi_indirect_light) and oracle must stay bit-identical through two refreshes."""
+    sc = scenes.cornell_scene(res=32, counts=(8, 4, 8), rays=64, atlas_res=256)
+    sc.uniform.normalBias = 0.1
+    gb = sc.meta["gbuffer"]
+    base = sc.light.numpy().view(np.uint16).copy()
+    cam = np.array([0.0, 0.0, 4.0], dtype=np.float32)
+    orc = oracle.OraclePipeline(sc)
+    pipe = ddgi.DDGIPipeline(sc.uniform)
+    pipe.set_scene(sc)
+    means = []
+    for f in range(34):
+        if f and f % 16 == 0:  # GI_FRAMES cadence (GlobalSurfaceAtlas.cpp:50, 842-847)
+            o_light = base.copy()
+            oracle.indirect_light(sc.uniform, orc.irradiance, orc.depth, o_light, base, gb["texel"], gb["pos"], gb["normal"], gb["albedo"],
+                                  gb["metallic"], 1.2, cam)
+            orc.os.light[...] = o_light  # the oracle scene reads this array in place
+            pipe.indirect_light(base, gb["texel"], gb["pos"], gb["normal"], gb["albedo"], gb["metallic"], 1.2, cam)
+            got_light = pipe.surface_light_cache()
+            assert np.array_equal(got_light, o_light), f"light cache differs on {(got_light != o_light).sum()} values after refresh at frame {f}"
+            means.append(float(f16(o_light)[..., :3].mean()))
+        rot = scenes.frame_rotation(f)
+        orc.update(rot)
+        pipe.update(rot)
+    assert_rays_match(pipe, orc)
+    assert_atlases_match(pipe, orc)
+    assert means[0] > float(f16(base)[..., :3].mean()) and means[1] >= means[0]  # each bounce adds energy
+    pipe.close()
