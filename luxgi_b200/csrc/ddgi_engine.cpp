@@ -86,6 +86,7 @@ struct LuxDDGIContext
     // per-frame tables
     DeviceBuffer dirs, wIrr, wDepth, scaleIrr, scaleDepth, nzIrr, nzDepth;
     DeviceBuffer origins, records, meta, chunkCounter; // wavefront trace scratch
+    DeviceBuffer sortTicket, binCounts, binBlockSums, sortedIdx; // sorted shade scratch (hit count lives in chunkCounter[1])
 
     // uGlobalSDF / uGlobalMipSDF / sdfData
     bool             hasSdf = false;
@@ -245,6 +246,13 @@ static int initializeProbeGrid(LuxDDGIContext& c)
         const size_t nrec = lux::trace_record_count(c.probeCount, u.raysPerProbe);
         if ((rc = allocZero(c, c.records, nrec * sizeof(float4))) != LUX_OK) return rc;
         if ((rc = allocZero(c, c.meta, nrec * sizeof(uint32_t))) != LUX_OK) return rc;
+        if (!(c.flags & LUX_DDGI_FLAG_SHADE_UNSORTED) && nrec < (size_t(1) << 32))
+        {
+            if ((rc = allocZero(c, c.sortTicket, nrec * sizeof(uint2))) != LUX_OK) return rc;
+            if ((rc = allocZero(c, c.sortedIdx, nrec * sizeof(uint32_t))) != LUX_OK) return rc;
+            if ((rc = allocZero(c, c.binCounts, lux::trace_sort_bins(c.probeCount, u.raysPerProbe) * sizeof(uint32_t))) != LUX_OK) return rc;
+            if ((rc = allocZero(c, c.binBlockSums, lux::trace_sort_blocks(c.probeCount, u.raysPerProbe) * sizeof(uint32_t))) != LUX_OK) return rc;
+        }
     }
     c.frames      = 0;
     c.pingPong    = 0;
@@ -354,6 +362,15 @@ static int system(LuxDDGIContext& c, const LuxTracePushConstants& push)
     p.steps    = nullptr;
     p.records  = (float4*)c.records.ptr;
     p.meta     = (uint32_t*)c.meta.ptr;
+    if (c.sortedIdx.ptr)
+    {
+        p.invChunkSize = c.hasAtlas ? 1.0f / c.atlasData.chunkSize : 0.0f;
+        p.sortTicket   = (uint2*)c.sortTicket.ptr;
+        p.binCounts    = (uint32_t*)c.binCounts.ptr;
+        p.binBlockSums = (uint32_t*)c.binBlockSums.ptr;
+        p.hitCount     = (uint32_t*)c.chunkCounter.ptr + 1;
+        p.sortedIdx    = (uint32_t*)c.sortedIdx.ptr;
+    }
     const int variant = (c.flags & LUX_DDGI_FLAG_TRACE_SIMPLE) ? 0 : (c.sdfTex ? 2 : 1);
     c.launches += launch_trace(p, variant, (unsigned int*)c.chunkCounter.ptr, c.stream, c.lightPending ? c.evLightReady : nullptr,
                                (c.flags & LUX_DDGI_FLAG_STAGE_TIMERS) ? c.ev[5] : nullptr);
@@ -601,7 +618,7 @@ int lux_ddgi_destroy(LuxDDGIContext* c)
     if (c->copyStream)
         cudaStreamSynchronize(c->copyStream);
     DeviceBuffer* all[] = {&c->radiance, &c->directionDepth, &c->irradiance[0], &c->irradiance[1], &c->depth[0], &c->depth[1],
-                           &c->dirs, &c->wIrr, &c->wDepth, &c->scaleIrr, &c->scaleDepth, &c->nzIrr, &c->nzDepth, &c->origins, &c->records, &c->meta, &c->chunkCounter, &c->sdf, &c->mip, &c->chunks, &c->cull,
+                           &c->dirs, &c->wIrr, &c->wDepth, &c->scaleIrr, &c->scaleDepth, &c->nzIrr, &c->nzDepth, &c->origins, &c->records, &c->meta, &c->chunkCounter, &c->sortTicket, &c->binCounts, &c->binBlockSums, &c->sortedIdx, &c->sdf, &c->mip, &c->chunks, &c->cull,
                            &c->objects, &c->objectInverse, &c->chunkMasks, &c->tiles, &c->light, &c->atlasDepth, &c->sky};
     for (DeviceBuffer* b : all)
         b->release();

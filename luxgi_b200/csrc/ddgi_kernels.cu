@@ -1189,6 +1189,218 @@ __global__ void __launch_bounds__(256, SHADE_BLOCKS_PER_SM) shade_kernel(const _
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Stage 2, sorted form (default): CLASSIFY -> SCAN -> SCATTER -> SHADE_SORTED.
+//
+// In ray order a warp holds hits of 32 parallel rays from a 240-voxel-long row of probes: they fall into ~12 different
+// culling chunks, so the surface-cache loops ran with 13-17 of 32 lanes (ncu, profiles/r1_v5_*).  The sorted form bins every
+// hit by (output window, culling chunk, chunk octant) with a counting sort and shades in bin order: the lanes of a warp then
+// walk the SAME culled object list with the same prefilter mask and mostly the same tiles.  Per-ray arithmetic is untouched
+// (each ray's result depends on no other ray), so results stay bit-identical to the ray-order kernel.
+//   classify      one thread per record, ray-order tiling of the old shade kernel: writes direction+distance for every ray and
+//                 the final radiance of misses / inside rays (coalesced 64-byte row segments); hits take a ticket in their bin
+//   scan          exclusive prefix sum over the bins (3 small kernels)
+//   scatter       sortedIdx[prefix[bin] + ticket] = record index
+//   shade_sorted  persistent grid over the sorted hit list: normal (6 taps) + surface cache; 8-byte radiance store per hit.
+// The leading "window" part of the key (2^22 records = 32 MiB of radiance) keeps those scattered stores inside an
+// L2-resident range, so sectors are merged in L2 before they reach HBM.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int SORT_WINDOW_SHIFT     = 22;
+constexpr int SORT_BINS_PER_WINDOW  = LUX_SURFACE_ATLAS_CHUNKS_RESOLUTION * LUX_SURFACE_ATLAS_CHUNKS_RESOLUTION * LUX_SURFACE_ATLAS_CHUNKS_RESOLUTION * 8;
+constexpr int SCAN_THREADS          = 1024;
+constexpr int SCAN_BINS_PER_BLOCK   = SCAN_THREADS * 4;
+
+// Bin of a hit position.  Only groups work, never enters a result: plain (approximate) arithmetic is fine.
+__device__ __forceinline__ uint32_t shade_bin(const TraceParams& P, f3 pos)
+{
+    const int   N    = LUX_SURFACE_ATLAS_CHUNKS_RESOLUTION;
+    const float half = (float)N * 0.5f, inv = P.invChunkSize;
+    float fx = pos.x * inv + half, fy = pos.y * inv + half, fz = pos.z * inv + half;
+    float gx = floorf(fx), gy = floorf(fy), gz = floorf(fz);
+    int cx = iclamp((int)gx, 0, N - 1), cy = iclamp((int)gy, 0, N - 1), cz = iclamp((int)gz, 0, N - 1);
+    int oct = ((fz - gz) >= 0.5f ? 4 : 0) | ((fy - gy) >= 0.5f ? 2 : 0) | ((fx - gx) >= 0.5f ? 1 : 0);
+    return (uint32_t)(((cz * N + cy) * N + cx) * 8 + oct);
+}
+
+__global__ void __launch_bounds__(256) classify_kernel(const __grid_constant__ TraceParams P, int rayGroups)
+{
+    __shared__ uint2 sRad[32][TRACE_RAYS_PER_BLOCK + 1];
+    __shared__ uint2 sDir[32][TRACE_RAYS_PER_BLOCK + 1];
+
+    const int lane = threadIdx.x & 31, sub = threadIdx.x >> 5;
+    const long long unit = blockIdx.x >> 1;
+    const int rayInUnit  = ((blockIdx.x & 1) << 3) + sub;
+    const long long g    = unit * UNIT_RAYS + rayInUnit * 32 + lane;
+    const int probeLocal = (int)(unit / rayGroups) * 32 + lane;
+    const int rayId      = (int)(unit % rayGroups) * TW_RAYS_PER_UNIT + rayInUnit;
+    const bool valid     = probeLocal < P.probeCount && rayId < P.raysPerProbe;
+    const LuxGlobalSDFData& data = P.sdf;
+
+    uint2 ticket = make_uint2(0xffffffffu, 0u);
+    if (valid)
+    {
+        const float4   rec  = __ldg(P.records + g);
+        const uint32_t meta = __ldg(P.meta + g);
+        const uint32_t hc = meta & 3u, kind = (meta >> 2) & 3u;
+        float4 d4 = __ldg(P.dirs + rayId);
+        f3     d  = {d4.x, d4.y, d4.z};
+        f4     radiance;
+        if (kind == RAY_HIT)
+        {
+            radiance = {0.0f, 0.0f, 0.0f, gmax(rec.x + data.cascadeVoxelSize[hc] * 0.5f, 0.0f)};
+            if (P.hasAtlas)
+            { // rgb comes from shade_sorted_kernel
+                float4 o4 = __ldg(P.origins + probeLocal);
+                f3     o  = {o4.x, o4.y, o4.z};
+                uint32_t bin = (uint32_t)(g >> SORT_WINDOW_SHIFT) * (uint32_t)SORT_BINS_PER_WINDOW + shade_bin(P, o + d * rec.x);
+                ticket = make_uint2(bin, atomicAdd(P.binCounts + bin, 1u));
+            }
+        }
+        else if (kind == RAY_INSIDE)
+            radiance = {0.0f, 0.0f, 0.0f, LUX_GLOBAL_SDF_WORLD_SIZE};
+        else
+        {
+            f3 s     = sample_sky(P, d);
+            radiance = {s.x, s.y, s.z, LUX_GLOBAL_SDF_WORLD_SIZE};
+        }
+        uint32_t r0 = f2h_bits(radiance.x), r1 = f2h_bits(radiance.y), r2 = f2h_bits(radiance.z);
+        uint32_t d0 = f2h_bits(d.x), d1 = f2h_bits(d.y), d2 = f2h_bits(d.z), d3 = f2h_bits(radiance.w);
+        sRad[lane][sub] = make_uint2(r0 | (r1 << 16), r2);
+        sDir[lane][sub] = make_uint2(d0 | (d1 << 16), d2 | (d3 << 16));
+        if (P.steps)
+            P.steps[(size_t)probeLocal * P.raysPerProbe + rayId] = (uint16_t)(meta >> 4);
+    }
+    P.sortTicket[g] = ticket;
+    __syncthreads();
+    const int pl = threadIdx.x / TRACE_RAYS_PER_BLOCK, rl = threadIdx.x % TRACE_RAYS_PER_BLOCK;
+    const int oProbe = (int)(unit / rayGroups) * 32 + pl;
+    const int oRay   = (int)(unit % rayGroups) * TW_RAYS_PER_UNIT + ((blockIdx.x & 1) << 3) + rl;
+    if (oProbe < P.probeCount && oRay < P.raysPerProbe)
+    {
+        size_t o = (size_t)oProbe * P.raysPerProbe + oRay;
+        P.radiance[o] = sRad[pl][rl];
+        P.dirDist[o]  = sDir[pl][rl];
+    }
+}
+
+// exclusive scan of one value per thread over a 1024-thread block; returns the prefix, *total = block sum
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* sWarp, uint32_t* total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+        uint32_t n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o)
+            inc += n;
+    }
+    if (lane == 31)
+        sWarp[warp] = inc;
+    __syncthreads();
+    if (warp == 0)
+    {
+        uint32_t w = sWarp[lane], winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            uint32_t n = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o)
+                winc += n;
+        }
+        sWarp[lane] = winc - w;
+        if (lane == 31)
+            sWarp[32] = winc;
+    }
+    __syncthreads();
+    uint32_t r = sWarp[warp] + inc - v;
+    *total     = sWarp[32];
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_reduce_kernel(const uint4* __restrict__ counts, uint32_t* __restrict__ blockSums)
+{
+    __shared__ uint32_t sWarp[33];
+    uint4    v = counts[(size_t)blockIdx.x * SCAN_THREADS + threadIdx.x];
+    uint32_t total;
+    block_exclusive_scan(v.x + v.y + v.z + v.w, sWarp, &total);
+    if (threadIdx.x == 0)
+        blockSums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_top_kernel(uint32_t* __restrict__ blockSums, int nb, uint32_t* __restrict__ total)
+{
+    __shared__ uint32_t sWarp[33];
+    uint32_t carry = 0;
+    for (int base = 0; base < nb; base += SCAN_THREADS)
+    {
+        int      i = base + threadIdx.x;
+        uint32_t v = i < nb ? blockSums[i] : 0u, t;
+        uint32_t e = block_exclusive_scan(v, sWarp, &t);
+        if (i < nb)
+            blockSums[i] = carry + e;
+        carry += t;
+    }
+    if (threadIdx.x == 0)
+        *total = carry;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(uint4* __restrict__ counts, const uint32_t* __restrict__ blockSums)
+{
+    __shared__ uint32_t sWarp[33];
+    const size_t i = (size_t)blockIdx.x * SCAN_THREADS + threadIdx.x;
+    uint4    v = counts[i];
+    uint32_t total;
+    uint32_t b = blockSums[blockIdx.x] + block_exclusive_scan(v.x + v.y + v.z + v.w, sWarp, &total);
+    counts[i]  = make_uint4(b, b + v.x, b + v.x + v.y, b + v.x + v.y + v.z);
+}
+
+__global__ void __launch_bounds__(256) scatter_kernel(const uint2* __restrict__ ticket, const uint32_t* __restrict__ prefix,
+                                                      uint32_t* __restrict__ sortedIdx, size_t records)
+{
+    size_t g = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (g >= records)
+        return;
+    uint2 t = __ldg(ticket + g);
+    if (t.x != 0xffffffffu)
+        sortedIdx[__ldg(prefix + t.x) + t.y] = (uint32_t)g;
+}
+
+template <bool TEX>
+__global__ void __launch_bounds__(256, SHADE_BLOCKS_PER_SM) shade_sorted_kernel(const __grid_constant__ TraceParams P, int rayGroups)
+{
+    __shared__ uint32_t sCand[TW_MAX_CAND][CAND_STRIDE];
+    const SdfSampler<TEX> sdf(P);
+    const LuxGlobalSDFData& data = P.sdf;
+    const uint32_t hits = *P.hitCount;
+    const float texelOffset = __fdiv_rn(1.0f, data.resolution);
+    for (uint32_t t = blockIdx.x * 256u + threadIdx.x; t < hits; t += gridDim.x * 256u)
+    {
+        const uint32_t g    = __ldg(P.sortedIdx + t);
+        const uint32_t unit = g / UNIT_RAYS, rem = g % UNIT_RAYS;
+        const int probeLocal = (int)(unit / rayGroups) * 32 + (int)(rem & 31u);
+        const int rayId      = (int)(unit % rayGroups) * TW_RAYS_PER_UNIT + (int)(rem >> 5);
+        const float4   rec = __ldg(P.records + g);
+        const uint32_t hc  = __ldg(P.meta + g) & 3u;
+        float4 d4 = __ldg(P.dirs + rayId);
+        float4 o4 = __ldg(P.origins + probeLocal);
+        f3     d  = {d4.x, d4.y, d4.z}, o = {o4.x, o4.y, o4.z};
+        float xp = sdf.sampleTex(rec.y + texelOffset, rec.z, rec.w);
+        float xn = sdf.sampleTex(rec.y - texelOffset, rec.z, rec.w);
+        float yp = sdf.sampleTex(rec.y, rec.z + texelOffset, rec.w);
+        float yn = sdf.sampleTex(rec.y, rec.z - texelOffset, rec.w);
+        float zp = sdf.sampleTex(rec.y, rec.z, rec.w + texelOffset);
+        float zn = sdf.sampleTex(rec.y, rec.z, rec.w - texelOffset);
+        f3    normal = normalize3({xp - xn, yp - yn, zp - zn});
+        f3    hitPosition      = o + d * rec.x;
+        float surfaceThreshold = data.cascadeVoxelSize[hc] * 1.05f;
+        f4    sc = sample_global_surface_atlas_2p(P, hitPosition, normal, surfaceThreshold, &sCand[0][threadIdx.x]);
+        uint32_t r0 = f2h_bits(sc.x), r1 = f2h_bits(sc.y), r2 = f2h_bits(sc.z);
+        P.radiance[(size_t)probeLocal * P.raysPerProbe + rayId] = make_uint2(r0 | (r1 << 16), r2);
+    }
+}
+
 __global__ void probe_origins_kernel(const TraceParams P, float4* __restrict__ origins)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1969,6 +2181,37 @@ void launch_probe_origins(const TraceParams& p, cudaStream_t s)
     probe_origins_kernel<<<(p.probeCount + 255) / 256, 256, 0, s>>>(p, const_cast<float4*>(p.origins));
 }
 
+size_t trace_sort_bins(int probeCount, int raysPerProbe)
+{
+    const size_t records = trace_record_count(probeCount, raysPerProbe);
+    const size_t windows = (records + (size_t(1) << SORT_WINDOW_SHIFT) - 1) >> SORT_WINDOW_SHIFT;
+    const size_t bins    = windows * SORT_BINS_PER_WINDOW;
+    return (bins + SCAN_BINS_PER_BLOCK - 1) / SCAN_BINS_PER_BLOCK * SCAN_BINS_PER_BLOCK;
+}
+size_t trace_sort_blocks(int probeCount, int raysPerProbe) { return trace_sort_bins(probeCount, raysPerProbe) / SCAN_BINS_PER_BLOCK; }
+
+// classify -> scan -> scatter -> shade_sorted (see the comment above classify_kernel); returns the number of launches
+template <bool TEX>
+static int launch_shade_sorted(const TraceParams& p, int rayGroups, long long units, cudaStream_t s)
+{
+    const size_t records = (size_t)units * UNIT_RAYS;
+    const size_t bins    = trace_sort_bins(p.probeCount, p.raysPerProbe);
+    const int    nb      = (int)(bins / SCAN_BINS_PER_BLOCK);
+    cudaMemsetAsync(p.binCounts, 0, bins * sizeof(uint32_t), s);
+    classify_kernel<<<(unsigned)(units * 2), 256, 0, s>>>(p, rayGroups);
+    if (!p.hasAtlas)
+        return 1; // hits carry no radiance without a surface cache: classify wrote the final values
+    scan_reduce_kernel<<<nb, SCAN_THREADS, 0, s>>>((const uint4*)p.binCounts, p.binBlockSums);
+    scan_top_kernel<<<1, SCAN_THREADS, 0, s>>>(p.binBlockSums, nb, p.hitCount);
+    scan_apply_kernel<<<nb, SCAN_THREADS, 0, s>>>((uint4*)p.binCounts, p.binBlockSums);
+    scatter_kernel<<<(unsigned)((records + 255) / 256), 256, 0, s>>>(p.sortTicket, p.binCounts, p.sortedIdx, records);
+    long long blocks = (long long)(records + 255) / 256;
+    if (blocks > 148ll * SHADE_BLOCKS_PER_SM)
+        blocks = 148ll * SHADE_BLOCKS_PER_SM;
+    shade_sorted_kernel<TEX><<<(unsigned)blocks, 256, 0, s>>>(p, rayGroups);
+    return 6;
+}
+
 int launch_trace(const TraceParams& p, int variant, unsigned int* chunkCounter, cudaStream_t s, cudaEvent_t beforeShade, cudaEvent_t afterMarch)
 {
     if (variant == 0)
@@ -1996,6 +2239,8 @@ int launch_trace(const TraceParams& p, int variant, unsigned int* chunkCounter, 
             cudaEventRecord(afterMarch, s);
         if (beforeShade) // the march never reads the surface cache: a pending light-cache upload only gates the shade
             cudaStreamWaitEvent(s, beforeShade, 0);
+        if (p.sortedIdx)
+            return 1 + launch_shade_sorted<true>(p, rayGroups, units, s);
         shade_kernel<true><<<(unsigned)(units * 2), 256, 0, s>>>(p, rayGroups);
     }
     else
@@ -2005,6 +2250,8 @@ int launch_trace(const TraceParams& p, int variant, unsigned int* chunkCounter, 
             cudaEventRecord(afterMarch, s);
         if (beforeShade)
             cudaStreamWaitEvent(s, beforeShade, 0);
+        if (p.sortedIdx)
+            return 1 + launch_shade_sorted<false>(p, rayGroups, units, s);
         shade_kernel<false><<<(unsigned)(units * 2), 256, 0, s>>>(p, rayGroups);
     }
     return 2;

@@ -45,6 +45,13 @@ struct TraceParams
     uint2*        radiance; // [probeCount][R] RGBA16F
     uint2*        dirDist;  // [probeCount][R] RGBA16F
     uint16_t*     steps;    // optional [probeCount][R] march-step counts (debug / roofline counters)
+    // sorted shade (null sortedIdx = shade in ray order)
+    float     invChunkSize;
+    uint2*    sortTicket;   // [records] (bin, ticket within bin) or (0xffffffff, -) for rays that need no shading
+    uint32_t* binCounts;    // [trace_sort_bins] hit histogram, turned into its exclusive prefix sum in place
+    uint32_t* binBlockSums; // [trace_sort_blocks]
+    uint32_t* hitCount;     // [1] number of hits = length of sortedIdx in use
+    uint32_t* sortedIdx;    // [records] record indices in bin order
 };
 
 struct BlendParams
@@ -85,6 +92,8 @@ void launch_object_inverse(const LuxObjectBuffer* objects, int count, float* inv
 int    launch_trace(const TraceParams& p, int variant, unsigned int* chunkCounter, cudaStream_t s, cudaEvent_t beforeShade,
                     cudaEvent_t afterMarch);
 size_t trace_record_count(int probeCount, int raysPerProbe);
+size_t trace_sort_bins(int probeCount, int raysPerProbe);   // bins of the sorted shade's counting sort (padded to the scan's block size)
+size_t trace_sort_blocks(int probeCount, int raysPerProbe); // scan blocks over those bins
 void   launch_probe_origins(const TraceParams& p, cudaStream_t s);
 void launch_blend_irradiance(const BlendParams& p, cudaStream_t s);
 void launch_blend_depth(const BlendParams& p, cudaStream_t s);

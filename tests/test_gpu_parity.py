@@ -207,7 +207,9 @@ def test_restore_resumes_bit_identically():
 
 
 @pytest.mark.parametrize("flags,name", [(0, "wavefront+tld4"), (abi.FLAG_SDF_LOADS, "wavefront+loads"), (abi.FLAG_TRACE_SIMPLE, "simple"),
-                                        (abi.FLAG_NO_PREFILTER, "wavefront, full object lists")])
+                                        (abi.FLAG_NO_PREFILTER, "wavefront, full object lists"),
+                                        (abi.FLAG_SHADE_UNSORTED, "wavefront, hits shaded in ray order"),
+                                        (abi.FLAG_SHADE_UNSORTED | abi.FLAG_SDF_LOADS, "wavefront+loads, ray order")])
 @pytest.mark.parametrize("cfg", ["c1", "city64"])
 def test_trace_variants_match_oracle(oracle, flags, name, cfg):
     """Every trace kernel variant (thread-per-ray, wavefront with explicit loads, wavefront with texture gathers)
