@@ -731,7 +731,7 @@ struct SdfSampler<true>
 };
 
 // One tile of one candidate object, split in two: the normal weight (cheap, rejects most tiles) ...
-__device__ __forceinline__ float tile_normal_weight(const LuxTileBuffer* __restrict__ tile, f3 normal, float* tm)
+__device__ __forceinline__ void load_tile_transform(const LuxTileBuffer* __restrict__ tile, float* tm)
 {
 #pragma unroll
     for (int i = 0; i < 4; i++)
@@ -739,6 +739,10 @@ __device__ __forceinline__ float tile_normal_weight(const LuxTileBuffer* __restr
         float4 c = __ldg(reinterpret_cast<const float4*>(tile->transform) + i);
         tm[i * 4 + 0] = c.x; tm[i * 4 + 1] = c.y; tm[i * 4 + 2] = c.z; tm[i * 4 + 3] = c.w;
     }
+}
+__device__ __forceinline__ float tile_normal_weight(const LuxTileBuffer* __restrict__ tile, f3 normal, float* tm)
+{
+    load_tile_transform(tile, tm);
     f3    nt = normalize3(mat4_mul_point(tm, normal, 1.0f));
     float nw = gclamp(nt.z, 0.0f, 1.0f);
     return __fdiv_rn(nw - LUX_SURFACE_ATLAS_TILE_NORMAL_THRESHOLD, 1.0f - LUX_SURFACE_ATLAS_TILE_NORMAL_THRESHOLD);
@@ -885,7 +889,10 @@ __device__ __forceinline__ f4 sample_global_surface_atlas_2p(const TraceParams& 
                 float tm[16];
                 float nw = tile_normal_weight(P.tiles + tileOffset, normal, tm);
                 if (nw > 0.0f)
+                {
                     passing |= 1u << i;
+                    cand[(TW_MAX_CAND + i) * CAND_STRIDE] = __float_as_uint(nw); // reused by pass B
+                }
             }
             while (passing)
             {
@@ -893,7 +900,8 @@ __device__ __forceinline__ f4 sample_global_surface_atlas_2p(const TraceParams& 
                 passing &= passing - 1;
                 const LuxTileBuffer* tile = P.tiles + __ldg(object->tileOffset + i);
                 float tm[16];
-                float nw = tile_normal_weight(tile, normal, tm);
+                load_tile_transform(tile, tm);
+                float nw = __uint_as_float(cand[(TW_MAX_CAND + i) * CAND_STRIDE]);
                 f4 s = tile_sample(P, tile, tm, localPosition, nw, surfaceThreshold);
                 result.x += s.x; result.y += s.y; result.z += s.z; result.w += s.w;
             }
@@ -951,8 +959,20 @@ __global__ void __launch_bounds__(32 * MARCH_WARPS, MARCH_BLOCKS_PER_SM) march_k
     const float chunkMarginDistance = __fdiv_rn((float)LUX_GLOBAL_SDF_RASTERIZE_CHUNK_MARGIN, data.resolution);
     const float cascadesCountF      = (float)data.cascadesCount;
 
-    long long poolNext = 0, poolEnd = 0; // warp-uniform
-    bool      exhausted = false;
+    // Per-cascade divisors (cascade extent and voxel size): warp-uniform, so they live in shared memory rather than in six
+    // registers per lane, and their reciprocals are taken once per block instead of once per ray.
+    __shared__ float4 sDiv[LUX_MAX_CASCADES]; // (2*cd, 1/(2*cd) or 0, voxel, 1/voxel or 0): 0 = not a power of two, divide
+    if (threadIdx.x < LUX_MAX_CASCADES)
+    {
+        ExactDivisor m(data.cascadePosDistance[threadIdx.x][3] * 2.0f), v(data.cascadeVoxelSize[threadIdx.x]);
+        sDiv[threadIdx.x] = make_float4(m.d, m.inv, v.d, v.inv);
+    }
+    __syncthreads();
+
+    long long chunkStart = 0;                       // warp-uniform: first ray of the warp's current chunk
+    int  poolOff = MARCH_CHUNK_RAYS;                // next unclaimed ray of the chunk
+    int  poolProbeBase = 0, poolRayBase = 0;        // probe / ray id of the chunk's first ray
+    bool exhausted = false;
 
     // per-lane ray state
     bool      active = false, nearSurface = true;
@@ -960,15 +980,12 @@ __global__ void __launch_bounds__(32 * MARCH_WARPS, MARCH_BLOCKS_PER_SM) march_k
     f3        origin = {0, 0, 0}, dir = {0, 0, 0}, traceEnd = {0, 0, 0}, cc = {0, 0, 0};
     uint32_t  cascade = 0, step = 0, totalSteps = 0;
     float     stepTime = 0.0f, farT = 0.0f, nextIntersectionStart = 0.0f, cd = 0.0f, voxelSize = 0.0f;
-    ExactDivisor divMaxDistance, divVoxel;
     const ExactDivisor divCascades(cascadesCountF);
 
     auto begin_cascade = [&]() {
         cc        = {data.cascadePosDistance[cascade][0], data.cascadePosDistance[cascade][1], data.cascadePosDistance[cascade][2]};
         cd        = data.cascadePosDistance[cascade][3];
         voxelSize = data.cascadeVoxelSize[cascade];
-        divMaxDistance = ExactDivisor(cd * 2.0f);
-        divVoxel       = ExactDivisor(voxelSize);
         f3    worldPosition = origin + dir * (voxelSize * 0.0f); // cascadeTraceStartBias = 0
         f3    ext = {cd, cd, cd};
         float nearT, fT;
@@ -996,8 +1013,8 @@ __global__ void __launch_bounds__(32 * MARCH_WARPS, MARCH_BLOCKS_PER_SM) march_k
         unsigned idle = __ballot_sync(FULL, !active);
         if (idle && (__popc(idle) >= MARCH_REFILL_MIN || idle == FULL) && !exhausted)
         {
-            if (poolNext >= poolEnd)
-            { // fetch the next chunk of rays
+            if (poolOff >= MARCH_CHUNK_RAYS)
+            { // fetch the next chunk of rays: 8 ray slots x 32 probes of one unit
                 unsigned int c = 0;
                 if (lane == 0)
                     c = atomicAdd(chunkCounter, 1u);
@@ -1006,23 +1023,25 @@ __global__ void __launch_bounds__(32 * MARCH_WARPS, MARCH_BLOCKS_PER_SM) march_k
                     exhausted = true;
                 else
                 {
-                    poolNext = (long long)c * MARCH_CHUNK_RAYS;
-                    poolEnd  = poolNext + MARCH_CHUNK_RAYS;
+                    const unsigned int unit = c / (UNIT_RAYS / MARCH_CHUNK_RAYS), half = c % (UNIT_RAYS / MARCH_CHUNK_RAYS);
+                    chunkStart    = (long long)c * MARCH_CHUNK_RAYS;
+                    poolOff       = 0;
+                    poolProbeBase = (int)(unit / (unsigned)rayGroups) * 32;
+                    poolRayBase   = (int)(unit % (unsigned)rayGroups) * TW_RAYS_PER_UNIT + (int)half * (MARCH_CHUNK_RAYS / 32);
                 }
             }
             if (!exhausted)
             {
-                const long long base = poolNext;
-                const int avail = (int)min((long long)__popc(idle), poolEnd - poolNext);
-                poolNext += avail;
+                const int base  = poolOff;
+                const int avail = min(__popc(idle), MARCH_CHUNK_RAYS - poolOff);
+                poolOff += avail;
                 const int rank = __popc(idle & ((1u << lane) - 1u));
                 if (!active && rank < avail)
                 {
-                    g = base + rank;
-                    const long long unit = g / UNIT_RAYS;
-                    const int rem = (int)(g % UNIT_RAYS);
-                    const int probeLocal = (int)(unit / rayGroups) * 32 + (rem & 31);
-                    const int rayId      = (int)(unit % rayGroups) * TW_RAYS_PER_UNIT + (rem >> 5);
+                    const int off        = base + rank;
+                    const int probeLocal = poolProbeBase + (off & 31);
+                    const int rayId      = poolRayBase + (off >> 5);
+                    g = chunkStart + off;
                     if (probeLocal < P.probeCount && rayId < P.raysPerProbe)
                     {
                         float4 o4 = __ldg(P.origins + probeLocal);
@@ -1066,9 +1085,13 @@ __global__ void __launch_bounds__(32 * MARCH_WARPS, MARCH_BLOCKS_PER_SM) march_k
                 f3 stepPosition = origin + dir * stepTime;
                 f3 pc           = stepPosition - cc;
                 float cascadeMaxDistance = cd * 2.0f;
-                f3 cuv = {gclamp(divMaxDistance.div(pc.x) + 0.5f, 0.0f, 1.0f),
-                          gclamp(divMaxDistance.div(pc.y) + 0.5f, 0.0f, 1.0f),
-                          gclamp(divMaxDistance.div(pc.z) + 0.5f, 0.0f, 1.0f)};
+                const float4 dv = sDiv[cascade];
+                f3 cuv;
+                if (dv.y != 0.0f) // power-of-two extent: x * (1/d) is the correctly rounded quotient
+                    cuv = {gclamp(pc.x * dv.y + 0.5f, 0.0f, 1.0f), gclamp(pc.y * dv.y + 0.5f, 0.0f, 1.0f), gclamp(pc.z * dv.y + 0.5f, 0.0f, 1.0f)};
+                else
+                    cuv = {gclamp(__fdiv_rn(pc.x, dv.x) + 0.5f, 0.0f, 1.0f), gclamp(__fdiv_rn(pc.y, dv.x) + 0.5f, 0.0f, 1.0f),
+                           gclamp(__fdiv_rn(pc.z, dv.x) + 0.5f, 0.0f, 1.0f)};
                 f3 uvw = {divCascades.div((float)cascade + cuv.x), cuv.y, cuv.z};
                 // The full-resolution tap is needed on ~87 % of the steps (measured tap counters, C4), and once a ray is near
                 // geometry it stays near: when the PREVIOUS step needed it, both taps are issued together, which removes one
@@ -1094,7 +1117,7 @@ __global__ void __launch_bounds__(32 * MARCH_WARPS, MARCH_BLOCKS_PER_SM) march_k
                 }
                 stepDistance *= cascadeMaxDistance;
                 float voxelHalf = voxelSize * 0.5f;
-                float minSurfaceThickness = voxelHalf * gclamp(divVoxel.div(stepTime), 0.0f, 1.0f);
+                float minSurfaceThickness = voxelHalf * gclamp(dv.w != 0.0f ? stepTime * dv.w : __fdiv_rn(stepTime, dv.z), 0.0f, 1.0f);
                 if (stepDistance < minSurfaceThickness)
                 {
                     float hitTime = gmax((stepTime + stepDistance) - minSurfaceThickness, 0.0f);
@@ -1123,7 +1146,7 @@ __global__ void __launch_bounds__(256, SHADE_BLOCKS_PER_SM) shade_kernel(const _
 {
     __shared__ uint2    sRad[32][TRACE_RAYS_PER_BLOCK + 1];
     __shared__ uint2    sDir[32][TRACE_RAYS_PER_BLOCK + 1];
-    __shared__ uint32_t sCand[TW_MAX_CAND][CAND_STRIDE];
+    __shared__ uint32_t sCand[TW_MAX_CAND + 6][CAND_STRIDE]; // candidates + the six tile normal weights
 
     const int lane = threadIdx.x & 31, sub = threadIdx.x >> 5; // sub = ray within the block's 8
     // block b covers half a unit: unit = b / 2, rays (b & 1) * 8 .. + 8 of the unit's 16
@@ -1222,64 +1245,93 @@ __device__ __forceinline__ uint32_t shade_bin(const TraceParams& P, f3 pos)
     return (uint32_t)(((cz * N + cy) * N + cx) * 8 + oct);
 }
 
-__global__ void __launch_bounds__(256) classify_kernel(const __grid_constant__ TraceParams P, int rayGroups)
+// One block = one unit (16 ray slots x 32 probes); each of the 128 threads owns CLASSIFY_RPT records of the same probe lane
+// and issues all their loads, then all their tickets, before the first use: the pass is a latency chain
+// (record -> bin -> returning atomic) per record, so memory-level parallelism per thread is what makes it stream.
+constexpr int CLASSIFY_RPT = 4;
+__global__ void __launch_bounds__(128) classify_kernel(const __grid_constant__ TraceParams P, int rayGroups)
 {
-    __shared__ uint2 sRad[32][TRACE_RAYS_PER_BLOCK + 1];
-    __shared__ uint2 sDir[32][TRACE_RAYS_PER_BLOCK + 1];
+    __shared__ uint2 sRad[32][TW_RAYS_PER_UNIT + 1];
+    __shared__ uint2 sDir[32][TW_RAYS_PER_UNIT + 1];
 
-    const int lane = threadIdx.x & 31, sub = threadIdx.x >> 5;
-    const long long unit = blockIdx.x >> 1;
-    const int rayInUnit  = ((blockIdx.x & 1) << 3) + sub;
-    const long long g    = unit * UNIT_RAYS + rayInUnit * 32 + lane;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long unit = blockIdx.x;
     const int probeLocal = (int)(unit / rayGroups) * 32 + lane;
-    const int rayId      = (int)(unit % rayGroups) * TW_RAYS_PER_UNIT + rayInUnit;
-    const bool valid     = probeLocal < P.probeCount && rayId < P.raysPerProbe;
+    const int rayBase    = (int)(unit % rayGroups) * TW_RAYS_PER_UNIT;
     const LuxGlobalSDFData& data = P.sdf;
+    const bool probeValid = probeLocal < P.probeCount;
 
-    uint2 ticket = make_uint2(0xffffffffu, 0u);
-    if (valid)
+    float4   rec[CLASSIFY_RPT];
+    uint32_t meta[CLASSIFY_RPT];
+    float4   d4[CLASSIFY_RPT];
+    bool     valid[CLASSIFY_RPT];
+    float4   o4 = probeValid ? __ldg(P.origins + probeLocal) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#pragma unroll
+    for (int k = 0; k < CLASSIFY_RPT; k++)
     {
-        const float4   rec  = __ldg(P.records + g);
-        const uint32_t meta = __ldg(P.meta + g);
-        const uint32_t hc = meta & 3u, kind = (meta >> 2) & 3u;
-        float4 d4 = __ldg(P.dirs + rayId);
-        f3     d  = {d4.x, d4.y, d4.z};
-        f4     radiance;
-        if (kind == RAY_HIT)
-        {
-            radiance = {0.0f, 0.0f, 0.0f, gmax(rec.x + data.cascadeVoxelSize[hc] * 0.5f, 0.0f)};
-            if (P.hasAtlas)
-            { // rgb comes from shade_sorted_kernel
-                float4 o4 = __ldg(P.origins + probeLocal);
-                f3     o  = {o4.x, o4.y, o4.z};
-                uint32_t bin = (uint32_t)(g >> SORT_WINDOW_SHIFT) * (uint32_t)SORT_BINS_PER_WINDOW + shade_bin(P, o + d * rec.x);
-                ticket = make_uint2(bin, atomicAdd(P.binCounts + bin, 1u));
-            }
-        }
-        else if (kind == RAY_INSIDE)
-            radiance = {0.0f, 0.0f, 0.0f, LUX_GLOBAL_SDF_WORLD_SIZE};
-        else
-        {
-            f3 s     = sample_sky(P, d);
-            radiance = {s.x, s.y, s.z, LUX_GLOBAL_SDF_WORLD_SIZE};
-        }
-        uint32_t r0 = f2h_bits(radiance.x), r1 = f2h_bits(radiance.y), r2 = f2h_bits(radiance.z);
-        uint32_t d0 = f2h_bits(d.x), d1 = f2h_bits(d.y), d2 = f2h_bits(d.z), d3 = f2h_bits(radiance.w);
-        sRad[lane][sub] = make_uint2(r0 | (r1 << 16), r2);
-        sDir[lane][sub] = make_uint2(d0 | (d1 << 16), d2 | (d3 << 16));
-        if (P.steps)
-            P.steps[(size_t)probeLocal * P.raysPerProbe + rayId] = (uint16_t)(meta >> 4);
+        const int rayInUnit = warp + k * 4;
+        const long long g   = unit * UNIT_RAYS + rayInUnit * 32 + lane;
+        valid[k] = probeValid && rayBase + rayInUnit < P.raysPerProbe;
+        rec[k]   = valid[k] ? __ldg(P.records + g) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        meta[k]  = valid[k] ? __ldg(P.meta + g) : 0u;
+        d4[k]    = valid[k] ? __ldg(P.dirs + rayBase + rayInUnit) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
-    P.sortTicket[g] = ticket;
-    __syncthreads();
-    const int pl = threadIdx.x / TRACE_RAYS_PER_BLOCK, rl = threadIdx.x % TRACE_RAYS_PER_BLOCK;
-    const int oProbe = (int)(unit / rayGroups) * 32 + pl;
-    const int oRay   = (int)(unit % rayGroups) * TW_RAYS_PER_UNIT + ((blockIdx.x & 1) << 3) + rl;
-    if (oProbe < P.probeCount && oRay < P.raysPerProbe)
+    uint2 ticket[CLASSIFY_RPT];
+#pragma unroll
+    for (int k = 0; k < CLASSIFY_RPT; k++)
     {
-        size_t o = (size_t)oProbe * P.raysPerProbe + oRay;
-        P.radiance[o] = sRad[pl][rl];
-        P.dirDist[o]  = sDir[pl][rl];
+        const long long g = unit * UNIT_RAYS + (warp + k * 4) * 32 + lane;
+        ticket[k] = make_uint2(0xffffffffu, 0u);
+        if (valid[k] && ((meta[k] >> 2) & 3u) == RAY_HIT && P.hasAtlas)
+        { // rgb comes from shade_sorted_kernel
+            f3 o = {o4.x, o4.y, o4.z}, d = {d4[k].x, d4[k].y, d4[k].z};
+            uint32_t bin = (uint32_t)(g >> SORT_WINDOW_SHIFT) * (uint32_t)SORT_BINS_PER_WINDOW + shade_bin(P, o + d * rec[k].x);
+            ticket[k] = make_uint2(bin, atomicAdd(P.binCounts + bin, 1u));
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < CLASSIFY_RPT; k++)
+    {
+        const int rayInUnit = warp + k * 4;
+        const long long g   = unit * UNIT_RAYS + rayInUnit * 32 + lane;
+        if (valid[k])
+        {
+            const uint32_t hc = meta[k] & 3u, kind = (meta[k] >> 2) & 3u;
+            f3 d = {d4[k].x, d4[k].y, d4[k].z};
+            f4 radiance;
+            if (kind == RAY_HIT)
+                radiance = {0.0f, 0.0f, 0.0f, gmax(rec[k].x + data.cascadeVoxelSize[hc] * 0.5f, 0.0f)};
+            else if (kind == RAY_INSIDE)
+                radiance = {0.0f, 0.0f, 0.0f, LUX_GLOBAL_SDF_WORLD_SIZE};
+            else
+            {
+                f3 s     = sample_sky(P, d);
+                radiance = {s.x, s.y, s.z, LUX_GLOBAL_SDF_WORLD_SIZE};
+            }
+            uint32_t r0 = f2h_bits(radiance.x), r1 = f2h_bits(radiance.y), r2 = f2h_bits(radiance.z);
+            uint32_t d0 = f2h_bits(d.x), d1 = f2h_bits(d.y), d2 = f2h_bits(d.z), d3 = f2h_bits(radiance.w);
+            sRad[lane][rayInUnit] = make_uint2(r0 | (r1 << 16), r2);
+            sDir[lane][rayInUnit] = make_uint2(d0 | (d1 << 16), d2 | (d3 << 16));
+            if (P.steps)
+                P.steps[(size_t)probeLocal * P.raysPerProbe + rayBase + rayInUnit] = (uint16_t)(meta[k] >> 4);
+        }
+        P.sortTicket[g] = ticket[k];
+    }
+    __syncthreads();
+    // transposed write-out: 16 consecutive rays (128 bytes) per probe
+#pragma unroll
+    for (int k = 0; k < CLASSIFY_RPT; k++)
+    {
+        const int idx = threadIdx.x + k * 128;
+        const int pl = idx / TW_RAYS_PER_UNIT, rl = idx % TW_RAYS_PER_UNIT;
+        const int oProbe = (int)(unit / rayGroups) * 32 + pl;
+        const int oRay   = rayBase + rl;
+        if (oProbe < P.probeCount && oRay < P.raysPerProbe)
+        {
+            size_t o = (size_t)oProbe * P.raysPerProbe + oRay;
+            P.radiance[o] = sRad[pl][rl];
+            P.dirDist[o]  = sDir[pl][rl];
+        }
     }
 }
 
@@ -1370,7 +1422,7 @@ __global__ void __launch_bounds__(256) scatter_kernel(const uint2* __restrict__ 
 template <bool TEX>
 __global__ void __launch_bounds__(256, SHADE_BLOCKS_PER_SM) shade_sorted_kernel(const __grid_constant__ TraceParams P, int rayGroups)
 {
-    __shared__ uint32_t sCand[TW_MAX_CAND][CAND_STRIDE];
+    __shared__ uint32_t sCand[TW_MAX_CAND + 6][CAND_STRIDE]; // candidates + the six tile normal weights
     const SdfSampler<TEX> sdf(P);
     const LuxGlobalSDFData& data = P.sdf;
     const uint32_t hits = *P.hitCount;
@@ -2198,7 +2250,7 @@ static int launch_shade_sorted(const TraceParams& p, int rayGroups, long long un
     const size_t bins    = trace_sort_bins(p.probeCount, p.raysPerProbe);
     const int    nb      = (int)(bins / SCAN_BINS_PER_BLOCK);
     cudaMemsetAsync(p.binCounts, 0, bins * sizeof(uint32_t), s);
-    classify_kernel<<<(unsigned)(units * 2), 256, 0, s>>>(p, rayGroups);
+    classify_kernel<<<(unsigned)units, 128, 0, s>>>(p, rayGroups);
     if (!p.hasAtlas)
         return 1; // hits carry no radiance without a surface cache: classify wrote the final values
     scan_reduce_kernel<<<nb, SCAN_THREADS, 0, s>>>((const uint4*)p.binCounts, p.binBlockSums);
