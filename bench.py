@@ -225,8 +225,14 @@ def run_lux(args):
     if u.probeCounts[2] % world:
         raise SystemExit(f"{world} GPUs do not divide Z={u.probeCounts[2]}")
     stream = torch.cuda.Stream(device=dev)
-    flags = abi.FLAG_STAGE_TIMERS | {"texture": 0, "loads": abi.FLAG_SDF_LOADS, "simple": abi.FLAG_TRACE_SIMPLE}[args.trace]
+    flags = {"texture": 0, "loads": abi.FLAG_SDF_LOADS, "simple": abi.FLAG_TRACE_SIMPLE}[args.trace]
+    if args.no_pipeline:
+        flags |= abi.FLAG_NO_PIPELINE
+    if args.unsorted:
+        flags |= abi.FLAG_SHADE_UNSORTED
     shard_rank, shard_world = (rank, world) if args.emulate_shard is None else tuple(int(x) for x in args.emulate_shard.split('/'))
+    # The measured pipe runs lux_ddgi_update as shipped (probe batches pipelined over two streams, no stage events); the per-stage
+    # times and the kernel roofline come from a second, serialized pass below (LUX_DDGI_FLAG_STAGE_TIMERS = one batch, one stream).
     pipe = ddgi.DDGIPipeline(u, device=local, rank=shard_rank, world=shard_world, flags=flags, stream=stream.cuda_stream)
     pipe.set_scene(sc)
     st = pipe.state()
@@ -290,39 +296,19 @@ def run_lux(args):
         sampler.start()
     launches0 = pipe.state().kernelLaunches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    stage = {"setup": 0.0, "trace": 0.0, "blend": 0.0, "march": 0.0, "shade": 0.0}
     with torch.cuda.stream(stream):
         e0.record(stream)
     t_wall0 = time.perf_counter()
     for _ in range(args.steps):
         step(f); f += 1
-        if args.stage_every_step:
-            pipe.synchronize()
-            t = pipe.stage_ms()
-            stage["setup"] += t.setup_ms; stage["trace"] += t.trace_ms; stage["blend"] += t.blend_ms
-            stage["march"] += t.march_ms; stage["shade"] += t.shade_ms
     with torch.cuda.stream(stream):
         e1.record(stream)
     barrier()
     t_wall = time.perf_counter() - t_wall0
     ms_total = e0.elapsed_time(e1)
-    if not args.stage_every_step:
-        t = pipe.stage_ms()
-        stage = {"setup": t.setup_ms * args.steps, "trace": t.trace_ms * args.steps, "blend": t.blend_ms * args.steps,
-                 "march": t.march_ms * args.steps, "shade": t.shade_ms * args.steps}
     launches = pipe.state().kernelLaunches - launches0
     clocks = sampler.stop() if rank == 0 else None
-    tm = torch.tensor([ms_total, stage["trace"], stage["blend"], stage["setup"], stage["march"], stage["shade"]], device=dev, dtype=torch.float64)
-    per_rank = None
-    if world > 1:
-        allr = [torch.zeros_like(tm) for _ in range(world)]
-        dist.all_gather(allr, tm)
-        per_rank = [[round(float(x) / args.steps, 4) for x in t.tolist()[1:3]] for t in allr]
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-    ms_total, trace_ms, blend_ms, setup_ms, march_ms, shade_ms = [float(x) for x in tm.tolist()]
-    ms_per_step = ms_total / args.steps
     P_timed = st.probeCount * world  # == P unless --emulate-shard
-    value = P_timed * R * args.steps / (ms_total * 1e-3)
 
     e2e_value, e2e_s, light_bytes, d2h_bytes = None, None, 0, 0
     if not args.no_e2e:
@@ -356,6 +342,31 @@ def run_lux(args):
 
 
         d2h_bytes = int(pin_irr.numel() + pin_dep.numel())
+    # ---- serialized stage pass: same workload, one batch on one stream, CUDA events around every stage -----------------------
+    pipe.close()
+    views.clear()
+    pipe = ddgi.DDGIPipeline(u, device=local, rank=shard_rank, world=shard_world, flags=flags | abi.FLAG_STAGE_TIMERS, stream=stream.cuda_stream)
+    pipe.set_scene(sc)
+    stage = {"setup": 0.0, "trace": 0.0, "blend": 0.0, "march": 0.0, "shade": 0.0}
+    for i in range(2 + args.steps):
+        pipe.update(rot_of(f)); f += 1
+        if i >= 2:
+            pipe.synchronize()
+            t = pipe.stage_ms()
+            stage["setup"] += t.setup_ms; stage["trace"] += t.trace_ms; stage["blend"] += t.blend_ms
+            stage["march"] += t.march_ms; stage["shade"] += t.shade_ms
+    torch.cuda.synchronize()
+    tm = torch.tensor([ms_total, stage["trace"], stage["blend"], stage["setup"], stage["march"], stage["shade"]], device=dev, dtype=torch.float64)
+    per_rank = None
+    if world > 1:
+        allr = [torch.zeros_like(tm) for _ in range(world)]
+        dist.all_gather(allr, tm)
+        per_rank = [[round(float(x) / args.steps, 4) for x in t.tolist()[1:3]] for t in allr]
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    ms_total, trace_ms, blend_ms, setup_ms, march_ms, shade_ms = [float(x) for x in tm.tolist()]
+    ms_per_step = ms_total / args.steps
+    value = P_timed * R * args.steps / (ms_total * 1e-3)
+
     if rank == 0:
         peaks, peak_kind = measured_peaks()
         hbm = float(peaks["hbm_gbs"])
@@ -388,7 +399,9 @@ def run_lux(args):
                            + ("" if world == 1 else (" (on the compute stream)" if args.sync_allgather else " overlapped with the next step's trace"))),
             "stage_ms": {"setup": setup_ms / args.steps, "trace": trace_launch_ms, "march": march_launch_ms, "shade": shade_launch_ms,
                          "blend_border": blend_launch_ms,
-                         "other_incl_allgather": ms_per_step - (setup_ms + trace_ms + blend_ms) / args.steps},
+                         "update_minus_stage_sum": ms_per_step - (setup_ms + trace_ms + blend_ms) / args.steps,
+                         "note": "stages timed in a second, serialized pass (one batch, one stream, CUDA events on the engine's stream); "
+                                 "ms_per_update is the shipped update: probe batches pipelined over two streams"},
             "trace_rays_per_s": probes_rank * world * R / (trace_launch_ms * 1e-3),
             "per_rank_trace_blend_ms": per_rank,
             "roofline": roofs[dominant],
@@ -427,7 +440,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--emulate-shard", default=None, help="r/w: run shard r of w on one GPU without any collective (profiling aid)")
     ap.add_argument("--sync-allgather", action="store_true", help="all-gather on the compute stream (no overlap with the next trace)")
-    ap.add_argument("--stage-every-step", action="store_true", help="sync + read stage timers every step (perturbs the total)")
+    ap.add_argument("--no-pipeline", action="store_true", help="A/B: one batch on one stream instead of two-stream probe batches")
+    ap.add_argument("--unsorted", action="store_true", help="A/B: shade hits in ray order (no counting sort by culling chunk)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -172,7 +172,8 @@ enum {
     LUX_DDGI_FLAG_SDF_LOADS     = 1u << 3, /* read the SDF with explicit fp16 global loads instead             */
     LUX_DDGI_FLAG_TRACE_SIMPLE  = 1u << 4, /* one-thread-per-ray trace kernel (no wavefront scheduling), for A/B */
     LUX_DDGI_FLAG_NO_PREFILTER  = 1u << 5, /* walk the full per-chunk object lists (no sub-cell candidate masks), for A/B */
-    LUX_DDGI_FLAG_SHADE_UNSORTED= 1u << 6  /* shade hits in ray order instead of culling-chunk order (no counting sort), for A/B */
+    LUX_DDGI_FLAG_SHADE_UNSORTED= 1u << 6, /* shade hits in ray order instead of culling-chunk order (no counting sort), for A/B */
+    LUX_DDGI_FLAG_NO_PIPELINE   = 1u << 7  /* lux_ddgi_update runs the shard as one batch on one stream (no two-stream batch pipelining), for A/B */
 };
 
 typedef struct LuxDDGICreateInfo {

@@ -162,6 +162,7 @@ FLAG_SDF_LOADS = 1 << 3
 FLAG_TRACE_SIMPLE = 1 << 4
 FLAG_NO_PREFILTER = 1 << 5
 FLAG_SHADE_UNSORTED = 1 << 6
+FLAG_NO_PIPELINE = 1 << 7
 BUF_RADIANCE, BUF_DIRECTION_DISTANCE, BUF_IRRADIANCE, BUF_DEPTH, BUF_IRRADIANCE_PREV, BUF_DEPTH_PREV = range(6)
 
 

@@ -10,10 +10,13 @@
 // There is no CPU fallback: creation fails with LUX_ERR_NO_DEVICE when no sm_100-class GPU is usable.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <vector>
 #include <new>
 #include <string>
 
@@ -86,7 +89,15 @@ struct LuxDDGIContext
     // per-frame tables
     DeviceBuffer dirs, wIrr, wDepth, scaleIrr, scaleDepth, nzIrr, nzDepth;
     DeviceBuffer origins, records, meta, chunkCounter; // wavefront trace scratch
-    DeviceBuffer sortTicket, binCounts, binBlockSums, sortedIdx; // sorted shade scratch (hit count lives in chunkCounter[1])
+    DeviceBuffer sortTicket, binCounts, binBlockSums, sortedIdx; // sorted shade scratch (hit counts live in chunkCounter[2b+1])
+    DeviceBuffer dirsHalf;                                       // [R] fp16 directions for the blend weights (pipelined update)
+
+    // Probe batches of lux_ddgi_update: each batch runs march -> shade -> blend on one of two streams, so that the tail of one
+    // batch's kernels (a few long rays, a last partial wave) overlaps the bulk of the next batch's.
+    struct Batch { int probeStart, probeCount; size_t recordStart, binStart, blockStart; };
+    std::vector<Batch> batches;
+    cudaStream_t auxStream = nullptr;
+    cudaEvent_t  evFork = nullptr, evJoin = nullptr, evWeights = nullptr;
 
     // uGlobalSDF / uGlobalMipSDF / sdfData
     bool             hasSdf = false;
@@ -246,14 +257,47 @@ static int initializeProbeGrid(LuxDDGIContext& c)
         const size_t nrec = lux::trace_record_count(c.probeCount, u.raysPerProbe);
         if ((rc = allocZero(c, c.records, nrec * sizeof(float4))) != LUX_OK) return rc;
         if ((rc = allocZero(c, c.meta, nrec * sizeof(uint32_t))) != LUX_OK) return rc;
+        // Batch plan.  Measured on B200 (C4, profiles/README): splitting a shard into probe batches that alternate between two streams
+        // does NOT pay off - each batch's kernels lose more to their own ramp-up / drain than the overlap wins back (8 batches: 9.2 ms
+        // vs 7.9 ms serial; 2 batches of a 1/8 shard: no change) - so the default is one batch.  LUX_DDGI_BATCH_RAYS=<rays per batch>
+        // keeps the batched form available for experiments and for the parity test that pins it.
+        const size_t rays = (size_t)c.probeCount * u.raysPerProbe;
+        int nb = 1;
+        if (const char* e = getenv("LUX_DDGI_BATCH_RAYS"))
+            nb = (int)std::min<size_t>(8, std::max<size_t>(1, rays / std::max<size_t>(1024, (size_t)atoll(e))));
+        if (c.flags & (LUX_DDGI_FLAG_STAGE_TIMERS | LUX_DDGI_FLAG_UNFUSED_BORDER | LUX_DDGI_FLAG_NO_PIPELINE))
+            nb = 1;
+        const int perBatch = ((c.probeCount + nb - 1) / nb + 31) / 32 * 32;
+        c.batches.clear();
+        size_t bins = 0, blocks = 0;
+        for (int p0 = 0; p0 < c.probeCount; p0 += perBatch)
+        {
+            LuxDDGIContext::Batch b{};
+            b.probeStart  = p0;
+            b.probeCount  = std::min(perBatch, c.probeCount - p0);
+            b.recordStart = lux::trace_record_count(p0, u.raysPerProbe);
+            b.binStart    = bins;
+            b.blockStart  = blocks;
+            bins += lux::trace_sort_bins(b.probeCount, u.raysPerProbe);
+            blocks += lux::trace_sort_blocks(b.probeCount, u.raysPerProbe);
+            c.batches.push_back(b);
+        }
+        bins   = std::max(bins, lux::trace_sort_bins(c.probeCount, u.raysPerProbe)); // the staged API shades the shard as one batch
+        blocks = std::max(blocks, lux::trace_sort_blocks(c.probeCount, u.raysPerProbe));
         if (!(c.flags & LUX_DDGI_FLAG_SHADE_UNSORTED) && nrec < (size_t(1) << 32))
         {
             if ((rc = allocZero(c, c.sortTicket, nrec * sizeof(uint2))) != LUX_OK) return rc;
             if ((rc = allocZero(c, c.sortedIdx, nrec * sizeof(uint32_t))) != LUX_OK) return rc;
-            if ((rc = allocZero(c, c.binCounts, lux::trace_sort_bins(c.probeCount, u.raysPerProbe) * sizeof(uint32_t))) != LUX_OK) return rc;
-            if ((rc = allocZero(c, c.binBlockSums, lux::trace_sort_blocks(c.probeCount, u.raysPerProbe) * sizeof(uint32_t))) != LUX_OK) return rc;
+            if ((rc = allocZero(c, c.binCounts, bins * sizeof(uint32_t))) != LUX_OK) return rc;
+            if ((rc = allocZero(c, c.binBlockSums, blocks * sizeof(uint32_t))) != LUX_OK) return rc;
         }
     }
+    else
+    {
+        c.batches.clear();
+        c.batches.push_back(LuxDDGIContext::Batch{0, c.probeCount, 0, 0, 0});
+    }
+    if ((rc = allocZero(c, c.dirsHalf, (size_t)u.raysPerProbe * sizeof(uint2))) != LUX_OK) return rc;
     c.frames      = 0;
     c.pingPong    = 0;
     c.lastWritten = 1;
@@ -298,8 +342,8 @@ static void mark(LuxDDGIContext& c, int i)
 
 namespace trace_rays {
 
-// trace_rays::system, SDF branch (DDGIRenderer.cpp:235-240, 302-328)
-static int system(LuxDDGIContext& c, const LuxTracePushConstants& push)
+// Per-frame setup of the trace: surface-cache prefilter (when the lists changed) and the frame's ray directions.
+static int setup(LuxDDGIContext& c, const LuxTracePushConstants& push)
 {
     if (!c.hasSdf)
         return fail(LUX_ERR_NOT_READY, "trace_rays: no global SDF bound (lux_ddgi_set_global_sdf)");
@@ -325,12 +369,21 @@ static int system(LuxDDGIContext& c, const LuxTracePushConstants& push)
         c.masksDirty = false;
     }
     mark(c, 0);
-    launch_ray_dirs(push.randomOrientation, u.raysPerProbe, (float4*)c.dirs.ptr, c.stream);
+    launch_ray_dirs(push.randomOrientation, u.raysPerProbe, (float4*)c.dirs.ptr, (uint2*)c.dirsHalf.ptr, c.stream);
     c.launches += 1;
     mark(c, 1);
+    return LUX_OK;
+}
 
+// The trace kernels of one probe batch (the whole shard when called through the staged API) on stream `s`.
+static int launchBatch(LuxDDGIContext& c, const LuxDDGIContext::Batch& b, int batchIndex, cudaStream_t s, bool timers)
+{
+    const LuxDDGIUniform& u = c.uniform;
     TraceParams p{};
     fillVolume(c, p);
+    p.probeBegin   = c.probeBegin + b.probeStart;
+    p.probeCount   = b.probeCount;
+    p.origins      = (const float4*)c.origins.ptr + b.probeStart;
     p.sdf          = c.sdfData;
     p.tex          = (const uint16_t*)c.sdf.ptr;
     p.mip          = (const uint16_t*)c.mip.ptr;
@@ -354,26 +407,39 @@ static int system(LuxDDGIContext& c, const LuxTracePushConstants& push)
         p.light         = (const uint2*)c.light.ptr;
         p.depth         = (const float*)c.atlasDepth.ptr;
     }
+    const size_t rayStart = (size_t)b.probeStart * u.raysPerProbe;
     p.skyFace  = c.skyFace;
     p.sky      = (const uint2*)c.sky.ptr;
     p.dirs     = (const float4*)c.dirs.ptr;
-    p.radiance = (uint2*)c.radiance.ptr;
-    p.dirDist  = (uint2*)c.directionDepth.ptr;
+    p.radiance = (uint2*)c.radiance.ptr + rayStart;
+    p.dirDist  = (uint2*)c.directionDepth.ptr + rayStart;
     p.steps    = nullptr;
-    p.records  = (float4*)c.records.ptr;
-    p.meta     = (uint32_t*)c.meta.ptr;
+    p.records  = c.records.ptr ? (float4*)c.records.ptr + b.recordStart : nullptr;
+    p.meta     = c.meta.ptr ? (uint32_t*)c.meta.ptr + b.recordStart : nullptr;
+    unsigned int* counters = (unsigned int*)c.chunkCounter.ptr + 2 * batchIndex; // [0] march chunk counter, [1] hit count
     if (c.sortedIdx.ptr)
     {
         p.invChunkSize = c.hasAtlas ? 1.0f / c.atlasData.chunkSize : 0.0f;
-        p.sortTicket   = (uint2*)c.sortTicket.ptr;
-        p.binCounts    = (uint32_t*)c.binCounts.ptr;
-        p.binBlockSums = (uint32_t*)c.binBlockSums.ptr;
-        p.hitCount     = (uint32_t*)c.chunkCounter.ptr + 1;
-        p.sortedIdx    = (uint32_t*)c.sortedIdx.ptr;
+        p.sortTicket   = (uint2*)c.sortTicket.ptr + b.recordStart;
+        p.binCounts    = (uint32_t*)c.binCounts.ptr + b.binStart;
+        p.binBlockSums = (uint32_t*)c.binBlockSums.ptr + b.blockStart;
+        p.hitCount     = counters + 1;
+        p.sortedIdx    = (uint32_t*)c.sortedIdx.ptr + b.recordStart;
     }
     const int variant = (c.flags & LUX_DDGI_FLAG_TRACE_SIMPLE) ? 0 : (c.sdfTex ? 2 : 1);
-    c.launches += launch_trace(p, variant, (unsigned int*)c.chunkCounter.ptr, c.stream, c.lightPending ? c.evLightReady : nullptr,
-                               (c.flags & LUX_DDGI_FLAG_STAGE_TIMERS) ? c.ev[5] : nullptr);
+    c.launches += launch_trace(p, variant, counters, s, c.lightPending ? c.evLightReady : nullptr,
+                               (timers && (c.flags & LUX_DDGI_FLAG_STAGE_TIMERS)) ? c.ev[5] : nullptr);
+    return LUX_OK;
+}
+
+// trace_rays::system, SDF branch (DDGIRenderer.cpp:235-240, 302-328): the whole shard as one batch on the context's stream
+static int system(LuxDDGIContext& c, const LuxTracePushConstants& push)
+{
+    int rc = setup(c, push);
+    if (rc != LUX_OK)
+        return rc;
+    const LuxDDGIContext::Batch whole{0, c.probeCount, 0, 0, 0};
+    launchBatch(c, whole, 0, c.stream, true);
     c.lightPending = false;
     cudaEventRecord(c.evShadeDone, c.stream);
     mark(c, 2);
@@ -386,21 +452,23 @@ static int system(LuxDDGIContext& c, const LuxTracePushConstants& push)
 
 namespace probe_update {
 
-// probe_update::system (DDGIRenderer.cpp:377-413): writeIdx = 1 - pingPong, firstFrame = (frames == 0)
-static int system(LuxDDGIContext& c)
+// The frame's probe-independent blend weights from a row of fp16 ray directions
+static void weights(LuxDDGIContext& c, const uint2* dirsHalf, cudaStream_t s)
 {
-    if (!c.raysValid)
-        return fail(LUX_ERR_NOT_READY, "probe_update: ray buffers are empty (call lux_ddgi_trace_rays or lux_ddgi_set_ray_buffers)");
     const LuxDDGIUniform& u = c.uniform;
-    const int writeIdx = 1 - c.pingPong;
+    c.launches += launch_blend_weights(dirsHalf, u.raysPerProbe, c.raysPadded, u.sharpness, (float*)c.wIrr.ptr, (float*)c.wDepth.ptr,
+                                       (float*)c.scaleIrr.ptr, (float*)c.scaleDepth.ptr, (uint32_t*)c.nzIrr.ptr, (uint32_t*)c.nzDepth.ptr, s);
+}
 
-    c.launches += launch_blend_weights((const uint2*)c.directionDepth.ptr, u.raysPerProbe, c.raysPadded, u.sharpness, (float*)c.wIrr.ptr,
-                                       (float*)c.wDepth.ptr, (float*)c.scaleIrr.ptr, (float*)c.scaleDepth.ptr, (uint32_t*)c.nzIrr.ptr,
-                                       (uint32_t*)c.nzDepth.ptr, c.stream);
-
+// Blend (+ fused border) of one probe batch on stream `s`; records evIrr / evDepth after the respective kernel when given.
+static void launchBatch(LuxDDGIContext& c, const LuxDDGIContext::Batch& b, cudaStream_t s, cudaEvent_t evIrr, cudaEvent_t evDepth)
+{
+    const LuxDDGIUniform& u = c.uniform;
+    const int    writeIdx = 1 - c.pingPong;
+    const size_t rayStart = (size_t)b.probeStart * u.raysPerProbe;
     BlendParams p{};
-    p.probeBegin   = c.probeBegin;
-    p.probeCount   = c.probeCount;
+    p.probeBegin   = c.probeBegin + b.probeStart;
+    p.probeCount   = b.probeCount;
     p.raysPerProbe = u.raysPerProbe;
     p.raysPadded   = c.raysPadded;
     p.probesPerRow = u.probeCounts[0] * u.probeCounts[1];
@@ -411,8 +479,8 @@ static int system(LuxDDGIContext& c)
     p.maxDistance  = u.maxDistance;
     p.firstFrame   = (c.frames == 0) ? 1 : 0; // DDGIRenderer.cpp:362
     p.fuseBorder   = (c.flags & LUX_DDGI_FLAG_UNFUSED_BORDER) ? 0 : 1;
-    p.radiance     = (const uint2*)c.radiance.ptr;
-    p.dirDist      = (const uint2*)c.directionDepth.ptr;
+    p.radiance     = (const uint2*)c.radiance.ptr + rayStart;
+    p.dirDist      = (const uint2*)c.directionDepth.ptr + rayStart;
     p.wIrr         = (const float*)c.wIrr.ptr;
     p.wDepth       = (const float*)c.wDepth.ptr;
     p.scaleIrr     = (const float*)c.scaleIrr.ptr;
@@ -423,15 +491,27 @@ static int system(LuxDDGIContext& c)
     p.outIrr       = (uint2*)c.irradiance[writeIdx].ptr;
     p.prevDepth    = (const uint32_t*)c.depth[c.pingPong].ptr;
     p.outDepth     = (uint32_t*)c.depth[writeIdx].ptr;
-    cudaStreamWaitEvent(c.stream, c.evCopyDone, 0); // row downloads of earlier frames must have left the atlases
-    launch_blend_irradiance(p, c.stream);
-    cudaEventRecord(c.evIrrDone, c.stream);
-    launch_blend_depth(p, c.stream);
-    cudaEventRecord(c.evDepthDone, c.stream);
+    launch_blend_irradiance(p, s);
+    if (evIrr)
+        cudaEventRecord(evIrr, s);
+    launch_blend_depth(p, s);
+    if (evDepth)
+        cudaEventRecord(evDepth, s);
     c.launches += 2;
+}
+
+// probe_update::system (DDGIRenderer.cpp:377-413): writeIdx = 1 - pingPong, firstFrame = (frames == 0)
+static int system(LuxDDGIContext& c)
+{
+    if (!c.raysValid)
+        return fail(LUX_ERR_NOT_READY, "probe_update: ray buffers are empty (call lux_ddgi_trace_rays or lux_ddgi_set_ray_buffers)");
+    weights(c, (const uint2*)c.directionDepth.ptr, c.stream); // the directions as stored in the ray buffer (row of the first probe)
+    cudaStreamWaitEvent(c.stream, c.evCopyDone, 0); // row downloads of earlier frames must have left the atlases
+    const LuxDDGIContext::Batch whole{0, c.probeCount, 0, 0, 0};
+    launchBatch(c, whole, c.stream, c.evIrrDone, c.evDepthDone);
     mark(c, 3);
     LUX_CUDA(cudaGetLastError());
-    c.lastWritten = writeIdx;
+    c.lastWritten = 1 - c.pingPong;
     return LUX_OK;
 }
 
@@ -593,8 +673,9 @@ int lux_ddgi_create(const LuxDDGIUniform* uniform, const LuxDDGICreateInfo* info
     for (auto& ev : c->ev)
         cudaEventCreate(&ev);
     cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking);
-    for (cudaEvent_t* e : {&c->evLightReady, &c->evShadeDone, &c->evIrrDone, &c->evDepthDone, &c->evCopyDone})
+    for (cudaEvent_t* e : {&c->evLightReady, &c->evShadeDone, &c->evIrrDone, &c->evDepthDone, &c->evCopyDone, &c->evFork, &c->evJoin, &c->evWeights})
         cudaEventCreateWithFlags(e, cudaEventDisableTiming);
+    cudaStreamCreateWithFlags(&c->auxStream, cudaStreamNonBlocking);
     rc = init::initializeProbeGrid(*c);
     if (rc == LUX_OK)
         rc = updateOrigins(*c);
@@ -617,8 +698,10 @@ int lux_ddgi_destroy(LuxDDGIContext* c)
     cudaStreamSynchronize(c->stream);
     if (c->copyStream)
         cudaStreamSynchronize(c->copyStream);
+    if (c->auxStream)
+        cudaStreamSynchronize(c->auxStream);
     DeviceBuffer* all[] = {&c->radiance, &c->directionDepth, &c->irradiance[0], &c->irradiance[1], &c->depth[0], &c->depth[1],
-                           &c->dirs, &c->wIrr, &c->wDepth, &c->scaleIrr, &c->scaleDepth, &c->nzIrr, &c->nzDepth, &c->origins, &c->records, &c->meta, &c->chunkCounter, &c->sortTicket, &c->binCounts, &c->binBlockSums, &c->sortedIdx, &c->sdf, &c->mip, &c->chunks, &c->cull,
+                           &c->dirs, &c->wIrr, &c->wDepth, &c->scaleIrr, &c->scaleDepth, &c->nzIrr, &c->nzDepth, &c->origins, &c->records, &c->meta, &c->chunkCounter, &c->sortTicket, &c->binCounts, &c->binBlockSums, &c->sortedIdx, &c->dirsHalf, &c->sdf, &c->mip, &c->chunks, &c->cull,
                            &c->objects, &c->objectInverse, &c->chunkMasks, &c->tiles, &c->light, &c->atlasDepth, &c->sky};
     for (DeviceBuffer* b : all)
         b->release();
@@ -626,11 +709,13 @@ int lux_ddgi_destroy(LuxDDGIContext* c)
     for (auto& ev : c->ev)
         if (ev)
             cudaEventDestroy(ev);
-    for (cudaEvent_t e : {c->evLightReady, c->evShadeDone, c->evIrrDone, c->evDepthDone, c->evCopyDone})
+    for (cudaEvent_t e : {c->evLightReady, c->evShadeDone, c->evIrrDone, c->evDepthDone, c->evCopyDone, c->evFork, c->evJoin, c->evWeights})
         if (e)
             cudaEventDestroy(e);
     if (c->copyStream)
         cudaStreamDestroy(c->copyStream);
+    if (c->auxStream)
+        cudaStreamDestroy(c->auxStream);
     if (c->ownStream)
         cudaStreamDestroy(c->stream);
     delete c;
@@ -826,6 +911,43 @@ int lux_ddgi_update(LuxDDGIContext* c, const float orientation[16])
     push.infiniteBounces = c->frames != 0 ? 1u : 0u; // DDGIRenderer.cpp:263
     push.numLights       = 0;
     push.intensity       = 1.0f;
+    if (!(c->flags & (LUX_DDGI_FLAG_STAGE_TIMERS | LUX_DDGI_FLAG_UNFUSED_BORDER | LUX_DDGI_FLAG_NO_PIPELINE | LUX_DDGI_FLAG_TRACE_SIMPLE)))
+    { // Shipped form of the update.  The blend weights depend on the frame's ray directions only, so they are computed on the
+      // auxiliary stream while the march runs; probe batches (normally one) alternate between the two streams.
+        int rc = trace_rays::setup(*c, push);
+        if (rc != LUX_OK)
+            return rc;
+        cudaStreamWaitEvent(c->stream, c->evCopyDone, 0); // row downloads of earlier frames must have left the atlases
+        cudaEventRecord(c->evFork, c->stream);
+        cudaStreamWaitEvent(c->auxStream, c->evFork, 0);
+        probe_update::weights(*c, (const uint2*)c->dirsHalf.ptr, c->auxStream);
+        cudaEventRecord(c->evWeights, c->auxStream);
+        const bool single = c->batches.size() == 1; // then the copy engine may start on each output as soon as its kernel is done
+        for (size_t b = 0; b < c->batches.size(); b++)
+        {
+            cudaStream_t s = (b & 1) ? c->auxStream : c->stream;
+            trace_rays::launchBatch(*c, c->batches[b], (int)b, s, false);
+            if (single)
+                cudaEventRecord(c->evShadeDone, s);
+            if (s == c->stream && b == 0)
+                cudaStreamWaitEvent(s, c->evWeights, 0);
+            probe_update::launchBatch(*c, c->batches[b], s, single ? c->evIrrDone : nullptr, single ? c->evDepthDone : nullptr);
+        }
+        cudaEventRecord(c->evJoin, c->auxStream);
+        cudaStreamWaitEvent(c->stream, c->evJoin, 0);
+        c->lightPending = false;
+        if (!single)
+        {
+            cudaEventRecord(c->evShadeDone, c->stream);
+            cudaEventRecord(c->evIrrDone, c->stream);
+            cudaEventRecord(c->evDepthDone, c->stream);
+        }
+        LUX_CUDA(cudaGetLastError());
+        c->raysValid   = true;
+        c->lastWritten = 1 - c->pingPong;
+        c->timed       = false;
+        return end_frame::system(*c);
+    }
     int rc = trace_rays::system(*c, push);
     if (rc != LUX_OK)
         return rc;

@@ -78,7 +78,8 @@ struct BlendParams
 };
 
 // per-frame setup: ray directions and the probe-independent blend weights
-void launch_ray_dirs(const float* rot16Host, int raysPerProbe, float4* dirs, cudaStream_t s); // rotation travels as a kernel argument
+// rotation travels as a kernel argument; dirsHalf (nullable) = the same directions rounded to fp16, as the blend reads them
+void launch_ray_dirs(const float* rot16Host, int raysPerProbe, float4* dirs, uint2* dirsHalf, cudaStream_t s);
 int  launch_blend_weights(const uint2* dirDistRow0, int raysPerProbe, int raysPadded, float sharpness, float* wIrr, float* wDepth,
                           float* scaleIrr, float* scaleDepth, uint32_t* nzIrr, uint32_t* nzDepth, cudaStream_t s);
 void launch_chunk_masks(const uint32_t* chunks, const uint32_t* cull, const LuxObjectBuffer* objects, const float* objectInverse,

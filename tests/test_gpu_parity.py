@@ -391,3 +391,25 @@ def test_infinite_bounce_refresh_closes_the_loop(oracle):
     assert_atlases_match(pipe, orc)
     assert means[0] > float(f16(base)[..., :3].mean()) and means[1] >= means[0]  # each bounce adds energy
     pipe.close()
+
+
+@pytest.mark.parametrize("cfg,batch_rays", [("city128", 32768), ("city64", 4096)])
+def test_pipelined_probe_batches_match_oracle(oracle, monkeypatch, cfg, batch_rays):
+    """lux_ddgi_update splits large shards into probe batches that alternate between two streams (march/shade/blend of one batch
+    overlap the tails of the previous one).  Forced here on small volumes through the LUX_DDGI_BATCH_RAYS test hook: three
+    frames (hysteresis on) must equal the oracle bit for bit, and equal the serialized one-batch form."""
+    sc = scenes.build(cfg)
+    rots = [scenes.frame_rotation(f) for f in range(3)]
+    orc = oracle.OraclePipeline(sc)
+    for r in rots:
+        orc.update(r)
+    monkeypatch.setenv("LUX_DDGI_BATCH_RAYS", str(batch_rays))
+    pipe = run_engine(sc, rots)
+    monkeypatch.delenv("LUX_DDGI_BATCH_RAYS")
+    serial = run_engine(sc, rots, flags=abi.FLAG_NO_PIPELINE)
+    assert_rays_match(pipe, orc)
+    assert_atlases_match(pipe, orc)
+    assert np.array_equal(pipe.irradiance, serial.irradiance) and np.array_equal(pipe.depth, serial.depth)
+    assert np.array_equal(pipe.radiance, serial.radiance)
+    pipe.close()
+    serial.close()
