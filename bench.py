@@ -382,13 +382,24 @@ def run_lux(args):
             return {"bound": "hbm", "kernel": kernel, "achieved": a, "peak": hbm, "unit": "GB/s", "frac": (a / hbm) if a else None,
                     "traffic": traffic.get(kernel), "peak_source": peak_kind, "algorithmic_bytes_per_launch": nbytes, "ms_per_launch": ms}
 
-        dominant = "march_kernel" if march_launch_ms >= shade_launch_ms else "shade_kernel"
+        def tsum(*names):
+            v = [traffic.get(n) for n in names]
+            return None if any(x is None for x in v) else float(sum(v))
+
+        shade_names = ("shade_kernel",) if args.unsorted else ("classify_kernel", "scatter_kernel", "shade_sorted_kernel")
+        traffic = dict(traffic)
+        traffic["shade_stage"] = tsum(*shade_names)
+        traffic["trace_stage"] = tsum("march_kernel", *shade_names)
+        traffic["blend_stage"] = tsum("blend_irradiance_kernel", "blend_depth_kernel")
+        dominant = "march_kernel" if march_launch_ms >= shade_launch_ms else "shade_stage"
         if march_launch_ms == 0.0:  # --trace simple: one kernel
-            dominant = "trace_kernel"
+            dominant = "trace_stage"
         roofs = {"march_kernel": roof("march_kernel", stages_b["march"], march_launch_ms),
-                 "shade_kernel": roof("shade_kernel", stages_b["shade"], shade_launch_ms),
-                 "trace_kernel": roof("trace_kernel", stages_b["trace"], trace_launch_ms),
-                 "blend": roof("blend_irradiance_kernel+blend_depth_kernel", stages_b["blend"], blend_launch_ms)}
+                 "shade_stage": roof("shade_stage", stages_b["shade"], shade_launch_ms),
+                 "trace_stage": roof("trace_stage", stages_b["trace"], trace_launch_ms),
+                 "blend": roof("blend_stage", stages_b["blend"], blend_launch_ms)}
+        roofs["shade_stage"]["kernels"] = "+".join(shade_names) + ("" if args.unsorted else " (+3 scan kernels)")
+        roofs["blend"]["kernels"] = "blend_irradiance_kernel+blend_depth_kernel"
         roofs["blend"]["fp32_tfma_per_s_dense_equivalent"] = probes_rank * R * 704 / (blend_launch_ms * 1e-3) / 1e12
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
