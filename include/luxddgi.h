@@ -128,6 +128,42 @@ typedef struct LuxGlobalSDFData {
 } LuxGlobalSDFData;
 
 /* ---------------------------------------------------------------------------------------------------------
+ * f3. Global SDF build: the step BEFORE the path.  Mesh distance fields are min-merged into the
+ *     cascade volume chunk by chunk (Shaders/SDF/SDFRasterizeModel.glsl:42-63 + SDFCommon.glsl:18-62, host
+ *     Engine/DDGI/GlobalDistanceField.cpp:460-848), then the quarter-resolution min-mip is built and flooded
+ *     (Shaders/SDF/GlobalSDFMipmap.comp:32-68, GlobalDistanceField.cpp:537-573,825-841).
+ * ------------------------------------------------------------------------------------------------------ */
+#define LUX_SDF_RASTERIZE_MODEL_MAX_COUNT 28 /* GlobalDistanceField.cpp:84, SDFRasterizeModel.glsl:8 */
+#define LUX_SDF_RASTERIZE_CHUNK_SIZE      32 /* GlobalDistanceField.cpp:88                            */
+#define LUX_SDF_RASTERIZE_CHUNK_MARGIN     4 /* GlobalDistanceField.cpp:91                            */
+#define LUX_SDF_MESH_MAX_MIPS              3 /* SDFBaker.cpp:158                                      */
+
+/* ObjectRasterizeData, std430, 176 bytes (Shaders/SDF/ObjectRasterizeData.glsl:7-17; host GlobalDistanceField.cpp:101-111) */
+typedef struct LuxObjectRasterizeData {
+    float worldToVolume[16];          /* @0   column-major */
+    float volumeToWorld[16];          /* @64               */
+    float volumeToUVWMul[3];          /* @128              */
+    float mipOffset;                  /* @140              */
+    float volumeToUVWAdd[3];          /* @144              */
+    float decodeMul;                  /* @156              */
+    float volumeLocalBoundsExtent[3]; /* @160              */
+    float decodeAdd;                  /* @172              */
+} LuxObjectRasterizeData;
+
+/* One mesh distance field = component::MeshDistanceField + the entity's world matrix (MeshDistanceField.h:15-26).
+ * Volume: R16F [z][y][x], value (d/maxDistance + 1)/2, mip m has size max(size >> m, 1), box-filtered (SDFBaker.cpp:96-204).
+ * Sampled trilinear inside ONE mip level with REPEAT addressing (Texture3D default wrap, RHI/Definitions.h:152-174). */
+typedef struct LuxMeshSDF {
+    const void* mips[LUX_SDF_MESH_MAX_MIPS];
+    uint32_t    size[3];
+    int32_t     mipCount;
+    float       aabbMin[3], aabbMax[3];
+    float       localToUVWMul[3], localToUVWAdd[3];
+    float       maxDistance;
+    float       worldMatrix[16]; /* column-major */
+} LuxMeshSDF;
+
+/* ---------------------------------------------------------------------------------------------------------
  * a6. Surface-cache records (Shaders/SDF/AtlasCommon.glsl:8-32; host GlobalSurfaceAtlas.cpp:59-73,
  *     SurfaceAtlasTile.h:117-125).
  * ------------------------------------------------------------------------------------------------------ */
@@ -190,7 +226,9 @@ typedef enum LuxBufferId {
     LUX_BUF_IRRADIANCE          = 2, /* RGBA16F [10Z+2][10XY+2], the atlas most recently written          */
     LUX_BUF_DEPTH               = 3, /* RG16F   [18Z+2][18XY+2], the atlas most recently written          */
     LUX_BUF_IRRADIANCE_PREV     = 4, /* the other half of the ping-pong pair                              */
-    LUX_BUF_DEPTH_PREV          = 5
+    LUX_BUF_DEPTH_PREV          = 5,
+    LUX_BUF_GLOBAL_SDF          = 6, /* R16F [res][res][res*cascades], the bound / built global SDF            */
+    LUX_BUF_GLOBAL_SDF_MIP      = 7  /* R16F [res/4][res/4][res/4*cascades]                                    */
 } LuxBufferId;
 
 typedef struct LuxDDGIState {
@@ -233,6 +271,19 @@ LUX_API int lux_ddgi_set_uniform(LuxDDGIContext* ctx, const LuxDDGIUniform* unif
 /* uGlobalSDF / uGlobalMipSDF + UniformBufferObject.sdfData (DDGIRenderer.cpp:304-305,314). fp16 texels. */
 LUX_API int lux_ddgi_set_global_sdf(LuxDDGIContext* ctx, const LuxGlobalSDFData* data,
                             const void* sdfR16F, const void* mipR16F, LuxMemKind kind);
+
+/* f3: builds the global SDF and its mip ON DEVICE from mesh distance fields and binds them like lux_ddgi_set_global_sdf.
+ * `data` gives the cascades (centre, half extent, voxel size = 2*extent/resolution, resolution, count); objects whose
+ * bounding sphere misses a cascade or is smaller than minObjectRadius are skipped (GlobalDistanceField.cpp:692-701).
+ * One-shot build (the reference's first frame: every chunk rasterized; its static-chunk caching across frames is not modelled).
+ * Mesh volumes are HOST pointers (they come from .sdf files). */
+LUX_API int lux_ddgi_build_global_sdf(LuxDDGIContext* ctx, const LuxGlobalSDFData* data, const LuxMeshSDF* meshes, int32_t meshCount,
+                                      float minObjectRadius);
+/* Rebuilds only the mip of the bound SDF (GlobalSDFMipmap.comp: one 4x min-downsample + 4 flood passes per cascade). */
+LUX_API int lux_ddgi_build_sdf_mip(LuxDDGIContext* ctx);
+/* Reader of the reference's baked .sdf files (cereal binary, SDFBaker.cpp:158-204 / :207-240).  Call with out == NULL to get the sizes:
+ * size[3], mipCount and the total number of fp16 texels over all mips; then with a buffer of that many uint16_t (mips back to back). */
+LUX_API int lux_ddgi_sdf_file_read(const char* path, uint32_t size[3], int32_t* mipCount, uint64_t* texels, uint16_t* out);
 
 /* SDFAtlasChunkBuffer, SDFCullObjectBuffer, SDFObjectBuffer, SDFAtlasTileBuffer, uSurfaceAtlasTex (RGBA16F,
  * linear/repeat), uSurfaceAtlasDepth (D32F, clamp), UniformBufferObject.data (DDGIRenderer.cpp:306-313).

@@ -67,6 +67,37 @@ class GlobalSDFData(C.Structure):
     ]
 
 
+class ObjectRasterizeData(C.Structure):  # ObjectRasterizeData.glsl:7-17, std430, 176 bytes
+    _fields_ = [
+        ("worldToVolume", C.c_float * 16),
+        ("volumeToWorld", C.c_float * 16),
+        ("volumeToUVWMul", C.c_float * 3),
+        ("mipOffset", C.c_float),
+        ("volumeToUVWAdd", C.c_float * 3),
+        ("decodeMul", C.c_float),
+        ("volumeLocalBoundsExtent", C.c_float * 3),
+        ("decodeAdd", C.c_float),
+    ]
+
+
+class MeshSDF(C.Structure):  # LuxMeshSDF: component::MeshDistanceField + world matrix
+    _fields_ = [
+        ("mips", C.c_void_p * 3),
+        ("size", C.c_uint32 * 3),
+        ("mipCount", C.c_int32),
+        ("aabbMin", C.c_float * 3),
+        ("aabbMax", C.c_float * 3),
+        ("localToUVWMul", C.c_float * 3),
+        ("localToUVWAdd", C.c_float * 3),
+        ("maxDistance", C.c_float),
+        ("worldMatrix", C.c_float * 16),
+    ]
+
+
+SDF_RASTERIZE_MODEL_MAX_COUNT = 28
+SDF_RASTERIZE_CHUNK_SIZE = 32
+
+
 class GlobalSurfaceAtlasData(C.Structure):
     _fields_ = [
         ("cameraPos", C.c_float * 3),
@@ -163,7 +194,7 @@ FLAG_TRACE_SIMPLE = 1 << 4
 FLAG_NO_PREFILTER = 1 << 5
 FLAG_SHADE_UNSORTED = 1 << 6
 FLAG_NO_PIPELINE = 1 << 7
-BUF_RADIANCE, BUF_DIRECTION_DISTANCE, BUF_IRRADIANCE, BUF_DEPTH, BUF_IRRADIANCE_PREV, BUF_DEPTH_PREV = range(6)
+BUF_RADIANCE, BUF_DIRECTION_DISTANCE, BUF_IRRADIANCE, BUF_DEPTH, BUF_IRRADIANCE_PREV, BUF_DEPTH_PREV, BUF_GLOBAL_SDF, BUF_GLOBAL_SDF_MIP = range(8)
 
 
 def make_uniform(start, step, counts, rays, max_distance=None, sharpness=50.0, hysteresis=0.98, normal_bias=1.0, gamma=5.0):

@@ -17,7 +17,7 @@ NVCC_FLAGS = [
     "-O3", "-lineinfo", "-std=c++17",
     "-fmad=false",            # numerics contract: FMA only where __fmaf_rn is written
     "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
-    "-Xcompiler", "-fPIC,-O2,-Wall,-fvisibility=hidden",
+    "-Xcompiler", "-fPIC,-O2,-Wall,-fvisibility=hidden,-ffp-contract=off",  # host float code (SDF build chunk lists) must not contract either
     "-Xptxas", "-v",
 ]
 

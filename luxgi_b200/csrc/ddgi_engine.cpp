@@ -739,6 +739,29 @@ int lux_ddgi_set_uniform(LuxDDGIContext* c, const LuxDDGIUniform* u)
     return updateOrigins(*c);
 }
 
+// (Re)creates the layered SDF textures over c->sdf / c->mip and publishes `data` as the bound GlobalSDFData.
+static int bindSdfTextures(LuxDDGIContext* c, const LuxGlobalSDFData* data)
+{
+    const int res = (int)data->resolution, mres = res / 4;
+    releaseSdfTextures(*c);
+    // Default SDF path = layered-texture gathers (chosen by ncu, profiles/r1_*): falls back to explicit loads when asked to
+    // (LUX_DDGI_FLAG_SDF_LOADS), for the simple kernel, or when the volume has more z-slices than a layered array allows.
+    const bool wantTex = !(c->flags & (LUX_DDGI_FLAG_SDF_LOADS | LUX_DDGI_FLAG_TRACE_SIMPLE)) && res <= 2048;
+    if ((c->flags & LUX_DDGI_FLAG_SDF_TEXTURE) && res > 2048)
+        return fail(LUX_ERR_UNSUPPORTED, "layered SDF textures support at most 2048 z-slices");
+    if (wantTex)
+    {
+        int rc;
+        const int w = res * (int)data->cascadesCount, mw = mres * (int)data->cascadesCount;
+        if ((rc = makeLayeredTexture(*c, c->sdf.ptr, w, res, res, &c->sdfArray, &c->sdfTex)) != LUX_OK) return rc;
+        if ((rc = makeLayeredTexture(*c, c->mip.ptr, mw, mres, mres, &c->mipArray, &c->mipTex)) != LUX_OK) return rc;
+    }
+    c->sdfData    = *data;
+    c->hasSdf     = true;
+    c->masksDirty = true;
+    return LUX_OK;
+}
+
 int lux_ddgi_set_global_sdf(LuxDDGIContext* c, const LuxGlobalSDFData* data, const void* sdf, const void* mip, LuxMemKind kind)
 {
     CHECK_CTX(c);
@@ -755,23 +778,343 @@ int lux_ddgi_set_global_sdf(LuxDDGIContext* c, const LuxGlobalSDFData* data, con
     int rc;
     if ((rc = upload(*c, c->sdf, sdf, n * 2, kind)) != LUX_OK) return rc;
     if ((rc = upload(*c, c->mip, mip, nm * 2, kind)) != LUX_OK) return rc;
-    releaseSdfTextures(*c);
-    // Default SDF path = layered-texture gathers (chosen by ncu, profiles/r1_*): falls back to explicit loads when asked to
-    // (LUX_DDGI_FLAG_SDF_LOADS), for the simple kernel, or when the volume has more z-slices than a layered array allows.
-    const bool wantTex = !(c->flags & (LUX_DDGI_FLAG_SDF_LOADS | LUX_DDGI_FLAG_TRACE_SIMPLE)) && res <= 2048;
-    if ((c->flags & LUX_DDGI_FLAG_SDF_TEXTURE) && res > 2048)
-        return fail(LUX_ERR_UNSUPPORTED, "layered SDF textures support at most 2048 z-slices");
-    if (wantTex)
-    {
-        const int w = res * (int)data->cascadesCount, mw = (int)mres * (int)data->cascadesCount;
-        if ((rc = makeLayeredTexture(*c, c->sdf.ptr, w, res, res, &c->sdfArray, &c->sdfTex)) != LUX_OK) return rc;
-        if ((rc = makeLayeredTexture(*c, c->mip.ptr, mw, (int)mres, (int)mres, &c->mipArray, &c->mipTex)) != LUX_OK) return rc;
-    }
+    rc = bindSdfTextures(c, data);
+    if (rc != LUX_OK)
+        return rc;
     if (kind == LUX_MEM_HOST)
         LUX_CUDA(cudaStreamSynchronize(c->stream)); // the caller may free its buffers on return
-    c->sdfData    = *data;
-    c->hasSdf     = true;
-    c->masksDirty = true;
+    return LUX_OK;
+}
+
+// ---- global SDF build ---------------------------------------------------------------------------
+// Host sequencing of merge_sdf::system's first frame (GlobalDistanceField.cpp:575-848) with chunkCalculate (:460-533),
+// getChunkId (:193-210) and fillFlood (:537-573).  Reference behaviours kept on purpose are listed in DESIGN.md §10.
+namespace {
+
+struct ChunkEntry
+{
+    int coord[3];
+    int count;
+    uint32_t models[LUX_SDF_RASTERIZE_MODEL_MAX_COUNT];
+};
+
+inline float clampf(float x, float lo, float hi) { float t = (x < lo) ? lo : x; return (hi < t) ? hi : t; } // glm::clamp = min(max(x, lo), hi)
+
+// mip of every cascade of the bound (c->sdf) volume into c->mip: one 4x min-downsample + 4 flood passes through a temporary
+int buildMipOnDevice(LuxDDGIContext* c, const LuxGlobalSDFData& data)
+{
+    const int res = (int)data.resolution, casc = (int)data.cascadesCount, mres = res / 4;
+    uint16_t* tmp = nullptr;
+    LUX_CUDA(cudaMalloc(&tmp, (size_t)mres * mres * mres * 2));
+    lux::launch_sdf_fill(tmp, (size_t)mres * mres * mres, 0x3c00, c->stream); // cleared to 1.0 (:633-635)
+    c->launches += 1;
+    for (int k = 0; k < casc; k++)
+    {
+        const float cascadeMaxDistance = data.cascadePosDistance[k][3] * 2.0f;
+        lux::launch_sdf_mip_pass((const uint16_t*)c->sdf.ptr, res * casc, res, (uint16_t*)c->mip.ptr, mres * casc, mres, mres, res, 4, k * res, k * mres,
+                                 cascadeMaxDistance, c->stream);
+        for (int i = 1; i < 5; i++)
+        {
+            if (i & 1) // Mip -> Tmp
+                lux::launch_sdf_mip_pass((const uint16_t*)c->mip.ptr, mres * casc, mres, tmp, mres, mres, mres, mres, 1, k * mres, 0, cascadeMaxDistance, c->stream);
+            else // Tmp -> Mip
+                lux::launch_sdf_mip_pass(tmp, mres, mres, (uint16_t*)c->mip.ptr, mres * casc, mres, mres, mres, 1, 0, k * mres, cascadeMaxDistance, c->stream);
+        }
+        c->launches += 5;
+    }
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    cudaFree(tmp);
+    LUX_CUDA(e);
+    LUX_CUDA(cudaGetLastError());
+    return LUX_OK;
+}
+
+int validateSdfData(const LuxGlobalSDFData* data)
+{
+    if (!data)
+        return fail(LUX_ERR_INVALID_ARG, "null GlobalSDFData");
+    if (data->cascadesCount < 1 || data->cascadesCount > LUX_MAX_CASCADES)
+        return fail(LUX_ERR_INVALID_ARG, "cascadesCount %u out of range", data->cascadesCount);
+    const int res = (int)data->resolution;
+    if (res < 4 || (float)res != data->resolution || res % 4 != 0)
+        return fail(LUX_ERR_INVALID_ARG, "resolution %g must be a positive multiple of 4", data->resolution);
+    return LUX_OK;
+}
+
+} // namespace
+
+int lux_ddgi_build_sdf_mip(LuxDDGIContext* c)
+{
+    CHECK_CTX(c);
+    if (!c->hasSdf)
+        return fail(LUX_ERR_NOT_READY, "no global SDF bound");
+    if (c->mip.borrowed)
+        return fail(LUX_ERR_UNSUPPORTED, "the bound mip is caller-owned device memory; upload it from the host or build the SDF with lux_ddgi_build_global_sdf");
+    int rc = buildMipOnDevice(c, c->sdfData);
+    if (rc != LUX_OK)
+        return rc;
+    const LuxGlobalSDFData data = c->sdfData;
+    return bindSdfTextures(c, &data);
+}
+
+int lux_ddgi_build_global_sdf(LuxDDGIContext* c, const LuxGlobalSDFData* data, const LuxMeshSDF* meshes, int32_t meshCount, float minObjectRadius)
+{
+    CHECK_CTX(c);
+    int rc = validateSdfData(data);
+    if (rc != LUX_OK)
+        return rc;
+    if (meshCount < 0 || (meshCount > 0 && !meshes))
+        return fail(LUX_ERR_INVALID_ARG, "bad mesh list");
+    const int res = (int)data->resolution, casc = (int)data->cascadesCount, texWidth = res * casc, mres = res / 4;
+    const int rasterizeChunks = (res + LUX_SDF_RASTERIZE_CHUNK_SIZE - 1) / LUX_SDF_RASTERIZE_CHUNK_SIZE;
+    for (int m = 0; m < meshCount; m++)
+    {
+        if (meshes[m].mipCount < 1 || meshes[m].mipCount > LUX_SDF_MESH_MAX_MIPS || meshes[m].mipCount < std::min(casc, 3))
+            return fail(LUX_ERR_INVALID_ARG, "mesh %d has %d mips; cascade level min(cascade, 2) must exist", m, meshes[m].mipCount);
+        for (int l = 0; l < meshes[m].mipCount; l++)
+            if (!meshes[m].mips[l])
+                return fail(LUX_ERR_INVALID_ARG, "mesh %d mip %d is null", m, l);
+    }
+    // volumes: caller-owned buffers are replaced by engine-owned ones, cleared to 1.0 (:633-635)
+    const size_t n = (size_t)res * res * texWidth, nm = (size_t)mres * mres * mres * casc;
+    for (DeviceBuffer* b : {&c->sdf, &c->mip})
+    {
+        const size_t bytes = (b == &c->sdf ? n : nm) * 2;
+        if (b->borrowed || b->bytes != bytes)
+        {
+            b->release();
+            LUX_CUDA(cudaMalloc(&b->ptr, bytes));
+            b->bytes = bytes;
+        }
+    }
+    lux::launch_sdf_fill((uint16_t*)c->sdf.ptr, n, 0x3c00, c->stream);
+    lux::launch_sdf_fill((uint16_t*)c->mip.ptr, nm, 0x3c00, c->stream);
+    c->launches += 2;
+
+    // mesh volumes (all mips, back to back) and records to the device
+    std::vector<lux::SdfMeshRecord> records((size_t)meshCount);
+    std::vector<size_t>             levelOffset((size_t)meshCount * LUX_SDF_MESH_MAX_MIPS, 0);
+    size_t texels = 0;
+    for (int m = 0; m < meshCount; m++)
+    {
+        const LuxMeshSDF& ms = meshes[m];
+        lux::SdfMeshRecord& r = records[(size_t)m];
+        std::memcpy(r.aabbMin, ms.aabbMin, 12); std::memcpy(r.aabbMax, ms.aabbMax, 12);
+        std::memcpy(r.localToUVWMul, ms.localToUVWMul, 12); std::memcpy(r.localToUVWAdd, ms.localToUVWAdd, 12);
+        r.maxDistance = ms.maxDistance;
+        std::memcpy(r.worldMatrix, ms.worldMatrix, 64);
+        for (int l = 0; l < ms.mipCount; l++)
+        {
+            levelOffset[(size_t)m * LUX_SDF_MESH_MAX_MIPS + l] = texels;
+            texels += (size_t)std::max(ms.size[0] >> l, 1u) * std::max(ms.size[1] >> l, 1u) * std::max(ms.size[2] >> l, 1u);
+        }
+    }
+    uint16_t* dVolumes = nullptr;
+    lux::SdfMeshRecord* dRecords = nullptr;
+    LuxObjectRasterizeData* dObjects = nullptr;
+    lux::SdfMeshLevel* dLevels = nullptr;
+    lux::SdfChunkDispatch* dDispatch = nullptr;
+    auto cleanup = [&]() { cudaFree(dVolumes); cudaFree(dRecords); cudaFree(dObjects); cudaFree(dLevels); cudaFree(dDispatch); };
+#define LUX_CUDA_CLEAN(call)                                                              \
+    do                                                                                    \
+    {                                                                                     \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess)                                                            \
+        {                                                                                 \
+            cleanup();                                                                    \
+            return fail(LUX_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_));           \
+        }                                                                                 \
+    } while (0)
+    LUX_CUDA_CLEAN(cudaMalloc(&dVolumes, std::max<size_t>(texels, 1) * 2));
+    LUX_CUDA_CLEAN(cudaMalloc(&dRecords, std::max<size_t>(records.size(), 1) * sizeof(lux::SdfMeshRecord)));
+    LUX_CUDA_CLEAN(cudaMalloc(&dObjects, std::max<size_t>(records.size(), 1) * sizeof(LuxObjectRasterizeData)));
+    LUX_CUDA_CLEAN(cudaMalloc(&dLevels, std::max<size_t>(records.size(), 1) * sizeof(lux::SdfMeshLevel)));
+    for (int m = 0; m < meshCount; m++)
+        for (int l = 0; l < meshes[m].mipCount; l++)
+        {
+            const size_t off = levelOffset[(size_t)m * LUX_SDF_MESH_MAX_MIPS + l];
+            const size_t cnt = (size_t)std::max(meshes[m].size[0] >> l, 1u) * std::max(meshes[m].size[1] >> l, 1u) * std::max(meshes[m].size[2] >> l, 1u);
+            LUX_CUDA_CLEAN(cudaMemcpyAsync(dVolumes + off, meshes[m].mips[l], cnt * 2, cudaMemcpyHostToDevice, c->stream));
+        }
+    if (meshCount > 0)
+        LUX_CUDA_CLEAN(cudaMemcpyAsync(dRecords, records.data(), records.size() * sizeof(lux::SdfMeshRecord), cudaMemcpyHostToDevice, c->stream));
+
+    for (int k = 0; k < casc; k++)
+    {
+        const float D = data->cascadePosDistance[k][3], cascadeMaxDistance = D * 2.0f, voxel = data->cascadeVoxelSize[k];
+        const float center[3] = {data->cascadePosDistance[k][0], data->cascadePosDistance[k][1], data->cascadePosDistance[k][2]};
+        const float bmin[3] = {center[0] - D, center[1] - D, center[2] - D}, bmax[3] = {center[0] + D, center[1] + D, center[2] + D};
+        const int   mipLevel = std::min(k, 2);
+        std::vector<ChunkEntry>          chunks;
+        std::vector<int>                 included; // mesh index per object index
+        for (int m = 0; m < meshCount; m++)
+        {
+            const LuxMeshSDF& ms = meshes[m];
+            const float* t = ms.worldMatrix;
+            // objectBounds = sdf.aabb.transform(world) (BoundingBox.cpp:10-22; abs() of the product in the third term is the reference's)
+            float cen[3], oldEdge[3], newCenter[3], newEdge[3], omn[3], omx[3];
+            for (int i = 0; i < 3; i++)
+            {
+                cen[i]     = (ms.aabbMax[i] + ms.aabbMin[i]) * 0.5f;
+                oldEdge[i] = (ms.aabbMax[i] - ms.aabbMin[i]) * 0.5f;
+            }
+            for (int r = 0; r < 3; r++)
+            {
+                newCenter[r] = ((t[0 + r] * cen[0] + t[4 + r] * cen[1]) + t[8 + r] * cen[2]) + t[12 + r] * 1.0f;
+                newEdge[r]   = std::fabs(t[0 + r]) * oldEdge[0] + std::fabs(t[4 + r]) * oldEdge[1] + std::fabs(t[8 + r] * oldEdge[2]);
+                omn[r]       = newCenter[r] - newEdge[r];
+                omx[r]       = newCenter[r] + newEdge[r];
+            }
+            // BoundingSphere(objectBounds) against the cascade box, minimum radius (:692-701)
+            float sc[3], dv[3], diag[3];
+            for (int i = 0; i < 3; i++)
+            {
+                sc[i]   = (omx[i] + omn[i]) * 0.5f;
+                dv[i]   = sc[i] - clampf(sc[i], bmin[i], bmax[i]);
+                diag[i] = omx[i] - omn[i];
+            }
+            const float radius = std::sqrt((diag[0] * diag[0] + diag[1] * diag[1]) + diag[2] * diag[2]) / 2.0f;
+            const float dist2  = (dv[0] * dv[0] + dv[1] * dv[1]) + dv[2] * dv[2];
+            if (!(dist2 <= radius * radius && radius >= minObjectRadius))
+                continue;
+            // getChunkId (:193-210): margin, bias, truncating division; its clamps are no-ops
+            const float objectMargin = voxel * (float)LUX_SDF_RASTERIZE_CHUNK_MARGIN, chunkSize = voxel * (float)LUX_SDF_RASTERIZE_CHUNK_SIZE;
+            int cmin[3], cmax[3];
+            for (int i = 0; i < 3; i++)
+            {
+                const float biasMin = bmin[i] + 0.1f;
+                cmin[i] = (int)(((omn[i] - objectMargin) - biasMin) / chunkSize);
+                cmax[i] = (int)(((omx[i] + objectMargin) - biasMin) / chunkSize);
+            }
+            const uint32_t objectIndex = (uint32_t)included.size();
+            included.push_back(m);
+            for (int z = cmin[2]; z <= cmax[2]; z++)
+                for (int y = cmin[1]; y <= cmax[1]; y++)
+                    for (int x = cmin[0]; x <= cmax[0]; x++)
+                    {
+                        ChunkEntry* ch = nullptr;
+                        for (ChunkEntry& e : chunks)
+                            if (e.coord[0] == x && e.coord[1] == y && e.coord[2] == z)
+                            {
+                                ch = &e;
+                                break;
+                            }
+                        if (!ch)
+                        {
+                            chunks.push_back(ChunkEntry{{x, y, z}, 0, {}});
+                            ch = &chunks.back();
+                        }
+                        if (ch->count == LUX_SDF_RASTERIZE_MODEL_MAX_COUNT)
+                            ch->count = 0; // :515-519 copies the empty next-layer entry over the full one: the list restarts
+                        ch->models[ch->count++] = objectIndex;
+                    }
+        }
+        // per-object device data of this cascade: records of the included meshes in object order, their mip level
+        std::vector<lux::SdfMeshRecord> objRecords(included.size());
+        std::vector<lux::SdfMeshLevel>  levels(included.size());
+        for (size_t i = 0; i < included.size(); i++)
+        {
+            const int m = included[i];
+            objRecords[i] = records[(size_t)m];
+            levels[i]     = lux::SdfMeshLevel{dVolumes + levelOffset[(size_t)m * LUX_SDF_MESH_MAX_MIPS + mipLevel], (int)std::max(meshes[m].size[0] >> mipLevel, 1u),
+                                              (int)std::max(meshes[m].size[1] >> mipLevel, 1u), (int)std::max(meshes[m].size[2] >> mipLevel, 1u)};
+        }
+        std::vector<lux::SdfChunkDispatch> dispatches;
+        for (const ChunkEntry& e : chunks)
+        {
+            if (e.coord[0] < 0 || e.coord[1] < 0 || e.coord[2] < 0 || e.coord[0] >= rasterizeChunks || e.coord[1] >= rasterizeChunks || e.coord[2] >= rasterizeChunks)
+                continue; // wholly outside the volume: every store would be out of bounds
+            lux::SdfChunkDispatch d{};
+            for (int i = 0; i < 3; i++)
+                d.coord[i] = e.coord[i] * LUX_SDF_RASTERIZE_CHUNK_SIZE;
+            d.count = e.count;
+            std::memcpy(d.models, e.models, sizeof(d.models));
+            d.read = 0; // layer 0 = SDFRasterizeModelNoRead; additive layers never receive models (see above)
+            dispatches.push_back(d);
+        }
+        if (!included.empty())
+        {
+            LUX_CUDA_CLEAN(cudaMemcpyAsync(dRecords, objRecords.data(), objRecords.size() * sizeof(lux::SdfMeshRecord), cudaMemcpyHostToDevice, c->stream));
+            LUX_CUDA_CLEAN(cudaMemcpyAsync(dLevels, levels.data(), levels.size() * sizeof(lux::SdfMeshLevel), cudaMemcpyHostToDevice, c->stream));
+            lux::launch_sdf_object_data(dRecords, (int)included.size(), k, dObjects, c->stream);
+            c->launches += 1;
+        }
+        if (!dispatches.empty())
+        {
+            cudaFree(dDispatch);
+            dDispatch = nullptr;
+            LUX_CUDA_CLEAN(cudaMalloc(&dDispatch, dispatches.size() * sizeof(lux::SdfChunkDispatch)));
+            LUX_CUDA_CLEAN(cudaMemcpyAsync(dDispatch, dispatches.data(), dispatches.size() * sizeof(lux::SdfChunkDispatch), cudaMemcpyHostToDevice, c->stream));
+            lux::SdfRasterizeParams rp{};
+            for (int i = 0; i < 3; i++)
+            {
+                rp.mul[i] = (bmax[i] - bmin[i]) / (float)res;
+                rp.add[i] = bmin[i] + voxel * 0.5f;
+            }
+            rp.maxDistance  = cascadeMaxDistance;
+            rp.res          = res;
+            rp.cascadeIndex = k;
+            rp.texWidth     = texWidth;
+            rp.objects      = dObjects;
+            rp.levels       = dLevels;
+            rp.dispatches   = dDispatch;
+            rp.sdf          = (uint16_t*)c->sdf.ptr;
+            lux::launch_sdf_rasterize(rp, (int)dispatches.size(), c->stream);
+            c->launches += 1;
+        }
+        LUX_CUDA_CLEAN(cudaStreamSynchronize(c->stream)); // host vectors of this cascade go out of scope
+    }
+#undef LUX_CUDA_CLEAN
+    cleanup();
+    LUX_CUDA(cudaGetLastError());
+    rc = buildMipOnDevice(c, *data);
+    if (rc != LUX_OK)
+        return rc;
+    return bindSdfTextures(c, data);
+}
+
+// .sdf reader (cereal BinaryOutputArchive of `uvec3 size, int32 mipCount, vector<uint8_t>` + one vector per further mip, SDFBaker.cpp:158-204)
+int lux_ddgi_sdf_file_read(const char* path, uint32_t size[3], int32_t* mipCount, uint64_t* texels, uint16_t* out)
+{
+    if (!path || !size || !mipCount || !texels)
+        return fail(LUX_ERR_INVALID_ARG, "null argument");
+    FILE* f = std::fopen(path, "rb");
+    if (!f)
+        return fail(LUX_ERR_INVALID_ARG, "cannot open %s", path);
+    auto bad = [&](const char* why) {
+        std::fclose(f);
+        return fail(LUX_ERR_INVALID_ARG, "%s: %s", path, why);
+    };
+    std::fseek(f, 0, SEEK_END);
+    const long fileBytes = std::ftell(f);
+    std::fseek(f, 0, SEEK_SET);
+    uint32_t hdr[4];
+    if (std::fread(hdr, 4, 4, f) != 4)
+        return bad("truncated header");
+    size[0] = hdr[0]; size[1] = hdr[1]; size[2] = hdr[2];
+    *mipCount = (int32_t)hdr[3];
+    if (*mipCount < 1 || *mipCount > LUX_SDF_MESH_MAX_MIPS || !size[0] || !size[1] || !size[2])
+        return bad("implausible size / mip count");
+    uint64_t total = 0;
+    for (int l = 0; l < *mipCount; l++)
+    {
+        uint64_t n = 0;
+        if (std::fread(&n, 8, 1, f) != 1)
+            return bad("truncated mip header");
+        const uint64_t want = (uint64_t)std::max(size[0] >> l, 1u) * std::max(size[1] >> l, 1u) * std::max(size[2] >> l, 1u);
+        if (n != want * 2)
+            return bad("mip byte count does not match the volume size");
+        if (out)
+        {
+            if (std::fread(out + total, 2, want, f) != want)
+                return bad("truncated mip data");
+        }
+        else if (std::fseek(f, (long)n, SEEK_CUR) != 0 || std::ftell(f) > fileBytes)
+            return bad("truncated mip data");
+        total += want;
+    }
+    *texels = total;
+    std::fclose(f);
     return LUX_OK;
 }
 
@@ -983,6 +1326,8 @@ static int bufferOf(LuxDDGIContext* c, LuxBufferId id, DeviceBuffer** out)
     case LUX_BUF_DEPTH: *out = &c->depth[c->lastWritten]; break;
     case LUX_BUF_IRRADIANCE_PREV: *out = &c->irradiance[1 - c->lastWritten]; break;
     case LUX_BUF_DEPTH_PREV: *out = &c->depth[1 - c->lastWritten]; break;
+    case LUX_BUF_GLOBAL_SDF: *out = &c->sdf; break;
+    case LUX_BUF_GLOBAL_SDF_MIP: *out = &c->mip; break;
     default: return fail(LUX_ERR_INVALID_ARG, "unknown buffer id %d", (int)id);
     }
     return LUX_OK;

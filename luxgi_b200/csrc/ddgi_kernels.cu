@@ -163,13 +163,9 @@ __global__ void blend_scales_kernel(const float* __restrict__ wIrr, const float*
 }
 
 // inverse(object.transform) (AtlasCommon.glsl:133), hoisted to upload time.  Cofactor expansion fixed by the contract.
-__global__ void object_inverse_kernel(const LuxObjectBuffer* __restrict__ objects, int count, float* __restrict__ inv)
+// inverse(mat4) of the numerics contract: cofactor expansion over 2x2 sub-determinants (DESIGN.md §4 rule 4)
+__device__ __forceinline__ void inverse4_dev(const float* __restrict__ m, float* __restrict__ o)
 {
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= count)
-        return;
-    const float* m = objects[k].transform;
-    float*       o = inv + (size_t)k * 16;
 #define A(r, c) m[(c)*4 + (r)]
 #define B(r, c) o[(c)*4 + (r)]
     float s0 = A(0, 0) * A(1, 1) - A(1, 0) * A(0, 1);
@@ -204,6 +200,14 @@ __global__ void object_inverse_kernel(const LuxObjectBuffer* __restrict__ object
     B(3, 3) = ((A(2, 0) * s3 - A(2, 1) * s1) + A(2, 2) * s0) * id;
 #undef A
 #undef B
+}
+
+__global__ void object_inverse_kernel(const LuxObjectBuffer* __restrict__ objects, int count, float* __restrict__ inv)
+{
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count)
+        return;
+    inverse4_dev(objects[k].transform, inv + (size_t)k * 16);
 }
 
 // Prefilter for the surface-cache object loop (AtlasCommon.glsl:125-139), built once per surface-cache upload.
@@ -2157,6 +2161,188 @@ __global__ void indirect_light_kernel(const __grid_constant__ LuxDDGIUniform ddg
     }
     uint32_t h0 = f2h_bits(outv[0]), h1 = f2h_bits(outv[1]), h2 = f2h_bits(outv[2]);
     light[idx] = make_uint2(h0 | (h1 << 16), h2 | (b.y & 0xffff0000u));
+}
+
+// =====================================================================================================================
+// Global SDF build: mesh distance fields -> cascade volume -> min-mip.
+//   sdf_object_data_kernel   chunkCalculate's ObjectRasterizeData (GlobalDistanceField.cpp:484-508), one thread per mesh
+//   sdf_rasterize_kernel     SDFRasterizeModel.glsl:42-63 + SDFCommon.glsl:18-62; one block = one 8x8x8 group of a chunk dispatch,
+//                            all chunk dispatches of a pipeline pass in ONE launch (chunks are independent)
+//   sdf_mip_kernel           GlobalSDFMipmap.comp:32-68
+// Mesh volumes are sampled in software (8 fp16 loads, fp32 nested lerps, REPEAT addressing at one integer mip level): the
+// texture unit's 8-bit filter weights would break parity, as for the global SDF.
+// =====================================================================================================================
+__global__ void sdf_object_data_kernel(const SdfMeshRecord* __restrict__ meshes, int count, int cascadeLevel, LuxObjectRasterizeData* __restrict__ out)
+{
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count)
+        return;
+    const SdfMeshRecord& ms = meshes[k];
+    LuxObjectRasterizeData o;
+    f3 mn = {ms.aabbMin[0], ms.aabbMin[1], ms.aabbMin[2]}, mx = {ms.aabbMax[0], ms.aabbMax[1], ms.aabbMax[2]};
+    f3 volumeCenter = (mx + mn) * 0.5f;
+    float worldToLocal[16];
+    inverse4_dev(ms.worldMatrix, worldToLocal);
+    const float tr[16] = {1.0f, 0.0f, 0.0f, 0.0f, 0.0f, 1.0f, 0.0f, 0.0f, 0.0f, 0.0f, 1.0f, 0.0f, -volumeCenter.x, -volumeCenter.y, -volumeCenter.z, 1.0f};
+    for (int c = 0; c < 4; c++)
+        for (int r = 0; r < 4; r++)
+            o.worldToVolume[c * 4 + r] = ((worldToLocal[0 * 4 + r] * tr[c * 4 + 0] + worldToLocal[1 * 4 + r] * tr[c * 4 + 1]) + worldToLocal[2 * 4 + r] * tr[c * 4 + 2]) +
+                                         worldToLocal[3 * 4 + r] * tr[c * 4 + 3];
+    inverse4_dev(o.worldToVolume, o.volumeToWorld);
+    f3 size = mx - mn;
+    o.volumeLocalBoundsExtent[0] = __fdiv_rn(size.x, 2.0f);
+    o.volumeLocalBoundsExtent[1] = __fdiv_rn(size.y, 2.0f);
+    o.volumeLocalBoundsExtent[2] = __fdiv_rn(size.z, 2.0f);
+    const float vc[3] = {volumeCenter.x, volumeCenter.y, volumeCenter.z};
+    for (int i = 0; i < 3; i++)
+    {
+        o.volumeToUVWMul[i] = ms.localToUVWMul[i];
+        o.volumeToUVWAdd[i] = ms.localToUVWAdd[i] + vc[i] * ms.localToUVWMul[i];
+    }
+    o.mipOffset = (float)min(cascadeLevel, 2);
+    o.decodeMul = ms.maxDistance;
+    o.decodeAdd = -ms.maxDistance;
+    out[k] = o;
+}
+
+__device__ __forceinline__ int wrap_repeat(int i, int n) { return ((i % n) + n) % n; }
+
+__device__ __forceinline__ float sample_mesh_sdf(const uint16_t* __restrict__ d, int W, int H, int D, float u, float v, float w)
+{
+    float x = u * (float)W - 0.5f, y = v * (float)H - 0.5f, z = w * (float)D - 0.5f;
+    float fx = floorf(x), fy = floorf(y), fz = floorf(z);
+    float ax = x - fx, ay = y - fy, az = z - fz;
+    int   ix = (int)fx, iy = (int)fy, iz = (int)fz;
+    int   x0 = wrap_repeat(ix, W), x1 = wrap_repeat(ix + 1, W), y0 = wrap_repeat(iy, H), y1 = wrap_repeat(iy + 1, H);
+    int   z0 = wrap_repeat(iz, D), z1 = wrap_repeat(iz + 1, D);
+    const uint16_t* p00 = d + ((size_t)z0 * H + y0) * W;
+    const uint16_t* p10 = d + ((size_t)z0 * H + y1) * W;
+    const uint16_t* p01 = d + ((size_t)z1 * H + y0) * W;
+    const uint16_t* p11 = d + ((size_t)z1 * H + y1) * W;
+    float c00 = lerp1(ld_h(p00 + x0), ld_h(p00 + x1), ax), c10 = lerp1(ld_h(p10 + x0), ld_h(p10 + x1), ax);
+    float c01 = lerp1(ld_h(p01 + x0), ld_h(p01 + x1), ax), c11 = lerp1(ld_h(p11 + x0), ld_h(p11 + x1), ax);
+    return lerp1(lerp1(c00, c10, ay), lerp1(c01, c11, ay), az);
+}
+
+__device__ __forceinline__ float combine_distance_to_sdf(float sdf, float distanceToSDF)
+{
+    if (sdf <= 0.0f && distanceToSDF <= 0.0f)
+        return sdf;
+    float maxSDF = gmax(sdf, 0.0f);
+    return __fsqrt_rn(maxSDF * maxSDF + distanceToSDF * distanceToSDF);
+}
+
+__global__ void __launch_bounds__(512) sdf_rasterize_kernel(const __grid_constant__ SdfRasterizeParams P)
+{
+    __shared__ SdfChunkDispatch sd;
+    const SdfChunkDispatch& gd = P.dispatches[blockIdx.x >> 6];
+    if (threadIdx.x < sizeof(SdfChunkDispatch) / 4)
+        reinterpret_cast<uint32_t*>(&sd)[threadIdx.x] = reinterpret_cast<const uint32_t*>(&gd)[threadIdx.x];
+    __syncthreads();
+    const int group = blockIdx.x & 63; // 4x4x4 groups of 8x8x8 voxels per chunk
+    const int x = ((group & 3) << 3) + (threadIdx.x & 7), y = (((group >> 2) & 3) << 3) + ((threadIdx.x >> 3) & 7), z = ((group >> 4) << 3) + (threadIdx.x >> 6);
+    const int vx = sd.coord[0] + x, vy = sd.coord[1] + y, vz = sd.coord[2] + z;
+    if (vx < 0 || vy < 0 || vz < 0 || vx >= P.res || vy >= P.res || vz >= P.res)
+        return; // out-of-bounds image access
+    f3 worldPos = {(float)vx * P.mul[0] + P.add[0], (float)vy * P.mul[1] + P.add[1], (float)vz * P.mul[2] + P.add[2]};
+    const size_t o = ((size_t)vz * P.res + vy) * P.texWidth + (vx + P.cascadeIndex * P.res);
+    float minDistance = P.maxDistance;
+    if (sd.read)
+        minDistance *= h2f_bits(P.sdf[o]);
+    for (int i = 0; i < sd.count; i++)
+    {
+        const uint32_t id = sd.models[i];
+        const LuxObjectRasterizeData& m = P.objects[id];
+        float w2v[16];
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+        {
+            float4 c = __ldg(reinterpret_cast<const float4*>(m.worldToVolume) + k);
+            w2v[k * 4 + 0] = c.x; w2v[k * 4 + 1] = c.y; w2v[k * 4 + 2] = c.z; w2v[k * 4 + 3] = c.w;
+        }
+        f3 volumePos = mat4_mul_point(w2v, worldPos, 1.0f);
+        f3 e = {__ldg(m.volumeLocalBoundsExtent + 0), __ldg(m.volumeLocalBoundsExtent + 1), __ldg(m.volumeLocalBoundsExtent + 2)};
+        f3 clamped = {gclamp(volumePos.x, -e.x, e.x), gclamp(volumePos.y, -e.y, e.y), gclamp(volumePos.z, -e.z, e.z)};
+        float v2w[16];
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+        {
+            float4 c = __ldg(reinterpret_cast<const float4*>(m.volumeToWorld) + k);
+            v2w[k * 4 + 0] = c.x; v2w[k * 4 + 1] = c.y; v2w[k * 4 + 2] = c.z; v2w[k * 4 + 3] = c.w;
+        }
+        f3    worldPosClamped  = mat4_mul_point(v2w, clamped, 1.0f);
+        float distanceToVolume = length3(worldPos - worldPosClamped);
+        if (distanceToVolume < 0.01f)
+            distanceToVolume = length3(volumePos - clamped);
+        distanceToVolume = gmax(distanceToVolume, 0.0f);
+        float objectDistance = distanceToVolume;
+        if (!(minDistance <= distanceToVolume))
+        {
+            const SdfMeshLevel lv = P.levels[id];
+            float u = volumePos.x * __ldg(m.volumeToUVWMul + 0) + __ldg(m.volumeToUVWAdd + 0);
+            float v = volumePos.y * __ldg(m.volumeToUVWMul + 1) + __ldg(m.volumeToUVWAdd + 1);
+            float w = volumePos.z * __ldg(m.volumeToUVWMul + 2) + __ldg(m.volumeToUVWAdd + 2);
+            float volumeDistance = (sample_mesh_sdf(lv.data, lv.w, lv.h, lv.d, u, v, w) * 2.0f - 1.0f) * __ldg(&m.decodeMul);
+            float result = combine_distance_to_sdf(volumeDistance, distanceToVolume);
+            if (distanceToVolume > 0.0f)
+                result = gmax(distanceToVolume, result);
+            objectDistance = result;
+        }
+        minDistance = gmin(minDistance, objectDistance);
+    }
+    P.sdf[o] = f2h_bits(gclamp(__fdiv_rn(minDistance, P.maxDistance), -1.0f, 1.0f));
+}
+
+__global__ void sdf_fill_kernel(uint16_t* __restrict__ p, size_t n, uint16_t v)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        p[i] = v;
+}
+
+__global__ void __launch_bounds__(64) sdf_mip_kernel(const uint16_t* __restrict__ src, int srcWidth, int srcHeight, uint16_t* __restrict__ dst, int dstWidth,
+                                                     int dstHeight, int outRes, int globalSDFResolution, int mipmapCoordScale, int cascadeTexOffsetX,
+                                                     int cascadeMipMapOffsetX, float maxDistance)
+{
+    const int x = blockIdx.x * 4 + (threadIdx.x & 3), y = blockIdx.y * 4 + ((threadIdx.x >> 2) & 3), z = blockIdx.z * 4 + (threadIdx.x >> 4);
+    if (x >= outRes || y >= outRes || z >= outRes)
+        return;
+    const int off[7][3] = {{0, 0, 0}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {-1, 0, 0}, {0, -1, 0}, {0, 0, -1}};
+    float minDistance = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 7; k++)
+    {
+        int cx = iclamp(x * mipmapCoordScale + off[k][0], 0, globalSDFResolution - 1);
+        int cy = iclamp(y * mipmapCoordScale + off[k][1], 0, globalSDFResolution - 1);
+        int cz = iclamp(z * mipmapCoordScale + off[k][2], 0, globalSDFResolution - 1);
+        float result = h2f_bits(src[((size_t)cz * srcHeight + cy) * srcWidth + cx + cascadeTexOffsetX]);
+        float len = length3({(float)off[k][0], (float)off[k][1], (float)off[k][2]});
+        float distanceToVoxel = len * __fdiv_rn(maxDistance, (float)globalSDFResolution);
+        result = combine_distance_to_sdf(result, distanceToVoxel);
+        minDistance = k == 0 ? result : gmin(minDistance, result);
+    }
+    dst[((size_t)z * dstHeight + y) * dstWidth + x + cascadeMipMapOffsetX] = f2h_bits(minDistance);
+}
+
+void launch_sdf_object_data(const SdfMeshRecord* meshes, int count, int cascadeLevel, LuxObjectRasterizeData* out, cudaStream_t s)
+{
+    if (count > 0)
+        sdf_object_data_kernel<<<(count + 63) / 64, 64, 0, s>>>(meshes, count, cascadeLevel, out);
+}
+
+void launch_sdf_rasterize(const SdfRasterizeParams& p, int dispatchCount, cudaStream_t s)
+{
+    if (dispatchCount > 0)
+        sdf_rasterize_kernel<<<(unsigned)dispatchCount * 64u, 512, 0, s>>>(p);
+}
+
+void launch_sdf_fill(uint16_t* p, size_t n, uint16_t value, cudaStream_t s) { sdf_fill_kernel<<<148 * 8, 256, 0, s>>>(p, n, value); }
+
+void launch_sdf_mip_pass(const uint16_t* src, int srcWidth, int srcHeight, uint16_t* dst, int dstWidth, int dstHeight, int outRes, int globalSDFResolution,
+                         int mipmapCoordScale, int cascadeTexOffsetX, int cascadeMipMapOffsetX, float maxDistance, cudaStream_t s)
+{
+    const unsigned g = (unsigned)(outRes + 3) / 4;
+    sdf_mip_kernel<<<dim3(g, g, g), 64, 0, s>>>(src, srcWidth, srcHeight, dst, dstWidth, dstHeight, outRes, globalSDFResolution, mipmapCoordScale,
+                                                cascadeTexOffsetX, cascadeMipMapOffsetX, maxDistance);
 }
 
 void launch_indirect_light(const LuxDDGIUniform& ddgi, const void* irr, const void* dep, void* light, const void* base, int count,

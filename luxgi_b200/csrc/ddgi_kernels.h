@@ -111,4 +111,36 @@ void launch_indirect_light(const LuxDDGIUniform& ddgi, const void* irr, const vo
                            const uint32_t* texel, const float* P, const float* N, const float* albedo, const float* metallic, float intensity,
                            const float* cameraPos, cudaStream_t s);
 
+// ---- global SDF build ----
+struct SdfMeshRecord // device copy of LuxMeshSDF without the host pointers
+{
+    float aabbMin[3], aabbMax[3];
+    float localToUVWMul[3], localToUVWAdd[3];
+    float maxDistance;
+    float worldMatrix[16];
+};
+struct SdfMeshLevel { const uint16_t* data; int w, h, d; }; // the mip level a cascade samples
+struct SdfChunkDispatch                                      // RasterizeConsts (GlobalDistanceField.cpp:161-166) + which pipeline
+{
+    int32_t  coord[3]; // first voxel of the chunk
+    int32_t  count;
+    uint32_t models[LUX_SDF_RASTERIZE_MODEL_MAX_COUNT];
+    int32_t  read;     // 1 = READ_DISTANCE variant (additive layer)
+};
+struct SdfRasterizeParams // ModelsRasterizeData (SDFRasterizeModel.glsl:16-24) + bindings
+{
+    float mul[3], add[3];
+    float maxDistance;
+    int   res, cascadeIndex, texWidth;
+    const LuxObjectRasterizeData* objects;
+    const SdfMeshLevel*           levels;
+    const SdfChunkDispatch*       dispatches;
+    uint16_t*                     sdf;
+};
+void launch_sdf_object_data(const SdfMeshRecord* meshes, int count, int cascadeLevel, LuxObjectRasterizeData* out, cudaStream_t s);
+void launch_sdf_rasterize(const SdfRasterizeParams& p, int dispatchCount, cudaStream_t s);
+void launch_sdf_fill(uint16_t* p, size_t n, uint16_t value, cudaStream_t s);
+void launch_sdf_mip_pass(const uint16_t* src, int srcWidth, int srcHeight, uint16_t* dst, int dstWidth, int dstHeight, int outRes, int globalSDFResolution,
+                         int mipmapCoordScale, int cascadeTexOffsetX, int cascadeMipMapOffsetX, float maxDistance, cudaStream_t s);
+
 } // namespace lux

@@ -25,7 +25,7 @@ EXPORTS = [
     "lux_ddgi_border_update", "lux_ddgi_end_frame", "lux_ddgi_update", "lux_ddgi_synchronize", "lux_ddgi_get_buffer",
     "lux_ddgi_download", "lux_ddgi_download_async", "lux_ddgi_download_rows_async", "lux_ddgi_set_ray_buffers", "lux_ddgi_restore", "lux_ddgi_get_state", "lux_ddgi_shard_layout",
     "lux_ddgi_get_stage_ms", "lux_ddgi_sample_irradiance", "lux_ddgi_sample_probe", "lux_ddgi_indirect_light",
-    "lux_ddgi_get_surface_light_cache",
+    "lux_ddgi_get_surface_light_cache", "lux_ddgi_build_global_sdf", "lux_ddgi_build_sdf_mip", "lux_ddgi_sdf_file_read",
 ]
 
 
@@ -75,6 +75,9 @@ def load():
         "lux_ddgi_sample_probe": [vp, i32, i32, vp, vp, vp, vp, vp, i32],
         "lux_ddgi_indirect_light": [vp, vp, i32, vp, vp, vp, vp, vp, C.c_float, vp, i32],
         "lux_ddgi_get_surface_light_cache": [vp, C.POINTER(vp), C.POINTER(sz)],
+        "lux_ddgi_build_global_sdf": [vp, C.POINTER(abi.GlobalSDFData), C.POINTER(abi.MeshSDF), i32, C.c_float],
+        "lux_ddgi_build_sdf_mip": [vp],
+        "lux_ddgi_sdf_file_read": [C.c_char_p, C.POINTER(C.c_uint32 * 3), C.POINTER(i32), C.POINTER(C.c_uint64), vp],
     }
     for name, argtypes in sig.items():
         fn = getattr(L, name)
@@ -181,6 +184,7 @@ class DDGIPipeline:
         if ks != km:
             raise ValueError("sdf and mip must both be host or both be device arrays")
         _check(self._lib.lux_ddgi_set_global_sdf(self._h, C.byref(sdf_data), ps, pm, ks))
+        self._sdf_data = sdf_data
         if ks == abi.MEM_DEVICE:
             self._keep += [k1, k2]
 
@@ -278,6 +282,10 @@ class DDGIPipeline:
 
     def _shape(self, buf):
         u = self.uniform
+        if buf in (abi.BUF_GLOBAL_SDF, abi.BUF_GLOBAL_SDF_MIP):
+            res, casc = int(self._sdf_data.resolution), int(self._sdf_data.cascadesCount)
+            r = res if buf == abi.BUF_GLOBAL_SDF else res // 4
+            return (r, r, r * casc)
         if buf in (abi.BUF_RADIANCE, abi.BUF_DIRECTION_DISTANCE):
             return (self.probe_count, self.rays, 4)
         if buf in (abi.BUF_IRRADIANCE, abi.BUF_IRRADIANCE_PREV):
@@ -326,6 +334,26 @@ class DDGIPipeline:
         _check(self._lib.lux_ddgi_sample_probe(self._h, w, h, _host_ptr(depth), _host_ptr(normals), _host_ptr(cam), _host_ptr(vpi), _host_ptr(out),
                                                abi.MEM_HOST))
         return out
+
+    # ---- global SDF build ---------------------------------------------------------------------
+    def build_global_sdf(self, sdf_data, meshes, min_object_radius=0.0):
+        """Merge mesh distance fields (luxgi_b200.meshsdf.MeshSDF) into the cascades of `sdf_data` on device, build the mip, bind both."""
+        from . import meshsdf
+
+        arr, keep = meshsdf.to_ctypes(meshes)
+        _check(self._lib.lux_ddgi_build_global_sdf(self._h, C.byref(sdf_data), arr, len(meshes), float(min_object_radius)))
+        self._sdf_data = sdf_data
+
+    def build_sdf_mip(self):
+        _check(self._lib.lux_ddgi_build_sdf_mip(self._h))
+
+    @property
+    def global_sdf(self):
+        return self.download(abi.BUF_GLOBAL_SDF)
+
+    @property
+    def global_sdf_mip(self):
+        return self.download(abi.BUF_GLOBAL_SDF_MIP)
 
     def indirect_light(self, base_light, texel, P, N, albedo, metallic, intensity, camera_pos):
         """Infinite-bounce refresh of the surface light cache (SDFAtlasIndirectLight.frag) for a list of atlas texels."""

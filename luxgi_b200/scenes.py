@@ -17,6 +17,7 @@ Nothing here is on the product path: the engine only ever sees the resulting buf
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass, field
 from typing import Optional
 
@@ -500,9 +501,67 @@ def city_scene(res: int = 512, lots: int = 48, counts=(64, 16, 64), rays: int = 
     return sc
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# C2 / C3: the reference's dark-room-emissive scene (BASELINE configs[1], [2])
+# ------------------------------------------------------------------------------------------------------------------
+DARK_ROOM_FIXTURE = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "c2_dark_room.npz")
+
+
+def dark_room_scene(counts=(16, 8, 16), rays: int = 256, atlas_res: int = 2048, device="cpu", with_atlas=True, hysteresis=0.98, gamma=0.85,
+                    fixture: str = DARK_ROOM_FIXTURE) -> Scene:
+    """Global SDF of Assets/dark-room-emissive.scene merged from its 100 baked mesh fields (tests/golden/make_c2_dark_room.py wrote the
+    fixture in the build container: 128^3, half extent 88, centre 0).  Probe volume over the world AABB of the meshes as
+    ddgi::on_game_start lays it out (start = AABB min, counts as configured, step = extent / (counts - 1)); gamma 0.85 is the shipped
+    scene's ddgiGamma.  Surface cache: one OBB object per mesh field (its world AABB), six tiles each; albedo from a hash of the mesh name,
+    emissive 10 on meshes whose name contains "Light" / "Emissive", one point light under the ceiling."""
+    import zlib
+
+    fx = np.load(fixture)
+    D, res = float(fx["half_extent"]), int(fx["resolution"])
+    dev = torch.device(device)
+    sdf = torch.from_numpy(fx["sdf"].view(np.float16).copy()).to(dev)
+    mip = torch.from_numpy(fx["mip"].view(np.float16).copy()).to(dev)
+    cen, half = fx["box_center"].astype(np.float64), fx["box_half"].astype(np.float64)
+    lo, hi = (cen - half).min(0), (cen + half).max(0)
+    inset = 2.0
+    start = lo + inset
+    step = (hi - lo - 2 * inset) / (np.asarray(counts, dtype=np.float64) - 1)
+    uni = abi.make_uniform(tuple(float(x) for x in start), tuple(float(x) for x in step), counts, rays, hysteresis=hysteresis, gamma=gamma)
+    sc = Scene("dark-room", uni, make_sdf_data((0.0, 0.0, 0.0), D, res), sdf, mip)
+    sc.meta = {"D": D, "res": res, "voxel": 2 * D / res, "build_stats": [int(x) for x in fx["stats"]]}
+    if with_atlas:
+        boxes = []
+        for k, (c, h, name, em) in enumerate(zip(cen, half, fx["names"], fx["emissive"])):
+            hsh = zlib.crc32(str(name).encode())
+            albedo = tuple(0.25 + 0.6 * ((hsh >> (8 * i)) & 255) / 255.0 for i in range(3))
+            boxes.append(BoxObject(c, np.maximum(h, 0.05), 0.0, albedo, (10.0, 10.0, 10.0) if em else (0.0, 0.0, 0.0), tag=k))
+        albedo_t = torch.tensor([b.albedo for b in boxes], dtype=torch.float32, device=dev)
+        emis_t = torch.tensor([b.emissive for b in boxes], dtype=torch.float32, device=dev)
+        light_pos = torch.tensor([float((lo[0] + hi[0]) * 0.5), float(hi[1] - 6.0), float((lo[2] + hi[2]) * 0.5)], device=dev)
+
+        def shade(wp, wn, oi):
+            l = light_pos - wp
+            r2 = (l * l).sum(-1, keepdim=True).clamp(min=4.0)
+            ndl = ((l * wn).sum(-1, keepdim=True) / torch.sqrt(r2)).clamp(min=0)
+            return albedo_t[oi] * (1500.0 * ndl / r2) + emis_t[oi]
+
+        per_row = int(math.ceil(math.sqrt(len(boxes) * 6)))
+        cell = atlas_res // per_row
+        gb = {}
+        (sc.atlas_data, sc.chunks, sc.cull, sc.objects, sc.tiles, sc.light, sc.depth) = build_surface_cache(
+            boxes, atlas_res, cell, 2.0 * D / abi.CHUNKS_RESOLUTION, shade, device=device, gbuffer=gb)
+        alb = np.asarray([b.albedo for b in boxes], dtype=np.float32)
+        gb["albedo"] = alb[gb["object"]]
+        gb["metallic"] = np.zeros(len(gb["texel"]), dtype=np.float32)
+        sc.meta["gbuffer"] = gb
+    return sc
+
+
 CONFIGS = {
     # name: (builder, kwargs) — SURVEY.md §8d
     "c1": (cornell_scene, dict(res=64, counts=(8, 8, 8), rays=64, atlas_res=512)),
+    "c2": (dark_room_scene, dict(counts=(16, 8, 16), rays=256, atlas_res=2048)),
+    "c3": (dark_room_scene, dict(counts=(32, 16, 32), rays=256, atlas_res=2048)),
     "c4": (city_scene, dict(res=512, lots=48, counts=(64, 16, 64), rays=512, atlas_res=4096)),
     "c5": (city_scene, dict(res=1024, lots=96, counts=(128, 32, 128), rays=1024, atlas_res=8192)),
     # reduced cities for tests

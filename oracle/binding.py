@@ -250,3 +250,75 @@ class OraclePipeline:
     @property
     def depth(self):
         return self.dep[self.ping]
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# global SDF build (row f3)
+# ----------------------------------------------------------------------------------------------------------------------
+def sdf_object_data(mesh, cascade_level):
+    """ObjectRasterizeData of a luxgi_b200.meshsdf.MeshSDF for one cascade level (chunkCalculate)."""
+    from luxgi_b200 import meshsdf
+
+    arr, keep = meshsdf.to_ctypes([mesh])
+    out = abi.ObjectRasterizeData()
+    L = lib()
+    L.oracle_sdf_object_data.restype = None
+    L.oracle_sdf_object_data.argtypes = [C.POINTER(abi.MeshSDF), C.c_int, C.POINTER(abi.ObjectRasterizeData)]
+    L.oracle_sdf_object_data(arr, int(cascade_level), C.byref(out))
+    return out
+
+
+def sdf_rasterize_chunk(sdf_bits, objs, meshes, mip_level, centre, D, res, cascade, chunk, ids, read, groups=None):
+    """One SDFRasterizeModel dispatch on `sdf_bits` (uint16 [res][res][res*cascades]) in place."""
+    L = lib()
+    voxel = np.float32(2 * D) / np.float32(res)
+    mul = (C.c_float * 3)(*[float(np.float32(2 * D) / np.float32(res))] * 3)
+    add = (C.c_float * 3)(*[float(np.float32(c) - np.float32(D) + voxel * np.float32(0.5)) for c in centre])
+    oarr = (abi.ObjectRasterizeData * len(objs))(*objs)
+    lv = [np.ascontiguousarray(m.levels[mip_level], dtype=np.float16) for m in meshes]
+    ptrs = (C.c_void_p * len(lv))(*[a.ctypes.data for a in lv])
+    sizes = np.ascontiguousarray([[a.shape[2], a.shape[1], a.shape[0]] for a in lv], dtype=np.int32)
+    cc = (C.c_int32 * 3)(*[int(x) for x in chunk])
+    idarr = (C.c_uint32 * max(1, len(ids)))(*[int(i) for i in ids])
+    L.oracle_sdf_rasterize_chunk.restype = C.c_int
+    L.oracle_sdf_rasterize_chunk.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    rc = L.oracle_sdf_rasterize_chunk(mul, add, float(np.float32(2 * D)), int(res), int(cascade), cc, len(ids), idarr, int(bool(read)), oarr, ptrs,
+                                      _ptr(sizes), _ptr(sdf_bits), int(sdf_bits.shape[2]))
+    assert rc == 0, rc
+
+
+def sdf_mip_pass(src, dst, out_res, res, scale, tex_off, mip_off, max_distance):
+    L = lib()
+    L.oracle_sdf_mip_pass.restype = C.c_int
+    L.oracle_sdf_mip_pass.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float]
+    rc = L.oracle_sdf_mip_pass(_ptr(src), src.shape[2], src.shape[1], _ptr(dst), dst.shape[2], dst.shape[1], int(out_res), int(res), int(scale),
+                               int(tex_off), int(mip_off), float(max_distance))
+    assert rc == 0, rc
+
+
+def sdf_build_mip(sdf_data, sdf_bits):
+    res, casc = int(sdf_data.resolution), int(sdf_data.cascadesCount)
+    mip = np.zeros((res // 4, res // 4, res // 4 * casc), dtype=np.uint16)
+    L = lib()
+    L.oracle_sdf_build_mip.restype = C.c_int
+    L.oracle_sdf_build_mip.argtypes = [C.POINTER(abi.GlobalSDFData), C.c_void_p, C.c_void_p]
+    assert L.oracle_sdf_build_mip(C.byref(sdf_data), _ptr(sdf_bits), _ptr(mip)) == 0
+    return mip
+
+
+def sdf_build(sdf_data, meshes, min_object_radius=0.0):
+    """One-shot global SDF build -> (sdf uint16 [res][res][res*casc], mip uint16, stats dict)."""
+    from luxgi_b200 import meshsdf
+
+    res, casc = int(sdf_data.resolution), int(sdf_data.cascadesCount)
+    sdf = np.zeros((res, res, res * casc), dtype=np.uint16)
+    mip = np.zeros((res // 4, res // 4, res // 4 * casc), dtype=np.uint16)
+    arr, keep = meshsdf.to_ctypes(meshes)
+    stats = (C.c_int32 * 4)()
+    L = lib()
+    L.oracle_sdf_build.restype = C.c_int
+    L.oracle_sdf_build.argtypes = [C.POINTER(abi.GlobalSDFData), C.POINTER(abi.MeshSDF), C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
+    rc = L.oracle_sdf_build(C.byref(sdf_data), arr, len(meshes), float(min_object_radius), _ptr(sdf), _ptr(mip), stats)
+    assert rc == 0, rc
+    return sdf, mip, dict(zip(("chunks", "models", "dropped_by_overflow", "chunks_out_of_range"), [int(x) for x in stats]))

@@ -1197,6 +1197,300 @@ int oracle_indirect_light(const LuxDDGIUniform* ddgi, const uint16_t* irr, const
     return 0;
 }
 
+} // extern "C"
+
+// =====================================================================================================================
+// Global SDF build ("next" row f3): the step before the path.
+//   device side   Shaders/SDF/SDFRasterizeModel.glsl:42-63 (main), Shaders/SDF/SDFCommon.glsl:18-62 (combineDistanceToSDF,
+//                 distanceToModelSDF), Shaders/SDF/GlobalSDFMipmap.comp:32-68
+//   host side     Engine/DDGI/GlobalDistanceField.cpp:193-210 (getChunkId), :460-533 (chunkCalculate), :537-573 (fillFlood),
+//                 :575-848 (merge_sdf::system, first frame: nothing cached), Math/BoundingBox.cpp:10-36, Math/BoundingSphere.cpp:9-13
+// Reference behaviours kept on purpose (each changes the output, so "same inputs -> same volume" needs them):
+//   * chunkCalculate's overflow loop assigns through a reference (`chunk = chunksCache[key]`, :515-519): when a chunk already
+//     holds 28 models the layer-0 entry is overwritten by the (empty) next-layer entry, i.e. the list restarts; additive layers
+//     never receive a model.  A chunk therefore keeps the LAST ((n-1) mod 28)+1 models registered for it.
+//   * getChunkId discards its glm::clamp results (:202-203): chunk ranges are not clamped to the cascade.  Chunks outside the
+//     volume would be out-of-bounds image stores (discarded under robust access); they are skipped here.
+//   * BoundingBox::transform takes abs() of the product in its third term (BoundingBox.cpp:17-19).
+//   * the flood passes add a WORLD-space voxel step to a NORMALISED distance (GlobalSDFMipmap.comp:44-45 with :831 maxDistance).
+//   * mesh volumes are sampled with REPEAT addressing (Texture3D default wrap) at an integer LOD.
+// =====================================================================================================================
+namespace {
+
+struct MeshTex // one mip level of a mesh distance field, R16F [z][y][x], trilinear, repeat
+{
+    const uint16_t* d;
+    int             w, h, dd;
+};
+
+inline float sampleMesh(const MeshTex& t, float u, float v, float w)
+{
+    float x = u * (float)t.w - 0.5f, y = v * (float)t.h - 0.5f, z = w * (float)t.dd - 0.5f;
+    float fx = std::floor(x), fy = std::floor(y), fz = std::floor(z);
+    float ax = x - fx, ay = y - fy, az = z - fz;
+    int   ix = (int)fx, iy = (int)fy, iz = (int)fz;
+    int   x0 = wrapi(ix, t.w), x1 = wrapi(ix + 1, t.w), y0 = wrapi(iy, t.h), y1 = wrapi(iy + 1, t.h), z0 = wrapi(iz, t.dd), z1 = wrapi(iz + 1, t.dd);
+    auto  T = [&](int xx, int yy, int zz) { return h2f(t.d[((size_t)zz * t.h + yy) * t.w + xx]); };
+    float c00 = lerp1(T(x0, y0, z0), T(x1, y0, z0), ax), c10 = lerp1(T(x0, y1, z0), T(x1, y1, z0), ax);
+    float c01 = lerp1(T(x0, y0, z1), T(x1, y0, z1), ax), c11 = lerp1(T(x0, y1, z1), T(x1, y1, z1), ax);
+    return lerp1(lerp1(c00, c10, ay), lerp1(c01, c11, ay), az);
+}
+
+// SDFCommon.glsl:18-39
+inline float combineDistanceToSDF(float sdf, float distanceToSDF)
+{
+    if (sdf <= 0.0f && distanceToSDF <= 0.0f)
+        return sdf;
+    float maxSDF = gmax(sdf, 0.0f);
+    return std::sqrt(maxSDF * maxSDF + distanceToSDF * distanceToSDF);
+}
+
+// SDFCommon.glsl:41-62
+inline float distanceToModelSDF(float minDistance, const LuxObjectRasterizeData& m, const MeshTex& tex, vec3 worldPos)
+{
+    vec3 volumePos = mat4_mul_point(m.worldToVolume, worldPos, 1.0f);
+    vec3 volumeUV  = {volumePos.x * m.volumeToUVWMul[0] + m.volumeToUVWAdd[0], volumePos.y * m.volumeToUVWMul[1] + m.volumeToUVWAdd[1],
+                      volumePos.z * m.volumeToUVWMul[2] + m.volumeToUVWAdd[2]};
+    vec3 e = {m.volumeLocalBoundsExtent[0], m.volumeLocalBoundsExtent[1], m.volumeLocalBoundsExtent[2]};
+    vec3 volumePosClamped = {gclamp(volumePos.x, -e.x, e.x), gclamp(volumePos.y, -e.y, e.y), gclamp(volumePos.z, -e.z, e.z)};
+    vec3 worldPosClamped  = mat4_mul_point(m.volumeToWorld, volumePosClamped, 1.0f);
+    float distanceToVolume = length3(sub(worldPos, worldPosClamped));
+    if (distanceToVolume < 0.01f)
+        distanceToVolume = length3(sub(volumePos, volumePosClamped));
+    distanceToVolume = gmax(distanceToVolume, 0.0f);
+    if (minDistance <= distanceToVolume)
+        return distanceToVolume;
+    float volumeDistance = (sampleMesh(tex, volumeUV.x, volumeUV.y, volumeUV.z) * 2.0f - 1.0f) * m.decodeMul;
+    float result = combineDistanceToSDF(volumeDistance, distanceToVolume);
+    if (distanceToVolume > 0.0f)
+        result = gmax(distanceToVolume, result);
+    return result;
+}
+
+
+inline void mat4_mul(const float* a, const float* b, float* o) // column-major a*b, sums in k order
+{
+    for (int c = 0; c < 4; c++)
+        for (int r = 0; r < 4; r++)
+            o[c * 4 + r] = ((a[0 * 4 + r] * b[c * 4 + 0] + a[1 * 4 + r] * b[c * 4 + 1]) + a[2 * 4 + r] * b[c * 4 + 2]) + a[3 * 4 + r] * b[c * 4 + 3];
+}
+
+struct ChunkList { int coord[3]; int count; uint32_t models[LUX_SDF_RASTERIZE_MODEL_MAX_COUNT]; };
+
+} // namespace
+
+extern "C" {
+
+// One SDFRasterizeModel dispatch: 32^3 voxels of chunk `chunkCoord` (voxel units) of cascade `cascadeIndex`.
+// ubo = ModelsRasterizeData (SDFRasterizeModel.glsl:16-24).  meshTex[i] must already be the mip level objects[i].mipOffset selects.
+int oracle_sdf_rasterize_chunk(const float* coordToPosMul3, const float* coordToPosAdd3, float maxDistance, int cascadeResolution, int cascadeIndex,
+                               const int32_t* chunkCoord3, int objectsCount, const uint32_t* objectIds, int readDistance,
+                               const LuxObjectRasterizeData* objects, const uint16_t* const* meshData, const int32_t* meshSizes /*[n][3]*/,
+                               uint16_t* globalSDF, int texWidth)
+{
+    const int C = LUX_SDF_RASTERIZE_CHUNK_SIZE, res = cascadeResolution;
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int z = 0; z < C; z++)
+        for (int y = 0; y < C; y++)
+            for (int x = 0; x < C; x++)
+            {
+                int vx = chunkCoord3[0] + x, vy = chunkCoord3[1] + y, vz = chunkCoord3[2] + z;
+                vec3 worldPos = {(float)vx * coordToPosMul3[0] + coordToPosAdd3[0], (float)vy * coordToPosMul3[1] + coordToPosAdd3[1],
+                                 (float)vz * coordToPosMul3[2] + coordToPosAdd3[2]};
+                int tx = vx + cascadeIndex * res;
+                if (vx < 0 || vy < 0 || vz < 0 || vx >= res || vy >= res || vz >= res)
+                    continue; // out-of-bounds image access
+                size_t o = ((size_t)vz * res + vy) * texWidth + tx;
+                float minDistance = maxDistance;
+                if (readDistance)
+                    minDistance *= h2f(globalSDF[o]);
+                for (int i = 0; i < objectsCount; i++)
+                {
+                    uint32_t id = objectIds[i];
+                    MeshTex  t{meshData[id], meshSizes[id * 3 + 0], meshSizes[id * 3 + 1], meshSizes[id * 3 + 2]};
+                    float d = distanceToModelSDF(minDistance, objects[id], t, worldPos);
+                    minDistance = gmin(minDistance, d);
+                }
+                globalSDF[o] = f2h(gclamp(minDistance / maxDistance, -1.0f, 1.0f));
+            }
+    return 0;
+}
+
+// One GlobalSDFMipmap dispatch over mipRes^3 outputs (GlobalSDFMipmap.comp:32-68).  src / dst are R16F [z][y][x] with the given row widths.
+int oracle_sdf_mip_pass(const uint16_t* src, int srcWidth, int srcHeight, uint16_t* dst, int dstWidth, int dstHeight, int outRes, int globalSDFResolution,
+                        int mipmapCoordScale, int cascadeTexOffsetX, int cascadeMipMapOffsetX, float maxDistance)
+{
+    static const int off[7][3] = {{0, 0, 0}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {-1, 0, 0}, {0, -1, 0}, {0, 0, -1}};
+#pragma omp parallel for collapse(2) schedule(static)
+    for (int z = 0; z < outRes; z++)
+        for (int y = 0; y < outRes; y++)
+            for (int x = 0; x < outRes; x++)
+            {
+                float minDistance = 0.0f;
+                for (int k = 0; k < 7; k++)
+                {
+                    int cx = iclamp(x * mipmapCoordScale + off[k][0], 0, globalSDFResolution - 1);
+                    int cy = iclamp(y * mipmapCoordScale + off[k][1], 0, globalSDFResolution - 1);
+                    int cz = iclamp(z * mipmapCoordScale + off[k][2], 0, globalSDFResolution - 1);
+                    float result = h2f(src[((size_t)cz * srcHeight + cy) * srcWidth + cx + cascadeTexOffsetX]);
+                    float len = length3({(float)off[k][0], (float)off[k][1], (float)off[k][2]});
+                    float distanceToVoxel = len * (maxDistance / (float)globalSDFResolution);
+                    result = combineDistanceToSDF(result, distanceToVoxel);
+                    minDistance = k == 0 ? result : gmin(minDistance, result);
+                }
+                dst[((size_t)z * dstHeight + y) * dstWidth + x + cascadeMipMapOffsetX] = f2h(minDistance);
+            }
+    return 0;
+}
+
+// Mip of every cascade: one downsample + 4 flood passes ping-ponging through a temporary (GlobalDistanceField.cpp:537-573, 825-841)
+int oracle_sdf_build_mip(const LuxGlobalSDFData* data, const uint16_t* sdf, uint16_t* mip)
+{
+    const int res = (int)data->resolution, casc = (int)data->cascadesCount, mres = res / 4;
+    std::vector<uint16_t> tmp((size_t)mres * mres * mres, f2h(1.0f));
+    for (int c = 0; c < casc; c++)
+    {
+        float cascadeMaxDistance = data->cascadePosDistance[c][3] * 2.0f;
+        oracle_sdf_mip_pass(sdf, res * casc, res, mip, mres * casc, mres, mres, res, 4, c * res, c * mres, cascadeMaxDistance);
+        for (int i = 1; i < 5; i++)
+        {
+            if (i & 1)
+                oracle_sdf_mip_pass(mip, mres * casc, mres, tmp.data(), mres, mres, mres, mres, 1, c * mres, 0, cascadeMaxDistance);
+            else
+                oracle_sdf_mip_pass(tmp.data(), mres, mres, mip, mres * casc, mres, mres, mres, 1, 0, c * mres, cascadeMaxDistance);
+        }
+    }
+    return 0;
+}
+
+// ObjectRasterizeData of one mesh for cascade level `cascadeLevel` (chunkCalculate, GlobalDistanceField.cpp:484-508)
+void oracle_sdf_object_data(const LuxMeshSDF* mesh, int cascadeLevel, LuxObjectRasterizeData* out)
+{
+    vec3 mn = {mesh->aabbMin[0], mesh->aabbMin[1], mesh->aabbMin[2]}, mx = {mesh->aabbMax[0], mesh->aabbMax[1], mesh->aabbMax[2]};
+    vec3 volumeCenter = mul(add(mx, mn), 0.5f);
+    float worldToLocal[16], tr[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, -volumeCenter.x, -volumeCenter.y, -volumeCenter.z, 1};
+    inverse4(mesh->worldMatrix, worldToLocal);
+    mat4_mul(worldToLocal, tr, out->worldToVolume);
+    inverse4(out->worldToVolume, out->volumeToWorld);
+    vec3 size = sub(mx, mn);
+    out->volumeLocalBoundsExtent[0] = size.x / 2.0f; out->volumeLocalBoundsExtent[1] = size.y / 2.0f; out->volumeLocalBoundsExtent[2] = size.z / 2.0f;
+    for (int i = 0; i < 3; i++)
+    {
+        out->volumeToUVWMul[i] = mesh->localToUVWMul[i];
+        out->volumeToUVWAdd[i] = mesh->localToUVWAdd[i] + (&volumeCenter.x)[i] * mesh->localToUVWMul[i];
+    }
+    out->mipOffset = (float)(cascadeLevel < 2 ? cascadeLevel : 2);
+    out->decodeMul = mesh->maxDistance;
+    out->decodeAdd = -mesh->maxDistance;
+}
+
+// The whole one-shot build: global SDF [res][res][res*cascades] (cleared to 1.0 first) and its mip.
+// chunkStats (nullable, 4 ints): chunks dispatched, models referenced, models dropped by the overflow bug, chunks skipped out of range
+int oracle_sdf_build(const LuxGlobalSDFData* data, const LuxMeshSDF* meshes, int meshCount, float minObjectRadius, uint16_t* sdf, uint16_t* mip,
+                     int32_t* chunkStats)
+{
+    if (!data || !meshes || !sdf || !mip)
+        return -1;
+    const int res = (int)data->resolution, casc = (int)data->cascadesCount, texWidth = res * casc;
+    const int rasterizeChunks = (res + LUX_SDF_RASTERIZE_CHUNK_SIZE - 1) / LUX_SDF_RASTERIZE_CHUNK_SIZE;
+    for (size_t i = 0; i < (size_t)res * res * texWidth; i++)
+        sdf[i] = f2h(1.0f);
+    int32_t stats[4] = {0, 0, 0, 0};
+    for (int c = 0; c < casc; c++)
+    {
+        const float D = data->cascadePosDistance[c][3], cascadeMaxDistance = D * 2.0f, voxel = data->cascadeVoxelSize[c];
+        const vec3  center = {data->cascadePosDistance[c][0], data->cascadePosDistance[c][1], data->cascadePosDistance[c][2]};
+        const vec3  bmin = {center.x - D, center.y - D, center.z - D}, bmax = {center.x + D, center.y + D, center.z + D};
+        std::vector<LuxObjectRasterizeData> objects;
+        std::vector<const uint16_t*>        meshData;
+        std::vector<int32_t>                meshSizes;
+        std::vector<ChunkList>              chunks; // insertion order; lookup by coordinate
+        auto findChunk = [&](int x, int y, int z) -> ChunkList& {
+            for (auto& ch : chunks)
+                if (ch.coord[0] == x && ch.coord[1] == y && ch.coord[2] == z)
+                    return ch;
+            chunks.push_back(ChunkList{{x, y, z}, 0, {}});
+            return chunks.back();
+        };
+        for (int m = 0; m < meshCount; m++)
+        {
+            const LuxMeshSDF& ms = meshes[m];
+            // BoundingBox::transform (BoundingBox.cpp:10-22)
+            const float* t = ms.worldMatrix;
+            vec3 amn = {ms.aabbMin[0], ms.aabbMin[1], ms.aabbMin[2]}, amx = {ms.aabbMax[0], ms.aabbMax[1], ms.aabbMax[2]};
+            vec3 newCenter = mat4_mul_point(t, mul(add(amx, amn), 0.5f), 1.0f);
+            vec3 oldEdge   = mul(sub(amx, amn), 0.5f);
+            vec3 newEdge   = {std::fabs(t[0]) * oldEdge.x + std::fabs(t[4]) * oldEdge.y + std::fabs(t[8] * oldEdge.z),
+                              std::fabs(t[1]) * oldEdge.x + std::fabs(t[5]) * oldEdge.y + std::fabs(t[9] * oldEdge.z),
+                              std::fabs(t[2]) * oldEdge.x + std::fabs(t[6]) * oldEdge.y + std::fabs(t[10] * oldEdge.z)};
+            vec3 omn = sub(newCenter, newEdge), omx = add(newCenter, newEdge);
+            // BoundingSphere(box) + intersectsWithSphere (BoundingSphere.cpp:9-13, BoundingBox.cpp:31-36)
+            vec3  sc = mul(add(omx, omn), 0.5f);
+            float radius = length3(sub(omx, omn)) / 2.0f;
+            vec3  cl = {gclamp(sc.x, bmin.x, bmax.x), gclamp(sc.y, bmin.y, bmax.y), gclamp(sc.z, bmin.z, bmax.z)};
+            vec3  dv = sub(sc, cl);
+            if (!(dot3(dv, dv) <= radius * radius && radius >= minObjectRadius))
+                continue;
+            // getChunkId (:193-210)
+            const float objectMargin = voxel * (float)LUX_SDF_RASTERIZE_CHUNK_MARGIN;
+            vec3 biasMin = {bmin.x + 0.1f, bmin.y + 0.1f, bmin.z + 0.1f};
+            vec3 lo = {(omn.x - objectMargin) - biasMin.x, (omn.y - objectMargin) - biasMin.y, (omn.z - objectMargin) - biasMin.z};
+            vec3 hi = {(omx.x + objectMargin) - biasMin.x, (omx.y + objectMargin) - biasMin.y, (omx.z + objectMargin) - biasMin.z};
+            const float chunkSize = voxel * (float)LUX_SDF_RASTERIZE_CHUNK_SIZE;
+            int cmin[3] = {(int)(lo.x / chunkSize), (int)(lo.y / chunkSize), (int)(lo.z / chunkSize)};
+            int cmax[3] = {(int)(hi.x / chunkSize), (int)(hi.y / chunkSize), (int)(hi.z / chunkSize)};
+            uint32_t objectIndex = (uint32_t)objects.size();
+            objects.emplace_back();
+            oracle_sdf_object_data(&ms, c, &objects.back());
+            int mipLevel = c < 2 ? c : 2;
+            if (mipLevel >= ms.mipCount)
+                return -2;
+            meshData.push_back((const uint16_t*)ms.mips[mipLevel]);
+            for (int i = 0; i < 3; i++)
+            {
+                uint32_t sz = ms.size[i] >> mipLevel;
+                meshSizes.push_back((int32_t)(sz ? sz : 1));
+            }
+            for (int z = cmin[2]; z <= cmax[2]; z++)
+                for (int y = cmin[1]; y <= cmax[1]; y++)
+                    for (int x = cmin[0]; x <= cmax[0]; x++)
+                    {
+                        ChunkList& ch = findChunk(x, y, z);
+                        if (ch.count == LUX_SDF_RASTERIZE_MODEL_MAX_COUNT)
+                        { // `chunk = chunksCache[nextLayerKey]` copies the empty next-layer entry over this one
+                            stats[2] += ch.count;
+                            ch.count = 0;
+                        }
+                        ch.models[ch.count++] = objectIndex;
+                    }
+        }
+        const float cmul[3] = {(bmax.x - bmin.x) / (float)res, (bmax.y - bmin.y) / (float)res, (bmax.z - bmin.z) / (float)res};
+        const float cadd[3] = {bmin.x + voxel * 0.5f, bmin.y + voxel * 0.5f, bmin.z + voxel * 0.5f};
+        for (const ChunkList& ch : chunks)
+        {
+            if (ch.coord[0] < 0 || ch.coord[1] < 0 || ch.coord[2] < 0 || ch.coord[0] >= rasterizeChunks || ch.coord[1] >= rasterizeChunks ||
+                ch.coord[2] >= rasterizeChunks)
+            {
+                stats[3]++;
+                continue;
+            }
+            int32_t cc[3] = {ch.coord[0] * LUX_SDF_RASTERIZE_CHUNK_SIZE, ch.coord[1] * LUX_SDF_RASTERIZE_CHUNK_SIZE, ch.coord[2] * LUX_SDF_RASTERIZE_CHUNK_SIZE};
+            oracle_sdf_rasterize_chunk(cmul, cadd, cascadeMaxDistance, res, c, cc, ch.count, ch.models, 0, objects.data(), meshData.data(),
+                                       meshSizes.data(), sdf, texWidth);
+            stats[0]++;
+            stats[1] += ch.count;
+        }
+    }
+    oracle_sdf_build_mip(data, sdf, mip);
+    if (chunkStats)
+        for (int i = 0; i < 4; i++)
+            chunkStats[i] = stats[i];
+    return 0;
+}
+
+} // extern "C"
+
+extern "C" {
 // Border copy list of one probe in ring-relative coordinates: out[n][4] = (srcx, srcy, dstx, dsty); returns n.
 int oracle_border_offsets(int side, int32_t* out)
 {

@@ -192,6 +192,52 @@ class TextureCube:
         return out
 
 
+class Texture3DMips:
+    """sampler3D with a mip chain (mesh distance fields): textureLod at an INTEGER lod = trilinear inside that level,
+    REPEAT addressing (the reference's Texture3D default wrap).  levels: list of fp16 arrays [d][h][w]."""
+
+    def __init__(self, levels):
+        self.levels = [np.ascontiguousarray(l, dtype=np.float16) for l in levels]
+        self.taps = 0
+
+    def sample(self, c, lod=0.0):
+        assert float(lod) == int(lod), "fractional LOD is not modelled"
+        d = self.levels[int(lod)]
+        D, H, W = d.shape
+        self.taps += 1
+        x = F(F(c[0] * F(W)) - F(0.5)); y = F(F(c[1] * F(H)) - F(0.5)); z = F(F(c[2] * F(D)) - F(0.5))
+        fx, fy, fz = F(math.floor(x)), F(math.floor(y)), F(math.floor(z))
+        ax, ay, az = F(x - fx), F(y - fy), F(z - fz)
+        ix, iy, iz = int(fx), int(fy), int(fz)
+        x0, x1, y0, y1, z0, z1 = ix % W, (ix + 1) % W, iy % H, (iy + 1) % H, iz % D, (iz + 1) % D
+        t = lambda xx, yy, zz: F(d[zz, yy, xx])
+        c00 = lerp(t(x0, y0, z0), t(x1, y0, z0), ax); c10 = lerp(t(x0, y1, z0), t(x1, y1, z0), ax)
+        c01 = lerp(t(x0, y0, z1), t(x1, y0, z1), ax); c11 = lerp(t(x0, y1, z1), t(x1, y1, z1), ax)
+        r = lerp(lerp(c00, c10, ay), lerp(c01, c11, ay), az)
+        return [r, F(0), F(0), F(1)]
+
+
+class StorageImage3D:
+    """image3D r16f: uint16 array [d][h][w]; out-of-bounds accesses are discarded / read zero (robust image access)."""
+
+    def __init__(self, bits_u16):
+        self.b = bits_u16
+
+    def _in(self, c):
+        z, y, x = s32(c[2]), s32(c[1]), s32(c[0])
+        D, H, W = self.b.shape
+        return (z, y, x) if (0 <= z < D and 0 <= y < H and 0 <= x < W) else None
+
+    def write(self, c, texel):
+        i = self._in(c)
+        if i is not None:
+            self.b[i] = f2h(texel[0])
+
+    def read(self, c):
+        i = self._in(c)
+        return [h2f(self.b[i]) if i is not None else F(0), F(0), F(0), F(1)]
+
+
 class StorageImage:
     """image2D with an fp16 format (rgba16f / rg16f): uint16 array [h][w][channels]."""
 
@@ -525,7 +571,10 @@ class Invocation:
         if name in ("CopyObject", "CopyLogical"): return copyv(x(2))
         if name == "Undef": return m.zero(a[0])
         if name == "Image": return x(2)
-        if name == "ImageSampleExplicitLod": return x(2).sample(x(3))
+        if name == "ImageSampleExplicitLod":
+            if isinstance(x(2), Texture3DMips):  # operands: mask (a[4], Lod = 0x2), lod id (a[5])
+                return x(2).sample(x(3), x(5) if (a[4] & 2) else F(0))
+            return x(2).sample(x(3))
         if name == "ImageGather": return x(2).gather(x(3), s32(x(4)))
         if name == "ImageFetch": return x(2).fetch(x(3))
         if name == "ImageQuerySizeLod": return [x(2).W, x(2).H]

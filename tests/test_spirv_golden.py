@@ -99,3 +99,46 @@ def test_sample_probe_matches_shipped_spirv(oracle):
     want = g["out"]
     assert (want[..., 3] > 0).sum() > 150 and np.isfinite(want).all()
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), f"max abs diff {np.abs(got - want).max()}"
+
+
+def test_sdf_build_matches_shipped_spirv(oracle):
+    """Row f3: the oracle's restatement of SDFRasterizeModel(.NoRead) and GlobalSDFMipmap against outputs of the reference's shipped
+    SPIR-V (tests/golden/make_spirv_golden_sdfbuild.py): two cascades (mesh mip 0 / 1, x offset), NoRead then READ_DISTANCE on the same
+    chunk, the 4x min-downsample and two flood passes.  Bit for bit on every voxel the golden run dispatched."""
+    from tests.golden import make_spirv_golden_sdfbuild as g
+
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "spirv_golden_sdfbuild.npz"))
+    meshes = g.golden_meshes()
+    RES, CASC = g.RES, g.CASC
+    one = np.float16(1.0).view(np.uint16)
+    mask = np.zeros((RES, RES, RES), dtype=bool)
+    for gx, gy, gz in gold["groups"]:
+        mask[gz * 8:gz * 8 + 8, gy * 8:gy * 8 + 8, gx * 8:gx * 8 + 8] = True
+    sdf = np.full((RES, RES, RES * CASC), one, dtype=np.uint16)
+    objs = [[oracle.sdf_object_data(m, c) for m in meshes] for c in range(CASC)]
+    (c0, D0), (c1, D1) = g.cascades()
+
+    def check(stage, cascade):
+        want, got = gold[stage][:, :, cascade * RES:(cascade + 1) * RES], sdf[:, :, cascade * RES:(cascade + 1) * RES]
+        assert np.array_equal(got[mask], want[mask]), f"{stage}: {(got[mask] != want[mask]).sum()} of {mask.sum()} voxels differ"
+        got[~mask] = want[~mask]  # voxels the golden run did not dispatch keep its (cleared) value for the next stage
+
+    oracle.sdf_rasterize_chunk(sdf, objs[0], meshes, 0, c0, D0, RES, 0, (0, 0, 0), [0, 1], read=False)
+    check("c0_noread", 0)
+    oracle.sdf_rasterize_chunk(sdf, objs[0], meshes, 0, c0, D0, RES, 0, (0, 0, 0), [2], read=True)
+    check("c0_read", 0)
+    oracle.sdf_rasterize_chunk(sdf, objs[1], meshes, 1, c1, D1, RES, 1, (0, 0, 0), [2, 0, 1], read=False)
+    check("c1_noread", 1)
+    assert np.array_equal(sdf, gold["c1_noread"])
+    assert (sdf != one).sum() > 10000 and sdf.view(np.float16).min() < 0  # the meshes really landed in the volume
+
+    mres = RES // 4
+    mip = np.full((mres, mres, mres * CASC), one, dtype=np.uint16)
+    tmp = np.full((mres, mres, mres), one, dtype=np.uint16)
+    for c, (_, D) in enumerate(g.cascades()):
+        oracle.sdf_mip_pass(sdf, mip, mres, RES, 4, c * RES, c * mres, 2 * D)
+    assert np.array_equal(mip, gold["mip_down"]), f"{(mip != gold['mip_down']).sum()} mip texels differ"
+    oracle.sdf_mip_pass(mip, tmp, mres, mres, 1, mres, 0, 2 * D1)
+    assert np.array_equal(tmp, gold["flood_tmp"])
+    oracle.sdf_mip_pass(tmp, mip, mres, mres, 1, 0, mres, 2 * D1)
+    assert np.array_equal(mip, gold["flood_mip"])
