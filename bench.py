@@ -317,21 +317,37 @@ def run_lux(args):
         pin_light = torch.empty(light_bytes, dtype=torch.uint8).pin_memory()
         pin_light.copy_(sc.light.reshape(-1).view(torch.uint8).cpu())
         irr_row_bytes, dep_row_bytes = u.irradianceTextureWidth * 8, u.depthTextureWidth * 4
-        pin_irr = torch.empty(st.irradianceRowCount * irr_row_bytes, dtype=torch.uint8).pin_memory()
-        pin_dep = torch.empty(st.depthRowCount * dep_row_bytes, dtype=torch.uint8).pin_memory()
+        # two sets of pinned result buffers: frame f's rows land while frame f+1 computes; the host waits for frame f-1's copies
+        # before it issues frame f+1, i.e. it receives EVERY frame's atlases, one frame late (how a renderer consumes them)
+        pin_irr = [torch.empty(st.irradianceRowCount * irr_row_bytes, dtype=torch.uint8).pin_memory() for _ in range(2)]
+        pin_dep = [torch.empty(st.depthRowCount * dep_row_bytes, dtype=torch.uint8).pin_memory() for _ in range(2)]
+        fences = []
+
         def e2e_step(f):
-            pipe.update_surface_light_cache_ptr(pin_light.data_ptr())  # H2D of this frame's light cache through the C ABI
+            if not args.e2e_skip_h2d:
+                pipe.update_surface_light_cache_ptr(pin_light.data_ptr())  # H2D of this frame's light cache through the C ABI
             step(f)
-            pipe.download_rows_async_ptr(abi.BUF_IRRADIANCE, st.irradianceRowBegin, st.irradianceRowCount, pin_irr.data_ptr())
-            pipe.download_rows_async_ptr(abi.BUF_DEPTH, st.depthRowBegin, st.depthRowCount, pin_dep.data_ptr())
-            pipe.synchronize()  # the caller consumes the atlases on the host every frame
+            k = f & 1
+            if not args.e2e_skip_d2h:
+                pipe.download_rows_async_ptr(abi.BUF_IRRADIANCE, st.irradianceRowBegin, st.irradianceRowCount, pin_irr[k].data_ptr())
+                pipe.download_rows_async_ptr(abi.BUF_DEPTH, st.depthRowBegin, st.depthRowCount, pin_dep[k].data_ptr())
+            fences.append(pipe.download_fence())
+            if len(fences) > 1:
+                pipe.wait_fence(fences.pop(0))  # frame f-1 is on the host now
+
+        def e2e_drain():
+            while fences:
+                pipe.wait_fence(fences.pop(0))
+            pipe.synchronize()
 
         for _ in range(max(1, args.warmup // 2)):
             e2e_step(f); f += 1
+        e2e_drain()
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
             e2e_step(f); f += 1
+        e2e_drain()  # the last frame's atlases are on the host inside the timed region too
         barrier()
         e2e_s = time.perf_counter() - t0
         te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
@@ -341,7 +357,7 @@ def run_lux(args):
         e2e_value = P * R * args.steps / e2e_s
 
 
-        d2h_bytes = int(pin_irr.numel() + pin_dep.numel())
+        d2h_bytes = int(pin_irr[0].numel() + pin_dep[0].numel())
     # ---- serialized stage pass: same workload, one batch on one stream, CUDA events around every stage -----------------------
     pipe.close()
     views.clear()
@@ -420,7 +436,7 @@ def run_lux(args):
             "clocks": clocks,
             "e2e": None if e2e_value is None else {"value": e2e_value, "unit": UNIT, "ms_per_update": e2e_s / args.steps * 1e3,
                     "h2d_bytes_per_step": light_bytes + 64, "d2h_bytes_per_step": d2h_bytes,
-                    "note": "per rank: light cache H2D from pinned memory, own atlas rows D2H into pinned memory, host sync every step"},
+                    "note": "per rank and per step: light cache H2D from pinned memory, own atlas rows D2H into pinned memory; the host waits for frame f-1's rows while frame f computes (every frame delivered, one frame late), all copies complete inside the timed region"},
             "gpu_launches": int(launches),
             "wall_s_timed_region": t_wall,
         }
@@ -449,6 +465,8 @@ def main():
     ap.add_argument("--trace", default="texture", choices=["texture", "loads", "simple"],
                     help="SDF read path / trace kernel variant: wavefront + tld4 gathers (default), wavefront + fp16 loads, thread-per-ray")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-skip-h2d", action="store_true", help="diagnosis only: e2e leg without the light-cache upload (the printed e2e is then NOT an end-to-end number)")
+    ap.add_argument("--e2e-skip-d2h", action="store_true", help="diagnosis only: e2e leg without the atlas downloads")
     ap.add_argument("--emulate-shard", default=None, help="r/w: run shard r of w on one GPU without any collective (profiling aid)")
     ap.add_argument("--sync-allgather", action="store_true", help="all-gather on the compute stream (no overlap with the next trace)")
     ap.add_argument("--no-pipeline", action="store_true", help="A/B: one batch on one stream instead of two-stream probe batches")

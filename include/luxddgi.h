@@ -319,6 +319,10 @@ LUX_API int lux_ddgi_download(LuxDDGIContext* ctx, LuxBufferId id, void* host, s
 LUX_API int lux_ddgi_download_async(LuxDDGIContext* ctx, LuxBufferId id, void* pinnedHost, size_t bytes);
 /* Rows [rowBegin, rowBegin + rowCount) of an atlas (e.g. the shard's own rows from lux_ddgi_get_state) into pinned memory. */
 LUX_API int lux_ddgi_download_rows_async(LuxDDGIContext* ctx, LuxBufferId id, int32_t rowBegin, int32_t rowCount, void* pinnedHost);
+/* Frame-pipelined consumers: a fence marks "every download enqueued so far"; waiting on the fence of frame f-1 while frame f computes
+ * keeps the device busy and still delivers every frame's atlases to the host (one frame of latency).  Up to 8 fences may be pending. */
+LUX_API int lux_ddgi_download_fence(LuxDDGIContext* ctx, uint64_t* fence);
+LUX_API int lux_ddgi_wait_fence(LuxDDGIContext* ctx, uint64_t fence);
 /* Overwrite the ray buffers (this shard's rows) — what probe_update consumes is whatever these hold, exactly as the
  * reference's blend reads the iRadiance / iDirectionDistance images (ProbeUpdate.glsl:53-64).  Lets a host (or a test)
  * run the blend stage on rays produced elsewhere. */

@@ -119,7 +119,10 @@ struct LuxDDGIContext
     // timers
     cudaEvent_t   ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // copy engine overlap: host<->device transfers run on their own stream, ordered against the kernels by events
-    cudaStream_t  copyStream = nullptr;
+    cudaStream_t  copyStream = nullptr;   // host -> device (light cache)
+    cudaStream_t  downStream = nullptr;   // device -> host (atlas rows): its own stream so both copy engines run at once
+    cudaEvent_t   fences[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    uint64_t      fenceSeq  = 0;
     cudaEvent_t   evLightReady = nullptr, evShadeDone = nullptr, evIrrDone = nullptr, evDepthDone = nullptr, evCopyDone = nullptr;
     bool          lightPending = false;
     bool          timed = false;
@@ -673,6 +676,9 @@ int lux_ddgi_create(const LuxDDGIUniform* uniform, const LuxDDGICreateInfo* info
     for (auto& ev : c->ev)
         cudaEventCreate(&ev);
     cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&c->downStream, cudaStreamNonBlocking);
+    for (cudaEvent_t& e : c->fences)
+        cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     for (cudaEvent_t* e : {&c->evLightReady, &c->evShadeDone, &c->evIrrDone, &c->evDepthDone, &c->evCopyDone, &c->evFork, &c->evJoin, &c->evWeights})
         cudaEventCreateWithFlags(e, cudaEventDisableTiming);
     cudaStreamCreateWithFlags(&c->auxStream, cudaStreamNonBlocking);
@@ -698,6 +704,8 @@ int lux_ddgi_destroy(LuxDDGIContext* c)
     cudaStreamSynchronize(c->stream);
     if (c->copyStream)
         cudaStreamSynchronize(c->copyStream);
+    if (c->downStream)
+        cudaStreamSynchronize(c->downStream);
     if (c->auxStream)
         cudaStreamSynchronize(c->auxStream);
     DeviceBuffer* all[] = {&c->radiance, &c->directionDepth, &c->irradiance[0], &c->irradiance[1], &c->depth[0], &c->depth[1],
@@ -714,6 +722,11 @@ int lux_ddgi_destroy(LuxDDGIContext* c)
             cudaEventDestroy(e);
     if (c->copyStream)
         cudaStreamDestroy(c->copyStream);
+    if (c->downStream)
+        cudaStreamDestroy(c->downStream);
+    for (cudaEvent_t e : c->fences)
+        if (e)
+            cudaEventDestroy(e);
     if (c->auxStream)
         cudaStreamDestroy(c->auxStream);
     if (c->ownStream)
@@ -1260,7 +1273,6 @@ int lux_ddgi_update(LuxDDGIContext* c, const float orientation[16])
         int rc = trace_rays::setup(*c, push);
         if (rc != LUX_OK)
             return rc;
-        cudaStreamWaitEvent(c->stream, c->evCopyDone, 0); // row downloads of earlier frames must have left the atlases
         cudaEventRecord(c->evFork, c->stream);
         cudaStreamWaitEvent(c->auxStream, c->evFork, 0);
         probe_update::weights(*c, (const uint2*)c->dirsHalf.ptr, c->auxStream);
@@ -1274,6 +1286,7 @@ int lux_ddgi_update(LuxDDGIContext* c, const float orientation[16])
                 cudaEventRecord(c->evShadeDone, s);
             if (s == c->stream && b == 0)
                 cudaStreamWaitEvent(s, c->evWeights, 0);
+            cudaStreamWaitEvent(s, c->evCopyDone, 0); // only the blend overwrites atlas rows an earlier frame's download may still read
             probe_update::launchBatch(*c, c->batches[b], s, single ? c->evIrrDone : nullptr, single ? c->evDepthDone : nullptr);
         }
         cudaEventRecord(c->evJoin, c->auxStream);
@@ -1313,6 +1326,7 @@ int lux_ddgi_synchronize(LuxDDGIContext* c)
     CHECK_CTX(c);
     LUX_CUDA(cudaStreamSynchronize(c->stream));
     LUX_CUDA(cudaStreamSynchronize(c->copyStream));
+    LUX_CUDA(cudaStreamSynchronize(c->downStream));
     return LUX_OK;
 }
 
@@ -1406,9 +1420,31 @@ int lux_ddgi_download_rows_async(LuxDDGIContext* c, LuxBufferId id, int32_t rowB
         return fail(LUX_ERR_INVALID_ARG, "rows [%d,%d) outside the atlas (%d rows)", rowBegin, rowBegin + rowCount, rows);
     // on the copy stream, as soon as the blend kernel that produced this atlas has finished
     const bool isIrr = (id == LUX_BUF_IRRADIANCE || id == LUX_BUF_IRRADIANCE_PREV);
-    LUX_CUDA(cudaStreamWaitEvent(c->copyStream, isIrr ? c->evIrrDone : c->evDepthDone, 0));
-    LUX_CUDA(cudaMemcpyAsync(pinnedHost, (const char*)b->ptr + rowBegin * rowBytes, rowCount * rowBytes, cudaMemcpyDeviceToHost, c->copyStream));
-    LUX_CUDA(cudaEventRecord(c->evCopyDone, c->copyStream));
+    LUX_CUDA(cudaStreamWaitEvent(c->downStream, isIrr ? c->evIrrDone : c->evDepthDone, 0));
+    LUX_CUDA(cudaMemcpyAsync(pinnedHost, (const char*)b->ptr + rowBegin * rowBytes, rowCount * rowBytes, cudaMemcpyDeviceToHost, c->downStream));
+    LUX_CUDA(cudaEventRecord(c->evCopyDone, c->downStream));
+    return LUX_OK;
+}
+
+int lux_ddgi_download_fence(LuxDDGIContext* c, uint64_t* fence)
+{
+    CHECK_CTX(c);
+    if (!fence)
+        return fail(LUX_ERR_INVALID_ARG, "null fence");
+    const uint64_t id = ++c->fenceSeq;
+    LUX_CUDA(cudaEventRecord(c->fences[id % 8], c->downStream));
+    *fence = id;
+    return LUX_OK;
+}
+
+int lux_ddgi_wait_fence(LuxDDGIContext* c, uint64_t fence)
+{
+    CHECK_CTX(c);
+    if (fence == 0 || fence > c->fenceSeq)
+        return fail(LUX_ERR_INVALID_ARG, "unknown fence %llu", (unsigned long long)fence);
+    if (c->fenceSeq - fence >= 8)
+        return LUX_OK; // its slot has been reused by a later fence on the same in-order stream: long complete
+    LUX_CUDA(cudaEventSynchronize(c->fences[fence % 8]));
     return LUX_OK;
 }
 

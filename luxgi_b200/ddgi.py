@@ -25,7 +25,7 @@ EXPORTS = [
     "lux_ddgi_border_update", "lux_ddgi_end_frame", "lux_ddgi_update", "lux_ddgi_synchronize", "lux_ddgi_get_buffer",
     "lux_ddgi_download", "lux_ddgi_download_async", "lux_ddgi_download_rows_async", "lux_ddgi_set_ray_buffers", "lux_ddgi_restore", "lux_ddgi_get_state", "lux_ddgi_shard_layout",
     "lux_ddgi_get_stage_ms", "lux_ddgi_sample_irradiance", "lux_ddgi_sample_probe", "lux_ddgi_indirect_light",
-    "lux_ddgi_get_surface_light_cache", "lux_ddgi_build_global_sdf", "lux_ddgi_build_sdf_mip", "lux_ddgi_sdf_file_read",
+    "lux_ddgi_get_surface_light_cache", "lux_ddgi_build_global_sdf", "lux_ddgi_build_sdf_mip", "lux_ddgi_sdf_file_read", "lux_ddgi_download_fence", "lux_ddgi_wait_fence",
 ]
 
 
@@ -77,6 +77,8 @@ def load():
         "lux_ddgi_get_surface_light_cache": [vp, C.POINTER(vp), C.POINTER(sz)],
         "lux_ddgi_build_global_sdf": [vp, C.POINTER(abi.GlobalSDFData), C.POINTER(abi.MeshSDF), i32, C.c_float],
         "lux_ddgi_build_sdf_mip": [vp],
+        "lux_ddgi_download_fence": [vp, C.POINTER(C.c_uint64)],
+        "lux_ddgi_wait_fence": [vp, C.c_uint64],
         "lux_ddgi_sdf_file_read": [C.c_char_p, C.POINTER(C.c_uint32 * 3), C.POINTER(i32), C.POINTER(C.c_uint64), vp],
     }
     for name, argtypes in sig.items():
@@ -312,6 +314,14 @@ class DDGIPipeline:
 
     def download_rows_async_ptr(self, buf, row_begin, row_count, host_ptr):
         _check(self._lib.lux_ddgi_download_rows_async(self._h, buf, int(row_begin), int(row_count), C.c_void_p(host_ptr)))
+
+    def download_fence(self) -> int:
+        f = C.c_uint64()
+        _check(self._lib.lux_ddgi_download_fence(self._h, C.byref(f)))
+        return f.value
+
+    def wait_fence(self, fence: int):
+        _check(self._lib.lux_ddgi_wait_fence(self._h, fence))
 
     def restore(self, irradiance, depth, frames, ping_pong):
         a, b = _as_host(irradiance), _as_host(depth)

@@ -413,3 +413,32 @@ def test_pipelined_probe_batches_match_oracle(oracle, monkeypatch, cfg, batch_ra
     assert np.array_equal(pipe.radiance, serial.radiance)
     pipe.close()
     serial.close()
+
+
+def test_pipelined_row_downloads_with_fences(oracle):
+    """Frame-pipelined consumer (bench.py's e2e loop): rows of frame f are copied on the download stream while frame f+1 computes;
+    waiting on frame f's fence one frame later delivers exactly frame f's atlas rows."""
+    import torch
+
+    sc = scenes.build("city64")
+    orc = oracle.OraclePipeline(sc)
+    pipe = ddgi.DDGIPipeline(sc.uniform)
+    pipe.set_scene(sc)
+    st = pipe.state()
+    u = sc.uniform
+    bufs = [torch.empty(st.irradianceRowCount * u.irradianceTextureWidth * 8, dtype=torch.uint8).pin_memory() for _ in range(2)]
+    fences, wants = [], []
+    for f in range(4):
+        rot = scenes.frame_rotation(f)
+        orc.update(rot)
+        wants.append(orc.irradiance[st.irradianceRowBegin:st.irradianceRowBegin + st.irradianceRowCount].copy())
+        pipe.update(rot)
+        pipe.download_rows_async_ptr(abi.BUF_IRRADIANCE, st.irradianceRowBegin, st.irradianceRowCount, bufs[f & 1].data_ptr())
+        fences.append(pipe.download_fence())
+        if f >= 1:
+            pipe.wait_fence(fences[f - 1])
+            got = bufs[(f - 1) & 1].numpy().view(np.uint16).reshape(wants[f - 1].shape)
+            assert np.array_equal(got, wants[f - 1]), f"frame {f - 1}"
+    pipe.wait_fence(fences[-1])
+    assert np.array_equal(bufs[1].numpy().view(np.uint16).reshape(wants[3].shape), wants[3])
+    pipe.close()
