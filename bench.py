@@ -235,6 +235,12 @@ def run_lux(args):
     # times and the kernel roofline come from a second, serialized pass below (LUX_DDGI_FLAG_STAGE_TIMERS = one batch, one stream).
     pipe = ddgi.DDGIPipeline(u, device=local, rank=shard_rank, world=shard_world, flags=flags, stream=stream.cuda_stream)
     pipe.set_scene(sc)
+    comm = None
+    if world > 1 and args.allgather == "lib":  # the exchange step behind the C ABI: lux_ddgi_update all-gathers the rows itself
+        from luxgi_b200 import nccl
+
+        comm = nccl.NcclComm(rank, world, local)
+        pipe.set_nccl_comm(comm.ptr)
     st = pipe.state()
     P, R = sc.probes, u.raysPerProbe
     rot_cache = {}
@@ -261,10 +267,10 @@ def run_lux(args):
         """One volume update.  At N > 1 the all-gather of the atlases written by step f runs on its own stream and overlaps the
         trace of step f+1 (the trace never reads the atlases); step f+2 is the first to overwrite the rows it sends from, so
         that step waits for it."""
-        if world > 1 and not args.sync_allgather and len(ag_done) >= 2:
+        if world > 1 and comm is None and not args.sync_allgather and len(ag_done) >= 2:
             stream.wait_event(ag_done[-2])
         pipe.update(rot_of(f))
-        if world > 1:  # one in-place all-gather per atlas (SURVEY §8e): own slab rows -> every rank's full atlas
+        if world > 1 and comm is None:  # --allgather torch: the same exchange issued by the host through torch.distributed
             side = stream if args.sync_allgather else ag_stream
             if side is not stream:
                 ev = torch.cuda.Event()
@@ -360,6 +366,8 @@ def run_lux(args):
         d2h_bytes = int(pin_irr[0].numel() + pin_dep[0].numel())
     # ---- serialized stage pass: same workload, one batch on one stream, CUDA events around every stage -----------------------
     pipe.close()
+    if comm is not None:
+        comm.destroy()
     views.clear()
     pipe = ddgi.DDGIPipeline(u, device=local, rank=shard_rank, world=shard_world, flags=flags | abi.FLAG_STAGE_TIMERS, stream=stream.cuda_stream)
     pipe.set_scene(sc)
@@ -423,7 +431,8 @@ def run_lux(args):
             "dtype": "f32", "data": "synthetic",
             "config": dict(workload_desc(args.workload, sc), parallelism=f"zslab{world}", l2_policy="inputs larger than L2 (no flush)",
                            sharding="probe z-slabs, SDF + surface cache replicated, in-place NCCL all-gather of atlas rows per step"
-                           + ("" if world == 1 else (" (on the compute stream)" if args.sync_allgather else " overlapped with the next step's trace"))),
+                           + ("" if world == 1 else ((" issued by lux_ddgi_update on the library's gather stream" if args.allgather == "lib" else " issued by the host (torch.distributed)")
+                                                     + (" on the compute stream" if args.sync_allgather else ", overlapped with the next step's trace")))),
             "stage_ms": {"setup": setup_ms / args.steps, "trace": trace_launch_ms, "march": march_launch_ms, "shade": shade_launch_ms,
                          "blend_border": blend_launch_ms,
                          "update_minus_stage_sum": ms_per_step - (setup_ms + trace_ms + blend_ms) / args.steps,
@@ -468,6 +477,8 @@ def main():
     ap.add_argument("--e2e-skip-h2d", action="store_true", help="diagnosis only: e2e leg without the light-cache upload (the printed e2e is then NOT an end-to-end number)")
     ap.add_argument("--e2e-skip-d2h", action="store_true", help="diagnosis only: e2e leg without the atlas downloads")
     ap.add_argument("--emulate-shard", default=None, help="r/w: run shard r of w on one GPU without any collective (profiling aid)")
+    ap.add_argument("--allgather", default="lib", choices=["lib", "torch"],
+                    help="N > 1: exchange inside lux_ddgi_update (ncclComm bound through the C ABI, default) or issued by this script through torch.distributed")
     ap.add_argument("--sync-allgather", action="store_true", help="all-gather on the compute stream (no overlap with the next trace)")
     ap.add_argument("--no-pipeline", action="store_true", help="A/B: one batch on one stream instead of two-stream probe batches")
     ap.add_argument("--unsorted", action="store_true", help="A/B: shade hits in ray order (no counting sort by culling chunk)")

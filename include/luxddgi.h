@@ -310,6 +310,12 @@ LUX_API int lux_ddgi_end_frame(LuxDDGIContext* ctx);     /* pingPong ^= 1; frame
  * (column-major mat4, as pushed at DDGIRenderer.cpp:271-272).  Asynchronous on the context's stream. */
 LUX_API int lux_ddgi_update(LuxDDGIContext* ctx, const float orientation[16]);
 
+/* Exchange step of a sharded volume.  `ncclComm` is the caller's ncclComm_t over the `world` ranks given at create time
+ * (rank order = shard order).  With a communicator bound, lux_ddgi_update ends with one in-place ncclAllGather per atlas (own slab rows ->
+ * every rank's full atlas) on an internal stream: it overlaps the next update's trace, the next blend into that atlas pair waits for it, and
+ * every reader of whole atlases (downloads, lux_ddgi_sample_*, lux_ddgi_indirect_light, lux_ddgi_synchronize) is ordered after it.
+ * libnccl.so.2 is bound with dlopen on first use.  NULL unbinds (the host then exchanges rows itself, see lux_ddgi_get_state). */
+LUX_API int lux_ddgi_set_nccl_comm(LuxDDGIContext* ctx, void* ncclComm);
 LUX_API int lux_ddgi_synchronize(LuxDDGIContext* ctx);
 
 /* Outputs.  Device pointers stay valid until destroy; `bytes` may be NULL. */

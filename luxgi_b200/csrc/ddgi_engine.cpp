@@ -9,6 +9,7 @@
 //   lux::ddgi::end_frame::system           :333-343
 // There is no CPU fallback: creation fails with LUX_ERR_NO_DEVICE when no sm_100-class GPU is usable.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <cmath>
@@ -121,6 +122,11 @@ struct LuxDDGIContext
     // copy engine overlap: host<->device transfers run on their own stream, ordered against the kernels by events
     cudaStream_t  copyStream = nullptr;   // host -> device (light cache)
     cudaStream_t  downStream = nullptr;   // device -> host (atlas rows): its own stream so both copy engines run at once
+    // exchange step: in-place NCCL all-gather of the updated atlas rows, on its own stream
+    void*         ncclComm = nullptr;
+    cudaStream_t  gatherStream = nullptr;
+    cudaEvent_t   evBlendDone = nullptr, evGather[2] = {nullptr, nullptr};
+    bool          gatherPending[2] = {false, false};
     cudaEvent_t   fences[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     uint64_t      fenceSeq  = 0;
     cudaEvent_t   evLightReady = nullptr, evShadeDone = nullptr, evIrrDone = nullptr, evDepthDone = nullptr, evCopyDone = nullptr;
@@ -128,6 +134,39 @@ struct LuxDDGIContext
     bool          timed = false;
     uint64_t      launches = 0;
 };
+
+// NCCL is bound at run time (dlopen): the library has no link-time dependency on it and single-GPU users never load it.
+namespace {
+struct NcclApi
+{
+    void* lib = nullptr;
+    int (*allGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    int (*groupStart)()                                                     = nullptr;
+    int (*groupEnd)()                                                       = nullptr;
+    const char* (*getErrorString)(int)                                      = nullptr;
+};
+NcclApi* ncclApi()
+{
+    static NcclApi api;
+    static bool    tried = false;
+    if (!tried)
+    {
+        tried = true;
+        // an already loaded libnccl.so.2 (e.g. the one a host framework brought) is reused: same soname
+        void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (lib)
+        {
+            api.allGather      = reinterpret_cast<decltype(api.allGather)>(dlsym(lib, "ncclAllGather"));
+            api.groupStart     = reinterpret_cast<decltype(api.groupStart)>(dlsym(lib, "ncclGroupStart"));
+            api.groupEnd       = reinterpret_cast<decltype(api.groupEnd)>(dlsym(lib, "ncclGroupEnd"));
+            api.getErrorString = reinterpret_cast<decltype(api.getErrorString)>(dlsym(lib, "ncclGetErrorString"));
+            if (api.allGather && api.groupStart && api.groupEnd && api.getErrorString)
+                api.lib = lib;
+        }
+    }
+    return api.lib ? &api : nullptr;
+}
+} // namespace
 
 namespace lux {
 namespace ddgi {
@@ -510,6 +549,8 @@ static int system(LuxDDGIContext& c)
         return fail(LUX_ERR_NOT_READY, "probe_update: ray buffers are empty (call lux_ddgi_trace_rays or lux_ddgi_set_ray_buffers)");
     weights(c, (const uint2*)c.directionDepth.ptr, c.stream); // the directions as stored in the ray buffer (row of the first probe)
     cudaStreamWaitEvent(c.stream, c.evCopyDone, 0); // row downloads of earlier frames must have left the atlases
+    if (c.gatherPending[1 - c.pingPong])               // ... and so must the all-gather that last read / wrote this pair
+        cudaStreamWaitEvent(c.stream, c.evGather[1 - c.pingPong], 0);
     const LuxDDGIContext::Batch whole{0, c.probeCount, 0, 0, 0};
     launchBatch(c, whole, c.stream, c.evIrrDone, c.evDepthDone);
     mark(c, 3);
@@ -724,6 +765,14 @@ int lux_ddgi_destroy(LuxDDGIContext* c)
         cudaStreamDestroy(c->copyStream);
     if (c->downStream)
         cudaStreamDestroy(c->downStream);
+    if (c->gatherStream)
+    {
+        cudaStreamSynchronize(c->gatherStream);
+        cudaStreamDestroy(c->gatherStream);
+        for (cudaEvent_t e : {c->evBlendDone, c->evGather[0], c->evGather[1]})
+            if (e)
+                cudaEventDestroy(e);
+    }
     for (cudaEvent_t e : c->fences)
         if (e)
             cudaEventDestroy(e);
@@ -1256,6 +1305,42 @@ int lux_ddgi_end_frame(LuxDDGIContext* c)
     return end_frame::system(*c);
 }
 
+// Exchange step: one in-place all-gather per atlas (own slab rows -> every rank's full atlas) on the gather stream, right after the
+// blend.  It overlaps the next frame's trace, which never reads the atlases; the blend that next overwrites this pair waits for it.
+static int enqueueAllGather(LuxDDGIContext* c)
+{
+    if (!c->ncclComm)
+        return LUX_OK;
+    NcclApi* n = ncclApi();
+    LuxDDGIState st{};
+    shardLayout(c->uniform, c->rank, c->world, &st);
+    const int    w        = c->lastWritten;
+    const size_t irrRow   = (size_t)c->uniform.irradianceTextureWidth * 8, depRow = (size_t)c->uniform.depthTextureWidth * 4;
+    char*        irr      = (char*)c->irradiance[w].ptr;
+    char*        dep      = (char*)c->depth[w].ptr;
+    LUX_CUDA(cudaEventRecord(c->evBlendDone, c->stream));
+    LUX_CUDA(cudaStreamWaitEvent(c->gatherStream, c->evBlendDone, 0));
+    int rc = n->groupStart();
+    if (rc == 0)
+        rc = n->allGather(irr + (size_t)st.irradianceRowBegin * irrRow, irr + irrRow, (size_t)st.irradianceRowCount * irrRow, /*ncclUint8*/ 1, c->ncclComm, c->gatherStream);
+    if (rc == 0)
+        rc = n->allGather(dep + (size_t)st.depthRowBegin * depRow, dep + depRow, (size_t)st.depthRowCount * depRow, 1, c->ncclComm, c->gatherStream);
+    const int rcEnd = n->groupEnd();
+    if (rc != 0 || rcEnd != 0)
+        return fail(LUX_ERR_CUDA, "ncclAllGather: %s", n->getErrorString(rc != 0 ? rc : rcEnd));
+    LUX_CUDA(cudaEventRecord(c->evGather[w], c->gatherStream));
+    c->gatherPending[w] = true;
+    return LUX_OK;
+}
+
+// Readers of the WHOLE current atlas (consumers, full downloads) run after the exchange of the frame that wrote it.
+static void waitAllGather(LuxDDGIContext* c, cudaStream_t s)
+{
+    for (int w = 0; w < 2; w++)
+        if (c->gatherPending[w])
+            cudaStreamWaitEvent(s, c->evGather[w], 0);
+}
+
 int lux_ddgi_update(LuxDDGIContext* c, const float orientation[16])
 {
     CHECK_CTX(c);
@@ -1287,6 +1372,8 @@ int lux_ddgi_update(LuxDDGIContext* c, const float orientation[16])
             if (s == c->stream && b == 0)
                 cudaStreamWaitEvent(s, c->evWeights, 0);
             cudaStreamWaitEvent(s, c->evCopyDone, 0); // only the blend overwrites atlas rows an earlier frame's download may still read
+            if (c->gatherPending[1 - c->pingPong])     // ... or the all-gather of two frames ago
+                cudaStreamWaitEvent(s, c->evGather[1 - c->pingPong], 0);
             probe_update::launchBatch(*c, c->batches[b], s, single ? c->evIrrDone : nullptr, single ? c->evDepthDone : nullptr);
         }
         cudaEventRecord(c->evJoin, c->auxStream);
@@ -1302,6 +1389,9 @@ int lux_ddgi_update(LuxDDGIContext* c, const float orientation[16])
         c->raysValid   = true;
         c->lastWritten = 1 - c->pingPong;
         c->timed       = false;
+        rc = enqueueAllGather(c);
+        if (rc != LUX_OK)
+            return rc;
         return end_frame::system(*c);
     }
     int rc = trace_rays::system(*c, push);
@@ -1318,7 +1408,32 @@ int lux_ddgi_update(LuxDDGIContext* c, const float orientation[16])
     }
     mark(*c, 4);
     c->timed = (c->flags & LUX_DDGI_FLAG_STAGE_TIMERS) != 0;
+    rc = enqueueAllGather(c);
+    if (rc != LUX_OK)
+        return rc;
     return end_frame::system(*c);
+}
+
+int lux_ddgi_set_nccl_comm(LuxDDGIContext* c, void* ncclComm)
+{
+    CHECK_CTX(c);
+    if (!ncclComm)
+    {
+        c->ncclComm = nullptr;
+        return LUX_OK;
+    }
+    if (c->world < 2)
+        return fail(LUX_ERR_INVALID_ARG, "a communicator needs a context created with world > 1");
+    if (!ncclApi())
+        return fail(LUX_ERR_UNSUPPORTED, "libnccl.so.2 could not be loaded (%s)", dlerror() ? dlerror() : "missing symbols");
+    if (!c->gatherStream)
+    {
+        LUX_CUDA(cudaStreamCreateWithFlags(&c->gatherStream, cudaStreamNonBlocking));
+        for (cudaEvent_t* e : {&c->evBlendDone, &c->evGather[0], &c->evGather[1]})
+            LUX_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    }
+    c->ncclComm = ncclComm;
+    return LUX_OK;
 }
 
 int lux_ddgi_synchronize(LuxDDGIContext* c)
@@ -1327,6 +1442,8 @@ int lux_ddgi_synchronize(LuxDDGIContext* c)
     LUX_CUDA(cudaStreamSynchronize(c->stream));
     LUX_CUDA(cudaStreamSynchronize(c->copyStream));
     LUX_CUDA(cudaStreamSynchronize(c->downStream));
+    if (c->gatherStream)
+        LUX_CUDA(cudaStreamSynchronize(c->gatherStream));
     return LUX_OK;
 }
 
@@ -1373,6 +1490,7 @@ int lux_ddgi_download(LuxDDGIContext* c, LuxBufferId id, void* host, size_t byte
         return rc;
     if (bytes != b->bytes)
         return fail(LUX_ERR_INVALID_ARG, "size mismatch: buffer holds %zu bytes, caller passed %zu", b->bytes, bytes);
+    waitAllGather(c, c->stream);
     LUX_CUDA(cudaMemcpyAsync(host, b->ptr, bytes, cudaMemcpyDeviceToHost, c->stream));
     LUX_CUDA(cudaStreamSynchronize(c->stream));
     return LUX_OK;
@@ -1389,6 +1507,7 @@ int lux_ddgi_download_async(LuxDDGIContext* c, LuxBufferId id, void* pinnedHost,
         return rc;
     if (bytes != b->bytes)
         return fail(LUX_ERR_INVALID_ARG, "size mismatch: buffer holds %zu bytes, caller passed %zu", b->bytes, bytes);
+    waitAllGather(c, c->stream);
     LUX_CUDA(cudaMemcpyAsync(pinnedHost, b->ptr, bytes, cudaMemcpyDeviceToHost, c->stream));
     return LUX_OK;
 }
@@ -1421,6 +1540,13 @@ int lux_ddgi_download_rows_async(LuxDDGIContext* c, LuxBufferId id, int32_t rowB
     // on the copy stream, as soon as the blend kernel that produced this atlas has finished
     const bool isIrr = (id == LUX_BUF_IRRADIANCE || id == LUX_BUF_IRRADIANCE_PREV);
     LUX_CUDA(cudaStreamWaitEvent(c->downStream, isIrr ? c->evIrrDone : c->evDepthDone, 0));
+    {
+        LuxDDGIState st{};
+        shardLayout(c->uniform, c->rank, c->world, &st);
+        const int ownBegin = isIrr ? st.irradianceRowBegin : st.depthRowBegin, ownCount = isIrr ? st.irradianceRowCount : st.depthRowCount;
+        if (rowBegin < ownBegin || rowBegin + rowCount > ownBegin + ownCount)
+            waitAllGather(c, c->downStream); // rows of other ranks arrive with the exchange
+    }
     LUX_CUDA(cudaMemcpyAsync(pinnedHost, (const char*)b->ptr + rowBegin * rowBytes, rowCount * rowBytes, cudaMemcpyDeviceToHost, c->downStream));
     LUX_CUDA(cudaEventRecord(c->evCopyDone, c->downStream));
     return LUX_OK;
@@ -1506,6 +1632,7 @@ static int stageToDevice(LuxDDGIContext* c, const void* src, size_t bytes, LuxMe
 int lux_ddgi_sample_irradiance(LuxDDGIContext* c, int32_t count, const float* P, const float* N, const float* Wo, float* out, LuxMemKind kind)
 {
     CHECK_CTX(c);
+    waitAllGather(c, c->stream);
     if (count < 0 || !P || !N || !Wo || !out)
         return fail(LUX_ERR_INVALID_ARG, "bad sample_irradiance arguments");
     if (c->frames == 0)
@@ -1539,6 +1666,7 @@ int lux_ddgi_sample_probe(LuxDDGIContext* c, int32_t width, int32_t height, cons
                           const float cameraPosition[4], const float viewProjInv[16], float* outRGBA32F, LuxMemKind kind)
 {
     CHECK_CTX(c);
+    waitAllGather(c, c->stream);
     if (width <= 0 || height <= 0 || !depthD32F || !normalsRGBA32F || !cameraPosition || !viewProjInv || !outRGBA32F)
         return fail(LUX_ERR_INVALID_ARG, "bad sample_probe arguments");
     if (c->frames == 0)
@@ -1571,6 +1699,7 @@ int lux_ddgi_indirect_light(LuxDDGIContext* c, const void* baseLightRGBA16F, int
                             LuxMemKind kind)
 {
     CHECK_CTX(c);
+    waitAllGather(c, c->stream);
     if (!c->hasAtlas)
         return fail(LUX_ERR_NOT_READY, "no surface cache bound");
     if (c->frames == 0)

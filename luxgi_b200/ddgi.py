@@ -25,7 +25,7 @@ EXPORTS = [
     "lux_ddgi_border_update", "lux_ddgi_end_frame", "lux_ddgi_update", "lux_ddgi_synchronize", "lux_ddgi_get_buffer",
     "lux_ddgi_download", "lux_ddgi_download_async", "lux_ddgi_download_rows_async", "lux_ddgi_set_ray_buffers", "lux_ddgi_restore", "lux_ddgi_get_state", "lux_ddgi_shard_layout",
     "lux_ddgi_get_stage_ms", "lux_ddgi_sample_irradiance", "lux_ddgi_sample_probe", "lux_ddgi_indirect_light",
-    "lux_ddgi_get_surface_light_cache", "lux_ddgi_build_global_sdf", "lux_ddgi_build_sdf_mip", "lux_ddgi_sdf_file_read", "lux_ddgi_download_fence", "lux_ddgi_wait_fence",
+    "lux_ddgi_get_surface_light_cache", "lux_ddgi_build_global_sdf", "lux_ddgi_build_sdf_mip", "lux_ddgi_sdf_file_read", "lux_ddgi_download_fence", "lux_ddgi_wait_fence", "lux_ddgi_set_nccl_comm",
 ]
 
 
@@ -79,6 +79,7 @@ def load():
         "lux_ddgi_build_sdf_mip": [vp],
         "lux_ddgi_download_fence": [vp, C.POINTER(C.c_uint64)],
         "lux_ddgi_wait_fence": [vp, C.c_uint64],
+        "lux_ddgi_set_nccl_comm": [vp, vp],
         "lux_ddgi_sdf_file_read": [C.c_char_p, C.POINTER(C.c_uint32 * 3), C.POINTER(i32), C.POINTER(C.c_uint64), vp],
     }
     for name, argtypes in sig.items():
@@ -314,6 +315,10 @@ class DDGIPipeline:
 
     def download_rows_async_ptr(self, buf, row_begin, row_count, host_ptr):
         _check(self._lib.lux_ddgi_download_rows_async(self._h, buf, int(row_begin), int(row_count), C.c_void_p(host_ptr)))
+
+    def set_nccl_comm(self, comm_ptr):
+        """Bind an ncclComm_t (integer address, e.g. luxgi_b200.nccl.NcclComm.ptr): lux_ddgi_update then all-gathers the atlas rows itself."""
+        _check(self._lib.lux_ddgi_set_nccl_comm(self._h, C.c_void_p(comm_ptr)))
 
     def download_fence(self) -> int:
         f = C.c_uint64()
