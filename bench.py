@@ -323,6 +323,11 @@ def run_lux(args):
         pin_light = torch.empty(light_bytes, dtype=torch.uint8).pin_memory()
         pin_light.copy_(sc.light.reshape(-1).view(torch.uint8).cpu())
         irr_row_bytes, dep_row_bytes = u.irradianceTextureWidth * 8, u.depthTextureWidth * 4
+        atlas_res = int(sc.atlas_data.resolution)
+        light_row_bytes, light_rows = atlas_res * 8, atlas_res // world
+        light_row0 = rank * light_rows
+        if comm is not None and atlas_res % world:
+            raise SystemExit("surface atlas rows do not divide by the number of GPUs")
         # two sets of pinned result buffers: frame f's rows land while frame f+1 computes; the host waits for frame f-1's copies
         # before it issues frame f+1, i.e. it receives EVERY frame's atlases, one frame late (how a renderer consumes them)
         pin_irr = [torch.empty(st.irradianceRowCount * irr_row_bytes, dtype=torch.uint8).pin_memory() for _ in range(2)]
@@ -330,8 +335,11 @@ def run_lux(args):
         fences = []
 
         def e2e_step(f):
-            if not args.e2e_skip_h2d:
-                pipe.update_surface_light_cache_ptr(pin_light.data_ptr())  # H2D of this frame's light cache through the C ABI
+            if not args.e2e_skip_h2d:  # H2D of this frame's light cache through the C ABI
+                if comm is not None:     # sharded: every rank uploads its 1/N of the rows, the library all-gathers them over NVLink
+                    pipe.update_surface_light_cache_rows_ptr(pin_light.data_ptr() + light_row0 * light_row_bytes, light_row0, light_rows)
+                else:
+                    pipe.update_surface_light_cache_ptr(pin_light.data_ptr())
             step(f)
             k = f & 1
             if not args.e2e_skip_d2h:
@@ -364,6 +372,7 @@ def run_lux(args):
 
 
         d2h_bytes = int(pin_irr[0].numel() + pin_dep[0].numel())
+    comm_used = comm is not None
     # ---- serialized stage pass: same workload, one batch on one stream, CUDA events around every stage -----------------------
     pipe.close()
     if comm is not None:
@@ -444,8 +453,8 @@ def run_lux(args):
             "roofline_stages": {k: v for k, v in roofs.items() if k != dominant and v["ms_per_launch"] > 0},
             "clocks": clocks,
             "e2e": None if e2e_value is None else {"value": e2e_value, "unit": UNIT, "ms_per_update": e2e_s / args.steps * 1e3,
-                    "h2d_bytes_per_step": light_bytes + 64, "d2h_bytes_per_step": d2h_bytes,
-                    "note": "per rank and per step: light cache H2D from pinned memory, own atlas rows D2H into pinned memory; the host waits for frame f-1's rows while frame f computes (every frame delivered, one frame late), all copies complete inside the timed region"},
+                    "h2d_bytes_per_step": (light_bytes // world if comm_used else light_bytes) + 64, "d2h_bytes_per_step": d2h_bytes,
+                    "note": "per rank and per step: light cache H2D from pinned memory (N > 1: own 1/N of its rows, all-gathered over NVLink by the library), own atlas rows D2H into pinned memory; the host waits for frame f-1's rows while frame f computes (every frame delivered, one frame late), all copies complete inside the timed region"},
             "gpu_launches": int(launches),
             "wall_s_timed_region": t_wall,
         }

@@ -295,6 +295,9 @@ LUX_API int lux_ddgi_set_surface_atlas(LuxDDGIContext* ctx, const LuxGlobalSurfa
                                const void* lightCacheRGBA16F, const float* depthD32F, LuxMemKind kind);
 /* Per-frame relight: replaces the light-cache texels only (same resolution). */
 LUX_API int lux_ddgi_update_surface_light_cache(LuxDDGIContext* ctx, const void* lightCacheRGBA16F, LuxMemKind kind);
+/* Same for a row range of the atlas.  With a communicator bound (lux_ddgi_set_nccl_comm) rank r passes rows [r*res/world, (r+1)*res/world)
+ * and the ranks all-gather them in place over NVLink: one light cache crosses PCIe per frame in total, not one per GPU. */
+LUX_API int lux_ddgi_update_surface_light_cache_rows(LuxDDGIContext* ctx, const void* lightRowsRGBA16F, int32_t rowBegin, int32_t rowCount, LuxMemKind kind);
 
 /* uSkybox: 6 faces (+X,-X,+Y,-Y,+Z,-Z) of faceSize^2 RGBA16F texels.  Default = the reference's 1x1 black
  * fallback cube (DDGIRenderer.cpp:308). */

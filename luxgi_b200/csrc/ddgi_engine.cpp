@@ -1247,6 +1247,37 @@ int lux_ddgi_update_surface_light_cache(LuxDDGIContext* c, const void* light, Lu
     return LUX_OK;
 }
 
+// Sharded relight: every rank uploads only ITS rows of the (replicated) light cache and the ranks exchange them over NVLink, so the
+// host -> device traffic of a frame is one light cache in total instead of one per GPU.
+int lux_ddgi_update_surface_light_cache_rows(LuxDDGIContext* c, const void* lightRows, int32_t rowBegin, int32_t rowCount, LuxMemKind kind)
+{
+    CHECK_CTX(c);
+    if (!c->hasAtlas)
+        return fail(LUX_ERR_NOT_READY, "no surface cache bound");
+    const int32_t res = (int32_t)c->atlasData.resolution;
+    if (!lightRows || rowBegin < 0 || rowCount <= 0 || rowBegin + rowCount > res)
+        return fail(LUX_ERR_INVALID_ARG, "bad light-cache row range [%d,%d) of %d", rowBegin, rowBegin + rowCount, res);
+    const size_t rowBytes = (size_t)res * 8;
+    if (c->light.borrowed)
+        return fail(LUX_ERR_UNSUPPORTED, "the bound light cache is caller-owned device memory");
+    if (c->ncclComm && (rowCount * c->world != res || rowBegin != c->rank * rowCount))
+        return fail(LUX_ERR_INVALID_ARG, "with a communicator bound, rank r must pass rows [r*res/world, (r+1)*res/world)");
+    char* base = (char*)c->light.ptr;
+    LUX_CUDA(cudaStreamWaitEvent(c->copyStream, c->evShadeDone, 0)); // the previous frame's shade is the only reader
+    LUX_CUDA(cudaMemcpyAsync(base + (size_t)rowBegin * rowBytes, lightRows, (size_t)rowCount * rowBytes,
+                             kind == LUX_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->copyStream));
+    if (c->ncclComm)
+    {
+        NcclApi* n = ncclApi();
+        int rc = n->allGather(base + (size_t)rowBegin * rowBytes, base, (size_t)rowCount * rowBytes, /*ncclUint8*/ 1, c->ncclComm, c->copyStream);
+        if (rc != 0)
+            return fail(LUX_ERR_CUDA, "ncclAllGather(light cache): %s", n->getErrorString(rc));
+    }
+    LUX_CUDA(cudaEventRecord(c->evLightReady, c->copyStream));
+    c->lightPending = true;
+    return LUX_OK;
+}
+
 int lux_ddgi_set_skybox(LuxDDGIContext* c, int32_t faceSize, const void* faces, LuxMemKind kind)
 {
     CHECK_CTX(c);

@@ -25,7 +25,7 @@ EXPORTS = [
     "lux_ddgi_border_update", "lux_ddgi_end_frame", "lux_ddgi_update", "lux_ddgi_synchronize", "lux_ddgi_get_buffer",
     "lux_ddgi_download", "lux_ddgi_download_async", "lux_ddgi_download_rows_async", "lux_ddgi_set_ray_buffers", "lux_ddgi_restore", "lux_ddgi_get_state", "lux_ddgi_shard_layout",
     "lux_ddgi_get_stage_ms", "lux_ddgi_sample_irradiance", "lux_ddgi_sample_probe", "lux_ddgi_indirect_light",
-    "lux_ddgi_get_surface_light_cache", "lux_ddgi_build_global_sdf", "lux_ddgi_build_sdf_mip", "lux_ddgi_sdf_file_read", "lux_ddgi_download_fence", "lux_ddgi_wait_fence", "lux_ddgi_set_nccl_comm",
+    "lux_ddgi_get_surface_light_cache", "lux_ddgi_build_global_sdf", "lux_ddgi_build_sdf_mip", "lux_ddgi_sdf_file_read", "lux_ddgi_download_fence", "lux_ddgi_wait_fence", "lux_ddgi_set_nccl_comm", "lux_ddgi_update_surface_light_cache_rows",
 ]
 
 
@@ -80,6 +80,7 @@ def load():
         "lux_ddgi_download_fence": [vp, C.POINTER(C.c_uint64)],
         "lux_ddgi_wait_fence": [vp, C.c_uint64],
         "lux_ddgi_set_nccl_comm": [vp, vp],
+        "lux_ddgi_update_surface_light_cache_rows": [vp, vp, i32, i32, i32],
         "lux_ddgi_sdf_file_read": [C.c_char_p, C.POINTER(C.c_uint32 * 3), C.POINTER(i32), C.POINTER(C.c_uint64), vp],
     }
     for name, argtypes in sig.items():
@@ -220,6 +221,9 @@ class DDGIPipeline:
 
     def update_surface_light_cache_ptr(self, host_ptr):
         _check(self._lib.lux_ddgi_update_surface_light_cache(self._h, C.c_void_p(host_ptr), abi.MEM_HOST))
+
+    def update_surface_light_cache_rows_ptr(self, host_ptr, row_begin, row_count):
+        _check(self._lib.lux_ddgi_update_surface_light_cache_rows(self._h, C.c_void_p(host_ptr), int(row_begin), int(row_count), abi.MEM_HOST))
 
     def set_skybox(self, face_size, faces):
         if not face_size or faces is None:

@@ -3,6 +3,7 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29533 tests/multi_gpu_check.py
 
 Every rank runs its z-slab of a small city volume for 4 frames with an ncclComm bound through lux_ddgi_set_nccl_comm and then
+(frame 2 relights through the sharded light-cache upload) and then
 compares its FULL atlases (own rows + the rows the all-gather delivered) with the CPU oracle's unsharded run, bit for bit; consumers
 (lux_ddgi_sample_irradiance at points spread over the whole volume) must see the complete atlas as well.  Prints one line per rank."""
 import os
@@ -31,8 +32,15 @@ def main():
     pipe.set_scene(sc)
     comm = nccl.NcclComm(rank, world, local)
     pipe.set_nccl_comm(comm.ptr)
+    res = int(sc.atlas_data.resolution)
+    rows = res // world
     for f in range(4):
         rot = scenes.frame_rotation(f)
+        if f == 2:  # sharded relight: every rank uploads its rows of a brighter light cache, the library all-gathers them
+            new_light = (sc.light.numpy().astype(np.float32) * 1.5).astype(np.float16)
+            orc.os.light[...] = new_light.view(np.uint16)
+            mine = torch.from_numpy(np.ascontiguousarray(new_light[rank * rows:(rank + 1) * rows])).pin_memory()
+            pipe.update_surface_light_cache_rows_ptr(mine.data_ptr(), rank * rows, rows)
         orc.update(rot)
         pipe.update(rot)
     ok_i = np.array_equal(pipe.irradiance, orc.irradiance)
