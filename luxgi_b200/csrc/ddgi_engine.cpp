@@ -1259,7 +1259,15 @@ int lux_ddgi_update_surface_light_cache_rows(LuxDDGIContext* c, const void* ligh
         return fail(LUX_ERR_INVALID_ARG, "bad light-cache row range [%d,%d) of %d", rowBegin, rowBegin + rowCount, res);
     const size_t rowBytes = (size_t)res * 8;
     if (c->light.borrowed)
-        return fail(LUX_ERR_UNSUPPORTED, "the bound light cache is caller-owned device memory");
+    { // never write into a caller-owned buffer: continue on a private copy
+        void* own = nullptr;
+        LUX_CUDA(cudaMalloc(&own, (size_t)res * rowBytes));
+        LUX_CUDA(cudaMemcpyAsync(own, c->light.ptr, (size_t)res * rowBytes, cudaMemcpyDeviceToDevice, c->stream));
+        LUX_CUDA(cudaStreamSynchronize(c->stream));
+        c->light.ptr      = own;
+        c->light.borrowed = false;
+        c->light.bytes    = (size_t)res * rowBytes;
+    }
     if (c->ncclComm && (rowCount * c->world != res || rowBegin != c->rank * rowCount))
         return fail(LUX_ERR_INVALID_ARG, "with a communicator bound, rank r must pass rows [r*res/world, (r+1)*res/world)");
     char* base = (char*)c->light.ptr;
