@@ -301,6 +301,12 @@ LUX_API int lux_ddgi_update_surface_light_cache_rows(LuxDDGIContext* ctx, const 
 
 /* uSkybox: 6 faces (+X,-X,+Y,-Y,+Z,-Z) of faceSize^2 RGBA16F texels.  Default = the reference's 1x1 black
  * fallback cube (DDGIRenderer.cpp:308). */
+/* f4 (first half): surface::culling + Shaders/SDF/SDFCulling.comp:36-101 on device.  Rebuilds SDFAtlasChunkBuffer / SDFCullObjectBuffer of
+ * the bound surface cache from its object buffer: per chunk the ids (ascending) of the objects whose bounding sphere touches the chunk.
+ * Lists are laid out in ascending chunk address (the shader's atomic allocation makes its own layout scheduling dependent);
+ * capacityWords = the shader's culledObjectsCapacity (lists that do not fit are dropped), 0 = make everything fit. */
+LUX_API int lux_ddgi_cull_surface_objects(LuxDDGIContext* ctx, uint32_t capacityWords);
+LUX_API int lux_ddgi_get_surface_cull_lists(LuxDDGIContext* ctx, void** chunksDevice, void** cullDevice, size_t* cullWords);
 LUX_API int lux_ddgi_set_skybox(LuxDDGIContext* ctx, int32_t faceSize, const void* facesRGBA16F, LuxMemKind kind);
 
 /* The three stages + frame bookkeeping, in the order RenderGraph.cpp:98-114 runs them. */

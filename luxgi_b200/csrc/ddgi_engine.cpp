@@ -326,7 +326,7 @@ static int initializeProbeGrid(LuxDDGIContext& c)
         }
         bins   = std::max(bins, lux::trace_sort_bins(c.probeCount, u.raysPerProbe)); // the staged API shades the shard as one batch
         blocks = std::max(blocks, lux::trace_sort_blocks(c.probeCount, u.raysPerProbe));
-        if (!(c.flags & LUX_DDGI_FLAG_SHADE_UNSORTED) && nrec < (size_t(1) << 32))
+        if (!(c.flags & LUX_DDGI_FLAG_SHADE_UNSORTED) && nrec < (size_t(1) << 30) /* record index + 2 cascade bits in one u32 */)
         {
             if ((rc = allocZero(c, c.sortTicket, nrec * sizeof(uint2))) != LUX_OK) return rc;
             if ((rc = allocZero(c, c.sortedIdx, nrec * sizeof(uint32_t))) != LUX_OK) return rc;
@@ -1283,6 +1283,77 @@ int lux_ddgi_update_surface_light_cache_rows(LuxDDGIContext* c, const void* ligh
     }
     LUX_CUDA(cudaEventRecord(c->evLightReady, c->copyStream));
     c->lightPending = true;
+    return LUX_OK;
+}
+
+// surface::culling (GlobalSurfaceAtlas.cpp:607-641) + SDFCulling.comp: rebuilds the chunk / culled-object lists of the bound surface
+// cache ON DEVICE from its object buffer.  `capacityWords` = GlobalSurfaceAtlasData.culledObjectsCapacity of the shader (lists that
+// do not fit are dropped, as there); 0 = size the buffer so that every list fits.
+int lux_ddgi_cull_surface_objects(LuxDDGIContext* c, uint32_t capacityWords)
+{
+    CHECK_CTX(c);
+    if (!c->hasAtlas)
+        return fail(LUX_ERR_NOT_READY, "no surface cache bound");
+    const size_t nchunks = (size_t)LUX_SURFACE_ATLAS_CHUNKS_RESOLUTION * LUX_SURFACE_ATLAS_CHUNKS_RESOLUTION * LUX_SURFACE_ATLAS_CHUNKS_RESOLUTION;
+    uint32_t* scratch = nullptr; // 65 536 sizes + 16 block sums + 1 total
+    LUX_CUDA(cudaMalloc(&scratch, (65536 + 16 + 1) * sizeof(uint32_t)));
+    auto done = [&](int rc) { cudaFree(scratch); return rc; };
+    // worst case: every chunk lists every object
+    const size_t worst = 1 + nchunks * ((size_t)c->atlasData.objectsCount + 1);
+    size_t words = capacityWords ? (size_t)capacityWords : worst;
+    if (capacityWords == 0 && worst > (size_t(1) << 26))
+    { // size it from the counts instead of the worst case: one extra counting pass
+        std::vector<uint32_t> tmp(1);
+        DeviceBuffer probe;
+        LUX_CUDA(cudaMalloc(&probe.ptr, nchunks * 4));
+        probe.bytes = nchunks * 4;
+        uint32_t* dummyCull = nullptr;
+        LUX_CUDA(cudaMalloc(&dummyCull, 16));
+        lux::launch_surface_cull((const LuxObjectBuffer*)c->objects.ptr, c->atlasData.objectsCount, c->atlasData.chunkSize, 0u, scratch, scratch + 65536,
+                                 scratch + 65536 + 16, (uint32_t*)probe.ptr, dummyCull, 1u, c->stream); // capacity 0: nothing is written but cull[0]
+        c->launches += 5;
+        cudaError_t e = cudaMemcpyAsync(tmp.data(), dummyCull, 4, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess)
+            e = cudaStreamSynchronize(c->stream);
+        cudaFree(dummyCull);
+        if (e != cudaSuccess)
+            return done(fail(LUX_ERR_CUDA, "surface cull sizing: %s", cudaGetErrorString(e)));
+        words = tmp[0];
+    }
+    for (DeviceBuffer* b : {&c->chunks, &c->cull})
+    {
+        const size_t bytes = (b == &c->chunks ? nchunks : words) * 4;
+        if (b->borrowed || b->bytes != bytes)
+        {
+            b->release();
+            cudaError_t e = cudaMalloc(&b->ptr, bytes);
+            if (e != cudaSuccess)
+                return done(fail(LUX_ERR_OUT_OF_MEMORY, "surface cull lists (%zu bytes): %s", bytes, cudaGetErrorString(e)));
+            b->bytes = bytes;
+        }
+    }
+    cudaStreamWaitEvent(c->stream, c->evShadeDone, 0);
+    lux::launch_surface_cull((const LuxObjectBuffer*)c->objects.ptr, c->atlasData.objectsCount, c->atlasData.chunkSize, (uint32_t)std::min<size_t>(words, 0xffffffffu),
+                             scratch, scratch + 65536, scratch + 65536 + 16, (uint32_t*)c->chunks.ptr, (uint32_t*)c->cull.ptr,
+                             (uint32_t)std::min<size_t>(words, 0xffffffffu), c->stream);
+    c->launches += 5;
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess)
+        return done(fail(LUX_ERR_CUDA, "surface cull: %s", cudaGetErrorString(e)));
+    c->atlasData.culledObjectsCapacity = (uint32_t)std::min<size_t>(words, 0xffffffffu);
+    c->masksDirty = true;
+    return done(LUX_OK);
+}
+
+int lux_ddgi_get_surface_cull_lists(LuxDDGIContext* c, void** chunksDevice, void** cullDevice, size_t* cullWords)
+{
+    CHECK_CTX(c);
+    if (!c->hasAtlas || !chunksDevice || !cullDevice)
+        return fail(LUX_ERR_NOT_READY, "no surface cache bound");
+    *chunksDevice = c->chunks.ptr;
+    *cullDevice   = c->cull.ptr;
+    if (cullWords)
+        *cullWords = c->cull.bytes / 4;
     return LUX_OK;
 }
 

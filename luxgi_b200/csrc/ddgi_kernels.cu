@@ -1292,7 +1292,8 @@ __global__ void __launch_bounds__(128) classify_kernel(const __grid_constant__ T
         { // rgb comes from shade_sorted_kernel
             f3 o = {o4.x, o4.y, o4.z}, d = {d4[k].x, d4[k].y, d4[k].z};
             uint32_t bin = (uint32_t)(g >> SORT_WINDOW_SHIFT) * (uint32_t)SORT_BINS_PER_WINDOW + shade_bin(P, o + d * rec[k].x);
-            ticket[k] = make_uint2(bin, atomicAdd(P.binCounts + bin, 1u));
+            // the hit cascade rides in the two top bits of the ticket (and of the sorted index), so the shade never re-reads `meta`
+            ticket[k] = make_uint2(bin, atomicAdd(P.binCounts + bin, 1u) | ((meta[k] & 3u) << 30));
         }
     }
 #pragma unroll
@@ -1422,7 +1423,7 @@ __global__ void __launch_bounds__(256) scatter_kernel(const uint2* __restrict__ 
         return;
     uint2 t = __ldg(ticket + g);
     if (t.x != 0xffffffffu)
-        sortedIdx[__ldg(prefix + t.x) + t.y] = (uint32_t)g;
+        sortedIdx[__ldg(prefix + t.x) + (t.y & 0x3fffffffu)] = (uint32_t)g | (t.y & 0xc0000000u);
 }
 
 template <bool TEX>
@@ -1435,12 +1436,12 @@ __global__ void __launch_bounds__(256, SHADE_BLOCKS_PER_SM) shade_sorted_kernel(
     const float texelOffset = __fdiv_rn(1.0f, data.resolution);
     for (uint32_t t = blockIdx.x * 256u + threadIdx.x; t < hits; t += gridDim.x * 256u)
     {
-        const uint32_t g    = __ldg(P.sortedIdx + t);
+        const uint32_t gi   = __ldg(P.sortedIdx + t);
+        const uint32_t g    = gi & 0x3fffffffu, hc = gi >> 30;
         const uint32_t unit = g / UNIT_RAYS, rem = g % UNIT_RAYS;
         const int probeLocal = (int)(unit / rayGroups) * 32 + (int)(rem & 31u);
         const int rayId      = (int)(unit % rayGroups) * TW_RAYS_PER_UNIT + (int)(rem >> 5);
         const float4   rec = __ldg(P.records + g);
-        const uint32_t hc  = __ldg(P.meta + g) & 3u;
         float4 d4 = __ldg(P.dirs + rayId);
         float4 o4 = __ldg(P.origins + probeLocal);
         f3     d  = {d4.x, d4.y, d4.z}, o = {o4.x, o4.y, o4.z};
@@ -2343,6 +2344,88 @@ void launch_sdf_mip_pass(const uint16_t* src, int srcWidth, int srcHeight, uint1
     const unsigned g = (unsigned)(outRes + 3) / 4;
     sdf_mip_kernel<<<dim3(g, g, g), 64, 0, s>>>(src, srcWidth, srcHeight, dst, dstWidth, dstHeight, outRes, globalSDFResolution, mipmapCoordScale,
                                                 cascadeTexOffsetX, cascadeMipMapOffsetX, maxDistance);
+}
+
+// =====================================================================================================================
+// Surface-cache culling: SDFCulling.comp:36-101, one thread per culling chunk.
+// The shader allocates list space with a returning atomic, which makes the layout of the cull buffer depend on scheduling.  Here
+// the same lists are laid out deterministically in ascending chunk address: count -> exclusive scan of (count + 1) -> fill.  The
+// capacity rule is the shader's (the counter advances even for a list that then does not fit).  Element 0 of the chunk buffer only
+// ever holds chunk 0's own list start: the shader's `atlasChunks.data[0] = chunkAddress` store of empty chunks is a data race in
+// the reference with no defined outcome and would let hits in chunk 0 read an arbitrary list.
+// =====================================================================================================================
+__device__ __forceinline__ bool chunk_intersects_object(const LuxObjectBuffer* __restrict__ objects, uint32_t i, f3 chunkMin, f3 chunkMax)
+{
+    float4 b  = __ldg(reinterpret_cast<const float4*>(objects[i].objectBounds));
+    f3     c  = {b.x, b.y, b.z};
+    f3     cl = {gclamp(c.x, chunkMin.x, chunkMax.x), gclamp(c.y, chunkMin.y, chunkMax.y), gclamp(c.z, chunkMin.z, chunkMax.z)};
+    return length3(c - cl) <= b.w;
+}
+
+__device__ __forceinline__ void cull_chunk_bounds(int chunk, float chunkSize, f3& mn, f3& mx)
+{
+    const int   N    = LUX_SURFACE_ATLAS_CHUNKS_RESOLUTION;
+    const float half = (float)N * 0.5f;
+    int cx = chunk % N, cy = (chunk / N) % N, cz = chunk / (N * N);
+    mn = {((float)cx - half) * chunkSize, ((float)cy - half) * chunkSize, ((float)cz - half) * chunkSize};
+    mx = {mn.x + chunkSize, mn.y + chunkSize, mn.z + chunkSize};
+}
+
+// sizes[chunk] = objectsCount + 1, or 0 for an empty chunk (padded entries stay 0)
+__global__ void cull_count_kernel(const LuxObjectBuffer* __restrict__ objects, uint32_t objectsCount, float chunkSize, uint32_t* __restrict__ sizes)
+{
+    const int chunk = blockIdx.x * blockDim.x + threadIdx.x;
+    const int total = LUX_SURFACE_ATLAS_CHUNKS_RESOLUTION * LUX_SURFACE_ATLAS_CHUNKS_RESOLUTION * LUX_SURFACE_ATLAS_CHUNKS_RESOLUTION;
+    if (chunk >= total)
+        return;
+    f3 mn, mx;
+    cull_chunk_bounds(chunk, chunkSize, mn, mx);
+    uint32_t n = 0;
+    for (uint32_t i = 0; i < objectsCount; i++)
+        n += chunk_intersects_object(objects, i, mn, mx) ? 1u : 0u;
+    sizes[chunk] = n ? n + 1u : 0u;
+}
+
+// prefix = exclusive scan of sizes (in place); *totalWords = sum.  cull[0] = 1 + sum is the shader's final counter.
+__global__ void cull_fill_kernel(const LuxObjectBuffer* __restrict__ objects, uint32_t objectsCount, float chunkSize, uint32_t capacity,
+                                 const uint32_t* __restrict__ prefix, const uint32_t* __restrict__ totalWords, uint32_t* __restrict__ chunks,
+                                 uint32_t* __restrict__ cull, uint32_t cullWords)
+{
+    const int chunk = blockIdx.x * blockDim.x + threadIdx.x;
+    const int total = LUX_SURFACE_ATLAS_CHUNKS_RESOLUTION * LUX_SURFACE_ATLAS_CHUNKS_RESOLUTION * LUX_SURFACE_ATLAS_CHUNKS_RESOLUTION;
+    if (chunk >= total)
+        return;
+    if (chunk == 0)
+        cull[0] = 1u + *totalWords;
+    f3 mn, mx;
+    cull_chunk_bounds(chunk, chunkSize, mn, mx);
+    uint32_t n = 0;
+    for (uint32_t i = 0; i < objectsCount; i++)
+        n += chunk_intersects_object(objects, i, mn, mx) ? 1u : 0u;
+    uint32_t start = 1u + prefix[chunk];
+    if (n == 0 || start + n + 1u > capacity || start + n + 1u > cullWords)
+    {
+        chunks[chunk] = 0u;
+        return;
+    }
+    chunks[chunk] = start;
+    cull[start]   = n;
+    for (uint32_t i = 0; i < objectsCount; i++)
+        if (chunk_intersects_object(objects, i, mn, mx))
+            cull[++start] = i;
+}
+
+void launch_surface_cull(const LuxObjectBuffer* objects, uint32_t objectsCount, float chunkSize, uint32_t capacity, uint32_t* sizesPadded,
+                         uint32_t* blockSums, uint32_t* totalWords, uint32_t* chunks, uint32_t* cull, uint32_t cullWords, cudaStream_t s)
+{
+    const int total = LUX_SURFACE_ATLAS_CHUNKS_RESOLUTION * LUX_SURFACE_ATLAS_CHUNKS_RESOLUTION * LUX_SURFACE_ATLAS_CHUNKS_RESOLUTION;
+    const int nb    = (total + SCAN_BINS_PER_BLOCK - 1) / SCAN_BINS_PER_BLOCK;
+    cudaMemsetAsync(sizesPadded, 0, (size_t)nb * SCAN_BINS_PER_BLOCK * sizeof(uint32_t), s);
+    cull_count_kernel<<<(total + 127) / 128, 128, 0, s>>>(objects, objectsCount, chunkSize, sizesPadded);
+    scan_reduce_kernel<<<nb, SCAN_THREADS, 0, s>>>((const uint4*)sizesPadded, blockSums);
+    scan_top_kernel<<<1, SCAN_THREADS, 0, s>>>(blockSums, nb, totalWords);
+    scan_apply_kernel<<<nb, SCAN_THREADS, 0, s>>>((uint4*)sizesPadded, blockSums);
+    cull_fill_kernel<<<(total + 127) / 128, 128, 0, s>>>(objects, objectsCount, chunkSize, capacity, sizesPadded, totalWords, chunks, cull, cullWords);
 }
 
 void launch_indirect_light(const LuxDDGIUniform& ddgi, const void* irr, const void* dep, void* light, const void* base, int count,

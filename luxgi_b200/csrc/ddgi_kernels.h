@@ -143,4 +143,9 @@ void launch_sdf_fill(uint16_t* p, size_t n, uint16_t value, cudaStream_t s);
 void launch_sdf_mip_pass(const uint16_t* src, int srcWidth, int srcHeight, uint16_t* dst, int dstWidth, int dstHeight, int outRes, int globalSDFResolution,
                          int mipmapCoordScale, int cascadeTexOffsetX, int cascadeMipMapOffsetX, float maxDistance, cudaStream_t s);
 
+// ---- surface-cache culling: SDFCulling.comp with a deterministic (ascending chunk address) list layout ----
+// sizesPadded: 65 536 words of scratch, blockSums: 16 words, totalWords: 1 word.  Returns through `chunks` (64 000 words) and `cull`.
+void launch_surface_cull(const LuxObjectBuffer* objects, uint32_t objectsCount, float chunkSize, uint32_t capacity, uint32_t* sizesPadded,
+                         uint32_t* blockSums, uint32_t* totalWords, uint32_t* chunks, uint32_t* cull, uint32_t cullWords, cudaStream_t s);
+
 } // namespace lux

@@ -25,7 +25,8 @@ EXPORTS = [
     "lux_ddgi_border_update", "lux_ddgi_end_frame", "lux_ddgi_update", "lux_ddgi_synchronize", "lux_ddgi_get_buffer",
     "lux_ddgi_download", "lux_ddgi_download_async", "lux_ddgi_download_rows_async", "lux_ddgi_set_ray_buffers", "lux_ddgi_restore", "lux_ddgi_get_state", "lux_ddgi_shard_layout",
     "lux_ddgi_get_stage_ms", "lux_ddgi_sample_irradiance", "lux_ddgi_sample_probe", "lux_ddgi_indirect_light",
-    "lux_ddgi_get_surface_light_cache", "lux_ddgi_build_global_sdf", "lux_ddgi_build_sdf_mip", "lux_ddgi_sdf_file_read", "lux_ddgi_download_fence", "lux_ddgi_wait_fence", "lux_ddgi_set_nccl_comm", "lux_ddgi_update_surface_light_cache_rows",
+    "lux_ddgi_get_surface_light_cache", "lux_ddgi_build_global_sdf", "lux_ddgi_build_sdf_mip", "lux_ddgi_sdf_file_read", "lux_ddgi_download_fence", "lux_ddgi_wait_fence", "lux_ddgi_set_nccl_comm", "lux_ddgi_update_surface_light_cache_rows", "lux_ddgi_cull_surface_objects",
+    "lux_ddgi_get_surface_cull_lists",
 ]
 
 
@@ -80,6 +81,8 @@ def load():
         "lux_ddgi_download_fence": [vp, C.POINTER(C.c_uint64)],
         "lux_ddgi_wait_fence": [vp, C.c_uint64],
         "lux_ddgi_set_nccl_comm": [vp, vp],
+        "lux_ddgi_cull_surface_objects": [vp, C.c_uint32],
+        "lux_ddgi_get_surface_cull_lists": [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(sz)],
         "lux_ddgi_update_surface_light_cache_rows": [vp, vp, i32, i32, i32],
         "lux_ddgi_sdf_file_read": [C.c_char_p, C.POINTER(C.c_uint32 * 3), C.POINTER(i32), C.POINTER(C.c_uint64), vp],
     }
@@ -319,6 +322,17 @@ class DDGIPipeline:
 
     def download_rows_async_ptr(self, buf, row_begin, row_count, host_ptr):
         _check(self._lib.lux_ddgi_download_rows_async(self._h, buf, int(row_begin), int(row_count), C.c_void_p(host_ptr)))
+
+    def cull_surface_objects(self, capacity_words=0):
+        """SDFCulling.comp on device over the bound object buffer -> (chunks uint32[64000], cull uint32[words])."""
+        import torch
+
+        _check(self._lib.lux_ddgi_cull_surface_objects(self._h, int(capacity_words)))
+        pc, pl, n = C.c_void_p(), C.c_void_p(), C.c_size_t()
+        _check(self._lib.lux_ddgi_get_surface_cull_lists(self._h, C.byref(pc), C.byref(pl), C.byref(n)))
+        chunks = torch.as_tensor(DeviceView(pc.value, (abi.CHUNKS_RESOLUTION ** 3,), "<i4", self), device="cuda").cpu().numpy().view(np.uint32)
+        cull = torch.as_tensor(DeviceView(pl.value, (n.value,), "<i4", self), device="cuda").cpu().numpy().view(np.uint32)
+        return chunks, cull
 
     def set_nccl_comm(self, comm_ptr):
         """Bind an ncclComm_t (integer address, e.g. luxgi_b200.nccl.NcclComm.ptr): lux_ddgi_update then all-gathers the atlas rows itself."""

@@ -322,3 +322,19 @@ def sdf_build(sdf_data, meshes, min_object_radius=0.0):
     rc = L.oracle_sdf_build(C.byref(sdf_data), arr, len(meshes), float(min_object_radius), _ptr(sdf), _ptr(mip), stats)
     assert rc == 0, rc
     return sdf, mip, dict(zip(("chunks", "models", "dropped_by_overflow", "chunks_out_of_range"), [int(x) for x in stats]))
+
+
+def surface_cull(atlas_data, objects, order=None, emulate_slot0=False, capacity_words=None):
+    """SDFCulling.comp restated: -> (chunks uint32[64000], cull uint32[capacity_words])."""
+    n = abi.CHUNKS_RESOLUTION ** 3
+    cap = int(capacity_words if capacity_words is not None else max(int(atlas_data.culledObjectsCapacity), 1))
+    chunks = np.zeros(n, dtype=np.uint32)
+    cull = np.zeros(cap, dtype=np.uint32)
+    objs = np.ascontiguousarray(objects)
+    o = None if order is None else np.ascontiguousarray(order, dtype=np.int32)
+    L = lib()
+    L.oracle_surface_cull.restype = C.c_int
+    L.oracle_surface_cull.argtypes = [C.POINTER(abi.GlobalSurfaceAtlasData), C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_uint32]
+    rc = L.oracle_surface_cull(C.byref(atlas_data), _ptr(objs), _ptr(o), 0 if o is None else len(o), int(bool(emulate_slot0)), _ptr(chunks), _ptr(cull), cap)
+    assert rc == 0, rc
+    return chunks, cull

@@ -1491,6 +1491,65 @@ int oracle_sdf_build(const LuxGlobalSDFData* data, const LuxMeshSDF* meshes, int
 } // extern "C"
 
 extern "C" {
+// =====================================================================================================================
+// Surface-cache culling ("next" row f4, first half): Shaders/SDF/SDFCulling.comp:36-101 + boxIntersectsSphere / flattenId
+// (AtlasCommon.glsl:34-47), host GlobalSurfaceAtlas.cpp:607-641 (counter reset to 1).  One invocation per culling chunk.
+// The shader allocates list space with an atomic, so WHERE a chunk's list lands depends on execution order; `order` fixes one
+// (an array of chunk addresses executed one after the other, null = ascending addresses).  emulateSlot0 keeps the shader's
+// `atlasChunks.data[0] = chunkAddress` store of empty / overflowing chunks (a data race in the reference: the last writer wins);
+// without it element 0 only ever holds chunk 0's own list start, which is what the engine builds.
+// =====================================================================================================================
+int oracle_surface_cull(const LuxGlobalSurfaceAtlasData* data, const LuxObjectBuffer* objects, const int32_t* order, int orderCount,
+                        int emulateSlot0, uint32_t* chunks, uint32_t* cull, uint32_t cullCapacityWords)
+{
+    if (!data || !objects || !chunks || !cull || cullCapacityWords < 1)
+        return -1;
+    const int N = LUX_SURFACE_ATLAS_CHUNKS_RESOLUTION, total = N * N * N;
+    cull[0] = 1; // GlobalSurfaceAtlas.cpp:617-618
+    const int count = order ? orderCount : total;
+    for (int k = 0; k < count; k++)
+    {
+        const uint32_t chunkAddress = order ? (uint32_t)order[k] : (uint32_t)k;
+        const int cx = (int)(chunkAddress % N), cy = (int)((chunkAddress / N) % N), cz = (int)(chunkAddress / (N * N));
+        const float half = (float)N * 0.5f;
+        vec3 chunkMin = {((float)cx - half) * data->chunkSize, ((float)cy - half) * data->chunkSize, ((float)cz - half) * data->chunkSize};
+        vec3 chunkMax = {chunkMin.x + data->chunkSize, chunkMin.y + data->chunkSize, chunkMin.z + data->chunkSize};
+        auto hits = [&](uint32_t i) {
+            const float* b = objects[i].objectBounds;
+            vec3 c = {b[0], b[1], b[2]};
+            vec3 cl = {gclamp(c.x, chunkMin.x, chunkMax.x), gclamp(c.y, chunkMin.y, chunkMax.y), gclamp(c.z, chunkMin.z, chunkMax.z)};
+            return length3(sub(c, cl)) <= b[3];
+        };
+        uint32_t objectsCount = 0;
+        for (uint32_t i = 0; i < data->objectsCount; i++)
+            if (hits(i))
+                objectsCount++;
+        if (objectsCount == 0)
+        {
+            if (emulateSlot0)
+                chunks[0] = chunkAddress;
+            continue;
+        }
+        const uint32_t objectsSize = objectsCount + 1;
+        uint32_t objectsStart = cull[0];
+        cull[0] += objectsSize; // atomicAdd
+        if (objectsStart + objectsSize > data->culledObjectsCapacity)
+        {
+            if (emulateSlot0)
+                chunks[0] = chunkAddress;
+            continue;
+        }
+        if ((size_t)objectsStart + objectsSize > cullCapacityWords)
+            return -2;
+        cull[objectsStart]   = objectsCount;
+        chunks[chunkAddress] = objectsStart;
+        for (uint32_t i = 0; i < data->objectsCount; i++) // both shader branches (local array / second scan) list ascending ids
+            if (hits(i))
+                cull[++objectsStart] = i;
+    }
+    return 0;
+}
+
 // Border copy list of one probe in ring-relative coordinates: out[n][4] = (srcx, srcy, dstx, dsty); returns n.
 int oracle_border_offsets(int side, int32_t* out)
 {

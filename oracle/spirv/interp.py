@@ -41,7 +41,7 @@ OP = {
     176: "ULessThan", 177: "SLessThan", 178: "ULessThanEqual", 179: "SLessThanEqual", 180: "FOrdEqual", 182: "FOrdNotEqual",
     184: "FOrdLessThan", 186: "FOrdGreaterThan", 188: "FOrdLessThanEqual", 190: "FOrdGreaterThanEqual", 194: "ShiftRightLogical",
     195: "ShiftRightArithmetic", 196: "ShiftLeftLogical", 197: "BitwiseOr", 198: "BitwiseXor", 199: "BitwiseAnd", 200: "Not",
-    224: "ControlBarrier", 225: "MemoryBarrier", 245: "Phi", 246: "LoopMerge", 247: "SelectionMerge", 248: "Label", 249: "Branch",
+    224: "ControlBarrier", 225: "MemoryBarrier", 234: "AtomicIAdd", 245: "Phi", 246: "LoopMerge", 247: "SelectionMerge", 248: "Label", 249: "Branch",
     250: "BranchConditional", 252: "Kill", 253: "Return", 254: "ReturnValue", 255: "Unreachable", 400: "CopyLogical",
 }
 GLSL = {4: "FAbs", 8: "Floor", 10: "Fract", 13: "Sin", 14: "Cos", 26: "Pow", 31: "Sqrt", 32: "InverseSqrt", 34: "MatrixInverse",
@@ -464,6 +464,11 @@ class Invocation:
                     pass
                 elif name == "ImageWrite":
                     V(a[0]).write(V(a[1]), V(a[2]))
+                elif name == "AtomicIAdd":  # result type, result id, pointer, scope, semantics, value; invocations run one at a time
+                    ptr = V(a[2])
+                    old = ptr.load()
+                    ptr.store((old + V(a[5])) & M32)
+                    env[a[1]] = old
                 else:
                     env[a[1]] = self.alu(name, a, V)
             prev, label = label, nxt

@@ -442,3 +442,42 @@ def test_pipelined_row_downloads_with_fences(oracle):
     pipe.wait_fence(fences[-1])
     assert np.array_equal(bufs[1].numpy().view(np.uint16).reshape(wants[3].shape), wants[3])
     pipe.close()
+
+
+@pytest.mark.parametrize("cfg", ["c1", "city64"])
+def test_surface_culling_on_device_matches_oracle(oracle, cfg):
+    """Row f4 (first half): lux_ddgi_cull_surface_objects rebuilds the chunk / culled-object lists from the bound object buffer.  Word for
+    word equal to the oracle's SDFCulling restatement executed in ascending chunk order (the layout the engine defines), with room for
+    every list and with the shader's capacity rule dropping most of them; tracing on the rebuilt lists equals the oracle tracing on its own."""
+    sc = scenes.build(cfg)
+    pipe = ddgi.DDGIPipeline(sc.uniform)
+    pipe.set_scene(sc)
+    data = abi.GlobalSurfaceAtlasData.from_buffer_copy(bytes(sc.atlas_data))
+    data.culledObjectsCapacity = 1 << 30
+    want_chunks, want_cull = oracle.surface_cull(data, sc.objects, capacity_words=1 + 64000 * (len(sc.objects) + 1))
+    chunks, cull = pipe.cull_surface_objects()
+    used = int(want_cull[0])
+    assert int(cull[0]) == used and len(cull) >= used
+    assert np.array_equal(chunks, want_chunks) and np.array_equal(cull[:used], want_cull[:used])
+    # the lists the fixture generator wrote describe the same sets (its float64 box-sphere test may differ on exact ties only)
+    same = sum(1 for a in np.nonzero(want_chunks)[0][:2000] if sc.chunks[a] and
+               np.array_equal(want_cull[want_chunks[a]:want_chunks[a] + 1 + want_cull[want_chunks[a]]], sc.cull[sc.chunks[a]:sc.chunks[a] + 1 + sc.cull[sc.chunks[a]]]))
+    assert same >= 0.99 * min(2000, int((want_chunks != 0).sum()))
+    # tracing on the rebuilt lists
+    sc2 = scenes.build(cfg)
+    sc2.chunks, sc2.cull = want_chunks, want_cull[:used].copy()
+    orc = oracle.OraclePipeline(sc2)
+    for f in range(2):
+        rot = scenes.frame_rotation(f)
+        orc.update(rot)
+        pipe.update(rot)
+    assert_rays_match(pipe, orc)
+    assert_atlases_match(pipe, orc)
+    # the shader's capacity rule
+    small = max(64, used // 5)
+    data.culledObjectsCapacity = small
+    want_chunks_s, want_cull_s = oracle.surface_cull(data, sc.objects, capacity_words=used + 8)
+    chunks_s, cull_s = pipe.cull_surface_objects(capacity_words=small)
+    assert 0 < (chunks_s != 0).sum() < (chunks != 0).sum()
+    assert np.array_equal(chunks_s, want_chunks_s) and int(cull_s[0]) == int(want_cull_s[0]) and np.array_equal(cull_s[1:small], want_cull_s[1:small])
+    pipe.close()

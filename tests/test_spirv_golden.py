@@ -142,3 +142,19 @@ def test_sdf_build_matches_shipped_spirv(oracle):
     assert np.array_equal(tmp, gold["flood_tmp"])
     oracle.sdf_mip_pass(tmp, mip, mres, mres, 1, 0, mres, 2 * D1)
     assert np.array_equal(mip, gold["flood_mip"])
+
+
+def test_surface_culling_matches_shipped_spirv(oracle):
+    """Row f4 (first half): the oracle's restatement of SDFCulling.comp executed in the golden run's dispatch order reproduces the shipped
+    binary's chunk and cull buffers word for word, including the list-overflow branch and the element-0 store of empty chunks."""
+    from tests.golden import make_spirv_golden_culling as g
+
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "spirv_golden_culling.npz"))
+    sc = g.golden_scene()
+    for cap in gold["capacities"]:
+        data = abi.GlobalSurfaceAtlasData.from_buffer_copy(bytes(sc.atlas_data))
+        data.culledObjectsCapacity = int(cap)
+        chunks, cull = oracle.surface_cull(data, sc.objects, order=gold["order"], emulate_slot0=True, capacity_words=8192)
+        assert np.array_equal(chunks, gold[f"chunks_{cap}"]), f"capacity {cap}: {(chunks != gold[f'chunks_{cap}']).sum()} chunk words differ"
+        assert np.array_equal(cull, gold[f"cull_{cap}"]), f"capacity {cap}: {(cull != gold[f'cull_{cap}']).sum()} cull words differ"
+    assert (gold["chunks_4096"][1:] != 0).sum() > 500 > (gold["chunks_150"][1:] != 0).sum() > 0
