@@ -164,6 +164,28 @@ typedef struct LuxMeshSDF {
 } LuxMeshSDF;
 
 /* ---------------------------------------------------------------------------------------------------------
+ * a5b. GlobalSDFTrace / GlobalSDFHit (Shaders/SDF/GlobalSDFTrace.glsl:4-12, GlobalSDFHit.glsl:4-11): the argument and result of
+ *      tracyGlobalSDF (SDFCommon.glsl:98-194), for its other users (row f4: SDFShadow.comp:140-148, SDFReflection.comp,
+ *      SDFDeferredLight.frag:101-109).  Plain C layout, 40 / 28 bytes.  minDistance is carried but, as in the reference, never read.
+ * ------------------------------------------------------------------------------------------------------ */
+typedef struct LuxGlobalSDFTrace {
+    float    worldPosition[3];
+    float    minDistance;
+    float    worldDirection[3];
+    float    maxDistance;
+    float    stepScale;
+    uint32_t needsHitNormal;
+} LuxGlobalSDFTrace;
+
+typedef struct LuxGlobalSDFHit {
+    float    hitNormal[3]; /* (0,0,0) unless needsHitNormal and hit */
+    float    hitTime;      /* < 0: miss (isHit, SDFCommon.glsl:73-76) */
+    uint32_t hitCascade;
+    uint32_t stepsCount;
+    float    hitSDF;
+} LuxGlobalSDFHit;
+
+/* ---------------------------------------------------------------------------------------------------------
  * a6. Surface-cache records (Shaders/SDF/AtlasCommon.glsl:8-32; host GlobalSurfaceAtlas.cpp:59-73,
  *     SurfaceAtlasTile.h:117-125).
  * ------------------------------------------------------------------------------------------------------ */
@@ -271,6 +293,11 @@ LUX_API int lux_ddgi_set_uniform(LuxDDGIContext* ctx, const LuxDDGIUniform* unif
 /* uGlobalSDF / uGlobalMipSDF + UniformBufferObject.sdfData (DDGIRenderer.cpp:304-305,314). fp16 texels. */
 LUX_API int lux_ddgi_set_global_sdf(LuxDDGIContext* ctx, const LuxGlobalSDFData* data,
                             const void* sdfR16F, const void* mipR16F, LuxMemKind kind);
+
+/* f4: tracyGlobalSDF for arbitrary rays through the bound global SDF (shadow / reflection / surface-cache light rays).
+ * cascadeTraceStartBias = the shader call's last argument (0 in GISDFRays / SDFShadow, 2 in SDFDeferredLight). */
+LUX_API int lux_ddgi_trace_global_sdf(LuxDDGIContext* ctx, int32_t count, const LuxGlobalSDFTrace* traces, float cascadeTraceStartBias,
+                                      LuxGlobalSDFHit* hits, LuxMemKind kind);
 
 /* f3: builds the global SDF and its mip ON DEVICE from mesh distance fields and binds them like lux_ddgi_set_global_sdf.
  * `data` gives the cascades (centre, half extent, voxel size = 2*extent/resolution, resolution, count); objects whose

@@ -7,6 +7,8 @@ GlobalSurfaceAtlasData / ObjectBuffer / TileBuffer (Shaders/SDF/AtlasCommon.glsl
 """
 import ctypes as C
 
+import numpy as np
+
 IRRADIANCE_OCT_SIZE = 8
 DEPTH_OCT_SIZE = 16
 GLOBAL_SDF_WORLD_SIZE = 60000.0
@@ -223,3 +225,10 @@ def make_uniform(start, step, counts, rays, max_distance=None, sharpness=50.0, h
 
 def probe_count(u):
     return u.probeCounts[0] * u.probeCounts[1] * u.probeCounts[2]
+
+
+# GlobalSDFTrace / GlobalSDFHit (row f4: lux_ddgi_trace_global_sdf), as numpy record dtypes
+SDF_TRACE_DTYPE = np.dtype([("worldPosition", "<f4", 3), ("minDistance", "<f4"), ("worldDirection", "<f4", 3), ("maxDistance", "<f4"),
+                            ("stepScale", "<f4"), ("needsHitNormal", "<u4")])
+SDF_HIT_DTYPE = np.dtype([("hitNormal", "<f4", 3), ("hitTime", "<f4"), ("hitCascade", "<u4"), ("stepsCount", "<u4"), ("hitSDF", "<f4")])
+assert SDF_TRACE_DTYPE.itemsize == 40 and SDF_HIT_DTYPE.itemsize == 28

@@ -1864,6 +1864,50 @@ int lux_ddgi_get_surface_light_cache(LuxDDGIContext* c, void** devicePtr, size_t
     return LUX_OK;
 }
 
+int lux_ddgi_trace_global_sdf(LuxDDGIContext* c, int32_t count, const LuxGlobalSDFTrace* traces, float cascadeTraceStartBias, LuxGlobalSDFHit* hits,
+                              LuxMemKind kind)
+{
+    CHECK_CTX(c);
+    if (!c->hasSdf)
+        return fail(LUX_ERR_NOT_READY, "no global SDF bound");
+    if (count < 0 || (count > 0 && (!traces || !hits)))
+        return fail(LUX_ERR_INVALID_ARG, "bad trace_global_sdf arguments");
+    if (count == 0)
+        return LUX_OK;
+    lux::TraceParams p{};
+    p.sdf      = c->sdfData;
+    p.tex      = (const uint16_t*)c->sdf.ptr;
+    p.mip      = (const uint16_t*)c->mip.ptr;
+    p.res      = (int)c->sdfData.resolution;
+    p.mipRes   = p.res / 4;
+    p.cascades = (int)c->sdfData.cascadesCount;
+    p.texObj   = c->sdfTex;
+    p.mipObj   = c->mipTex;
+    void *dT = nullptr, *dH = nullptr;
+    bool  oT = false;
+    int   rc = stageToDevice(c, traces, (size_t)count * sizeof(LuxGlobalSDFTrace), kind, &dT, &oT);
+    if (rc != LUX_OK)
+        return rc;
+    if (kind == LUX_MEM_DEVICE)
+        dH = hits;
+    else
+        LUX_CUDA(cudaMalloc(&dH, (size_t)count * sizeof(LuxGlobalSDFHit)));
+    lux::launch_sdf_rays(p, c->sdfTex != 0, count, (const LuxGlobalSDFTrace*)dT, cascadeTraceStartBias, (LuxGlobalSDFHit*)dH, c->stream);
+    c->launches += 1;
+    LUX_CUDA(cudaGetLastError());
+    if (kind != LUX_MEM_DEVICE)
+    {
+        cudaError_t e = cudaMemcpyAsync(hits, dH, (size_t)count * sizeof(LuxGlobalSDFHit), cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess)
+            e = cudaStreamSynchronize(c->stream);
+        cudaFree(dH);
+        if (oT)
+            cudaFree(dT);
+        LUX_CUDA(e);
+    }
+    return LUX_OK;
+}
+
 int lux_ddgi_get_stage_ms(LuxDDGIContext* c, LuxStageTimes* out)
 {
     CHECK_CTX(c);

@@ -736,6 +736,89 @@ struct SdfSampler<true>
     __device__ __forceinline__ float sampleMip(float u, float v, float w) const { return sample3D_tex(mip, mw, mh, mh, u, v, w); }
 };
 
+// tracyGlobalSDF (SDFCommon.glsl:98-194) in full generality, for its other users (row f4): one thread per ray.
+template <bool TEX>
+__global__ void __launch_bounds__(128) sdf_rays_kernel(const __grid_constant__ TraceParams P, int count, const LuxGlobalSDFTrace* __restrict__ traces,
+                                                       float cascadeTraceStartBias, LuxGlobalSDFHit* __restrict__ hits)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count)
+        return;
+    const SdfSampler<TEX> sdf(P);
+    const LuxGlobalSDFData& data = P.sdf;
+    const LuxGlobalSDFTrace tr = traces[k];
+    const f3 origin = {tr.worldPosition[0], tr.worldPosition[1], tr.worldPosition[2]}, dir = {tr.worldDirection[0], tr.worldDirection[1], tr.worldDirection[2]};
+    LuxGlobalSDFHit hit;
+    hit.hitNormal[0] = hit.hitNormal[1] = hit.hitNormal[2] = 0.0f;
+    hit.hitTime = -1.0f; hit.hitCascade = 0; hit.stepsCount = 0; hit.hitSDF = 0.0f;
+
+    const float traceMaxDistance    = gmin(tr.maxDistance, data.cascadePosDistance[data.cascadesCount - 1][3] * 2.0f);
+    const float chunkSizeDistance   = __fdiv_rn((float)LUX_GLOBAL_SDF_RASTERIZE_CHUNK_SIZE, data.resolution);
+    const float chunkMarginDistance = __fdiv_rn((float)LUX_GLOBAL_SDF_RASTERIZE_CHUNK_MARGIN, data.resolution);
+    const float cascadesCountF      = (float)data.cascadesCount;
+    float nextIntersectionStart = 0.0f;
+    const f3 traceEnd = origin + dir * traceMaxDistance;
+    for (uint32_t cascade = 0; cascade < data.cascadesCount && hit.hitTime < 0.0f; cascade++)
+    {
+        f3    c         = {data.cascadePosDistance[cascade][0], data.cascadePosDistance[cascade][1], data.cascadePosDistance[cascade][2]};
+        float cd        = data.cascadePosDistance[cascade][3];
+        float voxelSize = data.cascadeVoxelSize[cascade];
+        float voxelHalf = voxelSize * 0.5f;
+        f3    worldPosition = origin + dir * (voxelSize * cascadeTraceStartBias);
+        f3    ext = {cd, cd, cd};
+        float nearT, farT;
+        line_hit_aabb(worldPosition, traceEnd, c - ext, c + ext, nearT, farT);
+        nearT *= traceMaxDistance;
+        farT *= traceMaxDistance;
+        nearT = gmax(nearT, nextIntersectionStart);
+        float stepTime = nearT;
+        if (nearT >= farT)
+            stepTime = farT;
+        else
+            nextIntersectionStart = farT;
+        const float cascadeMaxDistance = cd * 2.0f;
+        uint32_t step = 0;
+        for (; step < LUX_GLOBAL_SDF_MAX_STEPS && stepTime < farT; step++)
+        {
+            f3 stepPosition = worldPosition + dir * stepTime;
+            f3 pc           = stepPosition - c;
+            f3 cuv = {gclamp(__fdiv_rn(pc.x, cascadeMaxDistance) + 0.5f, 0.0f, 1.0f), gclamp(__fdiv_rn(pc.y, cascadeMaxDistance) + 0.5f, 0.0f, 1.0f),
+                      gclamp(__fdiv_rn(pc.z, cascadeMaxDistance) + 0.5f, 0.0f, 1.0f)};
+            f3 uvw = {__fdiv_rn((float)cascade + cuv.x, cascadesCountF), cuv.y, cuv.z};
+            float stepDistance = sdf.sampleMip(uvw.x, uvw.y, uvw.z);
+            if (stepDistance < chunkSizeDistance)
+            {
+                float stepDistanceTex = sdf.sampleTex(uvw.x, uvw.y, uvw.z);
+                if (stepDistanceTex < chunkMarginDistance * 2.0f)
+                    stepDistance = stepDistanceTex;
+            }
+            else
+                stepDistance = chunkSizeDistance;
+            stepDistance *= cascadeMaxDistance;
+            float minSurfaceThickness = voxelHalf * gclamp(__fdiv_rn(stepTime, voxelSize), 0.0f, 1.0f);
+            if (stepDistance < minSurfaceThickness)
+            {
+                hit.hitTime    = gmax((stepTime + stepDistance) - minSurfaceThickness, 0.0f);
+                hit.hitCascade = cascade;
+                hit.hitSDF     = stepDistance;
+                if (tr.needsHitNormal)
+                {
+                    float o  = __fdiv_rn(1.0f, data.resolution);
+                    float xp = sdf.sampleTex(uvw.x + o, uvw.y, uvw.z), xn = sdf.sampleTex(uvw.x - o, uvw.y, uvw.z);
+                    float yp = sdf.sampleTex(uvw.x, uvw.y + o, uvw.z), yn = sdf.sampleTex(uvw.x, uvw.y - o, uvw.z);
+                    float zp = sdf.sampleTex(uvw.x, uvw.y, uvw.z + o), zn = sdf.sampleTex(uvw.x, uvw.y, uvw.z - o);
+                    f3 n = normalize3({xp - xn, yp - yn, zp - zn});
+                    hit.hitNormal[0] = n.x; hit.hitNormal[1] = n.y; hit.hitNormal[2] = n.z;
+                }
+                break;
+            }
+            stepTime += gmax(stepDistance * tr.stepScale, voxelSize);
+        }
+        hit.stepsCount += step;
+    }
+    hits[k] = hit;
+}
+
 // One tile of one candidate object, split in two: the normal weight (cheap, rejects most tiles) ...
 __device__ __forceinline__ void load_tile_transform(const LuxTileBuffer* __restrict__ tile, float* tm)
 {
@@ -1255,7 +1338,7 @@ __device__ __forceinline__ uint32_t shade_bin(const TraceParams& P, f3 pos)
 // and issues all their loads, then all their tickets, before the first use: the pass is a latency chain
 // (record -> bin -> returning atomic) per record, so memory-level parallelism per thread is what makes it stream.
 constexpr int CLASSIFY_RPT = 4;
-__global__ void __launch_bounds__(128) classify_kernel(const __grid_constant__ TraceParams P, int rayGroups)
+__global__ void __launch_bounds__(128, 12) classify_kernel(const __grid_constant__ TraceParams P, int rayGroups)
 {
     __shared__ uint2 sRad[32][TW_RAYS_PER_UNIT + 1];
     __shared__ uint2 sDir[32][TW_RAYS_PER_UNIT + 1];
@@ -2426,6 +2509,17 @@ void launch_surface_cull(const LuxObjectBuffer* objects, uint32_t objectsCount, 
     scan_top_kernel<<<1, SCAN_THREADS, 0, s>>>(blockSums, nb, totalWords);
     scan_apply_kernel<<<nb, SCAN_THREADS, 0, s>>>((uint4*)sizesPadded, blockSums);
     cull_fill_kernel<<<(total + 127) / 128, 128, 0, s>>>(objects, objectsCount, chunkSize, capacity, sizesPadded, totalWords, chunks, cull, cullWords);
+}
+
+void launch_sdf_rays(const TraceParams& p, bool useTextures, int count, const LuxGlobalSDFTrace* traces, float cascadeTraceStartBias,
+                     LuxGlobalSDFHit* hits, cudaStream_t s)
+{
+    if (count <= 0)
+        return;
+    if (useTextures)
+        sdf_rays_kernel<true><<<(count + 127) / 128, 128, 0, s>>>(p, count, traces, cascadeTraceStartBias, hits);
+    else
+        sdf_rays_kernel<false><<<(count + 127) / 128, 128, 0, s>>>(p, count, traces, cascadeTraceStartBias, hits);
 }
 
 void launch_indirect_light(const LuxDDGIUniform& ddgi, const void* irr, const void* dep, void* light, const void* base, int count,

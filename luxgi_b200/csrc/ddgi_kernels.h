@@ -111,6 +111,10 @@ void launch_indirect_light(const LuxDDGIUniform& ddgi, const void* irr, const vo
                            const uint32_t* texel, const float* P, const float* N, const float* albedo, const float* metallic, float intensity,
                            const float* cameraPos, cudaStream_t s);
 
+// tracyGlobalSDF for arbitrary rays; only the SDF fields of TraceParams are read
+void launch_sdf_rays(const TraceParams& p, bool useTextures, int count, const LuxGlobalSDFTrace* traces, float cascadeTraceStartBias,
+                     LuxGlobalSDFHit* hits, cudaStream_t s);
+
 // ---- global SDF build ----
 struct SdfMeshRecord // device copy of LuxMeshSDF without the host pointers
 {

@@ -26,7 +26,7 @@ EXPORTS = [
     "lux_ddgi_download", "lux_ddgi_download_async", "lux_ddgi_download_rows_async", "lux_ddgi_set_ray_buffers", "lux_ddgi_restore", "lux_ddgi_get_state", "lux_ddgi_shard_layout",
     "lux_ddgi_get_stage_ms", "lux_ddgi_sample_irradiance", "lux_ddgi_sample_probe", "lux_ddgi_indirect_light",
     "lux_ddgi_get_surface_light_cache", "lux_ddgi_build_global_sdf", "lux_ddgi_build_sdf_mip", "lux_ddgi_sdf_file_read", "lux_ddgi_download_fence", "lux_ddgi_wait_fence", "lux_ddgi_set_nccl_comm", "lux_ddgi_update_surface_light_cache_rows", "lux_ddgi_cull_surface_objects",
-    "lux_ddgi_get_surface_cull_lists",
+    "lux_ddgi_get_surface_cull_lists", "lux_ddgi_trace_global_sdf",
 ]
 
 
@@ -82,6 +82,7 @@ def load():
         "lux_ddgi_wait_fence": [vp, C.c_uint64],
         "lux_ddgi_set_nccl_comm": [vp, vp],
         "lux_ddgi_cull_surface_objects": [vp, C.c_uint32],
+        "lux_ddgi_trace_global_sdf": [vp, i32, vp, C.c_float, vp, i32],
         "lux_ddgi_get_surface_cull_lists": [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(sz)],
         "lux_ddgi_update_surface_light_cache_rows": [vp, vp, i32, i32, i32],
         "lux_ddgi_sdf_file_read": [C.c_char_p, C.POINTER(C.c_uint32 * 3), C.POINTER(i32), C.POINTER(C.c_uint64), vp],
@@ -322,6 +323,13 @@ class DDGIPipeline:
 
     def download_rows_async_ptr(self, buf, row_begin, row_count, host_ptr):
         _check(self._lib.lux_ddgi_download_rows_async(self._h, buf, int(row_begin), int(row_count), C.c_void_p(host_ptr)))
+
+    def trace_global_sdf(self, traces, start_bias=0.0) -> np.ndarray:
+        """tracyGlobalSDF for arbitrary rays: traces = abi.SDF_TRACE_DTYPE records -> abi.SDF_HIT_DTYPE records."""
+        traces = np.ascontiguousarray(traces, dtype=abi.SDF_TRACE_DTYPE)
+        hits = np.zeros(len(traces), dtype=abi.SDF_HIT_DTYPE)
+        _check(self._lib.lux_ddgi_trace_global_sdf(self._h, len(traces), _host_ptr(traces), float(start_bias), _host_ptr(hits), abi.MEM_HOST))
+        return hits
 
     def cull_surface_objects(self, capacity_words=0):
         """SDFCulling.comp on device over the bound object buffer -> (chunks uint32[64000], cull uint32[words])."""

@@ -338,3 +338,16 @@ def surface_cull(atlas_data, objects, order=None, emulate_slot0=False, capacity_
     rc = L.oracle_surface_cull(C.byref(atlas_data), _ptr(objs), _ptr(o), 0 if o is None else len(o), int(bool(emulate_slot0)), _ptr(chunks), _ptr(cull), cap)
     assert rc == 0, rc
     return chunks, cull
+
+
+def trace_global_sdf(sdf_data, sdf, mip, traces, start_bias=0.0):
+    """tracyGlobalSDF for arbitrary rays (abi.SDF_TRACE_DTYPE records) -> abi.SDF_HIT_DTYPE records."""
+    traces = np.ascontiguousarray(traces, dtype=abi.SDF_TRACE_DTYPE)
+    hits = np.zeros(len(traces), dtype=abi.SDF_HIT_DTYPE)
+    s, m = _np(sdf), _np(mip)
+    L = lib()
+    L.oracle_trace_global_sdf.restype = C.c_int
+    L.oracle_trace_global_sdf.argtypes = [C.POINTER(abi.GlobalSDFData), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.c_void_p]
+    rc = L.oracle_trace_global_sdf(C.byref(sdf_data), _ptr(s), _ptr(m), len(traces), _ptr(traces), float(start_bias), _ptr(hits))
+    assert rc == 0, rc
+    return hits

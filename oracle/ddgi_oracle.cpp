@@ -1550,6 +1550,33 @@ int oracle_surface_cull(const LuxGlobalSurfaceAtlasData* data, const LuxObjectBu
     return 0;
 }
 
+// tracyGlobalSDF for arbitrary rays (row f4: the shadow / reflection / surface-cache light rays call the same function with other
+// arguments).  needsHitNormal = false leaves the normal at (0,0,0) (SDFCommon.glsl:165-177); minDistance is never read, as in the reference.
+int oracle_trace_global_sdf(const LuxGlobalSDFData* sdfData, const uint16_t* sdf, const uint16_t* mip, int count, const LuxGlobalSDFTrace* traces,
+                            float cascadeTraceStartBias, LuxGlobalSDFHit* hits)
+{
+    if (!sdfData || !sdf || !mip || !traces || !hits)
+        return -1;
+    Scene sc{};
+    sc.sdfData = *sdfData;
+    const int res = (int)sdfData->resolution, casc = (int)sdfData->cascadesCount;
+    sc.tex = Tex3D{sdf, res * casc, res, res};
+    sc.mip = Tex3D{mip, (res / 4) * casc, res / 4, res / 4};
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int k = 0; k < count; k++)
+    {
+        const LuxGlobalSDFTrace& t = traces[k];
+        Counters cn;
+        Hit h = tracyGlobalSDF(sc, {t.worldPosition[0], t.worldPosition[1], t.worldPosition[2]}, {t.worldDirection[0], t.worldDirection[1], t.worldDirection[2]},
+                               t.maxDistance, t.stepScale, cascadeTraceStartBias, cn);
+        LuxGlobalSDFHit& o = hits[k];
+        const bool n = t.needsHitNormal && h.hitTime >= 0.0f;
+        o.hitNormal[0] = n ? h.hitNormal.x : 0.0f; o.hitNormal[1] = n ? h.hitNormal.y : 0.0f; o.hitNormal[2] = n ? h.hitNormal.z : 0.0f;
+        o.hitTime = h.hitTime; o.hitCascade = h.hitCascade; o.stepsCount = h.stepsCount; o.hitSDF = h.hitSDF;
+    }
+    return 0;
+}
+
 // Border copy list of one probe in ring-relative coordinates: out[n][4] = (srcx, srcy, dstx, dsty); returns n.
 int oracle_border_offsets(int side, int32_t* out)
 {

@@ -481,3 +481,34 @@ def test_surface_culling_on_device_matches_oracle(oracle, cfg):
     assert 0 < (chunks_s != 0).sum() < (chunks != 0).sum()
     assert np.array_equal(chunks_s, want_chunks_s) and int(cull_s[0]) == int(want_cull_s[0]) and np.array_equal(cull_s[1:small], want_cull_s[1:small])
     pipe.close()
+
+
+@pytest.mark.parametrize("cfg,flags", [("c1", 0), ("city64", 0), ("city64", abi.FLAG_SDF_LOADS)])
+def test_generic_global_sdf_trace_matches_oracle(oracle, cfg, flags):
+    """Row f4: lux_ddgi_trace_global_sdf = tracyGlobalSDF for arbitrary rays (shadow / reflection / surface-cache light rays): random origins,
+    directions, maxDistance, stepScale in {0.5, 1, 2}, needsHitNormal on and off, start bias 0 (GISDFRays, SDFShadow) and 2 (SDFDeferredLight).
+    Every field of every GlobalSDFHit equals the oracle's, bit for bit."""
+    sc = scenes.build(cfg, with_atlas=False)
+    pipe = ddgi.DDGIPipeline(sc.uniform, flags=flags)
+    pipe.set_global_sdf(sc.sdf_data, sc.sdf, sc.mip)
+    rng = np.random.default_rng(11)
+    n = 20000
+    c = np.array([sc.sdf_data.cascadePosDistance[0][i] for i in range(3)], dtype=np.float32)
+    D = float(sc.sdf_data.cascadePosDistance[0][3])
+    traces = np.zeros(n, dtype=abi.SDF_TRACE_DTYPE)
+    traces["worldPosition"] = (c + rng.uniform(-1.1 * D, 1.1 * D, size=(n, 3))).astype(np.float32)  # some origins outside the cascade
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    d[:64] = np.eye(3, dtype=np.float32)[rng.integers(0, 3, 64)] * rng.choice([-1.0, 1.0], size=(64, 1)).astype(np.float32)  # axis aligned
+    traces["worldDirection"] = d / np.linalg.norm(d, axis=1, keepdims=True)
+    traces["minDistance"] = rng.uniform(0, 1, n).astype(np.float32)
+    traces["maxDistance"] = np.where(rng.random(n) < 0.3, abi.GLOBAL_SDF_WORLD_SIZE, rng.uniform(0.5, 3 * D, n)).astype(np.float32)
+    traces["stepScale"] = rng.choice(np.float32([0.5, 1.0, 2.0]), n)
+    traces["needsHitNormal"] = rng.integers(0, 2, n)
+    for bias in (0.0, 2.0):
+        want = oracle.trace_global_sdf(sc.sdf_data, sc.sdf, sc.mip, traces, bias)
+        got = pipe.trace_global_sdf(traces, bias)
+        assert (want["hitTime"] >= 0).mean() > 0.2 and (want["hitTime"] < 0).mean() > 0.05
+        for f in abi.SDF_HIT_DTYPE.names:
+            a, b = got[f].view(np.uint32), want[f].view(np.uint32)
+            assert np.array_equal(a, b), f"bias {bias}: {f} differs on {(a != b).sum()} of {a.size} values"
+    pipe.close()

@@ -339,3 +339,47 @@ def test_cornell_frame_is_sane(oracle):
     c = p.counters
     assert c["mipTaps"] == c["steps"] + c["hits"]  # the hitting step breaks before step++ (SDFCommon.glsl:143-186)
     assert c["texTaps"] >= 6 * c["hits"]  # 6 normal taps per hit
+
+
+def test_generic_sdf_trace_reproduces_the_probe_trace(oracle):
+    """Row f4: oracle_trace_global_sdf is the same tracyGlobalSDF the probe trace calls (pinned by GISDFRays.comp.spv).  With that
+    shader's arguments (bias 0, stepScale 1, maxDistance = world size) its hit times give the probe trace's stored distances, its
+    normals are unit vectors; needsHitNormal = false returns a zero normal; a short maxDistance turns far hits into misses."""
+    sc = scenes.cornell_scene(res=32, counts=(2, 2, 2), rays=64)
+    rot = scenes.frame_rotation(3)
+    osc = oracle.OracleScene(sc)
+    rad, dd, _, _ = osc.trace(rot)
+    dirs = dd.view(np.float16).astype(np.float32)[0, :, :3]
+    # exact fp32 directions: rebuild them the way the engine / oracle do
+    L = oracle.lib()
+    d32 = np.zeros((sc.rays, 3), dtype=np.float32)
+    import ctypes as C
+    L.oracle_spherical_fibonacci.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    r16 = np.ascontiguousarray(rot, dtype=np.float32)
+    for i in range(sc.rays):
+        L.oracle_spherical_fibonacci(i, sc.rays, r16.ctypes.data_as(C.c_void_p), d32[i].ctypes.data_as(C.c_void_p))
+    assert np.allclose(d32, dirs, atol=2e-3)
+    u = sc.uniform
+    traces = np.zeros(sc.probes * sc.rays, dtype=abi.SDF_TRACE_DTYPE)
+    k = 0
+    for p in range(sc.probes):
+        o = [u.startPosition[a] + u.step[a] * c for a, c in enumerate((p % 2, (p // 2) % 2, p // 4))]
+        for r in range(sc.rays):
+            traces[k]["worldPosition"], traces[k]["worldDirection"] = o, d32[r]
+            traces[k]["maxDistance"], traces[k]["stepScale"], traces[k]["needsHitNormal"] = abi.GLOBAL_SDF_WORLD_SIZE, 1.0, 1
+            k += 1
+    hits = oracle.trace_global_sdf(sc.sdf_data, sc.sdf, sc.mip, traces, 0.0)
+    stored = dd.view(np.float16).astype(np.float32)[..., 3].reshape(-1)
+    hit = hits["hitTime"] >= 0
+    inside = hit & (hits["hitSDF"] <= 0) & (hits["hitTime"] <= sc.sdf_data.cascadeVoxelSize[0])
+    want = np.where(hit & ~inside, np.maximum(hits["hitTime"] + np.float32(0.5) * np.float32(sc.sdf_data.cascadeVoxelSize[0]), 0), np.float32(abi.GLOBAL_SDF_WORLD_SIZE))
+    assert np.array_equal(want.astype(np.float16), stored.astype(np.float16)) and hit.mean() > 0.9
+    n = np.linalg.norm(hits["hitNormal"][hit], axis=1)
+    assert np.allclose(n, 1.0, atol=1e-5)
+    t2 = traces.copy()
+    t2["needsHitNormal"] = 0
+    t2["maxDistance"] = 3.0
+    h2 = oracle.trace_global_sdf(sc.sdf_data, sc.sdf, sc.mip, t2, 0.0)
+    assert (h2["hitNormal"] == 0).all() and (h2["hitTime"] >= 0).sum() < hit.sum()
+    near = hit & (hits["hitTime"] < 2.0)
+    assert np.array_equal(h2["hitTime"][near], hits["hitTime"][near])  # maxDistance only shortens the ray
