@@ -2693,7 +2693,8 @@ static void launch_blend_irradiance_t(const BlendParams& p, cudaStream_t s)
 void launch_blend_irradiance(const BlendParams& p, cudaStream_t s)
 {
     // 64-probe tiles only when they still give every SM two blocks; measured on a 1/8 C4 shard (8192 probes): 0.264 -> 0.229 ms
-    if (p.probeCount >= 2 * 148 * 64)
+    static const int big = getenv("LUX_BLEND_IRR_PB64_MIN") ? atoi(getenv("LUX_BLEND_IRR_PB64_MIN")) : 2 * 148 * 64; // tuning hook
+    if (p.probeCount >= big)
         launch_blend_irradiance_t<64>(p, s);
     else
         launch_blend_irradiance_t<32>(p, s);
@@ -2739,7 +2740,10 @@ void launch_blend_depth(const BlendParams& p, cudaStream_t s)
         return;
     if (resident && p.probeCount >= 32 * 64 && launch_blend_depth_resident_t<32>(p, s))
         return;
-    if (p.probeCount >= 2 * 148 * 64)
+    // 32-probe tiles (two blocks per SM, 90 KB each) beat 64-probe tiles at every size measured: C4 full volume 0.83 -> 0.72 ms, 1/8 shard
+    // 0.123 -> 0.10 ms; the barrier between the staged ray chunks is hidden by the second block.  LUX_BLEND_DEPTH_PB64_MIN is a tuning hook.
+    static const int big = getenv("LUX_BLEND_DEPTH_PB64_MIN") ? atoi(getenv("LUX_BLEND_DEPTH_PB64_MIN")) : 0x7fffffff;
+    if (p.probeCount >= big)
         launch_blend_depth_t<64>(p, s);
     else if (p.probeCount >= 64 * 64)
         launch_blend_depth_t<32>(p, s);
