@@ -110,7 +110,7 @@ struct LuxDDGIContext
     // surface cache
     bool                      hasAtlas = false;
     LuxGlobalSurfaceAtlasData atlasData{};
-    DeviceBuffer              chunks, cull, objects, objectInverse, tiles, light, atlasDepth, chunkMasks;
+    DeviceBuffer              chunks, cull, objects, objectInverse, tiles, tileZRow, light, atlasDepth, chunkMasks;
     bool                      masksDirty = true;
 
     // sky
@@ -446,6 +446,7 @@ static int launchBatch(LuxDDGIContext& c, const LuxDDGIContext::Batch& b, int ba
         p.objectInverse = (const float*)c.objectInverse.ptr;
         p.chunkMasks    = (c.flags & LUX_DDGI_FLAG_NO_PREFILTER) ? nullptr : (const unsigned long long*)c.chunkMasks.ptr;
         p.tiles         = (const LuxTileBuffer*)c.tiles.ptr;
+        p.tileZRow      = (c.flags & LUX_DDGI_FLAG_NO_PREFILTER) ? nullptr : (const float4*)c.tileZRow.ptr;
         p.light         = (const uint2*)c.light.ptr;
         p.depth         = (const float*)c.atlasDepth.ptr;
     }
@@ -751,7 +752,7 @@ int lux_ddgi_destroy(LuxDDGIContext* c)
         cudaStreamSynchronize(c->auxStream);
     DeviceBuffer* all[] = {&c->radiance, &c->directionDepth, &c->irradiance[0], &c->irradiance[1], &c->depth[0], &c->depth[1],
                            &c->dirs, &c->wIrr, &c->wDepth, &c->scaleIrr, &c->scaleDepth, &c->nzIrr, &c->nzDepth, &c->origins, &c->records, &c->meta, &c->chunkCounter, &c->sortTicket, &c->binCounts, &c->binBlockSums, &c->sortedIdx, &c->dirsHalf, &c->sdf, &c->mip, &c->chunks, &c->cull,
-                           &c->objects, &c->objectInverse, &c->chunkMasks, &c->tiles, &c->light, &c->atlasDepth, &c->sky};
+                           &c->objects, &c->objectInverse, &c->chunkMasks, &c->tiles, &c->tileZRow, &c->light, &c->atlasDepth, &c->sky};
     for (DeviceBuffer* b : all)
         b->release();
     releaseSdfTextures(*c);
@@ -1213,6 +1214,14 @@ int lux_ddgi_set_surface_atlas(LuxDDGIContext* c, const LuxGlobalSurfaceAtlasDat
     }
     lux::launch_object_inverse((const LuxObjectBuffer*)c->objects.ptr, (int)objectsCount, (float*)c->objectInverse.ptr, c->stream);
     c->launches += objectsCount ? 1 : 0;
+    if (c->tileZRow.bytes != tilesCount * 16)
+    {
+        c->tileZRow.release();
+        LUX_CUDA(cudaMalloc(&c->tileZRow.ptr, tilesCount ? tilesCount * 16 : 1));
+        c->tileZRow.bytes = tilesCount * 16;
+    }
+    lux::launch_tile_zrow((const LuxTileBuffer*)c->tiles.ptr, (int)tilesCount, (float4*)c->tileZRow.ptr, c->stream);
+    c->launches += tilesCount ? 1 : 0;
     LUX_CUDA(cudaGetLastError());
     if (kind == LUX_MEM_HOST)
         LUX_CUDA(cudaStreamSynchronize(c->stream));

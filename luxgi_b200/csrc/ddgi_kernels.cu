@@ -975,6 +975,15 @@ __device__ __forceinline__ f4 sample_global_surface_atlas_2p(const TraceParams& 
                 uint32_t tileOffset = __ldg(object->tileOffset + i);
                 if (tileOffset == 0)
                     continue;
+                if (P.tileZRow)
+                { // Exact early reject: the weight is positive only if the z component of the transformed normal is; its sign is that
+                  // of the un-normalised z (normalize multiplies by a positive number, NaN compares false like the full path), and the
+                  // expression below is character for character the r.z of mat4_mul_point.  Three of a box's six faces leave here.
+                    float4 zr = __ldg(P.tileZRow + tileOffset);
+                    float  rz = ((zr.x * normal.x + zr.y * normal.y) + zr.z * normal.z) + zr.w * 1.0f;
+                    if (!(rz > 0.0f))
+                        continue;
+                }
                 float tm[16];
                 float nw = tile_normal_weight(P.tiles + tileOffset, normal, tm);
                 if (nw > 0.0f)
@@ -2570,6 +2579,20 @@ int launch_blend_weights(const uint2* dirsHalf, int R, int Rpad, float sharpness
     blend_scales_kernel<<<5, 64, 0, s>>>(wIrr, wDepth, R, scaleIrr, scaleDepth);
     blend_nonzero_kernel<<<(Rpad + 63) / 64, 64, 0, s>>>(wIrr, wDepth, Rpad, nzIrr, nzDepth);
     return 3;
+}
+
+// third row + translation of every tile transform, (m[2], m[6], m[10], m[14]): what the sign of a tile's normal weight depends on
+__global__ void tile_zrow_kernel(const LuxTileBuffer* __restrict__ tiles, int count, float4* __restrict__ out)
+{
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < count)
+        out[k] = make_float4(tiles[k].transform[2], tiles[k].transform[6], tiles[k].transform[10], tiles[k].transform[14]);
+}
+
+void launch_tile_zrow(const LuxTileBuffer* tiles, int count, float4* out, cudaStream_t s)
+{
+    if (count > 0)
+        tile_zrow_kernel<<<(count + 127) / 128, 128, 0, s>>>(tiles, count, out);
 }
 
 void launch_object_inverse(const LuxObjectBuffer* objects, int count, float* inv, cudaStream_t s)

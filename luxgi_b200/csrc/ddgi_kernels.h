@@ -32,6 +32,7 @@ struct TraceParams
     const float*           objectInverse; // [objects][16], inverse(object.transform) precomputed at upload
     const unsigned long long* chunkMasks; // [40^3][64] conservative per-sub-cell candidate masks, or null
     const LuxTileBuffer*   tiles;
+    const float4*          tileZRow;      // [tiles] (m[2], m[6], m[10], m[14]) of each tile transform, or null (exact early reject in the shade)
     const uint2*           light; // RGBA16F
     const float*           depth; // D32F
     // sky
@@ -85,6 +86,7 @@ int  launch_blend_weights(const uint2* dirDistRow0, int raysPerProbe, int raysPa
 void launch_chunk_masks(const uint32_t* chunks, const uint32_t* cull, const LuxObjectBuffer* objects, const float* objectInverse,
                         uint32_t objectsCount, float chunkSize, float thrMax, unsigned long long* masks, cudaStream_t s);
 void launch_object_inverse(const LuxObjectBuffer* objects, int count, float* inv, cudaStream_t s);
+void launch_tile_zrow(const LuxTileBuffer* tiles, int count, float4* out, cudaStream_t s);
 
 // variant 0: one thread per ray (simple); 1: wavefront (march + shade), explicit fp16 loads; 2: wavefront, layered-texture
 // gathers.  Returns the number of kernels launched.
