@@ -231,7 +231,7 @@ def run_lux(args):
     if args.unsorted:
         flags |= abi.FLAG_SHADE_UNSORTED
     shard_rank, shard_world = (rank, world) if args.emulate_shard is None else tuple(int(x) for x in args.emulate_shard.split('/'))
-    # The measured pipe runs lux_ddgi_update as shipped (probe batches pipelined over two streams, no stage events); the per-stage
+    # The measured pipe runs lux_ddgi_update as shipped (blend weights on a second stream during the march, no stage events); the per-stage
     # times and the kernel roofline come from a second, serialized pass below (LUX_DDGI_FLAG_STAGE_TIMERS = one batch, one stream).
     pipe = ddgi.DDGIPipeline(u, device=local, rank=shard_rank, world=shard_world, flags=flags, stream=stream.cuda_stream)
     pipe.set_scene(sc)
@@ -446,7 +446,7 @@ def run_lux(args):
                          "blend_border": blend_launch_ms,
                          "update_minus_stage_sum": ms_per_step - (setup_ms + trace_ms + blend_ms) / args.steps,
                          "note": "stages timed in a second, serialized pass (one batch, one stream, CUDA events on the engine's stream); "
-                                 "ms_per_update is the shipped update: probe batches pipelined over two streams"},
+                                 "ms_per_update is the shipped update (blend weights computed on a second stream during the march)"},
             "trace_rays_per_s": probes_rank * world * R / (trace_launch_ms * 1e-3),
             "per_rank_trace_blend_ms": per_rank,
             "roofline": roofs[dominant],

@@ -426,14 +426,25 @@ __device__ __forceinline__ Hit trace_global_sdf(const TraceParams& P, f3 origin,
     return hit;
 }
 
+__device__ __forceinline__ int wrap_texel(int a, int n)
+{
+    if (a >= -n && a < 2 * n)
+    {
+        a = a < 0 ? a + n : a;
+        return a >= n ? a - n : a;
+    }
+    return ((a % n) + n) % n;
+}
+
 __device__ __forceinline__ void gather_coords(float u, float v, int W, int H, bool repeat, int& i0, int& i1, int& j0, int& j1)
 {
     int a = (int)floorf(u * (float)W - 0.5f);
     int b = (int)floorf(v * (float)H - 0.5f);
     if (repeat)
-    {
-        i0 = ((a % W) + W) % W; i1 = (((a + 1) % W) + W) % W;
-        j0 = ((b % H) + H) % H; j1 = (((b + 1) % H) + H) % H;
+    { // repeat addressing; atlas coordinates live in [0, 1], so the texel index is within one period of the range: a conditional add /
+      // subtract gives the same residue as the two integer modulos (~20 instructions each), which remain for anything further out
+        i0 = wrap_texel(a, W); i1 = wrap_texel(a + 1, W);
+        j0 = wrap_texel(b, H); j1 = wrap_texel(b + 1, H);
     }
     else
     {
