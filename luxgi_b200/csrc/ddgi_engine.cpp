@@ -999,8 +999,6 @@ int lux_ddgi_build_global_sdf(LuxDDGIContext* c, const LuxGlobalSDFData* data, c
             const size_t cnt = (size_t)std::max(meshes[m].size[0] >> l, 1u) * std::max(meshes[m].size[1] >> l, 1u) * std::max(meshes[m].size[2] >> l, 1u);
             LUX_CUDA_CLEAN(cudaMemcpyAsync(dVolumes + off, meshes[m].mips[l], cnt * 2, cudaMemcpyHostToDevice, c->stream));
         }
-    if (meshCount > 0)
-        LUX_CUDA_CLEAN(cudaMemcpyAsync(dRecords, records.data(), records.size() * sizeof(lux::SdfMeshRecord), cudaMemcpyHostToDevice, c->stream));
 
     for (int k = 0; k < casc; k++)
     {
@@ -1314,10 +1312,13 @@ int lux_ddgi_cull_surface_objects(LuxDDGIContext* c, uint32_t capacityWords)
     { // size it from the counts instead of the worst case: one extra counting pass
         std::vector<uint32_t> tmp(1);
         DeviceBuffer probe;
-        LUX_CUDA(cudaMalloc(&probe.ptr, nchunks * 4));
+        uint32_t*    dummyCull = nullptr;
+        if (cudaMalloc(&probe.ptr, nchunks * 4) != cudaSuccess || cudaMalloc(&dummyCull, 16) != cudaSuccess)
+        {
+            probe.release();
+            return done(fail(LUX_ERR_OUT_OF_MEMORY, "surface cull sizing scratch"));
+        }
         probe.bytes = nchunks * 4;
-        uint32_t* dummyCull = nullptr;
-        LUX_CUDA(cudaMalloc(&dummyCull, 16));
         lux::launch_surface_cull((const LuxObjectBuffer*)c->objects.ptr, c->atlasData.objectsCount, c->atlasData.chunkSize, 0u, scratch, scratch + 65536,
                                  scratch + 65536 + 16, (uint32_t*)probe.ptr, dummyCull, 1u, c->stream); // capacity 0: nothing is written but cull[0]
         c->launches += 5;
@@ -1325,6 +1326,7 @@ int lux_ddgi_cull_surface_objects(LuxDDGIContext* c, uint32_t capacityWords)
         if (e == cudaSuccess)
             e = cudaStreamSynchronize(c->stream);
         cudaFree(dummyCull);
+        probe.release();
         if (e != cudaSuccess)
             return done(fail(LUX_ERR_CUDA, "surface cull sizing: %s", cudaGetErrorString(e)));
         words = tmp[0];
