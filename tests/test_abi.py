@@ -88,3 +88,25 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cpp", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in text.lower() or f in ("scenes.py",), f"{f} mentions the oracle"
+
+
+def test_header_is_plain_c_and_cpp(tmp_path):
+    """include/luxddgi.h is the boundary a C or C++ host binds: it must compile on its own as C99 and as C++17, and the struct sizes the
+    Python layer assumes must be the compiler's."""
+    import shutil
+    import subprocess
+
+    inc = os.path.join(ROOT, "include")
+    src = tmp_path / "abi_check.c"
+    src.write_text('#include "luxddgi.h"\n#include <stdio.h>\nint main(void) { printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(LuxDDGIUniform), '
+                   'sizeof(LuxTracePushConstants), sizeof(LuxGlobalSDFData), sizeof(LuxGlobalSurfaceAtlasData), sizeof(LuxObjectBuffer), sizeof(LuxTileBuffer), '
+                   'sizeof(LuxObjectRasterizeData), sizeof(LuxGlobalSDFTrace) + sizeof(LuxGlobalSDFHit)); return 0; }\n')
+    cc = shutil.which("gcc") or "/usr/bin/gcc"
+    exe = tmp_path / "abi_check"
+    subprocess.run([cc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", inc, str(src), "-o", str(exe)], check=True)
+    sizes = [int(x) for x in subprocess.run([str(exe)], stdout=subprocess.PIPE, text=True, check=True).stdout.split()]
+    assert sizes == [96, 80, 96, 32, 128, 96, 176, 40 + 28]
+    cxx = shutil.which("g++") or "/usr/bin/g++"
+    cpp = tmp_path / "abi_check.cpp"
+    cpp.write_text('#include "luxddgi.h"\nstatic_assert(sizeof(LuxDDGIUniform) == 96, "DDGIUniform");\nint main() { return sizeof(LuxMeshSDF) == 0; }\n')
+    subprocess.run([cxx, "-std=c++17", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-I", inc, str(cpp)], check=True)
