@@ -41,9 +41,10 @@ def load():
     global _LIB
     if _LIB is not None:
         return _LIB
-    if not os.path.exists(_LIB_PATH):
-        raise RuntimeError(f"{_LIB_PATH} is missing: build it with `python -m luxgi_b200.build` (there is no CPU fallback)")
-    L = C.CDLL(_LIB_PATH)
+    path = os.environ.get("LUX_DDGI_LIB", _LIB_PATH)  # tuning hook: an alternative build of the same library
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} is missing: build it with `python -m luxgi_b200.build` (there is no CPU fallback)")
+    L = C.CDLL(path)
     vp, i32, u32, sz = C.c_void_p, C.c_int32, C.c_uint32, C.c_size_t
     L.lux_ddgi_version.restype = u32
     L.lux_ddgi_last_error.restype = C.c_char_p
