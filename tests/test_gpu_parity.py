@@ -285,12 +285,18 @@ def probe_tiles(atlas, u, ids, side):
     return np.stack([atlas[1 + (p // per_row) * S: 1 + (p // per_row) * S + S, 1 + (p % per_row) * S: 1 + (p % per_row) * S + S] for p in ids])
 
 
-@pytest.mark.parametrize("cfg,sample", [("c4", 4096)])
+@pytest.mark.parametrize("cfg,sample", [("c4", 4096), ("c5", 2048)])
 def test_full_size_config_on_a_stratified_probe_subsample(oracle, cfg, sample):
-    """BASELINE configs[3] at FULL size (city 512^3, 64x16x64 probes, 512 rays, 33.5 M rays per update) on the GPU; the oracle
-    replays a stratified subsample of probes from the same device-generated inputs, two frames (the second
-    through the hysteresis branch).  Rays and the subsample's atlas tiles (interior + border) must match bit for bit."""
+    """BASELINE configs[3] and [4] at FULL size on one GPU (city 512^3, 64x16x64 probes, 512 rays = 33.5 M rays per update; city 1024^3,
+    128x32x128 probes, 1024 rays = 537 M rays per update, 2 GiB SDF); the oracle replays a stratified subsample of probes
+    from the same device-generated inputs, two frames (the second through the hysteresis branch).  Rays and the subsample's atlas tiles
+    (interior + border) must match bit for bit."""
     import torch
+
+    def ray_rows(pipe, buf, ids):  # gather the subsample's rows on the device: the C5 ray buffers are 4.3 GB each
+        pipe.synchronize()
+        t = torch.as_tensor(pipe.device_view(buf), device="cuda")
+        return t[torch.as_tensor(ids, device="cuda", dtype=torch.long)].cpu().numpy().view(np.uint16)
 
     sc = scenes.build(cfg, device="cuda")
     u = sc.uniform
@@ -305,7 +311,7 @@ def test_full_size_config_on_a_stratified_probe_subsample(oracle, cfg, sample):
         rot = scenes.frame_rotation(f)
         pipe.update(rot)
         rad, dd, _, _ = osc.trace(rot, probe_ids=ids)
-        grad, gdd = pipe.radiance[ids], pipe.direction_distance[ids]
+        grad, gdd = ray_rows(pipe, abi.BUF_RADIANCE, ids), ray_rows(pipe, abi.BUF_DIRECTION_DISTANCE, ids)
         assert np.array_equal(gdd, dd), f"frame {f}: direction/distance differ on {(gdd != dd).sum()} values"
         assert np.array_equal(grad, rad), f"frame {f}: radiance differs on {(grad != rad).sum()} values"
         oracle.blend_ids(u, rad, dd, irr[f % 2], dep[f % 2], irr[1 - f % 2], dep[1 - f % 2], first_frame=(f == 0), probe_ids=ids)
