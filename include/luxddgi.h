@@ -186,6 +186,23 @@ typedef struct LuxGlobalSDFHit {
 } LuxGlobalSDFHit;
 
 /* ---------------------------------------------------------------------------------------------------------
+ * Light, 64 bytes (Shaders/Common/Light.glsl:19-29), as SDFDeferredLight.frag's UniformBufferObject carries it (row f4).
+ * type: 0 directional, 1 spot, 2 point (Light.glsl:13-17).  direction.w is the soft-shadow radius (unused by the surface-cache pass).
+ * ------------------------------------------------------------------------------------------------------ */
+#define LUX_LIGHT_DIRECTIONAL 0.0f
+#define LUX_LIGHT_SPOT        1.0f
+#define LUX_LIGHT_POINT       2.0f
+typedef struct LuxLight {
+    float color[4];
+    float position[4];
+    float direction[4];
+    float intensity;
+    float radius;
+    float type;
+    float angle;
+} LuxLight;
+
+/* ---------------------------------------------------------------------------------------------------------
  * a6. Surface-cache records (Shaders/SDF/AtlasCommon.glsl:8-32; host GlobalSurfaceAtlas.cpp:59-73,
  *     SurfaceAtlasTile.h:117-125).
  * ------------------------------------------------------------------------------------------------------ */
@@ -293,6 +310,14 @@ LUX_API int lux_ddgi_set_uniform(LuxDDGIContext* ctx, const LuxDDGIUniform* unif
 /* uGlobalSDF / uGlobalMipSDF + UniformBufferObject.sdfData (DDGIRenderer.cpp:304-305,314). fp16 texels. */
 LUX_API int lux_ddgi_set_global_sdf(LuxDDGIContext* ctx, const LuxGlobalSDFData* data,
                             const void* sdfR16F, const void* mipR16F, LuxMemKind kind);
+
+/* f4: direct lighting of surface-cache texels = Shaders/SDF/SDFDeferredLight.frag:44-129 (fetchLight, shadow ray through the global SDF with
+ * start bias 2, BRDF of Raytraced/BRDF.glsl:65-83), blended ADDITIVELY into the RGBA16F light cache as the reference's pipeline does
+ * (GlobalSurfaceAtlas.cpp:950-972: BlendMode::Add, alpha += 1).  One call = one light over the listed atlas texels; the per-texel arrays are
+ * what SDFDeferredColor.frag captured there (world position, decoded normal, albedo, (metallic, roughness)).  cameraPos[3] = shadowBias. */
+LUX_API int lux_ddgi_surface_direct_light(LuxDDGIContext* ctx, const LuxLight* light, const float cameraPosBias[4], int32_t count,
+                                          const uint32_t* texelIndex, const float* worldPos, const float* normal, const float* albedo,
+                                          const float* metallicRoughness, LuxMemKind kind);
 
 /* f4: tracyGlobalSDF for arbitrary rays through the bound global SDF (shadow / reflection / surface-cache light rays).
  * cascadeTraceStartBias = the shader call's last argument (0 in GISDFRays / SDFShadow, 2 in SDFDeferredLight). */

@@ -227,6 +227,24 @@ def probe_count(u):
     return u.probeCounts[0] * u.probeCounts[1] * u.probeCounts[2]
 
 
+class Light(C.Structure):  # LuxLight = Common/Light.glsl:19-29, 64 bytes (row f4: lux_ddgi_surface_direct_light)
+    _fields_ = [("color", C.c_float * 4), ("position", C.c_float * 4), ("direction", C.c_float * 4), ("intensity", C.c_float), ("radius", C.c_float),
+                ("type", C.c_float), ("angle", C.c_float)]
+
+
+LIGHT_DIRECTIONAL, LIGHT_SPOT, LIGHT_POINT = 0.0, 1.0, 2.0
+
+
+def make_light(values16) -> Light:
+    """color[4], position[4], direction[4], intensity, radius, type, angle -> Light."""
+    v = [float(x) for x in values16]
+    assert len(v) == 16
+    l = Light()
+    l.color[:], l.position[:], l.direction[:] = v[0:4], v[4:8], v[8:12]
+    l.intensity, l.radius, l.type, l.angle = v[12:16]
+    return l
+
+
 # GlobalSDFTrace / GlobalSDFHit (row f4: lux_ddgi_trace_global_sdf), as numpy record dtypes
 SDF_TRACE_DTYPE = np.dtype([("worldPosition", "<f4", 3), ("minDistance", "<f4"), ("worldDirection", "<f4", 3), ("maxDistance", "<f4"),
                             ("stepScale", "<f4"), ("needsHitNormal", "<u4")])

@@ -1864,6 +1864,65 @@ int lux_ddgi_indirect_light(LuxDDGIContext* c, const void* baseLightRGBA16F, int
     return LUX_OK;
 }
 
+int lux_ddgi_surface_direct_light(LuxDDGIContext* c, const LuxLight* light, const float cameraPosBias[4], int32_t count, const uint32_t* texelIndex,
+                                  const float* worldPos, const float* normal, const float* albedo, const float* metallicRoughness, LuxMemKind kind)
+{
+    CHECK_CTX(c);
+    if (!c->hasSdf)
+        return fail(LUX_ERR_NOT_READY, "no global SDF bound");
+    if (!c->hasAtlas)
+        return fail(LUX_ERR_NOT_READY, "no surface cache bound");
+    if (count < 0 || !light || !cameraPosBias || (count > 0 && (!texelIndex || !worldPos || !normal || !albedo || !metallicRoughness)))
+        return fail(LUX_ERR_INVALID_ARG, "bad surface_direct_light arguments");
+    if (light->type != LUX_LIGHT_DIRECTIONAL && light->type != LUX_LIGHT_SPOT && light->type != LUX_LIGHT_POINT)
+        return fail(LUX_ERR_INVALID_ARG, "unknown light type");
+    if (count == 0)
+        return LUX_OK;
+    const size_t texels = (size_t)c->atlasData.resolution * c->atlasData.resolution;
+    if (c->light.borrowed)
+    { // never write into a caller-owned buffer: take a private copy first
+        void* own = nullptr;
+        LUX_CUDA(cudaMalloc(&own, texels * 8));
+        LUX_CUDA(cudaMemcpyAsync(own, c->light.ptr, texels * 8, cudaMemcpyDeviceToDevice, c->stream));
+        c->light.ptr      = own;
+        c->light.borrowed = false;
+        c->light.bytes    = texels * 8;
+    }
+    lux::TraceParams p{};
+    p.sdf      = c->sdfData;
+    p.tex      = (const uint16_t*)c->sdf.ptr;
+    p.mip      = (const uint16_t*)c->mip.ptr;
+    p.res      = (int)c->sdfData.resolution;
+    p.mipRes   = p.res / 4;
+    p.cascades = (int)c->sdfData.cascadesCount;
+    p.texObj   = c->sdfTex;
+    p.mipObj   = c->mipTex;
+    void *dT = nullptr, *dP = nullptr, *dN = nullptr, *dA = nullptr, *dM = nullptr;
+    bool  oT = false, oP = false, oN = false, oA = false, oM = false;
+    int   rc;
+    if ((rc = stageToDevice(c, texelIndex, (size_t)count * 4, kind, &dT, &oT)) == LUX_OK &&
+        (rc = stageToDevice(c, worldPos, (size_t)count * 12, kind, &dP, &oP)) == LUX_OK &&
+        (rc = stageToDevice(c, normal, (size_t)count * 12, kind, &dN, &oN)) == LUX_OK &&
+        (rc = stageToDevice(c, albedo, (size_t)count * 12, kind, &dA, &oA)) == LUX_OK &&
+        (rc = stageToDevice(c, metallicRoughness, (size_t)count * 8, kind, &dM, &oM)) == LUX_OK)
+    {
+        lux::launch_direct_light(p, c->sdfTex != 0, *light, cameraPosBias, c->light.ptr, count, (const uint32_t*)dT, (const float*)dP, (const float*)dN,
+                                 (const float*)dA, (const float*)dM, c->stream);
+        c->launches += 1;
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess && (oT || oP || oN || oA || oM))
+            e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess)
+            rc = fail(LUX_ERR_CUDA, "surface_direct_light: %s", cudaGetErrorString(e));
+    }
+    if (oT) cudaFree(dT);
+    if (oP) cudaFree(dP);
+    if (oN) cudaFree(dN);
+    if (oA) cudaFree(dA);
+    if (oM) cudaFree(dM);
+    return rc;
+}
+
 int lux_ddgi_get_surface_light_cache(LuxDDGIContext* c, void** devicePtr, size_t* bytes)
 {
     CHECK_CTX(c);

@@ -747,17 +747,12 @@ struct SdfSampler<true>
     __device__ __forceinline__ float sampleMip(float u, float v, float w) const { return sample3D_tex(mip, mw, mh, mh, u, v, w); }
 };
 
-// tracyGlobalSDF (SDFCommon.glsl:98-194) in full generality, for its other users (row f4): one thread per ray.
+// tracyGlobalSDF (SDFCommon.glsl:98-194) in full generality, for its other users (row f4): shadow, reflection and surface-cache light rays.
 template <bool TEX>
-__global__ void __launch_bounds__(128) sdf_rays_kernel(const __grid_constant__ TraceParams P, int count, const LuxGlobalSDFTrace* __restrict__ traces,
-                                                       float cascadeTraceStartBias, LuxGlobalSDFHit* __restrict__ hits)
+__device__ __forceinline__ LuxGlobalSDFHit trace_global_sdf_general(const TraceParams& P, const SdfSampler<TEX>& sdf, const LuxGlobalSDFTrace& tr,
+                                                                     float cascadeTraceStartBias)
 {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= count)
-        return;
-    const SdfSampler<TEX> sdf(P);
     const LuxGlobalSDFData& data = P.sdf;
-    const LuxGlobalSDFTrace tr = traces[k];
     const f3 origin = {tr.worldPosition[0], tr.worldPosition[1], tr.worldPosition[2]}, dir = {tr.worldDirection[0], tr.worldDirection[1], tr.worldDirection[2]};
     LuxGlobalSDFHit hit;
     hit.hitNormal[0] = hit.hitNormal[1] = hit.hitNormal[2] = 0.0f;
@@ -827,7 +822,20 @@ __global__ void __launch_bounds__(128) sdf_rays_kernel(const __grid_constant__ T
         }
         hit.stepsCount += step;
     }
-    hits[k] = hit;
+    return hit;
+}
+
+// one thread per ray of a caller-provided list (lux_ddgi_trace_global_sdf)
+template <bool TEX>
+__global__ void __launch_bounds__(128) sdf_rays_kernel(const __grid_constant__ TraceParams P, int count, const LuxGlobalSDFTrace* __restrict__ traces,
+                                                       float cascadeTraceStartBias, LuxGlobalSDFHit* __restrict__ hits)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count)
+        return;
+    const SdfSampler<TEX> sdf(P);
+    const LuxGlobalSDFTrace tr = traces[k];
+    hits[k] = trace_global_sdf_general<TEX>(P, sdf, tr, cascadeTraceStartBias);
 }
 
 // One tile of one candidate object, split in two: the normal weight (cheap, rejects most tiles) ...
@@ -2267,6 +2275,110 @@ __global__ void indirect_light_kernel(const __grid_constant__ LuxDDGIUniform ddg
     light[idx] = make_uint2(h0 | (h1 << 16), h2 | (b.y & 0xffff0000u));
 }
 
+// SDFDeferredLight.frag:44-129 (fetchLight for directional / point / spot lights, shadow ray through the global SDF with start bias 2,
+// BRDF of Raytraced/BRDF.glsl:8-36,65-83) for a list of surface-cache texels, blended additively into the RGBA16F light cache as the
+// reference's pipeline state does (GlobalSurfaceAtlas.cpp:950-972: BlendMode::Add, so alpha accumulates the 1.0 the shader writes).
+// One thread per listed texel; the shadow march reuses trace_global_sdf_general.  pow() is binary64, rounded once (contract §4).
+__device__ __forceinline__ float powd_rn(float x, float y) { return (float)pow((double)x, (double)y); }
+
+template <bool TEX>
+__global__ void __launch_bounds__(128) direct_light_kernel(const __grid_constant__ TraceParams P, const __grid_constant__ LuxLight L, float camX, float camY,
+                                                           float camZ, float shadowBias, uint2* __restrict__ light, int count,
+                                                           const uint32_t* __restrict__ texel, const float* __restrict__ Pw, const float* __restrict__ N,
+                                                           const float* __restrict__ albedo, const float* __restrict__ metallicRoughness)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count)
+        return;
+    const SdfSampler<TEX> sdf(P);
+    const float PI_F = 3.14159265358979323846f;
+    const f3    worldPos = {Pw[3 * k], Pw[3 * k + 1], Pw[3 * k + 2]}, normal = {N[3 * k], N[3 * k + 1], N[3 * k + 2]};
+    const float alb[3] = {albedo[3 * k], albedo[3 * k + 1], albedo[3 * k + 2]};
+    const float metallic = metallicRoughness[2 * k], roughness = metallicRoughness[2 * k + 1];
+    // fetchLight, SDFDeferredLight.frag:44-81
+    f3    Wi = {0.0f, 0.0f, 0.0f};
+    float dist = LUX_GLOBAL_SDF_WORLD_SIZE, atten = 1.0f;
+    const f3 lightPos = {L.position[0], L.position[1], L.position[2]};
+    if (L.type == LUX_LIGHT_DIRECTIONAL)
+        Wi = {-L.direction[0], -L.direction[1], -L.direction[2]};
+    else if (L.type == LUX_LIGHT_POINT)
+    {
+        f3    dir = lightPos - worldPos;
+        float d   = length3(dir);
+        Wi        = normalize3(dir);
+        atten     = __fdiv_rn(L.radius, powd_rn(d, 2.0f) + 1.0f);
+        dist      = d;
+    }
+    else if (L.type == LUX_LIGHT_SPOT)
+    {
+        f3    Lv          = lightPos - worldPos;
+        float cutoffAngle = 1.0f - L.angle;
+        f3    lightDir    = normalize3(Lv);
+        float d           = length3(Lv);
+        float theta       = dot3(lightDir, {L.direction[0], L.direction[1], L.direction[2]});
+        float epsilon     = cutoffAngle - cutoffAngle * 0.9f;
+        atten             = __fdiv_rn(theta - cutoffAngle, epsilon);
+        atten *= __fdiv_rn(L.radius, powd_rn(d, 2.0f) + 1.0f);
+        atten = gclamp(atten, 0.0f, 1.0f);
+        Wi    = lightDir;
+        dist  = d;
+    }
+    float shadowMask = 1.0f;
+    const float NoL  = dot3(normal, Wi);
+    const float bias = (2.0f * shadowBias) * gclamp(1.0f - NoL, 0.0f, 1.0f) + shadowBias;
+    if (NoL > 0.0f)
+    {
+        if (atten > 0.0f)
+        {
+            const f3 origin = worldPos + normal * shadowBias;
+            LuxGlobalSDFTrace tr;
+            tr.worldPosition[0] = origin.x; tr.worldPosition[1] = origin.y; tr.worldPosition[2] = origin.z;
+            tr.minDistance = 0.0f;
+            tr.worldDirection[0] = Wi.x; tr.worldDirection[1] = Wi.y; tr.worldDirection[2] = Wi.z;
+            tr.maxDistance = dist - bias;
+            tr.stepScale = 1.0f;
+            tr.needsHitNormal = 0u;
+            LuxGlobalSDFHit hit = trace_global_sdf_general<TEX>(P, sdf, tr, 2.0f);
+            shadowMask = hit.hitTime >= 0.0f ? 0.0f : 1.0f;
+        }
+    }
+    else
+        shadowMask = 0.0f;
+    const f3    cam  = {camX, camY, camZ};
+    const f3    view = normalize3(cam - worldPos);
+    const float intensity = powd_rn(L.intensity, 1.4f) + 0.1f;
+    const float Lrad[3] = {L.color[0] * intensity, L.color[1] * intensity, L.color[2] * intensity};
+    const f3    Lh = normalize3(Wi + view);
+    // BRDF, Raytraced/BRDF.glsl:65-83
+    const float Fd = 0.04f, EPSILON = 0.00001f;
+    const float cosLi = gmax(0.0f, dot3(normal, Wi)), cosLh = gmax(0.0f, dot3(normal, Lh)), NdotV = gmax(0.0f, dot3(normal, view));
+    const float ct = gmax(dot3(Lh, view), 0.0f);
+    const float p5 = powd_rn(gclamp(1.0f - ct, 0.0f, 1.0f), 5.0f);
+    const float alpha = roughness * roughness, alphaSq = alpha * alpha;
+    const float denom = (cosLh * cosLh) * (alphaSq - 1.0f) + 1.0f;
+    const float D     = __fdiv_rn(alphaSq, (PI_F * denom) * denom);
+    const float r1 = roughness + 1.0f, kk = __fdiv_rn(r1 * r1, 8.0f);
+    const float G   = __fdiv_rn(cosLi, cosLi * (1.0f - kk) + kk) * __fdiv_rn(NdotV, NdotV * (1.0f - kk) + kk);
+    const float den = gmax(EPSILON, (4.0f * cosLi) * NdotV);
+    const uint32_t idx = texel[k];
+    const uint2    b   = light[idx];
+    const f4       dst = unpack_rgba16f(b);
+    const float    dv[3] = {dst.x, dst.y, dst.z};
+    uint32_t h[4];
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+    {
+        float F0 = Fd * (1.0f - metallic) + alb[c] * metallic;
+        float F  = F0 + (1.0f - F0) * p5;
+        float kd = (1.0f - F) * (1.0f - metallic);
+        float br = __fdiv_rn(kd * alb[c], PI_F) + __fdiv_rn((F * D) * G, den);
+        float o  = (((br * Lrad[c]) * cosLi) * shadowMask) * atten;
+        h[c]     = f2h_bits(o + dv[c]);
+    }
+    h[3]       = f2h_bits(1.0f + dst.w);
+    light[idx] = make_uint2(h[0] | (h[1] << 16), h[2] | (h[3] << 16));
+}
+
 // =====================================================================================================================
 // Global SDF build: mesh distance fields -> cascade volume -> min-mip.
 //   sdf_object_data_kernel   chunkCalculate's ObjectRasterizeData (GlobalDistanceField.cpp:484-508), one thread per mesh
@@ -2540,6 +2652,20 @@ void launch_sdf_rays(const TraceParams& p, bool useTextures, int count, const Lu
         sdf_rays_kernel<true><<<(count + 127) / 128, 128, 0, s>>>(p, count, traces, cascadeTraceStartBias, hits);
     else
         sdf_rays_kernel<false><<<(count + 127) / 128, 128, 0, s>>>(p, count, traces, cascadeTraceStartBias, hits);
+}
+
+void launch_direct_light(const TraceParams& p, bool useTextures, const LuxLight& l, const float* cameraPosBias, void* light, int count,
+                         const uint32_t* texel, const float* P, const float* N, const float* albedo, const float* metallicRoughness, cudaStream_t s)
+{
+    if (count <= 0)
+        return;
+    const int grid = (count + 127) / 128;
+    if (useTextures)
+        direct_light_kernel<true><<<grid, 128, 0, s>>>(p, l, cameraPosBias[0], cameraPosBias[1], cameraPosBias[2], cameraPosBias[3], (uint2*)light, count, texel, P,
+                                                        N, albedo, metallicRoughness);
+    else
+        direct_light_kernel<false><<<grid, 128, 0, s>>>(p, l, cameraPosBias[0], cameraPosBias[1], cameraPosBias[2], cameraPosBias[3], (uint2*)light, count, texel, P,
+                                                         N, albedo, metallicRoughness);
 }
 
 void launch_indirect_light(const LuxDDGIUniform& ddgi, const void* irr, const void* dep, void* light, const void* base, int count,

@@ -117,6 +117,10 @@ void launch_indirect_light(const LuxDDGIUniform& ddgi, const void* irr, const vo
 void launch_sdf_rays(const TraceParams& p, bool useTextures, int count, const LuxGlobalSDFTrace* traces, float cascadeTraceStartBias,
                      LuxGlobalSDFHit* hits, cudaStream_t s);
 
+// SDFDeferredLight.frag for a list of surface-cache texels, additive into the RGBA16F light cache
+void launch_direct_light(const TraceParams& p, bool useTextures, const LuxLight& l, const float* cameraPosBias, void* light, int count,
+                         const uint32_t* texel, const float* P, const float* N, const float* albedo, const float* metallicRoughness, cudaStream_t s);
+
 // ---- global SDF build ----
 struct SdfMeshRecord // device copy of LuxMeshSDF without the host pointers
 {

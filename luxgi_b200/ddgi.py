@@ -26,7 +26,7 @@ EXPORTS = [
     "lux_ddgi_download", "lux_ddgi_download_async", "lux_ddgi_download_rows_async", "lux_ddgi_set_ray_buffers", "lux_ddgi_restore", "lux_ddgi_get_state", "lux_ddgi_shard_layout",
     "lux_ddgi_get_stage_ms", "lux_ddgi_sample_irradiance", "lux_ddgi_sample_probe", "lux_ddgi_indirect_light",
     "lux_ddgi_get_surface_light_cache", "lux_ddgi_build_global_sdf", "lux_ddgi_build_sdf_mip", "lux_ddgi_sdf_file_read", "lux_ddgi_download_fence", "lux_ddgi_wait_fence", "lux_ddgi_set_nccl_comm", "lux_ddgi_update_surface_light_cache_rows", "lux_ddgi_cull_surface_objects",
-    "lux_ddgi_get_surface_cull_lists", "lux_ddgi_trace_global_sdf",
+    "lux_ddgi_get_surface_cull_lists", "lux_ddgi_trace_global_sdf", "lux_ddgi_surface_direct_light",
 ]
 
 
@@ -77,6 +77,7 @@ def load():
         "lux_ddgi_sample_probe": [vp, i32, i32, vp, vp, vp, vp, vp, i32],
         "lux_ddgi_indirect_light": [vp, vp, i32, vp, vp, vp, vp, vp, C.c_float, vp, i32],
         "lux_ddgi_get_surface_light_cache": [vp, C.POINTER(vp), C.POINTER(sz)],
+        "lux_ddgi_surface_direct_light": [vp, C.POINTER(abi.Light), vp, i32, vp, vp, vp, vp, vp, i32],
         "lux_ddgi_build_global_sdf": [vp, C.POINTER(abi.GlobalSDFData), C.POINTER(abi.MeshSDF), i32, C.c_float],
         "lux_ddgi_build_sdf_mip": [vp],
         "lux_ddgi_download_fence": [vp, C.POINTER(C.c_uint64)],
@@ -406,6 +407,16 @@ class DDGIPipeline:
         base = None if base_light is None else _as_host(base_light)
         _check(self._lib.lux_ddgi_indirect_light(self._h, None if base is None else _host_ptr(base), len(texel), _host_ptr(texel), _host_ptr(P),
                                                  _host_ptr(N), _host_ptr(albedo), _host_ptr(metallic), float(intensity), _host_ptr(cam), abi.MEM_HOST))
+
+    def surface_direct_light(self, light, camera_pos_bias, texel, P, N, albedo, metallic_roughness):
+        """Direct lighting of surface-cache texels by one light (SDFDeferredLight.frag), added into the light cache; camera_pos_bias = (xyz, shadow bias)."""
+        texel = np.ascontiguousarray(texel, dtype=np.uint32)
+        P, N, albedo = (np.ascontiguousarray(a, dtype=np.float32).reshape(-1, 3) for a in (P, N, albedo))
+        mr = np.ascontiguousarray(metallic_roughness, dtype=np.float32).reshape(-1, 2)
+        cam = np.ascontiguousarray(camera_pos_bias, dtype=np.float32).reshape(4)
+        assert len(P) == len(N) == len(albedo) == len(mr) == len(texel)
+        _check(self._lib.lux_ddgi_surface_direct_light(self._h, C.byref(light), _host_ptr(cam), len(texel), _host_ptr(texel), _host_ptr(P), _host_ptr(N),
+                                                       _host_ptr(albedo), _host_ptr(mr), abi.MEM_HOST))
 
     def surface_light_cache(self) -> np.ndarray:
         p, n = C.c_void_p(), C.c_size_t()

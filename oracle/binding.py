@@ -351,3 +351,32 @@ def trace_global_sdf(sdf_data, sdf, mip, traces, start_bias=0.0):
     rc = L.oracle_trace_global_sdf(C.byref(sdf_data), _ptr(s), _ptr(m), len(traces), _ptr(traces), float(start_bias), _ptr(hits))
     assert rc == 0, rc
     return hits
+
+
+Light, make_light = abi.Light, abi.make_light
+
+
+def octohedral_to_direction(e):
+    e = np.ascontiguousarray(e, dtype=np.float32).reshape(-1, 2)
+    out = np.zeros((len(e), 3), dtype=np.float32)
+    L = lib()
+    L.oracle_octohedral_to_direction.restype = None
+    L.oracle_octohedral_to_direction.argtypes = [C.c_float, C.c_float, C.c_void_p]
+    for i in range(len(e)):
+        L.oracle_octohedral_to_direction(float(e[i, 0]), float(e[i, 1]), out[i].ctypes.data_as(C.c_void_p))
+    return out
+
+
+def surface_direct_light(sdf_data, sdf, mip, light, camera_pos_bias, light_cache, texel, P, N, albedo, metallic_roughness):
+    """SDFDeferredLight.frag for the listed atlas texels, blended additively into `light_cache` (uint16 RGBA16F atlas) in place."""
+    texel = np.ascontiguousarray(texel, dtype=np.uint32)
+    P, N, albedo = (np.ascontiguousarray(a, dtype=np.float32).reshape(-1, 3) for a in (P, N, albedo))
+    mr = np.ascontiguousarray(metallic_roughness, dtype=np.float32).reshape(-1, 2)
+    cam = np.ascontiguousarray(camera_pos_bias, dtype=np.float32).reshape(4)
+    s, m = _np(sdf), _np(mip)
+    L = lib()
+    L.oracle_surface_direct_light.restype = C.c_int
+    L.oracle_surface_direct_light.argtypes = [C.POINTER(abi.GlobalSDFData), C.c_void_p, C.c_void_p, C.POINTER(Light), C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 5
+    rc = L.oracle_surface_direct_light(C.byref(sdf_data), _ptr(s), _ptr(m), C.byref(light), _ptr(cam), _ptr(light_cache), len(texel), _ptr(texel), _ptr(P), _ptr(N),
+                                       _ptr(albedo), _ptr(mr))
+    assert rc == 0, rc

@@ -1577,6 +1577,127 @@ int oracle_trace_global_sdf(const LuxGlobalSDFData* sdfData, const uint16_t* sdf
     return 0;
 }
 
+} // extern "C"
+
+// Direct lighting of surface-cache texels ("next" row f4): Shaders/SDF/SDFDeferredLight.frag:44-129 with Raytraced/BRDF.glsl:8-36,65-83
+// and Common/Light.glsl:13-29; additive blend into the RGBA16F light cache (GlobalSurfaceAtlas.cpp:950-972).  pow() follows the contract
+// (binary64, rounded once); mix() is the literal x*(1-a) + y*a of the shipped binary's FMix.
+namespace {
+const float LUX_PI_F = 3.14159265358979323846f; // M_PI as Common.glsl defines it, rounded to binary32
+inline float ndfGGX(float cosLh, float roughness)
+{
+    float alpha = roughness * roughness, alphaSq = alpha * alpha;
+    float denom = (cosLh * cosLh) * (alphaSq - 1.0f) + 1.0f;
+    return alphaSq / ((LUX_PI_F * denom) * denom);
+}
+inline float gaSchlickG1(float cosTheta, float k) { return cosTheta / (cosTheta * (1.0f - k) + k); }
+inline float gaSchlickGGX(float cosLi, float NdotV, float roughness)
+{
+    float r = roughness + 1.0f, k = (r * r) / 8.0f;
+    return gaSchlickG1(cosLi, k) * gaSchlickG1(NdotV, k);
+}
+inline vec3 brdf(vec3 albedo, vec3 normal, float roughness, float metallic, vec3 view, vec3 halfV, vec3 lightDir)
+{
+    const float Fd = 0.04f, EPSILON = 0.00001f;
+    vec3  F0 = {Fd * (1.0f - metallic) + albedo.x * metallic, Fd * (1.0f - metallic) + albedo.y * metallic, Fd * (1.0f - metallic) + albedo.z * metallic};
+    float cosLi = gmax(0.0f, dot3(normal, lightDir)), cosLh = gmax(0.0f, dot3(normal, halfV)), NdotV = gmax(0.0f, dot3(normal, view));
+    float ct = gmax(dot3(halfV, view), 0.0f);
+    float p5 = pow_rn(gclamp(1.0f - ct, 0.0f, 1.0f), 5.0f);
+    vec3  F  = {F0.x + (1.0f - F0.x) * p5, F0.y + (1.0f - F0.y) * p5, F0.z + (1.0f - F0.z) * p5};
+    float D = ndfGGX(cosLh, roughness), G = gaSchlickGGX(cosLi, NdotV, roughness);
+    vec3  kd = {(1.0f - F.x) * (1.0f - metallic), (1.0f - F.y) * (1.0f - metallic), (1.0f - F.z) * (1.0f - metallic)};
+    float den = gmax(EPSILON, (4.0f * cosLi) * NdotV);
+    return {(kd.x * albedo.x) / LUX_PI_F + ((F.x * D) * G) / den, (kd.y * albedo.y) / LUX_PI_F + ((F.y * D) * G) / den, (kd.z * albedo.z) / LUX_PI_F + ((F.z * D) * G) / den};
+}
+} // namespace
+
+extern "C" int oracle_surface_direct_light(const LuxGlobalSDFData* sdfData, const uint16_t* sdf, const uint16_t* mip, const LuxLight* light,
+                                           const float* cameraPosBias, uint16_t* lightCache, int count, const uint32_t* texel, const float* P,
+                                           const float* N, const float* albedo, const float* metallicRoughness)
+{
+    if (!sdfData || !sdf || !mip || !light || !cameraPosBias || !lightCache || !texel || !P || !N || !albedo || !metallicRoughness)
+        return -1;
+    Scene sc{};
+    sc.sdfData = *sdfData;
+    const int res = (int)sdfData->resolution, casc = (int)sdfData->cascadesCount;
+    sc.tex = Tex3D{sdf, res * casc, res, res};
+    sc.mip = Tex3D{mip, (res / 4) * casc, res / 4, res / 4};
+    const LuxLight L = *light;
+    const float shadowBias = cameraPosBias[3];
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int k = 0; k < count; k++)
+    {
+        vec3 worldPos = {P[3 * k], P[3 * k + 1], P[3 * k + 2]}, normal = {N[3 * k], N[3 * k + 1], N[3 * k + 2]};
+        vec3 alb = {albedo[3 * k], albedo[3 * k + 1], albedo[3 * k + 2]};
+        float metallic = metallicRoughness[2 * k], roughness = metallicRoughness[2 * k + 1];
+        // fetchLight, SDFDeferredLight.frag:44-81
+        vec3  Wi = {0, 0, 0};
+        float dist = LUX_GLOBAL_SDF_WORLD_SIZE, atten = 1.0f;
+        if (L.type == LUX_LIGHT_DIRECTIONAL)
+        {
+            Wi = {-L.direction[0], -L.direction[1], -L.direction[2]};
+            dist = LUX_GLOBAL_SDF_WORLD_SIZE;
+            atten = 1.0f;
+        }
+        else if (L.type == LUX_LIGHT_POINT)
+        {
+            vec3 dir = sub({L.position[0], L.position[1], L.position[2]}, worldPos);
+            float d = length3(dir);
+            Wi = normalize3(dir);
+            atten = L.radius / (pow_rn(d, 2.0f) + 1.0f);
+            dist = d;
+        }
+        else if (L.type == LUX_LIGHT_SPOT)
+        {
+            vec3  Lv = sub({L.position[0], L.position[1], L.position[2]}, worldPos);
+            float cutoffAngle = 1.0f - L.angle;
+            vec3  lightDir = normalize3(Lv);
+            float d = length3(Lv);
+            float theta = dot3(lightDir, {L.direction[0], L.direction[1], L.direction[2]});
+            float epsilon = cutoffAngle - cutoffAngle * 0.9f;
+            atten = (theta - cutoffAngle) / epsilon;
+            atten *= L.radius / (pow_rn(d, 2.0f) + 1.0f);
+            atten = gclamp(atten, 0.0f, 1.0f);
+            Wi = lightDir;
+            dist = d;
+        }
+        float shadowMask = 1.0f;
+        float NoL = dot3(normal, Wi);
+        float bias = (2.0f * shadowBias) * gclamp(1.0f - NoL, 0.0f, 1.0f) + shadowBias;
+        if (NoL > 0.0f)
+        {
+            if (atten > 0.0f)
+            {
+                Counters cn;
+                vec3 origin = add(worldPos, mul(normal, shadowBias));
+                Hit  hit = tracyGlobalSDF(sc, origin, Wi, dist - bias, 1.0f, 2.0f, cn);
+                shadowMask = hit.hitTime >= 0.0f ? 0.0f : 1.0f;
+            }
+        }
+        else
+            shadowMask = 0.0f;
+        vec3  view = normalize3(sub({cameraPosBias[0], cameraPosBias[1], cameraPosBias[2]}, worldPos));
+        float intensity = pow_rn(L.intensity, 1.4f) + 0.1f;
+        vec3  Lrad = {L.color[0] * intensity, L.color[1] * intensity, L.color[2] * intensity};
+        vec3  Lh = normalize3(add(Wi, view));
+        float cosLi = gmax(0.0f, dot3(normal, Wi));
+        vec3  b = brdf(alb, normal, roughness, metallic, view, Lh, Wi);
+        float out[4] = {(((b.x * Lrad.x) * cosLi) * shadowMask) * atten, (((b.y * Lrad.y) * cosLi) * shadowMask) * atten,
+                        (((b.z * Lrad.z) * cosLi) * shadowMask) * atten, 1.0f};
+        size_t o = (size_t)texel[k] * 4;
+        for (int c = 0; c < 4; c++)
+            lightCache[o + c] = f2h(out[c] + h2f(lightCache[o + c])); // BlendMode::Add: src + dst
+    }
+    return 0;
+}
+
+extern "C" void oracle_octohedral_to_direction(float ex, float ey, float* out3)
+{
+    vec3 v = octohedralToDirection({ex, ey});
+    out3[0] = v.x; out3[1] = v.y; out3[2] = v.z;
+}
+
+extern "C" {
 // Border copy list of one probe in ring-relative coordinates: out[n][4] = (srcx, srcy, dstx, dsty); returns n.
 int oracle_border_offsets(int side, int32_t* out)
 {

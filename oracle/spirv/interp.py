@@ -31,7 +31,7 @@ OP = {
     43: "Constant", 44: "ConstantComposite", 46: "ConstantNull", 54: "Function", 55: "FunctionParameter", 56: "FunctionEnd",
     57: "FunctionCall", 59: "Variable", 61: "Load", 62: "Store", 65: "AccessChain", 66: "InBoundsAccessChain", 71: "Decorate",
     72: "MemberDecorate", 79: "VectorShuffle", 80: "CompositeConstruct", 81: "CompositeExtract", 82: "CompositeInsert",
-    83: "CopyObject", 88: "ImageSampleExplicitLod", 95: "ImageFetch", 96: "ImageGather", 98: "ImageRead", 99: "ImageWrite",
+    83: "CopyObject", 87: "ImageSampleImplicitLod", 88: "ImageSampleExplicitLod", 95: "ImageFetch", 96: "ImageGather", 98: "ImageRead", 99: "ImageWrite",
     100: "Image", 103: "ImageQuerySizeLod", 110: "ConvertFToS", 109: "ConvertFToU", 111: "ConvertSToF", 112: "ConvertUToF", 124: "Bitcast", 126: "SNegate",
     127: "FNegate", 128: "IAdd", 129: "FAdd", 130: "ISub", 131: "FSub", 132: "IMul", 133: "FMul", 134: "UDiv", 135: "SDiv",
     136: "FDiv", 137: "UMod", 138: "SRem", 139: "SMod", 141: "FMod", 142: "VectorTimesScalar", 143: "MatrixTimesScalar",
@@ -576,6 +576,7 @@ class Invocation:
         if name in ("CopyObject", "CopyLogical"): return copyv(x(2))
         if name == "Undef": return m.zero(a[0])
         if name == "Image": return x(2)
+        if name == "ImageSampleImplicitLod": return x(2).sample(x(3))  # fragment stage, single-level textures: LOD 0
         if name == "ImageSampleExplicitLod":
             if isinstance(x(2), Texture3DMips):  # operands: mask (a[4], Lod = 0x2), lod id (a[5])
                 return x(2).sample(x(3), x(5) if (a[4] & 2) else F(0))

@@ -518,3 +518,54 @@ def test_generic_global_sdf_trace_matches_oracle(oracle, cfg, flags):
             a, b = got[f].view(np.uint32), want[f].view(np.uint32)
             assert np.array_equal(a, b), f"bias {bias}: {f} differs on {(a != b).sum()} of {a.size} values"
     pipe.close()
+
+
+def test_surface_direct_light_matches_shipped_spirv_and_oracle(oracle):
+    """Row f4: lux_ddgi_surface_direct_light = SDFDeferredLight.frag (fetchLight, shadow ray with start bias 2, BRDF) added into the RGBA16F light cache.
+    (a) against the shipped SPIR-V's outColor on the golden G-buffer (tests/golden/spirv_golden_directlight.npz), bit for bit, for a directional,
+    a point and a spot light; (b) against the oracle on every G-buffer texel of the Cornell surface cache, the three lights accumulated one after
+    another on top of the scene's own light cache (additive blend, alpha counts the passes)."""
+    import os
+
+    from tests.golden import make_spirv_golden_directlight as g
+
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "spirv_golden_directlight.npz"))
+    sc = g.golden_scene()
+    res = int(sc.atlas_data.resolution)
+    for flags in (0, abi.FLAG_SDF_LOADS):
+        pipe = ddgi.DDGIPipeline(sc.uniform, flags=flags)
+        pipe.set_scene(sc)
+        # (a) golden replay into an empty light cache
+        n = len(gold["pos"])
+        normals = oracle.octohedral_to_direction(gold["oct_normal"])  # the value the shader decodes (a pure function of the stored input)
+        texel = np.arange(n, dtype=np.uint32)
+        for name in g.LIGHTS:
+            pipe.update_surface_light_cache(np.zeros((res, res, 4), dtype=np.uint16))
+            pipe.surface_direct_light(abi.make_light(gold[f"light_{name}"]), gold["camera"], texel, gold["pos"], normals, gold["albedo"], gold["pbr"])
+            got = pipe.surface_light_cache().reshape(-1, 4)
+            want = gold[f"out_{name}"].astype(np.float16).view(np.uint16)
+            assert np.array_equal(got[:n], want), f"{name}: {(got[:n] != want).sum()} of {want.size} fp16 values differ from the shipped shader"
+            assert not got[n:].any(), "texels outside the list were written"
+        # (b) whole G-buffer, three lights on top of the existing cache
+        gb = sc.meta["gbuffer"]
+        rng = np.random.default_rng(5)
+        k = len(gb["texel"])
+        nrm = gb["normal"].astype(np.float32) + rng.normal(scale=0.1, size=(k, 3)).astype(np.float32)
+        nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+        pbr = np.stack([rng.choice([0.0, 0.5, 1.0], k), rng.uniform(0.05, 1.0, k)], -1).astype(np.float32)
+        base = np.ascontiguousarray(sc.light.numpy().view(np.uint16)).reshape(res, res, 4).copy()
+        pipe.update_surface_light_cache(base)
+        want = base.reshape(-1, 4).copy()
+        for name in g.LIGHTS:
+            light = abi.make_light(gold[f"light_{name}"])
+            oracle.surface_direct_light(sc.sdf_data, sc.sdf, sc.mip, light, gold["camera"], want, gb["texel"], gb["pos"], nrm, gb["albedo"], pbr)
+            pipe.surface_direct_light(light, gold["camera"], gb["texel"], gb["pos"], nrm, gb["albedo"], pbr)
+        got = pipe.surface_light_cache().reshape(-1, 4)
+        assert (want != base.reshape(-1, 4)).any(1).sum() == len(np.unique(gb["texel"]))
+        assert np.array_equal(got, want), f"flags {flags}: {(got != want).sum()} of {want.size} fp16 values differ from the oracle"
+        # argument errors come back as status codes
+        bad = abi.make_light(gold["light_point"])
+        bad.type = 7.0
+        with pytest.raises(ddgi.LuxError):
+            pipe.surface_direct_light(bad, gold["camera"], texel, gold["pos"], normals, gold["albedo"], gold["pbr"])
+        pipe.close()

@@ -158,3 +158,24 @@ def test_surface_culling_matches_shipped_spirv(oracle):
         assert np.array_equal(chunks, gold[f"chunks_{cap}"]), f"capacity {cap}: {(chunks != gold[f'chunks_{cap}']).sum()} chunk words differ"
         assert np.array_equal(cull, gold[f"cull_{cap}"]), f"capacity {cap}: {(cull != gold[f'cull_{cap}']).sum()} cull words differ"
     assert (gold["chunks_4096"][1:] != 0).sum() > 500 > (gold["chunks_150"][1:] != 0).sum() > 0
+
+
+def test_surface_direct_light_matches_shipped_spirv(oracle):
+    """Row f4: the oracle's restatement of SDFDeferredLight.frag (fetchLight for the three light types, shadow ray with start bias 2, BRDF)
+    against the shipped binary executed per fragment: the shading added to an empty RGBA16F light cache equals fp16(outColor) bit for bit."""
+    from tests.golden import make_spirv_golden_directlight as g
+
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "spirv_golden_directlight.npz"))
+    sc = g.golden_scene()
+    n = len(gold["pos"])
+    normals = oracle.octohedral_to_direction(gold["oct_normal"])
+    texel = np.arange(n, dtype=np.uint32)
+    lit = 0
+    for name in g.LIGHTS:
+        cache = np.zeros((n, 4), dtype=np.uint16)
+        oracle.surface_direct_light(sc.sdf_data, sc.sdf, sc.mip, oracle.make_light(gold[f"light_{name}"]), gold["camera"], cache, texel, gold["pos"], normals,
+                                    gold["albedo"], gold["pbr"])
+        want = gold[f"out_{name}"].astype(np.float16).view(np.uint16)
+        assert np.array_equal(cache, want), f"{name}: {(cache != want).sum()} of {cache.size} fp16 values differ"
+        lit += int((gold[f"out_{name}"][:, :3].sum(1) > 0).sum())
+    assert lit > 60  # the three lights really shade something
