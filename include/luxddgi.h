@@ -410,6 +410,44 @@ LUX_API int lux_ddgi_sample_irradiance(LuxDDGIContext* ctx, int32_t count, const
 LUX_API int lux_ddgi_sample_probe(LuxDDGIContext* ctx, int32_t width, int32_t height, const float* depthD32F, const float* normalsRGBA32F,
                                   const float cameraPosition[4], const float viewProjInv[16], float* outRGBA32F, LuxMemKind kind);
 
+/* ---- the other tracyGlobalSDF users: screen-space passes over a width x height G-buffer ----
+ * Blue-noise inputs (Raytraced/BlueNoise.glsl:8-19): `sobolRGBA8` = the 256 x 1 RGBA8 texels of textures/blue_noise/sobol_256_4d.png,
+ * `scramblingRankingRGBA8` = the 128 x 128 RGBA8 texels of scrambling_ranking_128x128_2d_1spp.png (Engine/Noise/BlueNoise.h:15-26); a texel
+ * channel c reads as float(c) / 255 (UNORM). */
+
+/* Push constants of Shaders/SDF/SDFReflection.comp:66-78 (host: Engine/Raytrace/RaytracedReflection.cpp), 112 bytes. */
+typedef struct LuxReflectionPushConstants {
+    float    bias;               /* unused by the SDF branch */
+    float    trim;
+    float    intensity;          /* unused by the SDF branch */
+    float    roughDDGIIntensity;
+    uint32_t numLights;          /* unused */
+    uint32_t numFrames;
+    uint32_t sampleGI;           /* unused */
+    uint32_t approximateWithDDGI;
+    float    cameraPosition[4];
+    float    viewProjInv[16];    /* column-major */
+} LuxReflectionPushConstants;
+
+/* Shaders/SDF/SDFReflection.comp:84-163 (dispatch: RaytracedReflection.cpp:335-339): per pixel with depth != 1 one reflection ray from the
+ * G-buffer surface (pushed out by one cascade-0 voxel) through the bound global SDF.  roughness < 0.05: mirror ray; roughness > 0.45 and
+ * approximateWithDDGI == 1: roughDDGIIntensity * sampleIrradiance along the mirror direction (alpha 0); otherwise a GGX half vector from the
+ * blue-noise sample.  A hit returns the surface cache sampled with normal = -R (rgb normalised, alpha = weight sum), a miss the skybox texel.
+ * depth D32F [h][w]; normals RGBA32F [h][w][4] (xy = octahedral normal); pbr RGBA32F [h][w][4] (g = roughness); outRGBA16F [h][w][4] is
+ * read-modify-write: pixels with depth == 1 keep their previous contents, as the shader does not store them. */
+LUX_API int lux_ddgi_sdf_reflection(LuxDDGIContext* ctx, const LuxReflectionPushConstants* push, int32_t width, int32_t height, const float* depthD32F,
+                                    const float* normalsRGBA32F, const float* pbrRGBA32F, const uint8_t* sobolRGBA8,
+                                    const uint8_t* scramblingRankingRGBA8, void* outRGBA16F, LuxMemKind kind);
+
+/* Shaders/SDF/SDFShadow.comp:121-157 (UBO :25-32; host: Engine/Raytrace/RaytracedShadow.cpp): per pixel with depth != 1 one soft-shadow ray
+ * towards `light` (disk sample from the blue noise, light->direction[3] = light radius) through the bound global SDF, start bias 0, max
+ * distance tMax - bias.  Output: one uint32 per 8 x 4 pixel workgroup, bit (y % 4) * 8 + (x % 8) set = visible, [height/4][width/8]
+ * (R32UI image); width must be a multiple of 8 and height of 4.  As in the shader, a workgroup whose first pixel has depth == 1 stores
+ * nothing (its word keeps its previous contents) and pixels with depth == 1 contribute no bit: outMaskR32UI is read-modify-write. */
+LUX_API int lux_ddgi_sdf_shadow(LuxDDGIContext* ctx, const LuxLight* light, const float viewProjInv[16], uint32_t numFrames, float shadowBias,
+                                int32_t width, int32_t height, const float* depthD32F, const float* normalsRGBA32F, const uint8_t* sobolRGBA8,
+                                const uint8_t* scramblingRankingRGBA8, uint32_t* outMaskR32UI, LuxMemKind kind);
+
 /* Infinite-bounce feedback: surface::indirect_light::system (GlobalSurfaceAtlas.cpp:1004-1085) =
  * Shaders/SDF/SDFAtlasIndirectLight.frag:44-67, additive into the RGBA16F light cache.  For each listed atlas texel t:
  *   light[t].rgb = fp16( base[t].rgb + intensity * (min(albedo,0.9) - min(albedo,0.9)*metallic)/PI * sampleIrradiance(P, N, normalize(cameraPos-P)) )

@@ -245,6 +245,24 @@ def make_light(values16) -> Light:
     return l
 
 
+class ReflectionPushConstants(C.Structure):  # LuxReflectionPushConstants = SDFReflection.comp:66-78, 112 bytes
+    _fields_ = [("bias", C.c_float), ("trim", C.c_float), ("intensity", C.c_float), ("roughDDGIIntensity", C.c_float), ("numLights", C.c_uint32),
+                ("numFrames", C.c_uint32), ("sampleGI", C.c_uint32), ("approximateWithDDGI", C.c_uint32), ("cameraPosition", C.c_float * 4),
+                ("viewProjInv", C.c_float * 16)]
+
+
+def make_reflection_push(camera_position, view_proj_inv, num_frames=0, trim=1.0, rough_ddgi_intensity=1.0, approximate_with_ddgi=1) -> ReflectionPushConstants:
+    p = ReflectionPushConstants()
+    p.bias, p.trim, p.intensity, p.roughDDGIIntensity = 0.0, float(trim), 1.0, float(rough_ddgi_intensity)
+    p.numLights, p.numFrames, p.sampleGI, p.approximateWithDDGI = 0, int(num_frames), 0, int(approximate_with_ddgi)
+    p.cameraPosition[:] = [float(x) for x in list(camera_position)[:3]] + [1.0]
+    p.viewProjInv[:] = [float(x) for x in np.asarray(view_proj_inv, dtype=np.float32).reshape(16)]
+    return p
+
+
+assert C.sizeof(ReflectionPushConstants) == 112 and C.sizeof(Light) == 64
+
+
 # GlobalSDFTrace / GlobalSDFHit (row f4: lux_ddgi_trace_global_sdf), as numpy record dtypes
 SDF_TRACE_DTYPE = np.dtype([("worldPosition", "<f4", 3), ("minDistance", "<f4"), ("worldDirection", "<f4", 3), ("maxDistance", "<f4"),
                             ("stepScale", "<f4"), ("needsHitNormal", "<u4")])

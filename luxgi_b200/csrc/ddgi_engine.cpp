@@ -1923,6 +1923,126 @@ int lux_ddgi_surface_direct_light(LuxDDGIContext* c, const LuxLight* light, cons
     return rc;
 }
 
+// SDF + surface cache + sky fields of TraceParams, for the kernels that trace rays outside the probe update
+static void fillSceneParams(const LuxDDGIContext* c, lux::TraceParams& p)
+{
+    p.sdf      = c->sdfData;
+    p.tex      = (const uint16_t*)c->sdf.ptr;
+    p.mip      = (const uint16_t*)c->mip.ptr;
+    p.res      = (int)c->sdfData.resolution;
+    p.mipRes   = p.res / 4;
+    p.cascades = (int)c->sdfData.cascadesCount;
+    p.texObj   = c->sdfTex;
+    p.mipObj   = c->mipTex;
+    p.hasAtlas = c->hasAtlas ? 1 : 0;
+    if (c->hasAtlas)
+    {
+        p.chunkSize     = c->atlasData.chunkSize;
+        p.atlasRes      = c->atlasData.resolution;
+        p.objectsCount  = c->atlasData.objectsCount;
+        p.chunks        = (const uint32_t*)c->chunks.ptr;
+        p.cull          = (const uint32_t*)c->cull.ptr;
+        p.objects       = (const LuxObjectBuffer*)c->objects.ptr;
+        p.objectInverse = (const float*)c->objectInverse.ptr;
+        p.tiles         = (const LuxTileBuffer*)c->tiles.ptr;
+        p.light         = (const uint2*)c->light.ptr;
+        p.depth         = (const float*)c->atlasDepth.ptr;
+    }
+    p.skyFace = c->skyFace;
+    p.sky     = (const uint2*)c->sky.ptr;
+}
+
+namespace {
+// host or device inputs of one call staged on the context's stream; frees what it allocated when it goes out of scope
+struct Staged
+{
+    LuxDDGIContext* c;
+    LuxMemKind      kind;
+    void*           owned[8];
+    int             n = 0;
+    Staged(LuxDDGIContext* ctx, LuxMemKind k) : c(ctx), kind(k) {}
+    ~Staged()
+    {
+        for (int i = 0; i < n; i++)
+            cudaFree(owned[i]);
+    }
+    int in(const void* src, size_t bytes, void** dev)
+    {
+        bool o  = false;
+        int  rc = stageToDevice(c, src, bytes, kind, dev, &o);
+        if (rc == LUX_OK && o)
+            owned[n++] = *dev;
+        return rc;
+    }
+};
+} // namespace
+
+int lux_ddgi_sdf_reflection(LuxDDGIContext* c, const LuxReflectionPushConstants* push, int32_t width, int32_t height, const float* depthD32F,
+                            const float* normalsRGBA32F, const float* pbrRGBA32F, const uint8_t* sobolRGBA8, const uint8_t* scramblingRankingRGBA8,
+                            void* outRGBA16F, LuxMemKind kind)
+{
+    CHECK_CTX(c);
+    waitAllGather(c, c->stream);
+    if (!c->hasSdf)
+        return fail(LUX_ERR_NOT_READY, "no global SDF bound");
+    if (!push || width <= 0 || height <= 0 || !depthD32F || !normalsRGBA32F || !pbrRGBA32F || !sobolRGBA8 || !scramblingRankingRGBA8 || !outRGBA16F)
+        return fail(LUX_ERR_INVALID_ARG, "bad sdf_reflection arguments");
+    if (push->approximateWithDDGI == 1u && c->frames == 0)
+        return fail(LUX_ERR_NOT_READY, "approximateWithDDGI: no atlas has been written yet");
+    const size_t px = (size_t)width * height;
+    Staged st(c, kind);
+    void *dD, *dN, *dP, *dS, *dR, *dO;
+    int   rc;
+    if ((rc = st.in(depthD32F, px * 4, &dD)) != LUX_OK || (rc = st.in(normalsRGBA32F, px * 16, &dN)) != LUX_OK || (rc = st.in(pbrRGBA32F, px * 16, &dP)) != LUX_OK ||
+        (rc = st.in(sobolRGBA8, 256 * 4, &dS)) != LUX_OK || (rc = st.in(scramblingRankingRGBA8, 128 * 128 * 4, &dR)) != LUX_OK ||
+        (rc = st.in(outRGBA16F, px * 8, &dO)) != LUX_OK) // read-modify-write: depth == 1 pixels keep their contents
+        return rc;
+    lux::TraceParams p{};
+    fillSceneParams(c, p);
+    lux::launch_sdf_reflection(p, c->sdfTex != 0, c->uniform, *push, c->irradiance[c->lastWritten].ptr, c->depth[c->lastWritten].ptr, width, height,
+                               (const float*)dD, (const float*)dN, (const float*)dP, (const uint32_t*)dS, (const uint32_t*)dR, dO, c->stream);
+    c->launches += 1;
+    LUX_CUDA(cudaGetLastError());
+    if (kind != LUX_MEM_DEVICE)
+    {
+        LUX_CUDA(cudaMemcpyAsync(outRGBA16F, dO, px * 8, cudaMemcpyDeviceToHost, c->stream));
+        LUX_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    return LUX_OK;
+}
+
+int lux_ddgi_sdf_shadow(LuxDDGIContext* c, const LuxLight* light, const float viewProjInv[16], uint32_t numFrames, float shadowBias, int32_t width,
+                        int32_t height, const float* depthD32F, const float* normalsRGBA32F, const uint8_t* sobolRGBA8,
+                        const uint8_t* scramblingRankingRGBA8, uint32_t* outMaskR32UI, LuxMemKind kind)
+{
+    CHECK_CTX(c);
+    if (!c->hasSdf)
+        return fail(LUX_ERR_NOT_READY, "no global SDF bound");
+    if (!light || !viewProjInv || width <= 0 || height <= 0 || !depthD32F || !normalsRGBA32F || !sobolRGBA8 || !scramblingRankingRGBA8 || !outMaskR32UI)
+        return fail(LUX_ERR_INVALID_ARG, "bad sdf_shadow arguments");
+    if (width % 8 != 0 || height % 4 != 0)
+        return fail(LUX_ERR_INVALID_ARG, "sdf_shadow: width must be a multiple of 8 and height of 4 (one word per 8x4 workgroup), got %d x %d", width, height);
+    const size_t px = (size_t)width * height, words = (size_t)(width / 8) * (height / 4);
+    Staged st(c, kind);
+    void *dD, *dN, *dS, *dR, *dO;
+    int   rc;
+    if ((rc = st.in(depthD32F, px * 4, &dD)) != LUX_OK || (rc = st.in(normalsRGBA32F, px * 16, &dN)) != LUX_OK || (rc = st.in(sobolRGBA8, 256 * 4, &dS)) != LUX_OK ||
+        (rc = st.in(scramblingRankingRGBA8, 128 * 128 * 4, &dR)) != LUX_OK || (rc = st.in(outMaskR32UI, words * 4, &dO)) != LUX_OK)
+        return rc;
+    lux::TraceParams p{};
+    fillSceneParams(c, p);
+    lux::launch_sdf_shadow(p, c->sdfTex != 0, *light, viewProjInv, numFrames, shadowBias, width, height, (const float*)dD, (const float*)dN,
+                           (const uint32_t*)dS, (const uint32_t*)dR, (uint32_t*)dO, c->stream);
+    c->launches += 1;
+    LUX_CUDA(cudaGetLastError());
+    if (kind != LUX_MEM_DEVICE)
+    {
+        LUX_CUDA(cudaMemcpyAsync(outMaskR32UI, dO, words * 4, cudaMemcpyDeviceToHost, c->stream));
+        LUX_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    return LUX_OK;
+}
+
 int lux_ddgi_get_surface_light_cache(LuxDDGIContext* c, void** devicePtr, size_t* bytes)
 {
     CHECK_CTX(c);

@@ -2380,6 +2380,271 @@ __global__ void __launch_bounds__(128) direct_light_kernel(const __grid_constant
 }
 
 // =====================================================================================================================
+// The screen-space tracyGlobalSDF users: SDFReflection.comp and SDFShadow.comp over a G-buffer.
+// cross / reflect / the UNORM8 blue-noise fetch under the numerics contract: every product, sum and difference is rounded.
+// =====================================================================================================================
+__device__ __forceinline__ f3 cross3(f3 a, f3 b) { return {a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y}; }
+__device__ __forceinline__ f3 reflect3(f3 i, f3 n)
+{
+    float t = 2.0f * dot3(n, i);
+    return {i.x - t * n.x, i.y - t * n.y, i.z - t * n.z};
+}
+__device__ __forceinline__ float unorm8(uint32_t b) { return __fdiv_rn((float)b, 255.0f); }
+// sampleBlueNoise, Raytraced/BlueNoise.glsl:8-19; sobol = 256 x 1 RGBA8, scr = 128 x 128 RGBA8 (one uint32 per texel, r in the low byte)
+__device__ __forceinline__ float sample_blue_noise(int cx, int cy, int samplerIndex, int dimension, const uint32_t* __restrict__ sobol,
+                                                   const uint32_t* __restrict__ scr)
+{
+    cx           = cx % 128;
+    cy           = cy % 128;
+    samplerIndex = samplerIndex % 256;
+    dimension    = dimension % 4;
+    const uint32_t t = __ldg(scr + cy * 128 + cx);
+    int rankedIndex = samplerIndex ^ (int)gclamp(unorm8((t >> 16) & 0xffu) * 256.0f, 0.0f, 255.0f);
+    int value       = (int)gclamp(unorm8((__ldg(sobol + rankedIndex) >> (8 * dimension)) & 0xffu) * 256.0f, 0.0f, 255.0f);
+    value           = value ^ (int)gclamp(unorm8((t >> (8 * (dimension % 2))) & 0xffu) * 256.0f, 0.0f, 255.0f);
+    return __fdiv_rn(0.5f + (float)value, 256.0f);
+}
+__device__ __forceinline__ f3 world_position_from_depth(float tx, float ty, float d, const float* __restrict__ m) // Common/Math.glsl:35-42
+{
+    float sx = tx * 2.0f - 1.0f, sy = ty * 2.0f - 1.0f;
+    float wx = ((m[0] * sx + m[4] * sy) + m[8] * d) + m[12] * 1.0f;
+    float wy = ((m[1] * sx + m[5] * sy) + m[9] * d) + m[13] * 1.0f;
+    float wz = ((m[2] * sx + m[6] * sy) + m[10] * d) + m[14] * 1.0f;
+    float ww = ((m[3] * sx + m[7] * sy) + m[11] * d) + m[15] * 1.0f;
+    return {__fdiv_rn(wx, ww), __fdiv_rn(wy, ww), __fdiv_rn(wz, ww)};
+}
+__device__ __forceinline__ f3 octohedral_to_direction(float ex, float ey) // Common/Math.glsl:27-33
+{
+    f3 v = {ex, ey, (1.0f - fabsf(ex)) - fabsf(ey)};
+    if (v.z < 0.0f)
+    {
+        float s0 = (v.x >= 0.0f ? 1.0f : 0.0f) * 2.0f - 1.0f, s1 = (v.y >= 0.0f ? 1.0f : 0.0f) * 2.0f - 1.0f;
+        float nx = (1.0f - fabsf(v.y)) * s0, ny = (1.0f - fabsf(v.x)) * s1;
+        v.x = nx;
+        v.y = ny;
+    }
+    return normalize3(v);
+}
+// importanceSampleGGX(...).xyz, Raytraced/BRDF.glsl:176-201
+__device__ __forceinline__ f3 importance_sample_ggx(float ex, float ey, f3 N, float roughness)
+{
+    const float TWO_PI = 6.283185482025146484375f;
+    float a = roughness * roughness, m2 = a * a;
+    float phi      = TWO_PI * ex;
+    float cosTheta = __fsqrt_rn(__fdiv_rn(1.0f - ey, 1.0f + (m2 - 1.0f) * ey));
+    float sinTheta = __fsqrt_rn(1.0f - cosTheta * cosTheta);
+    f3    H  = {cos_rn(phi) * sinTheta, sin_rn(phi) * sinTheta, cosTheta};
+    f3    up = fabsf(N.z) < 0.999f ? f3{0.0f, 0.0f, 1.0f} : f3{1.0f, 0.0f, 0.0f};
+    f3    tangent   = normalize3(cross3(up, N));
+    f3    bitangent = cross3(N, tangent);
+    f3    sv = {(tangent.x * H.x + bitangent.x * H.y) + N.x * H.z, (tangent.y * H.x + bitangent.y * H.y) + N.y * H.z,
+                (tangent.z * H.x + bitangent.z * H.y) + N.z * H.z};
+    return normalize3(sv);
+}
+// texture(samplerCube, dir) with its alpha (sample_sky returns .rgb for the probe trace)
+__device__ __forceinline__ f4 sample_sky4(const TraceParams& P, f3 d)
+{
+    if (P.sky == nullptr || P.skyFace <= 0)
+        return {0.0f, 0.0f, 0.0f, 0.0f};
+    float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+    int   face;
+    float sc, tc, ma;
+    if (az >= ax && az >= ay) { face = d.z >= 0.0f ? 4 : 5; sc = d.z >= 0.0f ? d.x : -d.x; tc = -d.y; ma = az; }
+    else if (ay >= ax)        { face = d.y >= 0.0f ? 2 : 3; sc = d.x; tc = d.y >= 0.0f ? d.z : -d.z; ma = ay; }
+    else                      { face = d.x >= 0.0f ? 0 : 1; sc = d.x >= 0.0f ? -d.z : d.z; tc = -d.y; ma = ax; }
+    float u = 0.5f * __fdiv_rn(sc, ma) + 0.5f, v = 0.5f * __fdiv_rn(tc, ma) + 0.5f;
+    int   N = P.skyFace;
+    float x = u * (float)N - 0.5f, y = v * (float)N - 0.5f;
+    float fx = floorf(x), fy = floorf(y);
+    float axw = x - fx, ayw = y - fy;
+    int   x0 = iclamp((int)fx, 0, N - 1), x1 = iclamp((int)fx + 1, 0, N - 1);
+    int   y0 = iclamp((int)fy, 0, N - 1), y1 = iclamp((int)fy + 1, 0, N - 1);
+    const uint2* base = P.sky + (size_t)face * N * N;
+    f4 t00 = unpack_rgba16f(__ldg(base + (size_t)y0 * N + x0)), t10 = unpack_rgba16f(__ldg(base + (size_t)y0 * N + x1));
+    f4 t01 = unpack_rgba16f(__ldg(base + (size_t)y1 * N + x0)), t11 = unpack_rgba16f(__ldg(base + (size_t)y1 * N + x1));
+    f4 out;
+    out.x = lerp1(lerp1(t00.x, t10.x, axw), lerp1(t01.x, t11.x, axw), ayw);
+    out.y = lerp1(lerp1(t00.y, t10.y, axw), lerp1(t01.y, t11.y, axw), ayw);
+    out.z = lerp1(lerp1(t00.z, t10.z, axw), lerp1(t01.z, t11.z, axw), ayw);
+    out.w = lerp1(lerp1(t00.w, t10.w, axw), lerp1(t01.w, t11.w, axw), ayw);
+    return out;
+}
+
+struct ReflectionArgs
+{
+    LuxDDGIUniform             ddgi;
+    LuxReflectionPushConstants push;
+    const uint16_t *           irr, *dep;
+    int                        width, height;
+    const float *              gDepth, *gNormal, *gPbr;
+    const uint32_t *           sobol, *scr;
+    uint2*                     out;
+};
+
+// SDFReflection.comp:84-163, one thread per pixel
+template <bool TEX>
+__global__ void __launch_bounds__(128) sdf_reflection_kernel(const __grid_constant__ TraceParams P, const __grid_constant__ ReflectionArgs A)
+{
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= A.width * A.height)
+        return;
+    const int   x = o % A.width, y = o / A.width;
+    const float depth = __ldg(A.gDepth + o);
+    if (!(depth != 1.0f))
+        return;
+    const SdfSampler<TEX> sdf(P);
+    const float tx = __fdiv_rn((float)x + 0.5f, (float)A.width), ty = __fdiv_rn((float)y + 0.5f, (float)A.height);
+    f3           worldPos  = world_position_from_depth(tx, ty, depth, A.push.viewProjInv);
+    const float  roughness = __ldg(A.gPbr + 4 * (size_t)o + 1);
+    const float4 n4        = __ldg(reinterpret_cast<const float4*>(A.gNormal) + o);
+    const f3     normal    = octohedral_to_direction(n4.x, n4.y);
+    const f3     cam       = {A.push.cameraPosition[0], A.push.cameraPosition[1], A.push.cameraPosition[2]};
+    const f3     Wo        = normalize3(cam - worldPos);
+    worldPos               = worldPos + normal * P.sdf.cascadeVoxelSize[0];
+    const f3 negWo = {-Wo.x, -Wo.y, -Wo.z};
+    f4   color = {0.0f, 0.0f, 0.0f, 0.0f};
+    f3   R;
+    bool traceRay = true;
+    if (roughness < 0.05f) // MIRROR_REFLECTIONS_ROUGHNESS_THRESHOLD
+        R = reflect3(negWo, normal);
+    else if (roughness > 0.45f && A.push.approximateWithDDGI == 1u) // DDGI_REFLECTIONS_ROUGHNESS_THRESHOLD
+    {
+        R = reflect3(negWo, normal);
+        AtlasView ai{A.irr, A.ddgi.irradianceTextureWidth, A.ddgi.irradianceTextureHeight, 4}, ad{A.dep, A.ddgi.depthTextureWidth, A.ddgi.depthTextureHeight, 2};
+        f3 e     = sample_irradiance(A.ddgi, worldPos, R, Wo, ai, ad);
+        color    = {A.push.roughDDGIIntensity * e.x, A.push.roughDDGIIntensity * e.y, A.push.roughDDGIIntensity * e.z, 0.0f};
+        traceRay = false;
+    }
+    else
+    {
+        float xi0 = sample_blue_noise(x, y, (int)A.push.numFrames, 0, A.sobol, A.scr) * A.push.trim;
+        float xi1 = sample_blue_noise(x, y, (int)A.push.numFrames, 1, A.sobol, A.scr) * A.push.trim;
+        f3    Wh  = importance_sample_ggx(xi0, xi1, normal, roughness);
+        R         = reflect3(negWo, Wh);
+    }
+    if (traceRay)
+    { // trace(), SDFReflection.comp:86-117
+        LuxGlobalSDFTrace tr;
+        tr.worldPosition[0] = worldPos.x; tr.worldPosition[1] = worldPos.y; tr.worldPosition[2] = worldPos.z;
+        tr.minDistance = 0.0f;
+        tr.worldDirection[0] = R.x; tr.worldDirection[1] = R.y; tr.worldDirection[2] = R.z;
+        tr.maxDistance = LUX_GLOBAL_SDF_WORLD_SIZE;
+        tr.stepScale = 1.0f;
+        tr.needsHitNormal = 0u;
+        const LuxGlobalSDFHit hit = trace_global_sdf_general<TEX>(P, sdf, tr, 0.0f);
+        if (hit.hitTime >= 0.0f)
+        {
+            float surfaceThreshold = P.sdf.cascadeVoxelSize[hit.hitCascade] * 1.05f;
+            color = sample_global_surface_atlas(P, worldPos + R * hit.hitTime, {-R.x, -R.y, -R.z}, surfaceThreshold);
+        }
+        else
+            color = sample_sky4(P, R);
+    }
+    const uint32_t h0 = f2h_bits(color.x), h1 = f2h_bits(color.y), h2 = f2h_bits(color.z), h3 = f2h_bits(color.w);
+    A.out[o] = make_uint2(h0 | (h1 << 16), h2 | (h3 << 16));
+}
+
+struct ShadowArgs
+{
+    LuxLight         light;
+    float            viewProjInv[16];
+    uint32_t         numFrames;
+    float            shadowBias;
+    int              width, height;
+    const float *    gDepth, *gNormal;
+    const uint32_t * sobol, *scr;
+    uint32_t*        out;
+};
+
+// SDFShadow.comp:121-157 with fetchLight :42-117 (softShadow = true): one warp = one 8 x 4 workgroup, the visibility word is a ballot
+template <bool TEX>
+__global__ void __launch_bounds__(128) sdf_shadow_kernel(const __grid_constant__ TraceParams P, const __grid_constant__ ShadowArgs A)
+{
+    const int gw = A.width / 8, gh = A.height / 4;
+    const int g  = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+    if (g >= gw * gh) // whole warps leave together
+        return;
+    const int li = threadIdx.x & 31;
+    const int x = (g % gw) * 8 + (li % 8), y = (g / gw) * 4 + (li / 8);
+    const size_t o     = (size_t)y * A.width + x;
+    const float  depth = __ldg(A.gDepth + o);
+    const bool   live  = depth != 1.0f;
+    uint32_t     result = 0;
+    if (live)
+    {
+        const SdfSampler<TEX> sdf(P);
+        const LuxLight&       L = A.light;
+        const float PI_F = 3.1415926535897932384626433832795f;
+        const float tx = __fdiv_rn((float)x + 0.5f, (float)A.width), ty = __fdiv_rn((float)y + 0.5f, (float)A.height);
+        const f3     worldPos = world_position_from_depth(tx, ty, depth, A.viewProjInv);
+        const float4 n4       = __ldg(reinterpret_cast<const float4*>(A.gNormal) + o);
+        const f3     normal   = octohedral_to_direction(n4.x, n4.y);
+        const float  rx = sample_blue_noise(x, y, (int)A.numFrames, 0, A.sobol, A.scr), ry = sample_blue_noise(x, y, (int)A.numFrames, 1, A.sobol, A.scr);
+        f3    lightDir = {0.0f, 0.0f, 0.0f};
+        float lightRadius = 0.0f, tMax = 0.0f, attenuation = 0.0f;
+        const f3 lightPos = {L.position[0], L.position[1], L.position[2]};
+        if (L.type == LUX_LIGHT_DIRECTIONAL)
+        {
+            lightDir    = {-L.direction[0], -L.direction[1], -L.direction[2]};
+            tMax        = LUX_GLOBAL_SDF_WORLD_SIZE;
+            lightRadius = L.direction[3];
+            attenuation = 1.0f;
+        }
+        else if (L.type == LUX_LIGHT_POINT)
+        {
+            f3    dir  = lightPos - worldPos;
+            float dist = length3(dir);
+            lightDir    = normalize3(dir);
+            attenuation = 1.0f;
+            tMax        = dist;
+            lightRadius = __fdiv_rn(L.direction[3], dist);
+        }
+        else if (L.type == LUX_LIGHT_SPOT)
+        {
+            f3    Lv          = lightPos - worldPos;
+            float cutoffAngle = 1.0f - L.angle;
+            lightDir          = normalize3(Lv);
+            float dist        = length3(Lv);
+            float theta       = dot3(lightDir, {L.direction[0], L.direction[1], L.direction[2]});
+            float epsilon     = cutoffAngle - cutoffAngle * 0.9f;
+            attenuation       = __fdiv_rn(theta - cutoffAngle, epsilon);
+            attenuation *= __fdiv_rn(L.radius, powd_rn(dist, 2.0f) + 1.0f);
+            attenuation = gclamp(attenuation, 0.0f, 1.0f);
+            tMax        = dist;
+            lightRadius = __fdiv_rn(L.direction[3], dist);
+        }
+        const f3    lightTangent   = normalize3(cross3(lightDir, {0.0f, 1.0f, 0.0f}));
+        const f3    lightBitangent = normalize3(cross3(lightTangent, lightDir));
+        const float pointRadius = lightRadius * __fsqrt_rn(rx);
+        const float pointAngle  = (ry * 2.0f) * PI_F;
+        const float dx = pointRadius * cos_rn(pointAngle), dy = pointRadius * sin_rn(pointAngle);
+        const f3    wv = {(lightDir.x + dx * lightTangent.x) + dy * lightBitangent.x, (lightDir.y + dx * lightTangent.y) + dy * lightBitangent.y,
+                          (lightDir.z + dx * lightTangent.z) + dy * lightBitangent.z};
+        const f3    Wi = normalize3(wv);
+        attenuation *= gclamp(dot3(normal, Wi), 0.0f, 1.0f);
+        const float NoL = dot3(normal, Wi);
+        if (NoL > 0.0f && attenuation > 0.0f)
+        {
+            const float bias   = (2.0f * A.shadowBias) * gclamp(1.0f - NoL, 0.0f, 1.0f) + A.shadowBias;
+            const f3    origin = worldPos + normal * A.shadowBias;
+            LuxGlobalSDFTrace tr;
+            tr.worldPosition[0] = origin.x; tr.worldPosition[1] = origin.y; tr.worldPosition[2] = origin.z;
+            tr.minDistance = bias;
+            tr.worldDirection[0] = Wi.x; tr.worldDirection[1] = Wi.y; tr.worldDirection[2] = Wi.z;
+            tr.maxDistance = tMax - bias;
+            tr.stepScale = 1.0f;
+            tr.needsHitNormal = 0u;
+            const LuxGlobalSDFHit hit = trace_global_sdf_general<TEX>(P, sdf, tr, 0.0f);
+            result = hit.hitTime >= 0.0f ? 0u : 1u;
+        }
+    }
+    const uint32_t mask   = __ballot_sync(0xffffffffu, result != 0u);
+    const bool     stored = __shfl_sync(0xffffffffu, live ? 1 : 0, 0) != 0; // the shader's store sits inside lane 0's `depth != 1` branch
+    if (li == 0 && stored)
+        A.out[g] = mask;
+}
+
+// =====================================================================================================================
 // Global SDF build: mesh distance fields -> cascade volume -> min-mip.
 //   sdf_object_data_kernel   chunkCalculate's ObjectRasterizeData (GlobalDistanceField.cpp:484-508), one thread per mesh
 //   sdf_rasterize_kernel     SDFRasterizeModel.glsl:42-63 + SDFCommon.glsl:18-62; one block = one 8x8x8 group of a chunk dispatch,
@@ -2652,6 +2917,39 @@ void launch_sdf_rays(const TraceParams& p, bool useTextures, int count, const Lu
         sdf_rays_kernel<true><<<(count + 127) / 128, 128, 0, s>>>(p, count, traces, cascadeTraceStartBias, hits);
     else
         sdf_rays_kernel<false><<<(count + 127) / 128, 128, 0, s>>>(p, count, traces, cascadeTraceStartBias, hits);
+}
+
+void launch_sdf_reflection(const TraceParams& p, bool useTextures, const LuxDDGIUniform& ddgi, const LuxReflectionPushConstants& push, const void* irr,
+                           const void* dep, int width, int height, const float* gDepth, const float* gNormal, const float* gPbr, const uint32_t* sobol,
+                           const uint32_t* scr, void* out, cudaStream_t s)
+{
+    const int px = width * height;
+    if (px <= 0)
+        return;
+    ReflectionArgs a{ddgi, push, (const uint16_t*)irr, (const uint16_t*)dep, width, height, gDepth, gNormal, gPbr, sobol, scr, (uint2*)out};
+    if (useTextures)
+        sdf_reflection_kernel<true><<<(px + 127) / 128, 128, 0, s>>>(p, a);
+    else
+        sdf_reflection_kernel<false><<<(px + 127) / 128, 128, 0, s>>>(p, a);
+}
+
+void launch_sdf_shadow(const TraceParams& p, bool useTextures, const LuxLight& light, const float* viewProjInv, uint32_t numFrames, float shadowBias,
+                       int width, int height, const float* gDepth, const float* gNormal, const uint32_t* sobol, const uint32_t* scr, uint32_t* out,
+                       cudaStream_t s)
+{
+    const int groups = (width / 8) * (height / 4);
+    if (groups <= 0)
+        return;
+    ShadowArgs a{};
+    a.light = light;
+    for (int i = 0; i < 16; i++)
+        a.viewProjInv[i] = viewProjInv[i];
+    a.numFrames = numFrames; a.shadowBias = shadowBias; a.width = width; a.height = height;
+    a.gDepth = gDepth; a.gNormal = gNormal; a.sobol = sobol; a.scr = scr; a.out = out;
+    if (useTextures)
+        sdf_shadow_kernel<true><<<(groups + 3) / 4, 128, 0, s>>>(p, a);
+    else
+        sdf_shadow_kernel<false><<<(groups + 3) / 4, 128, 0, s>>>(p, a);
 }
 
 void launch_direct_light(const TraceParams& p, bool useTextures, const LuxLight& l, const float* cameraPosBias, void* light, int count,

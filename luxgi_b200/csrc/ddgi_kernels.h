@@ -121,6 +121,14 @@ void launch_sdf_rays(const TraceParams& p, bool useTextures, int count, const Lu
 void launch_direct_light(const TraceParams& p, bool useTextures, const LuxLight& l, const float* cameraPosBias, void* light, int count,
                          const uint32_t* texel, const float* P, const float* N, const float* albedo, const float* metallicRoughness, cudaStream_t s);
 
+// SDFReflection.comp / SDFShadow.comp over a G-buffer; sobol / scr = RGBA8 texels as uint32
+void launch_sdf_reflection(const TraceParams& p, bool useTextures, const LuxDDGIUniform& ddgi, const LuxReflectionPushConstants& push, const void* irr,
+                           const void* dep, int width, int height, const float* gDepth, const float* gNormal, const float* gPbr, const uint32_t* sobol,
+                           const uint32_t* scr, void* out, cudaStream_t s);
+void launch_sdf_shadow(const TraceParams& p, bool useTextures, const LuxLight& light, const float* viewProjInv, uint32_t numFrames, float shadowBias,
+                       int width, int height, const float* gDepth, const float* gNormal, const uint32_t* sobol, const uint32_t* scr, uint32_t* out,
+                       cudaStream_t s);
+
 // ---- global SDF build ----
 struct SdfMeshRecord // device copy of LuxMeshSDF without the host pointers
 {

@@ -27,6 +27,7 @@ EXPORTS = [
     "lux_ddgi_get_stage_ms", "lux_ddgi_sample_irradiance", "lux_ddgi_sample_probe", "lux_ddgi_indirect_light",
     "lux_ddgi_get_surface_light_cache", "lux_ddgi_build_global_sdf", "lux_ddgi_build_sdf_mip", "lux_ddgi_sdf_file_read", "lux_ddgi_download_fence", "lux_ddgi_wait_fence", "lux_ddgi_set_nccl_comm", "lux_ddgi_update_surface_light_cache_rows", "lux_ddgi_cull_surface_objects",
     "lux_ddgi_get_surface_cull_lists", "lux_ddgi_trace_global_sdf", "lux_ddgi_surface_direct_light",
+    "lux_ddgi_sdf_reflection", "lux_ddgi_sdf_shadow",
 ]
 
 
@@ -78,6 +79,8 @@ def load():
         "lux_ddgi_indirect_light": [vp, vp, i32, vp, vp, vp, vp, vp, C.c_float, vp, i32],
         "lux_ddgi_get_surface_light_cache": [vp, C.POINTER(vp), C.POINTER(sz)],
         "lux_ddgi_surface_direct_light": [vp, C.POINTER(abi.Light), vp, i32, vp, vp, vp, vp, vp, i32],
+        "lux_ddgi_sdf_reflection": [vp, C.POINTER(abi.ReflectionPushConstants), i32, i32, vp, vp, vp, vp, vp, vp, i32],
+        "lux_ddgi_sdf_shadow": [vp, C.POINTER(abi.Light), vp, C.c_uint32, C.c_float, i32, i32, vp, vp, vp, vp, vp, i32],
         "lux_ddgi_build_global_sdf": [vp, C.POINTER(abi.GlobalSDFData), C.POINTER(abi.MeshSDF), i32, C.c_float],
         "lux_ddgi_build_sdf_mip": [vp],
         "lux_ddgi_download_fence": [vp, C.POINTER(C.c_uint64)],
@@ -417,6 +420,33 @@ class DDGIPipeline:
         assert len(P) == len(N) == len(albedo) == len(mr) == len(texel)
         _check(self._lib.lux_ddgi_surface_direct_light(self._h, C.byref(light), _host_ptr(cam), len(texel), _host_ptr(texel), _host_ptr(P), _host_ptr(N),
                                                        _host_ptr(albedo), _host_ptr(mr), abi.MEM_HOST))
+
+    def sdf_reflection(self, push, depth, normals, pbr, sobol, scrambling, out=None) -> np.ndarray:
+        """SDFReflection.comp over a G-buffer (depth [h][w], normals / pbr [h][w][4] float32, RGBA8 blue-noise texels) -> RGBA16F bits [h][w][4];
+        `out` carries the previous image (pixels with depth == 1 keep it)."""
+        depth = np.ascontiguousarray(depth, dtype=np.float32)
+        h, w = depth.shape
+        normals = np.ascontiguousarray(normals, dtype=np.float32).reshape(h, w, 4)
+        pbr = np.ascontiguousarray(pbr, dtype=np.float32).reshape(h, w, 4)
+        sobol = np.ascontiguousarray(sobol, dtype=np.uint8).reshape(256, 4)
+        scrambling = np.ascontiguousarray(scrambling, dtype=np.uint8).reshape(128, 128, 4)
+        out = np.zeros((h, w, 4), dtype=np.uint16) if out is None else np.ascontiguousarray(out, dtype=np.uint16).reshape(h, w, 4)
+        _check(self._lib.lux_ddgi_sdf_reflection(self._h, C.byref(push), w, h, _host_ptr(depth), _host_ptr(normals), _host_ptr(pbr), _host_ptr(sobol),
+                                                 _host_ptr(scrambling), _host_ptr(out), abi.MEM_HOST))
+        return out
+
+    def sdf_shadow(self, light, view_proj_inv, num_frames, shadow_bias, depth, normals, sobol, scrambling, out=None) -> np.ndarray:
+        """SDFShadow.comp over a G-buffer -> uint32 visibility words [h/4][w/8] (bit (y%4)*8 + x%8 = visible); `out` carries the previous words."""
+        depth = np.ascontiguousarray(depth, dtype=np.float32)
+        h, w = depth.shape
+        normals = np.ascontiguousarray(normals, dtype=np.float32).reshape(h, w, 4)
+        vpi = np.ascontiguousarray(view_proj_inv, dtype=np.float32).reshape(16)
+        sobol = np.ascontiguousarray(sobol, dtype=np.uint8).reshape(256, 4)
+        scrambling = np.ascontiguousarray(scrambling, dtype=np.uint8).reshape(128, 128, 4)
+        out = np.zeros((h // 4, w // 8), dtype=np.uint32) if out is None else np.ascontiguousarray(out, dtype=np.uint32)
+        _check(self._lib.lux_ddgi_sdf_shadow(self._h, C.byref(light), _host_ptr(vpi), int(num_frames), float(shadow_bias), w, h, _host_ptr(depth),
+                                             _host_ptr(normals), _host_ptr(sobol), _host_ptr(scrambling), _host_ptr(out), abi.MEM_HOST))
+        return out
 
     def surface_light_cache(self) -> np.ndarray:
         p, n = C.c_void_p(), C.c_size_t()

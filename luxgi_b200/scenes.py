@@ -354,20 +354,48 @@ def cornell_boxes():
     return boxes
 
 
+CASCADE_DISTANCE_SCALES = (1.0, 2.5, 5.0, 10.0)  # GlobalDistanceField.cpp:600
+
+
+def make_sdf_data_cascades(centers, half_extents, res: int) -> abi.GlobalSDFData:
+    """GlobalSDFData of K nested cascades (GlobalDistanceField.cpp:262-279): cascade k occupies x in [k*res, (k+1)*res) of the volume."""
+    d = make_sdf_data(centers[0], half_extents[0], res)
+    for k, (c, h) in enumerate(zip(centers, half_extents)):
+        d.cascadePosDistance[k][:] = [float(c[0]), float(c[1]), float(c[2]), float(h)]
+        d.cascadeVoxelSize[k] = 2.0 * float(h) / res
+    d.cascadesCount = len(centers)
+    return d
+
+
 def cornell_scene(res: int = 64, counts=(8, 8, 8), rays: int = 64, atlas_res: int = 512, device="cpu", with_atlas=True,
-                  hysteresis=0.98, gamma=5.0) -> Scene:
+                  hysteresis=0.98, gamma=5.0, cascades: int = 1) -> Scene:
+    """cascades > 1: the reference's nested cascades (half extents in the ratio 1 : 2.5 : 5 : 10, the outermost = the room's 6.4), inner ones
+    off-centre; each is the same analytic field sampled on its own grid, side by side along x as the reference lays them out."""
     D = 6.4
     dev = torch.device(device)
     center = (0.0, 0.0, 0.0)
-    xs, ys, zs = voxel_centers(center, D, res, dev)
-    px, py, pz = xs[None, None, :], ys[None, :, None], zs[:, None, None]
     boxes = cornell_boxes()
-    room = -sd_box(px, py, pz, (0.0, 0.0, 0.0), (5.0, 5.0, 5.0))
-    d = room
-    for b in boxes[6:]:
-        d = torch.minimum(d, sd_box(px, py, pz, b.center, b.half, b.rot_y))
-    sdf = encode_sdf(d.expand(res, res, res), D).contiguous()
-    mip = build_mip(sdf, res, D)
+
+    def field(c, half):
+        xs, ys, zs = voxel_centers(c, half, res, dev)
+        px, py, pz = xs[None, None, :], ys[None, :, None], zs[:, None, None]
+        d = -sd_box(px, py, pz, (0.0, 0.0, 0.0), (5.0, 5.0, 5.0))
+        for b in boxes[6:]:
+            d = torch.minimum(d, sd_box(px, py, pz, b.center, b.half, b.rot_y))
+        f = encode_sdf(d.expand(res, res, res), half).contiguous()
+        return f, build_mip(f, res, half)
+
+    if cascades == 1:
+        sdf, mip = field(center, D)
+        sdf_data = make_sdf_data(center, D, res)
+    else:
+        assert 1 < cascades <= len(CASCADE_DISTANCE_SCALES)
+        halves = [D * CASCADE_DISTANCE_SCALES[k] / CASCADE_DISTANCE_SCALES[cascades - 1] for k in range(cascades)]
+        centers = [tuple(float(np.float32(o * (D - h))) + 0.0 for o in (0.25, -0.4, 0.15)) for h in halves]  # the outermost stays at the origin
+        parts = [field(c, h) for c, h in zip(centers, halves)]
+        sdf = torch.cat([p[0] for p in parts], dim=2).contiguous()
+        mip = torch.cat([p[1] for p in parts], dim=2).contiguous()
+        sdf_data = make_sdf_data_cascades(centers, halves, res)
 
     span = 8.4
     step = [span / (counts[0] - 1) if counts[0] > 1 else 1.2, span / (counts[1] - 1) if counts[1] > 1 else 1.2,
@@ -375,7 +403,7 @@ def cornell_scene(res: int = 64, counts=(8, 8, 8), rays: int = 64, atlas_res: in
     if tuple(counts) == (8, 8, 8):
         step = [1.2, 1.2, 1.2]
     uni = abi.make_uniform((-4.2, -4.2, -4.2), step, counts, rays, hysteresis=hysteresis, gamma=gamma)
-    sc = Scene("cornell", uni, make_sdf_data(center, D, res), sdf, mip)
+    sc = Scene("cornell", uni, sdf_data, sdf, mip)
 
     if with_atlas:
         albedo = torch.tensor([b.albedo for b in boxes], dtype=torch.float32, device=dev)

@@ -380,3 +380,43 @@ def surface_direct_light(sdf_data, sdf, mip, light, camera_pos_bias, light_cache
     rc = L.oracle_surface_direct_light(C.byref(sdf_data), _ptr(s), _ptr(m), C.byref(light), _ptr(cam), _ptr(light_cache), len(texel), _ptr(texel), _ptr(P), _ptr(N),
                                        _ptr(albedo), _ptr(mr))
     assert rc == 0, rc
+
+
+def _noise(sobol, scrambling):
+    sobol = np.ascontiguousarray(sobol, dtype=np.uint8).reshape(256, 4)
+    scrambling = np.ascontiguousarray(scrambling, dtype=np.uint8).reshape(128, 128, 4)
+    return sobol, scrambling
+
+
+def sdf_reflection(scene, irr, dep, push, g_depth, g_normal, g_pbr, sobol, scrambling, out):
+    """SDFReflection.comp over a G-buffer; `out` (uint16 [h][w][4], RGBA16F) is updated in place.  scene: OracleScene or Scene."""
+    osc = scene if isinstance(scene, OracleScene) else OracleScene(scene)
+    g_depth = np.ascontiguousarray(g_depth, dtype=np.float32)
+    h, w = g_depth.shape
+    g_normal = np.ascontiguousarray(g_normal, dtype=np.float32).reshape(h, w, 4)
+    g_pbr = np.ascontiguousarray(g_pbr, dtype=np.float32).reshape(h, w, 4)
+    sobol, scrambling = _noise(sobol, scrambling)
+    assert out.dtype == np.uint16 and out.shape == (h, w, 4) and out.flags.c_contiguous
+    L = lib()
+    L.oracle_sdf_reflection.restype = C.c_int
+    L.oracle_sdf_reflection.argtypes = [C.POINTER(SceneDesc), C.c_void_p, C.c_void_p, C.POINTER(abi.ReflectionPushConstants), C.c_int, C.c_int] + [C.c_void_p] * 6
+    rc = L.oracle_sdf_reflection(C.byref(osc.desc), _ptr(irr), _ptr(dep), C.byref(push), w, h, _ptr(g_depth), _ptr(g_normal), _ptr(g_pbr), _ptr(sobol),
+                                 _ptr(scrambling), _ptr(out))
+    assert rc == 0, rc
+
+
+def sdf_shadow(sdf_data, sdf, mip, light, view_proj_inv, num_frames, shadow_bias, g_depth, g_normal, sobol, scrambling, out_mask):
+    """SDFShadow.comp over a G-buffer; `out_mask` (uint32 [h/4][w/8]) is updated in place."""
+    g_depth = np.ascontiguousarray(g_depth, dtype=np.float32)
+    h, w = g_depth.shape
+    g_normal = np.ascontiguousarray(g_normal, dtype=np.float32).reshape(h, w, 4)
+    vpi = np.ascontiguousarray(view_proj_inv, dtype=np.float32).reshape(16)
+    sobol, scrambling = _noise(sobol, scrambling)
+    assert out_mask.dtype == np.uint32 and out_mask.shape == (h // 4, w // 8) and out_mask.flags.c_contiguous
+    s, m = _np(sdf), _np(mip)
+    L = lib()
+    L.oracle_sdf_shadow.restype = C.c_int
+    L.oracle_sdf_shadow.argtypes = [C.POINTER(abi.GlobalSDFData), C.c_void_p, C.c_void_p, C.POINTER(abi.Light), C.c_void_p, C.c_uint32, C.c_float, C.c_int, C.c_int] + [C.c_void_p] * 5
+    rc = L.oracle_sdf_shadow(C.byref(sdf_data), _ptr(s), _ptr(m), C.byref(light), _ptr(vpi), int(num_frames), float(shadow_bias), w, h, _ptr(g_depth), _ptr(g_normal),
+                             _ptr(sobol), _ptr(scrambling), _ptr(out_mask))
+    assert rc == 0, rc

@@ -536,10 +536,10 @@ vec4 sampleGlobalSurfaceAtlas(const Scene& sc, vec3 worldPosition, vec3 worldNor
 
 // texture(samplerCube, dir).rgb — Vulkan cube face selection (spec §16.5.4), bilinear inside the face,
 // clamp at face edges.  The reference binds a 1x1 fallback cube when the scene has no skybox.
-vec3 sampleSky(const Scene& sc, vec3 d)
+vec4 sampleSky4(const Scene& sc, vec3 d)
 {
     if (!sc.sky || sc.skyFace <= 0)
-        return {0, 0, 0};
+        return {0, 0, 0, 0};
     float ax = std::fabs(d.x), ay = std::fabs(d.y), az = std::fabs(d.z);
     int   face;
     float sc_, tc, ma;
@@ -554,14 +554,19 @@ vec3 sampleSky(const Scene& sc, vec3 d)
     int   x0 = iclamp((int)fx, 0, N - 1), x1 = iclamp((int)fx + 1, 0, N - 1);
     int   y0 = iclamp((int)fy, 0, N - 1), y1 = iclamp((int)fy + 1, 0, N - 1);
     const uint16_t* base = sc.sky + (size_t)face * N * N * 4;
-    float out[3];
-    for (int ch = 0; ch < 3; ch++)
+    float out[4];
+    for (int ch = 0; ch < 4; ch++)
     {
         float a = lerp1(h2f(base[((size_t)y0 * N + x0) * 4 + ch]), h2f(base[((size_t)y0 * N + x1) * 4 + ch]), axw);
         float b = lerp1(h2f(base[((size_t)y1 * N + x0) * 4 + ch]), h2f(base[((size_t)y1 * N + x1) * 4 + ch]), axw);
         out[ch] = lerp1(a, b, ayw);
     }
-    return {out[0], out[1], out[2]};
+    return {out[0], out[1], out[2], out[3]};
+}
+inline vec3 sampleSky(const Scene& sc, vec3 d)
+{
+    vec4 s = sampleSky4(sc, d);
+    return {s.x, s.y, s.z};
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1695,6 +1700,234 @@ extern "C" void oracle_octohedral_to_direction(float ex, float ey, float* out3)
 {
     vec3 v = octohedralToDirection({ex, ey});
     out3[0] = v.x; out3[1] = v.y; out3[2] = v.z;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// The screen-space tracyGlobalSDF users ("next" row f4): Shaders/SDF/SDFReflection.comp and Shaders/SDF/SDFShadow.comp with
+// Raytraced/BlueNoise.glsl:8-19, Raytraced/BRDF.glsl:176-201 (importanceSampleGGX), Common/Math.glsl:27-42.
+// cross / reflect follow the contract's reading of the GLSL.std.450 instructions: every product, sum and difference rounded.
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+inline vec3 cross3(vec3 a, vec3 b) { return {a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y}; }
+inline vec3 reflect3(vec3 i, vec3 n)
+{
+    float t = 2.0f * dot3(n, i);
+    return {i.x - t * n.x, i.y - t * n.y, i.z - t * n.z};
+}
+inline float unorm8(uint8_t b) { return (float)b / 255.0f; }
+// sampleBlueNoise, BlueNoise.glsl:8-19: sobol = 256 x 1 RGBA8, scramblingRanking = 128 x 128 RGBA8
+float sampleBlueNoise(int cx, int cy, int samplerIndex, int dimension, const uint8_t* sobol, const uint8_t* scr)
+{
+    cx = cx % 128;
+    cy = cy % 128;
+    samplerIndex = samplerIndex % 256;
+    dimension    = dimension % 4;
+    const uint8_t* t = scr + ((size_t)cy * 128 + cx) * 4;
+    int rankedIndex = samplerIndex ^ (int)gclamp(unorm8(t[2]) * 256.0f, 0.0f, 255.0f);
+    int value       = (int)gclamp(unorm8(sobol[(size_t)rankedIndex * 4 + dimension]) * 256.0f, 0.0f, 255.0f);
+    value           = value ^ (int)gclamp(unorm8(t[dimension % 2]) * 256.0f, 0.0f, 255.0f);
+    return (0.5f + (float)value) / 256.0f;
+}
+inline vec3 worldPositionFromDepth(float tx, float ty, float d, const float* m) // Common/Math.glsl:35-42
+{
+    float sx = tx * 2.0f - 1.0f, sy = ty * 2.0f - 1.0f;
+    float wx = ((m[0] * sx + m[4] * sy) + m[8] * d) + m[12] * 1.0f;
+    float wy = ((m[1] * sx + m[5] * sy) + m[9] * d) + m[13] * 1.0f;
+    float wz = ((m[2] * sx + m[6] * sy) + m[10] * d) + m[14] * 1.0f;
+    float ww = ((m[3] * sx + m[7] * sy) + m[11] * d) + m[15] * 1.0f;
+    return {wx / ww, wy / ww, wz / ww};
+}
+// importanceSampleGGX(...).xyz, BRDF.glsl:176-201 (the pdf is computed and dropped by the caller)
+vec3 importanceSampleGGX(vec2 E, vec3 N, float roughness)
+{
+    const float TWO_PI = 6.283185482025146484375f; // 2.0f * M_PI folded by glslang
+    float a = roughness * roughness, m2 = a * a;
+    float phi      = TWO_PI * E.x;
+    float cosTheta = std::sqrt((1.0f - E.y) / (1.0f + (m2 - 1.0f) * E.y));
+    float sinTheta = std::sqrt(1.0f - cosTheta * cosTheta);
+    vec3  H  = {cos_rn(phi) * sinTheta, sin_rn(phi) * sinTheta, cosTheta};
+    vec3  up = std::fabs(N.z) < 0.999f ? vec3{0.0f, 0.0f, 1.0f} : vec3{1.0f, 0.0f, 0.0f};
+    vec3  tangent   = normalize3(cross3(up, N));
+    vec3  bitangent = cross3(N, tangent);
+    vec3  sv = {(tangent.x * H.x + bitangent.x * H.y) + N.x * H.z, (tangent.y * H.x + bitangent.y * H.y) + N.y * H.z,
+                (tangent.z * H.x + bitangent.z * H.y) + N.z * H.z};
+    return normalize3(sv);
+}
+void fillScene(Scene& sc, const OracleSceneDesc* s)
+{
+    if (s->ddgi)
+        sc.ddgi = *s->ddgi;
+    sc.sdfData = *s->sdfData;
+    int res = (int)s->sdfData->resolution, casc = (int)s->sdfData->cascadesCount;
+    sc.tex = Tex3D{s->sdf, res * casc, res, res};
+    sc.mip = Tex3D{s->mip, (res / 4) * casc, res / 4, res / 4};
+    sc.hasAtlas = s->atlasData != nullptr;
+    if (sc.hasAtlas)
+        sc.atlasData = *s->atlasData;
+    sc.chunks = s->chunks; sc.cull = s->cull; sc.objects = s->objects; sc.tiles = s->tiles;
+    sc.light = s->light; sc.depth = s->depth;
+    sc.skyFace = s->skyFace; sc.sky = s->sky;
+}
+} // namespace
+
+// SDFReflection.comp:84-163.  gDepth [h][w] D32F, gNormal / gPbr [h][w][4] RGBA32F, out [h][w][4] RGBA16F (pixels with depth == 1 untouched).
+extern "C" int oracle_sdf_reflection(const OracleSceneDesc* s, const uint16_t* irr, const uint16_t* depthAtlas, const LuxReflectionPushConstants* push,
+                                     int width, int height, const float* gDepth, const float* gNormal, const float* gPbr, const uint8_t* sobol,
+                                     const uint8_t* scramblingRanking, uint16_t* out)
+{
+    if (!s || !s->ddgi || !s->sdfData || !s->sdf || !s->mip || !irr || !depthAtlas || !push || !gDepth || !gNormal || !gPbr || !sobol || !scramblingRanking || !out)
+        return -1;
+    Scene sc{};
+    fillScene(sc, s);
+    Atlas2D ai{irr, sc.ddgi.irradianceTextureWidth, sc.ddgi.irradianceTextureHeight, 4};
+    Atlas2D ad{depthAtlas, sc.ddgi.depthTextureWidth, sc.ddgi.depthTextureHeight, 2};
+    const float MIRROR = 0.05f, DDGI_ROUGH = 0.45f; // Reflection/ReflectionCommon.glsl:7-8
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int y = 0; y < height; y++)
+        for (int x = 0; x < width; x++)
+        {
+            size_t o = (size_t)y * width + x;
+            float  depth = gDepth[o];
+            if (!(depth != 1.0f))
+                continue;
+            float tx = ((float)x + 0.5f) / (float)width, ty = ((float)y + 0.5f) / (float)height;
+            vec3  worldPos  = worldPositionFromDepth(tx, ty, depth, push->viewProjInv);
+            float roughness = gPbr[4 * o + 1];
+            vec3  normal    = octohedralToDirection({gNormal[4 * o], gNormal[4 * o + 1]});
+            vec3  Wo        = normalize3(sub({push->cameraPosition[0], push->cameraPosition[1], push->cameraPosition[2]}, worldPos));
+            worldPos        = add(worldPos, mul(normal, sc.sdfData.cascadeVoxelSize[0]));
+            vec3 negWo = {-Wo.x, -Wo.y, -Wo.z};
+            vec4 color = {0, 0, 0, 0};
+            Counters cn;
+            auto trace = [&](vec3 R) -> vec4 { // trace(), SDFReflection.comp:86-117
+                Hit hit = tracyGlobalSDF(sc, worldPos, R, LUX_GLOBAL_SDF_WORLD_SIZE, 1.0f, 0.0f, cn);
+                if (hit.hitTime >= 0.0f)
+                {
+                    float surfaceThreshold = sc.sdfData.cascadeVoxelSize[hit.hitCascade] * 1.05f;
+                    return sampleGlobalSurfaceAtlas(sc, add(worldPos, mul(R, hit.hitTime)), {-R.x, -R.y, -R.z}, surfaceThreshold, cn);
+                }
+                return sampleSky4(sc, R);
+            };
+            if (roughness < MIRROR)
+                color = trace(reflect3(negWo, normal));
+            else if (roughness > DDGI_ROUGH && push->approximateWithDDGI == 1u)
+            {
+                vec3 R = reflect3(negWo, normal);
+                vec3 e = sampleIrradiance(sc.ddgi, worldPos, R, Wo, ai, ad);
+                color  = {push->roughDDGIIntensity * e.x, push->roughDDGIIntensity * e.y, push->roughDDGIIntensity * e.z, 0.0f};
+            }
+            else
+            {
+                vec2 Xi = {sampleBlueNoise(x, y, (int)push->numFrames, 0, sobol, scramblingRanking) * push->trim,
+                           sampleBlueNoise(x, y, (int)push->numFrames, 1, sobol, scramblingRanking) * push->trim};
+                vec3 Wh = importanceSampleGGX(Xi, normal, roughness);
+                color   = trace(reflect3(negWo, Wh));
+            }
+            out[4 * o] = f2h(color.x); out[4 * o + 1] = f2h(color.y); out[4 * o + 2] = f2h(color.z); out[4 * o + 3] = f2h(color.w);
+        }
+    return 0;
+}
+
+// SDFShadow.comp:121-157 with fetchLight :42-117 (softShadow = true).  outMask [height/4][width/8] uint32, read-modify-write.
+extern "C" int oracle_sdf_shadow(const LuxGlobalSDFData* sdfData, const uint16_t* sdf, const uint16_t* mip, const LuxLight* light, const float* viewProjInv,
+                                 uint32_t numFrames, float shadowBias, int width, int height, const float* gDepth, const float* gNormal,
+                                 const uint8_t* sobol, const uint8_t* scramblingRanking, uint32_t* outMask)
+{
+    if (!sdfData || !sdf || !mip || !light || !viewProjInv || !gDepth || !gNormal || !sobol || !scramblingRanking || !outMask || width % 8 || height % 4)
+        return -1;
+    Scene sc{};
+    sc.sdfData = *sdfData;
+    const int res = (int)sdfData->resolution, casc = (int)sdfData->cascadesCount;
+    sc.tex = Tex3D{sdf, res * casc, res, res};
+    sc.mip = Tex3D{mip, (res / 4) * casc, res / 4, res / 4};
+    const LuxLight L = *light;
+    const float PI_F = 3.1415926535897932384626433832795f; // Common/Math.glsl:6
+    const int gw = width / 8, gh = height / 4;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int g = 0; g < gw * gh; g++)
+    {
+        const int gx = g % gw, gy = g / gw;
+        uint32_t visibility = 0;
+        bool     stored = false;
+        for (int li = 0; li < 32; li++)
+        {
+            const int x = gx * 8 + (li % 8), y = gy * 4 + (li / 8);
+            size_t o = (size_t)y * width + x;
+            float  depth = gDepth[o];
+            if (!(depth != 1.0f))
+                continue;
+            if (li == 0)
+                stored = true;
+            float tx = ((float)x + 0.5f) / (float)width, ty = ((float)y + 0.5f) / (float)height;
+            vec3  worldPos = worldPositionFromDepth(tx, ty, depth, viewProjInv);
+            vec3  normal   = octohedralToDirection({gNormal[4 * o], gNormal[4 * o + 1]});
+            vec2  rnd = {sampleBlueNoise(x, y, (int)numFrames, 0, sobol, scramblingRanking), sampleBlueNoise(x, y, (int)numFrames, 1, sobol, scramblingRanking)};
+            // fetchLight(light, worldPos, normal, rnd, Wi, tMax, attenuation, true)
+            vec3  lightDir = {0, 0, 0}, Wi = {0, 0, 0};
+            float lightRadius = 0.0f, tMax = 0.0f, attenuation = 0.0f;
+            if (L.type == LUX_LIGHT_DIRECTIONAL)
+            {
+                lightDir = {-L.direction[0], -L.direction[1], -L.direction[2]};
+                tMax = LUX_GLOBAL_SDF_WORLD_SIZE;
+                Wi = lightDir;
+                lightRadius = L.direction[3];
+                attenuation = 1.0f;
+            }
+            else if (L.type == LUX_LIGHT_POINT)
+            {
+                vec3  dir  = sub({L.position[0], L.position[1], L.position[2]}, worldPos);
+                float dist = length3(dir);
+                lightDir = normalize3(dir);
+                attenuation = 1.0f;
+                Wi = lightDir;
+                tMax = dist;
+                lightRadius = L.direction[3] / dist;
+            }
+            else if (L.type == LUX_LIGHT_SPOT)
+            {
+                vec3  Lv = sub({L.position[0], L.position[1], L.position[2]}, worldPos);
+                float cutoffAngle = 1.0f - L.angle;
+                lightDir = normalize3(Lv);
+                float dist    = length3(Lv);
+                float theta   = dot3(lightDir, {L.direction[0], L.direction[1], L.direction[2]});
+                float epsilon = cutoffAngle - cutoffAngle * 0.9f;
+                attenuation = (theta - cutoffAngle) / epsilon;
+                attenuation *= L.radius / (pow_rn(dist, 2.0f) + 1.0f);
+                attenuation = gclamp(attenuation, 0.0f, 1.0f);
+                Wi = lightDir;
+                tMax = dist;
+                lightRadius = L.direction[3] / dist;
+            }
+            {
+                vec3  lightTangent   = normalize3(cross3(lightDir, {0.0f, 1.0f, 0.0f}));
+                vec3  lightBitangent = normalize3(cross3(lightTangent, lightDir));
+                float pointRadius = lightRadius * std::sqrt(rnd.x);
+                float pointAngle  = (rnd.y * 2.0f) * PI_F;
+                float dx = pointRadius * cos_rn(pointAngle), dy = pointRadius * sin_rn(pointAngle);
+                vec3  w = {(lightDir.x + dx * lightTangent.x) + dy * lightBitangent.x, (lightDir.y + dx * lightTangent.y) + dy * lightBitangent.y,
+                           (lightDir.z + dx * lightTangent.z) + dy * lightBitangent.z};
+                Wi = normalize3(w);
+            }
+            attenuation *= gclamp(dot3(normal, Wi), 0.0f, 1.0f);
+            float    NoL = dot3(normal, Wi);
+            uint32_t result = 0;
+            if (NoL > 0.0f)
+            {
+                if (attenuation > 0.0f)
+                {
+                    float bias = (2.0f * shadowBias) * gclamp(1.0f - NoL, 0.0f, 1.0f) + shadowBias;
+                    vec3  rayOrigin = add(worldPos, mul(normal, shadowBias));
+                    Counters cn;
+                    Hit hit = tracyGlobalSDF(sc, rayOrigin, Wi, tMax - bias, 1.0f, 0.0f, cn);
+                    result  = hit.hitTime >= 0.0f ? 0u : 1u;
+                }
+            }
+            visibility |= result << li;
+        }
+        if (stored)
+            outMask[(size_t)gy * gw + gx] = visibility;
+    }
+    return 0;
 }
 
 extern "C" {

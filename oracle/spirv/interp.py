@@ -30,7 +30,7 @@ OP = {
     29: "TypeRuntimeArray", 30: "TypeStruct", 32: "TypePointer", 33: "TypeFunction", 41: "ConstantTrue", 42: "ConstantFalse",
     43: "Constant", 44: "ConstantComposite", 46: "ConstantNull", 54: "Function", 55: "FunctionParameter", 56: "FunctionEnd",
     57: "FunctionCall", 59: "Variable", 61: "Load", 62: "Store", 65: "AccessChain", 66: "InBoundsAccessChain", 71: "Decorate",
-    72: "MemberDecorate", 79: "VectorShuffle", 80: "CompositeConstruct", 81: "CompositeExtract", 82: "CompositeInsert",
+    72: "MemberDecorate", 77: "VectorExtractDynamic", 79: "VectorShuffle", 80: "CompositeConstruct", 81: "CompositeExtract", 82: "CompositeInsert",
     83: "CopyObject", 87: "ImageSampleImplicitLod", 88: "ImageSampleExplicitLod", 95: "ImageFetch", 96: "ImageGather", 98: "ImageRead", 99: "ImageWrite",
     100: "Image", 103: "ImageQuerySizeLod", 110: "ConvertFToS", 109: "ConvertFToU", 111: "ConvertSToF", 112: "ConvertUToF", 124: "Bitcast", 126: "SNegate",
     127: "FNegate", 128: "IAdd", 129: "FAdd", 130: "ISub", 131: "FSub", 132: "IMul", 133: "FMul", 134: "UDiv", 135: "SDiv",
@@ -38,15 +38,15 @@ OP = {
     144: "VectorTimesMatrix", 145: "MatrixTimesVector", 146: "MatrixTimesMatrix", 148: "Dot", 154: "Any", 155: "All",
     164: "LogicalEqual", 165: "LogicalNotEqual", 166: "LogicalOr", 167: "LogicalAnd", 168: "LogicalNot", 169: "Select",
     170: "IEqual", 171: "INotEqual", 172: "UGreaterThan", 173: "SGreaterThan", 174: "UGreaterThanEqual", 175: "SGreaterThanEqual",
-    176: "ULessThan", 177: "SLessThan", 178: "ULessThanEqual", 179: "SLessThanEqual", 180: "FOrdEqual", 182: "FOrdNotEqual",
+    176: "ULessThan", 177: "SLessThan", 178: "ULessThanEqual", 179: "SLessThanEqual", 180: "FOrdEqual", 182: "FOrdNotEqual", 183: "FUnordNotEqual",
     184: "FOrdLessThan", 186: "FOrdGreaterThan", 188: "FOrdLessThanEqual", 190: "FOrdGreaterThanEqual", 194: "ShiftRightLogical",
     195: "ShiftRightArithmetic", 196: "ShiftLeftLogical", 197: "BitwiseOr", 198: "BitwiseXor", 199: "BitwiseAnd", 200: "Not",
-    224: "ControlBarrier", 225: "MemoryBarrier", 234: "AtomicIAdd", 245: "Phi", 246: "LoopMerge", 247: "SelectionMerge", 248: "Label", 249: "Branch",
+    224: "ControlBarrier", 225: "MemoryBarrier", 234: "AtomicIAdd", 241: "AtomicOr", 245: "Phi", 246: "LoopMerge", 247: "SelectionMerge", 248: "Label", 249: "Branch",
     250: "BranchConditional", 252: "Kill", 253: "Return", 254: "ReturnValue", 255: "Unreachable", 400: "CopyLogical",
 }
 GLSL = {4: "FAbs", 8: "Floor", 10: "Fract", 13: "Sin", 14: "Cos", 26: "Pow", 31: "Sqrt", 32: "InverseSqrt", 34: "MatrixInverse",
         37: "FMin", 38: "UMin", 39: "SMin", 40: "FMax", 41: "UMax", 42: "SMax", 43: "FClamp", 44: "UClamp", 45: "SClamp", 46: "FMix", 48: "Step",
-        66: "Length", 67: "Distance", 69: "Normalize"}
+        66: "Length", 67: "Distance", 68: "Cross", 69: "Normalize", 71: "Reflect"}
 DEC_BUILTIN, DEC_BINDING, DEC_SET = 11, 33, 34
 BUILTIN = {24: "NumWorkgroups", 25: "WorkgroupSize", 26: "WorkgroupId", 27: "LocalInvocationId", 28: "GlobalInvocationId", 29: "LocalInvocationIndex"}
 SC_FUNCTION, SC_WORKGROUP = 7, 4
@@ -185,10 +185,9 @@ class TextureCube:
         cl = lambda q: min(max(q, 0), N - 1)
         x0, x1, y0, y1 = cl(int(fx)), cl(int(fx) + 1), cl(int(fy)), cl(int(fy) + 1)
         out = []
-        for ch in range(3):
+        for ch in range(4):
             t = lambda xx, yy: F(self.f[face, yy, xx, ch])
             out.append(lerp(lerp(t(x0, y0), t(x1, y0), axw), lerp(t(x0, y1), t(x1, y1), axw), ayw))
-        out.append(F(1))
         return out
 
 
@@ -469,6 +468,11 @@ class Invocation:
                     old = ptr.load()
                     ptr.store((old + V(a[5])) & M32)
                     env[a[1]] = old
+                elif name == "AtomicOr":
+                    ptr = V(a[2])
+                    old = ptr.load()
+                    ptr.store((old | V(a[5])) & M32)
+                    env[a[1]] = old
                 else:
                     env[a[1]] = self.alu(name, a, V)
             prev, label = label, nxt
@@ -527,6 +531,7 @@ class Invocation:
                "UGreaterThanEqual": lambda p, q: p >= q, "SLessThan": lambda p, q: s32(p) < s32(q), "SLessThanEqual": lambda p, q: s32(p) <= s32(q),
                "SGreaterThan": lambda p, q: s32(p) > s32(q), "SGreaterThanEqual": lambda p, q: s32(p) >= s32(q),
                "IEqual": lambda p, q: (p & M32) == (q & M32), "INotEqual": lambda p, q: (p & M32) != (q & M32),
+               "FUnordNotEqual": lambda p, q: bool(p != q) or bool(np.isnan(p) or np.isnan(q)),
                "FOrdEqual": lambda p, q: bool(p == q), "FOrdNotEqual": lambda p, q: bool(p != q) and not (np.isnan(p) or np.isnan(q)),
                "FOrdLessThan": lambda p, q: bool(p < q), "FOrdGreaterThan": lambda p, q: bool(p > q),
                "FOrdLessThanEqual": lambda p, q: bool(p <= q), "FOrdGreaterThanEqual": lambda p, q: bool(p >= q),
@@ -549,6 +554,7 @@ class Invocation:
                     return p if isinstance(p, np.floating) else F(struct.unpack("<f", struct.pack("<I", p & M32))[0])
                 return struct.unpack("<I", struct.pack("<f", float(p)))[0] if isinstance(p, np.floating) else p & M32
             return vec(bc, x(2))
+        if name == "VectorExtractDynamic": return copyv(x(2)[x(3) & M32])
         if name == "CompositeExtract":
             v = x(2)
             for k in a[3:]:
@@ -624,6 +630,16 @@ class Invocation:
             with np.errstate(divide="ignore", invalid="ignore"):
                 inv = F(np.divide(F(1), F(np.sqrt(acc))))
                 return [F(e * inv) for e in v]
+        if op == "Cross":  # (a.y*b.z - b.y*a.z, a.z*b.x - b.z*a.x, a.x*b.y - b.x*a.y), every product and difference rounded
+            p, q = o[0], o[1]
+            return [F(F(p[1] * q[2]) - F(q[1] * p[2])), F(F(p[2] * q[0]) - F(q[2] * p[0])), F(F(p[0] * q[1]) - F(q[0] * p[1]))]
+        if op == "Reflect":  # I - 2 * dot(N, I) * N (the factor 2 is exact, so its position does not matter)
+            i, n = o[0], o[1]
+            d = F(n[0] * i[0])
+            for k in range(1, len(i)):
+                d = F(d + F(n[k] * i[k]))
+            t = F(F(2) * d)
+            return [F(e - F(t * nn)) for e, nn in zip(i, n)]
         if op == "MatrixInverse": return inverse4(o[0])
         raise NotImplementedError(f"GLSL.std.450 {num}")
 

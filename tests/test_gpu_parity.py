@@ -569,3 +569,140 @@ def test_surface_direct_light_matches_shipped_spirv_and_oracle(oracle):
         with pytest.raises(ddgi.LuxError):
             pipe.surface_direct_light(bad, gold["camera"], texel, gold["pos"], normals, gold["albedo"], gold["pbr"])
         pipe.close()
+
+
+@pytest.mark.parametrize("cascades", [2, 4])
+def test_cascaded_global_sdf_matches_oracle(oracle, cascades):
+    """The reference always runs a CASCADED global SDF (2 cascades, GlobalDistanceField.cpp:182-191; the structs carry 4): nested, off-centre
+    cascades side by side in one volume, most probes outside cascade 0.  Every trace variant reproduces the oracle's ray buffers and atlases bit
+    for bit over 3 frames, and the generic ray entry every GlobalSDFHit field incl. hitCascade; the oracle itself is pinned on this layout by
+    the shipped GISDFRays.comp.spv (tests/test_spirv_golden.py::test_cascaded_trace_matches_shipped_spirv)."""
+    sc = scenes.cornell_scene(res=64, counts=(8, 4, 8), rays=96, atlas_res=256, cascades=cascades)
+    rots = [scenes.frame_rotation(f) for f in range(3)]
+    orc = oracle.OraclePipeline(sc)
+    for r in rots:
+        orc.update(r)
+    for flags in (0, abi.FLAG_SDF_LOADS, abi.FLAG_TRACE_SIMPLE, abi.FLAG_SHADE_UNSORTED, abi.FLAG_NO_PREFILTER):
+        pipe = run_engine(sc, rots, flags=flags)
+        assert_rays_match(pipe, orc)
+        assert_atlases_match(pipe, orc)
+        if flags in (0, abi.FLAG_SDF_LOADS):
+            rng = np.random.default_rng(17)
+            n = 20000
+            traces = np.zeros(n, dtype=abi.SDF_TRACE_DTYPE)
+            traces["worldPosition"] = rng.uniform(-7.0, 7.0, size=(n, 3)).astype(np.float32)  # some origins outside every cascade
+            d = rng.normal(size=(n, 3)).astype(np.float32)
+            traces["worldDirection"] = d / np.linalg.norm(d, axis=1, keepdims=True)
+            traces["maxDistance"] = np.where(rng.random(n) < 0.5, abi.GLOBAL_SDF_WORLD_SIZE, rng.uniform(0.5, 12.0, n)).astype(np.float32)
+            traces["stepScale"] = rng.choice(np.float32([0.5, 1.0, 2.0]), n)
+            traces["needsHitNormal"] = rng.integers(0, 2, n)
+            for bias in (0.0, 2.0):
+                want = oracle.trace_global_sdf(sc.sdf_data, sc.sdf, sc.mip, traces, bias)
+                got = pipe.trace_global_sdf(traces, bias)
+                assert (np.bincount(want["hitCascade"][want["hitTime"] >= 0], minlength=cascades) > 0).all()
+                for f in abi.SDF_HIT_DTYPE.names:
+                    a, b = got[f].view(np.uint32), want[f].view(np.uint32)
+                    assert np.array_equal(a, b), f"flags {flags} bias {bias}: {f} differs on {(a != b).sum()} of {a.size} values"
+        pipe.close()
+
+
+def _screen_inputs(w, h, seed, eye=(0.3, 0.4, 3.9), target=(-0.2, -0.5, -1.0)):
+    from tests.golden.make_spirv_golden_consumer import look_at_perspective
+
+    rng = np.random.default_rng(seed)
+    vp = look_at_perspective(np.array(eye, dtype=np.float64), np.array(target, dtype=np.float64), np.array([0.0, 1.0, 0.0]), np.radians(70), w / h, 0.1, 50.0)
+    vpi = np.linalg.inv(vp).astype(np.float32).T.reshape(16).copy()
+    depth = rng.uniform(0.90, 0.985, (h, w)).astype(np.float32)
+    far = rng.random((h, w)) < 0.1
+    depth[far] = rng.uniform(0.9975, 0.9995, int(far.sum())).astype(np.float32)
+    depth[rng.random((h, w)) < 0.05] = 1.0
+    depth[0, 0] = 1.0
+    nrm = np.zeros((h, w, 4), dtype=np.float32)
+    nrm[..., :2] = rng.uniform(-1, 1, (h, w, 2))
+    pbr = np.zeros((h, w, 4), dtype=np.float32)
+    pbr[..., 1] = rng.choice(np.float32([0.01, 0.04, 0.2, 0.44, 0.5, 0.9]), (h, w))
+    sobol = rng.integers(0, 256, (256, 4), dtype=np.uint8)
+    scr = rng.integers(0, 256, (128, 128, 4), dtype=np.uint8)
+    return vpi, depth, nrm, pbr, sobol, scr
+
+
+def test_sdf_reflection_matches_shipped_spirv_and_oracle(oracle):
+    """Row f4: lux_ddgi_sdf_reflection = SDFReflection.comp.  (a) the RGBA16F image of the shipped SPIR-V on the golden G-buffer
+    (tests/golden/spirv_golden_screen.npz), bit for bit, approximateWithDDGI on and off, texture and load SDF paths; (b) against the oracle on a
+    150 x 130 G-buffer (ragged against every block size) in the 2-cascade Cornell scene after two probe updates of the engine itself."""
+    from tests.golden import make_spirv_golden as base
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "spirv_golden_screen.npz"))
+    sc = base.golden_scene()
+    sc.uniform = abi.DDGIUniform.from_buffer_copy(g["uniform"].tobytes())
+    for flags in (0, abi.FLAG_SDF_LOADS):
+        pipe = ddgi.DDGIPipeline(sc.uniform, flags=flags)
+        pipe.set_scene(sc)
+        pipe.restore(g["irradiance"], g["depth_atlas"], 2, 0)
+        for approx in (1, 0):
+            frames, trim, inten = g[f"refl_params_{approx}"]
+            push = abi.make_reflection_push(g["refl_camera"], g["refl_view_proj_inv"], int(frames), trim, inten, approx)
+            got = pipe.sdf_reflection(push, g["refl_depth"], g["refl_normal"], g["refl_pbr"], g["sobol"], g["scrambling"], out=np.full(g["refl_out_1"].shape, 0x3555, dtype=np.uint16))
+            want = g[f"refl_out_{approx}"]
+            assert np.array_equal(got, want), f"flags {flags} approximateWithDDGI={approx}: {(got != want).any(-1).sum()} pixels differ from the shipped shader"
+        pipe.close()
+    # (b)
+    sc = scenes.cornell_scene(res=32, counts=(4, 4, 4), rays=64, atlas_res=256, cascades=2)
+    sky = np.zeros((6, 2, 2, 4), dtype=np.float16)
+    sky[...] = np.random.default_rng(2).uniform(0, 2, sky.shape)
+    sc.sky_face, sc.sky = 2, sky
+    sc.uniform.normalBias = 0.1
+    pipe = ddgi.DDGIPipeline(sc.uniform)
+    pipe.set_scene(sc)
+    for f in range(2):
+        pipe.update(scenes.frame_rotation(f))
+    irr, dep = pipe.irradiance, pipe.depth
+    w, h = 150, 130
+    vpi, depth, nrm, pbr, sobol, scr = _screen_inputs(w, h, 41)
+    for approx in (1, 0):
+        push = abi.make_reflection_push([0.3, 0.4, 3.9], vpi, 3, 0.9, 1.1, approx)
+        want = np.full((h, w, 4), 0x1234, dtype=np.uint16)
+        oracle.sdf_reflection(sc, irr, dep, push, depth, nrm, pbr, sobol, scr, want)
+        got = pipe.sdf_reflection(push, depth, nrm, pbr, sobol, scr, out=np.full((h, w, 4), 0x1234, dtype=np.uint16))
+        assert (want[..., 0] == 0x1234).sum() >= (depth == 1.0).sum() > 100
+        assert np.array_equal(got, want), f"approximateWithDDGI={approx}: {(got != want).any(-1).sum()} of {w * h} pixels differ from the oracle"
+    pipe.close()
+
+
+def test_sdf_shadow_matches_shipped_spirv_and_oracle(oracle):
+    """Row f4: lux_ddgi_sdf_shadow = SDFShadow.comp.  (a) the R32UI words of the shipped SPIR-V on the golden G-buffer for a directional, a point
+    and a spot light, incl. the workgroup that stores nothing; (b) against the oracle on a 160 x 96 G-buffer in the 2-cascade Cornell scene."""
+    from tests.golden import make_spirv_golden as base
+    from tests.golden import make_spirv_golden_screen as gs
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "spirv_golden_screen.npz"))
+    sc = base.golden_scene()
+    h, w = g["shadow_depth"].shape
+    for flags in (0, abi.FLAG_SDF_LOADS):
+        pipe = ddgi.DDGIPipeline(sc.uniform, flags=flags)
+        pipe.set_global_sdf(sc.sdf_data, sc.sdf, sc.mip)
+        for name in gs.LIGHTS:
+            got = pipe.sdf_shadow(abi.make_light(g[f"shadow_light_{name}"]), g["shadow_view_proj_inv"], int(g["shadow_frames"]), float(g["shadow_bias"]),
+                                  g["shadow_depth"], g["shadow_normal"], g["sobol"], g["scrambling"], out=np.full((h // 4, w // 8), 0xDEADBEEF, dtype=np.uint32))
+            want = g[f"shadow_out_{name}"]
+            assert np.array_equal(got, want), f"flags {flags} {name}: {[hex(int(a)) for a in got.reshape(-1)]} != {[hex(int(a)) for a in want.reshape(-1)]}"
+        with pytest.raises(ddgi.LuxError):
+            pipe.sdf_shadow(abi.make_light(g["shadow_light_point"]), g["shadow_view_proj_inv"], 0, 0.1, g["shadow_depth"][:6], g["shadow_normal"][:6], g["sobol"], g["scrambling"])
+        pipe.close()
+    # (b)
+    sc = scenes.cornell_scene(res=32, counts=(2, 2, 2), rays=32, atlas_res=256, cascades=2, with_atlas=False)
+    pipe = ddgi.DDGIPipeline(sc.uniform)
+    pipe.set_global_sdf(sc.sdf_data, sc.sdf, sc.mip)
+    w, h = 160, 96
+    vpi, depth, nrm, _, sobol, scr = _screen_inputs(w, h, 43)
+    bits = 0
+    for name in gs.LIGHTS:
+        light = abi.make_light(g[f"shadow_light_{name}"])
+        want = np.full((h // 4, w // 8), 0xDEADBEEF, dtype=np.uint32)
+        oracle.sdf_shadow(sc.sdf_data, sc.sdf, sc.mip, light, vpi, 7, 0.05, depth, nrm, sobol, scr, want)
+        got = pipe.sdf_shadow(light, vpi, 7, 0.05, depth, nrm, sobol, scr, out=np.full((h // 4, w // 8), 0xDEADBEEF, dtype=np.uint32))
+        assert np.array_equal(got, want), f"{name}: {(got != want).sum()} of {want.size} words differ from the oracle"
+        assert want[0, 0] == 0xDEADBEEF  # pixel (0, 0) is sky
+        bits += sum(bin(int(v)).count("1") for v in want.reshape(-1) if v != 0xDEADBEEF)
+    assert 500 < bits < 0.9 * 3 * w * h
+    pipe.close()

@@ -179,3 +179,79 @@ def test_surface_direct_light_matches_shipped_spirv(oracle):
         assert np.array_equal(cache, want), f"{name}: {(cache != want).sum()} of {cache.size} fp16 values differ"
         lit += int((gold[f"out_{name}"][:, :3].sum(1) > 0).sum())
     assert lit > 60  # the three lights really shade something
+
+
+@pytest.mark.parametrize("k", [2, 4])
+def test_cascaded_trace_matches_shipped_spirv(oracle, k):
+    """The cascaded global SDF (the reference always runs 2 cascades): GISDFRays.comp.spv executed on the Cornell scene with 2 and 4 nested,
+    off-centre cascades laid side by side in one volume (tests/golden/make_spirv_golden_cascades.py).  Ray buffers and tap counts of the
+    oracle equal the shipped binary's bit for bit: cascade entry from outside, the hand-over to the next cascade, per-cascade voxel sizes in
+    the thickness test, the hit bias and the surface threshold, and the filter bleed across cascade seams in x."""
+    import zlib
+
+    from tests.golden import make_spirv_golden_cascades as g
+
+    gold = np.load(os.path.join(os.path.dirname(PATH), "spirv_golden_cascades.npz"))
+    sc = g.golden_scene(k)
+    assert np.uint32(zlib.crc32(sc.sdf.numpy().tobytes() + sc.mip.numpy().tobytes())) == gold[f"c{k}_crc"], "the procedural scene changed: regenerate the fixture"
+    rad, dd, _, cn = oracle.OracleScene(sc).trace(gold[f"c{k}_rotation"])
+    assert np.array_equal(dd, gold[f"c{k}_direction_distance"]), f"{(dd != gold[f'c{k}_direction_distance']).sum()} direction / distance values differ"
+    assert np.array_equal(rad, gold[f"c{k}_radiance"]), f"{(rad != gold[f'c{k}_radiance']).sum()} radiance values differ"
+    assert cn["texTaps"] == int(gold[f"c{k}_tex_taps"]) and cn["mipTaps"] == int(gold[f"c{k}_mip_taps"])
+    # the fixture really crosses cascades: rays from the same origins hit in every cascade
+    u = sc.uniform
+    tr = np.zeros(abi.probe_count(u) * u.raysPerProbe, dtype=abi.SDF_TRACE_DTYPE)
+    d = dd.view(np.float16)[..., :3].astype(np.float32).reshape(-1, 3)
+    tr["worldDirection"] = d / np.linalg.norm(d, axis=1, keepdims=True)
+    ids = np.repeat(np.arange(abi.probe_count(u)), u.raysPerProbe)
+    grid = np.stack([ids % u.probeCounts[0], (ids // u.probeCounts[0]) % u.probeCounts[1], ids // (u.probeCounts[0] * u.probeCounts[1])], -1)
+    tr["worldPosition"] = (np.float32(list(u.startPosition)[:3]) + grid.astype(np.float32) * np.float32(list(u.step)[:3])).astype(np.float32)
+    tr["maxDistance"], tr["stepScale"] = abi.GLOBAL_SDF_WORLD_SIZE, 1.0
+    hits = oracle.trace_global_sdf(sc.sdf_data, sc.sdf, sc.mip, tr, 0.0)
+    per_cascade = np.bincount(hits["hitCascade"][hits["hitTime"] >= 0], minlength=k)
+    assert (per_cascade > 0).all(), per_cascade
+
+
+def _screen_golden():
+    from tests.golden import make_spirv_golden as base
+
+    g = np.load(os.path.join(os.path.dirname(PATH), "spirv_golden_screen.npz"))
+    sc = base.golden_scene()
+    sc.uniform = abi.DDGIUniform.from_buffer_copy(g["uniform"].tobytes())
+    return g, sc
+
+
+def test_sdf_reflection_matches_shipped_spirv(oracle):
+    """Row f4: the oracle's restatement of SDFReflection.comp (mirror / GGX-sampled / DDGI-approximated branches, reflection ray through the
+    global SDF, surface cache sampled with normal = -R, skybox on a miss, blue-noise sampler) against the RGBA16F image written by the shipped
+    binary (tests/golden/make_spirv_golden_screen.py), bit for bit, with approximateWithDDGI on and off; depth == 1 pixels stay untouched."""
+    g, sc = _screen_golden()
+    for approx in (1, 0):
+        frames, trim, inten = g[f"refl_params_{approx}"]
+        push = abi.make_reflection_push(g["refl_camera"], g["refl_view_proj_inv"], int(frames), trim, inten, approx)
+        out = np.full(g[f"refl_out_{approx}"].shape, 0x3555, dtype=np.uint16)
+        oracle.sdf_reflection(sc, g["irradiance"], g["depth_atlas"], push, g["refl_depth"], g["refl_normal"], g["refl_pbr"], g["sobol"], g["scrambling"], out)
+        want = g[f"refl_out_{approx}"]
+        assert np.array_equal(out, want), f"approximateWithDDGI={approx}: {(out != want).any(-1).sum()} of {out.shape[0] * out.shape[1]} pixels differ"
+        assert (want[..., 0] == 0x3555).sum() == 3 and (want.view(np.float16)[..., :3].astype(np.float32).sum(-1) > 0).sum() > 150
+    assert not np.array_equal(g["refl_out_0"], g["refl_out_1"])  # the DDGI branch really ran
+
+
+def test_sdf_shadow_matches_shipped_spirv(oracle):
+    """Row f4: the oracle's restatement of SDFShadow.comp (soft-shadow disk sample from the blue noise, shadow ray with start bias 0, one
+    visibility bit per pixel of an 8x4 workgroup) against the R32UI words written by the shipped binary for a directional, a point and a spot
+    light; the workgroup whose first pixel is sky keeps its previous word."""
+    from tests.golden import make_spirv_golden_screen as gs
+
+    g, sc = _screen_golden()
+    h, w = g["shadow_depth"].shape
+    seen = 0
+    for name in gs.LIGHTS:
+        out = np.full((h // 4, w // 8), 0xDEADBEEF, dtype=np.uint32)
+        oracle.sdf_shadow(sc.sdf_data, sc.sdf, sc.mip, oracle.make_light(g[f"shadow_light_{name}"]), g["shadow_view_proj_inv"], int(g["shadow_frames"]),
+                          float(g["shadow_bias"]), g["shadow_depth"], g["shadow_normal"], g["sobol"], g["scrambling"], out)
+        want = g[f"shadow_out_{name}"]
+        assert np.array_equal(out, want), f"{name}: {[hex(int(a)) for a in out.reshape(-1)]} != {[hex(int(a)) for a in want.reshape(-1)]}"
+        assert want[0, 0] == 0xDEADBEEF
+        seen += sum(bin(int(v)).count("1") for v in want.reshape(-1)[1:])
+    assert seen > 40  # visible and shadowed pixels both occur
