@@ -3,6 +3,8 @@
 north_star tolerances: hit distances within 1e-3 scene units, atlas texels within 1e-3 relative / 1e-4 absolute.
 Under the numerics contract the engine is expected to be BIT-IDENTICAL to the oracle; the tests assert
 the stated tolerances and additionally require that at most a handful of fp16 values differ at all."""
+import os
+
 import numpy as np
 import pytest
 
