@@ -243,6 +243,7 @@ def run_lux(args):
         pipe.set_nccl_comm(comm.ptr)
     st = pipe.state()
     P, R = sc.probes, u.raysPerProbe
+    l2_gbs = pipe.measure_l2_read_bandwidth() if rank == 0 else None  # denominator of the request-level roofline; ~0.1 s, outside every timed region
     rot_cache = {}
 
     def rot_of(f):
@@ -464,6 +465,18 @@ def run_lux(args):
                                     "sample": f"{r['sample_probes']} stratified probes x {R} rays, 1 update (trace + literal blend + border), "
                                               f"{r['sec_per_step']:.1f} s; trace share {r['trace_frac']:.2f}",
                                     "counters_per_ray": {k: v / r["rays"] for k, v in r["counters"].items()}}
+        if "cpu_baseline" in line and l2_gbs:
+            # request-level (L2) roofline of the trace, SURVEY §8d B_trace_req: 16 B per trilinear tap (8 fp16 texels; the oracle's tap counters on
+            # the stratified sample, normal taps included), 16 B of ray-record stores per ray, 112 B per surface-cache tile sample (one depth gather
+            # + three colour gathers); scaled from the sample to this rank's rays
+            cpr = line["cpu_baseline"]["counters_per_ray"]
+            req = probes_rank * R * (16.0 * (cpr["mipTaps"] + cpr["texTaps"]) + 16.0 + 112.0 * cpr["tileSamples"])
+            a = req / (trace_launch_ms * 1e-3) / 1e9
+            t_hbm, t_l2 = stages_b["trace"] / (hbm * 1e9), req / (l2_gbs * 1e9)
+            line["roofline_l2"] = {"bound": "l2", "kernel": "trace_stage", "achieved": a, "peak": l2_gbs, "unit": "GB/s", "frac": a / l2_gbs,
+                                   "request_bytes_per_launch": req, "ms_per_launch": trace_launch_ms,
+                                   "peak_source": "measured live before the timed region: lux_ddgi_measure_l2_read_bandwidth (64 MiB read-only sweep by every SM, best of 5)",
+                                   "floor_ms": {"hbm": t_hbm * 1e3, "l2": t_l2 * 1e3}, "binding": "l2" if t_l2 > t_hbm else "hbm"}
         print(json.dumps(line), flush=True)
     pipe.close()
     if world > 1:

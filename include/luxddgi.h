@@ -410,6 +410,11 @@ LUX_API int lux_ddgi_sample_irradiance(LuxDDGIContext* ctx, int32_t count, const
 LUX_API int lux_ddgi_sample_probe(LuxDDGIContext* ctx, int32_t width, int32_t height, const float* depthD32F, const float* normalsRGBA32F,
                                   const float cameraPosition[4], const float viewProjInv[16], float* outRGBA32F, LuxMemKind kind);
 
+/* Measurement aid (the L2 bandwidth the request-level roofline of the trace is quoted against is measured, not assumed): read-only
+ * sweeps of a `bytes`-sized device buffer (rounded down to a multiple of 16 KiB; default 64 MiB when 0) that fits in L2, every SM reading the
+ * whole buffer, timed with CUDA events on the context's stream; best of `repeats` (>= 1) launches after one warm-up.  *gbPerSecond = bytes read / s / 1e9. */
+LUX_API int lux_ddgi_measure_l2_read_bandwidth(LuxDDGIContext* ctx, size_t bytes, int32_t repeats, float* gbPerSecond);
+
 /* ---- the other tracyGlobalSDF users: screen-space passes over a width x height G-buffer ----
  * Blue-noise inputs (Raytraced/BlueNoise.glsl:8-19): `sobolRGBA8` = the 256 x 1 RGBA8 texels of textures/blue_noise/sobol_256_4d.png,
  * `scramblingRankingRGBA8` = the 128 x 128 RGBA8 texels of scrambling_ranking_128x128_2d_1spp.png (Engine/Noise/BlueNoise.h:15-26); a texel

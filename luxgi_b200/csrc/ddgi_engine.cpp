@@ -2098,6 +2098,49 @@ int lux_ddgi_trace_global_sdf(LuxDDGIContext* c, int32_t count, const LuxGlobalS
     return LUX_OK;
 }
 
+int lux_ddgi_measure_l2_read_bandwidth(LuxDDGIContext* c, size_t bytes, int32_t repeats, float* gbPerSecond)
+{
+    CHECK_CTX(c);
+    if (!gbPerSecond || repeats < 1)
+        return fail(LUX_ERR_INVALID_ARG, "bad measure_l2_read_bandwidth arguments");
+    if (bytes == 0)
+        bytes = (size_t)64 << 20;
+    bytes &= ~(size_t)16383;
+    if (bytes == 0 || bytes > ((size_t)1 << 32))
+        return fail(LUX_ERR_INVALID_ARG, "measure_l2_read_bandwidth: buffer size out of range");
+    int sms = 0, dev = 0;
+    LUX_CUDA(cudaGetDevice(&dev));
+    LUX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int blocks = sms * 8; // 8 resident blocks of 256 threads per SM
+    void*     buf    = nullptr;
+    LUX_CUDA(cudaMalloc(&buf, bytes + 16));
+    cudaError_t e = cudaMemsetAsync(buf, 0, bytes + 16, c->stream);
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (e == cudaSuccess) e = cudaEventCreate(&e0);
+    if (e == cudaSuccess) e = cudaEventCreate(&e1);
+    float best = 0.0f;
+    for (int r = 0; e == cudaSuccess && r <= repeats; r++) // r = 0 warms the L2
+    {
+        cudaEventRecord(e0, c->stream);
+        lux::launch_l2_sweep(buf, bytes, blocks, (uint32_t*)((char*)buf + bytes), c->stream);
+        cudaEventRecord(e1, c->stream);
+        e = cudaEventSynchronize(e1);
+        float ms = 0.0f;
+        if (e == cudaSuccess)
+            e = cudaEventElapsedTime(&ms, e0, e1);
+        if (e == cudaSuccess && r > 0 && ms > 0.0f)
+            best = std::fmax(best, (float)((double)bytes * blocks / (ms * 1e-3) / 1e9));
+    }
+    c->launches += repeats + 1;
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    cudaFree(buf);
+    if (e != cudaSuccess)
+        return fail(LUX_ERR_CUDA, "measure_l2_read_bandwidth: %s", cudaGetErrorString(e));
+    *gbPerSecond = best;
+    return LUX_OK;
+}
+
 int lux_ddgi_get_stage_ms(LuxDDGIContext* c, LuxStageTimes* out)
 {
     CHECK_CTX(c);

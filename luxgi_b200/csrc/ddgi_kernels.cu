@@ -2952,6 +2952,31 @@ void launch_sdf_shadow(const TraceParams& p, bool useTextures, const LuxLight& l
         sdf_shadow_kernel<false><<<(groups + 3) / 4, 128, 0, s>>>(p, a);
 }
 
+// L2 read bandwidth (the denominator of the request-level roofline): every block sweeps the whole buffer once, from a
+// block-dependent start so that the SMs are spread over the buffer at any moment, with ld.global.cg (no L1 allocation) and four independent
+// 16-byte loads in flight per thread.  After the first touch every line is an L2 hit as long as the buffer fits in L2.
+__global__ void __launch_bounds__(256) l2_sweep_kernel(const uint4* __restrict__ buf, unsigned int n16, uint32_t* __restrict__ sink)
+{
+    const unsigned int start = (unsigned int)(((unsigned long long)blockIdx.x * n16) / gridDim.x) & ~1023u;
+    uint32_t acc = 0;
+    for (unsigned int base = 0; base < n16; base += 1024)
+    {
+        unsigned int i = start + base + threadIdx.x;
+        if (i >= n16)
+            i -= n16;
+        // n16 is a multiple of 1024, so the four loads of one thread stay inside [0, n16)
+        uint4 a = __ldcg(buf + i), b = __ldcg(buf + i + 256), c = __ldcg(buf + i + 512), d = __ldcg(buf + i + 768);
+        acc ^= a.x ^ b.y ^ c.z ^ d.w;
+    }
+    if (acc == 0x9e3779b9u) // never true for the zero-filled buffer; keeps the loads alive
+        sink[0] = acc;
+}
+
+void launch_l2_sweep(const void* buf, size_t bytes, int blocks, uint32_t* sink, cudaStream_t s)
+{
+    l2_sweep_kernel<<<blocks, 256, 0, s>>>((const uint4*)buf, (unsigned int)(bytes / 16), sink);
+}
+
 void launch_direct_light(const TraceParams& p, bool useTextures, const LuxLight& l, const float* cameraPosBias, void* light, int count,
                          const uint32_t* texel, const float* P, const float* N, const float* albedo, const float* metallicRoughness, cudaStream_t s)
 {

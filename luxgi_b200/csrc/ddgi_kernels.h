@@ -129,6 +129,9 @@ void launch_sdf_shadow(const TraceParams& p, bool useTextures, const LuxLight& l
                        int width, int height, const float* gDepth, const float* gNormal, const uint32_t* sobol, const uint32_t* scr, uint32_t* out,
                        cudaStream_t s);
 
+// measurement aid: one sweep of `bytes` (multiple of 16 KiB) by each of `blocks` blocks through L2
+void launch_l2_sweep(const void* buf, size_t bytes, int blocks, uint32_t* sink, cudaStream_t s);
+
 // ---- global SDF build ----
 struct SdfMeshRecord // device copy of LuxMeshSDF without the host pointers
 {

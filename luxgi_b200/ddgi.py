@@ -27,7 +27,7 @@ EXPORTS = [
     "lux_ddgi_get_stage_ms", "lux_ddgi_sample_irradiance", "lux_ddgi_sample_probe", "lux_ddgi_indirect_light",
     "lux_ddgi_get_surface_light_cache", "lux_ddgi_build_global_sdf", "lux_ddgi_build_sdf_mip", "lux_ddgi_sdf_file_read", "lux_ddgi_download_fence", "lux_ddgi_wait_fence", "lux_ddgi_set_nccl_comm", "lux_ddgi_update_surface_light_cache_rows", "lux_ddgi_cull_surface_objects",
     "lux_ddgi_get_surface_cull_lists", "lux_ddgi_trace_global_sdf", "lux_ddgi_surface_direct_light",
-    "lux_ddgi_sdf_reflection", "lux_ddgi_sdf_shadow",
+    "lux_ddgi_sdf_reflection", "lux_ddgi_sdf_shadow", "lux_ddgi_measure_l2_read_bandwidth",
 ]
 
 
@@ -79,6 +79,7 @@ def load():
         "lux_ddgi_indirect_light": [vp, vp, i32, vp, vp, vp, vp, vp, C.c_float, vp, i32],
         "lux_ddgi_get_surface_light_cache": [vp, C.POINTER(vp), C.POINTER(sz)],
         "lux_ddgi_surface_direct_light": [vp, C.POINTER(abi.Light), vp, i32, vp, vp, vp, vp, vp, i32],
+        "lux_ddgi_measure_l2_read_bandwidth": [vp, sz, i32, C.POINTER(C.c_float)],
         "lux_ddgi_sdf_reflection": [vp, C.POINTER(abi.ReflectionPushConstants), i32, i32, vp, vp, vp, vp, vp, vp, i32],
         "lux_ddgi_sdf_shadow": [vp, C.POINTER(abi.Light), vp, C.c_uint32, C.c_float, i32, i32, vp, vp, vp, vp, vp, i32],
         "lux_ddgi_build_global_sdf": [vp, C.POINTER(abi.GlobalSDFData), C.POINTER(abi.MeshSDF), i32, C.c_float],
@@ -447,6 +448,12 @@ class DDGIPipeline:
         _check(self._lib.lux_ddgi_sdf_shadow(self._h, C.byref(light), _host_ptr(vpi), int(num_frames), float(shadow_bias), w, h, _host_ptr(depth),
                                              _host_ptr(normals), _host_ptr(sobol), _host_ptr(scrambling), _host_ptr(out), abi.MEM_HOST))
         return out
+
+    def measure_l2_read_bandwidth(self, nbytes=0, repeats=5) -> float:
+        """GB/s of read-only sweeps of an L2-resident buffer (default 64 MiB): the denominator of the request-level roofline."""
+        out = C.c_float()
+        _check(self._lib.lux_ddgi_measure_l2_read_bandwidth(self._h, int(nbytes), int(repeats), C.byref(out)))
+        return float(out.value)
 
     def surface_light_cache(self) -> np.ndarray:
         p, n = C.c_void_p(), C.c_size_t()

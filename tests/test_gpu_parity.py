@@ -708,3 +708,17 @@ def test_sdf_shadow_matches_shipped_spirv_and_oracle(oracle):
         bits += sum(bin(int(v)).count("1") for v in want.reshape(-1) if v != 0xDEADBEEF)
     assert 500 < bits < 0.9 * 3 * w * h
     pipe.close()
+
+
+def test_l2_bandwidth_measurement():
+    """lux_ddgi_measure_l2_read_bandwidth (the denominator of bench.py's request-level roofline): an L2-resident sweep must come out above the
+    HBM copy bandwidth of MEASURED_PEAKS.json and below anything physical; a 1 GiB sweep (larger than L2) must be slower than the 64 MiB one."""
+    sc = scenes.cornell_scene(res=32, counts=(2, 2, 2), rays=32, atlas_res=256, with_atlas=False)
+    pipe = ddgi.DDGIPipeline(sc.uniform)
+    l2 = pipe.measure_l2_read_bandwidth()
+    big = pipe.measure_l2_read_bandwidth(1 << 30, repeats=2)
+    print("L2 read sweep GB/s:", l2, " 1 GiB sweep GB/s:", big)
+    assert 3000.0 < l2 < 100000.0 and big < l2
+    with pytest.raises(ddgi.LuxError):
+        pipe.measure_l2_read_bandwidth(repeats=0)
+    pipe.close()
