@@ -456,6 +456,7 @@ LUX_API int lux_ddgi_sdf_shadow(LuxDDGIContext* ctx, const LuxLight* light, cons
 /* Infinite-bounce feedback: surface::indirect_light::system (GlobalSurfaceAtlas.cpp:1004-1085) =
  * Shaders/SDF/SDFAtlasIndirectLight.frag:44-67, additive into the RGBA16F light cache.  For each listed atlas texel t:
  *   light[t].rgb = fp16( base[t].rgb + intensity * (min(albedo,0.9) - min(albedo,0.9)*metallic)/PI * sampleIrradiance(P, N, normalize(cameraPos-P)) )
+ *   light[t].a   = fp16( base[t].a + 1 )   (the shader writes alpha 1 and the pass blends ONE + ONE on alpha as well, RHI/Vulkan/VulkanPipeline.cpp:160-165)
  * `baseLightRGBA16F` (full atlas; emissive + direct light, i.e. the cache after CopyEmissive + SDFDeferredLight) may be NULL to
  * add onto the current contents.  The rasterisation of tiles into texel lists stays with the caller. */
 LUX_API int lux_ddgi_indirect_light(LuxDDGIContext* ctx, const void* baseLightRGBA16F, int32_t count, const uint32_t* texelIndex,

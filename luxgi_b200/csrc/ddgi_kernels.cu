@@ -2272,7 +2272,8 @@ __global__ void indirect_light_kernel(const __grid_constant__ LuxDDGIUniform ddg
         outv[c]       = dv[c] + (intensity * diffuse) * Ev[c];
     }
     uint32_t h0 = f2h_bits(outv[0]), h1 = f2h_bits(outv[1]), h2 = f2h_bits(outv[2]);
-    light[idx] = make_uint2(h0 | (h1 << 16), h2 | (b.y & 0xffff0000u));
+    uint32_t h3 = f2h_bits(dst.w + 1.0f); // the shader writes alpha 1 and the pass blends ONE + ONE on alpha too (VulkanPipeline.cpp:160-165)
+    light[idx] = make_uint2(h0 | (h1 << 16), h2 | (h3 << 16));
 }
 
 // SDFDeferredLight.frag:44-129 (fetchLight for directional / point / spot lights, shadow ray through the global SDF with start bias 2,

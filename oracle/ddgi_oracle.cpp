@@ -1196,8 +1196,7 @@ int oracle_indirect_light(const LuxDDGIUniform* ddgi, const uint16_t* irr, const
             float dst     = h2f(base ? base[o + c] : light[o + c]);
             light[o + c]  = f2h(dst + out);
         }
-        if (base)
-            light[o + 3] = base[o + 3];
+        light[o + 3] = f2h(h2f(base ? base[o + 3] : light[o + 3]) + 1.0f); // the shader writes alpha 1 and the pass blends ONE + ONE on alpha too (VulkanPipeline.cpp:160-165)
     }
     return 0;
 }

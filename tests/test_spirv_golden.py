@@ -255,3 +255,27 @@ def test_sdf_shadow_matches_shipped_spirv(oracle):
         assert want[0, 0] == 0xDEADBEEF
         seen += sum(bin(int(v)).count("1") for v in want.reshape(-1)[1:])
     assert seen > 40  # visible and shadowed pixels both occur
+
+
+def test_indirect_light_matches_shipped_spirv(oracle):
+    """Row f1: the oracle's restatement of SDFAtlasIndirectLight.frag (min(albedo, 0.9), (albedo - albedo * metallic) / PI, intensity * diffuse *
+    sampleIrradiance) against the shipped binary executed per fragment (tests/golden/make_spirv_golden_indirectlight.py): what the additive pass
+    leaves in an empty RGBA16F light cache equals fp16(outColor) bit for bit, alpha included; a second pass on top adds again."""
+    g = np.load(os.path.join(os.path.dirname(PATH), "spirv_golden_indirectlight.npz"))
+    u = abi.DDGIUniform.from_buffer_copy(g["uniform"].tobytes())
+    n = len(g["pos"])
+    normals = oracle.octohedral_to_direction(g["oct_normal"])
+    texel = np.arange(n, dtype=np.uint32)
+    cache = np.zeros((n, 4), dtype=np.uint16)
+    cam = g["camera"]
+    oracle.indirect_light(u, g["irradiance"], g["depth_atlas"], cache, None, texel, g["pos"], normals, g["albedo"], g["metallic"], float(cam[3]), cam[:3])
+    want = g["out"].astype(np.float16).view(np.uint16)
+    assert np.array_equal(cache, want), f"{(cache != want).sum()} of {cache.size} fp16 values differ"
+    assert (g["out"][:, :3].sum(1) > 0).sum() > 150 and (g["albedo"] > 0.9).any()
+    # with a base atlas: listed texels = base + indirect (alpha = base alpha + 1)
+    base = np.random.default_rng(1).uniform(0, 2, (n, 4)).astype(np.float16)
+    cache2 = np.zeros((n, 4), dtype=np.uint16)
+    oracle.indirect_light(u, g["irradiance"], g["depth_atlas"], cache2, base.view(np.uint16), texel, g["pos"], normals, g["albedo"], g["metallic"], float(cam[3]), cam[:3])
+    want2 = (base.astype(np.float32) + g["out"].astype(np.float32)).astype(np.float16)
+    d = np.abs(cache2.view(np.float16).astype(np.float32) - want2.astype(np.float32))
+    assert (d <= 2e-3 * np.abs(want2.astype(np.float32)) + 1e-6).all()  # one fp32 add then one fp16 rounding, against fp16(out) added in fp32
