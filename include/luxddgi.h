@@ -186,7 +186,7 @@ typedef struct LuxGlobalSDFHit {
 } LuxGlobalSDFHit;
 
 /* ---------------------------------------------------------------------------------------------------------
- * Light, 64 bytes (Shaders/Common/Light.glsl:19-29), as SDFDeferredLight.frag's UniformBufferObject carries it (row f4).
+ * Light, 64 bytes (Shaders/Common/Light.glsl:19-29; host twin Scene/Component/Light.h:21-33 LightData), as SDFDeferredLight.frag's UniformBufferObject carries it (row f4).
  * type: 0 directional, 1 spot, 2 point (Light.glsl:13-17).  direction.w is the soft-shadow radius (unused by the surface-cache pass).
  * ------------------------------------------------------------------------------------------------------ */
 #define LUX_LIGHT_DIRECTIONAL 0.0f
