@@ -279,3 +279,22 @@ def test_indirect_light_matches_shipped_spirv(oracle):
     want2 = (base.astype(np.float32) + g["out"].astype(np.float32)).astype(np.float16)
     d = np.abs(cache2.view(np.float16).astype(np.float32) - want2.astype(np.float32))
     assert (d <= 2e-3 * np.abs(want2.astype(np.float32)) + 1e-6).all()  # one fp32 add then one fp16 rounding, against fp16(out) added in fp32
+
+
+def test_open_scene_trace_matches_shipped_spirv(oracle):
+    """The miss / sky path of GISDFRays.comp.spv: a reduced open city under a 4x4-texel cube sky (71 % of the rays leave the cascade and take
+    a bilinear sky texel; long open-space steps take the `stepDistance = chunkSizeDistance` branch; hits see emissive window bands).  Ray
+    buffers and tap counts of the oracle equal the shipped binary's bit for bit."""
+    import zlib
+
+    from tests.golden import make_spirv_golden_cascades as g
+
+    gold = np.load(os.path.join(os.path.dirname(PATH), "spirv_golden_cascades.npz"))
+    sc = g.open_scene()
+    assert np.uint32(zlib.crc32(sc.sdf.numpy().tobytes() + sc.mip.numpy().tobytes())) == gold["open_crc"], "the procedural scene changed: regenerate the fixture"
+    assert np.uint32(zlib.crc32(sc.light.numpy().tobytes() + sc.depth.numpy().tobytes())) == gold["open_light_crc"], "the procedural surface cache changed"
+    rad, dd, _, cn = oracle.OracleScene(sc).trace(gold["open_rotation"])
+    assert np.array_equal(dd, gold["open_direction_distance"]) and np.array_equal(rad, gold["open_radiance"])
+    assert cn["texTaps"] == int(gold["open_tex_taps"]) and cn["mipTaps"] == int(gold["open_mip_taps"])
+    miss = dd.view(np.float16)[..., 3] >= 60000
+    assert 0.5 < miss.mean() < 0.9 and len(np.unique(rad[miss][:, :3], axis=0)) > 20  # distinct bilinear sky values (every probe shares the 32 directions)
