@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libluxddgi.so")
 SOURCES = ["ddgi_kernels.cu", "ddgi_engine.cpp"]
-HEADERS = ["ddgi_kernels.h", "ddgi_math.cuh", os.path.join("..", "..", "include", "luxddgi.h")]
+HEADERS = ["ddgi_kernels.h", "ddgi_math.cuh", "march_kernel.inc", os.path.join("..", "..", "include", "luxddgi.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -36,17 +36,36 @@ def needs_build():
     return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
 
 
+LIB_EXPERIMENTAL = os.path.join(HERE, "libluxddgi_experimental.so")
+
+
+def build_experimental(verbose=False):
+    """The same library with the opt-in kernels compiled in (-DLUX_EXPERIMENTAL_OPEN_SKIP), next to the measured build; load it with
+    LUX_DDGI_LIB=<path>.  Kept apart because a second instantiation of the march perturbs ptxas' code for the shipped kernel."""
+    global LIB
+    shipped, LIB = LIB, LIB_EXPERIMENTAL
+    os.environ["LUX_BUILD_EXPERIMENTAL"] = "1"
+    try:
+        return build(force=True, verbose=verbose)
+    finally:
+        LIB = shipped
+        del os.environ["LUX_BUILD_EXPERIMENTAL"]
+
+
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
     env = dict(os.environ)
     env.pop("CXX", None)  # the image exports a g++ wrapper nvcc does not need
     env.pop("CC", None)
-    cmd = [nvcc(), "-shared", "-o", LIB] + NVCC_FLAGS + ["-x", "cu"] + [os.path.join(CSRC, f) for f in SOURCES]
+    flags = list(NVCC_FLAGS)
+    if os.environ.get("LUX_BUILD_EXPERIMENTAL"):  # opt-in kernels that are not part of the measured build (LUX_DDGI_FLAG_OPEN_SKIP)
+        flags += ["-DLUX_EXPERIMENTAL_OPEN_SKIP"]
+    cmd = [nvcc(), "-shared", "-o", LIB] + flags + ["-x", "cu"] + [os.path.join(CSRC, f) for f in SOURCES]
     cmd += ["-ccbin", "/usr/bin/g++"] if os.path.exists("/usr/bin/g++") else []
     res = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     log = res.stdout
-    with open(os.path.join(HERE, "build.log"), "w") as f:
+    with open(os.path.join(HERE, "build.log" if LIB != LIB_EXPERIMENTAL else "build_experimental.log"), "w") as f:
         f.write(" ".join(cmd) + "\n" + log)
     if res.returncode != 0:
         sys.stderr.write(log)
@@ -57,4 +76,7 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True))
+    if "--experimental" in sys.argv:
+        print(build_experimental(verbose=True))
+    else:
+        print(build(force="--force" in sys.argv, verbose=True))

@@ -104,6 +104,8 @@ struct LuxDDGIContext
     bool             hasSdf = false;
     LuxGlobalSDFData sdfData{};
     DeviceBuffer     sdf, mip;
+    DeviceBuffer     openBits;          // LUX_DDGI_FLAG_OPEN_SKIP: open-space table of the mip volume, rebuilt lazily when the volume changes
+    bool             openDirty = true;
     cudaArray_t         sdfArray = nullptr, mipArray = nullptr;
     cudaTextureObject_t sdfTex = 0, mipTex = 0;
 
@@ -410,6 +412,22 @@ static int setup(LuxDDGIContext& c, const LuxTracePushConstants& push)
         LUX_CUDA(cudaGetLastError());
         c.masksDirty = false;
     }
+    if ((c.flags & LUX_DDGI_FLAG_OPEN_SKIP) && !(c.flags & LUX_DDGI_FLAG_TRACE_SIMPLE) && c.openDirty)
+    { // open-space table of the mip volume (experimental march variant); volumes whose mip side is not a multiple of 4 run without it
+        const int mres = (int)c.sdfData.resolution / 4, mw = mres * (int)c.sdfData.cascadesCount;
+        c.openBits.release();
+        if (mres >= 4 && mres % 4 == 0)
+        {
+            const size_t cells = (size_t)(mw / 4) * (mres / 4) * (mres / 4), bytes = ((cells + 31) / 32) * 4;
+            LUX_CUDA(cudaMalloc(&c.openBits.ptr, bytes));
+            c.openBits.bytes = bytes;
+            const float chunkSizeDistance = (float)LUX_GLOBAL_SDF_RASTERIZE_CHUNK_SIZE / c.sdfData.resolution;
+            lux::launch_open_table(c.mip.ptr, mw, mres, mres, chunkSizeDistance * (1.0f + 0.0009765625f), (uint32_t*)c.openBits.ptr, c.stream);
+            c.launches += 1;
+            LUX_CUDA(cudaGetLastError());
+        }
+        c.openDirty = false;
+    }
     mark(c, 0);
     launch_ray_dirs(push.randomOrientation, u.raysPerProbe, (float4*)c.dirs.ptr, (uint2*)c.dirsHalf.ptr, c.stream);
     c.launches += 1;
@@ -453,6 +471,9 @@ static int launchBatch(LuxDDGIContext& c, const LuxDDGIContext::Batch& b, int ba
     const size_t rayStart = (size_t)b.probeStart * u.raysPerProbe;
     p.skyFace  = c.skyFace;
     p.sky      = (const uint2*)c.sky.ptr;
+    OpenTableArgs open{};
+    if ((c.flags & LUX_DDGI_FLAG_OPEN_SKIP) && c.openBits.ptr)
+        open = OpenTableArgs{(const uint32_t*)c.openBits.ptr, p.mipRes * p.cascades / 4, p.mipRes / 4, p.mipRes / 4};
     p.dirs     = (const float4*)c.dirs.ptr;
     p.radiance = (uint2*)c.radiance.ptr + rayStart;
     p.dirDist  = (uint2*)c.directionDepth.ptr + rayStart;
@@ -471,7 +492,7 @@ static int launchBatch(LuxDDGIContext& c, const LuxDDGIContext::Batch& b, int ba
     }
     const int variant = (c.flags & LUX_DDGI_FLAG_TRACE_SIMPLE) ? 0 : (c.sdfTex ? 2 : 1);
     c.launches += launch_trace(p, variant, counters, s, c.lightPending ? c.evLightReady : nullptr,
-                               (timers && (c.flags & LUX_DDGI_FLAG_STAGE_TIMERS)) ? c.ev[5] : nullptr);
+                               (timers && (c.flags & LUX_DDGI_FLAG_STAGE_TIMERS)) ? c.ev[5] : nullptr, open.bits ? &open : nullptr);
     return LUX_OK;
 }
 
@@ -687,6 +708,8 @@ int lux_ddgi_create(const LuxDDGIUniform* uniform, const LuxDDGICreateInfo* info
     if (prop.major != 10)
         return fail(LUX_ERR_NO_DEVICE, "device %d is sm_%d%d; this build contains sm_100a code only", ci.device, prop.major, prop.minor);
     LUX_CUDA(cudaSetDevice(ci.device));
+    if ((ci.flags & LUX_DDGI_FLAG_OPEN_SKIP) && !lux::open_skip_compiled())
+        return fail(LUX_ERR_UNSUPPORTED, "LUX_DDGI_FLAG_OPEN_SKIP needs a library built with -DLUX_EXPERIMENTAL_OPEN_SKIP (LUX_BUILD_EXPERIMENTAL=1 python -m luxgi_b200.build --force)");
 
     LuxDDGIContext* c = new (std::nothrow) LuxDDGIContext();
     if (!c)
@@ -822,6 +845,7 @@ static int bindSdfTextures(LuxDDGIContext* c, const LuxGlobalSDFData* data)
     c->sdfData    = *data;
     c->hasSdf     = true;
     c->masksDirty = true;
+    c->openDirty  = true;
     return LUX_OK;
 }
 

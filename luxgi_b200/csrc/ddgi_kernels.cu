@@ -1062,196 +1062,16 @@ constexpr int MARCH_REFILL_MIN  = 8;                                       // re
 
 enum RayKind : uint32_t { RAY_MISS = 0, RAY_INSIDE = 1, RAY_HIT = 2 };
 
-template <bool TEX>
-__global__ void __launch_bounds__(32 * MARCH_WARPS, MARCH_BLOCKS_PER_SM) march_kernel(const __grid_constant__ TraceParams P, int numChunks, int rayGroups,
-                                                                    unsigned int* __restrict__ chunkCounter)
-{
-    const int      lane = threadIdx.x & 31;
-    const unsigned FULL = 0xffffffffu;
-    const SdfSampler<TEX> sdf(P);
-    const LuxGlobalSDFData& data = P.sdf;
-
-    const float traceMaxDistance    = gmin(LUX_GLOBAL_SDF_WORLD_SIZE, data.cascadePosDistance[data.cascadesCount - 1][3] * 2.0f);
-    const float chunkSizeDistance   = __fdiv_rn((float)LUX_GLOBAL_SDF_RASTERIZE_CHUNK_SIZE, data.resolution);
-    const float chunkMarginDistance = __fdiv_rn((float)LUX_GLOBAL_SDF_RASTERIZE_CHUNK_MARGIN, data.resolution);
-    const float cascadesCountF      = (float)data.cascadesCount;
-
-    // Per-cascade divisors (cascade extent and voxel size): warp-uniform, so they live in shared memory rather than in six
-    // registers per lane, and their reciprocals are taken once per block instead of once per ray.
-    __shared__ float4 sDiv[LUX_MAX_CASCADES]; // (2*cd, 1/(2*cd) or 0, voxel, 1/voxel or 0): 0 = not a power of two, divide
-    if (threadIdx.x < LUX_MAX_CASCADES)
-    {
-        ExactDivisor m(data.cascadePosDistance[threadIdx.x][3] * 2.0f), v(data.cascadeVoxelSize[threadIdx.x]);
-        sDiv[threadIdx.x] = make_float4(m.d, m.inv, v.d, v.inv);
-    }
-    __syncthreads();
-
-    long long chunkStart = 0;                       // warp-uniform: first ray of the warp's current chunk
-    int  poolOff = MARCH_CHUNK_RAYS;                // next unclaimed ray of the chunk
-    int  poolProbeBase = 0, poolRayBase = 0;        // probe / ray id of the chunk's first ray
-    bool exhausted = false;
-
-    // per-lane ray state
-    bool      active = false, nearSurface = true;
-    long long g = 0;
-    f3        origin = {0, 0, 0}, dir = {0, 0, 0}, traceEnd = {0, 0, 0}, cc = {0, 0, 0};
-    uint32_t  cascade = 0, step = 0, totalSteps = 0;
-    float     stepTime = 0.0f, farT = 0.0f, nextIntersectionStart = 0.0f, cd = 0.0f, voxelSize = 0.0f;
-    const ExactDivisor divCascades(cascadesCountF);
-
-    auto begin_cascade = [&]() {
-        cc        = {data.cascadePosDistance[cascade][0], data.cascadePosDistance[cascade][1], data.cascadePosDistance[cascade][2]};
-        cd        = data.cascadePosDistance[cascade][3];
-        voxelSize = data.cascadeVoxelSize[cascade];
-        f3    worldPosition = origin + dir * (voxelSize * 0.0f); // cascadeTraceStartBias = 0
-        f3    ext = {cd, cd, cd};
-        float nearT, fT;
-        line_hit_aabb(worldPosition, traceEnd, cc - ext, cc + ext, nearT, fT);
-        nearT *= traceMaxDistance;
-        fT *= traceMaxDistance;
-        nearT    = gmax(nearT, nextIntersectionStart);
-        stepTime = nearT;
-        if (nearT >= fT)
-            stepTime = fT;
-        else
-            nextIntersectionStart = fT;
-        farT = fT;
-        step = 0;
-    };
-    auto finish = [&](uint32_t kind, float hitTime, f3 uvw) {
-        P.records[g] = make_float4(hitTime, uvw.x, uvw.y, uvw.z);
-        P.meta[g]    = cascade | (kind << 2) | (totalSteps << 4);
-        active       = false;
-    };
-
-    while (true)
-    {
-        // ---- refill idle lanes, in batches ----
-        unsigned idle = __ballot_sync(FULL, !active);
-        if (idle && (__popc(idle) >= MARCH_REFILL_MIN || idle == FULL) && !exhausted)
-        {
-            if (poolOff >= MARCH_CHUNK_RAYS)
-            { // fetch the next chunk of rays: 8 ray slots x 32 probes of one unit
-                unsigned int c = 0;
-                if (lane == 0)
-                    c = atomicAdd(chunkCounter, 1u);
-                c = __shfl_sync(FULL, c, 0);
-                if ((int)c >= numChunks)
-                    exhausted = true;
-                else
-                {
-                    const unsigned int unit = c / (UNIT_RAYS / MARCH_CHUNK_RAYS), half = c % (UNIT_RAYS / MARCH_CHUNK_RAYS);
-                    chunkStart    = (long long)c * MARCH_CHUNK_RAYS;
-                    poolOff       = 0;
-                    poolProbeBase = (int)(unit / (unsigned)rayGroups) * 32;
-                    poolRayBase   = (int)(unit % (unsigned)rayGroups) * TW_RAYS_PER_UNIT + (int)half * (MARCH_CHUNK_RAYS / 32);
-                }
-            }
-            if (!exhausted)
-            {
-                const int base  = poolOff;
-                const int avail = min(__popc(idle), MARCH_CHUNK_RAYS - poolOff);
-                poolOff += avail;
-                const int rank = __popc(idle & ((1u << lane) - 1u));
-                if (!active && rank < avail)
-                {
-                    const int off        = base + rank;
-                    const int probeLocal = poolProbeBase + (off & 31);
-                    const int rayId      = poolRayBase + (off >> 5);
-                    g = chunkStart + off;
-                    if (probeLocal < P.probeCount && rayId < P.raysPerProbe)
-                    {
-                        float4 o4 = __ldg(P.origins + probeLocal);
-                        float4 d4 = __ldg(P.dirs + rayId);
-                        origin    = {o4.x, o4.y, o4.z};
-                        dir       = {d4.x, d4.y, d4.z};
-                        traceEnd  = origin + dir * traceMaxDistance;
-                        cascade   = 0;
-                        totalSteps = 0;
-                        nextIntersectionStart = 0.0f;
-                        begin_cascade();
-                        nearSurface = true; // probes sit near geometry more often than not
-                        active = true;
-                    }
-                }
-            }
-        }
-        if (!__any_sync(FULL, active))
-        {
-            if (exhausted)
-                break;
-            continue;
-        }
-
-        // ---- one march iteration for every active lane (SDFCommon.glsl:143-190) ----
-        if (active)
-        {
-            if (!(step < LUX_GLOBAL_SDF_MAX_STEPS && stepTime < farT))
-            {
-                totalSteps += step;
-                if (cascade + 1 < data.cascadesCount)
-                {
-                    cascade++;
-                    begin_cascade();
-                }
-                else
-                    finish(RAY_MISS, -1.0f, {0.0f, 0.0f, 0.0f});
-            }
-            else
-            {
-                f3 stepPosition = origin + dir * stepTime;
-                f3 pc           = stepPosition - cc;
-                float cascadeMaxDistance = cd * 2.0f;
-                const float4 dv = sDiv[cascade];
-                f3 cuv;
-                if (dv.y != 0.0f) // power-of-two extent: x * (1/d) is the correctly rounded quotient
-                    cuv = {gclamp(pc.x * dv.y + 0.5f, 0.0f, 1.0f), gclamp(pc.y * dv.y + 0.5f, 0.0f, 1.0f), gclamp(pc.z * dv.y + 0.5f, 0.0f, 1.0f)};
-                else
-                    cuv = {gclamp(__fdiv_rn(pc.x, dv.x) + 0.5f, 0.0f, 1.0f), gclamp(__fdiv_rn(pc.y, dv.x) + 0.5f, 0.0f, 1.0f),
-                           gclamp(__fdiv_rn(pc.z, dv.x) + 0.5f, 0.0f, 1.0f)};
-                f3 uvw = {divCascades.div((float)cascade + cuv.x), cuv.y, cuv.z};
-                // The full-resolution tap is needed on ~87 % of the steps (measured tap counters, C4), and once a ray is near
-                // geometry it stays near: when the PREVIOUS step needed it, both taps are issued together, which removes one
-                // dependent texture round trip per step.  In open space only the mip is read (speculating there pulled the whole
-                // 512^3 volume through L2: 9.8 GB of DRAM traffic per update instead of 1.2 GB, profiles/r1_v5_*).  The value is
-                // only USED under the reference's condition, so results are unchanged.
-                float stepDistance = sdf.sampleMip(uvw.x, uvw.y, uvw.z);
-                float stepDistanceTex = 0.0f;
-                if (nearSurface)
-                    stepDistanceTex = sdf.sampleTex(uvw.x, uvw.y, uvw.z);
-                if (stepDistance < chunkSizeDistance)
-                {
-                    if (!nearSurface)
-                        stepDistanceTex = sdf.sampleTex(uvw.x, uvw.y, uvw.z);
-                    nearSurface = true;
-                    if (stepDistanceTex < chunkMarginDistance * 2.0f)
-                        stepDistance = stepDistanceTex;
-                }
-                else
-                {
-                    nearSurface  = false;
-                    stepDistance = chunkSizeDistance;
-                }
-                stepDistance *= cascadeMaxDistance;
-                float voxelHalf = voxelSize * 0.5f;
-                float minSurfaceThickness = voxelHalf * gclamp(dv.w != 0.0f ? stepTime * dv.w : __fdiv_rn(stepTime, dv.z), 0.0f, 1.0f);
-                if (stepDistance < minSurfaceThickness)
-                {
-                    float hitTime = gmax((stepTime + stepDistance) - minSurfaceThickness, 0.0f);
-                    totalSteps += step;
-                    // probe inside geometry (GISDFRays.comp:93-96) needs neither normal nor surface cache
-                    bool inside = (stepDistance <= 0.0f && hitTime <= data.cascadeVoxelSize[0]);
-                    finish(inside ? RAY_INSIDE : RAY_HIT, hitTime, uvw);
-                }
-                else
-                {
-                    stepTime += gmax(stepDistance * 1.0f, voxelSize);
-                    step++;
-                }
-            }
-        }
-    }
-}
+#define MARCH_OPEN_SKIP 0
+#include "march_kernel.inc"
+#undef MARCH_OPEN_SKIP
+#ifdef LUX_EXPERIMENTAL_OPEN_SKIP // a second instantiation of the march perturbs ptxas' register allocation of the shipped one (1024 -> 1016
+                                  // SASS instructions, different spills), so the experimental variant is compiled only on request (build.py)
+#define MARCH_OPEN_SKIP 1
+#define MARCH_OPEN_SMEM_WORDS 8192u
+#include "march_kernel.inc"
+#undef MARCH_OPEN_SKIP
+#endif
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Stage 2: SHADE.  One thread per ray record, in the same [32 probes] x [8 rays] tiling as the simple kernel, so a warp
@@ -2978,6 +2798,54 @@ void launch_l2_sweep(const void* buf, size_t bytes, int blocks, uint32_t* sink, 
     l2_sweep_kernel<<<blocks, 256, 0, s>>>((const uint4*)buf, (unsigned int)(bytes / 16), sink);
 }
 
+bool open_skip_compiled()
+{
+#ifdef LUX_EXPERIMENTAL_OPEN_SKIP
+    return true;
+#else
+    return false;
+#endif
+}
+
+#ifdef LUX_EXPERIMENTAL_OPEN_SKIP
+// Open-space table (LUX_DDGI_FLAG_OPEN_SKIP): bit of cell (cx, cy, cz) = every mip texel in [4c - 1, 4c + 4]^3 (clamped to the volume, i.e. every
+// texel a trilinear tap placed anywhere in the cell can touch, cascade seams included) is >= threshold.  threshold = chunkSizeDistance * (1 + 2^-10):
+// three nested fp32 lerps of values in [-1, 1] stay within 1e-6 of the convex combination, far inside the margin.  One thread per cell, one
+// ballot per 32 consecutive cells.
+__global__ void __launch_bounds__(256) open_table_kernel(const uint16_t* __restrict__ mip, int W, int H, int D, float threshold, uint32_t* __restrict__ bits)
+{
+    const int cw = W / 4, ch = H / 4, cd = D / 4;
+    const unsigned int cells = (unsigned int)cw * ch * cd;
+    const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool open = false;
+    if (i < cells)
+    {
+        const int cx = (int)(i % cw), cy = (int)((i / cw) % ch), cz = (int)(i / ((unsigned int)cw * ch));
+        open = true;
+        for (int z = max(4 * cz - 1, 0); z <= min(4 * cz + 4, D - 1) && open; z++)
+            for (int y = max(4 * cy - 1, 0); y <= min(4 * cy + 4, H - 1) && open; y++)
+                for (int x = max(4 * cx - 1, 0); x <= min(4 * cx + 4, W - 1); x++)
+                    if (!(h2f_bits(__ldg(mip + ((size_t)z * H + y) * W + x)) >= threshold))
+                    {
+                        open = false;
+                        break;
+                    }
+    }
+    const uint32_t word = __ballot_sync(0xffffffffu, open);
+    if ((threadIdx.x & 31) == 0 && i < ((cells + 31u) & ~31u))
+        bits[i >> 5] = word;
+}
+
+void launch_open_table(const void* mipR16F, int mipW, int mipH, int mipD, float threshold, uint32_t* bits, cudaStream_t s)
+{
+    const unsigned int cells = (unsigned int)(mipW / 4) * (mipH / 4) * (mipD / 4);
+    if (cells)
+        open_table_kernel<<<(cells + 255) / 256, 256, 0, s>>>((const uint16_t*)mipR16F, mipW, mipH, mipD, threshold, bits);
+}
+#else
+void launch_open_table(const void*, int, int, int, float, uint32_t*, cudaStream_t) {}
+#endif
+
 void launch_direct_light(const TraceParams& p, bool useTextures, const LuxLight& l, const float* cameraPosBias, void* light, int count,
                          const uint32_t* texel, const float* P, const float* N, const float* albedo, const float* metallicRoughness, cudaStream_t s)
 {
@@ -3113,7 +2981,7 @@ static int launch_shade_sorted(const TraceParams& p, int rayGroups, long long un
     return 6;
 }
 
-int launch_trace(const TraceParams& p, int variant, unsigned int* chunkCounter, cudaStream_t s, cudaEvent_t beforeShade, cudaEvent_t afterMarch)
+int launch_trace(const TraceParams& p, int variant, unsigned int* chunkCounter, cudaStream_t s, cudaEvent_t beforeShade, cudaEvent_t afterMarch, const OpenTableArgs* open)
 {
     if (variant == 0)
     {
@@ -3133,9 +3001,22 @@ int launch_trace(const TraceParams& p, int variant, unsigned int* chunkCounter, 
     const long long persistent = 148ll * MARCH_BLOCKS_PER_SM; // one resident generation of 8-warp blocks per SM
     if (blocks > persistent)
         blocks = persistent;
+#ifdef LUX_EXPERIMENTAL_OPEN_SKIP
+    size_t openSmem = 0;
+    if (open && open->bits)
+    {
+        const size_t words = ((size_t)open->w * open->h * open->d + 31) / 32;
+        openSmem = words <= MARCH_OPEN_SMEM_WORDS ? words * 4 : 0;
+    }
+#endif
     if (variant == 2)
     {
-        march_kernel<true><<<(unsigned)blocks, 32 * MARCH_WARPS, 0, s>>>(p, chunks, rayGroups, chunkCounter);
+#ifdef LUX_EXPERIMENTAL_OPEN_SKIP
+        if (open && open->bits)
+            march_open_kernel<true><<<(unsigned)blocks, 32 * MARCH_WARPS, openSmem, s>>>(p, chunks, rayGroups, chunkCounter, *open);
+        else
+#endif
+            march_kernel<true><<<(unsigned)blocks, 32 * MARCH_WARPS, 0, s>>>(p, chunks, rayGroups, chunkCounter);
         if (afterMarch)
             cudaEventRecord(afterMarch, s);
         if (beforeShade) // the march never reads the surface cache: a pending light-cache upload only gates the shade
@@ -3146,7 +3027,12 @@ int launch_trace(const TraceParams& p, int variant, unsigned int* chunkCounter, 
     }
     else
     {
-        march_kernel<false><<<(unsigned)blocks, 32 * MARCH_WARPS, 0, s>>>(p, chunks, rayGroups, chunkCounter);
+#ifdef LUX_EXPERIMENTAL_OPEN_SKIP
+        if (open && open->bits)
+            march_open_kernel<false><<<(unsigned)blocks, 32 * MARCH_WARPS, openSmem, s>>>(p, chunks, rayGroups, chunkCounter, *open);
+        else
+#endif
+            march_kernel<false><<<(unsigned)blocks, 32 * MARCH_WARPS, 0, s>>>(p, chunks, rayGroups, chunkCounter);
         if (afterMarch)
             cudaEventRecord(afterMarch, s);
         if (beforeShade)

@@ -55,6 +55,13 @@ struct TraceParams
     uint32_t* sortedIdx;    // [records] record indices in bin order
 };
 
+// optional open-space table over the mip volume (LUX_DDGI_FLAG_OPEN_SKIP): one bit per cell of 4x4x4 mip texels
+struct OpenTableArgs
+{
+    const uint32_t* bits;    // null = off
+    int             w, h, d; // cells per axis of the whole (side-by-side) mip volume
+};
+
 struct BlendParams
 {
     int   probeBegin, probeCount;
@@ -92,8 +99,10 @@ void launch_tile_zrow(const LuxTileBuffer* tiles, int count, float4* out, cudaSt
 // gathers.  Returns the number of kernels launched.
 // `beforeShade` (nullable): event the stream waits on before the first kernel that reads the surface cache.
 // `afterMarch` (nullable): recorded between the march and the shade kernel (stage timers).
+// `open` (nullable): open-space table for the experimental march variant (LUX_DDGI_FLAG_OPEN_SKIP).
+struct OpenTableArgs;
 int    launch_trace(const TraceParams& p, int variant, unsigned int* chunkCounter, cudaStream_t s, cudaEvent_t beforeShade,
-                    cudaEvent_t afterMarch);
+                    cudaEvent_t afterMarch, const OpenTableArgs* open = nullptr);
 size_t trace_record_count(int probeCount, int raysPerProbe);
 size_t trace_sort_bins(int probeCount, int raysPerProbe);   // bins of the sorted shade's counting sort (padded to the scan's block size)
 size_t trace_sort_blocks(int probeCount, int raysPerProbe); // scan blocks over those bins
@@ -131,6 +140,10 @@ void launch_sdf_shadow(const TraceParams& p, bool useTextures, const LuxLight& l
 
 // measurement aid: one sweep of `bytes` (multiple of 16 KiB) by each of `blocks` blocks through L2
 void launch_l2_sweep(const void* buf, size_t bytes, int blocks, uint32_t* sink, cudaStream_t s);
+
+// open-space table of the mip volume [mipD][mipH][mipW] (LUX_DDGI_FLAG_OPEN_SKIP): bits[(cz * ch + cy) * cw + cx], cw = mipW / 4, ...
+bool open_skip_compiled(); // false unless built with -DLUX_EXPERIMENTAL_OPEN_SKIP
+void launch_open_table(const void* mipR16F, int mipW, int mipH, int mipD, float threshold, uint32_t* bits, cudaStream_t s);
 
 // ---- global SDF build ----
 struct SdfMeshRecord // device copy of LuxMeshSDF without the host pointers

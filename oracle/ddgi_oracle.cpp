@@ -26,6 +26,7 @@
 //
 // Build: see oracle/Makefile (g++ -O2 -ffp-contract=off -fopenmp -shared).
 
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
@@ -236,8 +237,25 @@ inline GatherCoords gatherCoords(float u, float v, int W, int H, bool repeat)
     return g;
 }
 
+// Conservative "open space" table over the mip volume, the CPU twin of the engine's optional mip-tap skip (LUX_DDGI_FLAG_OPEN_SKIP): one bit per
+// cell of 4x4x4 mip texels, set when every texel a trilinear tap placed anywhere in the cell can touch (the cell dilated by one texel, clamped
+// at the volume's edges, cascade seams included because cells tile the whole side-by-side volume) is >= threshold.  A set bit proves that
+// tracyGlobalSDF's mip tap there returns >= chunkSizeDistance, i.e. the march takes its `stepDistance = chunkSizeDistance` branch without
+// needing the tap.  It never changes a result; the oracle only uses it to CHECK that claim (Counters::openViolations must stay 0).
+struct OpenTable
+{
+    int                   cw = 0, ch = 0, cd = 0; // cells per axis of the whole mip volume
+    std::vector<uint32_t> bits;
+    bool open(int cx, int cy, int cz) const
+    {
+        size_t i = ((size_t)cz * ch + cy) * cw + cx;
+        return (bits[i >> 5] >> (i & 31)) & 1u;
+    }
+};
+
 struct Scene
 {
+    const OpenTable*           open = nullptr;
     LuxDDGIUniform             ddgi;
     LuxGlobalSDFData           sdfData;
     Tex3D                      tex, mip;
@@ -256,6 +274,7 @@ struct Scene
 struct Counters
 {
     uint64_t mipTaps = 0, texTaps = 0, hits = 0, tileSamples = 0, steps = 0, objectsVisited = 0;
+    uint64_t openSteps = 0, openViolations = 0; // only with Scene::open (validation of the engine's open-space table, see buildOpenTable)
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -388,6 +407,19 @@ Hit tracyGlobalSDF(const Scene& sc, vec3 origin, vec3 dir, float maxDistance, fl
             vec3  textureUV = {((float)cascade + cascadeUV.x) / cascadesCountF, cascadeUV.y, cascadeUV.z};
 
             float stepDistance = sample3D(sc.mip, textureUV.x, textureUV.y, textureUV.z, &cn.mipTaps);
+            if (sc.open)
+            { // the cell the engine would look up: floor(fl(u * W) / 4) per axis, clamped
+                const OpenTable& ot = *sc.open;
+                int cx = iclamp((int)((textureUV.x * (float)sc.mip.w) * 0.25f), 0, ot.cw - 1);
+                int cy = iclamp((int)((textureUV.y * (float)sc.mip.h) * 0.25f), 0, ot.ch - 1);
+                int cz = iclamp((int)((textureUV.z * (float)sc.mip.d) * 0.25f), 0, ot.cd - 1);
+                if (ot.open(cx, cy, cz))
+                {
+                    cn.openSteps++;
+                    if (stepDistance < chunkSizeDistance)
+                        cn.openViolations++;
+                }
+            }
             if (stepDistance < chunkSizeDistance)
             {
                 float stepDistanceTex = sample3D(sc.tex, textureUV.x, textureUV.y, textureUV.z, &cn.texTaps);
@@ -1556,6 +1588,80 @@ int oracle_surface_cull(const LuxGlobalSurfaceAtlasData* data, const LuxObjectBu
 
 // tracyGlobalSDF for arbitrary rays (row f4: the shadow / reflection / surface-cache light rays call the same function with other
 // arguments).  needsHitNormal = false leaves the normal at (0,0,0) (SDFCommon.glsl:165-177); minDistance is never read, as in the reference.
+} // extern "C"
+
+// threshold = chunkSizeDistance * (1 + 2^-10): three nested fp32 lerps of values in [-1, 1] err by < 1e-6, the margin is >= 3e-5 at res 1024
+OpenTable buildOpenTable(const Tex3D& mip, float chunkSizeDistance)
+{
+    OpenTable t;
+    if (mip.w % 4 || mip.h % 4 || mip.d % 4)
+        return t;
+    t.cw = mip.w / 4; t.ch = mip.h / 4; t.cd = mip.d / 4;
+    const float threshold = chunkSizeDistance * (1.0f + 0.0009765625f);
+    const size_t cells = (size_t)t.cw * t.ch * t.cd;
+    t.bits.assign((cells + 31) / 32, 0u);
+#pragma omp parallel for schedule(static)
+    for (long long w = 0; w < (long long)t.bits.size(); w++)
+    {
+        uint32_t word = 0;
+        for (int b = 0; b < 32; b++)
+        {
+            size_t i = (size_t)w * 32 + b;
+            if (i >= cells)
+                break;
+            int cx = (int)(i % t.cw), cy = (int)((i / t.cw) % t.ch), cz = (int)(i / ((size_t)t.cw * t.ch));
+            bool open = true;
+            for (int z = std::max(4 * cz - 1, 0); z <= std::min(4 * cz + 4, mip.d - 1) && open; z++)
+                for (int y = std::max(4 * cy - 1, 0); y <= std::min(4 * cy + 4, mip.h - 1) && open; y++)
+                    for (int x = std::max(4 * cx - 1, 0); x <= std::min(4 * cx + 4, mip.w - 1); x++)
+                        if (!(mip.texel(x, y, z) >= threshold))
+                        {
+                            open = false;
+                            break;
+                        }
+            word |= (open ? 1u : 0u) << b;
+        }
+        t.bits[w] = word;
+    }
+    return t;
+}
+
+extern "C" {
+// Validation of the open-space table on a ray list: out = {march steps, steps in open cells, violations (open cell but mip tap < chunkSizeDistance,
+// must be 0), open cells, cells}.  bitsOut (optional, ceil(cells / 32) words) receives the table for comparison with the engine's.
+int oracle_open_space_stats(const LuxGlobalSDFData* sdfData, const uint16_t* sdf, const uint16_t* mip, int count, const LuxGlobalSDFTrace* traces,
+                            float cascadeTraceStartBias, uint64_t* out, uint32_t* bitsOut)
+{
+    if (!sdfData || !sdf || !mip || count < 0 || (count > 0 && !traces) || !out)
+        return -1;
+    Scene sc{};
+    sc.sdfData = *sdfData;
+    const int res = (int)sdfData->resolution, casc = (int)sdfData->cascadesCount;
+    sc.tex = Tex3D{sdf, res * casc, res, res};
+    sc.mip = Tex3D{mip, (res / 4) * casc, res / 4, res / 4};
+    OpenTable table = buildOpenTable(sc.mip, (float)LUX_GLOBAL_SDF_RASTERIZE_CHUNK_SIZE / sdfData->resolution);
+    if (table.bits.empty())
+        return -2;
+    sc.open = &table;
+    uint64_t steps = 0, openSteps = 0, violations = 0;
+#pragma omp parallel for schedule(dynamic, 64) reduction(+ : steps, openSteps, violations)
+    for (int k = 0; k < count; k++)
+    {
+        const LuxGlobalSDFTrace& t = traces[k];
+        Counters cn;
+        tracyGlobalSDF(sc, {t.worldPosition[0], t.worldPosition[1], t.worldPosition[2]}, {t.worldDirection[0], t.worldDirection[1], t.worldDirection[2]},
+                       t.maxDistance, t.stepScale, cascadeTraceStartBias, cn);
+        steps += cn.mipTaps; openSteps += cn.openSteps; violations += cn.openViolations;
+    }
+    uint64_t openCells = 0;
+    for (uint32_t w : table.bits)
+        openCells += (uint64_t)__builtin_popcount(w);
+    out[0] = steps; out[1] = openSteps; out[2] = violations; out[3] = openCells; out[4] = (uint64_t)table.cw * table.ch * table.cd;
+    if (bitsOut)
+        std::memcpy(bitsOut, table.bits.data(), table.bits.size() * 4);
+    return 0;
+}
+
 int oracle_trace_global_sdf(const LuxGlobalSDFData* sdfData, const uint16_t* sdf, const uint16_t* mip, int count, const LuxGlobalSDFTrace* traces,
                             float cascadeTraceStartBias, LuxGlobalSDFHit* hits)
 {
