@@ -1994,7 +1994,7 @@ struct Staged
     {
         bool o  = false;
         int  rc = stageToDevice(c, src, bytes, kind, dev, &o);
-        if (rc == LUX_OK && o)
+        if (o) // also when the copy failed after the allocation succeeded
             owned[n++] = *dev;
         return rc;
     }
