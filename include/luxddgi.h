@@ -317,7 +317,8 @@ LUX_API int lux_ddgi_set_global_sdf(LuxDDGIContext* ctx, const LuxGlobalSDFData*
 /* f4: direct lighting of surface-cache texels = Shaders/SDF/SDFDeferredLight.frag:44-129 (fetchLight, shadow ray through the global SDF with
  * start bias 2, BRDF of Raytraced/BRDF.glsl:65-83), blended ADDITIVELY into the RGBA16F light cache as the reference's pipeline does
  * (GlobalSurfaceAtlas.cpp:950-972: BlendMode::Add, alpha += 1).  One call = one light over the listed atlas texels; the per-texel arrays are
- * what SDFDeferredColor.frag captured there (world position, decoded normal, albedo, (metallic, roughness)).  cameraPos[3] = shadowBias. */
+ * what SDFDeferredColor.frag captured there (world position, decoded normal, albedo, (metallic, roughness)).  cameraPos[3] = shadowBias.
+ * Every texelIndex must be < resolution^2 of the bound surface cache (not checked on the device). */
 LUX_API int lux_ddgi_surface_direct_light(LuxDDGIContext* ctx, const LuxLight* light, const float cameraPosBias[4], int32_t count,
                                           const uint32_t* texelIndex, const float* worldPos, const float* normal, const float* albedo,
                                           const float* metallicRoughness, LuxMemKind kind);

@@ -10,7 +10,11 @@
 //     tests/golden/border_offsets.json and compared entry by entry;
 //   * golden vectors produced by EXECUTING the reference's shipped SPIR-V binaries (Assets/shaders/spv/DDGI/*.comp.spv)
 //     with the interpreter in oracle/spirv/ (tests/golden/README.md): trace and border reproduce them bit for bit, blend
-//     bit for bit in `unfused` mode and within 1 fp16 ulp in the contract's FMA mode (tests/test_spirv_golden.py);
+//     bit for bit in `unfused` mode and within 1 fp16 ulp in the contract's FMA mode (tests/test_spirv_golden.py); the trace also on
+//     2- and 4-cascade volumes and on an open scene (sky path);
+//   * the rows either side of the path the same way, from Assets/shaders/spv/{DDGI/SampleProbe.comp, SDF/SDFRasterizeModel*.comp,
+//     SDF/GlobalSDFMipmap.comp, SDF/SDFCulling.comp, SDF/SDFDeferredLight.frag, SDF/SDFAtlasIndirectLight.frag, SDF/SDFReflection.comp,
+//     SDF/SDFShadow.comp}.spv, all bit for bit;
 //   * closed-form known-answer tests (tests/test_oracle_kat.py).
 //
 // Every function cites the reference file:line it follows (paths relative to Code/Maple/src/).
