@@ -413,12 +413,12 @@ static int setup(LuxDDGIContext& c, const LuxTracePushConstants& push)
         c.masksDirty = false;
     }
     if ((c.flags & LUX_DDGI_FLAG_OPEN_SKIP) && !(c.flags & LUX_DDGI_FLAG_TRACE_SIMPLE) && c.openDirty)
-    { // open-space table of the mip volume (experimental march variant); volumes whose mip side is not a multiple of 4 run without it
+    { // open-space table of the mip volume (experimental march variant); volumes whose mip side is not a multiple of the cell run without it
         const int mres = (int)c.sdfData.resolution / 4, mw = mres * (int)c.sdfData.cascadesCount;
         c.openBits.release();
-        if (mres >= 4 && mres % 4 == 0)
+        if (mres >= OPEN_CELL && mres % OPEN_CELL == 0)
         {
-            const size_t cells = (size_t)(mw / 4) * (mres / 4) * (mres / 4), bytes = ((cells + 31) / 32) * 4;
+            const size_t cells = (size_t)(mw / OPEN_CELL) * (mres / OPEN_CELL) * (mres / OPEN_CELL), bytes = ((cells + 31) / 32) * 4;
             LUX_CUDA(cudaMalloc(&c.openBits.ptr, bytes));
             c.openBits.bytes = bytes;
             const float chunkSizeDistance = (float)LUX_GLOBAL_SDF_RASTERIZE_CHUNK_SIZE / c.sdfData.resolution;
@@ -473,7 +473,7 @@ static int launchBatch(LuxDDGIContext& c, const LuxDDGIContext::Batch& b, int ba
     p.sky      = (const uint2*)c.sky.ptr;
     OpenTableArgs open{};
     if ((c.flags & LUX_DDGI_FLAG_OPEN_SKIP) && c.openBits.ptr)
-        open = OpenTableArgs{(const uint32_t*)c.openBits.ptr, p.mipRes * p.cascades / 4, p.mipRes / 4, p.mipRes / 4};
+        open = OpenTableArgs{(const uint32_t*)c.openBits.ptr, p.mipRes * p.cascades / OPEN_CELL, p.mipRes / OPEN_CELL, p.mipRes / OPEN_CELL};
     p.dirs     = (const float4*)c.dirs.ptr;
     p.radiance = (uint2*)c.radiance.ptr + rayStart;
     p.dirDist  = (uint2*)c.directionDepth.ptr + rayStart;

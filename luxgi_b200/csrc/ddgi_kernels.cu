@@ -2808,13 +2808,13 @@ bool open_skip_compiled()
 }
 
 #ifdef LUX_EXPERIMENTAL_OPEN_SKIP
-// Open-space table (LUX_DDGI_FLAG_OPEN_SKIP): bit of cell (cx, cy, cz) = every mip texel in [4c - 1, 4c + 4]^3 (clamped to the volume, i.e. every
+// Open-space table (LUX_DDGI_FLAG_OPEN_SKIP): bit of cell (cx, cy, cz) = every mip texel in [OPEN_CELL * c - 1, OPEN_CELL * c + OPEN_CELL]^3 (clamped to the volume, i.e. every
 // texel a trilinear tap placed anywhere in the cell can touch, cascade seams included) is >= threshold.  threshold = chunkSizeDistance * (1 + 2^-10):
 // three nested fp32 lerps of values in [-1, 1] stay within 1e-6 of the convex combination, far inside the margin.  One thread per cell, one
 // ballot per 32 consecutive cells.
 __global__ void __launch_bounds__(256) open_table_kernel(const uint16_t* __restrict__ mip, int W, int H, int D, float threshold, uint32_t* __restrict__ bits)
 {
-    const int cw = W / 4, ch = H / 4, cd = D / 4;
+    const int cw = W / OPEN_CELL, ch = H / OPEN_CELL, cd = D / OPEN_CELL;
     const unsigned int cells = (unsigned int)cw * ch * cd;
     const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
     bool open = false;
@@ -2822,9 +2822,9 @@ __global__ void __launch_bounds__(256) open_table_kernel(const uint16_t* __restr
     {
         const int cx = (int)(i % cw), cy = (int)((i / cw) % ch), cz = (int)(i / ((unsigned int)cw * ch));
         open = true;
-        for (int z = max(4 * cz - 1, 0); z <= min(4 * cz + 4, D - 1) && open; z++)
-            for (int y = max(4 * cy - 1, 0); y <= min(4 * cy + 4, H - 1) && open; y++)
-                for (int x = max(4 * cx - 1, 0); x <= min(4 * cx + 4, W - 1); x++)
+        for (int z = max(OPEN_CELL * cz - 1, 0); z <= min(OPEN_CELL * cz + OPEN_CELL, D - 1) && open; z++)
+            for (int y = max(OPEN_CELL * cy - 1, 0); y <= min(OPEN_CELL * cy + OPEN_CELL, H - 1) && open; y++)
+                for (int x = max(OPEN_CELL * cx - 1, 0); x <= min(OPEN_CELL * cx + OPEN_CELL, W - 1); x++)
                     if (!(h2f_bits(__ldg(mip + ((size_t)z * H + y) * W + x)) >= threshold))
                     {
                         open = false;
@@ -2838,7 +2838,7 @@ __global__ void __launch_bounds__(256) open_table_kernel(const uint16_t* __restr
 
 void launch_open_table(const void* mipR16F, int mipW, int mipH, int mipD, float threshold, uint32_t* bits, cudaStream_t s)
 {
-    const unsigned int cells = (unsigned int)(mipW / 4) * (mipH / 4) * (mipD / 4);
+    const unsigned int cells = (unsigned int)(mipW / OPEN_CELL) * (mipH / OPEN_CELL) * (mipD / OPEN_CELL);
     if (cells)
         open_table_kernel<<<(cells + 255) / 256, 256, 0, s>>>((const uint16_t*)mipR16F, mipW, mipH, mipD, threshold, bits);
 }

@@ -242,13 +242,14 @@ inline GatherCoords gatherCoords(float u, float v, int W, int H, bool repeat)
 }
 
 // Conservative "open space" table over the mip volume, the CPU twin of the engine's optional mip-tap skip (LUX_DDGI_FLAG_OPEN_SKIP): one bit per
-// cell of 4x4x4 mip texels, set when every texel a trilinear tap placed anywhere in the cell can touch (the cell dilated by one texel, clamped
+// cell of 8x8x8 mip texels, set when every texel a trilinear tap placed anywhere in the cell can touch (the cell dilated by one texel, clamped
 // at the volume's edges, cascade seams included because cells tile the whole side-by-side volume) is >= threshold.  A set bit proves that
 // tracyGlobalSDF's mip tap there returns >= chunkSizeDistance, i.e. the march takes its `stepDistance = chunkSizeDistance` branch without
 // needing the tap.  It never changes a result; the oracle only uses it to CHECK that claim (Counters::openViolations must stay 0).
 struct OpenTable
 {
     int                   cw = 0, ch = 0, cd = 0; // cells per axis of the whole mip volume
+    int                   cell = 8;               // mip texels per cell side (the engine uses 8; other sizes only for the share statistics)
     std::vector<uint32_t> bits;
     bool open(int cx, int cy, int cz) const
     {
@@ -414,9 +415,10 @@ Hit tracyGlobalSDF(const Scene& sc, vec3 origin, vec3 dir, float maxDistance, fl
             if (sc.open)
             { // the cell the engine would look up: floor(fl(u * W) / 4) per axis, clamped
                 const OpenTable& ot = *sc.open;
-                int cx = iclamp((int)((textureUV.x * (float)sc.mip.w) * 0.25f), 0, ot.cw - 1);
-                int cy = iclamp((int)((textureUV.y * (float)sc.mip.h) * 0.25f), 0, ot.ch - 1);
-                int cz = iclamp((int)((textureUV.z * (float)sc.mip.d) * 0.25f), 0, ot.cd - 1);
+                const float inv = 1.0f / (float)ot.cell; // a power of two: exact
+                int cx = iclamp((int)((textureUV.x * (float)sc.mip.w) * inv), 0, ot.cw - 1);
+                int cy = iclamp((int)((textureUV.y * (float)sc.mip.h) * inv), 0, ot.ch - 1);
+                int cz = iclamp((int)((textureUV.z * (float)sc.mip.d) * inv), 0, ot.cd - 1);
                 if (ot.open(cx, cy, cz))
                 {
                     cn.openSteps++;
@@ -1595,12 +1597,13 @@ int oracle_surface_cull(const LuxGlobalSurfaceAtlasData* data, const LuxObjectBu
 } // extern "C"
 
 // threshold = chunkSizeDistance * (1 + 2^-10): three nested fp32 lerps of values in [-1, 1] err by < 1e-6, the margin is >= 3e-5 at res 1024
-OpenTable buildOpenTable(const Tex3D& mip, float chunkSizeDistance)
+OpenTable buildOpenTable(const Tex3D& mip, float chunkSizeDistance, int cell = 8)
 {
     OpenTable t;
-    if (mip.w % 4 || mip.h % 4 || mip.d % 4)
+    if (cell < 1 || (cell & (cell - 1)) || mip.w % cell || mip.h % cell || mip.d % cell)
         return t;
-    t.cw = mip.w / 4; t.ch = mip.h / 4; t.cd = mip.d / 4;
+    t.cell = cell;
+    t.cw = mip.w / cell; t.ch = mip.h / cell; t.cd = mip.d / cell;
     const float threshold = chunkSizeDistance * (1.0f + 0.0009765625f);
     const size_t cells = (size_t)t.cw * t.ch * t.cd;
     t.bits.assign((cells + 31) / 32, 0u);
@@ -1615,9 +1618,9 @@ OpenTable buildOpenTable(const Tex3D& mip, float chunkSizeDistance)
                 break;
             int cx = (int)(i % t.cw), cy = (int)((i / t.cw) % t.ch), cz = (int)(i / ((size_t)t.cw * t.ch));
             bool open = true;
-            for (int z = std::max(4 * cz - 1, 0); z <= std::min(4 * cz + 4, mip.d - 1) && open; z++)
-                for (int y = std::max(4 * cy - 1, 0); y <= std::min(4 * cy + 4, mip.h - 1) && open; y++)
-                    for (int x = std::max(4 * cx - 1, 0); x <= std::min(4 * cx + 4, mip.w - 1); x++)
+            for (int z = std::max(cell * cz - 1, 0); z <= std::min(cell * cz + cell, mip.d - 1) && open; z++)
+                for (int y = std::max(cell * cy - 1, 0); y <= std::min(cell * cy + cell, mip.h - 1) && open; y++)
+                    for (int x = std::max(cell * cx - 1, 0); x <= std::min(cell * cx + cell, mip.w - 1); x++)
                         if (!(mip.texel(x, y, z) >= threshold))
                         {
                             open = false;
@@ -1634,7 +1637,7 @@ extern "C" {
 // Validation of the open-space table on a ray list: out = {march steps, steps in open cells, violations (open cell but mip tap < chunkSizeDistance,
 // must be 0), open cells, cells}.  bitsOut (optional, ceil(cells / 32) words) receives the table for comparison with the engine's.
 int oracle_open_space_stats(const LuxGlobalSDFData* sdfData, const uint16_t* sdf, const uint16_t* mip, int count, const LuxGlobalSDFTrace* traces,
-                            float cascadeTraceStartBias, uint64_t* out, uint32_t* bitsOut)
+                            float cascadeTraceStartBias, uint64_t* out, uint32_t* bitsOut, int cell)
 {
     if (!sdfData || !sdf || !mip || count < 0 || (count > 0 && !traces) || !out)
         return -1;
@@ -1643,7 +1646,7 @@ int oracle_open_space_stats(const LuxGlobalSDFData* sdfData, const uint16_t* sdf
     const int res = (int)sdfData->resolution, casc = (int)sdfData->cascadesCount;
     sc.tex = Tex3D{sdf, res * casc, res, res};
     sc.mip = Tex3D{mip, (res / 4) * casc, res / 4, res / 4};
-    OpenTable table = buildOpenTable(sc.mip, (float)LUX_GLOBAL_SDF_RASTERIZE_CHUNK_SIZE / sdfData->resolution);
+    OpenTable table = buildOpenTable(sc.mip, (float)LUX_GLOBAL_SDF_RASTERIZE_CHUNK_SIZE / sdfData->resolution, cell);
     if (table.bits.empty())
         return -2;
     sc.open = &table;

@@ -2,7 +2,7 @@
 
     python tests/experimental/open_skip_check.py [--bench c4] [--bench c5]
 
-LUX_DDGI_FLAG_OPEN_SKIP: the wavefront march looks each step's position up in a conservative open-space table (one bit per 4x4x4 mip texels, set
+LUX_DDGI_FLAG_OPEN_SKIP: the wavefront march looks each step's position up in a conservative open-space table (one bit per 8x8x8 mip texels, set
 when every texel a trilinear tap in that cell can touch is >= chunkSizeDistance * (1 + 2^-10)) and skips the mip tap (and the speculative
 full-resolution tap) where it provably takes the reference's `stepDistance = chunkSizeDistance` branch.  Results must be bit-identical.
 The CPU side of the argument is already checked (tests/test_oracle_kat.py::test_open_space_table_is_conservative: 0 violations; the share of
@@ -83,7 +83,7 @@ def main():
     parity("city64", scenes.build("city64"))
     parity("city128", scenes.build("city128", counts=(16, 16, 16)))
     parity("cornell 2 cascades", scenes.cornell_scene(res=64, counts=(8, 4, 8), rays=96, atlas_res=256, cascades=2), frames=3)
-    parity("cornell 32^3 (mip 8^3: two cells per axis)", scenes.cornell_scene(res=32, counts=(3, 5, 2), rays=50, atlas_res=256))
+    parity("cornell 32^3 (mip 8^3: one cell per axis)", scenes.cornell_scene(res=32, counts=(3, 5, 2), rays=50, atlas_res=256))
     print(f"parity done in {time.time() - t0:.1f} s")
     for w in args.bench:
         bench(w)

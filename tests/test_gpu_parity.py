@@ -711,14 +711,14 @@ def test_sdf_shadow_matches_shipped_spirv_and_oracle(oracle):
 
 
 def test_l2_bandwidth_measurement():
-    """lux_ddgi_measure_l2_read_bandwidth (the denominator of bench.py's request-level roofline): an L2-resident sweep must come out above the
-    HBM copy bandwidth of MEASURED_PEAKS.json and below anything physical; a 1 GiB sweep (larger than L2) must be slower than the 64 MiB one."""
+    """lux_ddgi_measure_l2_read_bandwidth (the denominator of bench.py's request-level roofline): an L2-resident sweep must come out well above
+    HBM bandwidth and below anything physical (measured: 21.5 TB/s for 64 MiB; 17 TB/s for 1 GiB, which the staggered blocks also serve mostly from L2)."""
     sc = scenes.cornell_scene(res=32, counts=(2, 2, 2), rays=32, atlas_res=256, with_atlas=False)
     pipe = ddgi.DDGIPipeline(sc.uniform)
     l2 = pipe.measure_l2_read_bandwidth()
     big = pipe.measure_l2_read_bandwidth(1 << 30, repeats=2)
     print("L2 read sweep GB/s:", l2, " 1 GiB sweep GB/s:", big)
-    assert 3000.0 < l2 < 100000.0 and big < l2
+    assert 8000.0 < l2 < 100000.0 and 3000.0 < big < 100000.0
     with pytest.raises(ddgi.LuxError):
         pipe.measure_l2_read_bandwidth(repeats=0)
     pipe.close()
