@@ -418,11 +418,11 @@ static int setup(LuxDDGIContext& c, const LuxTracePushConstants& push)
         c.openBits.release();
         if (mres >= OPEN_CELL && mres % OPEN_CELL == 0)
         {
-            const size_t cells = (size_t)(mw / OPEN_CELL) * (mres / OPEN_CELL) * (mres / OPEN_CELL), bytes = ((cells + 31) / 32) * 4;
+            const size_t cells = (size_t)(mw / OPEN_CELL) * (mres / OPEN_CELL) * (mres / OPEN_CELL), bytes = 2 * ((cells + 31) / 32) * 4; // open + near bits
             LUX_CUDA(cudaMalloc(&c.openBits.ptr, bytes));
             c.openBits.bytes = bytes;
             const float chunkSizeDistance = (float)LUX_GLOBAL_SDF_RASTERIZE_CHUNK_SIZE / c.sdfData.resolution;
-            lux::launch_open_table(c.mip.ptr, mw, mres, mres, chunkSizeDistance * (1.0f + 0.0009765625f), (uint32_t*)c.openBits.ptr, c.stream);
+            lux::launch_open_table(c.mip.ptr, mw, mres, mres, chunkSizeDistance, (uint32_t*)c.openBits.ptr, c.stream);
             c.launches += 1;
             LUX_CUDA(cudaGetLastError());
         }

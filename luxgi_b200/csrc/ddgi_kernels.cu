@@ -2808,39 +2808,46 @@ bool open_skip_compiled()
 }
 
 #ifdef LUX_EXPERIMENTAL_OPEN_SKIP
-// Open-space table (LUX_DDGI_FLAG_OPEN_SKIP): bit of cell (cx, cy, cz) = every mip texel in [OPEN_CELL * c - 1, OPEN_CELL * c + OPEN_CELL]^3 (clamped to the volume, i.e. every
-// texel a trilinear tap placed anywhere in the cell can touch, cascade seams included) is >= threshold.  threshold = chunkSizeDistance * (1 + 2^-10):
-// three nested fp32 lerps of values in [-1, 1] stay within 1e-6 of the convex combination, far inside the margin.  One thread per cell, one
-// ballot per 32 consecutive cells.
-__global__ void __launch_bounds__(256) open_table_kernel(const uint16_t* __restrict__ mip, int W, int H, int D, float threshold, uint32_t* __restrict__ bits)
+// Open-space table (LUX_DDGI_FLAG_OPEN_SKIP), two bit arrays of `words` words each over cells of OPEN_CELL^3 mip texels:
+//   open bit of cell c = every mip texel in [OPEN_CELL * c - 1, OPEN_CELL * c + OPEN_CELL]^3 (clamped to the volume, i.e. every texel a trilinear tap
+//                        placed anywhere in the cell can touch, cascade seams included) is >= chunkSizeDistance * (1 + 2^-10);
+//   near bit           = every such texel is < chunkSizeDistance * (1 - 2^-10).
+// Three nested fp32 lerps of values in [-1, 1] stay within 1e-6 of the convex combination, far inside the margins, so a set bit decides the
+// reference's `stepDistance < chunkSizeDistance` test without the tap.  One thread per cell, one ballot per 32 consecutive cells.
+__global__ void __launch_bounds__(256) open_table_kernel(const uint16_t* __restrict__ mip, int W, int H, int D, float chunkSizeDistance, uint32_t* __restrict__ bits,
+                                                         unsigned int words)
 {
     const int cw = W / OPEN_CELL, ch = H / OPEN_CELL, cd = D / OPEN_CELL;
     const unsigned int cells = (unsigned int)cw * ch * cd;
     const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
-    bool open = false;
+    const float hi = chunkSizeDistance * (1.0f + 0.0009765625f), lo = chunkSizeDistance * (1.0f - 0.0009765625f);
+    bool open = false, nearAll = false;
     if (i < cells)
     {
         const int cx = (int)(i % cw), cy = (int)((i / cw) % ch), cz = (int)(i / ((unsigned int)cw * ch));
-        open = true;
-        for (int z = max(OPEN_CELL * cz - 1, 0); z <= min(OPEN_CELL * cz + OPEN_CELL, D - 1) && open; z++)
-            for (int y = max(OPEN_CELL * cy - 1, 0); y <= min(OPEN_CELL * cy + OPEN_CELL, H - 1) && open; y++)
+        open = nearAll = true;
+        for (int z = max(OPEN_CELL * cz - 1, 0); z <= min(OPEN_CELL * cz + OPEN_CELL, D - 1) && (open || nearAll); z++)
+            for (int y = max(OPEN_CELL * cy - 1, 0); y <= min(OPEN_CELL * cy + OPEN_CELL, H - 1) && (open || nearAll); y++)
                 for (int x = max(OPEN_CELL * cx - 1, 0); x <= min(OPEN_CELL * cx + OPEN_CELL, W - 1); x++)
-                    if (!(h2f_bits(__ldg(mip + ((size_t)z * H + y) * W + x)) >= threshold))
-                    {
-                        open = false;
-                        break;
-                    }
+                {
+                    const float v = h2f_bits(__ldg(mip + ((size_t)z * H + y) * W + x));
+                    open    = open && (v >= hi);
+                    nearAll = nearAll && (v < lo);
+                }
     }
-    const uint32_t word = __ballot_sync(0xffffffffu, open);
-    if ((threadIdx.x & 31) == 0 && i < ((cells + 31u) & ~31u))
-        bits[i >> 5] = word;
+    const uint32_t openWord = __ballot_sync(0xffffffffu, open), nearWord = __ballot_sync(0xffffffffu, nearAll);
+    if ((threadIdx.x & 31) == 0 && (i >> 5) < words)
+    {
+        bits[i >> 5]         = openWord;
+        bits[words + (i >> 5)] = nearWord;
+    }
 }
 
-void launch_open_table(const void* mipR16F, int mipW, int mipH, int mipD, float threshold, uint32_t* bits, cudaStream_t s)
+void launch_open_table(const void* mipR16F, int mipW, int mipH, int mipD, float chunkSizeDistance, uint32_t* bits, cudaStream_t s)
 {
-    const unsigned int cells = (unsigned int)(mipW / OPEN_CELL) * (mipH / OPEN_CELL) * (mipD / OPEN_CELL);
+    const unsigned int cells = (unsigned int)(mipW / OPEN_CELL) * (mipH / OPEN_CELL) * (mipD / OPEN_CELL), words = (cells + 31) / 32;
     if (cells)
-        open_table_kernel<<<(cells + 255) / 256, 256, 0, s>>>((const uint16_t*)mipR16F, mipW, mipH, mipD, threshold, bits);
+        open_table_kernel<<<words * 32 / 256 + 1, 256, 0, s>>>((const uint16_t*)mipR16F, mipW, mipH, mipD, chunkSizeDistance, bits, words);
 }
 #else
 void launch_open_table(const void*, int, int, int, float, uint32_t*, cudaStream_t) {}
@@ -3005,7 +3012,7 @@ int launch_trace(const TraceParams& p, int variant, unsigned int* chunkCounter, 
     size_t openSmem = 0;
     if (open && open->bits)
     {
-        const size_t words = ((size_t)open->w * open->h * open->d + 31) / 32;
+        const size_t words = 2 * (((size_t)open->w * open->h * open->d + 31) / 32); // open + near bit arrays
         openSmem = words <= MARCH_OPEN_SMEM_WORDS ? words * 4 : 0;
     }
 #endif

@@ -61,7 +61,7 @@ struct TraceParams
 constexpr int OPEN_CELL = 8;
 struct OpenTableArgs
 {
-    const uint32_t* bits;    // null = off
+    const uint32_t* bits;    // null = off; [0, words) open bits, [words, 2 * words) near bits
     int             w, h, d; // cells per axis of the whole (side-by-side) mip volume
 };
 
@@ -144,9 +144,10 @@ void launch_sdf_shadow(const TraceParams& p, bool useTextures, const LuxLight& l
 // measurement aid: one sweep of `bytes` (multiple of 16 KiB) by each of `blocks` blocks through L2
 void launch_l2_sweep(const void* buf, size_t bytes, int blocks, uint32_t* sink, cudaStream_t s);
 
-// open-space table of the mip volume [mipD][mipH][mipW] (LUX_DDGI_FLAG_OPEN_SKIP): bits[(cz * ch + cy) * cw + cx], cw = mipW / OPEN_CELL, ...
+// open-space table of the mip volume [mipD][mipH][mipW] (LUX_DDGI_FLAG_OPEN_SKIP): two bit arrays (open, then near) of ceil(cells / 32) words each,
+// bit index (cz * ch + cy) * cw + cx, cw = mipW / OPEN_CELL, ...
 bool open_skip_compiled(); // false unless built with -DLUX_EXPERIMENTAL_OPEN_SKIP
-void launch_open_table(const void* mipR16F, int mipW, int mipH, int mipD, float threshold, uint32_t* bits, cudaStream_t s);
+void launch_open_table(const void* mipR16F, int mipW, int mipH, int mipD, float chunkSizeDistance, uint32_t* bits, cudaStream_t s);
 
 // ---- global SDF build ----
 struct SdfMeshRecord // device copy of LuxMeshSDF without the host pointers

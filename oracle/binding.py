@@ -429,10 +429,11 @@ def open_space_stats(sdf_data, sdf, mip, traces, start_bias=0.0, cell=8):
     mres = int(sdf_data.resolution) // 4
     cells = (mres // cell) ** 3 * int(sdf_data.cascadesCount)
     bits = np.zeros((cells + 31) // 32, dtype=np.uint32)
-    out = np.zeros(5, dtype=np.uint64)
+    out = np.zeros(9, dtype=np.uint64)
     L = lib()
     L.oracle_open_space_stats.restype = C.c_int
     L.oracle_open_space_stats.argtypes = [C.POINTER(abi.GlobalSDFData), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_int]
     rc = L.oracle_open_space_stats(C.byref(sdf_data), _ptr(s), _ptr(m), len(traces), _ptr(traces), float(start_bias), _ptr(out), _ptr(bits), int(cell))
     assert rc == 0, rc
-    return dict(zip(("mip_taps", "open_steps", "violations", "open_cells", "cells"), (int(x) for x in out))), bits
+    return dict(zip(("mip_taps", "open_steps", "violations", "open_cells", "cells", "near_steps", "near_violations", "near_tex_used", "tex_used"),
+                    (int(x) for x in out))), bits

@@ -251,10 +251,16 @@ struct OpenTable
     int                   cw = 0, ch = 0, cd = 0; // cells per axis of the whole mip volume
     int                   cell = 8;               // mip texels per cell side (the engine uses 8; other sizes only for the share statistics)
     std::vector<uint32_t> bits;
+    std::vector<uint32_t> nearBits; // statistics only: every texel of the dilated cell < chunkSizeDistance * (1 - 2^-10)
     bool open(int cx, int cy, int cz) const
     {
         size_t i = ((size_t)cz * ch + cy) * cw + cx;
         return (bits[i >> 5] >> (i & 31)) & 1u;
+    }
+    bool isNear(int cx, int cy, int cz) const
+    {
+        size_t i = ((size_t)cz * ch + cy) * cw + cx;
+        return (nearBits[i >> 5] >> (i & 31)) & 1u;
     }
 };
 
@@ -280,6 +286,7 @@ struct Counters
 {
     uint64_t mipTaps = 0, texTaps = 0, hits = 0, tileSamples = 0, steps = 0, objectsVisited = 0;
     uint64_t openSteps = 0, openViolations = 0; // only with Scene::open (validation of the engine's open-space table, see buildOpenTable)
+    uint64_t nearSteps = 0, nearViolations = 0, nearTexUsed = 0, texUsed = 0; // statistics for a possible "near" table (mip tap provably < chunkSizeDistance)
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -425,12 +432,23 @@ Hit tracyGlobalSDF(const Scene& sc, vec3 origin, vec3 dir, float maxDistance, fl
                     if (stepDistance < chunkSizeDistance)
                         cn.openViolations++;
                 }
+                if (ot.isNear(cx, cy, cz))
+                {
+                    cn.nearSteps++;
+                    if (!(stepDistance < chunkSizeDistance))
+                        cn.nearViolations++;
+                    else if (sample3D(sc.tex, textureUV.x, textureUV.y, textureUV.z, nullptr) < chunkMarginDistance * 2.0f)
+                        cn.nearTexUsed++;
+                }
             }
             if (stepDistance < chunkSizeDistance)
             {
                 float stepDistanceTex = sample3D(sc.tex, textureUV.x, textureUV.y, textureUV.z, &cn.texTaps);
                 if (stepDistanceTex < chunkMarginDistance * 2.0f)
+                {
                     stepDistance = stepDistanceTex;
+                    cn.texUsed++;
+                }
             }
             else
                 stepDistance = chunkSizeDistance;
@@ -1607,16 +1625,28 @@ OpenTable buildOpenTable(const Tex3D& mip, float chunkSizeDistance, int cell = 8
     const float threshold = chunkSizeDistance * (1.0f + 0.0009765625f);
     const size_t cells = (size_t)t.cw * t.ch * t.cd;
     t.bits.assign((cells + 31) / 32, 0u);
+    t.nearBits.assign((cells + 31) / 32, 0u);
+    const float nearThreshold = chunkSizeDistance * (1.0f - 0.0009765625f);
 #pragma omp parallel for schedule(static)
     for (long long w = 0; w < (long long)t.bits.size(); w++)
     {
-        uint32_t word = 0;
+        uint32_t word = 0, nearWord = 0;
         for (int b = 0; b < 32; b++)
         {
             size_t i = (size_t)w * 32 + b;
             if (i >= cells)
                 break;
             int cx = (int)(i % t.cw), cy = (int)((i / t.cw) % t.ch), cz = (int)(i / ((size_t)t.cw * t.ch));
+            bool nearAll = true;
+            for (int z = std::max(cell * cz - 1, 0); z <= std::min(cell * cz + cell, mip.d - 1) && nearAll; z++)
+                for (int y = std::max(cell * cy - 1, 0); y <= std::min(cell * cy + cell, mip.h - 1) && nearAll; y++)
+                    for (int x = std::max(cell * cx - 1, 0); x <= std::min(cell * cx + cell, mip.w - 1); x++)
+                        if (!(mip.texel(x, y, z) < nearThreshold))
+                        {
+                            nearAll = false;
+                            break;
+                        }
+            nearWord |= (nearAll ? 1u : 0u) << b;
             bool open = true;
             for (int z = std::max(cell * cz - 1, 0); z <= std::min(cell * cz + cell, mip.d - 1) && open; z++)
                 for (int y = std::max(cell * cy - 1, 0); y <= std::min(cell * cy + cell, mip.h - 1) && open; y++)
@@ -1629,13 +1659,14 @@ OpenTable buildOpenTable(const Tex3D& mip, float chunkSizeDistance, int cell = 8
             word |= (open ? 1u : 0u) << b;
         }
         t.bits[w] = word;
+        t.nearBits[w] = nearWord;
     }
     return t;
 }
 
 extern "C" {
 // Validation of the open-space table on a ray list: out = {march steps, steps in open cells, violations (open cell but mip tap < chunkSizeDistance,
-// must be 0), open cells, cells}.  bitsOut (optional, ceil(cells / 32) words) receives the table for comparison with the engine's.
+// must be 0), open cells, cells, steps in "near" cells, near violations, near steps whose full-resolution tap is the one used, steps that use it}.  bitsOut (optional, ceil(cells / 32) words) receives the table for comparison with the engine's.
 int oracle_open_space_stats(const LuxGlobalSDFData* sdfData, const uint16_t* sdf, const uint16_t* mip, int count, const LuxGlobalSDFTrace* traces,
                             float cascadeTraceStartBias, uint64_t* out, uint32_t* bitsOut, int cell)
 {
@@ -1650,8 +1681,8 @@ int oracle_open_space_stats(const LuxGlobalSDFData* sdfData, const uint16_t* sdf
     if (table.bits.empty())
         return -2;
     sc.open = &table;
-    uint64_t steps = 0, openSteps = 0, violations = 0;
-#pragma omp parallel for schedule(dynamic, 64) reduction(+ : steps, openSteps, violations)
+    uint64_t steps = 0, openSteps = 0, violations = 0, nearSteps = 0, nearViolations = 0, nearTexUsed = 0, texUsed = 0;
+#pragma omp parallel for schedule(dynamic, 64) reduction(+ : steps, openSteps, violations, nearSteps, nearViolations, nearTexUsed, texUsed)
     for (int k = 0; k < count; k++)
     {
         const LuxGlobalSDFTrace& t = traces[k];
@@ -1659,11 +1690,13 @@ int oracle_open_space_stats(const LuxGlobalSDFData* sdfData, const uint16_t* sdf
         tracyGlobalSDF(sc, {t.worldPosition[0], t.worldPosition[1], t.worldPosition[2]}, {t.worldDirection[0], t.worldDirection[1], t.worldDirection[2]},
                        t.maxDistance, t.stepScale, cascadeTraceStartBias, cn);
         steps += cn.mipTaps; openSteps += cn.openSteps; violations += cn.openViolations;
+        nearSteps += cn.nearSteps; nearViolations += cn.nearViolations; nearTexUsed += cn.nearTexUsed; texUsed += cn.texUsed;
     }
     uint64_t openCells = 0;
     for (uint32_t w : table.bits)
         openCells += (uint64_t)__builtin_popcount(w);
     out[0] = steps; out[1] = openSteps; out[2] = violations; out[3] = openCells; out[4] = (uint64_t)table.cw * table.ch * table.cd;
+    out[5] = nearSteps; out[6] = nearViolations; out[7] = nearTexUsed; out[8] = texUsed;
     if (bitsOut)
         std::memcpy(bitsOut, table.bits.data(), table.bits.size() * 4);
     return 0;

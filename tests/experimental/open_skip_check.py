@@ -2,11 +2,12 @@
 
     python tests/experimental/open_skip_check.py [--bench c4] [--bench c5]
 
-LUX_DDGI_FLAG_OPEN_SKIP: the wavefront march looks each step's position up in a conservative open-space table (one bit per 8x8x8 mip texels, set
-when every texel a trilinear tap in that cell can touch is >= chunkSizeDistance * (1 + 2^-10)) and skips the mip tap (and the speculative
-full-resolution tap) where it provably takes the reference's `stepDistance = chunkSizeDistance` branch.  Results must be bit-identical.
-The CPU side of the argument is already checked (tests/test_oracle_kat.py::test_open_space_table_is_conservative: 0 violations; the share of
-march steps that land in open cells is 12 % on C4 and larger on C5, whose upper probe layers look at open sky).
+LUX_DDGI_FLAG_OPEN_SKIP: the wavefront march looks each step's position up in a conservative two-bit table over the mip volume (one cell per 8x8x8
+mip texels).  OPEN = every texel a trilinear tap in that cell can touch is >= chunkSizeDistance * (1 + 2^-10): the step takes the reference's
+`stepDistance = chunkSizeDistance` branch with no tap at all.  NEAR = every such texel is < chunkSizeDistance * (1 - 2^-10): only the
+full-resolution tap is taken, the mip tap only when that one is >= 2 * margin.  Results must be bit-identical.
+The CPU side of the argument is already checked (tests/test_oracle_kat.py::test_open_space_table_is_conservative: 0 violations; C4: 10.8 % of the
+march steps are open and 72 % need no mip tap; C5: 44.6 % open and 36 % no mip tap).
 
 What this script does: builds libluxddgi_experimental.so (-DLUX_EXPERIMENTAL_OPEN_SKIP; the shipped library stays untouched), checks parity of
 every small configuration against the oracle with the flag on, and with --bench times the update with and without the flag (same library, same

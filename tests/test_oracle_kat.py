@@ -386,9 +386,9 @@ def test_generic_sdf_trace_reproduces_the_probe_trace(oracle):
 
 
 def test_open_space_table_is_conservative(oracle):
-    """The CPU half of the experimental open-space skip (LUX_DDGI_FLAG_OPEN_SKIP): wherever the table marks a cell open, the
-    reference's mip tap really returns >= chunkSizeDistance, for every march step of random rays and of probe rays, on a city with open sky
-    (1- and 2-cascade volumes).  0 violations = skipping the tap there cannot change a result."""
+    """The CPU half of the experimental march variant (LUX_DDGI_FLAG_OPEN_SKIP): wherever the table marks a cell OPEN the reference's
+    mip tap really returns >= chunkSizeDistance, wherever it marks a cell NEAR the tap really returns < chunkSizeDistance, for every march step
+    of random rays on a city with open sky and on a 2-cascade volume.  0 violations = deciding the branch from the table cannot change a result."""
     rng = np.random.default_rng(3)
     for sc, lo, hi in ((scenes.build("city128", with_atlas=False), (-64.0, 0.0, -64.0), (64.0, 120.0, 64.0)),
                        (scenes.cornell_scene(res=64, counts=(2, 2, 2), rays=32, atlas_res=256, with_atlas=False, cascades=2), (-6.0, -6.0, -6.0), (6.0, 6.0, 6.0))):
@@ -398,9 +398,12 @@ def test_open_space_table_is_conservative(oracle):
         d = rng.normal(size=(n, 3)).astype(np.float32)
         tr["worldDirection"] = d / np.linalg.norm(d, axis=1, keepdims=True)
         tr["maxDistance"], tr["stepScale"] = abi.GLOBAL_SDF_WORLD_SIZE, 1.0
-        st, bits = oracle.open_space_stats(sc.sdf_data, sc.sdf, sc.mip, tr)
-        print(st)
-        assert st["violations"] == 0 and st["mip_taps"] > n
-        assert int(sum(bin(int(w)).count("1") for w in bits)) == st["open_cells"]
-        if sc.name == "city":
-            assert st["open_cells"] > 0.2 * st["cells"] and st["open_steps"] > 0.05 * st["mip_taps"]  # the table is worth something
+        for cell in (8, 4):
+            st, bits = oracle.open_space_stats(sc.sdf_data, sc.sdf, sc.mip, tr, cell=cell)
+            print(sc.name, cell, st)
+            assert st["violations"] == 0 and st["near_violations"] == 0 and st["mip_taps"] > n
+            assert int(sum(bin(int(w)).count("1") for w in bits)) == st["open_cells"]
+            assert st["near_tex_used"] <= st["near_steps"] and st["near_tex_used"] <= st["tex_used"]
+            if sc.name == "city":
+                assert st["open_cells"] > 0.15 * st["cells"] and st["open_steps"] > 0.03 * st["mip_taps"]  # the table is worth something
+                assert st["near_steps"] > 0.3 * st["mip_taps"]
