@@ -56,7 +56,7 @@ struct TraceParams
 };
 
 // optional open-space table over the mip volume (LUX_DDGI_FLAG_OPEN_SKIP): one bit per cell of OPEN_CELL^3 mip texels.  The share of march
-// steps the table proves open barely depends on the cell size (C4, oracle statistics: 12.3 / 12.1 / 11.7 / 10.8 % at 1 / 2 / 4 / 8 texels), so
+// steps the table proves open barely depends on the cell size (C4, CPU-side statistics, DESIGN §11: 12.3 / 12.1 / 11.7 / 10.8 % at 1 / 2 / 4 / 8 texels), so
 // the cell is 8: 4 KiB of table for a 1024^3 volume, small enough to sit in shared memory without shrinking the L1 the gathers live in.
 constexpr int OPEN_CELL = 8;
 struct OpenTableArgs
