@@ -437,3 +437,17 @@ def open_space_stats(sdf_data, sdf, mip, traces, start_bias=0.0, cell=8):
     assert rc == 0, rc
     return dict(zip(("mip_taps", "open_steps", "violations", "open_cells", "cells", "near_steps", "near_violations", "near_tex_used", "tex_used"),
                     (int(x) for x in out))), bits
+
+
+def trace_global_sdf_open_skip(sdf_data, sdf, mip, traces, start_bias=0.0, cell=8):
+    """tracyGlobalSDF with the experimental march's table-driven control flow -> (hits, (mip taps, full-resolution taps) actually taken)."""
+    traces = np.ascontiguousarray(traces, dtype=abi.SDF_TRACE_DTYPE)
+    hits = np.zeros(len(traces), dtype=abi.SDF_HIT_DTYPE)
+    taps = np.zeros(2, dtype=np.uint64)
+    s, m = _np(sdf), _np(mip)
+    L = lib()
+    L.oracle_trace_global_sdf_open_skip.restype = C.c_int
+    L.oracle_trace_global_sdf_open_skip.argtypes = [C.POINTER(abi.GlobalSDFData), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_int]
+    rc = L.oracle_trace_global_sdf_open_skip(C.byref(sdf_data), _ptr(s), _ptr(m), len(traces), _ptr(traces), float(start_bias), _ptr(hits), _ptr(taps), int(cell))
+    assert rc == 0, rc
+    return hits, (int(taps[0]), int(taps[1]))

@@ -267,6 +267,7 @@ struct OpenTable
 struct Scene
 {
     const OpenTable*           open = nullptr;
+    bool                       openEmulate = false; // decide the mip test FROM the table, statement for statement as march_open_kernel does
     LuxDDGIUniform             ddgi;
     LuxGlobalSDFData           sdfData;
     Tex3D                      tex, mip;
@@ -418,6 +419,52 @@ Hit tracyGlobalSDF(const Scene& sc, vec3 origin, vec3 dir, float maxDistance, fl
                                gclamp(posInCascade.z / cascadeMaxDistance + 0.5f, 0.0f, 1.0f)};
             vec3  textureUV = {((float)cascade + cascadeUV.x) / cascadesCountF, cascadeUV.y, cascadeUV.z};
 
+            if (sc.open && sc.openEmulate)
+            { // the experimental march's control flow (march_kernel.inc, MARCH_OPEN_SKIP): same table, same decisions, same taps
+                const OpenTable& ot = *sc.open;
+                const float inv = 1.0f / (float)ot.cell;
+                int cx = std::min((int)((textureUV.x * (float)sc.mip.w) * inv), ot.cw - 1);
+                int cy = std::min((int)((textureUV.y * (float)sc.mip.h) * inv), ot.ch - 1);
+                int cz = std::min((int)((textureUV.z * (float)sc.mip.d) * inv), ot.cd - 1);
+                float d;
+                if (ot.open(cx, cy, cz))
+                    d = chunkSizeDistance;
+                else if (ot.isNear(cx, cy, cz))
+                {
+                    float t = sample3D(sc.tex, textureUV.x, textureUV.y, textureUV.z, &cn.texTaps);
+                    d = t;
+                    if (!(t < chunkMarginDistance * 2.0f))
+                        d = sample3D(sc.mip, textureUV.x, textureUV.y, textureUV.z, &cn.mipTaps);
+                }
+                else
+                {
+                    d = sample3D(sc.mip, textureUV.x, textureUV.y, textureUV.z, &cn.mipTaps);
+                    if (d < chunkSizeDistance)
+                    {
+                        float t = sample3D(sc.tex, textureUV.x, textureUV.y, textureUV.z, &cn.texTaps);
+                        if (t < chunkMarginDistance * 2.0f)
+                            d = t;
+                    }
+                    else
+                        d = chunkSizeDistance;
+                }
+                d *= cascadeMaxDistance;
+                float thick = voxelHalf * gclamp(stepTime / voxelSize, 0.0f, 1.0f);
+                if (d < thick)
+                {
+                    hit.hitTime    = gmax((stepTime + d) - thick, 0.0f);
+                    hit.hitCascade = cascade;
+                    hit.hitSDF     = d;
+                    float o = 1.0f / data.resolution;
+                    float xp = sample3D(sc.tex, textureUV.x + o, textureUV.y, textureUV.z, &cn.texTaps), xn = sample3D(sc.tex, textureUV.x - o, textureUV.y, textureUV.z, &cn.texTaps);
+                    float yp = sample3D(sc.tex, textureUV.x, textureUV.y + o, textureUV.z, &cn.texTaps), yn = sample3D(sc.tex, textureUV.x, textureUV.y - o, textureUV.z, &cn.texTaps);
+                    float zp = sample3D(sc.tex, textureUV.x, textureUV.y, textureUV.z + o, &cn.texTaps), zn = sample3D(sc.tex, textureUV.x, textureUV.y, textureUV.z - o, &cn.texTaps);
+                    hit.hitNormal = normalize3({xp - xn, yp - yn, zp - zn});
+                    break;
+                }
+                stepTime += gmax(d * stepScale, voxelSize);
+                continue;
+            }
             float stepDistance = sample3D(sc.mip, textureUV.x, textureUV.y, textureUV.z, &cn.mipTaps);
             if (sc.open)
             { // the cell the engine would look up: floor(fl(u * W) / 4) per axis, clamped
@@ -1665,6 +1712,44 @@ OpenTable buildOpenTable(const Tex3D& mip, float chunkSizeDistance, int cell = 8
 }
 
 extern "C" {
+// tracyGlobalSDF with the experimental march's table-driven control flow (Scene::openEmulate): hits must equal oracle_trace_global_sdf's bit for bit;
+// tapsOut (optional) = {mip taps, full-resolution taps} actually taken.
+int oracle_trace_global_sdf_open_skip(const LuxGlobalSDFData* sdfData, const uint16_t* sdf, const uint16_t* mip, int count, const LuxGlobalSDFTrace* traces,
+                                      float cascadeTraceStartBias, LuxGlobalSDFHit* hits, uint64_t* tapsOut, int cell)
+{
+    if (!sdfData || !sdf || !mip || count < 0 || (count > 0 && (!traces || !hits)))
+        return -1;
+    Scene sc{};
+    sc.sdfData = *sdfData;
+    const int res = (int)sdfData->resolution, casc = (int)sdfData->cascadesCount;
+    sc.tex = Tex3D{sdf, res * casc, res, res};
+    sc.mip = Tex3D{mip, (res / 4) * casc, res / 4, res / 4};
+    OpenTable table = buildOpenTable(sc.mip, (float)LUX_GLOBAL_SDF_RASTERIZE_CHUNK_SIZE / sdfData->resolution, cell);
+    if (table.bits.empty())
+        return -2;
+    sc.open = &table;
+    sc.openEmulate = true;
+    uint64_t mipTaps = 0, texTaps = 0;
+#pragma omp parallel for schedule(dynamic, 64) reduction(+ : mipTaps, texTaps)
+    for (int k = 0; k < count; k++)
+    {
+        const LuxGlobalSDFTrace& t = traces[k];
+        Counters cn;
+        Hit h = tracyGlobalSDF(sc, {t.worldPosition[0], t.worldPosition[1], t.worldPosition[2]}, {t.worldDirection[0], t.worldDirection[1], t.worldDirection[2]},
+                               t.maxDistance, t.stepScale, cascadeTraceStartBias, cn);
+        LuxGlobalSDFHit& o = hits[k];
+        bool wantN = t.needsHitNormal != 0 && h.hitTime >= 0.0f;
+        o.hitNormal[0] = wantN ? h.hitNormal.x : 0.0f; o.hitNormal[1] = wantN ? h.hitNormal.y : 0.0f; o.hitNormal[2] = wantN ? h.hitNormal.z : 0.0f;
+        o.hitTime = h.hitTime; o.hitCascade = h.hitCascade; o.stepsCount = h.stepsCount; o.hitSDF = h.hitSDF;
+        mipTaps += cn.mipTaps; texTaps += cn.texTaps;
+    }
+    if (tapsOut)
+    {
+        tapsOut[0] = mipTaps; tapsOut[1] = texTaps;
+    }
+    return 0;
+}
+
 // Validation of the open-space table on a ray list: out = {march steps, steps in open cells, violations (open cell but mip tap < chunkSizeDistance,
 // must be 0), open cells, cells, steps in "near" cells, near violations, near steps whose full-resolution tap is the one used, steps that use it}.  bitsOut (optional, ceil(cells / 32) words) receives the table for comparison with the engine's.
 int oracle_open_space_stats(const LuxGlobalSDFData* sdfData, const uint16_t* sdf, const uint16_t* mip, int count, const LuxGlobalSDFTrace* traces,

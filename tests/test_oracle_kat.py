@@ -407,3 +407,13 @@ def test_open_space_table_is_conservative(oracle):
             if sc.name == "city":
                 assert st["open_cells"] > 0.15 * st["cells"] and st["open_steps"] > 0.03 * st["mip_taps"]  # the table is worth something
                 assert st["near_steps"] > 0.3 * st["mip_taps"]
+        # the experimental march's control flow, statement for statement (decisions taken FROM the table): every GlobalSDFHit field is unchanged
+        tr["needsHitNormal"] = 1
+        tr["stepScale"] = rng.choice(np.float32([0.5, 1.0, 2.0]), n)
+        for bias in (0.0, 2.0):
+            want = oracle.trace_global_sdf(sc.sdf_data, sc.sdf, sc.mip, tr, bias)
+            got, (mip_taps, tex_taps) = oracle.trace_global_sdf_open_skip(sc.sdf_data, sc.sdf, sc.mip, tr, bias)
+            for f in abi.SDF_HIT_DTYPE.names:
+                assert np.array_equal(got[f].view(np.uint32), want[f].view(np.uint32)), (sc.name, bias, f)
+            print(sc.name, "bias", bias, "mip taps taken", mip_taps, "of", int(want["stepsCount"].sum() + (want["hitTime"] >= 0).sum()))
+            assert mip_taps < 0.7 * (want["stepsCount"].sum() + (want["hitTime"] >= 0).sum())
