@@ -451,3 +451,16 @@ def trace_global_sdf_open_skip(sdf_data, sdf, mip, traces, start_bias=0.0, cell=
     rc = L.oracle_trace_global_sdf_open_skip(C.byref(sdf_data), _ptr(s), _ptr(m), len(traces), _ptr(traces), float(start_bias), _ptr(hits), _ptr(taps), int(cell))
     assert rc == 0, rc
     return hits, (int(taps[0]), int(taps[1]))
+
+
+def step_classes(sdf_data, sdf, mip, traces, max_steps=96, start_bias=0.0, cell=8):
+    """Per-step class of every ray, uint8 [n][max_steps]: 0 ended, 1 open (no tap), 2 near (full-resolution tap only), 3 near (both taps), 4 undecided (both)."""
+    traces = np.ascontiguousarray(traces, dtype=abi.SDF_TRACE_DTYPE)
+    out = np.zeros((len(traces), max_steps), dtype=np.uint8)
+    s, m = _np(sdf), _np(mip)
+    L = lib()
+    L.oracle_step_classes.restype = C.c_int
+    L.oracle_step_classes.argtypes = [C.POINTER(abi.GlobalSDFData), C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.c_int, C.c_void_p, C.c_int]
+    rc = L.oracle_step_classes(C.byref(sdf_data), _ptr(s), _ptr(m), len(traces), _ptr(traces), float(start_bias), int(max_steps), _ptr(out), int(cell))
+    assert rc == 0, rc
+    return out

@@ -288,6 +288,8 @@ struct Counters
     uint64_t mipTaps = 0, texTaps = 0, hits = 0, tileSamples = 0, steps = 0, objectsVisited = 0;
     uint64_t openSteps = 0, openViolations = 0; // only with Scene::open (validation of the engine's open-space table, see buildOpenTable)
     uint64_t nearSteps = 0, nearViolations = 0, nearTexUsed = 0, texUsed = 0; // statistics for a possible "near" table (mip tap provably < chunkSizeDistance)
+    uint8_t* classOut = nullptr; // optional per-step class trace of one ray: 1 open, 2 near + full-resolution tap used, 3 near + both taps, 4 undecided (both)
+    int      classCap = 0, classN = 0;
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -479,14 +481,21 @@ Hit tracyGlobalSDF(const Scene& sc, vec3 origin, vec3 dir, float maxDistance, fl
                     if (stepDistance < chunkSizeDistance)
                         cn.openViolations++;
                 }
+                uint8_t cls = ot.open(cx, cy, cz) ? 1 : 4;
                 if (ot.isNear(cx, cy, cz))
                 {
                     cn.nearSteps++;
+                    cls = 3;
                     if (!(stepDistance < chunkSizeDistance))
                         cn.nearViolations++;
                     else if (sample3D(sc.tex, textureUV.x, textureUV.y, textureUV.z, nullptr) < chunkMarginDistance * 2.0f)
+                    {
                         cn.nearTexUsed++;
+                        cls = 2;
+                    }
                 }
+                if (cn.classOut && cn.classN < cn.classCap)
+                    cn.classOut[cn.classN++] = cls;
             }
             if (stepDistance < chunkSizeDistance)
             {
@@ -1746,6 +1755,36 @@ int oracle_trace_global_sdf_open_skip(const LuxGlobalSDFData* sdfData, const uin
     if (tapsOut)
     {
         tapsOut[0] = mipTaps; tapsOut[1] = texTaps;
+    }
+    return 0;
+}
+
+// Per-step class trace of every ray (see Counters::classOut), [count][maxSteps] bytes, 0 = the ray has ended: input of the warp-coherence
+// estimate in DESIGN §11 (a SIMT warp pays for a tap as soon as ONE of its lanes needs it).
+int oracle_step_classes(const LuxGlobalSDFData* sdfData, const uint16_t* sdf, const uint16_t* mip, int count, const LuxGlobalSDFTrace* traces,
+                        float cascadeTraceStartBias, int maxSteps, uint8_t* out, int cell)
+{
+    if (!sdfData || !sdf || !mip || count < 0 || (count > 0 && (!traces || !out)) || maxSteps < 1)
+        return -1;
+    Scene sc{};
+    sc.sdfData = *sdfData;
+    const int res = (int)sdfData->resolution, casc = (int)sdfData->cascadesCount;
+    sc.tex = Tex3D{sdf, res * casc, res, res};
+    sc.mip = Tex3D{mip, (res / 4) * casc, res / 4, res / 4};
+    OpenTable table = buildOpenTable(sc.mip, (float)LUX_GLOBAL_SDF_RASTERIZE_CHUNK_SIZE / sdfData->resolution, cell);
+    if (table.bits.empty())
+        return -2;
+    sc.open = &table;
+    std::memset(out, 0, (size_t)count * maxSteps);
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int k = 0; k < count; k++)
+    {
+        const LuxGlobalSDFTrace& t = traces[k];
+        Counters cn;
+        cn.classOut = out + (size_t)k * maxSteps;
+        cn.classCap = maxSteps;
+        tracyGlobalSDF(sc, {t.worldPosition[0], t.worldPosition[1], t.worldPosition[2]}, {t.worldDirection[0], t.worldDirection[1], t.worldDirection[2]},
+                       t.maxDistance, t.stepScale, cascadeTraceStartBias, cn);
     }
     return 0;
 }
