@@ -5,12 +5,16 @@ Purpose: pin the CPU oracle against the reference's own compiled binaries
 DepthBorderUpdate}.comp.spv`).  The interpreter executes the SPIR-V invocation by invocation (workgroups in lock-step at
 OpControlBarrier) on small inputs; `tests/golden/make_spirv_golden.py` stores the results as fixtures.
 
-Scope: exactly the ~75 core opcodes and 16 GLSL.std.450 instructions those five modules use (opcode numbers from the
+It also executes the shipped binaries of the rows either side of the path (`DDGI/SampleProbe.comp`, `SDF/{SDFRasterizeModel,
+SDFRasterizeModelNoRead,GlobalSDFMipmap,SDFCulling,SDFReflection,SDFShadow}.comp` and the fragment shaders `SDF/{SDFDeferredLight,
+SDFAtlasIndirectLight}.frag`, one invocation per fragment with the stage inputs set by the caller): tests/golden/make_spirv_golden_*.py.
+
+Scope: exactly the ~80 core opcodes and 18 GLSL.std.450 instructions those fourteen modules use (opcode numbers from the
 public SPIR-V 1.5 specification).  Anything else raises NotImplementedError.
 
 Numerics: binary32 via numpy.float32 scalars, one rounding per SPIR-V instruction, NO contraction.  Operations whose
 precision Vulkan leaves to the implementation follow the repo's numerics contract: sin/cos/pow through
-binary64, normalize = v * (1/sqrt(dot)), MatrixInverse = cofactor expansion, FMin/FMax/FClamp select-based, texture
+binary64, normalize = v * (1/sqrt(dot)), MatrixInverse = cofactor expansion, Cross / Reflect with every product and sum rounded, FMin/FMax/FClamp select-based, texture
 filtering with fp32 weights and nested lerps, image stores RTNE to fp16.
 """
 from __future__ import annotations
