@@ -309,3 +309,24 @@ def test_fuzz_oracle_vs_shipped_spirv(oracle):
 
     configs, rays, bad = fz.run(seed=7, seconds=60.0, max_configs=12, verbose=False)
     assert configs == 12 and rays > 1000 and bad == 0
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/Assets/shaders/spv/DDGI/DepthProbeUpdate.comp.spv"), reason="needs the reference's shipped SPIR-V (build container only)")
+def test_fuzz_blend_vs_shipped_spirv(oracle):
+    """A bounded slice of tests/golden/fuzz_blend_vs_spirv.py: random volume parameters, ray buffers (zero / large radiance, misses, weights under the
+    gate), previous atlases, first and later frames against the shipped {Irradiance,Depth}{ProbeUpdate,BorderUpdate}.comp.spv executed live: bit for bit
+    in `unfused` mode (literal and hoisted formulation), within 1 fp16 ulp in the contract's FMA mode, borders bit for bit."""
+    from tests.golden import fuzz_blend_vs_spirv as fz
+
+    configs, values, bad = fz.run(seed=11, seconds=120.0, max_configs=3, verbose=False)
+    assert configs == 3 and values > 3000 and bad == 0
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/Assets/shaders/spv/SDF/SDFReflection.comp.spv"), reason="needs the reference's shipped SPIR-V (build container only)")
+def test_fuzz_screen_shaders_vs_shipped_spirv(oracle):
+    """A bounded slice of tests/golden/fuzz_screen_vs_spirv.py: SDFReflection / SDFShadow executed live on random G-buffers (normals at the +z pole,
+    roughness on the 0.05 / 0.45 thresholds), noise textures, frame numbers and lights; the oracle's image / words are bit-identical."""
+    from tests.golden import fuzz_screen_vs_spirv as fz
+
+    configs, px, bad = fz.run(seed=5, seconds=60.0, max_configs=3, verbose=False)
+    assert configs == 3 and bad == 0
