@@ -330,3 +330,13 @@ def test_fuzz_screen_shaders_vs_shipped_spirv(oracle):
 
     configs, px, bad = fz.run(seed=5, seconds=60.0, max_configs=3, verbose=False)
     assert configs == 3 and bad == 0
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/Assets/shaders/spv/SDF/SDFDeferredLight.frag.spv"), reason="needs the reference's shipped SPIR-V (build container only)")
+def test_fuzz_surface_lighting_vs_shipped_spirv(oracle):
+    """A bounded slice of tests/golden/fuzz_light_vs_spirv.py: SDFDeferredLight.frag / SDFAtlasIndirectLight.frag executed live per fragment with random
+    lights (all three types), cameras, shadow biases and G-buffer values; the oracle's light-cache values are bit-identical."""
+    from tests.golden import fuzz_light_vs_spirv as fz
+
+    configs, texels, bad = fz.run(seed=9, seconds=60.0, max_configs=6, verbose=False)
+    assert configs == 6 and bad == 0
