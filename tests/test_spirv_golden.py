@@ -340,3 +340,13 @@ def test_fuzz_surface_lighting_vs_shipped_spirv(oracle):
 
     configs, texels, bad = fz.run(seed=9, seconds=60.0, max_configs=6, verbose=False)
     assert configs == 6 and bad == 0
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/Assets/shaders/spv/DDGI/SampleProbe.comp.spv"), reason="needs the reference's shipped SPIR-V (build container only)")
+def test_fuzz_sample_probe_vs_shipped_spirv(oracle):
+    """A bounded slice of tests/golden/fuzz_consumer_vs_spirv.py: SampleProbe.comp.spv executed live with a random camera (possibly outside the probe
+    volume), random depths / normals / normalBias and atlases of random fp16 values; the oracle's RGBA32F image is bit-identical."""
+    from tests.golden import fuzz_consumer_vs_spirv as fz
+
+    configs, px, bad = fz.run(seed=4, seconds=60.0, max_configs=1, verbose=False)
+    assert configs == 1 and px == 256 and bad == 0
