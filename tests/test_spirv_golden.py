@@ -350,3 +350,13 @@ def test_fuzz_sample_probe_vs_shipped_spirv(oracle):
 
     configs, px, bad = fz.run(seed=4, seconds=60.0, max_configs=1, verbose=False)
     assert configs == 1 and px == 256 and bad == 0
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/Assets/shaders/spv/SDF/SDFCulling.comp.spv"), reason="needs the reference's shipped SPIR-V (build container only)")
+def test_fuzz_culling_vs_shipped_spirv(oracle):
+    """A bounded slice of tests/golden/fuzz_culling_vs_spirv.py: SDFCulling.comp.spv executed live on random object buffers, chunk sizes, capacities and
+    workgroup subsets; the oracle in the same execution order reproduces chunk and cull buffers word for word."""
+    from tests.golden import fuzz_culling_vs_spirv as fz
+
+    configs, lists, bad = fz.run(seed=3, seconds=60.0, max_configs=25, verbose=False)
+    assert configs == 25 and lists > 200 and bad == 0
