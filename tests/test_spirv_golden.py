@@ -360,3 +360,13 @@ def test_fuzz_culling_vs_shipped_spirv(oracle):
 
     configs, lists, bad = fz.run(seed=3, seconds=60.0, max_configs=25, verbose=False)
     assert configs == 25 and lists > 200 and bad == 0
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/Assets/shaders/spv/SDF/SDFRasterizeModel.comp.spv"), reason="needs the reference's shipped SPIR-V (build container only)")
+def test_fuzz_sdf_build_vs_shipped_spirv(oracle):
+    """A bounded slice of tests/golden/fuzz_sdfbuild_vs_spirv.py: SDFRasterizeModelNoRead / SDFRasterizeModel / GlobalSDFMipmap executed live on random mesh
+    distance fields, cascades, model splits, workgroups and mip inputs; every voxel the binaries wrote is reproduced bit for bit."""
+    from tests.golden import fuzz_sdfbuild_vs_spirv as fz
+
+    configs, touched, bad = fz.run(seed=6, seconds=60.0, max_configs=5, verbose=False)
+    assert configs == 5 and touched > 1000 and bad == 0
