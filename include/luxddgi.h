@@ -248,10 +248,9 @@ enum {
     LUX_DDGI_FLAG_TRACE_SIMPLE  = 1u << 4, /* one-thread-per-ray trace kernel (no wavefront scheduling), for A/B */
     LUX_DDGI_FLAG_NO_PREFILTER  = 1u << 5, /* walk the full per-chunk object lists (no sub-cell candidate masks), for A/B */
     LUX_DDGI_FLAG_SHADE_UNSORTED= 1u << 6, /* shade hits in ray order instead of culling-chunk order (no counting sort), for A/B */
-    LUX_DDGI_FLAG_NO_PIPELINE   = 1u << 7, /* lux_ddgi_update runs the shard as one batch on one stream (no two-stream batch pipelining), for A/B */
-    LUX_DDGI_FLAG_OPEN_SKIP     = 1u << 8  /* EXPERIMENTAL, off by default: the wavefront march consults a conservative table over the mip volume (two bits per 8x8x8
-                                            * mip texels) and skips the mip tap where its comparison with chunkSizeDistance is provable; results are unchanged.
-                                            * Compiled only with -DLUX_EXPERIMENTAL_OPEN_SKIP (otherwise lux_ddgi_create returns LUX_ERR_UNSUPPORTED) */
+    LUX_DDGI_FLAG_NO_PIPELINE   = 1u << 7, /* lux_ddgi_update computes the blend weights on the context's stream instead of a second one, for A/B */
+    LUX_DDGI_FLAG_MARCH_PROBE_MAJOR = 1u << 8 /* wavefront march in the round-1 work order (probe groups outermost, ray ids as they come) instead of direction
+                                            * clusters outermost over spatially tiled probe groups; same results, for A/B of the DRAM traffic */
 };
 
 typedef struct LuxDDGICreateInfo {

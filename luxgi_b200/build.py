@@ -36,22 +36,6 @@ def needs_build():
     return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
 
 
-LIB_EXPERIMENTAL = os.path.join(HERE, "libluxddgi_experimental.so")
-
-
-def build_experimental(verbose=False):
-    """The same library with the opt-in kernels compiled in (-DLUX_EXPERIMENTAL_OPEN_SKIP), next to the measured build; load it with
-    LUX_DDGI_LIB=<path>.  Kept apart because a second instantiation of the march perturbs ptxas' code for the shipped kernel."""
-    global LIB
-    shipped, LIB = LIB, LIB_EXPERIMENTAL
-    os.environ["LUX_BUILD_EXPERIMENTAL"] = "1"
-    try:
-        return build(force=True, verbose=verbose)
-    finally:
-        LIB = shipped
-        del os.environ["LUX_BUILD_EXPERIMENTAL"]
-
-
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
@@ -59,13 +43,11 @@ def build(force=False, verbose=False):
     env.pop("CXX", None)  # the image exports a g++ wrapper nvcc does not need
     env.pop("CC", None)
     flags = list(NVCC_FLAGS)
-    if os.environ.get("LUX_BUILD_EXPERIMENTAL"):  # opt-in kernels that are not part of the measured build (LUX_DDGI_FLAG_OPEN_SKIP)
-        flags += ["-DLUX_EXPERIMENTAL_OPEN_SKIP"]
     cmd = [nvcc(), "-shared", "-o", LIB] + flags + ["-x", "cu"] + [os.path.join(CSRC, f) for f in SOURCES]
     cmd += ["-ccbin", "/usr/bin/g++"] if os.path.exists("/usr/bin/g++") else []
     res = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     log = res.stdout
-    with open(os.path.join(HERE, "build.log" if LIB != LIB_EXPERIMENTAL else "build_experimental.log"), "w") as f:
+    with open(os.path.join(HERE, "build.log"), "w") as f:
         f.write(" ".join(cmd) + "\n" + log)
     if res.returncode != 0:
         sys.stderr.write(log)
@@ -76,7 +58,4 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    if "--experimental" in sys.argv:
-        print(build_experimental(verbose=True))
-    else:
-        print(build(force="--force" in sys.argv, verbose=True))
+    print(build(force="--force" in sys.argv, verbose=True))

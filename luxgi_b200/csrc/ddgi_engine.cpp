@@ -90,13 +90,11 @@ struct LuxDDGIContext
     // per-frame tables
     DeviceBuffer dirs, wIrr, wDepth, scaleIrr, scaleDepth, nzIrr, nzDepth;
     DeviceBuffer origins, records, meta, chunkCounter; // wavefront trace scratch
-    DeviceBuffer sortTicket, binCounts, binBlockSums, sortedIdx; // sorted shade scratch (hit counts live in chunkCounter[2b+1])
+    DeviceBuffer sortTicket, binCounts, binBlockSums, sortedIdx; // sorted shade scratch (the hit count lives in chunkCounter[1])
     DeviceBuffer dirsHalf;                                       // [R] fp16 directions for the blend weights (pipelined update)
+    DeviceBuffer pgOrder, pgIndex, rayOrder, raySlot;            // march order tables (init::marchOrder)
+    int          probeGroups = 0, rayClusters = 0;
 
-    // Probe batches of lux_ddgi_update: each batch runs march -> shade -> blend on one of two streams, so that the tail of one
-    // batch's kernels (a few long rays, a last partial wave) overlaps the bulk of the next batch's.
-    struct Batch { int probeStart, probeCount; size_t recordStart, binStart, blockStart; };
-    std::vector<Batch> batches;
     cudaStream_t auxStream = nullptr;
     cudaEvent_t  evFork = nullptr, evJoin = nullptr, evWeights = nullptr;
 
@@ -104,8 +102,6 @@ struct LuxDDGIContext
     bool             hasSdf = false;
     LuxGlobalSDFData sdfData{};
     DeviceBuffer     sdf, mip;
-    DeviceBuffer     openBits;          // LUX_DDGI_FLAG_OPEN_SKIP: open-space table of the mip volume, rebuilt lazily when the volume changes
-    bool             openDirty = true;
     cudaArray_t         sdfArray = nullptr, mipArray = nullptr;
     cudaTextureObject_t sdfTex = 0, mipTex = 0;
 
@@ -271,6 +267,100 @@ static int validate(const LuxDDGIUniform& u)
     return LUX_OK;
 }
 
+// Work order of the wavefront march (csrc/march_kernel.inc): which probe group and which ray directions the k-th chunk holds.  Any order gives
+// the same results (every ray is independent); this one makes the rays in flight a narrow beam from a compact block of probes:
+//  * probe groups (32 consecutive probe ids = a run along x) are visited tile by tile: tiles of 32 x 16 x 16 probes in Morton order of the tile
+//    coordinates, groups inside a tile by (z, y);
+//  * ray ids are clustered by direction: the un-rotated spherical-Fibonacci directions (DDGICommon.glsl:42-52) are sorted along a Hilbert curve
+//    over their octahedral image, and every run of MARCH_CLUSTER_RAYS slots of that order is one cluster.  The per-frame rotation is rigid, so the
+//    clusters stay clusters.  (Consecutive Fibonacci indices are 137.5 degrees apart in azimuth: the id order itself is as incoherent as it gets.)
+static uint32_t hilbertIndex(uint32_t n, uint32_t x, uint32_t y)
+{
+    uint32_t d = 0;
+    for (uint32_t s = n / 2; s > 0; s /= 2)
+    {
+        const uint32_t rx = (x & s) ? 1u : 0u, ry = (y & s) ? 1u : 0u;
+        d += s * s * ((3u * rx) ^ ry);
+        if (!ry)
+        {
+            if (rx)
+            {
+                x = n - 1 - x;
+                y = n - 1 - y;
+            }
+            std::swap(x, y);
+        }
+    }
+    return d;
+}
+static uint32_t spread3(uint32_t v) // 10 bits -> every third bit
+{
+    v &= 0x3ffu;
+    v = (v | (v << 16)) & 0x030000ffu;
+    v = (v | (v << 8)) & 0x0300f00fu;
+    v = (v | (v << 4)) & 0x030c30c3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+static int marchOrder(LuxDDGIContext& c)
+{
+    const LuxDDGIUniform& u = c.uniform;
+    const int X = u.probeCounts[0], Y = u.probeCounts[1];
+    const int PG = (c.probeCount + 31) / 32;
+    const int R = u.raysPerProbe, slots = (R + lux::MARCH_CLUSTER_RAYS - 1) / lux::MARCH_CLUSTER_RAYS * lux::MARCH_CLUSTER_RAYS;
+    const bool identity = (c.flags & LUX_DDGI_FLAG_MARCH_PROBE_MAJOR) != 0; // the round-1 order: ids as they come, probe groups outermost
+    std::vector<uint32_t> order(PG), index(PG);
+    std::vector<std::pair<uint64_t, uint32_t>> keyed(PG);
+    for (int g = 0; g < PG; g++)
+    {
+        const int id = g * 32, x = id % X, y = (id / X) % Y, z = id / (X * Y); // first probe of the group, shard-local
+        const uint64_t tile = spread3((uint32_t)(x / 32)) | (spread3((uint32_t)(y / 16)) << 1) | ((uint64_t)spread3((uint32_t)(z / 16)) << 2);
+        const uint64_t in = ((uint64_t)(z % 16) << 16) | ((uint64_t)(y % 16) << 8) | (uint64_t)(x % 32);
+        keyed[g] = {identity ? (uint64_t)g : ((tile << 24) | in), (uint32_t)g};
+    }
+    std::sort(keyed.begin(), keyed.end());
+    for (int i = 0; i < PG; i++)
+    {
+        order[i]               = keyed[i].second;
+        index[keyed[i].second] = (uint32_t)i;
+    }
+    std::vector<uint16_t> rayOrder(slots), raySlot(slots);
+    std::vector<std::pair<uint32_t, uint16_t>> rk(R);
+    for (int i = 0; i < R; i++)
+    {
+        const double ab = i * 0.6180339887498949, phi = 6.283185307179586 * (ab - std::floor(ab));
+        const double ct = 1.0 - (2.0 * i + 1.0) / R, st = std::sqrt(std::max(0.0, 1.0 - ct * ct));
+        double x = std::cos(phi) * st, y = std::sin(phi) * st, z = ct;
+        const double n = std::fabs(x) + std::fabs(y) + std::fabs(z);
+        x /= n; y /= n;
+        if (z < 0.0)
+        { // fold the lower hemisphere outwards (octahedral map)
+            const double fx = (1.0 - std::fabs(y)) * (x >= 0.0 ? 1.0 : -1.0), fy = (1.0 - std::fabs(x)) * (y >= 0.0 ? 1.0 : -1.0);
+            x = fx; y = fy;
+        }
+        const uint32_t N = 1024;
+        const uint32_t qx = (uint32_t)std::min<double>(N - 1, std::max(0.0, (x * 0.5 + 0.5) * N)), qy = (uint32_t)std::min<double>(N - 1, std::max(0.0, (y * 0.5 + 0.5) * N));
+        rk[i] = {identity ? (uint32_t)i : hilbertIndex(N, qx, qy), (uint16_t)i};
+    }
+    std::sort(rk.begin(), rk.end());
+    for (int s = 0; s < slots; s++)
+        rayOrder[s] = (uint16_t)(s < R ? rk[s].second : s); // padding slots keep ids >= R: never traced
+    for (int s = 0; s < slots; s++)
+        raySlot[rayOrder[s]] = (uint16_t)s;
+    int rc;
+    if ((rc = allocZero(c, c.pgOrder, (size_t)PG * sizeof(uint32_t))) != LUX_OK) return rc;
+    if ((rc = allocZero(c, c.pgIndex, (size_t)PG * sizeof(uint32_t))) != LUX_OK) return rc;
+    if ((rc = allocZero(c, c.rayOrder, (size_t)slots * sizeof(uint16_t))) != LUX_OK) return rc;
+    if ((rc = allocZero(c, c.raySlot, (size_t)slots * sizeof(uint16_t))) != LUX_OK) return rc;
+    LUX_CUDA(cudaMemcpy(c.pgOrder.ptr, order.data(), (size_t)PG * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    LUX_CUDA(cudaMemcpy(c.pgIndex.ptr, index.data(), (size_t)PG * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    LUX_CUDA(cudaMemcpy(c.rayOrder.ptr, rayOrder.data(), (size_t)slots * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    LUX_CUDA(cudaMemcpy(c.raySlot.ptr, raySlot.data(), (size_t)slots * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    c.probeGroups = PG;
+    c.rayClusters = slots / lux::MARCH_CLUSTER_RAYS;
+    return LUX_OK;
+}
+
 // init::initializeProbeGrid, DDGIRenderer.cpp:163-211.  The reference caps probes at int16 max (:169); this engine does not.
 static int initializeProbeGrid(LuxDDGIContext& c)
 {
@@ -301,45 +391,16 @@ static int initializeProbeGrid(LuxDDGIContext& c)
         const size_t nrec = lux::trace_record_count(c.probeCount, u.raysPerProbe);
         if ((rc = allocZero(c, c.records, nrec * sizeof(float4))) != LUX_OK) return rc;
         if ((rc = allocZero(c, c.meta, nrec * sizeof(uint32_t))) != LUX_OK) return rc;
-        // Batch plan.  Measured on B200 (C4, profiles/README): splitting a shard into probe batches that alternate between two streams
-        // does NOT pay off - each batch's kernels lose more to their own ramp-up / drain than the overlap wins back (8 batches: 9.2 ms
-        // vs 7.9 ms serial; 2 batches of a 1/8 shard: no change) - so the default is one batch.  LUX_DDGI_BATCH_RAYS=<rays per batch>
-        // keeps the batched form available for experiments and for the parity test that pins it.
-        const size_t rays = (size_t)c.probeCount * u.raysPerProbe;
-        int nb = 1;
-        if (const char* e = getenv("LUX_DDGI_BATCH_RAYS"))
-            nb = (int)std::min<size_t>(8, std::max<size_t>(1, rays / std::max<size_t>(1024, (size_t)atoll(e))));
-        if (c.flags & (LUX_DDGI_FLAG_STAGE_TIMERS | LUX_DDGI_FLAG_UNFUSED_BORDER | LUX_DDGI_FLAG_NO_PIPELINE))
-            nb = 1;
-        const int perBatch = ((c.probeCount + nb - 1) / nb + 31) / 32 * 32;
-        c.batches.clear();
-        size_t bins = 0, blocks = 0;
-        for (int p0 = 0; p0 < c.probeCount; p0 += perBatch)
-        {
-            LuxDDGIContext::Batch b{};
-            b.probeStart  = p0;
-            b.probeCount  = std::min(perBatch, c.probeCount - p0);
-            b.recordStart = lux::trace_record_count(p0, u.raysPerProbe);
-            b.binStart    = bins;
-            b.blockStart  = blocks;
-            bins += lux::trace_sort_bins(b.probeCount, u.raysPerProbe);
-            blocks += lux::trace_sort_blocks(b.probeCount, u.raysPerProbe);
-            c.batches.push_back(b);
-        }
-        bins   = std::max(bins, lux::trace_sort_bins(c.probeCount, u.raysPerProbe)); // the staged API shades the shard as one batch
-        blocks = std::max(blocks, lux::trace_sort_blocks(c.probeCount, u.raysPerProbe));
         if (!(c.flags & LUX_DDGI_FLAG_SHADE_UNSORTED) && nrec < (size_t(1) << 30) /* record index + 2 cascade bits in one u32 */)
         {
             if ((rc = allocZero(c, c.sortTicket, nrec * sizeof(uint2))) != LUX_OK) return rc;
+            // padding records (probe lanes / ray slots beyond the volume) are never marched, so nothing ever writes their ticket: "not a hit" once, here
+            LUX_CUDA(cudaMemsetAsync(c.sortTicket.ptr, 0xff, nrec * sizeof(uint2), c.stream));
             if ((rc = allocZero(c, c.sortedIdx, nrec * sizeof(uint32_t))) != LUX_OK) return rc;
-            if ((rc = allocZero(c, c.binCounts, bins * sizeof(uint32_t))) != LUX_OK) return rc;
-            if ((rc = allocZero(c, c.binBlockSums, blocks * sizeof(uint32_t))) != LUX_OK) return rc;
+            if ((rc = allocZero(c, c.binCounts, lux::trace_sort_bins() * sizeof(uint32_t))) != LUX_OK) return rc;
+            if ((rc = allocZero(c, c.binBlockSums, lux::trace_sort_blocks() * sizeof(uint32_t))) != LUX_OK) return rc;
         }
-    }
-    else
-    {
-        c.batches.clear();
-        c.batches.push_back(LuxDDGIContext::Batch{0, c.probeCount, 0, 0, 0});
+        if ((rc = marchOrder(c)) != LUX_OK) return rc;
     }
     if ((rc = allocZero(c, c.dirsHalf, (size_t)u.raysPerProbe * sizeof(uint2))) != LUX_OK) return rc;
     c.frames      = 0;
@@ -412,22 +473,6 @@ static int setup(LuxDDGIContext& c, const LuxTracePushConstants& push)
         LUX_CUDA(cudaGetLastError());
         c.masksDirty = false;
     }
-    if ((c.flags & LUX_DDGI_FLAG_OPEN_SKIP) && !(c.flags & LUX_DDGI_FLAG_TRACE_SIMPLE) && c.openDirty)
-    { // open-space table of the mip volume (experimental march variant); volumes whose mip side is not a multiple of the cell run without it
-        const int mres = (int)c.sdfData.resolution / 4, mw = mres * (int)c.sdfData.cascadesCount;
-        c.openBits.release();
-        if (mres >= OPEN_CELL && mres % OPEN_CELL == 0)
-        {
-            const size_t cells = (size_t)(mw / OPEN_CELL) * (mres / OPEN_CELL) * (mres / OPEN_CELL), bytes = 2 * ((cells + 31) / 32) * 4; // open + near bits
-            LUX_CUDA(cudaMalloc(&c.openBits.ptr, bytes));
-            c.openBits.bytes = bytes;
-            const float chunkSizeDistance = (float)LUX_GLOBAL_SDF_RASTERIZE_CHUNK_SIZE / c.sdfData.resolution;
-            lux::launch_open_table(c.mip.ptr, mw, mres, mres, chunkSizeDistance, (uint32_t*)c.openBits.ptr, c.stream);
-            c.launches += 1;
-            LUX_CUDA(cudaGetLastError());
-        }
-        c.openDirty = false;
-    }
     mark(c, 0);
     launch_ray_dirs(push.randomOrientation, u.raysPerProbe, (float4*)c.dirs.ptr, (uint2*)c.dirsHalf.ptr, c.stream);
     c.launches += 1;
@@ -435,15 +480,11 @@ static int setup(LuxDDGIContext& c, const LuxTracePushConstants& push)
     return LUX_OK;
 }
 
-// The trace kernels of one probe batch (the whole shard when called through the staged API) on stream `s`.
-static int launchBatch(LuxDDGIContext& c, const LuxDDGIContext::Batch& b, int batchIndex, cudaStream_t s, bool timers)
+// The trace kernels of the shard on stream `s`.
+static int launch(LuxDDGIContext& c, cudaStream_t s, bool timers)
 {
-    const LuxDDGIUniform& u = c.uniform;
     TraceParams p{};
     fillVolume(c, p);
-    p.probeBegin   = c.probeBegin + b.probeStart;
-    p.probeCount   = b.probeCount;
-    p.origins      = (const float4*)c.origins.ptr + b.probeStart;
     p.sdf          = c.sdfData;
     p.tex          = (const uint16_t*)c.sdf.ptr;
     p.mip          = (const uint16_t*)c.mip.ptr;
@@ -468,31 +509,34 @@ static int launchBatch(LuxDDGIContext& c, const LuxDDGIContext::Batch& b, int ba
         p.light         = (const uint2*)c.light.ptr;
         p.depth         = (const float*)c.atlasDepth.ptr;
     }
-    const size_t rayStart = (size_t)b.probeStart * u.raysPerProbe;
     p.skyFace  = c.skyFace;
     p.sky      = (const uint2*)c.sky.ptr;
-    OpenTableArgs open{};
-    if ((c.flags & LUX_DDGI_FLAG_OPEN_SKIP) && c.openBits.ptr)
-        open = OpenTableArgs{(const uint32_t*)c.openBits.ptr, p.mipRes * p.cascades / OPEN_CELL, p.mipRes / OPEN_CELL, p.mipRes / OPEN_CELL};
     p.dirs     = (const float4*)c.dirs.ptr;
-    p.radiance = (uint2*)c.radiance.ptr + rayStart;
-    p.dirDist  = (uint2*)c.directionDepth.ptr + rayStart;
+    p.radiance = (uint2*)c.radiance.ptr;
+    p.dirDist  = (uint2*)c.directionDepth.ptr;
     p.steps    = nullptr;
-    p.records  = c.records.ptr ? (float4*)c.records.ptr + b.recordStart : nullptr;
-    p.meta     = c.meta.ptr ? (uint32_t*)c.meta.ptr + b.recordStart : nullptr;
-    unsigned int* counters = (unsigned int*)c.chunkCounter.ptr + 2 * batchIndex; // [0] march chunk counter, [1] hit count
+    p.records  = (float4*)c.records.ptr;
+    p.meta     = (uint32_t*)c.meta.ptr;
+    p.pgOrder  = (const uint32_t*)c.pgOrder.ptr;
+    p.pgIndex  = (const uint32_t*)c.pgIndex.ptr;
+    p.rayOrder = (const uint16_t*)c.rayOrder.ptr;
+    p.raySlot  = (const uint16_t*)c.raySlot.ptr;
+    p.probeGroups = c.probeGroups;
+    p.rayClusters = c.rayClusters;
+    p.probeMajor  = (c.flags & LUX_DDGI_FLAG_MARCH_PROBE_MAJOR) ? 1 : 0;
+    unsigned int* counters = (unsigned int*)c.chunkCounter.ptr; // [0] march chunk counter, [1] hit count
     if (c.sortedIdx.ptr)
     {
         p.invChunkSize = c.hasAtlas ? 1.0f / c.atlasData.chunkSize : 0.0f;
-        p.sortTicket   = (uint2*)c.sortTicket.ptr + b.recordStart;
-        p.binCounts    = (uint32_t*)c.binCounts.ptr + b.binStart;
-        p.binBlockSums = (uint32_t*)c.binBlockSums.ptr + b.blockStart;
+        p.sortTicket   = (uint2*)c.sortTicket.ptr;
+        p.binCounts    = (uint32_t*)c.binCounts.ptr;
+        p.binBlockSums = (uint32_t*)c.binBlockSums.ptr;
         p.hitCount     = counters + 1;
-        p.sortedIdx    = (uint32_t*)c.sortedIdx.ptr + b.recordStart;
+        p.sortedIdx    = (uint32_t*)c.sortedIdx.ptr;
     }
     const int variant = (c.flags & LUX_DDGI_FLAG_TRACE_SIMPLE) ? 0 : (c.sdfTex ? 2 : 1);
     c.launches += launch_trace(p, variant, counters, s, c.lightPending ? c.evLightReady : nullptr,
-                               (timers && (c.flags & LUX_DDGI_FLAG_STAGE_TIMERS)) ? c.ev[5] : nullptr, open.bits ? &open : nullptr);
+                               (timers && (c.flags & LUX_DDGI_FLAG_STAGE_TIMERS)) ? c.ev[5] : nullptr);
     return LUX_OK;
 }
 
@@ -502,8 +546,7 @@ static int system(LuxDDGIContext& c, const LuxTracePushConstants& push)
     int rc = setup(c, push);
     if (rc != LUX_OK)
         return rc;
-    const LuxDDGIContext::Batch whole{0, c.probeCount, 0, 0, 0};
-    launchBatch(c, whole, 0, c.stream, true);
+    launch(c, c.stream, true);
     c.lightPending = false;
     cudaEventRecord(c.evShadeDone, c.stream);
     mark(c, 2);
@@ -524,15 +567,14 @@ static void weights(LuxDDGIContext& c, const uint2* dirsHalf, cudaStream_t s)
                                        (float*)c.scaleIrr.ptr, (float*)c.scaleDepth.ptr, (uint32_t*)c.nzIrr.ptr, (uint32_t*)c.nzDepth.ptr, s);
 }
 
-// Blend (+ fused border) of one probe batch on stream `s`; records evIrr / evDepth after the respective kernel when given.
-static void launchBatch(LuxDDGIContext& c, const LuxDDGIContext::Batch& b, cudaStream_t s, cudaEvent_t evIrr, cudaEvent_t evDepth)
+// Blend (+ fused border) of the shard on stream `s`; records evIrr / evDepth after the respective kernel when given.
+static void launch(LuxDDGIContext& c, cudaStream_t s, cudaEvent_t evIrr, cudaEvent_t evDepth)
 {
     const LuxDDGIUniform& u = c.uniform;
     const int    writeIdx = 1 - c.pingPong;
-    const size_t rayStart = (size_t)b.probeStart * u.raysPerProbe;
     BlendParams p{};
-    p.probeBegin   = c.probeBegin + b.probeStart;
-    p.probeCount   = b.probeCount;
+    p.probeBegin   = c.probeBegin;
+    p.probeCount   = c.probeCount;
     p.raysPerProbe = u.raysPerProbe;
     p.raysPadded   = c.raysPadded;
     p.probesPerRow = u.probeCounts[0] * u.probeCounts[1];
@@ -543,8 +585,8 @@ static void launchBatch(LuxDDGIContext& c, const LuxDDGIContext::Batch& b, cudaS
     p.maxDistance  = u.maxDistance;
     p.firstFrame   = (c.frames == 0) ? 1 : 0; // DDGIRenderer.cpp:362
     p.fuseBorder   = (c.flags & LUX_DDGI_FLAG_UNFUSED_BORDER) ? 0 : 1;
-    p.radiance     = (const uint2*)c.radiance.ptr + rayStart;
-    p.dirDist      = (const uint2*)c.directionDepth.ptr + rayStart;
+    p.radiance     = (const uint2*)c.radiance.ptr;
+    p.dirDist      = (const uint2*)c.directionDepth.ptr;
     p.wIrr         = (const float*)c.wIrr.ptr;
     p.wDepth       = (const float*)c.wDepth.ptr;
     p.scaleIrr     = (const float*)c.scaleIrr.ptr;
@@ -573,8 +615,7 @@ static int system(LuxDDGIContext& c)
     cudaStreamWaitEvent(c.stream, c.evCopyDone, 0); // row downloads of earlier frames must have left the atlases
     if (c.gatherPending[1 - c.pingPong])               // ... and so must the all-gather that last read / wrote this pair
         cudaStreamWaitEvent(c.stream, c.evGather[1 - c.pingPong], 0);
-    const LuxDDGIContext::Batch whole{0, c.probeCount, 0, 0, 0};
-    launchBatch(c, whole, c.stream, c.evIrrDone, c.evDepthDone);
+    launch(c, c.stream, c.evIrrDone, c.evDepthDone);
     mark(c, 3);
     LUX_CUDA(cudaGetLastError());
     c.lastWritten = 1 - c.pingPong;
@@ -708,8 +749,6 @@ int lux_ddgi_create(const LuxDDGIUniform* uniform, const LuxDDGICreateInfo* info
     if (prop.major != 10)
         return fail(LUX_ERR_NO_DEVICE, "device %d is sm_%d%d; this build contains sm_100a code only", ci.device, prop.major, prop.minor);
     LUX_CUDA(cudaSetDevice(ci.device));
-    if ((ci.flags & LUX_DDGI_FLAG_OPEN_SKIP) && !lux::open_skip_compiled())
-        return fail(LUX_ERR_UNSUPPORTED, "LUX_DDGI_FLAG_OPEN_SKIP needs a library built with -DLUX_EXPERIMENTAL_OPEN_SKIP (LUX_BUILD_EXPERIMENTAL=1 python -m luxgi_b200.build --force)");
 
     LuxDDGIContext* c = new (std::nothrow) LuxDDGIContext();
     if (!c)
@@ -845,7 +884,6 @@ static int bindSdfTextures(LuxDDGIContext* c, const LuxGlobalSDFData* data)
     c->sdfData    = *data;
     c->hasSdf     = true;
     c->masksDirty = true;
-    c->openDirty  = true;
     return LUX_OK;
 }
 
@@ -1499,7 +1537,7 @@ int lux_ddgi_update(LuxDDGIContext* c, const float orientation[16])
     push.intensity       = 1.0f;
     if (!(c->flags & (LUX_DDGI_FLAG_STAGE_TIMERS | LUX_DDGI_FLAG_UNFUSED_BORDER | LUX_DDGI_FLAG_NO_PIPELINE | LUX_DDGI_FLAG_TRACE_SIMPLE)))
     { // Shipped form of the update.  The blend weights depend on the frame's ray directions only, so they are computed on the
-      // auxiliary stream while the march runs; probe batches (normally one) alternate between the two streams.
+      // auxiliary stream while the march runs.
         int rc = trace_rays::setup(*c, push);
         if (rc != LUX_OK)
             return rc;
@@ -1507,29 +1545,14 @@ int lux_ddgi_update(LuxDDGIContext* c, const float orientation[16])
         cudaStreamWaitEvent(c->auxStream, c->evFork, 0);
         probe_update::weights(*c, (const uint2*)c->dirsHalf.ptr, c->auxStream);
         cudaEventRecord(c->evWeights, c->auxStream);
-        const bool single = c->batches.size() == 1; // then the copy engine may start on each output as soon as its kernel is done
-        for (size_t b = 0; b < c->batches.size(); b++)
-        {
-            cudaStream_t s = (b & 1) ? c->auxStream : c->stream;
-            trace_rays::launchBatch(*c, c->batches[b], (int)b, s, false);
-            if (single)
-                cudaEventRecord(c->evShadeDone, s);
-            if (s == c->stream && b == 0)
-                cudaStreamWaitEvent(s, c->evWeights, 0);
-            cudaStreamWaitEvent(s, c->evCopyDone, 0); // only the blend overwrites atlas rows an earlier frame's download may still read
-            if (c->gatherPending[1 - c->pingPong])     // ... or the all-gather of two frames ago
-                cudaStreamWaitEvent(s, c->evGather[1 - c->pingPong], 0);
-            probe_update::launchBatch(*c, c->batches[b], s, single ? c->evIrrDone : nullptr, single ? c->evDepthDone : nullptr);
-        }
-        cudaEventRecord(c->evJoin, c->auxStream);
-        cudaStreamWaitEvent(c->stream, c->evJoin, 0);
+        trace_rays::launch(*c, c->stream, false);
+        cudaEventRecord(c->evShadeDone, c->stream); // the copy engine may start on each output as soon as its kernel is done
+        cudaStreamWaitEvent(c->stream, c->evWeights, 0);
+        cudaStreamWaitEvent(c->stream, c->evCopyDone, 0); // only the blend overwrites atlas rows an earlier frame's download may still read
+        if (c->gatherPending[1 - c->pingPong])            // ... or the all-gather of two frames ago
+            cudaStreamWaitEvent(c->stream, c->evGather[1 - c->pingPong], 0);
+        probe_update::launch(*c, c->stream, c->evIrrDone, c->evDepthDone);
         c->lightPending = false;
-        if (!single)
-        {
-            cudaEventRecord(c->evShadeDone, c->stream);
-            cudaEventRecord(c->evIrrDone, c->stream);
-            cudaEventRecord(c->evDepthDone, c->stream);
-        }
         LUX_CUDA(cudaGetLastError());
         c->raysValid   = true;
         c->lastWritten = 1 - c->pingPong;

@@ -11,6 +11,7 @@
 //
 // Compiled with -fmad=false; see ddgi_math.cuh for the numerics contract.
 #include <cstdlib>
+#include <cstring>
 
 #include "ddgi_kernels.h"
 #include "ddgi_math.cuh"
@@ -1050,7 +1051,7 @@ __device__ __forceinline__ f3 probe_origin(const TraceParams& P, int probeId)
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int MARCH_WARPS       = 8;
 #ifndef MARCH_BLOCKS_PER_SM
-#define MARCH_BLOCKS_PER_SM 5 // 48 registers, 40 warps per SM: measured 3.59 -> 3.50 ms on C4 (6 blocks spill and lose)
+#define MARCH_BLOCKS_PER_SM 4 // 64 registers, 32 warps per SM: with 48 (5 blocks) ptxas serialises the two taps of a step to save registers (SASS inspected)
 #endif
 #ifndef SHADE_BLOCKS_PER_SM
 #define SHADE_BLOCKS_PER_SM 5
@@ -1062,16 +1063,40 @@ constexpr int MARCH_REFILL_MIN  = 8;                                       // re
 
 enum RayKind : uint32_t { RAY_MISS = 0, RAY_INSIDE = 1, RAY_HIT = 2 };
 
-#define MARCH_OPEN_SKIP 0
+// Bin of a hit position.  Only groups work, never enters a result: plain (approximate) arithmetic is fine.
+__device__ __forceinline__ uint32_t shade_bin(const TraceParams& P, f3 pos)
+{
+    const int   N    = LUX_SURFACE_ATLAS_CHUNKS_RESOLUTION;
+    const float half = (float)N * 0.5f, inv = P.invChunkSize;
+    float fx = pos.x * inv + half, fy = pos.y * inv + half, fz = pos.z * inv + half;
+    float gx = floorf(fx), gy = floorf(fy), gz = floorf(fz);
+    int cx = iclamp((int)gx, 0, N - 1), cy = iclamp((int)gy, 0, N - 1), cz = iclamp((int)gz, 0, N - 1);
+    int oct = ((fz - gz) >= 0.5f ? 4 : 0) | ((fy - gy) >= 0.5f ? 2 : 0) | ((fx - gx) >= 0.5f ? 1 : 0);
+    return (uint32_t)(((cz * N + cy) * N + cx) * 8 + oct);
+}
+
+// MARCH ORDER.  Chunk c (64 records: 2 ray slots x 32 probe lanes) <-> (probe group, first ray slot); record index = c * 64 + j * 32 + lane.
+// Everything downstream of the march (classify, scatter, shade) addresses records through these two functions.
+struct MarchChunk { uint32_t probeGroup, slot0; };
+__device__ __forceinline__ MarchChunk march_chunk(const TraceParams& P, unsigned int c)
+{
+    const unsigned int perPair = MARCH_CLUSTER_RAYS / 2;
+    const unsigned int pair = c % perPair, q = c / perPair;
+    unsigned int cluster, pgIdx;
+    if (P.probeMajor) { cluster = q % (unsigned)P.rayClusters; pgIdx = q / (unsigned)P.rayClusters; }
+    else              { pgIdx = q % (unsigned)P.probeGroups; cluster = q / (unsigned)P.probeGroups; }
+    return {__ldg(P.pgOrder + pgIdx), cluster * MARCH_CLUSTER_RAYS + pair * 2};
+}
+// record index of (probe group, ray id, probe lane)
+__device__ __forceinline__ uint32_t march_record(const TraceParams& P, uint32_t probeGroup, uint32_t rayId, uint32_t lane)
+{
+    const unsigned int slot = __ldg(P.raySlot + rayId), cluster = slot / MARCH_CLUSTER_RAYS, k = slot % MARCH_CLUSTER_RAYS;
+    const unsigned int pgIdx = __ldg(P.pgIndex + probeGroup);
+    const unsigned int q = P.probeMajor ? pgIdx * (unsigned)P.rayClusters + cluster : cluster * (unsigned)P.probeGroups + pgIdx;
+    return ((q * (MARCH_CLUSTER_RAYS / 2) + (k >> 1)) * 2 + (k & 1)) * 32 + lane;
+}
+
 #include "march_kernel.inc"
-#undef MARCH_OPEN_SKIP
-#ifdef LUX_EXPERIMENTAL_OPEN_SKIP // a second instantiation of the march perturbs ptxas' register allocation of the shipped one (1024 -> 1016
-                                  // SASS instructions, different spills), so the experimental variant is compiled only on request (build.py)
-#define MARCH_OPEN_SKIP 1
-#define MARCH_OPEN_SMEM_WORDS 8192u
-#include "march_kernel.inc"
-#undef MARCH_OPEN_SKIP
-#endif
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Stage 2: SHADE.  One thread per ray record, in the same [32 probes] x [8 rays] tiling as the simple kernel, so a warp
@@ -1089,10 +1114,10 @@ __global__ void __launch_bounds__(256, SHADE_BLOCKS_PER_SM) shade_kernel(const _
     // block b covers half a unit: unit = b / 2, rays (b & 1) * 8 .. + 8 of the unit's 16
     const long long unit = blockIdx.x >> 1;
     const int rayInUnit  = ((blockIdx.x & 1) << 3) + sub;
-    const long long g    = unit * UNIT_RAYS + rayInUnit * 32 + lane;
     const int probeLocal = (int)(unit / rayGroups) * 32 + lane;
     const int rayId      = (int)(unit % rayGroups) * TW_RAYS_PER_UNIT + rayInUnit;
     const bool valid     = probeLocal < P.probeCount && rayId < P.raysPerProbe;
+    const uint32_t g     = valid ? march_record(P, (uint32_t)(unit / rayGroups), (uint32_t)rayId, (uint32_t)lane) : 0u;
     const SdfSampler<TEX> sdf(P);
     const LuxGlobalSDFData& data = P.sdf;
 
@@ -1150,41 +1175,29 @@ __global__ void __launch_bounds__(256, SHADE_BLOCKS_PER_SM) shade_kernel(const _
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Stage 2, sorted form (default): CLASSIFY -> SCAN -> SCATTER -> SHADE_SORTED.
+// Stage 2, sorted form (default): CLASSIFY, SCAN -> SCATTER -> SHADE_SORTED.
 //
 // In ray order a warp holds hits of 32 parallel rays from a 240-voxel-long row of probes: they fall into ~12 different
 // culling chunks, so the surface-cache loops ran with 13-17 of 32 lanes (ncu, profiles/r1_v5_*).  The sorted form bins every
-// hit by (output window, culling chunk, chunk octant) with a counting sort and shades in bin order: the lanes of a warp then
-// walk the SAME culled object list with the same prefilter mask and mostly the same tiles.  Per-ray arithmetic is untouched
-// (each ray's result depends on no other ray), so results stay bit-identical to the ray-order kernel.
-//   classify      one thread per record, ray-order tiling of the old shade kernel: writes direction+distance for every ray and
-//                 the final radiance of misses / inside rays (coalesced 64-byte row segments); hits take a ticket in their bin
-//   scan          exclusive prefix sum over the bins (3 small kernels)
-//   scatter       sortedIdx[prefix[bin] + ticket] = record index
+// hit by (culling chunk, chunk octant) with a counting sort and shades in bin order: the lanes of a warp then walk the SAME
+// culled object list with the same prefilter mask and mostly the same tiles, and the whole pass reads each part of the SDF
+// shell and of the surface-cache atlases once (one sweep over the scene; round 1 keyed the sort by 4 M-record output windows
+// first and swept the scene once per window: 105 GB of DRAM traffic on C5).  Per-ray arithmetic is untouched (each ray's
+// result depends on no other ray), so results stay bit-identical to the ray-order kernel.
+//   march         every hit takes a ticket in its bin when its record is written (one returning atomic, hidden by the march)
+//   classify      one thread per record, ray-order tiling: writes direction+distance for every ray and the final radiance of
+//                 misses / inside rays (coalesced 128-byte row segments)
+//   scan          exclusive prefix sum over the 512 000 bins (3 small kernels)
+//   scatter       sortedIdx[prefix[bin] + ticket] = record index; streams the tickets in march order, in which the hits of a bin
+//                 that were ticketed together also sit together, so the 4-byte stores of a sector meet in L2
 //   shade_sorted  persistent grid over the sorted hit list: normal (6 taps) + surface cache; 8-byte radiance store per hit.
-// The leading "window" part of the key (2^22 records = 32 MiB of radiance) keeps those scattered stores inside an
-// L2-resident range, so sectors are merged in L2 before they reach HBM.
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int SORT_WINDOW_SHIFT     = 22;
-constexpr int SORT_BINS_PER_WINDOW  = LUX_SURFACE_ATLAS_CHUNKS_RESOLUTION * LUX_SURFACE_ATLAS_CHUNKS_RESOLUTION * LUX_SURFACE_ATLAS_CHUNKS_RESOLUTION * 8;
+constexpr int SORT_BINS             = LUX_SURFACE_ATLAS_CHUNKS_RESOLUTION * LUX_SURFACE_ATLAS_CHUNKS_RESOLUTION * LUX_SURFACE_ATLAS_CHUNKS_RESOLUTION * 8;
 constexpr int SCAN_THREADS          = 1024;
 constexpr int SCAN_BINS_PER_BLOCK   = SCAN_THREADS * 4;
 
-// Bin of a hit position.  Only groups work, never enters a result: plain (approximate) arithmetic is fine.
-__device__ __forceinline__ uint32_t shade_bin(const TraceParams& P, f3 pos)
-{
-    const int   N    = LUX_SURFACE_ATLAS_CHUNKS_RESOLUTION;
-    const float half = (float)N * 0.5f, inv = P.invChunkSize;
-    float fx = pos.x * inv + half, fy = pos.y * inv + half, fz = pos.z * inv + half;
-    float gx = floorf(fx), gy = floorf(fy), gz = floorf(fz);
-    int cx = iclamp((int)gx, 0, N - 1), cy = iclamp((int)gy, 0, N - 1), cz = iclamp((int)gz, 0, N - 1);
-    int oct = ((fz - gz) >= 0.5f ? 4 : 0) | ((fy - gy) >= 0.5f ? 2 : 0) | ((fx - gx) >= 0.5f ? 1 : 0);
-    return (uint32_t)(((cz * N + cy) * N + cx) * 8 + oct);
-}
-
-// One block = one unit (16 ray slots x 32 probes); each of the 128 threads owns CLASSIFY_RPT records of the same probe lane
-// and issues all their loads, then all their tickets, before the first use: the pass is a latency chain
-// (record -> bin -> returning atomic) per record, so memory-level parallelism per thread is what makes it stream.
+// One block = 16 consecutive ray ids x 32 probes of one group; each of the 128 threads owns CLASSIFY_RPT records of the same probe lane and issues
+// all their loads before the first use.  A pure streaming pass since the march takes the sort tickets: 20 bytes in, 16 bytes out per ray.
 constexpr int CLASSIFY_RPT = 4;
 __global__ void __launch_bounds__(128, 12) classify_kernel(const __grid_constant__ TraceParams P, int rayGroups)
 {
@@ -1193,7 +1206,8 @@ __global__ void __launch_bounds__(128, 12) classify_kernel(const __grid_constant
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long unit = blockIdx.x;
-    const int probeLocal = (int)(unit / rayGroups) * 32 + lane;
+    const uint32_t probeGroup = (uint32_t)(unit / rayGroups);
+    const int probeLocal = (int)probeGroup * 32 + lane;
     const int rayBase    = (int)(unit % rayGroups) * TW_RAYS_PER_UNIT;
     const LuxGlobalSDFData& data = P.sdf;
     const bool probeValid = probeLocal < P.probeCount;
@@ -1202,42 +1216,26 @@ __global__ void __launch_bounds__(128, 12) classify_kernel(const __grid_constant
     uint32_t meta[CLASSIFY_RPT];
     float4   d4[CLASSIFY_RPT];
     bool     valid[CLASSIFY_RPT];
-    float4   o4 = probeValid ? __ldg(P.origins + probeLocal) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 #pragma unroll
     for (int k = 0; k < CLASSIFY_RPT; k++)
     {
-        const int rayInUnit = warp + k * 4;
-        const long long g   = unit * UNIT_RAYS + rayInUnit * 32 + lane;
-        valid[k] = probeValid && rayBase + rayInUnit < P.raysPerProbe;
-        rec[k]   = valid[k] ? __ldg(P.records + g) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        meta[k]  = valid[k] ? __ldg(P.meta + g) : 0u;
-        d4[k]    = valid[k] ? __ldg(P.dirs + rayBase + rayInUnit) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-    }
-    uint2 ticket[CLASSIFY_RPT];
-#pragma unroll
-    for (int k = 0; k < CLASSIFY_RPT; k++)
-    {
-        const long long g = unit * UNIT_RAYS + (warp + k * 4) * 32 + lane;
-        ticket[k] = make_uint2(0xffffffffu, 0u);
-        if (valid[k] && ((meta[k] >> 2) & 3u) == RAY_HIT && P.hasAtlas)
-        { // rgb comes from shade_sorted_kernel
-            f3 o = {o4.x, o4.y, o4.z}, d = {d4[k].x, d4[k].y, d4[k].z};
-            uint32_t bin = (uint32_t)(g >> SORT_WINDOW_SHIFT) * (uint32_t)SORT_BINS_PER_WINDOW + shade_bin(P, o + d * rec[k].x);
-            // the hit cascade rides in the two top bits of the ticket (and of the sorted index), so the shade never re-reads `meta`
-            ticket[k] = make_uint2(bin, atomicAdd(P.binCounts + bin, 1u) | ((meta[k] & 3u) << 30));
-        }
+        const int rayId = rayBase + warp + k * 4;
+        valid[k] = probeValid && rayId < P.raysPerProbe;
+        const uint32_t g = valid[k] ? march_record(P, probeGroup, (uint32_t)rayId, (uint32_t)lane) : 0u;
+        rec[k]   = valid[k] ? __ldcs(P.records + g) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        meta[k]  = valid[k] ? __ldcs(P.meta + g) : 0u;
+        d4[k]    = valid[k] ? __ldg(P.dirs + rayId) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
 #pragma unroll
     for (int k = 0; k < CLASSIFY_RPT; k++)
     {
         const int rayInUnit = warp + k * 4;
-        const long long g   = unit * UNIT_RAYS + rayInUnit * 32 + lane;
         if (valid[k])
         {
             const uint32_t hc = meta[k] & 3u, kind = (meta[k] >> 2) & 3u;
             f3 d = {d4[k].x, d4[k].y, d4[k].z};
             f4 radiance;
-            if (kind == RAY_HIT)
+            if (kind == RAY_HIT) // rgb comes from the shade kernel (zero without a surface cache)
                 radiance = {0.0f, 0.0f, 0.0f, gmax(rec[k].x + data.cascadeVoxelSize[hc] * 0.5f, 0.0f)};
             else if (kind == RAY_INSIDE)
                 radiance = {0.0f, 0.0f, 0.0f, LUX_GLOBAL_SDF_WORLD_SIZE};
@@ -1253,7 +1251,6 @@ __global__ void __launch_bounds__(128, 12) classify_kernel(const __grid_constant
             if (P.steps)
                 P.steps[(size_t)probeLocal * P.raysPerProbe + rayBase + rayInUnit] = (uint16_t)(meta[k] >> 4);
         }
-        P.sortTicket[g] = ticket[k];
     }
     __syncthreads();
     // transposed write-out: 16 consecutive rays (128 bytes) per probe
@@ -1262,7 +1259,7 @@ __global__ void __launch_bounds__(128, 12) classify_kernel(const __grid_constant
     {
         const int idx = threadIdx.x + k * 128;
         const int pl = idx / TW_RAYS_PER_UNIT, rl = idx % TW_RAYS_PER_UNIT;
-        const int oProbe = (int)(unit / rayGroups) * 32 + pl;
+        const int oProbe = (int)probeGroup * 32 + pl;
         const int oRay   = rayBase + rl;
         if (oProbe < P.probeCount && oRay < P.raysPerProbe)
         {
@@ -1352,7 +1349,7 @@ __global__ void __launch_bounds__(256) scatter_kernel(const uint2* __restrict__ 
     size_t g = (size_t)blockIdx.x * 256 + threadIdx.x;
     if (g >= records)
         return;
-    uint2 t = __ldg(ticket + g);
+    uint2 t = __ldcs(ticket + g);
     if (t.x != 0xffffffffu)
         sortedIdx[__ldg(prefix + t.x) + (t.y & 0x3fffffffu)] = (uint32_t)g | (t.y & 0xc0000000u);
 }
@@ -1369,9 +1366,9 @@ __global__ void __launch_bounds__(256, SHADE_BLOCKS_PER_SM) shade_sorted_kernel(
     {
         const uint32_t gi   = __ldg(P.sortedIdx + t);
         const uint32_t g    = gi & 0x3fffffffu, hc = gi >> 30;
-        const uint32_t unit = g / UNIT_RAYS, rem = g % UNIT_RAYS;
-        const int probeLocal = (int)(unit / rayGroups) * 32 + (int)(rem & 31u);
-        const int rayId      = (int)(unit % rayGroups) * TW_RAYS_PER_UNIT + (int)(rem >> 5);
+        const MarchChunk mc  = march_chunk(P, g >> 6);
+        const int probeLocal = (int)mc.probeGroup * 32 + (int)(g & 31u);
+        const int rayId      = (int)__ldg(P.rayOrder + mc.slot0 + ((g >> 5) & 1u));
         const float4   rec = __ldg(P.records + g);
         float4 d4 = __ldg(P.dirs + rayId);
         float4 o4 = __ldg(P.origins + probeLocal);
@@ -1729,135 +1726,6 @@ __global__ void __launch_bounds__(512) blend_depth_kernel(const __grid_constant_
     }
 }
 
-// Depth, resident form (used whenever the probes' distances fit in shared memory: R <= ~780 at 64 probes per block,
-// <= ~1560 at 32).  ncu on the chunked kernel showed the sparsity win being eaten by the per-chunk block barriers: within a
-// 32-ray chunk some warp always owns a fully live texel row, so every chunk costs its densest warp.  Here the block loads
-// the distances of ALL rays once, synchronises once, and then each warp walks its own live-ray list over the whole ray
-// range without any further block-wide barrier; weights come straight from L1/L2 (one broadcast float4 pair per texel
-// group, prefetched one live ray ahead).  Lane l owns probes l and l+32 (conflict-free column reads of D[p][R+1]).
-template <int PB>
-__global__ void __launch_bounds__(512) blend_depth_resident_kernel(const __grid_constant__ BlendParams P)
-{
-    constexpr int N = 256, NT = 512, NP = PB / 32, M = 2 * PB; // NP probes per lane
-    extern __shared__ __align__(16) float smem[];
-    const int R = P.raysPerProbe, RS = P.raysPadded + 1; // odd row stride: column reads hit 32 distinct banks
-    float* D  = smem;  // [PB][RS] d = min(maxDistance, dist - 0.01)
-    float* Cs = smem;  // epilogue overlay [M][N]
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int probe0 = blockIdx.x * PB;
-
-    for (int idx = tid; idx < PB * P.raysPadded; idx += NT)
-    {
-        int   p = idx / P.raysPadded, k = idx % P.raysPadded; // consecutive threads -> consecutive rays (coalesced, conflict-free)
-        float d = 0.0f;
-        if (probe0 + p < P.probeCount && k < R)
-        {
-            uint2 t = __ldg(P.dirDist + (size_t)(probe0 + p) * R + k);
-            d = gmin(P.maxDistance, h2f_bits((uint16_t)(t.y >> 16)) - 0.01f); // ProbeUpdate.glsl:75
-            if (d == -1.0f)
-                d = P.maxDistance;
-        }
-        D[p * RS + k] = d;
-    }
-    __syncthreads();
-
-    float acc[2][2 * NP][8];
-#pragma unroll
-    for (int g = 0; g < 2; g++)
-#pragma unroll
-        for (int i = 0; i < 2 * NP; i++)
-#pragma unroll
-            for (int j = 0; j < 8; j++)
-                acc[g][i][j] = 0.0f;
-
-    const float4* W4 = reinterpret_cast<const float4*>(P.wDepth) + warp * 4; // this warp's 16 weights of ray k: W4[k*64 .. +3]
-    float4 w[4], wn[4];
-    for (int k0 = 0; k0 < P.raysPadded; k0 += 32)
-    {
-        const uint32_t zl   = (__ldg(P.nzDepth + k0 + lane) >> (warp * 2)) & 3u;
-        uint32_t       live = __ballot_sync(0xffffffffu, zl != 0u);
-        if (!live)
-            continue;
-        int k = k0 + __ffs(live) - 1;
-        live &= live - 1;
-#pragma unroll
-        for (int q = 0; q < 4; q++)
-            w[q] = __ldg(W4 + (size_t)k * 64 + q);
-        while (true)
-        {
-            int kn = -1;
-            if (live)
-            { // prefetch the next live ray's weights while this one is accumulated
-                kn = k0 + __ffs(live) - 1;
-                live &= live - 1;
-#pragma unroll
-                for (int q = 0; q < 4; q++)
-                    wn[q] = __ldg(W4 + (size_t)kn * 64 + q);
-            }
-            float a[2 * NP];
-#pragma unroll
-            for (int i = 0; i < NP; i++)
-            {
-                float d      = D[(lane + 32 * i) * RS + k];
-                a[2 * i]     = d;
-                a[2 * i + 1] = d * d;
-            }
-            const float b[2][8] = {{w[0].x, w[0].y, w[0].z, w[0].w, w[1].x, w[1].y, w[1].z, w[1].w},
-                                   {w[2].x, w[2].y, w[2].z, w[2].w, w[3].x, w[3].y, w[3].z, w[3].w}};
-            // the warp's two blocks are horizontal neighbours (an 8x2-texel patch): mostly live together, so no per-block branch
-#pragma unroll
-            for (int g = 0; g < 2; g++)
-#pragma unroll
-                for (int i = 0; i < 2 * NP; i++)
-#pragma unroll
-                    for (int j = 0; j < 8; j++)
-                        acc[g][i][j] = __fmaf_rn(a[i], b[g][j], acc[g][i][j]);
-            if (kn < 0)
-                break;
-            k = kn;
-#pragma unroll
-            for (int q = 0; q < 4; q++)
-                w[q] = wn[q];
-        }
-    }
-    __syncthreads(); // every warp is done reading D before the epilogue overlays it
-
-#pragma unroll
-    for (int g = 0; g < 2; g++)
-#pragma unroll
-        for (int i = 0; i < 2 * NP; i++)
-        {
-            const int row = (lane + 32 * (i >> 1)) * 2 + (i & 1); // m = probe*2 + {d, d*d}
-            float4* dst = reinterpret_cast<float4*>(Cs + row * N + (warp * 2 + g) * 8);
-            dst[0] = make_float4(acc[g][i][0], acc[g][i][1], acc[g][i][2], acc[g][i][3]);
-            dst[1] = make_float4(acc[g][i][4], acc[g][i][5], acc[g][i][6], acc[g][i][7]);
-        }
-    __syncthreads();
-
-    for (int idx = tid; idx < PB * N; idx += NT)
-    {
-        int p = idx / N, t = idx % N;
-        int probeLocal = probe0 + p;
-        if (probeLocal >= P.probeCount)
-            continue;
-        int   probe = P.probeBegin + probeLocal;
-        int i, j; // column t of the weight matrix -> texel (i, j)
-        depth_texel_of_column(t, i, j);
-        float s = __ldg(P.scaleDepth + (j * 16 + i));
-        float r = Cs[(p * 2 + 0) * N + t] * s, g = Cs[(p * 2 + 1) * N + t] * s;
-        int bx = (probe % P.probesPerRow) * 18 + 1, by = (probe / P.probesPerRow) * 18 + 1;
-        if (!P.firstFrame)
-        {
-            uint32_t pv = __ldg(P.prevDepth + (size_t)(by + j + 1) * P.depthWidth + (bx + i + 1));
-            r = mixh(r, h2f_bits((uint16_t)(pv & 0xffffu)), P.hysteresis);
-            g = mixh(g, h2f_bits((uint16_t)(pv >> 16)), P.hysteresis);
-        }
-        uint32_t o = (uint32_t)f2h_bits(r) | ((uint32_t)f2h_bits(g) << 16);
-        store_with_border<uint32_t>(P.outDepth, P.depthWidth, bx, by, 16, i, j, o, P.fuseBorder != 0);
-    }
-    (void)M;
-}
 
 // Standalone border pass (BorderUpdate.glsl:136-156): one warp-sized group of threads per probe and atlas.
 template <typename T, int SIDE>
@@ -2798,61 +2666,6 @@ void launch_l2_sweep(const void* buf, size_t bytes, int blocks, uint32_t* sink, 
     l2_sweep_kernel<<<blocks, 256, 0, s>>>((const uint4*)buf, (unsigned int)(bytes / 16), sink);
 }
 
-bool open_skip_compiled()
-{
-#ifdef LUX_EXPERIMENTAL_OPEN_SKIP
-    return true;
-#else
-    return false;
-#endif
-}
-
-#ifdef LUX_EXPERIMENTAL_OPEN_SKIP
-// Open-space table (LUX_DDGI_FLAG_OPEN_SKIP), two bit arrays of `words` words each over cells of OPEN_CELL^3 mip texels:
-//   open bit of cell c = every mip texel in [OPEN_CELL * c - 1, OPEN_CELL * c + OPEN_CELL]^3 (clamped to the volume, i.e. every texel a trilinear tap
-//                        placed anywhere in the cell can touch, cascade seams included) is >= chunkSizeDistance * (1 + 2^-10);
-//   near bit           = every such texel is < chunkSizeDistance * (1 - 2^-10).
-// Three nested fp32 lerps of values in [-1, 1] stay within 1e-6 of the convex combination, far inside the margins, so a set bit decides the
-// reference's `stepDistance < chunkSizeDistance` test without the tap.  One thread per cell, one ballot per 32 consecutive cells.
-__global__ void __launch_bounds__(256) open_table_kernel(const uint16_t* __restrict__ mip, int W, int H, int D, float chunkSizeDistance, uint32_t* __restrict__ bits,
-                                                         unsigned int words)
-{
-    const int cw = W / OPEN_CELL, ch = H / OPEN_CELL, cd = D / OPEN_CELL;
-    const unsigned int cells = (unsigned int)cw * ch * cd;
-    const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const float hi = chunkSizeDistance * (1.0f + 0.0009765625f), lo = chunkSizeDistance * (1.0f - 0.0009765625f);
-    bool open = false, nearAll = false;
-    if (i < cells)
-    {
-        const int cx = (int)(i % cw), cy = (int)((i / cw) % ch), cz = (int)(i / ((unsigned int)cw * ch));
-        open = nearAll = true;
-        for (int z = max(OPEN_CELL * cz - 1, 0); z <= min(OPEN_CELL * cz + OPEN_CELL, D - 1) && (open || nearAll); z++)
-            for (int y = max(OPEN_CELL * cy - 1, 0); y <= min(OPEN_CELL * cy + OPEN_CELL, H - 1) && (open || nearAll); y++)
-                for (int x = max(OPEN_CELL * cx - 1, 0); x <= min(OPEN_CELL * cx + OPEN_CELL, W - 1); x++)
-                {
-                    const float v = h2f_bits(__ldg(mip + ((size_t)z * H + y) * W + x));
-                    open    = open && (v >= hi);
-                    nearAll = nearAll && (v < lo);
-                }
-    }
-    const uint32_t openWord = __ballot_sync(0xffffffffu, open), nearWord = __ballot_sync(0xffffffffu, nearAll);
-    if ((threadIdx.x & 31) == 0 && (i >> 5) < words)
-    {
-        bits[i >> 5]         = openWord;
-        bits[words + (i >> 5)] = nearWord;
-    }
-}
-
-void launch_open_table(const void* mipR16F, int mipW, int mipH, int mipD, float chunkSizeDistance, uint32_t* bits, cudaStream_t s)
-{
-    const unsigned int cells = (unsigned int)(mipW / OPEN_CELL) * (mipH / OPEN_CELL) * (mipD / OPEN_CELL), words = (cells + 31) / 32;
-    if (cells)
-        open_table_kernel<<<words * 32 / 256 + 1, 256, 0, s>>>((const uint16_t*)mipR16F, mipW, mipH, mipD, chunkSizeDistance, bits, words);
-}
-#else
-void launch_open_table(const void*, int, int, int, float, uint32_t*, cudaStream_t) {}
-#endif
-
 void launch_direct_light(const TraceParams& p, bool useTextures, const LuxLight& l, const float* cameraPosBias, void* light, int count,
                          const uint32_t* texel, const float* P, const float* N, const float* albedo, const float* metallicRoughness, cudaStream_t s)
 {
@@ -2957,23 +2770,15 @@ void launch_probe_origins(const TraceParams& p, cudaStream_t s)
     probe_origins_kernel<<<(p.probeCount + 255) / 256, 256, 0, s>>>(p, const_cast<float4*>(p.origins));
 }
 
-size_t trace_sort_bins(int probeCount, int raysPerProbe)
-{
-    const size_t records = trace_record_count(probeCount, raysPerProbe);
-    const size_t windows = (records + (size_t(1) << SORT_WINDOW_SHIFT) - 1) >> SORT_WINDOW_SHIFT;
-    const size_t bins    = windows * SORT_BINS_PER_WINDOW;
-    return (bins + SCAN_BINS_PER_BLOCK - 1) / SCAN_BINS_PER_BLOCK * SCAN_BINS_PER_BLOCK;
-}
-size_t trace_sort_blocks(int probeCount, int raysPerProbe) { return trace_sort_bins(probeCount, raysPerProbe) / SCAN_BINS_PER_BLOCK; }
+size_t trace_sort_bins() { return ((size_t)SORT_BINS + SCAN_BINS_PER_BLOCK - 1) / SCAN_BINS_PER_BLOCK * SCAN_BINS_PER_BLOCK; }
+size_t trace_sort_blocks() { return trace_sort_bins() / SCAN_BINS_PER_BLOCK; }
 
-// classify -> scan -> scatter -> shade_sorted (see the comment above classify_kernel); returns the number of launches
+// classify, scan -> scatter -> shade_sorted (see the comment above classify_kernel); returns the number of launches
 template <bool TEX>
 static int launch_shade_sorted(const TraceParams& p, int rayGroups, long long units, cudaStream_t s)
 {
     const size_t records = (size_t)units * UNIT_RAYS;
-    const size_t bins    = trace_sort_bins(p.probeCount, p.raysPerProbe);
-    const int    nb      = (int)(bins / SCAN_BINS_PER_BLOCK);
-    cudaMemsetAsync(p.binCounts, 0, bins * sizeof(uint32_t), s);
+    const int    nb      = (int)trace_sort_blocks();
     classify_kernel<<<(unsigned)units, 128, 0, s>>>(p, rayGroups);
     if (!p.hasAtlas)
         return 1; // hits carry no radiance without a surface cache: classify wrote the final values
@@ -2988,7 +2793,66 @@ static int launch_shade_sorted(const TraceParams& p, int rayGroups, long long un
     return 6;
 }
 
-int launch_trace(const TraceParams& p, int variant, unsigned int* chunkCounter, cudaStream_t s, cudaEvent_t beforeShade, cudaEvent_t afterMarch, const OpenTableArgs* open)
+// x / d as ExactDivisor does it on the device: the reciprocal when d is a power of two (then x * (1/d) is the correctly rounded quotient), else 0
+static float exact_reciprocal(float d)
+{
+    uint32_t b;
+    memcpy(&b, &d, 4);
+    const uint32_t e = (b >> 23) & 0xffu;
+    return (((b & 0x7fffffu) == 0u) && e > 2u && e < 252u) ? 1.0f / d : 0.0f;
+}
+// TraceParams::mc (host float arithmetic is IEEE binary32 here: no contraction, no extended precision; see build.py)
+static void march_consts(TraceParams& p)
+{
+    const LuxGlobalSDFData& d = p.sdf;
+    TraceParams::MarchConsts& m = p.mc;
+    const float last2 = d.cascadePosDistance[d.cascadesCount - 1][3] * 2.0f;
+    m.traceMaxDistance     = last2 < LUX_GLOBAL_SDF_WORLD_SIZE ? last2 : LUX_GLOBAL_SDF_WORLD_SIZE; // gmin(WORLD_SIZE, last2)
+    m.chunkSizeDistance    = (float)LUX_GLOBAL_SDF_RASTERIZE_CHUNK_SIZE / d.resolution;
+    m.chunkMarginDistance2 = ((float)LUX_GLOBAL_SDF_RASTERIZE_CHUNK_MARGIN / d.resolution) * 2.0f;
+    m.cascadesCountF       = (float)d.cascadesCount;
+    m.cascadesInv          = exact_reciprocal(m.cascadesCountF);
+    m.mipW = (float)(p.mipRes * p.cascades); m.mipH = (float)p.mipRes;
+    m.texW = (float)(p.res * p.cascades);    m.texH = (float)p.res;
+    m.mipDm1 = p.mipRes - 1; m.texDm1 = p.res - 1;
+    for (int i = 0; i < 3; i++)
+        m.cc0[i] = d.cascadePosDistance[0][i];
+    m.cd0 = d.cascadePosDistance[0][3];
+    m.m0 = m.cd0 * 2.0f; m.minv0 = exact_reciprocal(m.m0);
+    m.v0 = d.cascadeVoxelSize[0]; m.vinv0 = exact_reciprocal(m.v0);
+}
+
+template <bool TEX>
+static int launch_wavefront(const TraceParams& pIn, unsigned int* chunkCounter, cudaStream_t s, cudaEvent_t beforeShade, cudaEvent_t afterMarch)
+{
+    TraceParams p = pIn;
+    march_consts(p);
+    const int rayGroups   = (p.raysPerProbe + TW_RAYS_PER_UNIT - 1) / TW_RAYS_PER_UNIT;
+    const int probeGroups = (p.probeCount + 31) / 32;
+    const long long units = (long long)rayGroups * probeGroups;
+    const int chunks      = (int)(units * (UNIT_RAYS / MARCH_CHUNK_RAYS));
+    cudaMemsetAsync(chunkCounter, 0, sizeof(unsigned int), s);
+    if (p.sortTicket)
+        cudaMemsetAsync(p.binCounts, 0, trace_sort_bins() * sizeof(uint32_t), s);
+    long long blocks = ((long long)chunks + MARCH_WARPS - 1) / MARCH_WARPS;
+    const long long persistent = 148ll * MARCH_BLOCKS_PER_SM; // one resident generation of 8-warp blocks per SM
+    if (blocks > persistent)
+        blocks = persistent;
+    if (p.cascades > 1)
+        march_kernel<TEX, true><<<(unsigned)blocks, 32 * MARCH_WARPS, 0, s>>>(p, chunks, chunkCounter);
+    else
+        march_kernel<TEX, false><<<(unsigned)blocks, 32 * MARCH_WARPS, 0, s>>>(p, chunks, chunkCounter);
+    if (afterMarch)
+        cudaEventRecord(afterMarch, s);
+    if (beforeShade) // the march never reads the surface cache: a pending light-cache upload only gates the shade
+        cudaStreamWaitEvent(s, beforeShade, 0);
+    if (p.sortedIdx)
+        return 1 + launch_shade_sorted<TEX>(p, rayGroups, units, s);
+    shade_kernel<TEX><<<(unsigned)(units * 2), 256, 0, s>>>(p, rayGroups);
+    return 2;
+}
+
+int launch_trace(const TraceParams& p, int variant, unsigned int* chunkCounter, cudaStream_t s, cudaEvent_t beforeShade, cudaEvent_t afterMarch)
 {
     if (variant == 0)
     {
@@ -2999,56 +2863,7 @@ int launch_trace(const TraceParams& p, int variant, unsigned int* chunkCounter, 
         trace_kernel<<<grid, block, 0, s>>>(p);
         return 1;
     }
-    const int rayGroups   = (p.raysPerProbe + TW_RAYS_PER_UNIT - 1) / TW_RAYS_PER_UNIT;
-    const int probeGroups = (p.probeCount + 31) / 32;
-    const long long units = (long long)rayGroups * probeGroups;
-    const int chunks      = (int)(units * (UNIT_RAYS / MARCH_CHUNK_RAYS));
-    cudaMemsetAsync(chunkCounter, 0, sizeof(unsigned int), s);
-    long long blocks = ((long long)chunks + MARCH_WARPS - 1) / MARCH_WARPS;
-    const long long persistent = 148ll * MARCH_BLOCKS_PER_SM; // one resident generation of 8-warp blocks per SM
-    if (blocks > persistent)
-        blocks = persistent;
-#ifdef LUX_EXPERIMENTAL_OPEN_SKIP
-    size_t openSmem = 0;
-    if (open && open->bits)
-    {
-        const size_t words = 2 * (((size_t)open->w * open->h * open->d + 31) / 32); // open + near bit arrays
-        openSmem = words <= MARCH_OPEN_SMEM_WORDS ? words * 4 : 0;
-    }
-#endif
-    if (variant == 2)
-    {
-#ifdef LUX_EXPERIMENTAL_OPEN_SKIP
-        if (open && open->bits)
-            march_open_kernel<true><<<(unsigned)blocks, 32 * MARCH_WARPS, openSmem, s>>>(p, chunks, rayGroups, chunkCounter, *open);
-        else
-#endif
-            march_kernel<true><<<(unsigned)blocks, 32 * MARCH_WARPS, 0, s>>>(p, chunks, rayGroups, chunkCounter);
-        if (afterMarch)
-            cudaEventRecord(afterMarch, s);
-        if (beforeShade) // the march never reads the surface cache: a pending light-cache upload only gates the shade
-            cudaStreamWaitEvent(s, beforeShade, 0);
-        if (p.sortedIdx)
-            return 1 + launch_shade_sorted<true>(p, rayGroups, units, s);
-        shade_kernel<true><<<(unsigned)(units * 2), 256, 0, s>>>(p, rayGroups);
-    }
-    else
-    {
-#ifdef LUX_EXPERIMENTAL_OPEN_SKIP
-        if (open && open->bits)
-            march_open_kernel<false><<<(unsigned)blocks, 32 * MARCH_WARPS, openSmem, s>>>(p, chunks, rayGroups, chunkCounter, *open);
-        else
-#endif
-            march_kernel<false><<<(unsigned)blocks, 32 * MARCH_WARPS, 0, s>>>(p, chunks, rayGroups, chunkCounter);
-        if (afterMarch)
-            cudaEventRecord(afterMarch, s);
-        if (beforeShade)
-            cudaStreamWaitEvent(s, beforeShade, 0);
-        if (p.sortedIdx)
-            return 1 + launch_shade_sorted<false>(p, rayGroups, units, s);
-        shade_kernel<false><<<(unsigned)(units * 2), 256, 0, s>>>(p, rayGroups);
-    }
-    return 2;
+    return variant == 2 ? launch_wavefront<true>(p, chunkCounter, s, beforeShade, afterMarch) : launch_wavefront<false>(p, chunkCounter, s, beforeShade, afterMarch);
 }
 
 template <int PB>
@@ -3058,20 +2873,15 @@ static void launch_blend_irradiance_t(const BlendParams& p, cudaStream_t s)
     size_t main = (size_t)(KC * (M + 2) + 2 * KC * 64 + 2 * KC) * sizeof(float) + (size_t)2 * PB * KC * sizeof(uint2);
     size_t epi  = (size_t)M * 64 * sizeof(float);
     size_t smem = main > epi ? main : epi;
-    static bool attr = false;
-    if (!attr)
-    {
-        cudaFuncSetAttribute(blend_irradiance_kernel<PB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr = true;
-    }
+    // per launch: the attribute is per device (and per context), a process-wide "done" flag would leave a second GPU's context without it
+    cudaFuncSetAttribute(blend_irradiance_kernel<PB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     blend_irradiance_kernel<PB><<<(p.probeCount + PB - 1) / PB, 256, smem, s>>>(p);
 }
 
 void launch_blend_irradiance(const BlendParams& p, cudaStream_t s)
 {
     // 64-probe tiles only when they still give every SM two blocks; measured on a 1/8 C4 shard (8192 probes): 0.264 -> 0.229 ms
-    static const int big = getenv("LUX_BLEND_IRR_PB64_MIN") ? atoi(getenv("LUX_BLEND_IRR_PB64_MIN")) : 2 * 148 * 64; // tuning hook
-    if (p.probeCount >= big)
+    if (p.probeCount >= 2 * 148 * 64)
         launch_blend_irradiance_t<64>(p, s);
     else
         launch_blend_irradiance_t<32>(p, s);
@@ -3084,45 +2894,15 @@ static void launch_blend_depth_t(const BlendParams& p, cudaStream_t s)
     size_t main = (size_t)(KC * (M + 4) + 2 * KC * 256 + 2 * KC) * sizeof(float) + (size_t)2 * PB * KC * sizeof(uint2);
     size_t epi  = (size_t)M * 256 * sizeof(float);
     size_t smem = main > epi ? main : epi;
-    static bool attr = false;
-    if (!attr)
-    {
-        cudaFuncSetAttribute(blend_depth_kernel<PB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr = true;
-    }
+    cudaFuncSetAttribute(blend_depth_kernel<PB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     blend_depth_kernel<PB><<<(p.probeCount + PB - 1) / PB, 512, smem, s>>>(p);
-}
-
-template <int PB>
-static bool launch_blend_depth_resident_t(const BlendParams& p, cudaStream_t s)
-{
-    size_t main = (size_t)PB * (p.raysPadded + 1) * sizeof(float), epi = (size_t)2 * PB * 256 * sizeof(float);
-    size_t smem = main > epi ? main : epi;
-    if (smem > 200 * 1024)
-        return false;
-    static size_t attr = 0;
-    if (smem > attr)
-    {
-        cudaFuncSetAttribute(blend_depth_resident_kernel<PB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
-        attr = 200 * 1024;
-    }
-    blend_depth_resident_kernel<PB><<<(p.probeCount + PB - 1) / PB, 512, smem, s>>>(p);
-    return true;
 }
 
 void launch_blend_depth(const BlendParams& p, cudaStream_t s)
 {
-    static const bool resident = getenv("LUX_DEPTH_RESIDENT") != nullptr;
-    if (resident && p.probeCount >= 64 * 64 && launch_blend_depth_resident_t<64>(p, s))
-        return;
-    if (resident && p.probeCount >= 32 * 64 && launch_blend_depth_resident_t<32>(p, s))
-        return;
     // 32-probe tiles (two blocks per SM, 90 KB each) beat 64-probe tiles at every size measured: C4 full volume 0.83 -> 0.72 ms, 1/8 shard
-    // 0.123 -> 0.10 ms; the barrier between the staged ray chunks is hidden by the second block.  LUX_BLEND_DEPTH_PB64_MIN is a tuning hook.
-    static const int big = getenv("LUX_BLEND_DEPTH_PB64_MIN") ? atoi(getenv("LUX_BLEND_DEPTH_PB64_MIN")) : 0x7fffffff;
-    if (p.probeCount >= big)
-        launch_blend_depth_t<64>(p, s);
-    else if (p.probeCount >= 64 * 64)
+    // 0.123 -> 0.10 ms; the barrier between the staged ray chunks is hidden by the second block.
+    if (p.probeCount >= 64 * 64)
         launch_blend_depth_t<32>(p, s);
     else
         launch_blend_depth_t<16>(p, s);

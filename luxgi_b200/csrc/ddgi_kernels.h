@@ -41,28 +41,36 @@ struct TraceParams
     // rays
     const float4* dirs;     // [R] normalize(mat3(rot) * sphericalFibonacci(r, R))
     const float4* origins;  // [probeCount] probeLocation of this shard's probes
-    float4*       records;  // wavefront trace: per ray (hitTime, hit u, v, w), indexed [probeGroup][rayGroup][16][32]
+    float4*       records;  // wavefront trace: per ray (hitTime, hit u, v, w), indexed in MARCH ORDER (see MarchOrder)
     uint32_t*     meta;     // wavefront trace: cascade | kind << 2 | steps << 4
+    // march order: the march walks direction clusters (outer) x probe groups (inner) so that the rays in flight form a
+    // narrow beam from a compact block of probes; record index = chunk * 64 + slot.  Tables are built on the host at create time.
+    const uint32_t* pgOrder;  // [probeGroups] visiting order of the 32-probe groups (spatially tiled)
+    const uint32_t* pgIndex;  // [probeGroups] its inverse
+    const uint16_t* rayOrder; // [raySlots]    ray id in each slot: runs of MARCH_CLUSTER_RAYS slots are angularly adjacent directions; >= raysPerProbe = padding
+    const uint16_t* raySlot;  // [raySlots]    its inverse
+    int             probeGroups, rayClusters; // rayClusters = raySlots / MARCH_CLUSTER_RAYS
+    // kernel-uniform values of the march, computed once on the host with the same IEEE operations the device would use: they are read straight
+    // from the constant bank instead of occupying a register per lane (march_consts())
+    struct MarchConsts
+    {
+        float traceMaxDistance, chunkSizeDistance, chunkMarginDistance2;
+        float cascadesCountF, cascadesInv; // (float)cascadesCount and its reciprocal when the division is exact (power of two), else 0
+        float mipW, mipH, texW, texH;      // texture extents as floats
+        int   mipDm1, texDm1;              // depth - 1
+        float cc0[3], cd0, m0, minv0, v0, vinv0; // cascade 0: centre, half extent, 2*cd, 1/(2*cd) or 0, voxel, 1/voxel or 0
+    } mc;
+    int             probeMajor;               // 1 = [probe group][cluster] loop nest (the round-1 order; LUX_DDGI_FLAG_MARCH_PROBE_MAJOR), 0 = [cluster][probe group]
     uint2*        radiance; // [probeCount][R] RGBA16F
     uint2*        dirDist;  // [probeCount][R] RGBA16F
     uint16_t*     steps;    // optional [probeCount][R] march-step counts (debug / roofline counters)
     // sorted shade (null sortedIdx = shade in ray order)
     float     invChunkSize;
-    uint2*    sortTicket;   // [records] (bin, ticket within bin) or (0xffffffff, -) for rays that need no shading
+    uint2*    sortTicket;   // [records] (bin, ticket within bin | cascade << 30) or (0xffffffff, -) for rays that need no shading; written by the march
     uint32_t* binCounts;    // [trace_sort_bins] hit histogram, turned into its exclusive prefix sum in place
     uint32_t* binBlockSums; // [trace_sort_blocks]
     uint32_t* hitCount;     // [1] number of hits = length of sortedIdx in use
     uint32_t* sortedIdx;    // [records] record indices in bin order
-};
-
-// optional open-space table over the mip volume (LUX_DDGI_FLAG_OPEN_SKIP): one bit per cell of OPEN_CELL^3 mip texels.  The share of march
-// steps the table proves open barely depends on the cell size (C4, CPU-side statistics, DESIGN §11: 12.3 / 12.1 / 11.7 / 10.8 % at 1 / 2 / 4 / 8 texels), so
-// the cell is 8: 4 KiB of table for a 1024^3 volume, small enough to sit in shared memory without shrinking the L1 the gathers live in.
-constexpr int OPEN_CELL = 8;
-struct OpenTableArgs
-{
-    const uint32_t* bits;    // null = off; [0, words) open bits, [words, 2 * words) near bits
-    int             w, h, d; // cells per axis of the whole (side-by-side) mip volume
 };
 
 struct BlendParams
@@ -102,13 +110,12 @@ void launch_tile_zrow(const LuxTileBuffer* tiles, int count, float4* out, cudaSt
 // gathers.  Returns the number of kernels launched.
 // `beforeShade` (nullable): event the stream waits on before the first kernel that reads the surface cache.
 // `afterMarch` (nullable): recorded between the march and the shade kernel (stage timers).
-// `open` (nullable): open-space table for the experimental march variant (LUX_DDGI_FLAG_OPEN_SKIP).
-struct OpenTableArgs;
 int    launch_trace(const TraceParams& p, int variant, unsigned int* chunkCounter, cudaStream_t s, cudaEvent_t beforeShade,
-                    cudaEvent_t afterMarch, const OpenTableArgs* open = nullptr);
+                    cudaEvent_t afterMarch);
+constexpr int MARCH_CLUSTER_RAYS = 16; // directions per cluster = ray slots per record unit
 size_t trace_record_count(int probeCount, int raysPerProbe);
-size_t trace_sort_bins(int probeCount, int raysPerProbe);   // bins of the sorted shade's counting sort (padded to the scan's block size)
-size_t trace_sort_blocks(int probeCount, int raysPerProbe); // scan blocks over those bins
+size_t trace_sort_bins();   // bins of the sorted shade's counting sort (culling chunks x octants, padded to the scan's block size)
+size_t trace_sort_blocks(); // scan blocks over those bins
 void   launch_probe_origins(const TraceParams& p, cudaStream_t s);
 void launch_blend_irradiance(const BlendParams& p, cudaStream_t s);
 void launch_blend_depth(const BlendParams& p, cudaStream_t s);
@@ -143,11 +150,6 @@ void launch_sdf_shadow(const TraceParams& p, bool useTextures, const LuxLight& l
 
 // measurement aid: one sweep of `bytes` (multiple of 16 KiB) by each of `blocks` blocks through L2
 void launch_l2_sweep(const void* buf, size_t bytes, int blocks, uint32_t* sink, cudaStream_t s);
-
-// open-space table of the mip volume [mipD][mipH][mipW] (LUX_DDGI_FLAG_OPEN_SKIP): two bit arrays (open, then near) of ceil(cells / 32) words each,
-// bit index (cz * ch + cy) * cw + cx, cw = mipW / OPEN_CELL, ...
-bool open_skip_compiled(); // false unless built with -DLUX_EXPERIMENTAL_OPEN_SKIP
-void launch_open_table(const void* mipR16F, int mipW, int mipH, int mipD, float chunkSizeDistance, uint32_t* bits, cudaStream_t s);
 
 // ---- global SDF build ----
 struct SdfMeshRecord // device copy of LuxMeshSDF without the host pointers

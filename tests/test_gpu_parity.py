@@ -211,7 +211,9 @@ def test_restore_resumes_bit_identically():
 @pytest.mark.parametrize("flags,name", [(0, "wavefront+tld4"), (abi.FLAG_SDF_LOADS, "wavefront+loads"), (abi.FLAG_TRACE_SIMPLE, "simple"),
                                         (abi.FLAG_NO_PREFILTER, "wavefront, full object lists"),
                                         (abi.FLAG_SHADE_UNSORTED, "wavefront, hits shaded in ray order"),
-                                        (abi.FLAG_SHADE_UNSORTED | abi.FLAG_SDF_LOADS, "wavefront+loads, ray order")])
+                                        (abi.FLAG_SHADE_UNSORTED | abi.FLAG_SDF_LOADS, "wavefront+loads, ray order"),
+                                        (abi.FLAG_MARCH_PROBE_MAJOR, "wavefront, probe-major march order"),
+                                        (abi.FLAG_MARCH_PROBE_MAJOR | abi.FLAG_SHADE_UNSORTED, "probe-major march order, ray-order shade")])
 @pytest.mark.parametrize("cfg", ["c1", "city64"])
 def test_trace_variants_match_oracle(oracle, flags, name, cfg):
     """Every trace kernel variant (thread-per-ray, wavefront with explicit loads, wavefront with texture gathers)
@@ -269,7 +271,7 @@ def test_64_frame_convergence_shipped_scene_parameters(oracle):
 
 
 def test_large_probe_count_big_tile_kernels(oracle):
-    """4096 probes: the 64-probe blend tiles (irradiance<64>, resident depth<64>) and many march chunks per warp."""
+    """4096 probes: the 32-probe depth tiles (blend_depth_kernel<32>; irradiance<64> needs >= 18 944 probes and is covered by the full-size test) and many march chunks per warp."""
     sc = scenes.cornell_scene(res=32, counts=(16, 16, 16), rays=96, atlas_res=256)
     rots = [scenes.frame_rotation(f) for f in range(2)]
     orc = oracle.OraclePipeline(sc)
@@ -401,26 +403,26 @@ def test_infinite_bounce_refresh_closes_the_loop(oracle):
     pipe.close()
 
 
-@pytest.mark.parametrize("cfg,batch_rays", [("city128", 32768), ("city64", 4096)])
-def test_pipelined_probe_batches_match_oracle(oracle, monkeypatch, cfg, batch_rays):
-    """lux_ddgi_update splits large shards into probe batches that alternate between two streams (march/shade/blend of one batch
-    overlap the tails of the previous one).  Forced here on small volumes through the LUX_DDGI_BATCH_RAYS test hook: three
-    frames (hysteresis on) must equal the oracle bit for bit, and equal the serialized one-batch form."""
+@pytest.mark.parametrize("cfg", ["city128", "city64"])
+def test_march_work_order_does_not_change_results(oracle, cfg):
+    """The wavefront march visits direction clusters (outer) x spatially tiled probe groups (inner); records are addressed in that order by
+    every later stage.  Three frames (hysteresis on) must equal the oracle bit for bit in the shipped order, in the round-1 probe-major order
+    (LUX_DDGI_FLAG_MARCH_PROBE_MAJOR) and with the weights computed on the context's stream (LUX_DDGI_FLAG_NO_PIPELINE)."""
     sc = scenes.build(cfg)
     rots = [scenes.frame_rotation(f) for f in range(3)]
     orc = oracle.OraclePipeline(sc)
     for r in rots:
         orc.update(r)
-    monkeypatch.setenv("LUX_DDGI_BATCH_RAYS", str(batch_rays))
     pipe = run_engine(sc, rots)
-    monkeypatch.delenv("LUX_DDGI_BATCH_RAYS")
     serial = run_engine(sc, rots, flags=abi.FLAG_NO_PIPELINE)
+    major = run_engine(sc, rots, flags=abi.FLAG_MARCH_PROBE_MAJOR)
     assert_rays_match(pipe, orc)
     assert_atlases_match(pipe, orc)
-    assert np.array_equal(pipe.irradiance, serial.irradiance) and np.array_equal(pipe.depth, serial.depth)
-    assert np.array_equal(pipe.radiance, serial.radiance)
+    for other in (serial, major):
+        assert np.array_equal(pipe.irradiance, other.irradiance) and np.array_equal(pipe.depth, other.depth)
+        assert np.array_equal(pipe.radiance, other.radiance) and np.array_equal(pipe.direction_distance, other.direction_distance)
+        other.close()
     pipe.close()
-    serial.close()
 
 
 def test_pipelined_row_downloads_with_fences(oracle):
