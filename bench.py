@@ -98,11 +98,13 @@ class ClockSampler:
 
 
 def workload_desc(name, sc):
+    """The `config` object: the same keys and values in both arms (the driver compares them)."""
     u = sc.uniform
     return {"workload": f"{name}: {sc.name} SDF {int(sc.sdf_data.resolution)}^3 fp16, {u.probeCounts[0]}x{u.probeCounts[1]}x{u.probeCounts[2]} probes, "
                         f"{u.raysPerProbe} rays/probe",
             "probes": sc.probes, "rays_per_probe": u.raysPerProbe, "sdf_res": int(sc.sdf_data.resolution),
-            "surface_atlas_res": int(sc.atlas_data.resolution) if sc.atlas_data is not None else 0}
+            "surface_atlas_res": int(sc.atlas_data.resolution) if sc.atlas_data is not None else 0,
+            "l2_policy": "inputs larger than L2 (no flush)"}
 
 
 def algorithmic_bytes(sc, probes):
@@ -134,15 +136,30 @@ def measured_traffic(workload, world):
 # reference arm / cpu baseline: the oracle on host cores
 # ----------------------------------------------------------------------------------------------------------------------
 def oracle_sample_ids(sc, n):
+    """n probes stratified over the whole volume: one per stratum of P / n consecutive ids, at a pseudo-random offset inside the stratum
+    (a plain stride of P / n is a multiple of the grid's x extent on the bench volumes, i.e. a sample of ONE face of the volume,
+    whose rays leave the SDF early: round 1's sample under-counted the march steps per ray by a third)."""
     P = sc.probes
     n = min(n, P)
-    return (np.arange(n, dtype=np.int64) * P // n).astype(np.int32)  # stratified over the whole volume
+    i = np.arange(n, dtype=np.int64)
+    lo = i * P // n
+    width = np.maximum((i + 1) * P // n - lo, 1)
+    off = (i * 2654435761 + 40503) % width
+    return (lo + off).astype(np.int32)
+
+
+def host_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
 
 
 def time_oracle(sc, rot, sample_probes, steps, warmup):
     """One step = trace + literal (naive) blend + border of `sample_probes` stratified probes on all host threads."""
     from oracle import binding as ob
 
+    ob.lib().oracle_set_threads(host_threads())  # torchrun exports OMP_NUM_THREADS=1: the CPU arm uses every core it may run on regardless
     osc = ob.OracleScene(sc)
     ids = oracle_sample_ids(sc, sample_probes)
     n = len(ids)
@@ -200,6 +217,58 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def multi_gpu_parity(sc, local, rank, world, flags, stream, dev, frames=2, sample=256):
+    """N > 1 only, after the timed region: fresh contexts run `frames` updates with the in-library all-gather; every rank checksums its FULL
+    atlases on the device (they must be identical on all ranks: own rows + the rows NCCL delivered), and rank 0 replays a stratified probe
+    subsample of the WHOLE volume on the CPU oracle and compares those probes' atlas tiles (interior + border) bit for bit."""
+    import torch
+    import torch.distributed as dist
+
+    from luxgi_b200 import abi, ddgi, nccl, scenes
+    from oracle import binding as ob
+
+    u = sc.uniform
+    pipe = ddgi.DDGIPipeline(u, device=local, rank=rank, world=world, flags=flags, stream=stream.cuda_stream)
+    pipe.set_scene(sc)
+    comm = nccl.NcclComm(rank, world, local)
+    pipe.set_nccl_comm(comm.ptr)
+    ids = oracle_sample_ids(sc, sample)
+    if rank == 0:
+        ob.lib().oracle_set_threads(host_threads())
+        osc = ob.OracleScene(sc)
+        irr = [ob.new_atlases(u)[0] for _ in range(2)]
+        dep = [ob.new_atlases(u)[1] for _ in range(2)]
+    for f in range(frames):
+        rot = scenes.frame_rotation(f)
+        pipe.update(rot)
+        if rank == 0:
+            rad, dd, _, _ = osc.trace(rot, probe_ids=ids)
+            ob.blend_ids(u, rad, dd, irr[f % 2], dep[f % 2], irr[1 - f % 2], dep[1 - f % 2], first_frame=(f == 0), probe_ids=ids)
+    pipe.synchronize()
+    sums = []
+    for buf in (abi.BUF_IRRADIANCE, abi.BUF_DEPTH):
+        t = torch.as_tensor(pipe.device_view(buf), device=dev).reshape(-1).view(torch.int16).to(torch.int64)
+        w = (torch.arange(t.numel(), device=dev, dtype=torch.int64) % 65521) + 1
+        sums += [int(t.sum().item()), int((t * w).sum().item() & 0x7fffffffffffffff)]
+    mine = torch.tensor(sums, device=dev, dtype=torch.int64)
+    every = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(every, mine)
+    same = all(bool(torch.equal(e, every[0])) for e in every)
+    ok_oracle, bad = True, 0
+    if rank == 0:
+        per_row = u.probeCounts[0] * u.probeCounts[1]
+        for got, want, side in ((pipe.irradiance, irr[frames % 2], 8), (pipe.depth, dep[frames % 2], 16)):
+            S = side + 2
+            for p_ in ids:
+                r0, c0 = 1 + (int(p_) // per_row) * S, 1 + (int(p_) % per_row) * S
+                bad += int((got[r0:r0 + S, c0:c0 + S] != want[r0:r0 + S, c0:c0 + S]).sum())
+        ok_oracle = bad == 0
+    pipe.close()
+    comm.destroy()
+    return {"status": "ok" if (same and ok_oracle) else "FAILED", "frames": frames, "atlas_checksums_equal_on_all_ranks": same,
+            "probes_checked_against_oracle": int(len(ids)), "differing_fp16_values": bad}
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------------------------------
@@ -230,6 +299,7 @@ def run_lux(args):
         flags |= abi.FLAG_NO_PIPELINE
     if args.unsorted:
         flags |= abi.FLAG_SHADE_UNSORTED
+    flags |= args.extra_flags
     shard_rank, shard_world = (rank, world) if args.emulate_shard is None else tuple(int(x) for x in args.emulate_shard.split('/'))
     # The measured pipe runs lux_ddgi_update as shipped (blend weights on a second stream during the march, no stage events); the per-stage
     # times and the kernel roofline come from a second, serialized pass below (LUX_DDGI_FLAG_STAGE_TIMERS = one batch, one stream).
@@ -398,6 +468,11 @@ def run_lux(args):
         per_rank = [[round(float(x) / args.steps, 4) for x in t.tolist()[1:3]] for t in allr]
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
     ms_total, trace_ms, blend_ms, setup_ms, march_ms, shade_ms = [float(x) for x in tm.tolist()]
+    parity = None
+    if world > 1 and args.emulate_shard is None and not args.no_parity:
+        pipe.close()
+        pipe = None
+        parity = multi_gpu_parity(sc, local, rank, world, flags, stream, dev)
     ms_per_step = ms_total / args.steps
     value = P_timed * R * args.steps / (ms_total * 1e-3)
 
@@ -439,10 +514,11 @@ def run_lux(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "ms_per_update": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": dict(workload_desc(args.workload, sc), parallelism=f"zslab{world}", l2_policy="inputs larger than L2 (no flush)",
-                           sharding="probe z-slabs, SDF + surface cache replicated, in-place NCCL all-gather of atlas rows per step"
-                           + ("" if world == 1 else ((" issued by lux_ddgi_update on the library's gather stream" if args.allgather == "lib" else " issued by the host (torch.distributed)")
-                                                     + (" on the compute stream" if args.sync_allgather else ", overlapped with the next step's trace")))),
+            "config": workload_desc(args.workload, sc),
+            "parallelism": {"layout": f"zslab{world}",
+                            "sharding": "probe z-slabs, SDF + surface cache replicated, in-place NCCL all-gather of atlas rows per step"
+                            + ("" if world == 1 else ((" issued by lux_ddgi_update on the library's gather stream" if args.allgather == "lib" else " issued by the host (torch.distributed)")
+                                                      + (" on the compute stream" if args.sync_allgather else ", overlapped with the next step's trace")))},
             "stage_ms": {"setup": setup_ms / args.steps, "trace": trace_launch_ms, "march": march_launch_ms, "shade": shade_launch_ms,
                          "blend_border": blend_launch_ms,
                          "update_minus_stage_sum": ms_per_step - (setup_ms + trace_ms + blend_ms) / args.steps,
@@ -457,6 +533,7 @@ def run_lux(args):
                     "h2d_bytes_per_step": (light_bytes // world if comm_used else light_bytes) + 64, "d2h_bytes_per_step": d2h_bytes,
                     "note": "per rank and per step: light cache H2D from pinned memory (N > 1: own 1/N of its rows, all-gathered over NVLink by the library), own atlas rows D2H into pinned memory; the host waits for frame f-1's rows while frame f computes (every frame delivered, one frame late), all copies complete inside the timed region"},
             "gpu_launches": int(launches),
+            "multi_gpu_parity": parity,
             "wall_s_timed_region": t_wall,
         }
         if world == 1 and not args.no_cpu_baseline:
@@ -477,8 +554,11 @@ def run_lux(args):
                                    "request_bytes_per_launch": req, "ms_per_launch": trace_launch_ms,
                                    "peak_source": "measured live before the timed region: lux_ddgi_measure_l2_read_bandwidth (64 MiB read-only sweep by every SM, best of 5)",
                                    "floor_ms": {"hbm": t_hbm * 1e3, "l2": t_l2 * 1e3}, "binding": "l2" if t_l2 > t_hbm else "hbm"}
+        if parity is not None:
+            sys.stderr.write(f"multi_gpu_parity: {parity['status']}\n")
         print(json.dumps(line), flush=True)
-    pipe.close()
+    if pipe is not None:
+        pipe.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -498,6 +578,7 @@ def main():
     ap.add_argument("--trace", default="texture", choices=["texture", "loads", "simple"],
                     help="SDF read path / trace kernel variant: wavefront + tld4 gathers (default), wavefront + fp16 loads, thread-per-ray")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the post-run parity pass (atlas checksums across ranks + oracle subsample on rank 0)")
     ap.add_argument("--e2e-skip-h2d", action="store_true", help="diagnosis only: e2e leg without the light-cache upload (the printed e2e is then NOT an end-to-end number)")
     ap.add_argument("--e2e-skip-d2h", action="store_true", help="diagnosis only: e2e leg without the atlas downloads")
     ap.add_argument("--emulate-shard", default=None, help="r/w: run shard r of w on one GPU without any collective (profiling aid)")
@@ -505,6 +586,7 @@ def main():
                     help="N > 1: exchange inside lux_ddgi_update (ncclComm bound through the C ABI, default) or issued by this script through torch.distributed")
     ap.add_argument("--sync-allgather", action="store_true", help="all-gather on the compute stream (no overlap with the next trace)")
     ap.add_argument("--no-pipeline", action="store_true", help="A/B: one batch on one stream instead of two-stream probe batches")
+    ap.add_argument("--extra-flags", type=lambda v: int(v, 0), default=0, help="A/B: LUX_DDGI_FLAG_* bits OR-ed into the context flags")
     ap.add_argument("--unsorted", action="store_true", help="A/B: shade hits in ray order (no counting sort by culling chunk)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -524,6 +524,7 @@ static int launch(LuxDDGIContext& c, cudaStream_t s, bool timers)
     p.probeGroups = c.probeGroups;
     p.rayClusters = c.rayClusters;
     p.probeMajor  = (c.flags & LUX_DDGI_FLAG_MARCH_PROBE_MAJOR) ? 1 : 0;
+    p.march64     = (c.flags & LUX_DDGI_FLAG_MARCH_64REG) ? 1 : ((c.flags & (1u << 10)) ? 2 : 0); // bit 10: 40 warps at 48 registers (experiment)
     unsigned int* counters = (unsigned int*)c.chunkCounter.ptr; // [0] march chunk counter, [1] hit count
     if (c.sortedIdx.ptr)
     {

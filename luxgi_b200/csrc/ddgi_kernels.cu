@@ -1049,10 +1049,8 @@ __device__ __forceinline__ f3 probe_origin(const TraceParams& P, int probeId)
 // Ray index g enumerates [probeGroup][rayGroup][rayInUnit (16)][probeLane (32)], so lanes that refill together take
 // adjacent probes with the same direction.
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int MARCH_WARPS       = 8;
-#ifndef MARCH_BLOCKS_PER_SM
-#define MARCH_BLOCKS_PER_SM 4 // 64 registers, 32 warps per SM: with 48 (5 blocks) ptxas serialises the two taps of a step to save registers (SASS inspected)
-#endif
+// Two occupancy points of the march (ptxas keeps the four gathers of a step together from 56 registers up; at 48 it serialises the taps):
+//   6 warps x 6 blocks = 36 warps per SM at 56 registers (default), 8 warps x 4 blocks = 32 warps at 64 registers (LUX_DDGI_FLAG_MARCH_64REG).
 #ifndef SHADE_BLOCKS_PER_SM
 #define SHADE_BLOCKS_PER_SM 5
 #endif
@@ -2834,14 +2832,21 @@ static int launch_wavefront(const TraceParams& pIn, unsigned int* chunkCounter, 
     cudaMemsetAsync(chunkCounter, 0, sizeof(unsigned int), s);
     if (p.sortTicket)
         cudaMemsetAsync(p.binCounts, 0, trace_sort_bins() * sizeof(uint32_t), s);
-    long long blocks = ((long long)chunks + MARCH_WARPS - 1) / MARCH_WARPS;
-    const long long persistent = 148ll * MARCH_BLOCKS_PER_SM; // one resident generation of 8-warp blocks per SM
-    if (blocks > persistent)
-        blocks = persistent;
+    auto launch = [&](auto kernel, int warps, int blocksPerSM) {
+        long long blocks = ((long long)chunks + warps - 1) / warps;
+        const long long persistent = 148ll * blocksPerSM; // one resident generation per SM
+        if (blocks > persistent)
+            blocks = persistent;
+        kernel<<<(unsigned)blocks, 32 * warps, 0, s>>>(p, chunks, chunkCounter);
+    };
     if (p.cascades > 1)
-        march_kernel<TEX, true><<<(unsigned)blocks, 32 * MARCH_WARPS, 0, s>>>(p, chunks, chunkCounter);
+        launch(march_kernel<TEX, true, 8, 4>, 8, 4);
+    else if (p.march64 == 1)
+        launch(march_kernel<TEX, false, 8, 4>, 8, 4);
+    else if (p.march64 == 2)
+        launch(march_kernel<TEX, false, 8, 5>, 8, 5);
     else
-        march_kernel<TEX, false><<<(unsigned)blocks, 32 * MARCH_WARPS, 0, s>>>(p, chunks, chunkCounter);
+        launch(march_kernel<TEX, false, 6, 6>, 6, 6);
     if (afterMarch)
         cudaEventRecord(afterMarch, s);
     if (beforeShade) // the march never reads the surface cache: a pending light-cache upload only gates the shade

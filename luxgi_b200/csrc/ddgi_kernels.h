@@ -60,6 +60,7 @@ struct TraceParams
         int   mipDm1, texDm1;              // depth - 1
         float cc0[3], cd0, m0, minv0, v0, vinv0; // cascade 0: centre, half extent, 2*cd, 1/(2*cd) or 0, voxel, 1/voxel or 0
     } mc;
+    int             march64;                  // A/B: 32 warps per SM at 64 registers instead of 36 at 56 (LUX_DDGI_FLAG_MARCH_64REG)
     int             probeMajor;               // 1 = [probe group][cluster] loop nest (the round-1 order; LUX_DDGI_FLAG_MARCH_PROBE_MAJOR), 0 = [cluster][probe group]
     uint2*        radiance; // [probeCount][R] RGBA16F
     uint2*        dirDist;  // [probeCount][R] RGBA16F
