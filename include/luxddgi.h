@@ -249,7 +249,8 @@ enum {
     LUX_DDGI_FLAG_NO_PREFILTER  = 1u << 5, /* walk the full per-chunk object lists (no sub-cell candidate masks), for A/B */
     LUX_DDGI_FLAG_SHADE_UNSORTED= 1u << 6, /* shade hits in ray order instead of culling-chunk order (no counting sort), for A/B */
     LUX_DDGI_FLAG_NO_PIPELINE   = 1u << 7, /* lux_ddgi_update computes the blend weights on the context's stream instead of a second one, for A/B */
-    LUX_DDGI_FLAG_MARCH_64REG   = 1u << 9, /* march kernel at 32 warps per SM / 64 registers instead of 36 / 56, for A/B */
+    LUX_DDGI_FLAG_MARCH_ROWS    = 1u << 9, /* force row chunks in the march (a warp = 32 x-adjacent probes x one direction); default: by volume size */
+    LUX_DDGI_FLAG_MARCH_BEAMS   = 1u << 10,/* force beam chunks (a warp = one probe x 32 angularly adjacent directions)                        */
     LUX_DDGI_FLAG_MARCH_PROBE_MAJOR = 1u << 8 /* wavefront march in the round-1 work order (probe groups outermost, ray ids as they come) instead of direction
                                             * clusters outermost over spatially tiled probe groups; same results, for A/B of the DRAM traffic */
 };

@@ -196,7 +196,8 @@ FLAG_TRACE_SIMPLE = 1 << 4
 FLAG_NO_PREFILTER = 1 << 5
 FLAG_SHADE_UNSORTED = 1 << 6
 FLAG_NO_PIPELINE = 1 << 7
-FLAG_MARCH_64REG = 1 << 9  # A/B: march occupancy point
+FLAG_MARCH_ROWS = 1 << 9  # force row chunks in the march
+FLAG_MARCH_BEAMS = 1 << 10  # force beam chunks
 FLAG_MARCH_PROBE_MAJOR = 1 << 8  # A/B: the round-1 march work order
 BUF_RADIANCE, BUF_DIRECTION_DISTANCE, BUF_IRRADIANCE, BUF_DEPTH, BUF_IRRADIANCE_PREV, BUF_DEPTH_PREV, BUF_GLOBAL_SDF, BUF_GLOBAL_SDF_MIP = range(8)
 

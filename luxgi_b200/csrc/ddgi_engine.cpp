@@ -92,8 +92,9 @@ struct LuxDDGIContext
     DeviceBuffer origins, records, meta, chunkCounter; // wavefront trace scratch
     DeviceBuffer sortTicket, binCounts, binBlockSums, sortedIdx; // sorted shade scratch (the hit count lives in chunkCounter[1])
     DeviceBuffer dirsHalf;                                       // [R] fp16 directions for the blend weights (pipelined update)
-    DeviceBuffer pgOrder, pgIndex, rayOrder, raySlot;            // march order tables (init::marchOrder)
-    int          probeGroups = 0, rayClusters = 0;
+    DeviceBuffer unitOrder, unitIndex, rayOrder, raySlot;        // march order tables (init::marchOrder)
+    int          probeUnits = 0, rayClusters = 0;
+    int          marchBeam  = -1;                                // chunk shape the tables were built for (-1 = none yet)
 
     cudaStream_t auxStream = nullptr;
     cudaEvent_t  evFork = nullptr, evJoin = nullptr, evWeights = nullptr;
@@ -267,13 +268,14 @@ static int validate(const LuxDDGIUniform& u)
     return LUX_OK;
 }
 
-// Work order of the wavefront march (csrc/march_kernel.inc): which probe group and which ray directions the k-th chunk holds.  Any order gives
-// the same results (every ray is independent); this one makes the rays in flight a narrow beam from a compact block of probes:
-//  * probe groups (32 consecutive probe ids = a run along x) are visited tile by tile: tiles of 32 x 16 x 16 probes in Morton order of the tile
-//    coordinates, groups inside a tile by (z, y);
+// Work order of the wavefront march (csrc/march_kernel.inc): which probes and which ray directions the k-th chunk holds.  Any order gives
+// the same results (every ray is independent); this one makes the rays in flight a narrow cone leaving a compact block of probes:
+//  * probe units (beam chunks: 2 consecutive probe ids; row chunks: 32, a run along x) are visited tile by tile: tiles of 32 x 16 x 16 probes
+//    in Morton order of the tile coordinates, units inside a tile by (z, y, x);
 //  * ray ids are clustered by direction: the un-rotated spherical-Fibonacci directions (DDGICommon.glsl:42-52) are sorted along a Hilbert curve
-//    over their octahedral image, and every run of MARCH_CLUSTER_RAYS slots of that order is one cluster.  The per-frame rotation is rigid, so the
-//    clusters stay clusters.  (Consecutive Fibonacci indices are 137.5 degrees apart in azimuth: the id order itself is as incoherent as it gets.)
+//    over their octahedral image, and every run of MARCH_CLUSTER_RAYS (32) slots of that order is one cluster.  The per-frame rotation is rigid,
+//    so the clusters stay clusters.  (Consecutive Fibonacci indices are 137.5 degrees apart in azimuth: the id order itself is as incoherent
+//    as it gets.)
 static uint32_t hilbertIndex(uint32_t n, uint32_t x, uint32_t y)
 {
     uint32_t d = 0;
@@ -302,18 +304,19 @@ static uint32_t spread3(uint32_t v) // 10 bits -> every third bit
     v = (v | (v << 2)) & 0x09249249u;
     return v;
 }
-static int marchOrder(LuxDDGIContext& c)
+static int marchOrder(LuxDDGIContext& c, bool beam)
 {
     const LuxDDGIUniform& u = c.uniform;
     const int X = u.probeCounts[0], Y = u.probeCounts[1];
-    const int PG = (c.probeCount + 31) / 32;
+    const int unit = beam ? 2 : 32;
+    const int PG = (c.probeCount + unit - 1) / unit; // probe units
     const int R = u.raysPerProbe, slots = (R + lux::MARCH_CLUSTER_RAYS - 1) / lux::MARCH_CLUSTER_RAYS * lux::MARCH_CLUSTER_RAYS;
-    const bool identity = (c.flags & LUX_DDGI_FLAG_MARCH_PROBE_MAJOR) != 0; // the round-1 order: ids as they come, probe groups outermost
+    const bool identity = (c.flags & LUX_DDGI_FLAG_MARCH_PROBE_MAJOR) != 0; // ids as they come, probe units outermost
     std::vector<uint32_t> order(PG), index(PG);
     std::vector<std::pair<uint64_t, uint32_t>> keyed(PG);
     for (int g = 0; g < PG; g++)
     {
-        const int id = g * 32, x = id % X, y = (id / X) % Y, z = id / (X * Y); // first probe of the group, shard-local
+        const int id = g * unit, x = id % X, y = (id / X) % Y, z = id / (X * Y); // first probe of the unit, shard-local
         const uint64_t tile = spread3((uint32_t)(x / 32)) | (spread3((uint32_t)(y / 16)) << 1) | ((uint64_t)spread3((uint32_t)(z / 16)) << 2);
         const uint64_t in = ((uint64_t)(z % 16) << 16) | ((uint64_t)(y % 16) << 8) | (uint64_t)(x % 32);
         keyed[g] = {identity ? (uint64_t)g : ((tile << 24) | in), (uint32_t)g};
@@ -348,15 +351,20 @@ static int marchOrder(LuxDDGIContext& c)
     for (int s = 0; s < slots; s++)
         raySlot[rayOrder[s]] = (uint16_t)s;
     int rc;
-    if ((rc = allocZero(c, c.pgOrder, (size_t)PG * sizeof(uint32_t))) != LUX_OK) return rc;
-    if ((rc = allocZero(c, c.pgIndex, (size_t)PG * sizeof(uint32_t))) != LUX_OK) return rc;
+    if ((rc = allocZero(c, c.unitOrder, (size_t)PG * sizeof(uint32_t))) != LUX_OK) return rc;
+    if ((rc = allocZero(c, c.unitIndex, (size_t)PG * sizeof(uint32_t))) != LUX_OK) return rc;
     if ((rc = allocZero(c, c.rayOrder, (size_t)slots * sizeof(uint16_t))) != LUX_OK) return rc;
     if ((rc = allocZero(c, c.raySlot, (size_t)slots * sizeof(uint16_t))) != LUX_OK) return rc;
-    LUX_CUDA(cudaMemcpy(c.pgOrder.ptr, order.data(), (size_t)PG * sizeof(uint32_t), cudaMemcpyHostToDevice));
-    LUX_CUDA(cudaMemcpy(c.pgIndex.ptr, index.data(), (size_t)PG * sizeof(uint32_t), cudaMemcpyHostToDevice));
-    LUX_CUDA(cudaMemcpy(c.rayOrder.ptr, rayOrder.data(), (size_t)slots * sizeof(uint16_t), cudaMemcpyHostToDevice));
-    LUX_CUDA(cudaMemcpy(c.raySlot.ptr, raySlot.data(), (size_t)slots * sizeof(uint16_t), cudaMemcpyHostToDevice));
-    c.probeGroups = PG;
+    LUX_CUDA(cudaMemcpyAsync(c.unitOrder.ptr, order.data(), (size_t)PG * sizeof(uint32_t), cudaMemcpyHostToDevice, c.stream));
+    LUX_CUDA(cudaMemcpyAsync(c.unitIndex.ptr, index.data(), (size_t)PG * sizeof(uint32_t), cudaMemcpyHostToDevice, c.stream));
+    LUX_CUDA(cudaMemcpyAsync(c.rayOrder.ptr, rayOrder.data(), (size_t)slots * sizeof(uint16_t), cudaMemcpyHostToDevice, c.stream));
+    LUX_CUDA(cudaMemcpyAsync(c.raySlot.ptr, raySlot.data(), (size_t)slots * sizeof(uint16_t), cudaMemcpyHostToDevice, c.stream));
+    LUX_CUDA(cudaStreamSynchronize(c.stream)); // the host vectors go out of scope
+    c.probeUnits = PG;
+    c.marchBeam  = beam ? 1 : 0;
+    if (c.sortTicket.ptr) // padding records (lanes / slots beyond the volume) are never marched, so nothing ever writes their ticket: "not a hit", and
+                          // which records are padding depends on the chunk shape
+        LUX_CUDA(cudaMemsetAsync(c.sortTicket.ptr, 0xff, c.sortTicket.bytes, c.stream));
     c.rayClusters = slots / lux::MARCH_CLUSTER_RAYS;
     return LUX_OK;
 }
@@ -388,19 +396,17 @@ static int initializeProbeGrid(LuxDDGIContext& c)
     if ((rc = allocZero(c, c.chunkCounter, 64)) != LUX_OK) return rc;
     if (!(c.flags & LUX_DDGI_FLAG_TRACE_SIMPLE))
     {
-        const size_t nrec = lux::trace_record_count(c.probeCount, u.raysPerProbe);
+        const size_t nrec = lux::trace_record_capacity(c.probeCount, u.raysPerProbe);
         if ((rc = allocZero(c, c.records, nrec * sizeof(float4))) != LUX_OK) return rc;
         if ((rc = allocZero(c, c.meta, nrec * sizeof(uint32_t))) != LUX_OK) return rc;
         if (!(c.flags & LUX_DDGI_FLAG_SHADE_UNSORTED) && nrec < (size_t(1) << 30) /* record index + 2 cascade bits in one u32 */)
         {
             if ((rc = allocZero(c, c.sortTicket, nrec * sizeof(uint2))) != LUX_OK) return rc;
-            // padding records (probe lanes / ray slots beyond the volume) are never marched, so nothing ever writes their ticket: "not a hit" once, here
-            LUX_CUDA(cudaMemsetAsync(c.sortTicket.ptr, 0xff, nrec * sizeof(uint2), c.stream));
             if ((rc = allocZero(c, c.sortedIdx, nrec * sizeof(uint32_t))) != LUX_OK) return rc;
             if ((rc = allocZero(c, c.binCounts, lux::trace_sort_bins() * sizeof(uint32_t))) != LUX_OK) return rc;
             if ((rc = allocZero(c, c.binBlockSums, lux::trace_sort_blocks() * sizeof(uint32_t))) != LUX_OK) return rc;
         }
-        if ((rc = marchOrder(c)) != LUX_OK) return rc;
+        c.marchBeam = -1; // tables are built by the first trace, when the bound volume decides the chunk shape (trace_rays::setup)
     }
     if ((rc = allocZero(c, c.dirsHalf, (size_t)u.raysPerProbe * sizeof(uint2))) != LUX_OK) return rc;
     c.frames      = 0;
@@ -473,6 +479,21 @@ static int setup(LuxDDGIContext& c, const LuxTracePushConstants& push)
         LUX_CUDA(cudaGetLastError());
         c.masksDirty = false;
     }
+    if (!(c.flags & LUX_DDGI_FLAG_TRACE_SIMPLE))
+    { // Chunk shape of the march.  Beams (a warp = one probe's rays into a narrow cone) need far fewer sector requests per gather, but their
+      // lanes spread over many z-slices, and a slice of a large volume is a 2 MiB page of its own: measured on B200, beams win while the
+      // full-resolution volume is within the TLB's reach (C4, 256 MiB: 3.28 vs 3.99 ms) and lose beyond it (C5, 2 GiB: 118 vs 91 ms).
+        const size_t sdfBytes = (size_t)c.sdfData.resolution * c.sdfData.resolution * c.sdfData.resolution * c.sdfData.cascadesCount * 2;
+        bool beam = sdfBytes <= (size_t(256) << 20);
+        if (c.flags & LUX_DDGI_FLAG_MARCH_ROWS) beam = false;
+        if (c.flags & LUX_DDGI_FLAG_MARCH_BEAMS) beam = true;
+        if (c.marchBeam != (beam ? 1 : 0))
+        {
+            int rc = init::marchOrder(c, beam);
+            if (rc != LUX_OK)
+                return rc;
+        }
+    }
     mark(c, 0);
     launch_ray_dirs(push.randomOrientation, u.raysPerProbe, (float4*)c.dirs.ptr, (uint2*)c.dirsHalf.ptr, c.stream);
     c.launches += 1;
@@ -517,14 +538,14 @@ static int launch(LuxDDGIContext& c, cudaStream_t s, bool timers)
     p.steps    = nullptr;
     p.records  = (float4*)c.records.ptr;
     p.meta     = (uint32_t*)c.meta.ptr;
-    p.pgOrder  = (const uint32_t*)c.pgOrder.ptr;
-    p.pgIndex  = (const uint32_t*)c.pgIndex.ptr;
+    p.unitOrder = (const uint32_t*)c.unitOrder.ptr;
+    p.unitIndex = (const uint32_t*)c.unitIndex.ptr;
+    p.beam      = c.marchBeam;
     p.rayOrder = (const uint16_t*)c.rayOrder.ptr;
     p.raySlot  = (const uint16_t*)c.raySlot.ptr;
-    p.probeGroups = c.probeGroups;
+    p.probeUnits  = c.probeUnits;
     p.rayClusters = c.rayClusters;
     p.probeMajor  = (c.flags & LUX_DDGI_FLAG_MARCH_PROBE_MAJOR) ? 1 : 0;
-    p.march64     = (c.flags & LUX_DDGI_FLAG_MARCH_64REG) ? 1 : ((c.flags & (1u << 10)) ? 2 : 0); // bit 10: 40 warps at 48 registers (experiment)
     unsigned int* counters = (unsigned int*)c.chunkCounter.ptr; // [0] march chunk counter, [1] hit count
     if (c.sortedIdx.ptr)
     {

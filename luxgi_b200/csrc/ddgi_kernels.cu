@@ -679,15 +679,13 @@ __global__ void __launch_bounds__(32 * TRACE_RAYS_PER_BLOCK) trace_kernel(const 
 //
 // Same arithmetic as trace_kernel, restructured for SIMT convergence (ncu on the simple kernel, C4: 7 of 32 lanes
 // active on average; 11/32 in the march loop, 2/32 in the surface-cache loops — profiles/r1_v1_*):
-//   * a warp owns a pool of 32 probes x TW_RAYS_PER_UNIT directions and its lanes REFILL from the pool as their rays
-//     terminate, so the march loop always runs (almost) full; lanes that refill together take adjacent probes with the
-//     same direction, which keeps their SDF taps on neighbouring rows;
-//   * hits are not shaded where they occur: they go to a per-warp shared-memory queue and are shaded 32 at a time;
+//   * MARCH (march_kernel.inc): persistent warps pull 64-ray chunks (2 probes x 32 angularly adjacent directions) and their lanes REFILL from
+//     the chunk as their rays terminate, so the step loop always runs (almost) full; a finished ray leaves a record;
+//   * hits are not shaded where they occur: they are counting-sorted by culling chunk and shaded in that order (shade_sorted_kernel);
 //   * surface-cache sampling first SCANS the chunk's object list for candidates and then loops over candidates and
 //     tiles, so the expensive tile code is entered by all lanes together.  Tile contributions are accumulated in the
 //     reference's (object, tile) order; skipped terms are exact zeros, so the sums are bit-identical.
 
-constexpr int TW_RAYS_PER_UNIT = 16;
 constexpr int TW_MAX_CAND      = 8;
 constexpr int CAND_STRIDE      = 256; // candidate scratch is [TW_MAX_CAND][256 threads]: conflict-free per lane
 
@@ -1041,22 +1039,20 @@ __device__ __forceinline__ f3 probe_origin(const TraceParams& P, int probeId)
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Stage 1 of the wavefront trace: MARCH.  Persistent warps pull chunks of rays from a global counter; lanes refill
-// from the warp's pool in batches (so ray setup also runs on many lanes) and every loop iteration is one sphere-trace
-// step for all active lanes.  A finished ray leaves a 20-byte record (hit time, hit uvw, cascade, kind, steps);
-// nothing is shaded here, which keeps the register count low and the occupancy high.
-//
-// Ray index g enumerates [probeGroup][rayGroup][rayInUnit (16)][probeLane (32)], so lanes that refill together take
-// adjacent probes with the same direction.
+// Stage 1 of the wavefront trace: MARCH (march_kernel.inc).  Persistent warps pull chunks of rays from a global counter; lanes refill
+// from the warp's chunk in batches and every loop iteration is one sphere-trace step for all active lanes.  A finished ray leaves a 20-byte
+// record (hit time, hit uvw, cascade, kind, steps) and, if it hit, a ticket in the shade's counting sort; nothing is shaded here.
 // ---------------------------------------------------------------------------------------------------------------------
-// Two occupancy points of the march (ptxas keeps the four gathers of a step together from 56 registers up; at 48 it serialises the taps):
-//   6 warps x 6 blocks = 36 warps per SM at 56 registers (default), 8 warps x 4 blocks = 32 warps at 64 registers (LUX_DDGI_FLAG_MARCH_64REG).
+// Occupancy: 8 warps x 4 blocks = 32 warps per SM at 64 registers.  ptxas keeps the four gathers of a step together from 56 registers up (at 48
+// it serialises the two taps to save registers, SASS inspected); measured on B200 (profiles/r2_march_occupancy.md): 48 / 56 / 64 registers =
+// 4.12 / 4.16 / 3.99 ms on C4 and 91.8 / 94.5 / 91.2 ms on C5.
+constexpr int MARCH_WARPS = 8;
+#define MARCH_BLOCKS_PER_SM 4
 #ifndef SHADE_BLOCKS_PER_SM
 #define SHADE_BLOCKS_PER_SM 5
 #endif
-constexpr int MARCH_CHUNK_RAYS  = 64;                                      // rays per pool fetch (8 directions x 32 probes): small, so
+constexpr int MARCH_CHUNK_RAYS  = 64;                                      // rays per pool fetch (2 probes x 32 directions): small, so
                                                                            // that shards with few rays per warp still balance
-constexpr int UNIT_RAYS         = 32 * TW_RAYS_PER_UNIT;                   // 512
 constexpr int MARCH_REFILL_MIN  = 8;                                       // refill when this many lanes are idle
 
 enum RayKind : uint32_t { RAY_MISS = 0, RAY_INSIDE = 1, RAY_HIT = 2 };
@@ -1073,25 +1069,44 @@ __device__ __forceinline__ uint32_t shade_bin(const TraceParams& P, f3 pos)
     return (uint32_t)(((cz * N + cy) * N + cx) * 8 + oct);
 }
 
-// MARCH ORDER.  Chunk c (64 records: 2 ray slots x 32 probe lanes) <-> (probe group, first ray slot); record index = c * 64 + j * 32 + lane.
-// Everything downstream of the march (classify, scatter, shade) addresses records through these two functions.
-struct MarchChunk { uint32_t probeGroup, slot0; };
+// MARCH ORDER (TraceParams::beam).  Chunk c (64 records = [j][lane]) <-> (probe unit, direction cluster[, direction pair]); record index =
+// c * 64 + j * 32 + lane.  Everything downstream of the march (classify, scatter, shade) addresses records through these functions.
+struct MarchChunk { uint32_t probe0, slot0; }; // first probe (shard-local id) and first ray slot of the chunk
+__device__ __forceinline__ void march_split(const TraceParams& P, unsigned int q, unsigned int& cluster, unsigned int& unitIdx)
+{
+    if (P.probeMajor) { cluster = q % (unsigned)P.rayClusters; unitIdx = q / (unsigned)P.rayClusters; }
+    else              { unitIdx = q % (unsigned)P.probeUnits; cluster = q / (unsigned)P.probeUnits; }
+}
+__device__ __forceinline__ unsigned int march_join(const TraceParams& P, unsigned int cluster, unsigned int unitIdx)
+{
+    return P.probeMajor ? unitIdx * (unsigned)P.rayClusters + cluster : cluster * (unsigned)P.probeUnits + unitIdx;
+}
 __device__ __forceinline__ MarchChunk march_chunk(const TraceParams& P, unsigned int c)
 {
-    const unsigned int perPair = MARCH_CLUSTER_RAYS / 2;
-    const unsigned int pair = c % perPair, q = c / perPair;
-    unsigned int cluster, pgIdx;
-    if (P.probeMajor) { cluster = q % (unsigned)P.rayClusters; pgIdx = q / (unsigned)P.rayClusters; }
-    else              { pgIdx = q % (unsigned)P.probeGroups; cluster = q / (unsigned)P.probeGroups; }
-    return {__ldg(P.pgOrder + pgIdx), cluster * MARCH_CLUSTER_RAYS + pair * 2};
+    unsigned int cluster, unitIdx;
+    if (P.beam)
+    {
+        march_split(P, c, cluster, unitIdx);
+        return {__ldg(P.unitOrder + unitIdx) * 2u, cluster * MARCH_CLUSTER_RAYS};
+    }
+    march_split(P, c / (MARCH_CLUSTER_RAYS / 2), cluster, unitIdx);
+    return {__ldg(P.unitOrder + unitIdx) * 32u, cluster * MARCH_CLUSTER_RAYS + (c % (MARCH_CLUSTER_RAYS / 2)) * 2u};
 }
-// record index of (probe group, ray id, probe lane)
-__device__ __forceinline__ uint32_t march_record(const TraceParams& P, uint32_t probeGroup, uint32_t rayId, uint32_t lane)
+// record index of (shard-local probe, ray id)
+__device__ __forceinline__ uint32_t march_record(const TraceParams& P, uint32_t probeLocal, uint32_t rayId)
 {
-    const unsigned int slot = __ldg(P.raySlot + rayId), cluster = slot / MARCH_CLUSTER_RAYS, k = slot % MARCH_CLUSTER_RAYS;
-    const unsigned int pgIdx = __ldg(P.pgIndex + probeGroup);
-    const unsigned int q = P.probeMajor ? pgIdx * (unsigned)P.rayClusters + cluster : cluster * (unsigned)P.probeGroups + pgIdx;
-    return ((q * (MARCH_CLUSTER_RAYS / 2) + (k >> 1)) * 2 + (k & 1)) * 32 + lane;
+    const unsigned int slot = __ldg(P.raySlot + rayId), cluster = slot / MARCH_CLUSTER_RAYS, s = slot % MARCH_CLUSTER_RAYS;
+    if (P.beam)
+        return march_join(P, cluster, __ldg(P.unitIndex + (probeLocal >> 1))) * 64u + (probeLocal & 1u) * 32u + s;
+    const unsigned int c = march_join(P, cluster, __ldg(P.unitIndex + (probeLocal >> 5))) * (MARCH_CLUSTER_RAYS / 2) + (s >> 1);
+    return c * 64u + (s & 1u) * 32u + (probeLocal & 31u);
+}
+struct RayOfRecord { int probeLocal, rayId; };
+__device__ __forceinline__ RayOfRecord march_ray(const TraceParams& P, uint32_t g)
+{
+    const MarchChunk mc = march_chunk(P, g >> 6);
+    const uint32_t j = (g >> 5) & 1u, lane = g & 31u;
+    return {(int)(mc.probe0 + (P.beam ? j : lane)), (int)__ldg(P.rayOrder + mc.slot0 + (P.beam ? lane : j))};
 }
 
 #include "march_kernel.inc"
@@ -1102,74 +1117,55 @@ __device__ __forceinline__ uint32_t march_record(const TraceParams& P, uint32_t 
 // Misses take the sky, inside-geometry rays are black, hits get their normal (six taps) and surface-cache radiance.
 // ---------------------------------------------------------------------------------------------------------------------
 template <bool TEX>
-__global__ void __launch_bounds__(256, SHADE_BLOCKS_PER_SM) shade_kernel(const __grid_constant__ TraceParams P, int rayGroups)
+__global__ void __launch_bounds__(256, SHADE_BLOCKS_PER_SM) shade_kernel(const __grid_constant__ TraceParams P)
 {
-    __shared__ uint2    sRad[32][TRACE_RAYS_PER_BLOCK + 1];
-    __shared__ uint2    sDir[32][TRACE_RAYS_PER_BLOCK + 1];
     __shared__ uint32_t sCand[TW_MAX_CAND + 6][CAND_STRIDE]; // candidates + the six tile normal weights
-
-    const int lane = threadIdx.x & 31, sub = threadIdx.x >> 5; // sub = ray within the block's 8
-    // block b covers half a unit: unit = b / 2, rays (b & 1) * 8 .. + 8 of the unit's 16
-    const long long unit = blockIdx.x >> 1;
-    const int rayInUnit  = ((blockIdx.x & 1) << 3) + sub;
-    const int probeLocal = (int)(unit / rayGroups) * 32 + lane;
-    const int rayId      = (int)(unit % rayGroups) * TW_RAYS_PER_UNIT + rayInUnit;
-    const bool valid     = probeLocal < P.probeCount && rayId < P.raysPerProbe;
-    const uint32_t g     = valid ? march_record(P, (uint32_t)(unit / rayGroups), (uint32_t)rayId, (uint32_t)lane) : 0u;
+    // one thread per ray in [probe][ray] order: consecutive threads write consecutive rays of a probe
+    const long long item = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (item >= (long long)P.probeCount * P.raysPerProbe)
+        return;
+    const int probeLocal = (int)(item / P.raysPerProbe), rayId = (int)(item % P.raysPerProbe);
+    const uint32_t g = march_record(P, (uint32_t)probeLocal, (uint32_t)rayId);
     const SdfSampler<TEX> sdf(P);
     const LuxGlobalSDFData& data = P.sdf;
 
-    if (valid)
+    const float4   rec  = __ldg(P.records + g);
+    const uint32_t meta = __ldg(P.meta + g);
+    const uint32_t hc = meta & 3u, kind = (meta >> 2) & 3u;
+    float4 d4 = __ldg(P.dirs + rayId);
+    f3     d  = {d4.x, d4.y, d4.z};
+    f4     radiance;
+    if (kind == RAY_HIT)
     {
-        const float4   rec  = __ldg(P.records + g);
-        const uint32_t meta = __ldg(P.meta + g);
-        const uint32_t hc = meta & 3u, kind = (meta >> 2) & 3u;
-        float4 d4 = __ldg(P.dirs + rayId);
-        f3     d  = {d4.x, d4.y, d4.z};
-        f4     radiance;
-        if (kind == RAY_HIT)
-        {
-            float4 o4 = __ldg(P.origins + probeLocal);
-            f3     o  = {o4.x, o4.y, o4.z};
-            const float texelOffset = __fdiv_rn(1.0f, data.resolution);
-            float xp = sdf.sampleTex(rec.y + texelOffset, rec.z, rec.w);
-            float xn = sdf.sampleTex(rec.y - texelOffset, rec.z, rec.w);
-            float yp = sdf.sampleTex(rec.y, rec.z + texelOffset, rec.w);
-            float yn = sdf.sampleTex(rec.y, rec.z - texelOffset, rec.w);
-            float zp = sdf.sampleTex(rec.y, rec.z, rec.w + texelOffset);
-            float zn = sdf.sampleTex(rec.y, rec.z, rec.w - texelOffset);
-            f3    normal = normalize3({xp - xn, yp - yn, zp - zn});
-            f3    hitPosition      = o + d * rec.x;
-            float surfaceThreshold = data.cascadeVoxelSize[hc] * 1.05f;
-            f4    sc = sample_global_surface_atlas_2p(P, hitPosition, normal, surfaceThreshold, &sCand[0][threadIdx.x]);
-            radiance   = {sc.x, sc.y, sc.z, rec.x};
-            radiance.w = gmax(radiance.w + data.cascadeVoxelSize[hc] * 0.5f, 0.0f);
-        }
-        else if (kind == RAY_INSIDE)
-            radiance = {0.0f, 0.0f, 0.0f, LUX_GLOBAL_SDF_WORLD_SIZE};
-        else
-        {
-            f3 s     = sample_sky(P, d);
-            radiance = {s.x, s.y, s.z, LUX_GLOBAL_SDF_WORLD_SIZE};
-        }
-        uint32_t r0 = f2h_bits(radiance.x), r1 = f2h_bits(radiance.y), r2 = f2h_bits(radiance.z);
-        uint32_t d0 = f2h_bits(d.x), d1 = f2h_bits(d.y), d2 = f2h_bits(d.z), d3 = f2h_bits(radiance.w);
-        sRad[lane][sub] = make_uint2(r0 | (r1 << 16), r2);
-        sDir[lane][sub] = make_uint2(d0 | (d1 << 16), d2 | (d3 << 16));
-        if (P.steps)
-            P.steps[(size_t)probeLocal * P.raysPerProbe + rayId] = (uint16_t)(meta >> 4);
+        float4 o4 = __ldg(P.origins + probeLocal);
+        f3     o  = {o4.x, o4.y, o4.z};
+        const float texelOffset = __fdiv_rn(1.0f, data.resolution);
+        float xp = sdf.sampleTex(rec.y + texelOffset, rec.z, rec.w);
+        float xn = sdf.sampleTex(rec.y - texelOffset, rec.z, rec.w);
+        float yp = sdf.sampleTex(rec.y, rec.z + texelOffset, rec.w);
+        float yn = sdf.sampleTex(rec.y, rec.z - texelOffset, rec.w);
+        float zp = sdf.sampleTex(rec.y, rec.z, rec.w + texelOffset);
+        float zn = sdf.sampleTex(rec.y, rec.z, rec.w - texelOffset);
+        f3    normal = normalize3({xp - xn, yp - yn, zp - zn});
+        f3    hitPosition      = o + d * rec.x;
+        float surfaceThreshold = data.cascadeVoxelSize[hc] * 1.05f;
+        f4    sc = sample_global_surface_atlas_2p(P, hitPosition, normal, surfaceThreshold, &sCand[0][threadIdx.x]);
+        radiance   = {sc.x, sc.y, sc.z, rec.x};
+        radiance.w = gmax(radiance.w + data.cascadeVoxelSize[hc] * 0.5f, 0.0f);
     }
-    __syncthreads();
-    // transposed write-out: 8 consecutive rays (64 bytes) per probe
-    const int pl = threadIdx.x / TRACE_RAYS_PER_BLOCK, rl = threadIdx.x % TRACE_RAYS_PER_BLOCK;
-    const int oProbe = (int)(unit / rayGroups) * 32 + pl;
-    const int oRay   = (int)(unit % rayGroups) * TW_RAYS_PER_UNIT + ((blockIdx.x & 1) << 3) + rl;
-    if (oProbe < P.probeCount && oRay < P.raysPerProbe)
+    else if (kind == RAY_INSIDE)
+        radiance = {0.0f, 0.0f, 0.0f, LUX_GLOBAL_SDF_WORLD_SIZE};
+    else
     {
-        size_t o = (size_t)oProbe * P.raysPerProbe + oRay;
-        P.radiance[o] = sRad[pl][rl];
-        P.dirDist[o]  = sDir[pl][rl];
+        f3 s     = sample_sky(P, d);
+        radiance = {s.x, s.y, s.z, LUX_GLOBAL_SDF_WORLD_SIZE};
     }
+    uint32_t r0 = f2h_bits(radiance.x), r1 = f2h_bits(radiance.y), r2 = f2h_bits(radiance.z);
+    uint32_t d0 = f2h_bits(d.x), d1 = f2h_bits(d.y), d2 = f2h_bits(d.z), d3 = f2h_bits(radiance.w);
+    P.radiance[item] = make_uint2(r0 | (r1 << 16), r2);
+    P.dirDist[item]  = make_uint2(d0 | (d1 << 16), d2 | (d3 << 16));
+    if (P.steps)
+        P.steps[item] = (uint16_t)(meta >> 4);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -1194,19 +1190,70 @@ constexpr int SORT_BINS             = LUX_SURFACE_ATLAS_CHUNKS_RESOLUTION * LUX_
 constexpr int SCAN_THREADS          = 1024;
 constexpr int SCAN_BINS_PER_BLOCK   = SCAN_THREADS * 4;
 
-// One block = 16 consecutive ray ids x 32 probes of one group; each of the 128 threads owns CLASSIFY_RPT records of the same probe lane and issues
-// all their loads before the first use.  A pure streaming pass since the march takes the sort tickets: 20 bytes in, 16 bytes out per ray.
+// One thread per ray in [probe][ray] order, CLASSIFY_RPT rays per thread with all loads issued before the first use.  Reads are a gather (a
+// probe's rays sit in its clusters' records, 32 at a time), but a block covers whole rows of a probe, so every sector it touches is used completely
+// while it is in L1 / L2; writes are consecutive rays of a probe.  A streaming pass: 20 bytes in, 16 bytes out per ray.
 constexpr int CLASSIFY_RPT = 4;
-__global__ void __launch_bounds__(128, 12) classify_kernel(const __grid_constant__ TraceParams P, int rayGroups)
+__global__ void __launch_bounds__(256) classify_kernel(const __grid_constant__ TraceParams P)
 {
-    __shared__ uint2 sRad[32][TW_RAYS_PER_UNIT + 1];
-    __shared__ uint2 sDir[32][TW_RAYS_PER_UNIT + 1];
+    const LuxGlobalSDFData& data = P.sdf;
+    const long long total = (long long)P.probeCount * P.raysPerProbe;
+    const long long base  = (long long)blockIdx.x * (256 * CLASSIFY_RPT) + threadIdx.x;
+    float4   rec[CLASSIFY_RPT];
+    uint32_t meta[CLASSIFY_RPT];
+    int      ray[CLASSIFY_RPT];
+#pragma unroll
+    for (int k = 0; k < CLASSIFY_RPT; k++)
+    {
+        const long long item = base + k * 256;
+        const bool valid = item < total;
+        const int probeLocal = valid ? (int)(item / P.raysPerProbe) : 0;
+        ray[k] = valid ? (int)(item % P.raysPerProbe) : -1;
+        const uint32_t g = valid ? march_record(P, (uint32_t)probeLocal, (uint32_t)ray[k]) : 0u;
+        rec[k]  = valid ? __ldg(P.records + g) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        meta[k] = valid ? __ldg(P.meta + g) : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < CLASSIFY_RPT; k++)
+    {
+        if (ray[k] < 0)
+            continue;
+        const long long item = base + k * 256;
+        const float4 d4 = __ldg(P.dirs + ray[k]);
+        const uint32_t hc = meta[k] & 3u, kind = (meta[k] >> 2) & 3u;
+        f3 d = {d4.x, d4.y, d4.z};
+        f4 radiance;
+        if (kind == RAY_HIT) // rgb comes from the shade kernel (zero without a surface cache)
+            radiance = {0.0f, 0.0f, 0.0f, gmax(rec[k].x + data.cascadeVoxelSize[hc] * 0.5f, 0.0f)};
+        else if (kind == RAY_INSIDE)
+            radiance = {0.0f, 0.0f, 0.0f, LUX_GLOBAL_SDF_WORLD_SIZE};
+        else
+        {
+            f3 s     = sample_sky(P, d);
+            radiance = {s.x, s.y, s.z, LUX_GLOBAL_SDF_WORLD_SIZE};
+        }
+        uint32_t r0 = f2h_bits(radiance.x), r1 = f2h_bits(radiance.y), r2 = f2h_bits(radiance.z);
+        uint32_t d0 = f2h_bits(d.x), d1 = f2h_bits(d.y), d2 = f2h_bits(d.z), d3 = f2h_bits(radiance.w);
+        P.radiance[item] = make_uint2(r0 | (r1 << 16), r2);
+        P.dirDist[item]  = make_uint2(d0 | (d1 << 16), d2 | (d3 << 16));
+        if (P.steps)
+            P.steps[item] = (uint16_t)(meta[k] >> 4);
+    }
+}
+
+// The same pass for ROW chunks (TraceParams::beam == 0): there the 32 lanes of a record row are 32 x-adjacent probes of one ray, so a block takes
+// 32 probes x 16 consecutive ray ids, reads whole 512-byte record rows and transposes through shared memory to write 128-byte row segments.
+constexpr int CLASSIFY_ROW_RAYS = 16;
+__global__ void __launch_bounds__(128, 12) classify_rows_kernel(const __grid_constant__ TraceParams P, int rayGroups)
+{
+    __shared__ uint2 sRad[32][CLASSIFY_ROW_RAYS + 1];
+    __shared__ uint2 sDir[32][CLASSIFY_ROW_RAYS + 1];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long unit = blockIdx.x;
     const uint32_t probeGroup = (uint32_t)(unit / rayGroups);
     const int probeLocal = (int)probeGroup * 32 + lane;
-    const int rayBase    = (int)(unit % rayGroups) * TW_RAYS_PER_UNIT;
+    const int rayBase    = (int)(unit % rayGroups) * CLASSIFY_ROW_RAYS;
     const LuxGlobalSDFData& data = P.sdf;
     const bool probeValid = probeLocal < P.probeCount;
 
@@ -1219,7 +1266,7 @@ __global__ void __launch_bounds__(128, 12) classify_kernel(const __grid_constant
     {
         const int rayId = rayBase + warp + k * 4;
         valid[k] = probeValid && rayId < P.raysPerProbe;
-        const uint32_t g = valid[k] ? march_record(P, probeGroup, (uint32_t)rayId, (uint32_t)lane) : 0u;
+        const uint32_t g = valid[k] ? march_record(P, (uint32_t)probeLocal, (uint32_t)rayId) : 0u;
         rec[k]   = valid[k] ? __ldcs(P.records + g) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         meta[k]  = valid[k] ? __ldcs(P.meta + g) : 0u;
         d4[k]    = valid[k] ? __ldg(P.dirs + rayId) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -1256,7 +1303,7 @@ __global__ void __launch_bounds__(128, 12) classify_kernel(const __grid_constant
     for (int k = 0; k < CLASSIFY_RPT; k++)
     {
         const int idx = threadIdx.x + k * 128;
-        const int pl = idx / TW_RAYS_PER_UNIT, rl = idx % TW_RAYS_PER_UNIT;
+        const int pl = idx / CLASSIFY_ROW_RAYS, rl = idx % CLASSIFY_ROW_RAYS;
         const int oProbe = (int)probeGroup * 32 + pl;
         const int oRay   = rayBase + rl;
         if (oProbe < P.probeCount && oRay < P.raysPerProbe)
@@ -1353,7 +1400,7 @@ __global__ void __launch_bounds__(256) scatter_kernel(const uint2* __restrict__ 
 }
 
 template <bool TEX>
-__global__ void __launch_bounds__(256, SHADE_BLOCKS_PER_SM) shade_sorted_kernel(const __grid_constant__ TraceParams P, int rayGroups)
+__global__ void __launch_bounds__(256, SHADE_BLOCKS_PER_SM) shade_sorted_kernel(const __grid_constant__ TraceParams P)
 {
     __shared__ uint32_t sCand[TW_MAX_CAND + 6][CAND_STRIDE]; // candidates + the six tile normal weights
     const SdfSampler<TEX> sdf(P);
@@ -1364,9 +1411,8 @@ __global__ void __launch_bounds__(256, SHADE_BLOCKS_PER_SM) shade_sorted_kernel(
     {
         const uint32_t gi   = __ldg(P.sortedIdx + t);
         const uint32_t g    = gi & 0x3fffffffu, hc = gi >> 30;
-        const MarchChunk mc  = march_chunk(P, g >> 6);
-        const int probeLocal = (int)mc.probeGroup * 32 + (int)(g & 31u);
-        const int rayId      = (int)__ldg(P.rayOrder + mc.slot0 + ((g >> 5) & 1u));
+        const RayOfRecord rr = march_ray(P, g);
+        const int probeLocal = rr.probeLocal, rayId = rr.rayId;
         const float4   rec = __ldg(P.records + g);
         float4 d4 = __ldg(P.dirs + rayId);
         float4 o4 = __ldg(P.origins + probeLocal);
@@ -2755,13 +2801,13 @@ void launch_chunk_masks(const uint32_t* chunks, const uint32_t* cull, const LuxO
     chunk_masks_kernel<<<N * N * N, 64, 0, s>>>(chunks, cull, objects, objectInverse, objectsCount, chunkSize, thrMax, masks);
 }
 
-size_t trace_record_count(int probeCount, int raysPerProbe)
+size_t trace_record_count(int probeCount, int raysPerProbe, bool beam)
 {
-    const long long rayGroups   = (raysPerProbe + TW_RAYS_PER_UNIT - 1) / TW_RAYS_PER_UNIT;
-    const long long probeGroups = (probeCount + 31) / 32;
-    const long long units       = rayGroups * probeGroups;
-    return (size_t)(units * UNIT_RAYS);
+    const size_t slots = (size_t)(raysPerProbe + MARCH_CLUSTER_RAYS - 1) / MARCH_CLUSTER_RAYS * MARCH_CLUSTER_RAYS;
+    const size_t unit  = beam ? 2 : 32;
+    return ((size_t)probeCount + unit - 1) / unit * unit * slots; // chunks x 64
 }
+size_t trace_record_capacity(int probeCount, int raysPerProbe) { return trace_record_count(probeCount, raysPerProbe, false); }
 
 void launch_probe_origins(const TraceParams& p, cudaStream_t s)
 {
@@ -2773,11 +2819,18 @@ size_t trace_sort_blocks() { return trace_sort_bins() / SCAN_BINS_PER_BLOCK; }
 
 // classify, scan -> scatter -> shade_sorted (see the comment above classify_kernel); returns the number of launches
 template <bool TEX>
-static int launch_shade_sorted(const TraceParams& p, int rayGroups, long long units, cudaStream_t s)
+static int launch_shade_sorted(const TraceParams& p, cudaStream_t s)
 {
-    const size_t records = (size_t)units * UNIT_RAYS;
+    const size_t records = trace_record_count(p.probeCount, p.raysPerProbe, p.beam != 0);
+    const size_t rays    = (size_t)p.probeCount * p.raysPerProbe;
     const int    nb      = (int)trace_sort_blocks();
-    classify_kernel<<<(unsigned)units, 128, 0, s>>>(p, rayGroups);
+    if (p.beam)
+        classify_kernel<<<(unsigned)((rays + 256 * CLASSIFY_RPT - 1) / (256 * CLASSIFY_RPT)), 256, 0, s>>>(p);
+    else
+    {
+        const int rayGroups = (p.raysPerProbe + CLASSIFY_ROW_RAYS - 1) / CLASSIFY_ROW_RAYS;
+        classify_rows_kernel<<<(unsigned)((size_t)rayGroups * ((p.probeCount + 31) / 32)), 128, 0, s>>>(p, rayGroups);
+    }
     if (!p.hasAtlas)
         return 1; // hits carry no radiance without a surface cache: classify wrote the final values
     scan_reduce_kernel<<<nb, SCAN_THREADS, 0, s>>>((const uint4*)p.binCounts, p.binBlockSums);
@@ -2787,7 +2840,7 @@ static int launch_shade_sorted(const TraceParams& p, int rayGroups, long long un
     long long blocks = (long long)(records + 255) / 256;
     if (blocks > 148ll * SHADE_BLOCKS_PER_SM)
         blocks = 148ll * SHADE_BLOCKS_PER_SM;
-    shade_sorted_kernel<TEX><<<(unsigned)blocks, 256, 0, s>>>(p, rayGroups);
+    shade_sorted_kernel<TEX><<<(unsigned)blocks, 256, 0, s>>>(p);
     return 6;
 }
 
@@ -2825,35 +2878,32 @@ static int launch_wavefront(const TraceParams& pIn, unsigned int* chunkCounter, 
 {
     TraceParams p = pIn;
     march_consts(p);
-    const int rayGroups   = (p.raysPerProbe + TW_RAYS_PER_UNIT - 1) / TW_RAYS_PER_UNIT;
-    const int probeGroups = (p.probeCount + 31) / 32;
-    const long long units = (long long)rayGroups * probeGroups;
-    const int chunks      = (int)(units * (UNIT_RAYS / MARCH_CHUNK_RAYS));
+    const int chunks = (int)(trace_record_count(p.probeCount, p.raysPerProbe, p.beam != 0) / MARCH_CHUNK_RAYS);
     cudaMemsetAsync(chunkCounter, 0, sizeof(unsigned int), s);
     if (p.sortTicket)
         cudaMemsetAsync(p.binCounts, 0, trace_sort_bins() * sizeof(uint32_t), s);
-    auto launch = [&](auto kernel, int warps, int blocksPerSM) {
-        long long blocks = ((long long)chunks + warps - 1) / warps;
-        const long long persistent = 148ll * blocksPerSM; // one resident generation per SM
-        if (blocks > persistent)
-            blocks = persistent;
-        kernel<<<(unsigned)blocks, 32 * warps, 0, s>>>(p, chunks, chunkCounter);
-    };
+    long long blocks = ((long long)chunks + MARCH_WARPS - 1) / MARCH_WARPS;
+    const long long persistent = 148ll * MARCH_BLOCKS_PER_SM; // one resident generation per SM
+    if (blocks > persistent)
+        blocks = persistent;
     if (p.cascades > 1)
-        launch(march_kernel<TEX, true, 8, 4>, 8, 4);
-    else if (p.march64 == 1)
-        launch(march_kernel<TEX, false, 8, 4>, 8, 4);
-    else if (p.march64 == 2)
-        launch(march_kernel<TEX, false, 8, 5>, 8, 5);
+    {
+        if (p.beam) march_kernel<TEX, true, true><<<(unsigned)blocks, 32 * MARCH_WARPS, 0, s>>>(p, chunks, chunkCounter);
+        else        march_kernel<TEX, true, false><<<(unsigned)blocks, 32 * MARCH_WARPS, 0, s>>>(p, chunks, chunkCounter);
+    }
     else
-        launch(march_kernel<TEX, false, 6, 6>, 6, 6);
+    {
+        if (p.beam) march_kernel<TEX, false, true><<<(unsigned)blocks, 32 * MARCH_WARPS, 0, s>>>(p, chunks, chunkCounter);
+        else        march_kernel<TEX, false, false><<<(unsigned)blocks, 32 * MARCH_WARPS, 0, s>>>(p, chunks, chunkCounter);
+    }
     if (afterMarch)
         cudaEventRecord(afterMarch, s);
     if (beforeShade) // the march never reads the surface cache: a pending light-cache upload only gates the shade
         cudaStreamWaitEvent(s, beforeShade, 0);
     if (p.sortedIdx)
-        return 1 + launch_shade_sorted<TEX>(p, rayGroups, units, s);
-    shade_kernel<TEX><<<(unsigned)(units * 2), 256, 0, s>>>(p, rayGroups);
+        return 1 + launch_shade_sorted<TEX>(p, s);
+    const size_t rays = (size_t)p.probeCount * p.raysPerProbe;
+    shade_kernel<TEX><<<(unsigned)((rays + 255) / 256), 256, 0, s>>>(p);
     return 2;
 }
 

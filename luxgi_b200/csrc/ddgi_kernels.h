@@ -43,13 +43,19 @@ struct TraceParams
     const float4* origins;  // [probeCount] probeLocation of this shard's probes
     float4*       records;  // wavefront trace: per ray (hitTime, hit u, v, w), indexed in MARCH ORDER (see MarchOrder)
     uint32_t*     meta;     // wavefront trace: cascade | kind << 2 | steps << 4
-    // march order: the march walks direction clusters (outer) x probe groups (inner) so that the rays in flight form a
-    // narrow beam from a compact block of probes; record index = chunk * 64 + slot.  Tables are built on the host at create time.
-    const uint32_t* pgOrder;  // [probeGroups] visiting order of the 32-probe groups (spatially tiled)
-    const uint32_t* pgIndex;  // [probeGroups] its inverse
-    const uint16_t* rayOrder; // [raySlots]    ray id in each slot: runs of MARCH_CLUSTER_RAYS slots are angularly adjacent directions; >= raysPerProbe = padding
-    const uint16_t* raySlot;  // [raySlots]    its inverse
-    int             probeGroups, rayClusters; // rayClusters = raySlots / MARCH_CLUSTER_RAYS
+    // march order.  A chunk = 64 records = [j = 0..1][lane = 0..31], walked [direction cluster][probe unit] over spatially
+    // tiled probe units; record index = chunk * 64 + j * 32 + lane.  Two shapes of a chunk:
+    //   beam = 1: 2 x-adjacent probes (j) x one cluster of 32 angularly adjacent directions (lane): a warp holds rays that leave one point into
+    //             a narrow cone and share the sectors of their first taps.  Used while the volume's pages fit the TLB (see ddgi_engine.cpp).
+    //   beam = 0: 32 x-adjacent probes (lane) x 2 directions of a cluster (j): a warp holds parallel rays, whose taps stay in two z-slices = two
+    //             2 MiB pages per gather.  Used for volumes beyond the TLB's reach (C5).
+    // Tables are built on the host (init::marchOrder).
+    const uint32_t* unitOrder; // [probeUnits] visiting order of the probe units (pairs or groups of 32), spatially tiled
+    const uint32_t* unitIndex; // [probeUnits] its inverse
+    const uint16_t* rayOrder;  // [raySlots]   ray id in each slot: runs of MARCH_CLUSTER_RAYS slots are angularly adjacent directions; >= raysPerProbe = padding
+    const uint16_t* raySlot;   // [raySlots]   its inverse
+    int             probeUnits, rayClusters; // rayClusters = raySlots / MARCH_CLUSTER_RAYS
+    int             beam;
     // kernel-uniform values of the march, computed once on the host with the same IEEE operations the device would use: they are read straight
     // from the constant bank instead of occupying a register per lane (march_consts())
     struct MarchConsts
@@ -60,8 +66,7 @@ struct TraceParams
         int   mipDm1, texDm1;              // depth - 1
         float cc0[3], cd0, m0, minv0, v0, vinv0; // cascade 0: centre, half extent, 2*cd, 1/(2*cd) or 0, voxel, 1/voxel or 0
     } mc;
-    int             march64;                  // A/B: 32 warps per SM at 64 registers instead of 36 at 56 (LUX_DDGI_FLAG_MARCH_64REG)
-    int             probeMajor;               // 1 = [probe group][cluster] loop nest (the round-1 order; LUX_DDGI_FLAG_MARCH_PROBE_MAJOR), 0 = [cluster][probe group]
+    int             probeMajor;               // 1 = [probe unit][cluster] loop nest over ids as they come (LUX_DDGI_FLAG_MARCH_PROBE_MAJOR), 0 = [cluster][probe unit]
     uint2*        radiance; // [probeCount][R] RGBA16F
     uint2*        dirDist;  // [probeCount][R] RGBA16F
     uint16_t*     steps;    // optional [probeCount][R] march-step counts (debug / roofline counters)
@@ -113,8 +118,9 @@ void launch_tile_zrow(const LuxTileBuffer* tiles, int count, float4* out, cudaSt
 // `afterMarch` (nullable): recorded between the march and the shade kernel (stage timers).
 int    launch_trace(const TraceParams& p, int variant, unsigned int* chunkCounter, cudaStream_t s, cudaEvent_t beforeShade,
                     cudaEvent_t afterMarch);
-constexpr int MARCH_CLUSTER_RAYS = 16; // directions per cluster = ray slots per record unit
-size_t trace_record_count(int probeCount, int raysPerProbe);
+constexpr int MARCH_CLUSTER_RAYS = 32; // directions per cluster = lanes of a warp
+size_t trace_record_count(int probeCount, int raysPerProbe, bool beam);
+size_t trace_record_capacity(int probeCount, int raysPerProbe); // enough for either chunk shape
 size_t trace_sort_bins();   // bins of the sorted shade's counting sort (culling chunks x octants, padded to the scan's block size)
 size_t trace_sort_blocks(); // scan blocks over those bins
 void   launch_probe_origins(const TraceParams& p, cudaStream_t s);

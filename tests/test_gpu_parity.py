@@ -213,7 +213,10 @@ def test_restore_resumes_bit_identically():
                                         (abi.FLAG_SHADE_UNSORTED, "wavefront, hits shaded in ray order"),
                                         (abi.FLAG_SHADE_UNSORTED | abi.FLAG_SDF_LOADS, "wavefront+loads, ray order"),
                                         (abi.FLAG_MARCH_PROBE_MAJOR, "wavefront, probe-major march order"),
-                                        (abi.FLAG_MARCH_PROBE_MAJOR | abi.FLAG_SHADE_UNSORTED, "probe-major march order, ray-order shade")])
+                                        (abi.FLAG_MARCH_PROBE_MAJOR | abi.FLAG_SHADE_UNSORTED, "probe-major march order, ray-order shade"),
+                                        (abi.FLAG_MARCH_ROWS, "row chunks (the shape large volumes get)"),
+                                        (abi.FLAG_MARCH_ROWS | abi.FLAG_SDF_LOADS, "row chunks + loads"),
+                                        (abi.FLAG_MARCH_ROWS | abi.FLAG_MARCH_PROBE_MAJOR | abi.FLAG_SHADE_UNSORTED, "row chunks, probe-major, ray-order shade")])
 @pytest.mark.parametrize("cfg", ["c1", "city64"])
 def test_trace_variants_match_oracle(oracle, flags, name, cfg):
     """Every trace kernel variant (thread-per-ray, wavefront with explicit loads, wavefront with texture gathers)
@@ -236,7 +239,7 @@ def test_ragged_sizes(oracle):
     orc = oracle.OraclePipeline(sc)
     for r in rots:
         orc.update(r)
-    for flags in (0, abi.FLAG_SDF_LOADS, abi.FLAG_TRACE_SIMPLE):
+    for flags in (0, abi.FLAG_MARCH_ROWS, abi.FLAG_SDF_LOADS, abi.FLAG_MARCH_ROWS | abi.FLAG_SDF_LOADS, abi.FLAG_TRACE_SIMPLE):
         pipe = run_engine(sc, rots, flags=flags)
         assert_rays_match(pipe, orc)
         assert_atlases_match(pipe, orc)
@@ -405,8 +408,9 @@ def test_infinite_bounce_refresh_closes_the_loop(oracle):
 
 @pytest.mark.parametrize("cfg", ["city128", "city64"])
 def test_march_work_order_does_not_change_results(oracle, cfg):
-    """The wavefront march visits direction clusters (outer) x spatially tiled probe groups (inner); records are addressed in that order by
-    every later stage.  Three frames (hysteresis on) must equal the oracle bit for bit in the shipped order, in the round-1 probe-major order
+    """The wavefront march visits direction clusters (outer) x spatially tiled probe units (inner), in beam chunks (2 probes x 32 adjacent
+    directions; small volumes) or row chunks (32 probes x 2 directions; volumes beyond the TLB's reach); records are addressed in that order
+    by every later stage.  Three frames (hysteresis on) must equal the oracle bit for bit in both chunk shapes, in probe-major order
     (LUX_DDGI_FLAG_MARCH_PROBE_MAJOR) and with the weights computed on the context's stream (LUX_DDGI_FLAG_NO_PIPELINE)."""
     sc = scenes.build(cfg)
     rots = [scenes.frame_rotation(f) for f in range(3)]
@@ -416,9 +420,11 @@ def test_march_work_order_does_not_change_results(oracle, cfg):
     pipe = run_engine(sc, rots)
     serial = run_engine(sc, rots, flags=abi.FLAG_NO_PIPELINE)
     major = run_engine(sc, rots, flags=abi.FLAG_MARCH_PROBE_MAJOR)
+    rows = run_engine(sc, rots, flags=abi.FLAG_MARCH_ROWS)
+    beams = run_engine(sc, rots, flags=abi.FLAG_MARCH_BEAMS)
     assert_rays_match(pipe, orc)
     assert_atlases_match(pipe, orc)
-    for other in (serial, major):
+    for other in (serial, major, rows, beams):
         assert np.array_equal(pipe.irradiance, other.irradiance) and np.array_equal(pipe.depth, other.depth)
         assert np.array_equal(pipe.radiance, other.radiance) and np.array_equal(pipe.direction_distance, other.direction_distance)
         other.close()
@@ -586,7 +592,8 @@ def test_cascaded_global_sdf_matches_oracle(oracle, cascades):
     orc = oracle.OraclePipeline(sc)
     for r in rots:
         orc.update(r)
-    for flags in (0, abi.FLAG_SDF_LOADS, abi.FLAG_TRACE_SIMPLE, abi.FLAG_SHADE_UNSORTED, abi.FLAG_NO_PREFILTER):
+    for flags in (0, abi.FLAG_SDF_LOADS, abi.FLAG_TRACE_SIMPLE, abi.FLAG_SHADE_UNSORTED, abi.FLAG_NO_PREFILTER, abi.FLAG_MARCH_ROWS,
+                  abi.FLAG_MARCH_ROWS | abi.FLAG_SDF_LOADS):
         pipe = run_engine(sc, rots, flags=flags)
         assert_rays_match(pipe, orc)
         assert_atlases_match(pipe, orc)
