@@ -338,6 +338,16 @@ LUX_API int lux_ddgi_build_global_sdf(LuxDDGIContext* ctx, const LuxGlobalSDFDat
                                       float minObjectRadius);
 /* Rebuilds only the mip of the bound SDF (GlobalSDFMipmap.comp: one 4x min-downsample + 4 flood passes per cascade). */
 LUX_API int lux_ddgi_build_sdf_mip(LuxDDGIContext* ctx);
+/* Per-frame partial refresh of the bound global SDF = the cached path of merge_sdf::system (GlobalDistanceField.cpp:652-657: a cascade is
+ * revisited every 2 / 3 / 5 / 11 frames; :775-848: only chunks whose object lists changed are re-rasterized, then the cascade's mip is rebuilt
+ * and flooded).  The texels of the 32^3-voxel rasterize chunks [chunkMin, chunkMax] (inclusive chunk coordinates, clipped to the volume) of
+ * `cascade` replace the bound ones - in the linear volume AND in the layered-texture copy the trace reads - without re-allocating or re-copying
+ * anything else.  texelsR16F = the region as a dense box [dz][dy][dx] of fp16 texels, dx = 32 * (chunkMax[0] - chunkMin[0] + 1) etc. (clipped
+ * the same way); NULL = "the bound volume is caller-owned device memory (LUX_MEM_DEVICE) and already holds the new texels: refresh the texture
+ * copy of the region only".  rebuildMip != 0 rebuilds the mip of that cascade on device (downsample + 4 flood passes, as the reference does after
+ * any chunk dispatch) and refreshes its texture copy.  Cost is proportional to the region (plus the cascade's mip when asked). */
+LUX_API int lux_ddgi_update_global_sdf_region(LuxDDGIContext* ctx, uint32_t cascade, const int32_t chunkMin[3], const int32_t chunkMax[3],
+                                              const void* texelsR16F, LuxMemKind kind, int32_t rebuildMip);
 /* Reader of the reference's baked .sdf files (cereal binary, SDFBaker.cpp:158-204 / :207-240).  Call with out == NULL to get the sizes:
  * size[3], mipCount and the total number of fp16 texels over all mips; then with a buffer of that many uint16_t (mips back to back). */
 LUX_API int lux_ddgi_sdf_file_read(const char* path, uint32_t size[3], int32_t* mipCount, uint64_t* texels, uint16_t* out);

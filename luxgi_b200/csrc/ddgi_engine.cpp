@@ -104,6 +104,7 @@ struct LuxDDGIContext
     LuxGlobalSDFData sdfData{};
     DeviceBuffer     sdf, mip;
     cudaArray_t         sdfArray = nullptr, mipArray = nullptr;
+    DeviceBuffer        mipScratch;        // one cascade's mip: flood ping-pong of lux_ddgi_update_global_sdf_region (kept between calls)
     cudaTextureObject_t sdfTex = 0, mipTex = 0;
 
     // surface cache
@@ -700,6 +701,19 @@ static void shardLayout(const LuxDDGIUniform& u, int rank, int world, LuxDDGISta
         LUX_CUDA(cudaSetDevice((ctx)->device));                         \
     } while (0)
 
+// Ordering of the surface light cache between the copy stream (host uploads) and its users on the context's stream.
+//   lightAcquire: before any kernel / copy on c->stream that reads or writes c->light - waits for a pending upload.
+//   lightRelease: after it - the next upload on the copy stream waits for this point (evShadeDone = "last use of the light cache on c->stream").
+static void lightAcquire(LuxDDGIContext* c)
+{
+    if (c->lightPending)
+    {
+        cudaStreamWaitEvent(c->stream, c->evLightReady, 0);
+        c->lightPending = false;
+    }
+}
+static void lightRelease(LuxDDGIContext* c) { cudaEventRecord(c->evShadeDone, c->stream); }
+
 extern "C" {
 
 uint32_t lux_ddgi_version(void) { return LUXDDGI_VERSION; }
@@ -836,7 +850,8 @@ int lux_ddgi_destroy(LuxDDGIContext* c)
         cudaStreamSynchronize(c->auxStream);
     DeviceBuffer* all[] = {&c->radiance, &c->directionDepth, &c->irradiance[0], &c->irradiance[1], &c->depth[0], &c->depth[1],
                            &c->dirs, &c->wIrr, &c->wDepth, &c->scaleIrr, &c->scaleDepth, &c->nzIrr, &c->nzDepth, &c->origins, &c->records, &c->meta, &c->chunkCounter, &c->sortTicket, &c->binCounts, &c->binBlockSums, &c->sortedIdx, &c->dirsHalf, &c->sdf, &c->mip, &c->chunks, &c->cull,
-                           &c->objects, &c->objectInverse, &c->chunkMasks, &c->tiles, &c->tileZRow, &c->light, &c->atlasDepth, &c->sky};
+                           &c->objects, &c->objectInverse, &c->chunkMasks, &c->tiles, &c->tileZRow, &c->light, &c->atlasDepth, &c->sky,
+                           &c->unitOrder, &c->unitIndex, &c->rayOrder, &c->raySlot, &c->mipScratch};
     for (DeviceBuffer* b : all)
         b->release();
     releaseSdfTextures(*c);
@@ -930,6 +945,122 @@ int lux_ddgi_set_global_sdf(LuxDDGIContext* c, const LuxGlobalSDFData* data, con
         return rc;
     if (kind == LUX_MEM_HOST)
         LUX_CUDA(cudaStreamSynchronize(c->stream)); // the caller may free its buffers on return
+    return LUX_OK;
+}
+
+static int stageToDevice(LuxDDGIContext* c, const void* src, size_t bytes, LuxMemKind kind, void** dev, bool* owned);
+
+// Copies the box [x0, x0+dx) x [y0, y0+dy) x [z0, z0+dz) of a linear R16F volume of row length `w` texels and `h` rows per slice into the same
+// box of a layered array (layer = z).
+static int refreshLayeredRegion(LuxDDGIContext* c, cudaArray_t arr, const void* linear, int w, int h, int x0, int y0, int z0, int dx, int dy, int dz)
+{
+    cudaMemcpy3DParms cp{};
+    cp.srcPtr   = make_cudaPitchedPtr(const_cast<void*>(linear), (size_t)w * 2, (size_t)w, (size_t)h);
+    cp.srcPos   = make_cudaPos((size_t)x0 * 2, (size_t)y0, (size_t)z0); // x in bytes for pitched pointers
+    cp.dstArray = arr;
+    cp.dstPos   = make_cudaPos((size_t)x0, (size_t)y0, (size_t)z0);     // x in elements for arrays
+    cp.extent   = make_cudaExtent((size_t)dx, (size_t)dy, (size_t)dz);
+    cp.kind     = cudaMemcpyDeviceToDevice;
+    LUX_CUDA(cudaMemcpy3DAsync(&cp, c->stream));
+    return LUX_OK;
+}
+
+int lux_ddgi_update_global_sdf_region(LuxDDGIContext* c, uint32_t cascade, const int32_t chunkMin[3], const int32_t chunkMax[3], const void* texels,
+                                      LuxMemKind kind, int32_t rebuildMip)
+{
+    CHECK_CTX(c);
+    if (!c->hasSdf)
+        return fail(LUX_ERR_NOT_READY, "no global SDF bound (lux_ddgi_set_global_sdf)");
+    if (!chunkMin || !chunkMax || cascade >= c->sdfData.cascadesCount)
+        return fail(LUX_ERR_INVALID_ARG, "bad region arguments");
+    if (!texels && !c->sdf.borrowed)
+        return fail(LUX_ERR_INVALID_ARG, "texels == NULL needs a caller-owned (LUX_MEM_DEVICE) volume that already holds the new texels");
+    const int res = (int)c->sdfData.resolution, casc = (int)c->sdfData.cascadesCount, mres = res / 4, w = res * casc, mw = mres * casc;
+    int lo[3], n[3];
+    for (int i = 0; i < 3; i++)
+    {
+        if (chunkMin[i] > chunkMax[i])
+            return fail(LUX_ERR_INVALID_ARG, "empty chunk range on axis %d", i);
+        lo[i] = std::max(chunkMin[i], 0) * LUX_SDF_RASTERIZE_CHUNK_SIZE;
+        const int hi = std::min((chunkMax[i] + 1) * LUX_SDF_RASTERIZE_CHUNK_SIZE, res);
+        n[i] = hi - lo[i];
+        if (n[i] <= 0)
+            return LUX_OK; // wholly outside the volume: nothing to do (the reference's out-of-range chunks store nothing either)
+    }
+    const int x0 = (int)cascade * res + lo[0];
+    // the trace of the previous frame may still read the volume: everything below is ordered behind it on the context's stream
+    if (texels)
+    {
+        void* dT = nullptr;
+        bool  owned = false;
+        int   rc = stageToDevice(c, texels, (size_t)n[0] * n[1] * n[2] * 2, kind, &dT, &owned);
+        if (rc != LUX_OK)
+            return rc;
+        if (c->sdf.borrowed)
+        { // never write into a caller-owned volume: continue on a private copy
+            void* own = nullptr;
+            cudaError_t e = cudaMalloc(&own, c->sdf.bytes);
+            if (e == cudaSuccess)
+                e = cudaMemcpyAsync(own, c->sdf.ptr, c->sdf.bytes, cudaMemcpyDeviceToDevice, c->stream);
+            if (e != cudaSuccess)
+            {
+                if (owned) cudaFree(dT);
+                return fail(LUX_ERR_OUT_OF_MEMORY, "private copy of the global SDF: %s", cudaGetErrorString(e));
+            }
+            c->sdf.ptr      = own;
+            c->sdf.borrowed = false;
+        }
+        cudaMemcpy3DParms cp{};
+        cp.srcPtr = make_cudaPitchedPtr(dT, (size_t)n[0] * 2, (size_t)n[0], (size_t)n[1]);
+        cp.dstPtr = make_cudaPitchedPtr(c->sdf.ptr, (size_t)w * 2, (size_t)w, (size_t)res);
+        cp.dstPos = make_cudaPos((size_t)x0 * 2, (size_t)lo[1], (size_t)lo[2]);
+        cp.extent = make_cudaExtent((size_t)n[0] * 2, (size_t)n[1], (size_t)n[2]);
+        cp.kind   = cudaMemcpyDeviceToDevice;
+        cudaError_t e = cudaMemcpy3DAsync(&cp, c->stream);
+        if (e == cudaSuccess && owned)
+            e = cudaStreamSynchronize(c->stream);
+        if (owned)
+            cudaFree(dT);
+        if (e != cudaSuccess)
+            return fail(LUX_ERR_CUDA, "update_global_sdf_region: %s", cudaGetErrorString(e));
+    }
+    int rc;
+    if (c->sdfArray && (rc = refreshLayeredRegion(c, c->sdfArray, c->sdf.ptr, w, res, x0, lo[1], lo[2], n[0], n[1], n[2])) != LUX_OK)
+        return rc;
+    if (rebuildMip)
+    {
+        if (c->mip.borrowed)
+        { // the mip becomes library-owned the first time the library rebuilds it
+            void* own = nullptr;
+            LUX_CUDA(cudaMalloc(&own, c->mip.bytes));
+            LUX_CUDA(cudaMemcpyAsync(own, c->mip.ptr, c->mip.bytes, cudaMemcpyDeviceToDevice, c->stream));
+            c->mip.ptr      = own;
+            c->mip.borrowed = false;
+        }
+        const size_t scratchBytes = (size_t)mres * mres * mres * 2;
+        if (c->mipScratch.bytes != scratchBytes)
+        {
+            c->mipScratch.release();
+            LUX_CUDA(cudaMalloc(&c->mipScratch.ptr, scratchBytes));
+            c->mipScratch.bytes = scratchBytes;
+        }
+        uint16_t*   tmp = (uint16_t*)c->mipScratch.ptr;
+        const int   k   = (int)cascade;
+        const float cascadeMaxDistance = c->sdfData.cascadePosDistance[k][3] * 2.0f;
+        lux::launch_sdf_fill(tmp, (size_t)mres * mres * mres, 0x3c00, c->stream);
+        lux::launch_sdf_mip_pass((const uint16_t*)c->sdf.ptr, w, res, (uint16_t*)c->mip.ptr, mw, mres, mres, res, 4, k * res, k * mres, cascadeMaxDistance, c->stream);
+        for (int i = 1; i < 5; i++)
+        {
+            if (i & 1)
+                lux::launch_sdf_mip_pass((const uint16_t*)c->mip.ptr, mw, mres, tmp, mres, mres, mres, mres, 1, k * mres, 0, cascadeMaxDistance, c->stream);
+            else
+                lux::launch_sdf_mip_pass(tmp, mres, mres, (uint16_t*)c->mip.ptr, mw, mres, mres, mres, 1, 0, k * mres, cascadeMaxDistance, c->stream);
+        }
+        c->launches += 6;
+        LUX_CUDA(cudaGetLastError());
+        if (c->mipArray && (rc = refreshLayeredRegion(c, c->mipArray, c->mip.ptr, mw, mres, k * mres, 0, 0, mres, mres, mres)) != LUX_OK)
+            return rc;
+    }
     return LUX_OK;
 }
 
@@ -1091,6 +1222,7 @@ int lux_ddgi_build_global_sdf(LuxDDGIContext* c, const LuxGlobalSDFData* data, c
         const float bmin[3] = {center[0] - D, center[1] - D, center[2] - D}, bmax[3] = {center[0] + D, center[1] + D, center[2] + D};
         const int   mipLevel = std::min(k, 2);
         std::vector<ChunkEntry>          chunks;
+        std::vector<int>                 chunkSlot((size_t)rasterizeChunks * rasterizeChunks * rasterizeChunks, -1); // dense (z, y, x) -> index into `chunks`
         std::vector<int>                 included; // mesh index per object index
         for (int m = 0; m < meshCount; m++)
         {
@@ -1133,22 +1265,25 @@ int lux_ddgi_build_global_sdf(LuxDDGIContext* c, const LuxGlobalSDFData* data, c
             }
             const uint32_t objectIndex = (uint32_t)included.size();
             included.push_back(m);
+            // The reference registers the object with every chunk of the UNCLAMPED range (its clamps are no-ops); chunks outside the volume are
+            // dropped below and do not influence the lists of the chunks inside it, so only the in-range part is walked (an object much larger
+            // than the cascade would otherwise cost (extent / chunkSize)^3 entries).
+            for (int i = 0; i < 3; i++)
+            {
+                cmin[i] = std::max(cmin[i], 0);
+                cmax[i] = std::min(cmax[i], rasterizeChunks - 1);
+            }
             for (int z = cmin[2]; z <= cmax[2]; z++)
                 for (int y = cmin[1]; y <= cmax[1]; y++)
                     for (int x = cmin[0]; x <= cmax[0]; x++)
                     {
-                        ChunkEntry* ch = nullptr;
-                        for (ChunkEntry& e : chunks)
-                            if (e.coord[0] == x && e.coord[1] == y && e.coord[2] == z)
-                            {
-                                ch = &e;
-                                break;
-                            }
-                        if (!ch)
+                        int& slot = chunkSlot[((size_t)z * rasterizeChunks + y) * rasterizeChunks + x];
+                        if (slot < 0)
                         {
+                            slot = (int)chunks.size();
                             chunks.push_back(ChunkEntry{{x, y, z}, 0, {}});
-                            ch = &chunks.back();
                         }
+                        ChunkEntry* ch = &chunks[(size_t)slot];
                         if (ch->count == LUX_SDF_RASTERIZE_MODEL_MAX_COUNT)
                             ch->count = 0; // :515-519 copies the empty next-layer entry over the full one: the list restarts
                         ch->models[ch->count++] = objectIndex;
@@ -1351,6 +1486,7 @@ int lux_ddgi_update_surface_light_cache_rows(LuxDDGIContext* c, const void* ligh
     const size_t rowBytes = (size_t)res * 8;
     if (c->light.borrowed)
     { // never write into a caller-owned buffer: continue on a private copy
+        lightAcquire(c);
         void* own = nullptr;
         LUX_CUDA(cudaMalloc(&own, (size_t)res * rowBytes));
         LUX_CUDA(cudaMemcpyAsync(own, c->light.ptr, (size_t)res * rowBytes, cudaMemcpyDeviceToDevice, c->stream));
@@ -1758,8 +1894,8 @@ int lux_ddgi_wait_fence(LuxDDGIContext* c, uint64_t fence)
     CHECK_CTX(c);
     if (fence == 0 || fence > c->fenceSeq)
         return fail(LUX_ERR_INVALID_ARG, "unknown fence %llu", (unsigned long long)fence);
-    if (c->fenceSeq - fence >= 8)
-        return LUX_OK; // its slot has been reused by a later fence on the same in-order stream: long complete
+    // The slot may have been re-recorded by a later fence (8 slots).  That fence sits later on the same in-order stream, so waiting for it
+    // implies this one: recorded is not the same as executed, hence never "return without waiting".
     LUX_CUDA(cudaEventSynchronize(c->fences[fence % 8]));
     return LUX_OK;
 }
@@ -1897,6 +2033,7 @@ int lux_ddgi_indirect_light(LuxDDGIContext* c, const void* baseLightRGBA16F, int
     if (count < 0 || !texelIndex || !worldPos || !normal || !albedo || !metallic || !cameraPos)
         return fail(LUX_ERR_INVALID_ARG, "bad indirect_light arguments");
     const size_t texels = (size_t)c->atlasData.resolution * c->atlasData.resolution;
+    lightAcquire(c);
     if (c->light.borrowed)
     { // never write into a caller-owned buffer: take a private copy first
         void* own = nullptr;
@@ -1920,6 +2057,7 @@ int lux_ddgi_indirect_light(LuxDDGIContext* c, const void* baseLightRGBA16F, int
     lux::launch_indirect_light(c->uniform, c->irradiance[c->lastWritten].ptr, c->depth[c->lastWritten].ptr, c->light.ptr, dB, count,
                                (const uint32_t*)dT, (const float*)dP, (const float*)dN, (const float*)dA, (const float*)dM, intensity, cameraPos,
                                c->stream);
+    lightRelease(c);
     c->launches += count > 0 ? 1 : 0;
     LUX_CUDA(cudaGetLastError());
     if (oB || oT || oP || oN || oA || oM)
@@ -1948,6 +2086,7 @@ int lux_ddgi_surface_direct_light(LuxDDGIContext* c, const LuxLight* light, cons
     if (count == 0)
         return LUX_OK;
     const size_t texels = (size_t)c->atlasData.resolution * c->atlasData.resolution;
+    lightAcquire(c);
     if (c->light.borrowed)
     { // never write into a caller-owned buffer: take a private copy first
         void* own = nullptr;
@@ -1977,6 +2116,7 @@ int lux_ddgi_surface_direct_light(LuxDDGIContext* c, const LuxLight* light, cons
     {
         lux::launch_direct_light(p, c->sdfTex != 0, *light, cameraPosBias, c->light.ptr, count, (const uint32_t*)dT, (const float*)dP, (const float*)dN,
                                  (const float*)dA, (const float*)dM, c->stream);
+        lightRelease(c);
         c->launches += 1;
         cudaError_t e = cudaGetLastError();
         if (e == cudaSuccess && (oT || oP || oN || oA || oM))
@@ -2068,8 +2208,10 @@ int lux_ddgi_sdf_reflection(LuxDDGIContext* c, const LuxReflectionPushConstants*
         return rc;
     lux::TraceParams p{};
     fillSceneParams(c, p);
+    lightAcquire(c);
     lux::launch_sdf_reflection(p, c->sdfTex != 0, c->uniform, *push, c->irradiance[c->lastWritten].ptr, c->depth[c->lastWritten].ptr, width, height,
                                (const float*)dD, (const float*)dN, (const float*)dP, (const uint32_t*)dS, (const uint32_t*)dR, dO, c->stream);
+    lightRelease(c);
     c->launches += 1;
     LUX_CUDA(cudaGetLastError());
     if (kind != LUX_MEM_DEVICE)
@@ -2117,6 +2259,12 @@ int lux_ddgi_get_surface_light_cache(LuxDDGIContext* c, void** devicePtr, size_t
     CHECK_CTX(c);
     if (!c->hasAtlas || !devicePtr)
         return fail(LUX_ERR_NOT_READY, "no surface cache bound");
+    if (c->lightPending) // a host upload may still be in flight on the copy stream: the pointer handed out is valid for immediate use on ANY stream
+    {
+        LUX_CUDA(cudaEventSynchronize(c->evLightReady));
+        c->lightPending = false;
+    }
+    LUX_CUDA(cudaStreamSynchronize(c->stream)); // ... and so are this library's own writers (direct / indirect light)
     *devicePtr = c->light.ptr;
     if (bytes)
         *bytes = c->light.bytes;

@@ -1572,6 +1572,7 @@ __global__ void __launch_bounds__(256) blend_irradiance_kernel(const __grid_cons
         const int st = c & 1;
         cp_async_wait_all();
         __syncthreads(); // chunk c landed; everybody is done computing chunk c-1
+        int bad = 0; // a non-finite radiance (fp16 Inf / NaN) in this chunk: Inf * 0 would poison texels whose weight is gated to zero
         for (int idx = tid; idx < PB * KC; idx += NT)
         {
             int   p = idx / KC, k = idx % KC;
@@ -1580,10 +1581,11 @@ __global__ void __launch_bounds__(256) blend_irradiance_kernel(const __grid_cons
             dst[0] = h2f_bits((uint16_t)(t.x & 0xffffu));
             dst[1] = h2f_bits((uint16_t)(t.x >> 16));
             dst[2] = h2f_bits((uint16_t)(t.y & 0xffffu));
+            bad |= ((t.x & 0x7c00u) == 0x7c00u) | ((t.x & 0x7c000000u) == 0x7c000000u) | ((t.y & 0x7c00u) == 0x7c00u);
         }
         if (c + 1 < nChunks)
             prefetch((c + 1) * KC, st ^ 1);
-        __syncthreads();
+        const bool anyBad = __syncthreads_or(bad) != 0;
         const float*    B = Bs + st * KC * N;
         const uint32_t* Z = Zs + st * KC;
         // rays of this chunk with a non-zero weight for the warp's texel group (KC == 32: one ballot), visited in ray order
@@ -1597,11 +1599,22 @@ __global__ void __launch_bounds__(256) blend_irradiance_kernel(const __grid_cons
             float4 b0 = *reinterpret_cast<const float4*>(B + k * N + grp * 8);
             float4 b1 = *reinterpret_cast<const float4*>(B + k * N + grp * 8 + 4);
             b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+            if (!anyBad)
+            {
 #pragma unroll
-            for (int i = 0; i < TR; i++)
+                for (int i = 0; i < TR; i++)
 #pragma unroll
-                for (int j = 0; j < 8; j++)
-                    acc[i][j] = __fmaf_rn(a[i], b[j], acc[i][j]);
+                    for (int j = 0; j < 8; j++)
+                        acc[i][j] = __fmaf_rn(a[i], b[j], acc[i][j]);
+            }
+            else
+            { // the reference SKIPS a ray whose weight is below the gate (ProbeUpdate.glsl:93): a gated (zero) weight must not meet an Inf
+#pragma unroll
+                for (int i = 0; i < TR; i++)
+#pragma unroll
+                    for (int j = 0; j < 8; j++)
+                        acc[i][j] = b[j] != 0.0f ? __fmaf_rn(a[i], b[j], acc[i][j]) : acc[i][j];
+            }
         }
     }
     __syncthreads(); // before the epilogue overlays the staging buffers
@@ -1691,6 +1704,7 @@ __global__ void __launch_bounds__(512) blend_depth_kernel(const __grid_constant_
         const int st = c & 1, k0 = c * KC;
         cp_async_wait_all();
         __syncthreads();
+        int bad = 0;
         for (int idx = tid; idx < PB * KC; idx += NT)
         {
             int   p = idx / KC, k = idx % KC;
@@ -1702,11 +1716,12 @@ __global__ void __launch_bounds__(512) blend_depth_kernel(const __grid_constant_
                 if (d == -1.0f)
                     d = P.maxDistance;
             }
+            bad |= !(fabsf(d * d) <= 3.0e38f); // Inf / NaN distance (or one whose square overflows): see the irradiance kernel
             *reinterpret_cast<float2*>(As + k * MS + p * 2) = make_float2(d, d * d);
         }
         if (c + 1 < nChunks)
             prefetch((c + 1) * KC, st ^ 1);
-        __syncthreads();
+        const bool anyBad = __syncthreads_or(bad) != 0;
         const float*    B = Bs + st * KC * N;
         const uint32_t* Z = Zs + st * KC;
         uint32_t live = __ballot_sync(0xffffffffu, ((Z[lane] >> (warp * 2)) & 3u) != 0u);
@@ -1726,11 +1741,22 @@ __global__ void __launch_bounds__(512) blend_depth_kernel(const __grid_constant_
                 float4 b0 = *reinterpret_cast<const float4*>(B + k * N + (warp * 2 + g) * 8);
                 float4 b1 = *reinterpret_cast<const float4*>(B + k * N + (warp * 2 + g) * 8 + 4);
                 b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+                if (!anyBad)
+                {
 #pragma unroll
-                for (int i = 0; i < TR; i++)
+                    for (int i = 0; i < TR; i++)
 #pragma unroll
-                    for (int j = 0; j < 8; j++)
-                        acc[g][i][j] = __fmaf_rn(a[i], b[j], acc[g][i][j]);
+                        for (int j = 0; j < 8; j++)
+                            acc[g][i][j] = __fmaf_rn(a[i], b[j], acc[g][i][j]);
+                }
+                else
+                {
+#pragma unroll
+                    for (int i = 0; i < TR; i++)
+#pragma unroll
+                        for (int j = 0; j < 8; j++)
+                            acc[g][i][j] = b[j] != 0.0f ? __fmaf_rn(a[i], b[j], acc[g][i][j]) : acc[g][i][j];
+                }
             }
         }
     }

@@ -27,7 +27,7 @@ EXPORTS = [
     "lux_ddgi_get_stage_ms", "lux_ddgi_sample_irradiance", "lux_ddgi_sample_probe", "lux_ddgi_indirect_light",
     "lux_ddgi_get_surface_light_cache", "lux_ddgi_build_global_sdf", "lux_ddgi_build_sdf_mip", "lux_ddgi_sdf_file_read", "lux_ddgi_download_fence", "lux_ddgi_wait_fence", "lux_ddgi_set_nccl_comm", "lux_ddgi_update_surface_light_cache_rows", "lux_ddgi_cull_surface_objects",
     "lux_ddgi_get_surface_cull_lists", "lux_ddgi_trace_global_sdf", "lux_ddgi_surface_direct_light",
-    "lux_ddgi_sdf_reflection", "lux_ddgi_sdf_shadow", "lux_ddgi_measure_l2_read_bandwidth",
+    "lux_ddgi_sdf_reflection", "lux_ddgi_sdf_shadow", "lux_ddgi_measure_l2_read_bandwidth", "lux_ddgi_update_global_sdf_region",
 ]
 
 
@@ -84,6 +84,7 @@ def load():
         "lux_ddgi_sdf_shadow": [vp, C.POINTER(abi.Light), vp, C.c_uint32, C.c_float, i32, i32, vp, vp, vp, vp, vp, i32],
         "lux_ddgi_build_global_sdf": [vp, C.POINTER(abi.GlobalSDFData), C.POINTER(abi.MeshSDF), i32, C.c_float],
         "lux_ddgi_build_sdf_mip": [vp],
+        "lux_ddgi_update_global_sdf_region": [vp, C.c_uint32, C.POINTER(C.c_int32), C.POINTER(C.c_int32), vp, C.c_int, C.c_int32],
         "lux_ddgi_download_fence": [vp, C.POINTER(C.c_uint64)],
         "lux_ddgi_wait_fence": [vp, C.c_uint64],
         "lux_ddgi_set_nccl_comm": [vp, vp],
@@ -393,6 +394,16 @@ class DDGIPipeline:
 
     def build_sdf_mip(self):
         _check(self._lib.lux_ddgi_build_sdf_mip(self._h))
+
+    def update_global_sdf_region(self, cascade, chunk_min, chunk_max, texels, rebuild_mip=True):
+        """texels: numpy uint16 / float16 box [dz][dy][dx] of the (clipped) chunk range, or None when the bound device volume was updated in place."""
+        lo = (C.c_int32 * 3)(*[int(v) for v in chunk_min])
+        hi = (C.c_int32 * 3)(*[int(v) for v in chunk_max])
+        ptr = None
+        if texels is not None:
+            texels = np.ascontiguousarray(texels)
+            ptr = texels.ctypes.data_as(C.c_void_p)
+        _check(self._lib.lux_ddgi_update_global_sdf_region(self._h, int(cascade), lo, hi, ptr, abi.MEM_HOST, 1 if rebuild_mip else 0))
 
     @property
     def global_sdf(self):

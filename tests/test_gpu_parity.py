@@ -110,6 +110,37 @@ def test_blend_stage_alone_on_oracle_rays(oracle):
     pipe.close()
 
 
+def test_blend_skips_gated_rays_even_when_their_radiance_is_infinite(oracle):
+    """ProbeUpdate.glsl:93 skips a ray whose weight is below 1e-8; the engine stores such weights as exact zeros and multiplies.  An fp16 Inf
+    radiance (an HDR sky or light cache above 65504 rounded by the RGBA16F store) must therefore not reach texels it is gated from: Inf * 0 is
+    NaN and would stay in the atlas through the hysteresis.  Texels that DO see the ray become Inf in the oracle and the engine alike."""
+    sc = scenes.build("c1")
+    u = sc.uniform
+    osc = oracle.OracleScene(sc)
+    rot = scenes.frame_rotation(0)
+    rad, dd, _, _ = osc.trace(rot)
+    rad = rad.copy()
+    rng = np.random.default_rng(3)
+    for p_, r_ in zip(rng.integers(0, rad.shape[0], 40), rng.integers(0, rad.shape[1], 40)):
+        rad[p_, r_, int(rng.integers(0, 3))] = 0x7c00  # +Inf
+    irr = [oracle.new_atlases(u)[0] for _ in range(2)]
+    dep = [oracle.new_atlases(u)[1] for _ in range(2)]
+    pipe = ddgi.DDGIPipeline(u)
+    for f in range(2):
+        oracle.blend(u, rad, dd, irr[f % 2], dep[f % 2], irr[1 - f % 2], dep[1 - f % 2], first_frame=(f == 0))
+        oracle.border(u, irr[1 - f % 2], dep[1 - f % 2])
+        pipe.set_ray_buffers(rad, dd)
+        pipe.probe_update()
+        pipe.border_update()
+        pipe.end_frame()
+    want, got = irr[0], pipe.irradiance
+    assert np.array_equal(got, want), f"{(got != want).sum()} irradiance values differ"
+    assert np.array_equal(pipe.depth, dep[0])
+    wf = f16(want)[..., :3]
+    assert np.isinf(wf).any() and not np.isnan(wf).any() and np.isfinite(wf).mean() > 0.5  # some texels see the Inf rays, most do not, none is NaN
+    pipe.close()
+
+
 def test_uniform_field_known_answer_on_gpu():
     """SURVEY §7.3 closed form, no oracle involved: every ray returns L and d."""
     u = abi.make_uniform((0, 0, 0), (1, 1, 1), (4, 4, 2), 128, max_distance=6.0, gamma=5.0)

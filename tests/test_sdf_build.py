@@ -242,8 +242,9 @@ def test_c2_dark_room_64_frame_convergence(oracle):
 
 @pytest.mark.gpu
 def test_c3_infinite_bounce_on_the_dark_room(oracle):
-    """BASELINE configs[2]: 32x16x32 probes, 256 rays, previous-frame irradiance fed into the surface-cache lighting (refresh at frame 16,
-    GI_FRAMES cadence): light cache and atlases bit-identical to the oracle after the refresh has been traced."""
+    """BASELINE configs[2] at its specified length: 32x16x32 probes, 256 rays, 64 frames, the previous frame's irradiance fed into
+    the surface-cache lighting every 16 frames (GI_FRAMES cadence; refreshes at frames 16, 32, 48 and 64, the last one traced by a 65th frame).
+    Light cache after every refresh, ray buffers and atlases at the end: bit-identical to the oracle."""
     from luxgi_b200 import ddgi
 
     sc = scenes.build("c3")
@@ -253,17 +254,80 @@ def test_c3_infinite_bounce_on_the_dark_room(oracle):
     orc = oracle.OraclePipeline(sc)
     pipe = ddgi.DDGIPipeline(sc.uniform)
     pipe.set_scene(sc)
-    for f in range(18):
-        if f == 16:
+    means = [float(f16(base)[..., :3].mean())]
+    for f in range(65):
+        if f and f % 16 == 0:
             o_light = base.copy()
             oracle.indirect_light(sc.uniform, orc.irradiance, orc.depth, o_light, base, gb["texel"], gb["pos"], gb["normal"], gb["albedo"], gb["metallic"], 1.2, cam)
             orc.os.light[...] = o_light
             pipe.indirect_light(base, gb["texel"], gb["pos"], gb["normal"], gb["albedo"], gb["metallic"], 1.2, cam)
             got = pipe.surface_light_cache()
-            assert np.array_equal(got, o_light), f"{(got != o_light).sum()} light-cache values differ"
-            assert f16(o_light)[..., :3].mean() > f16(base)[..., :3].mean()
+            assert np.array_equal(got, o_light), f"refresh at frame {f}: {(got != o_light).sum()} light-cache values differ"
+            means.append(float(f16(o_light)[..., :3].mean()))
         rot = scenes.frame_rotation(f)
         orc.update(rot)
         pipe.update(rot)
-    assert np.array_equal(pipe.radiance, orc.rad) and np.array_equal(pipe.irradiance, orc.irradiance) and np.array_equal(pipe.depth, orc.depth)
+    assert len(means) == 5 and means[1] > means[0] and all(b >= a * 0.999 for a, b in zip(means[1:], means[2:])), means  # bounces add energy, then settle
+    assert np.array_equal(pipe.radiance, orc.rad) and np.array_equal(pipe.direction_distance, orc.dd)
+    assert np.array_equal(pipe.irradiance, orc.irradiance) and np.array_equal(pipe.depth, orc.depth)
     pipe.close()
+
+
+@pytest.mark.gpu
+def test_partial_global_sdf_update_equals_full_reupload(oracle):
+    """lux_ddgi_update_global_sdf_region = the cached path of merge_sdf::system (GlobalDistanceField.cpp:652-657, 775-848): patching the texels of
+    a few 32^3 chunks (+ the cascade's mip rebuilt on device) must leave the engine in exactly the state a full re-upload of the modified volume
+    gives: linear volume, mip, layered-texture copy (seen through the trace) - for both SDF read paths, on a two-cascade volume, twice in a row."""
+    from luxgi_b200 import ddgi
+
+    sc = scenes.cornell_scene(res=64, counts=(6, 4, 6), rays=96, atlas_res=256, cascades=2)
+    res, casc = 64, 2
+    rots = [scenes.frame_rotation(f) for f in range(3)]
+    sdf0 = sc.sdf.numpy().view(np.uint16).copy().reshape(res, res, res * casc)
+
+    def with_blob(vol, cascade, centre, radius):
+        """a solid sphere min-merged into one cascade: the kind of change a moved object causes"""
+        out = vol.copy()
+        D = sc.sdf_data.cascadePosDistance[cascade][3]
+        c0 = np.array([sc.sdf_data.cascadePosDistance[cascade][i] for i in range(3)], dtype=np.float32)
+        ax = [(np.arange(res, dtype=np.float32) + 0.5) * (2 * D / res) - D + c0[i] for i in range(3)]
+        Z, Y, X = np.meshgrid(ax[2], ax[1], ax[0], indexing="ij")
+        d = np.sqrt((X - centre[0]) ** 2 + (Y - centre[1]) ** 2 + (Z - centre[2]) ** 2) - radius
+        enc = np.clip(d / (2 * D), -1, 1).astype(np.float16)
+        blk = out[:, :, cascade * res:(cascade + 1) * res].view(np.float16)
+        out[:, :, cascade * res:(cascade + 1) * res] = np.minimum(blk, enc).view(np.uint16)
+        return out
+
+    for flags in (0, abi.FLAG_SDF_LOADS):
+        part = ddgi.DDGIPipeline(sc.uniform, flags=flags)
+        part.set_scene(sc)
+        part.update(rots[0])
+        vol = sdf0
+        for step, (cascade, centre, radius, lo, hi) in enumerate([(0, (0.6, -0.2, 0.5), 0.45, (1, 0, 1), (1, 1, 1)), (1, (-2.5, 1.0, -1.0), 1.1, (0, 0, 0), (0, 1, 1))]):
+            new = with_blob(vol, cascade, centre, radius)
+            x0, x1 = cascade * res + lo[0] * 32, cascade * res + (hi[0] + 1) * 32
+            box = new[lo[2] * 32:(hi[2] + 1) * 32, lo[1] * 32:(hi[1] + 1) * 32, x0:x1]
+            # outside the patched chunks nothing may have changed (else the test would compare apples with oranges)
+            mask = np.ones_like(new, dtype=bool)
+            mask[lo[2] * 32:(hi[2] + 1) * 32, lo[1] * 32:(hi[1] + 1) * 32, x0:x1] = False
+            new[mask] = vol[mask]
+            part.update_global_sdf_region(cascade, lo, hi, box, rebuild_mip=True)
+            part.update(rots[1 + step])
+            full = ddgi.DDGIPipeline(sc.uniform, flags=flags)
+            full.set_scene(sc)
+            full.update(rots[0])
+            if step == 1:
+                full.update(rots[1])  # keep the two contexts at the same frame count (hysteresis)
+            want_mip = oracle.sdf_build_mip(sc.sdf_data, new.reshape(-1))
+            full.set_global_sdf(sc.sdf_data, new.reshape(-1).view(np.float16), np.asarray(want_mip).view(np.float16))
+            full.update(rots[1 + step])
+            assert np.array_equal(part.global_sdf.reshape(-1), new.reshape(-1)), "linear volume differs after the region update"
+            assert np.array_equal(part.global_sdf_mip.reshape(-1), np.asarray(want_mip).reshape(-1)), "mip differs from the oracle's rebuild"
+            if step == 0:  # same history on both sides: everything must agree bit for bit
+                assert np.array_equal(part.direction_distance, full.direction_distance) and np.array_equal(part.radiance, full.radiance)
+                assert np.array_equal(part.irradiance, full.irradiance) and np.array_equal(part.depth, full.depth)
+            else:          # the full context skipped step 0's volume for one frame: compare the rays of this frame only
+                assert np.array_equal(part.direction_distance, full.direction_distance) and np.array_equal(part.radiance, full.radiance)
+            vol = new
+            full.close()
+        part.close()
