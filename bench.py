@@ -387,7 +387,7 @@ def run_lux(args):
     clocks = sampler.stop() if rank == 0 else None
     P_timed = st.probeCount * world  # == P unless --emulate-shard
 
-    e2e_value, e2e_s, light_bytes, d2h_bytes = None, None, 0, 0
+    e2e_value, e2e_s, light_bytes, d2h_bytes, region_ms = None, None, 0, 0, None
     if not args.no_e2e:
         # ---- end to end through the C ABI with host buffers --------------------------------------------------------------
         light_bytes = int(sc.atlas_data.resolution) ** 2 * 8
@@ -443,6 +443,18 @@ def run_lux(args):
 
 
         d2h_bytes = int(pin_irr[0].numel() + pin_dep[0].numel())
+        # per-frame boundary cost of a scene change: one dirty 32^3 rasterize chunk patched into the bound volume + the cascade's mip rebuilt
+        # (lux_ddgi_update_global_sdf_region; the texels are the volume's own, so results do not change)
+        res = int(sc.sdf_data.resolution)
+        if res >= 64 and rank == 0:
+            box = sc.sdf.reshape(res, res, -1)[32:64, 32:64, 32:64].contiguous().cpu().numpy().view(np.uint16)
+            pipe.update_global_sdf_region(0, (1, 1, 1), (1, 1, 1), box, rebuild_mip=True)
+            pipe.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(8):
+                pipe.update_global_sdf_region(0, (1, 1, 1), (1, 1, 1), box, rebuild_mip=True)
+            pipe.synchronize()
+            region_ms = (time.perf_counter() - t0) / 8 * 1e3
     comm_used = comm is not None
     # ---- serialized stage pass: same workload, one batch on one stream, CUDA events around every stage -----------------------
     pipe.close()
@@ -531,6 +543,8 @@ def run_lux(args):
             "clocks": clocks,
             "e2e": None if e2e_value is None else {"value": e2e_value, "unit": UNIT, "ms_per_update": e2e_s / args.steps * 1e3,
                     "h2d_bytes_per_step": (light_bytes // world if comm_used else light_bytes) + 64, "d2h_bytes_per_step": d2h_bytes,
+                    "sdf_region_update_ms": region_ms,
+                    "sdf_region_update_note": "not part of the timed steps: one dirty 32^3 chunk (64 KiB from host memory) patched into the bound global SDF + that cascade's mip rebuilt on device (lux_ddgi_update_global_sdf_region), the per-frame call of a renderer whose scene changed; a full lux_ddgi_set_global_sdf re-upload is the alternative it replaces",
                     "note": "per rank and per step: light cache H2D from pinned memory (N > 1: own 1/N of its rows, all-gathered over NVLink by the library), own atlas rows D2H into pinned memory; the host waits for frame f-1's rows while frame f computes (every frame delivered, one frame late), all copies complete inside the timed region"},
             "gpu_launches": int(launches),
             "multi_gpu_parity": parity,

@@ -955,10 +955,12 @@ static int stageToDevice(LuxDDGIContext* c, const void* src, size_t bytes, LuxMe
 static int refreshLayeredRegion(LuxDDGIContext* c, cudaArray_t arr, const void* linear, int w, int h, int x0, int y0, int z0, int dx, int dy, int dz)
 {
     cudaMemcpy3DParms cp{};
-    cp.srcPtr   = make_cudaPitchedPtr(const_cast<void*>(linear), (size_t)w * 2, (size_t)w, (size_t)h);
-    cp.srcPos   = make_cudaPos((size_t)x0 * 2, (size_t)y0, (size_t)z0); // x in bytes for pitched pointers
+    // the source box starts at the offset pointer (same pitch and slice height), so no srcPos is involved: the runtime documents pointer positions
+    // in bytes but scales them by the array's element size once an array takes part in the copy (measured: a byte offset read the wrong columns)
+    const uint16_t* src = (const uint16_t*)linear + ((size_t)z0 * h + y0) * w + x0;
+    cp.srcPtr   = make_cudaPitchedPtr(const_cast<uint16_t*>(src), (size_t)w * 2, (size_t)w, (size_t)h);
     cp.dstArray = arr;
-    cp.dstPos   = make_cudaPos((size_t)x0, (size_t)y0, (size_t)z0);     // x in elements for arrays
+    cp.dstPos   = make_cudaPos((size_t)x0, (size_t)y0, (size_t)z0);     // array positions are in elements
     cp.extent   = make_cudaExtent((size_t)dx, (size_t)dy, (size_t)dz);
     cp.kind     = cudaMemcpyDeviceToDevice;
     LUX_CUDA(cudaMemcpy3DAsync(&cp, c->stream));
