@@ -2897,6 +2897,7 @@ static void march_consts(TraceParams& p)
     m.cd0 = d.cascadePosDistance[0][3];
     m.m0 = m.cd0 * 2.0f; m.minv0 = exact_reciprocal(m.m0);
     m.v0 = d.cascadeVoxelSize[0]; m.vinv0 = exact_reciprocal(m.v0);
+    m.negZero2 = 0x8000000080000000ull;
 }
 
 template <bool TEX>

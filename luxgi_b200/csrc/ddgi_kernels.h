@@ -65,6 +65,7 @@ struct TraceParams
         float mipW, mipH, texW, texH;      // texture extents as floats
         int   mipDm1, texDm1;              // depth - 1
         float cc0[3], cd0, m0, minv0, v0, vinv0; // cascade 0: centre, half extent, 2*cd, 1/(2*cd) or 0, voxel, 1/voxel or 0
+        unsigned long long negZero2;       // (-0.0f, -0.0f): the addend that turns a packed fma into an exactly rounded packed multiply (march_kernel.inc)
     } mc;
     int             probeMajor;               // 1 = [probe unit][cluster] loop nest over ids as they come (LUX_DDGI_FLAG_MARCH_PROBE_MAJOR), 0 = [cluster][probe unit]
     uint2*        radiance; // [probeCount][R] RGBA16F
