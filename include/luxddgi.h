@@ -251,6 +251,8 @@ enum {
     LUX_DDGI_FLAG_NO_PIPELINE   = 1u << 7, /* lux_ddgi_update computes the blend weights on the context's stream instead of a second one, for A/B */
     LUX_DDGI_FLAG_MARCH_ROWS    = 1u << 9, /* force row chunks in the march (a warp = 32 x-adjacent probes x one direction); default: by volume size */
     LUX_DDGI_FLAG_MARCH_BEAMS   = 1u << 10,/* force beam chunks (a warp = one probe x 32 angularly adjacent directions)                        */
+    LUX_DDGI_FLAG_BLEND_TC      = 1u << 11,/* opt-in: the blend as a tensor-core GEMM (fp16 hi / lo split operands, fp32 accumulation).  NOT the reference's
+                                            * summation order: held to the north-star tolerance (1e-3 relative / 1e-4 absolute), not bit-exact         */
     LUX_DDGI_FLAG_MARCH_PROBE_MAJOR = 1u << 8 /* wavefront march in the round-1 work order (probe groups outermost, ray ids as they come) instead of direction
                                             * clusters outermost over spatially tiled probe groups; same results, for A/B of the DRAM traffic */
 };

@@ -92,6 +92,7 @@ struct LuxDDGIContext
     DeviceBuffer origins, records, meta, chunkCounter; // wavefront trace scratch
     DeviceBuffer sortTicket, binCounts, binBlockSums, sortedIdx; // sorted shade scratch (the hit count lives in chunkCounter[1])
     DeviceBuffer dirsHalf;                                       // [R] fp16 directions for the blend weights (pipelined update)
+    DeviceBuffer tcW[4];                                         // LUX_DDGI_FLAG_BLEND_TC: irradiance hi / lo [64][kPad], depth hi / lo [256][kPad] fp16
     DeviceBuffer unitOrder, unitIndex, rayOrder, raySlot;        // march order tables (init::marchOrder)
     int          probeUnits = 0, rayClusters = 0;
     int          marchBeam  = -1;                                // chunk shape the tables were built for (-1 = none yet)
@@ -410,6 +411,12 @@ static int initializeProbeGrid(LuxDDGIContext& c)
         c.marchBeam = -1; // tables are built by the first trace, when the bound volume decides the chunk shape (trace_rays::setup)
     }
     if ((rc = allocZero(c, c.dirsHalf, (size_t)u.raysPerProbe * sizeof(uint2))) != LUX_OK) return rc;
+    if (c.flags & LUX_DDGI_FLAG_BLEND_TC)
+    {
+        const size_t kPad = (size_t)lux::blend_tc_kpad(u.raysPerProbe);
+        for (int i = 0; i < 4; i++)
+            if ((rc = allocZero(c, c.tcW[i], (i < 2 ? 64 : 256) * kPad * sizeof(uint16_t))) != LUX_OK) return rc;
+    }
     c.frames      = 0;
     c.pingPong    = 0;
     c.lastWritten = 1;
@@ -588,6 +595,12 @@ static void weights(LuxDDGIContext& c, const uint2* dirsHalf, cudaStream_t s)
     const LuxDDGIUniform& u = c.uniform;
     c.launches += launch_blend_weights(dirsHalf, u.raysPerProbe, c.raysPadded, u.sharpness, (float*)c.wIrr.ptr, (float*)c.wDepth.ptr,
                                        (float*)c.scaleIrr.ptr, (float*)c.scaleDepth.ptr, (uint32_t*)c.nzIrr.ptr, (uint32_t*)c.nzDepth.ptr, s);
+    if (c.flags & LUX_DDGI_FLAG_BLEND_TC)
+    {
+        lux::launch_blend_tc_weights((const float*)c.wIrr.ptr, (const float*)c.wDepth.ptr, c.raysPadded, lux::blend_tc_kpad(u.raysPerProbe), (uint16_t*)c.tcW[0].ptr,
+                                     (uint16_t*)c.tcW[1].ptr, (uint16_t*)c.tcW[2].ptr, (uint16_t*)c.tcW[3].ptr, s);
+        c.launches += 2;
+    }
 }
 
 // Blend (+ fused border) of the shard on stream `s`; records evIrr / evDepth after the respective kernel when given.
@@ -620,10 +633,16 @@ static void launch(LuxDDGIContext& c, cudaStream_t s, cudaEvent_t evIrr, cudaEve
     p.outIrr       = (uint2*)c.irradiance[writeIdx].ptr;
     p.prevDepth    = (const uint32_t*)c.depth[c.pingPong].ptr;
     p.outDepth     = (uint32_t*)c.depth[writeIdx].ptr;
-    launch_blend_irradiance(p, s);
+    const bool tc   = (c.flags & LUX_DDGI_FLAG_BLEND_TC) != 0;
+    const int  kPad = lux::blend_tc_kpad(u.raysPerProbe);
+    if (tc)
+        lux::launch_blend_irradiance_tc(p, (const uint16_t*)c.tcW[0].ptr, (const uint16_t*)c.tcW[1].ptr, kPad, s);
+    else
+        launch_blend_irradiance(p, s);
     if (evIrr)
         cudaEventRecord(evIrr, s);
-    launch_blend_depth(p, s);
+    if (!tc || !lux::launch_blend_depth_tc(p, (const uint16_t*)c.tcW[2].ptr, (const uint16_t*)c.tcW[3].ptr, kPad, s))
+        launch_blend_depth(p, s);
     if (evDepth)
         cudaEventRecord(evDepth, s);
     c.launches += 2;
@@ -851,7 +870,7 @@ int lux_ddgi_destroy(LuxDDGIContext* c)
     DeviceBuffer* all[] = {&c->radiance, &c->directionDepth, &c->irradiance[0], &c->irradiance[1], &c->depth[0], &c->depth[1],
                            &c->dirs, &c->wIrr, &c->wDepth, &c->scaleIrr, &c->scaleDepth, &c->nzIrr, &c->nzDepth, &c->origins, &c->records, &c->meta, &c->chunkCounter, &c->sortTicket, &c->binCounts, &c->binBlockSums, &c->sortedIdx, &c->dirsHalf, &c->sdf, &c->mip, &c->chunks, &c->cull,
                            &c->objects, &c->objectInverse, &c->chunkMasks, &c->tiles, &c->tileZRow, &c->light, &c->atlasDepth, &c->sky,
-                           &c->unitOrder, &c->unitIndex, &c->rayOrder, &c->raySlot, &c->mipScratch};
+                           &c->unitOrder, &c->unitIndex, &c->rayOrder, &c->raySlot, &c->mipScratch, &c->tcW[0], &c->tcW[1], &c->tcW[2], &c->tcW[3]};
     for (DeviceBuffer* b : all)
         b->release();
     releaseSdfTextures(*c);

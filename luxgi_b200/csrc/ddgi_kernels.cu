@@ -1524,6 +1524,38 @@ __device__ __forceinline__ void lds_row(const float* __restrict__ p, float* a)
 // max(0, cos) on half of it.  Skipped terms are exact zeros, so every accumulator still sees the reference's sum in ray
 // order.  A fragments are lane-contiguous (conflict-free), B fragments are warp broadcasts.
 
+// Epilogue of the irradiance blend (ProbeUpdate.glsl:133-151 + BorderUpdate.glsl): Cs = [3 * PB rows (probe, channel)][64 texels] weighted sums.
+template <int PB, int NT>
+__device__ __forceinline__ void irradiance_epilogue(const BlendParams& P, const float* Cs, int probe0, int tid)
+{
+    constexpr int N = 64;
+    const uint32_t one = 0x3c00u; // fp16 1.0 (alpha, ProbeUpdate.glsl:150)
+    for (int idx = tid; idx < PB * N; idx += NT)
+    {
+        int p = idx / N, t = idx % N;
+        int probeLocal = probe0 + p;
+        if (probeLocal >= P.probeCount)
+            continue;
+        int   probe = P.probeBegin + probeLocal;
+        float s = __ldg(P.scaleIrr + t);
+        float r = Cs[(p * 3 + 0) * N + t] * s, g = Cs[(p * 3 + 1) * N + t] * s, b = Cs[(p * 3 + 2) * N + t] * s;
+        r = pow_rn(r, P.invGamma);
+        g = pow_rn(g, P.invGamma);
+        b = pow_rn(b, P.invGamma);
+        int i = t & 7, j = t >> 3;
+        int bx = (probe % P.probesPerRow) * 10 + 1, by = (probe / P.probesPerRow) * 10 + 1;
+        if (!P.firstFrame)
+        {
+            f4 prev = unpack_rgba16f(__ldg(P.prevIrr + (size_t)(by + j + 1) * P.irrWidth + (bx + i + 1)));
+            r = mixh(r, prev.x, P.hysteresis);
+            g = mixh(g, prev.y, P.hysteresis);
+            b = mixh(b, prev.z, P.hysteresis);
+        }
+        uint2 o = make_uint2((uint32_t)f2h_bits(r) | ((uint32_t)f2h_bits(g) << 16), (uint32_t)f2h_bits(b) | (one << 16));
+        store_with_border<uint2>(P.outIrr, P.irrWidth, bx, by, 8, i, j, o, P.fuseBorder != 0);
+    }
+}
+
 // Irradiance: PB probes per block, rows m = p*3 + channel (M = 3*PB), 8 warps = the 8 rows of the 8x8 octahedral map.
 template <int PB>
 __global__ void __launch_bounds__(256) blend_irradiance_kernel(const __grid_constant__ BlendParams P)
@@ -1628,7 +1660,14 @@ __global__ void __launch_bounds__(256) blend_irradiance_kernel(const __grid_cons
     }
     __syncthreads();
 
-    const uint32_t one = 0x3c00u; // fp16 1.0 (alpha, ProbeUpdate.glsl:150)
+    irradiance_epilogue<PB, NT>(P, Cs, probe0, tid);
+}
+
+// Epilogue of the depth blend: Cs = [2 * PB rows (probe, {d, d*d})][256 weight-matrix columns].
+template <int PB, int NT>
+__device__ __forceinline__ void depth_epilogue(const BlendParams& P, const float* Cs, int probe0, int tid)
+{
+    constexpr int N = 256;
     for (int idx = tid; idx < PB * N; idx += NT)
     {
         int p = idx / N, t = idx % N;
@@ -1636,22 +1675,19 @@ __global__ void __launch_bounds__(256) blend_irradiance_kernel(const __grid_cons
         if (probeLocal >= P.probeCount)
             continue;
         int   probe = P.probeBegin + probeLocal;
-        float s = __ldg(P.scaleIrr + t);
-        float r = Cs[(p * 3 + 0) * N + t] * s, g = Cs[(p * 3 + 1) * N + t] * s, b = Cs[(p * 3 + 2) * N + t] * s;
-        r = pow_rn(r, P.invGamma);
-        g = pow_rn(g, P.invGamma);
-        b = pow_rn(b, P.invGamma);
-        int i = t & 7, j = t >> 3;
-        int bx = (probe % P.probesPerRow) * 10 + 1, by = (probe / P.probesPerRow) * 10 + 1;
+        int i, j; // column t of the weight matrix -> texel (i, j)
+        depth_texel_of_column(t, i, j);
+        float s = __ldg(P.scaleDepth + (j * 16 + i));
+        float r = Cs[(p * 2 + 0) * N + t] * s, g = Cs[(p * 2 + 1) * N + t] * s;
+        int bx = (probe % P.probesPerRow) * 18 + 1, by = (probe / P.probesPerRow) * 18 + 1;
         if (!P.firstFrame)
         {
-            f4 prev = unpack_rgba16f(__ldg(P.prevIrr + (size_t)(by + j + 1) * P.irrWidth + (bx + i + 1)));
-            r = mixh(r, prev.x, P.hysteresis);
-            g = mixh(g, prev.y, P.hysteresis);
-            b = mixh(b, prev.z, P.hysteresis);
+            uint32_t pv = __ldg(P.prevDepth + (size_t)(by + j + 1) * P.depthWidth + (bx + i + 1));
+            r = mixh(r, h2f_bits((uint16_t)(pv & 0xffffu)), P.hysteresis);
+            g = mixh(g, h2f_bits((uint16_t)(pv >> 16)), P.hysteresis);
         }
-        uint2 o = make_uint2((uint32_t)f2h_bits(r) | ((uint32_t)f2h_bits(g) << 16), (uint32_t)f2h_bits(b) | (one << 16));
-        store_with_border<uint2>(P.outIrr, P.irrWidth, bx, by, 8, i, j, o, P.fuseBorder != 0);
+        uint32_t o = (uint32_t)f2h_bits(r) | ((uint32_t)f2h_bits(g) << 16);
+        store_with_border<uint32_t>(P.outDepth, P.depthWidth, bx, by, 16, i, j, o, P.fuseBorder != 0);
     }
 }
 
@@ -1773,29 +1809,11 @@ __global__ void __launch_bounds__(512) blend_depth_kernel(const __grid_constant_
         }
     __syncthreads();
 
-    for (int idx = tid; idx < PB * N; idx += NT)
-    {
-        int p = idx / N, t = idx % N;
-        int probeLocal = probe0 + p;
-        if (probeLocal >= P.probeCount)
-            continue;
-        int   probe = P.probeBegin + probeLocal;
-        int i, j; // column t of the weight matrix -> texel (i, j)
-        depth_texel_of_column(t, i, j);
-        float s = __ldg(P.scaleDepth + (j * 16 + i));
-        float r = Cs[(p * 2 + 0) * N + t] * s, g = Cs[(p * 2 + 1) * N + t] * s;
-        int bx = (probe % P.probesPerRow) * 18 + 1, by = (probe / P.probesPerRow) * 18 + 1;
-        if (!P.firstFrame)
-        {
-            uint32_t pv = __ldg(P.prevDepth + (size_t)(by + j + 1) * P.depthWidth + (bx + i + 1));
-            r = mixh(r, h2f_bits((uint16_t)(pv & 0xffffu)), P.hysteresis);
-            g = mixh(g, h2f_bits((uint16_t)(pv >> 16)), P.hysteresis);
-        }
-        uint32_t o = (uint32_t)f2h_bits(r) | ((uint32_t)f2h_bits(g) << 16);
-        store_with_border<uint32_t>(P.outDepth, P.depthWidth, bx, by, 16, i, j, o, P.fuseBorder != 0);
-    }
+    depth_epilogue<PB, NT>(P, Cs, probe0, tid);
 }
 
+
+#include "blend_tc.inc"
 
 // Standalone border pass (BorderUpdate.glsl:136-156): one warp-sized group of threads per probe and atlas.
 template <typename T, int SIDE>
@@ -2897,7 +2915,6 @@ static void march_consts(TraceParams& p)
     m.cd0 = d.cascadePosDistance[0][3];
     m.m0 = m.cd0 * 2.0f; m.minv0 = exact_reciprocal(m.m0);
     m.v0 = d.cascadeVoxelSize[0]; m.vinv0 = exact_reciprocal(m.v0);
-    m.negZero2 = 0x8000000080000000ull;
 }
 
 template <bool TEX>
@@ -2988,6 +3005,33 @@ void launch_blend_depth(const BlendParams& p, cudaStream_t s)
         launch_blend_depth_t<32>(p, s);
     else
         launch_blend_depth_t<16>(p, s);
+}
+
+// ---- tensor-core blend (LUX_DDGI_FLAG_BLEND_TC, blend_tc.inc) ----
+int blend_tc_kpad(int raysPerProbe) { return (raysPerProbe + TC_KC - 1) / TC_KC * TC_KC; }
+
+void launch_blend_tc_weights(const float* wIrr, const float* wDepth, int rowsPadded, int kPad, uint16_t* irrHi, uint16_t* irrLo, uint16_t* depthHi,
+                             uint16_t* depthLo, cudaStream_t s)
+{
+    blend_tc_weights_kernel<<<(64 * kPad + 255) / 256, 256, 0, s>>>(wIrr, rowsPadded, kPad, 64, irrHi, irrLo);
+    blend_tc_weights_kernel<<<(256 * kPad + 255) / 256, 256, 0, s>>>(wDepth, rowsPadded, kPad, 256, depthHi, depthLo);
+}
+
+void launch_blend_irradiance_tc(const BlendParams& p, const uint16_t* hi, const uint16_t* lo, int kPad, cudaStream_t s)
+{
+    const size_t smem = 192 * 64 * sizeof(float); // the epilogue overlay is the larger of the two uses
+    cudaFuncSetAttribute(blend_irradiance_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    blend_irradiance_tc_kernel<<<(p.probeCount + 63) / 64, 256, smem, s>>>(p, hi, lo, kPad);
+}
+
+bool launch_blend_depth_tc(const BlendParams& p, const uint16_t* hi, const uint16_t* lo, int kPad, cudaStream_t s)
+{
+    if (!(p.maxDistance * p.maxDistance < 60000.0f)) // d * d must stay inside fp16
+        return false;
+    const size_t smem = (size_t)(2 * 64 + 2 * 256) * TC_LD * sizeof(uint16_t);
+    cudaFuncSetAttribute(blend_depth_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    blend_depth_tc_kernel<<<(p.probeCount + 31) / 32, 256, smem, s>>>(p, hi, lo, kPad);
+    return true;
 }
 
 void launch_border(uint2* irr, int irrWidth, uint32_t* depth, int depthWidth, int probesPerRow, int probeBegin, int probeCount,

@@ -65,7 +65,6 @@ struct TraceParams
         float mipW, mipH, texW, texH;      // texture extents as floats
         int   mipDm1, texDm1;              // depth - 1
         float cc0[3], cd0, m0, minv0, v0, vinv0; // cascade 0: centre, half extent, 2*cd, 1/(2*cd) or 0, voxel, 1/voxel or 0
-        unsigned long long negZero2;       // (-0.0f, -0.0f): the addend that turns a packed fma into an exactly rounded packed multiply (march_kernel.inc)
     } mc;
     int             probeMajor;               // 1 = [probe unit][cluster] loop nest over ids as they come (LUX_DDGI_FLAG_MARCH_PROBE_MAJOR), 0 = [cluster][probe unit]
     uint2*        radiance; // [probeCount][R] RGBA16F
@@ -126,6 +125,12 @@ size_t trace_sort_bins();   // bins of the sorted shade's counting sort (culling
 size_t trace_sort_blocks(); // scan blocks over those bins
 void   launch_probe_origins(const TraceParams& p, cudaStream_t s);
 void launch_blend_irradiance(const BlendParams& p, cudaStream_t s);
+// tensor-core blend (LUX_DDGI_FLAG_BLEND_TC): weights transposed / scaled / split into fp16 hi + lo [n][kPad], then the two GEMM kernels
+int  blend_tc_kpad(int raysPerProbe);
+void launch_blend_tc_weights(const float* wIrr, const float* wDepth, int rowsPadded, int kPad, uint16_t* irrHi, uint16_t* irrLo, uint16_t* depthHi,
+                             uint16_t* depthLo, cudaStream_t s);
+void launch_blend_irradiance_tc(const BlendParams& p, const uint16_t* hi, const uint16_t* lo, int kPad, cudaStream_t s);
+bool launch_blend_depth_tc(const BlendParams& p, const uint16_t* hi, const uint16_t* lo, int kPad, cudaStream_t s); // false: not applicable, use the FP32 kernel
 void launch_blend_depth(const BlendParams& p, cudaStream_t s);
 void launch_border(uint2* irr, int irrWidth, uint32_t* depth, int depthWidth, int probesPerRow, int probeBegin, int probeCount,
                    cudaStream_t s);

@@ -241,6 +241,35 @@ def test_c2_dark_room_64_frame_convergence(oracle):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("cfg,frames", [("c1", 8), ("city64", 8), ("c2", 64)])
+def test_tensor_core_blend_stays_inside_the_north_star_tolerance(oracle, cfg, frames):
+    """LUX_DDGI_FLAG_BLEND_TC: the blend as a tensor-core GEMM (fp16 hi / lo split weights and distances, fp32 accumulation) does not sum in the
+    reference's ray order, so it is held to the north-star tolerance instead of bit-exactness: every atlas texel within 1e-3 relative / 1e-4
+    absolute of the oracle after `frames` frames of hysteresis feedback (64 on BASELINE configs[1]), never more than 2 fp16 ulps away, and the
+    ray buffers - which the blend does not touch - still bit-identical."""
+    from luxgi_b200 import abi, ddgi
+
+    sc = scenes.build(cfg)
+    orc = oracle.OraclePipeline(sc)
+    pipe = ddgi.DDGIPipeline(sc.uniform, flags=abi.FLAG_BLEND_TC)
+    pipe.set_scene(sc)
+    for f in range(frames):
+        rot = scenes.frame_rotation(f)
+        orc.update(rot)
+        pipe.update(rot)
+    assert np.array_equal(pipe.radiance, orc.rad) and np.array_equal(pipe.direction_distance, orc.dd)
+    for name, got, want in (("irradiance", pipe.irradiance, orc.irradiance), ("depth", pipe.depth, orc.depth)):
+        g, w = f16(got), f16(want)
+        assert np.isfinite(g).all()
+        err = np.abs(g - w)
+        assert np.all(err <= 1e-4 + 1e-3 * np.abs(w)), (name, float(err.max()), int((err > 1e-4 + 1e-3 * np.abs(w)).sum()))
+        ulp = np.abs(got.astype(np.int32) - want.astype(np.int32))
+        print(cfg, name, "differing fp16 values", int((ulp > 0).sum()), "of", ulp.size, "max ulp", int(ulp.max()))
+        assert int(ulp.max()) <= 2
+    pipe.close()
+
+
+@pytest.mark.gpu
 def test_c3_infinite_bounce_on_the_dark_room(oracle):
     """BASELINE configs[2] at its specified length: 32x16x32 probes, 256 rays, 64 frames, the previous frame's irradiance fed into
     the surface-cache lighting every 16 frames (GI_FRAMES cadence; refreshes at frames 16, 32, 48 and 64, the last one traced by a 65th frame).
