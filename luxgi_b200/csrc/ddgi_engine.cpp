@@ -554,7 +554,9 @@ static int launch(LuxDDGIContext& c, cudaStream_t s, bool timers)
     p.probeUnits  = c.probeUnits;
     p.rayClusters = c.rayClusters;
     p.probeMajor  = (c.flags & LUX_DDGI_FLAG_MARCH_PROBE_MAJOR) ? 1 : 0;
-    unsigned int* counters = (unsigned int*)c.chunkCounter.ptr; // [0] march chunk counter, [1] hit count
+    unsigned int* counters = (unsigned int*)c.chunkCounter.ptr; // [0] march chunk counter, [1] hit count, [2] non-finite ray value seen
+    p.nonFinite = counters + 2;
+    cudaMemsetAsync(counters + 2, 0, sizeof(unsigned int), s);
     if (c.sortedIdx.ptr)
     {
         p.invChunkSize = c.hasAtlas ? 1.0f / c.atlasData.chunkSize : 0.0f;
@@ -629,6 +631,7 @@ static void launch(LuxDDGIContext& c, cudaStream_t s, cudaEvent_t evIrr, cudaEve
     p.scaleDepth   = (const float*)c.scaleDepth.ptr;
     p.nzIrr        = (const uint32_t*)c.nzIrr.ptr;
     p.nzDepth      = (const uint32_t*)c.nzDepth.ptr;
+    p.nonFinite    = (const uint32_t*)c.chunkCounter.ptr + 2;
     p.prevIrr      = (const uint2*)c.irradiance[c.pingPong].ptr;
     p.outIrr       = (uint2*)c.irradiance[writeIdx].ptr;
     p.prevDepth    = (const uint32_t*)c.depth[c.pingPong].ptr;
@@ -1636,6 +1639,8 @@ int lux_ddgi_set_ray_buffers(LuxDDGIContext* c, const void* radiance, const void
     cudaMemcpyKind k = kind == LUX_MEM_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
     LUX_CUDA(cudaMemcpyAsync(c->radiance.ptr, radiance, bytes, k, c->stream));
     LUX_CUDA(cudaMemcpyAsync(c->directionDepth.ptr, directionDistance, bytes, k, c->stream));
+    // caller-provided rays are not scanned: the blend takes its guarded loop (exact either way, ~4 % slower), see blend_irradiance_kernel
+    LUX_CUDA(cudaMemsetAsync((unsigned int*)c->chunkCounter.ptr + 2, 0xff, sizeof(unsigned int), c->stream));
     LUX_CUDA(cudaStreamSynchronize(c->stream));
     c->raysValid = true;
     return LUX_OK;

@@ -608,6 +608,15 @@ __device__ __forceinline__ f3 sample_sky(const TraceParams& P, f3 d)
 // Thread (x = probe lane, y = ray in group).  A warp holds 32 consecutive probes tracing the SAME ray direction:
 // parallel rays from a row of probes stay spatially coherent (adjacent SDF rows, same surface-cache objects) and
 // terminate after similar step counts, unlike the 32 divergent directions of one probe.
+// fp16 Inf / NaN in any of the packed halves of an RGBA16F texel about to be stored: raise the frame's flag (read by the blend)
+__device__ __forceinline__ void flag_non_finite(const TraceParams& P, uint2 texel)
+{
+    const bool bad = ((texel.x & 0x7c00u) == 0x7c00u) | ((texel.x & 0x7c000000u) == 0x7c000000u) | ((texel.y & 0x7c00u) == 0x7c00u) |
+                     ((texel.y & 0x7c000000u) == 0x7c000000u);
+    if (bad && P.nonFinite)
+        atomicOr(P.nonFinite, 1u);
+}
+
 constexpr int TRACE_RAYS_PER_BLOCK = 8;
 
 __global__ void __launch_bounds__(32 * TRACE_RAYS_PER_BLOCK) trace_kernel(const __grid_constant__ TraceParams P)
@@ -657,6 +666,7 @@ __global__ void __launch_bounds__(32 * TRACE_RAYS_PER_BLOCK) trace_kernel(const 
         uint32_t d0 = f2h_bits(direction.x), d1 = f2h_bits(direction.y), d2 = f2h_bits(direction.z), d3 = f2h_bits(radiance.w);
         sRad[lane][rayInGroup] = make_uint2(r0 | (r1 << 16), r2); // alpha = 0
         sDir[lane][rayInGroup] = make_uint2(d0 | (d1 << 16), d2 | (d3 << 16));
+        flag_non_finite(P, make_uint2(r0 | (r1 << 16), r2 | (d3 << 16)));
         if (P.steps)
             P.steps[(size_t)probeLocal * P.raysPerProbe + rayId] = (uint16_t)hit.steps;
     }
@@ -1057,6 +1067,7 @@ constexpr int MARCH_REFILL_MIN  = 8;                                       // re
 
 enum RayKind : uint32_t { RAY_MISS = 0, RAY_INSIDE = 1, RAY_HIT = 2 };
 
+constexpr int SORT_CELLS_PER_CHUNK = 64;
 // Bin of a hit position.  Only groups work, never enters a result: plain (approximate) arithmetic is fine.
 __device__ __forceinline__ uint32_t shade_bin(const TraceParams& P, f3 pos)
 {
@@ -1065,8 +1076,9 @@ __device__ __forceinline__ uint32_t shade_bin(const TraceParams& P, f3 pos)
     float fx = pos.x * inv + half, fy = pos.y * inv + half, fz = pos.z * inv + half;
     float gx = floorf(fx), gy = floorf(fy), gz = floorf(fz);
     int cx = iclamp((int)gx, 0, N - 1), cy = iclamp((int)gy, 0, N - 1), cz = iclamp((int)gz, 0, N - 1);
-    int oct = ((fz - gz) >= 0.5f ? 4 : 0) | ((fy - gy) >= 0.5f ? 2 : 0) | ((fx - gx) >= 0.5f ? 1 : 0);
-    return (uint32_t)(((cz * N + cy) * N + cx) * 8 + oct);
+    // sub-cell of the chunk = the 4 x 4 x 4 grid of the prefilter masks (chunk_masks_kernel): the hits of a bin share the candidate mask
+    int sx = iclamp((int)((fx - gx) * 4.0f), 0, 3), sy = iclamp((int)((fy - gy) * 4.0f), 0, 3), sz = iclamp((int)((fz - gz) * 4.0f), 0, 3);
+    return (uint32_t)(((cz * N + cy) * N + cx) * SORT_CELLS_PER_CHUNK + ((sz * 4 + sy) * 4 + sx));
 }
 
 // MARCH ORDER (TraceParams::beam).  Chunk c (64 records = [j][lane]) <-> (probe unit, direction cluster[, direction pair]); record index =
@@ -1164,6 +1176,7 @@ __global__ void __launch_bounds__(256, SHADE_BLOCKS_PER_SM) shade_kernel(const _
     uint32_t d0 = f2h_bits(d.x), d1 = f2h_bits(d.y), d2 = f2h_bits(d.z), d3 = f2h_bits(radiance.w);
     P.radiance[item] = make_uint2(r0 | (r1 << 16), r2);
     P.dirDist[item]  = make_uint2(d0 | (d1 << 16), d2 | (d3 << 16));
+    flag_non_finite(P, make_uint2(r0 | (r1 << 16), r2 | (d3 << 16)));
     if (P.steps)
         P.steps[item] = (uint16_t)(meta >> 4);
 }
@@ -1173,7 +1186,7 @@ __global__ void __launch_bounds__(256, SHADE_BLOCKS_PER_SM) shade_kernel(const _
 //
 // In ray order a warp holds hits of 32 parallel rays from a 240-voxel-long row of probes: they fall into ~12 different
 // culling chunks, so the surface-cache loops ran with 13-17 of 32 lanes (ncu, profiles/r1_v5_*).  The sorted form bins every
-// hit by (culling chunk, chunk octant) with a counting sort and shades in bin order: the lanes of a warp then walk the SAME
+// hit by (culling chunk, 4 x 4 x 4 sub-cell of the chunk = the cell of the prefilter masks) with a counting sort and shades in bin order: the lanes of a warp then walk the SAME
 // culled object list with the same prefilter mask and mostly the same tiles, and the whole pass reads each part of the SDF
 // shell and of the surface-cache atlases once (one sweep over the scene; round 1 keyed the sort by 4 M-record output windows
 // first and swept the scene once per window: 105 GB of DRAM traffic on C5).  Per-ray arithmetic is untouched (each ray's
@@ -1181,12 +1194,12 @@ __global__ void __launch_bounds__(256, SHADE_BLOCKS_PER_SM) shade_kernel(const _
 //   march         every hit takes a ticket in its bin when its record is written (one returning atomic, hidden by the march)
 //   classify      one thread per record, ray-order tiling: writes direction+distance for every ray and the final radiance of
 //                 misses / inside rays (coalesced 128-byte row segments)
-//   scan          exclusive prefix sum over the 512 000 bins (3 small kernels)
+//   scan          exclusive prefix sum over the 4 096 000 bins (3 small kernels)
 //   scatter       sortedIdx[prefix[bin] + ticket] = record index; streams the tickets in march order, in which the hits of a bin
 //                 that were ticketed together also sit together, so the 4-byte stores of a sector meet in L2
 //   shade_sorted  persistent grid over the sorted hit list: normal (6 taps) + surface cache; 8-byte radiance store per hit.
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int SORT_BINS             = LUX_SURFACE_ATLAS_CHUNKS_RESOLUTION * LUX_SURFACE_ATLAS_CHUNKS_RESOLUTION * LUX_SURFACE_ATLAS_CHUNKS_RESOLUTION * 8;
+constexpr int SORT_BINS             = LUX_SURFACE_ATLAS_CHUNKS_RESOLUTION * LUX_SURFACE_ATLAS_CHUNKS_RESOLUTION * LUX_SURFACE_ATLAS_CHUNKS_RESOLUTION * SORT_CELLS_PER_CHUNK;
 constexpr int SCAN_THREADS          = 1024;
 constexpr int SCAN_BINS_PER_BLOCK   = SCAN_THREADS * 4;
 
@@ -1236,6 +1249,7 @@ __global__ void __launch_bounds__(256) classify_kernel(const __grid_constant__ T
         uint32_t d0 = f2h_bits(d.x), d1 = f2h_bits(d.y), d2 = f2h_bits(d.z), d3 = f2h_bits(radiance.w);
         P.radiance[item] = make_uint2(r0 | (r1 << 16), r2);
         P.dirDist[item]  = make_uint2(d0 | (d1 << 16), d2 | (d3 << 16));
+        flag_non_finite(P, make_uint2(r0 | (r1 << 16), r2 | (d3 << 16)));
         if (P.steps)
             P.steps[item] = (uint16_t)(meta[k] >> 4);
     }
@@ -1293,6 +1307,7 @@ __global__ void __launch_bounds__(128, 12) classify_rows_kernel(const __grid_con
             uint32_t d0 = f2h_bits(d.x), d1 = f2h_bits(d.y), d2 = f2h_bits(d.z), d3 = f2h_bits(radiance.w);
             sRad[lane][rayInUnit] = make_uint2(r0 | (r1 << 16), r2);
             sDir[lane][rayInUnit] = make_uint2(d0 | (d1 << 16), d2 | (d3 << 16));
+            flag_non_finite(P, make_uint2(r0 | (r1 << 16), r2 | (d3 << 16)));
             if (P.steps)
                 P.steps[(size_t)probeLocal * P.raysPerProbe + rayBase + rayInUnit] = (uint16_t)(meta[k] >> 4);
         }
@@ -1388,15 +1403,26 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(uint4* __restr
     counts[i]  = make_uint4(b, b + v.x, b + v.x + v.y, b + v.x + v.y + v.z);
 }
 
+constexpr int SCATTER_RPT = 4; // records per thread: the pass is a chain ticket -> prefix -> store per record, so loads are batched
 __global__ void __launch_bounds__(256) scatter_kernel(const uint2* __restrict__ ticket, const uint32_t* __restrict__ prefix,
                                                       uint32_t* __restrict__ sortedIdx, size_t records)
 {
-    size_t g = (size_t)blockIdx.x * 256 + threadIdx.x;
-    if (g >= records)
-        return;
-    uint2 t = __ldcs(ticket + g);
-    if (t.x != 0xffffffffu)
-        sortedIdx[__ldg(prefix + t.x) + (t.y & 0x3fffffffu)] = (uint32_t)g | (t.y & 0xc0000000u);
+    const size_t g0 = (size_t)blockIdx.x * (256 * SCATTER_RPT) + threadIdx.x;
+    uint2    t[SCATTER_RPT];
+    uint32_t base[SCATTER_RPT];
+#pragma unroll
+    for (int k = 0; k < SCATTER_RPT; k++)
+    {
+        const size_t g = g0 + (size_t)k * 256;
+        t[k] = g < records ? __ldcs(ticket + g) : make_uint2(0xffffffffu, 0u);
+    }
+#pragma unroll
+    for (int k = 0; k < SCATTER_RPT; k++)
+        base[k] = t[k].x != 0xffffffffu ? __ldg(prefix + t[k].x) : 0u;
+#pragma unroll
+    for (int k = 0; k < SCATTER_RPT; k++)
+        if (t[k].x != 0xffffffffu)
+            sortedIdx[base[k] + (t[k].y & 0x3fffffffu)] = (uint32_t)(g0 + (size_t)k * 256) | (t[k].y & 0xc0000000u);
 }
 
 template <bool TEX>
@@ -1429,6 +1455,7 @@ __global__ void __launch_bounds__(256, SHADE_BLOCKS_PER_SM) shade_sorted_kernel(
         f4    sc = sample_global_surface_atlas_2p(P, hitPosition, normal, surfaceThreshold, &sCand[0][threadIdx.x]);
         uint32_t r0 = f2h_bits(sc.x), r1 = f2h_bits(sc.y), r2 = f2h_bits(sc.z);
         P.radiance[(size_t)probeLocal * P.raysPerProbe + rayId] = make_uint2(r0 | (r1 << 16), r2);
+        flag_non_finite(P, make_uint2(r0 | (r1 << 16), r2));
     }
 }
 
@@ -1573,6 +1600,9 @@ __global__ void __launch_bounds__(256) blend_irradiance_kernel(const __grid_cons
     const int tid = threadIdx.x, lane = tid & 31, grp = tid >> 5;
     const int probe0 = blockIdx.x * PB;
     const int R = P.raysPerProbe;
+    // A non-finite ray value (fp16 Inf / NaN: an HDR sky or light cache beyond 65504) somewhere in the ray buffers - flagged by whoever wrote them.
+    // Inf * 0 would poison texels whose weight is gated to zero, where the reference SKIPS the ray (ProbeUpdate.glsl:93): the guarded loop then.
+    const bool anyBad = P.nonFinite != nullptr && __ldg(P.nonFinite) != 0u;
 
     float acc[TR][8];
 #pragma unroll
@@ -1604,7 +1634,6 @@ __global__ void __launch_bounds__(256) blend_irradiance_kernel(const __grid_cons
         const int st = c & 1;
         cp_async_wait_all();
         __syncthreads(); // chunk c landed; everybody is done computing chunk c-1
-        int bad = 0; // a non-finite radiance (fp16 Inf / NaN) in this chunk: Inf * 0 would poison texels whose weight is gated to zero
         for (int idx = tid; idx < PB * KC; idx += NT)
         {
             int   p = idx / KC, k = idx % KC;
@@ -1613,11 +1642,10 @@ __global__ void __launch_bounds__(256) blend_irradiance_kernel(const __grid_cons
             dst[0] = h2f_bits((uint16_t)(t.x & 0xffffu));
             dst[1] = h2f_bits((uint16_t)(t.x >> 16));
             dst[2] = h2f_bits((uint16_t)(t.y & 0xffffu));
-            bad |= ((t.x & 0x7c00u) == 0x7c00u) | ((t.x & 0x7c000000u) == 0x7c000000u) | ((t.y & 0x7c00u) == 0x7c00u);
         }
         if (c + 1 < nChunks)
             prefetch((c + 1) * KC, st ^ 1);
-        const bool anyBad = __syncthreads_or(bad) != 0;
+        __syncthreads();
         const float*    B = Bs + st * KC * N;
         const uint32_t* Z = Zs + st * KC;
         // rays of this chunk with a non-zero weight for the warp's texel group (KC == 32: one ballot), visited in ray order
@@ -1707,6 +1735,7 @@ __global__ void __launch_bounds__(512) blend_depth_kernel(const __grid_constant_
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int probe0 = blockIdx.x * PB;
     const int R = P.raysPerProbe;
+    const bool anyBad = P.nonFinite != nullptr && __ldg(P.nonFinite) != 0u; // see blend_irradiance_kernel
 
     float acc[2][TR][8];
 #pragma unroll
@@ -1740,7 +1769,6 @@ __global__ void __launch_bounds__(512) blend_depth_kernel(const __grid_constant_
         const int st = c & 1, k0 = c * KC;
         cp_async_wait_all();
         __syncthreads();
-        int bad = 0;
         for (int idx = tid; idx < PB * KC; idx += NT)
         {
             int   p = idx / KC, k = idx % KC;
@@ -1752,12 +1780,11 @@ __global__ void __launch_bounds__(512) blend_depth_kernel(const __grid_constant_
                 if (d == -1.0f)
                     d = P.maxDistance;
             }
-            bad |= !(fabsf(d * d) <= 3.0e38f); // Inf / NaN distance (or one whose square overflows): see the irradiance kernel
             *reinterpret_cast<float2*>(As + k * MS + p * 2) = make_float2(d, d * d);
         }
         if (c + 1 < nChunks)
             prefetch((c + 1) * KC, st ^ 1);
-        const bool anyBad = __syncthreads_or(bad) != 0;
+        __syncthreads();
         const float*    B = Bs + st * KC * N;
         const uint32_t* Z = Zs + st * KC;
         uint32_t live = __ballot_sync(0xffffffffu, ((Z[lane] >> (warp * 2)) & 3u) != 0u);
@@ -2880,7 +2907,7 @@ static int launch_shade_sorted(const TraceParams& p, cudaStream_t s)
     scan_reduce_kernel<<<nb, SCAN_THREADS, 0, s>>>((const uint4*)p.binCounts, p.binBlockSums);
     scan_top_kernel<<<1, SCAN_THREADS, 0, s>>>(p.binBlockSums, nb, p.hitCount);
     scan_apply_kernel<<<nb, SCAN_THREADS, 0, s>>>((uint4*)p.binCounts, p.binBlockSums);
-    scatter_kernel<<<(unsigned)((records + 255) / 256), 256, 0, s>>>(p.sortTicket, p.binCounts, p.sortedIdx, records);
+    scatter_kernel<<<(unsigned)((records + 256 * SCATTER_RPT - 1) / (256 * SCATTER_RPT)), 256, 0, s>>>(p.sortTicket, p.binCounts, p.sortedIdx, records);
     long long blocks = (long long)(records + 255) / 256;
     if (blocks > 148ll * SHADE_BLOCKS_PER_SM)
         blocks = 148ll * SHADE_BLOCKS_PER_SM;

@@ -70,6 +70,7 @@ struct TraceParams
     uint2*        radiance; // [probeCount][R] RGBA16F
     uint2*        dirDist;  // [probeCount][R] RGBA16F
     uint16_t*     steps;    // optional [probeCount][R] march-step counts (debug / roofline counters)
+    uint32_t*     nonFinite; // [1] set when a non-finite fp16 value is written to the ray buffers (the blend then guards gated weights)
     // sorted shade (null sortedIdx = shade in ray order)
     float     invChunkSize;
     uint2*    sortTicket;   // [records] (bin, ticket within bin | cascade << 30) or (0xffffffff, -) for rays that need no shading; written by the march
@@ -96,6 +97,7 @@ struct BlendParams
     const float* scaleDepth; // [256]
     const uint32_t* nzIrr;   // [raysPadded] bit g: texel group g (8 consecutive texels) has a non-zero weight for this ray
     const uint32_t* nzDepth; // [raysPadded]
+    const uint32_t* nonFinite; // [1] (nullable) != 0: the ray buffers may hold fp16 Inf / NaN
     const uint2* prevIrr;  // RGBA16F atlas
     uint2*       outIrr;
     const uint32_t* prevDepth; // RG16F atlas
