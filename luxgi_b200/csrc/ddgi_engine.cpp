@@ -96,6 +96,8 @@ struct LuxDDGIContext
     DeviceBuffer unitOrder, unitIndex, rayOrder, raySlot;        // march order tables (init::marchOrder)
     int          probeUnits = 0, rayClusters = 0;
     int          marchBeam  = -1;                                // chunk shape the tables were built for (-1 = none yet)
+    DeviceBuffer probeTaps;                                      // [probeCount] float2: the first step's taps at each probe position (march step 0)
+    bool         probeTapsDirty = true;                          // the volume or the probe positions changed
 
     cudaStream_t auxStream = nullptr;
     cudaEvent_t  evFork = nullptr, evJoin = nullptr, evWeights = nullptr;
@@ -449,6 +451,7 @@ static int updateOrigins(LuxDDGIContext& c)
     fillVolume(c, p);
     lux::launch_probe_origins(p, c.stream);
     c.launches += 1;
+    c.probeTapsDirty = true;
     LUX_CUDA(cudaGetLastError());
     return LUX_OK;
 }
@@ -554,6 +557,23 @@ static int launch(LuxDDGIContext& c, cudaStream_t s, bool timers)
     p.probeUnits  = c.probeUnits;
     p.rayClusters = c.rayClusters;
     p.probeMajor  = (c.flags & LUX_DDGI_FLAG_MARCH_PROBE_MAJOR) ? 1 : 0;
+    if (!(c.flags & LUX_DDGI_FLAG_TRACE_SIMPLE))
+    { // per-probe cache of the first step's taps (march_kernel.inc): rebuilt when the volume or the probe positions changed
+        if (c.probeTaps.bytes != (size_t)c.probeCount * sizeof(float2))
+        {
+            c.probeTaps.release();
+            LUX_CUDA(cudaMalloc(&c.probeTaps.ptr, (size_t)c.probeCount * sizeof(float2)));
+            c.probeTaps.bytes = (size_t)c.probeCount * sizeof(float2);
+            c.probeTapsDirty  = true;
+        }
+        if (c.probeTapsDirty)
+        {
+            lux::launch_probe_taps(p, c.sdfTex != 0, (float2*)c.probeTaps.ptr, s);
+            c.launches += 1;
+            c.probeTapsDirty = false;
+        }
+        p.probeTaps = (const float2*)c.probeTaps.ptr;
+    }
     unsigned int* counters = (unsigned int*)c.chunkCounter.ptr; // [0] march chunk counter, [1] hit count, [2] non-finite ray value seen
     p.nonFinite = counters + 2;
     cudaMemsetAsync(counters + 2, 0, sizeof(unsigned int), s);
@@ -873,7 +893,7 @@ int lux_ddgi_destroy(LuxDDGIContext* c)
     DeviceBuffer* all[] = {&c->radiance, &c->directionDepth, &c->irradiance[0], &c->irradiance[1], &c->depth[0], &c->depth[1],
                            &c->dirs, &c->wIrr, &c->wDepth, &c->scaleIrr, &c->scaleDepth, &c->nzIrr, &c->nzDepth, &c->origins, &c->records, &c->meta, &c->chunkCounter, &c->sortTicket, &c->binCounts, &c->binBlockSums, &c->sortedIdx, &c->dirsHalf, &c->sdf, &c->mip, &c->chunks, &c->cull,
                            &c->objects, &c->objectInverse, &c->chunkMasks, &c->tiles, &c->tileZRow, &c->light, &c->atlasDepth, &c->sky,
-                           &c->unitOrder, &c->unitIndex, &c->rayOrder, &c->raySlot, &c->mipScratch, &c->tcW[0], &c->tcW[1], &c->tcW[2], &c->tcW[3]};
+                           &c->unitOrder, &c->unitIndex, &c->rayOrder, &c->raySlot, &c->mipScratch, &c->probeTaps, &c->tcW[0], &c->tcW[1], &c->tcW[2], &c->tcW[3]};
     for (DeviceBuffer* b : all)
         b->release();
     releaseSdfTextures(*c);
@@ -943,6 +963,7 @@ static int bindSdfTextures(LuxDDGIContext* c, const LuxGlobalSDFData* data)
     c->sdfData    = *data;
     c->hasSdf     = true;
     c->masksDirty = true;
+    c->probeTapsDirty = true;
     return LUX_OK;
 }
 
@@ -1085,6 +1106,7 @@ int lux_ddgi_update_global_sdf_region(LuxDDGIContext* c, uint32_t cascade, const
         if (c->mipArray && (rc = refreshLayeredRegion(c, c->mipArray, c->mip.ptr, mw, mres, k * mres, 0, 0, mres, mres, mres)) != LUX_OK)
             return rc;
     }
+    c->probeTapsDirty = true; // a probe may sit in the patched chunks
     return LUX_OK;
 }
 

@@ -2944,6 +2944,17 @@ static void march_consts(TraceParams& p)
     m.v0 = d.cascadeVoxelSize[0]; m.vinv0 = exact_reciprocal(m.v0);
 }
 
+void launch_probe_taps(const TraceParams& pIn, bool useTextures, float2* taps, cudaStream_t s)
+{
+    TraceParams p = pIn;
+    march_consts(p);
+    const int grid = (p.probeCount + 127) / 128;
+    if (useTextures)
+        probe_taps_kernel<true><<<grid, 128, 0, s>>>(p, taps);
+    else
+        probe_taps_kernel<false><<<grid, 128, 0, s>>>(p, taps);
+}
+
 template <bool TEX>
 static int launch_wavefront(const TraceParams& pIn, unsigned int* chunkCounter, cudaStream_t s, cudaEvent_t beforeShade, cudaEvent_t afterMarch)
 {

@@ -70,6 +70,7 @@ struct TraceParams
     uint2*        radiance; // [probeCount][R] RGBA16F
     uint2*        dirDist;  // [probeCount][R] RGBA16F
     uint16_t*     steps;    // optional [probeCount][R] march-step counts (debug / roofline counters)
+    const float2* probeTaps; // [probeCount] (mip tap, full-resolution tap) at each probe position in cascade 0, or null (march_kernel.inc: step 0)
     uint32_t*     nonFinite; // [1] set when a non-finite fp16 value is written to the ray buffers (the blend then guards gated weights)
     // sorted shade (null sortedIdx = shade in ray order)
     float     invChunkSize;
@@ -126,6 +127,7 @@ size_t trace_record_capacity(int probeCount, int raysPerProbe); // enough for ei
 size_t trace_sort_bins();   // bins of the sorted shade's counting sort (culling chunks x octants, padded to the scan's block size)
 size_t trace_sort_blocks(); // scan blocks over those bins
 void   launch_probe_origins(const TraceParams& p, cudaStream_t s);
+void   launch_probe_taps(const TraceParams& p, bool useTextures, float2* taps, cudaStream_t s); // per-probe cache of the first step's taps
 void launch_blend_irradiance(const BlendParams& p, cudaStream_t s);
 // tensor-core blend (LUX_DDGI_FLAG_BLEND_TC): weights transposed / scaled / split into fp16 hi + lo [n][kPad], then the two GEMM kernels
 int  blend_tc_kpad(int raysPerProbe);
