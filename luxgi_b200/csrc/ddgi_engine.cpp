@@ -92,6 +92,8 @@ struct LuxDDGIContext
     DeviceBuffer origins, records, meta, chunkCounter; // wavefront trace scratch
     DeviceBuffer sortTicket, binCounts, binBlockSums, sortedIdx; // sorted shade scratch (the hit count lives in chunkCounter[1])
     DeviceBuffer dirsHalf;                                       // [R] fp16 directions for the blend weights (pipelined update)
+    DeviceBuffer blendLists;                                     // live-ray lists of the list blend (lux::BlendLists layout)
+    bool         useBlendLists = false;
     DeviceBuffer tcW[4];                                         // LUX_DDGI_FLAG_BLEND_TC: irradiance hi / lo [64][kPad], depth hi / lo [256][kPad] fp16
     DeviceBuffer unitOrder, unitIndex, rayOrder, raySlot;        // march order tables (init::marchOrder)
     int          probeUnits = 0, rayClusters = 0;
@@ -413,6 +415,9 @@ static int initializeProbeGrid(LuxDDGIContext& c)
         c.marchBeam = -1; // tables are built by the first trace, when the bound volume decides the chunk shape (trace_rays::setup)
     }
     if ((rc = allocZero(c, c.dirsHalf, (size_t)u.raysPerProbe * sizeof(uint2))) != LUX_OK) return rc;
+    c.useBlendLists = !(c.flags & (LUX_DDGI_FLAG_BLEND_TC | LUX_DDGI_FLAG_BLEND_TILES)) &&
+                      ((c.flags & LUX_DDGI_FLAG_BLEND_LISTS) || lux::blend_lists_preferred(c.probeCount));
+    if (c.useBlendLists && (rc = allocZero(c, c.blendLists, lux::blend_lists_bytes(u.raysPerProbe, c.raysPadded))) != LUX_OK) return rc;
     if (c.flags & LUX_DDGI_FLAG_BLEND_TC)
     {
         const size_t kPad = (size_t)lux::blend_tc_kpad(u.raysPerProbe);
@@ -617,6 +622,9 @@ static void weights(LuxDDGIContext& c, const uint2* dirsHalf, cudaStream_t s)
     const LuxDDGIUniform& u = c.uniform;
     c.launches += launch_blend_weights(dirsHalf, u.raysPerProbe, c.raysPadded, u.sharpness, (float*)c.wIrr.ptr, (float*)c.wDepth.ptr,
                                        (float*)c.scaleIrr.ptr, (float*)c.scaleDepth.ptr, (uint32_t*)c.nzIrr.ptr, (uint32_t*)c.nzDepth.ptr, s);
+    if (c.useBlendLists)
+        c.launches += lux::launch_blend_lists((const float*)c.wIrr.ptr, (const float*)c.wDepth.ptr, u.raysPerProbe,
+                                              lux::blend_lists_layout(c.blendLists.ptr, u.raysPerProbe, c.raysPadded), s);
     if (c.flags & LUX_DDGI_FLAG_BLEND_TC)
     {
         lux::launch_blend_tc_weights((const float*)c.wIrr.ptr, (const float*)c.wDepth.ptr, c.raysPadded, lux::blend_tc_kpad(u.raysPerProbe), (uint16_t*)c.tcW[0].ptr,
@@ -658,13 +666,18 @@ static void launch(LuxDDGIContext& c, cudaStream_t s, cudaEvent_t evIrr, cudaEve
     p.outDepth     = (uint32_t*)c.depth[writeIdx].ptr;
     const bool tc   = (c.flags & LUX_DDGI_FLAG_BLEND_TC) != 0;
     const int  kPad = lux::blend_tc_kpad(u.raysPerProbe);
+    const lux::BlendLists lists = c.useBlendLists ? lux::blend_lists_layout(c.blendLists.ptr, u.raysPerProbe, c.raysPadded) : lux::BlendLists{};
     if (tc)
         lux::launch_blend_irradiance_tc(p, (const uint16_t*)c.tcW[0].ptr, (const uint16_t*)c.tcW[1].ptr, kPad, s);
+    else if (c.useBlendLists)
+        lux::launch_blend_irradiance_lists(p, lists, s);
     else
         launch_blend_irradiance(p, s);
     if (evIrr)
         cudaEventRecord(evIrr, s);
-    if (!tc || !lux::launch_blend_depth_tc(p, (const uint16_t*)c.tcW[2].ptr, (const uint16_t*)c.tcW[3].ptr, kPad, s))
+    if (c.useBlendLists)
+        lux::launch_blend_depth_lists(p, lists, s);
+    else if (!tc || !lux::launch_blend_depth_tc(p, (const uint16_t*)c.tcW[2].ptr, (const uint16_t*)c.tcW[3].ptr, kPad, s))
         launch_blend_depth(p, s);
     if (evDepth)
         cudaEventRecord(evDepth, s);
@@ -891,7 +904,7 @@ int lux_ddgi_destroy(LuxDDGIContext* c)
     if (c->auxStream)
         cudaStreamSynchronize(c->auxStream);
     DeviceBuffer* all[] = {&c->radiance, &c->directionDepth, &c->irradiance[0], &c->irradiance[1], &c->depth[0], &c->depth[1],
-                           &c->dirs, &c->wIrr, &c->wDepth, &c->scaleIrr, &c->scaleDepth, &c->nzIrr, &c->nzDepth, &c->origins, &c->records, &c->meta, &c->chunkCounter, &c->sortTicket, &c->binCounts, &c->binBlockSums, &c->sortedIdx, &c->dirsHalf, &c->sdf, &c->mip, &c->chunks, &c->cull,
+                           &c->dirs, &c->blendLists, &c->wIrr, &c->wDepth, &c->scaleIrr, &c->scaleDepth, &c->nzIrr, &c->nzDepth, &c->origins, &c->records, &c->meta, &c->chunkCounter, &c->sortTicket, &c->binCounts, &c->binBlockSums, &c->sortedIdx, &c->dirsHalf, &c->sdf, &c->mip, &c->chunks, &c->cull,
                            &c->objects, &c->objectInverse, &c->chunkMasks, &c->tiles, &c->tileZRow, &c->light, &c->atlasDepth, &c->sky,
                            &c->unitOrder, &c->unitIndex, &c->rayOrder, &c->raySlot, &c->mipScratch, &c->probeTaps, &c->tcW[0], &c->tcW[1], &c->tcW[2], &c->tcW[3]};
     for (DeviceBuffer* b : all)

@@ -1840,6 +1840,7 @@ __global__ void __launch_bounds__(512) blend_depth_kernel(const __grid_constant_
 }
 
 
+#include "blend_lists.inc"
 #include "blend_tc.inc"
 
 // Standalone border pass (BorderUpdate.glsl:136-156): one warp-sized group of threads per probe and atlas.
@@ -3043,6 +3044,49 @@ void launch_blend_depth(const BlendParams& p, cudaStream_t s)
         launch_blend_depth_t<32>(p, s);
     else
         launch_blend_depth_t<16>(p, s);
+}
+
+// ---- list blend (blend_lists.inc) ----
+static size_t align16(size_t v) { return (v + 15) & ~size_t(15); }
+BlendLists blend_lists_layout(void* base, int raysPerProbe, int raysPadded)
+{
+    BlendLists L{};
+    L.cap         = raysPadded + LB_PAD;
+    L.irrPhases   = (raysPerProbe + LBI_KP - 1) / LBI_KP;
+    L.depthPhases = (raysPerProbe + LBD_KP - 1) / LBD_KP;
+    unsigned char* p = static_cast<unsigned char*>(base);
+    L.irrW     = reinterpret_cast<float4*>(p);   p += align16((size_t)LBI_GROUPS * L.cap * sizeof(float4));
+    L.depthW   = reinterpret_cast<float4*>(p);   p += align16((size_t)LBD_GROUPS * L.cap * sizeof(float4));
+    L.irrIdx   = reinterpret_cast<uint16_t*>(p); p += align16((size_t)LBI_GROUPS * L.cap * sizeof(uint16_t));
+    L.depthIdx = reinterpret_cast<uint16_t*>(p); p += align16((size_t)LBD_GROUPS * L.cap * sizeof(uint16_t));
+    L.irrOff   = reinterpret_cast<uint32_t*>(p); p += align16((size_t)LBI_GROUPS * (L.irrPhases + 1) * sizeof(uint32_t));
+    L.depthOff = reinterpret_cast<uint32_t*>(p);
+    return L;
+}
+size_t blend_lists_bytes(int raysPerProbe, int raysPadded)
+{
+    const BlendLists L = blend_lists_layout(nullptr, raysPerProbe, raysPadded);
+    return (size_t)(reinterpret_cast<unsigned char*>(L.depthOff) - static_cast<unsigned char*>(nullptr)) + align16((size_t)LBD_GROUPS * (L.depthPhases + 1) * sizeof(uint32_t));
+}
+int launch_blend_lists(const float* wIrr, const float* wDepth, int raysPerProbe, const BlendLists& lists, cudaStream_t s)
+{
+    blend_lists_kernel<<<LBI_GROUPS + LBD_GROUPS, 32, 0, s>>>(wIrr, wDepth, raysPerProbe, lists);
+    return 1;
+}
+bool blend_lists_preferred(int probeCount) { return probeCount >= 148 * LB_PB; }
+void launch_blend_irradiance_lists(const BlendParams& p, const BlendLists& lists, cudaStream_t s)
+{
+    const size_t smem = (size_t)LBI_KP * 3 * LB_PB * sizeof(float) + (size_t)LB_PB * LBI_RAW_LD * sizeof(uint2) +
+                        (LBI_THREADS / 32) * (2 * sizeof(LbStage) + 2 * sizeof(uint64_t) + 4 * sizeof(int));
+    cudaFuncSetAttribute(blend_irradiance_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); // per launch: the attribute is per device
+    blend_irradiance_lists_kernel<<<(p.probeCount + LB_PB - 1) / LB_PB, LBI_THREADS, smem, s>>>(p, lists);
+}
+void launch_blend_depth_lists(const BlendParams& p, const BlendLists& lists, cudaStream_t s)
+{
+    const size_t smem = (size_t)LBD_KP * LB_PB * sizeof(float) + (size_t)LB_PB * LBD_RAW_LD * sizeof(uint32_t) +
+                        (LBD_THREADS / 32) * (2 * sizeof(LbStage) + 2 * sizeof(uint64_t) + 8 * sizeof(int));
+    cudaFuncSetAttribute(blend_depth_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    blend_depth_lists_kernel<<<(p.probeCount + LB_PB - 1) / LB_PB, LBD_THREADS, smem, s>>>(p, lists);
 }
 
 // ---- tensor-core blend (LUX_DDGI_FLAG_BLEND_TC, blend_tc.inc) ----

@@ -105,6 +105,24 @@ struct BlendParams
     uint32_t*       outDepth;
 };
 
+// Live-ray lists of the list blend (blend_lists.inc): per group of 2 x 2 texels the rays with a non-zero weight, in ray order, with their weights
+struct BlendLists
+{
+    float4*   irrW;     // [16][cap]  weights of the group's four texels
+    uint16_t* irrIdx;   // [16][cap]  byte offset of the ray's values within its staged phase
+    uint32_t* irrOff;   // [16][irrPhases + 1]  list position at which each phase of rays begins
+    float4*   depthW;   // [64][cap]
+    uint16_t* depthIdx; // [64][cap]
+    uint32_t* depthOff; // [64][depthPhases + 1]
+    int       cap, irrPhases, depthPhases;
+};
+size_t     blend_lists_bytes(int raysPerProbe, int raysPadded);
+BlendLists blend_lists_layout(void* base, int raysPerProbe, int raysPadded);
+int        launch_blend_lists(const float* wIrr, const float* wDepth, int raysPerProbe, const BlendLists& lists, cudaStream_t s); // returns the launch count
+bool       blend_lists_preferred(int probeCount); // the list kernels pay off once every SM gets full 64-probe tiles
+void       launch_blend_irradiance_lists(const BlendParams& p, const BlendLists& lists, cudaStream_t s);
+void       launch_blend_depth_lists(const BlendParams& p, const BlendLists& lists, cudaStream_t s);
+
 // per-frame setup: ray directions and the probe-independent blend weights
 // rotation travels as a kernel argument; dirsHalf (nullable) = the same directions rounded to fp16, as the blend reads them
 void launch_ray_dirs(const float* rot16Host, int raysPerProbe, float4* dirs, uint2* dirsHalf, cudaStream_t s);

@@ -317,6 +317,55 @@ def test_large_probe_count_big_tile_kernels(oracle):
     pipe.close()
 
 
+@pytest.mark.parametrize("counts,rays", [((3, 5, 2), 50), ((8, 8, 8), 64), ((5, 4, 7), 300), ((4, 4, 5), 1024)])
+def test_list_blend_equals_oracle_and_tiled_blend(oracle, counts, rays):
+    """The list form of the FP32 blend (blend_lists.inc; the default from 148 x 64 probes per shard, forced here): per group of 2 x 2 texels the
+    frame's rays with a non-zero weight are walked in ray order, so every texel sees the reference's sum (ProbeUpdate.glsl:66-103) - bit for bit
+    the oracle and the tiled kernels.  Ragged cases: probe counts that are no multiple of 64, ray counts that are no multiple of the 64- / 256-ray
+    phases (50: one partial phase; 300: 5 irradiance / 2 depth phases; 1024: 16 / 4), three frames so that the hysteresis branch runs."""
+    sc = scenes.cornell_scene(res=32, counts=counts, rays=rays, atlas_res=256)
+    rots = [scenes.frame_rotation(f) for f in range(3)]
+    orc = oracle.OraclePipeline(sc)
+    for r in rots:
+        orc.update(r)
+    a = run_engine(sc, rots, flags=abi.FLAG_BLEND_LISTS)
+    b = run_engine(sc, rots, flags=abi.FLAG_BLEND_TILES)
+    c = run_engine(sc, rots, flags=abi.FLAG_BLEND_LISTS | abi.FLAG_UNFUSED_BORDER, staged=True)
+    for p_ in (a, b, c):
+        assert_atlases_match(p_, orc)
+    assert np.array_equal(a.irradiance, b.irradiance) and np.array_equal(a.depth, b.depth)
+    assert np.array_equal(a.irradiance, c.irradiance) and np.array_equal(a.depth, c.depth)
+    for p_ in (a, b, c):
+        p_.close()
+
+
+def test_list_blend_skips_gated_rays_with_infinite_radiance(oracle):
+    """Same contract as the tiled kernels (test_blend_skips_gated_rays_...): a gated (zero) weight must not meet an fp16 Inf."""
+    sc = scenes.build("c1")
+    u = sc.uniform
+    osc = oracle.OracleScene(sc)
+    rad, dd, _, _ = osc.trace(scenes.frame_rotation(0))
+    rad = rad.copy()
+    rng = np.random.default_rng(5)
+    for p_, r_ in zip(rng.integers(0, rad.shape[0], 40), rng.integers(0, rad.shape[1], 40)):
+        rad[p_, r_, int(rng.integers(0, 3))] = 0x7c00  # +Inf
+    irr = [oracle.new_atlases(u)[0] for _ in range(2)]
+    dep = [oracle.new_atlases(u)[1] for _ in range(2)]
+    pipe = ddgi.DDGIPipeline(u, flags=abi.FLAG_BLEND_LISTS)
+    for f in range(2):
+        oracle.blend(u, rad, dd, irr[f % 2], dep[f % 2], irr[1 - f % 2], dep[1 - f % 2], first_frame=(f == 0))
+        oracle.border(u, irr[1 - f % 2], dep[1 - f % 2])
+        pipe.set_ray_buffers(rad, dd)
+        pipe.probe_update()
+        pipe.border_update()
+        pipe.end_frame()
+    assert np.array_equal(pipe.irradiance, irr[0]), f"{(pipe.irradiance != irr[0]).sum()} irradiance values differ"
+    assert np.array_equal(pipe.depth, dep[0])
+    wf = f16(irr[0])[..., :3]
+    assert np.isinf(wf).any() and not np.isnan(wf).any()
+    pipe.close()
+
+
 def probe_tiles(atlas, u, ids, side):
     S = side + 2
     per_row = u.probeCounts[0] * u.probeCounts[1]
