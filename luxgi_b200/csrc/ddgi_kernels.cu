@@ -1064,6 +1064,8 @@ constexpr int MARCH_WARPS = 8;
 constexpr int MARCH_CHUNK_RAYS  = 64;                                      // rays per pool fetch (2 probes x 32 directions): small, so
                                                                            // that shards with few rays per warp still balance
 constexpr int MARCH_REFILL_MIN  = 8;                                       // refill when this many lanes are idle
+constexpr unsigned int MARCH_BATCH       = 16;                             // consecutive chunks a block draws at a time (rows: one unit x one cluster)
+constexpr unsigned int MARCH_BATCH_SLOTS = 32;                             // published batch ids kept per block (a waiter reads its slot at once)
 
 enum RayKind : uint32_t { RAY_MISS = 0, RAY_INSIDE = 1, RAY_HIT = 2 };
 
@@ -3060,31 +3062,36 @@ BlendLists blend_lists_layout(void* base, int raysPerProbe, int raysPadded)
     L.irrIdx   = reinterpret_cast<uint16_t*>(p); p += align16((size_t)LBI_GROUPS * L.cap * sizeof(uint16_t));
     L.depthIdx = reinterpret_cast<uint16_t*>(p); p += align16((size_t)LBD_GROUPS * L.cap * sizeof(uint16_t));
     L.irrOff   = reinterpret_cast<uint32_t*>(p); p += align16((size_t)LBI_GROUPS * (L.irrPhases + 1) * sizeof(uint32_t));
-    L.depthOff = reinterpret_cast<uint32_t*>(p);
+    L.depthOff = reinterpret_cast<uint32_t*>(p); p += align16((size_t)LBD_GROUPS * (L.depthPhases + 1) * sizeof(uint32_t));
+    L.irrMean     = reinterpret_cast<float*>(p); p += align16(LBI_GROUPS * sizeof(float));
+    L.depthMean   = reinterpret_cast<float*>(p); p += align16(LBD_GROUPS * sizeof(float));
+    L.irrAssign   = reinterpret_cast<uint8_t*>(p); p += align16(LBI_GROUPS);
+    L.depthAssign = reinterpret_cast<uint8_t*>(p);
     return L;
 }
 size_t blend_lists_bytes(int raysPerProbe, int raysPadded)
 {
     const BlendLists L = blend_lists_layout(nullptr, raysPerProbe, raysPadded);
-    return (size_t)(reinterpret_cast<unsigned char*>(L.depthOff) - static_cast<unsigned char*>(nullptr)) + align16((size_t)LBD_GROUPS * (L.depthPhases + 1) * sizeof(uint32_t));
+    return (size_t)(reinterpret_cast<unsigned char*>(L.depthAssign) - static_cast<unsigned char*>(nullptr)) + align16(LBD_GROUPS);
 }
 int launch_blend_lists(const float* wIrr, const float* wDepth, int raysPerProbe, const BlendLists& lists, cudaStream_t s)
 {
     blend_lists_kernel<<<LBI_GROUPS + LBD_GROUPS, 32, 0, s>>>(wIrr, wDepth, raysPerProbe, lists);
-    return 1;
+    blend_assign_kernel<<<1, 64, 0, s>>>(lists);
+    return 2;
 }
 bool blend_lists_preferred(int probeCount) { return probeCount >= 148 * LB_PB; }
 void launch_blend_irradiance_lists(const BlendParams& p, const BlendLists& lists, cudaStream_t s)
 {
     const size_t smem = (size_t)LBI_KP * 3 * LB_PB * sizeof(float) + (size_t)LB_PB * LBI_RAW_LD * sizeof(uint2) +
-                        (LBI_THREADS / 32) * (2 * sizeof(LbStage) + 2 * sizeof(uint64_t) + 4 * sizeof(int));
+                        (LBI_THREADS / 32) * (2 * sizeof(LbStage) + 2 * sizeof(uint64_t) + 6 * sizeof(int));
     cudaFuncSetAttribute(blend_irradiance_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); // per launch: the attribute is per device
     blend_irradiance_lists_kernel<<<(p.probeCount + LB_PB - 1) / LB_PB, LBI_THREADS, smem, s>>>(p, lists);
 }
 void launch_blend_depth_lists(const BlendParams& p, const BlendLists& lists, cudaStream_t s)
 {
     const size_t smem = (size_t)LBD_KP * LB_PB * sizeof(float) + (size_t)LB_PB * LBD_RAW_LD * sizeof(uint32_t) +
-                        (LBD_THREADS / 32) * (2 * sizeof(LbStage) + 2 * sizeof(uint64_t) + 8 * sizeof(int));
+                        (LBD_THREADS / 32) * (2 * sizeof(LbStage) + 2 * sizeof(uint64_t) + 12 * sizeof(int));
     cudaFuncSetAttribute(blend_depth_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     blend_depth_lists_kernel<<<(p.probeCount + LB_PB - 1) / LB_PB, LBD_THREADS, smem, s>>>(p, lists);
 }

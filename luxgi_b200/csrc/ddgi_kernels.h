@@ -114,6 +114,10 @@ struct BlendLists
     float4*   depthW;   // [64][cap]
     uint16_t* depthIdx; // [64][cap]
     uint32_t* depthOff; // [64][depthPhases + 1]
+    float*    irrMean;     // [16]  mean id of the group's live rays
+    float*    depthMean;   // [64]
+    uint8_t*  irrAssign;   // [8 warps][2]   groups owned by each warp of a block this frame
+    uint8_t*  depthAssign; // [16 warps][4]
     int       cap, irrPhases, depthPhases;
 };
 size_t     blend_lists_bytes(int raysPerProbe, int raysPadded);
