@@ -1056,15 +1056,23 @@ __device__ __forceinline__ f3 probe_origin(const TraceParams& P, int probeId)
 // Occupancy: 8 warps x 4 blocks = 32 warps per SM at 64 registers.  ptxas keeps the four gathers of a step together from 56 registers up (at 48
 // it serialises the two taps to save registers, SASS inspected); measured on B200 (profiles/r2_march_occupancy.md): 48 / 56 / 64 registers =
 // 4.12 / 4.16 / 3.99 ms on C4 and 91.8 / 94.5 / 91.2 ms on C5.
-constexpr int MARCH_WARPS = 8;
+#ifndef MARCH_WARPS_N
+#define MARCH_WARPS_N 8
+#endif
+#ifndef MARCH_BLOCKS_PER_SM
 #define MARCH_BLOCKS_PER_SM 4
+#endif
+#ifndef MARCH_BATCH_N
+#define MARCH_BATCH_N 16
+#endif
+constexpr int MARCH_WARPS = MARCH_WARPS_N;
 #ifndef SHADE_BLOCKS_PER_SM
 #define SHADE_BLOCKS_PER_SM 5
 #endif
 constexpr int MARCH_CHUNK_RAYS  = 64;                                      // rays per pool fetch (2 probes x 32 directions): small, so
                                                                            // that shards with few rays per warp still balance
 constexpr int MARCH_REFILL_MIN  = 8;                                       // refill when this many lanes are idle
-constexpr unsigned int MARCH_BATCH       = 16;                             // consecutive chunks a block draws at a time (rows: one unit x one cluster)
+constexpr unsigned int MARCH_BATCH       = MARCH_BATCH_N;                             // consecutive chunks a block draws at a time (rows: one unit x one cluster)
 constexpr unsigned int MARCH_BATCH_SLOTS = 32;                             // published batch ids kept per block (a waiter reads its slot at once)
 
 enum RayKind : uint32_t { RAY_MISS = 0, RAY_INSIDE = 1, RAY_HIT = 2 };
