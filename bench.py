@@ -507,11 +507,11 @@ def run_lux(args):
             v = [traffic.get(n) for n in names]
             return None if any(x is None for x in v) else float(sum(v))
 
-        shade_names = ("shade_kernel",) if args.unsorted else ("classify_kernel", "scatter_kernel", "shade_sorted_kernel")
+        shade_names = ("shade_kernel",) if args.unsorted else ("classify", "scatter", "shade_sorted")
         traffic = dict(traffic)
         traffic["shade_stage"] = tsum(*shade_names)
         traffic["trace_stage"] = tsum("march_kernel", *shade_names)
-        traffic["blend_stage"] = tsum("blend_irradiance_kernel", "blend_depth_kernel")
+        traffic["blend_stage"] = tsum("blend_irradiance", "blend_depth")
         dominant = "march_kernel" if march_launch_ms >= shade_launch_ms else "shade_stage"
         if march_launch_ms == 0.0:  # --trace simple: one kernel
             dominant = "trace_stage"
@@ -519,8 +519,10 @@ def run_lux(args):
                  "shade_stage": roof("shade_stage", stages_b["shade"], shade_launch_ms),
                  "trace_stage": roof("trace_stage", stages_b["trace"], trace_launch_ms),
                  "blend": roof("blend_stage", stages_b["blend"], blend_launch_ms)}
-        roofs["shade_stage"]["kernels"] = "+".join(shade_names) + ("" if args.unsorted else " (+3 scan kernels)")
-        roofs["blend"]["kernels"] = "blend_irradiance_kernel+blend_depth_kernel"
+        roofs["shade_stage"]["kernels"] = "shade_kernel" if args.unsorted else "classify_rows_kernel+scatter_kernel+shade_sorted_kernel (+3 scan kernels)"
+        roofs["blend"]["kernels"] = ("blend_irradiance_tc_kernel+blend_depth_tc_kernel" if flags & abi.FLAG_BLEND_TC else
+                                    "blend_irradiance_lists_kernel+blend_depth_lists_kernel" if probes_rank >= 148 * 64 and not flags & abi.FLAG_BLEND_TILES
+                                    else "blend_irradiance_kernel+blend_depth_kernel")
         roofs["blend"]["fp32_tfma_per_s_dense_equivalent"] = probes_rank * R * 704 / (blend_launch_ms * 1e-3) / 1e12
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

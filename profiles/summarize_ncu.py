@@ -28,6 +28,9 @@ KEEP = [
     "smsp__average_warps_issue_stalled_tex_throttle_per_issue_active.ratio",
     "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "sm__inst_executed_pipe_tex.sum",
 ]
+# kernel name fragment -> role key of profiles/traffic.json (what bench.py sums per stage)
+ROLES = [("march_kernel", "march_kernel"), ("classify", "classify"), ("scatter_kernel", "scatter"), ("shade_sorted", "shade_sorted"), ("shade_kernel", "shade_kernel"),
+         ("blend_irradiance", "blend_irradiance"), ("blend_depth", "blend_depth")]
 UNIT_SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
 
 
@@ -50,7 +53,8 @@ def main():
             for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
                 b += float(r[col[k]].replace(",", "")) * UNIT_SCALE.get(units[col[k]], 1.0)
             name = r[col["Kernel Name"]].split("(")[0].replace("void ", "").split("<")[0].replace("lux::", "")
-            traffic[name] = traffic.get(name, 0.0) + b
+            role = next((r for key, r in ROLES if key in name), name)
+            traffic[role] = traffic.get(role, 0.0) + b
     json.dump(summary, open(out, "w"), indent=1)
     print("wrote", out, len(summary), "kernels")
     if traffic_key:
