@@ -256,6 +256,7 @@ enum {
     LUX_DDGI_FLAG_BLEND_LISTS   = 1u << 12,/* force the list form of the FP32 blend (per texel group, the frame's rays with a non-zero weight; bit-identical to
                                             * the tiled form).  Default: by probe count (>= 148 x 64 probes in the shard)                               */
     LUX_DDGI_FLAG_BLEND_TILES   = 1u << 13,/* force the tiled form (32-ray chunks, zero skipping per 8-texel group), for A/B                            */
+    LUX_DDGI_FLAG_BLEND_TC_MMA_SYNC = 1u << 14,/* with BLEND_TC: the mma.sync kernels instead of the tcgen05 / TMA ones, for A/B                   */
     LUX_DDGI_FLAG_MARCH_PROBE_MAJOR = 1u << 8 /* wavefront march in the round-1 work order (probe groups outermost, ray ids as they come) instead of direction
                                             * clusters outermost over spatially tiled probe groups; same results, for A/B of the DRAM traffic */
 };

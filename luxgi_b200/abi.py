@@ -201,6 +201,7 @@ FLAG_MARCH_BEAMS = 1 << 10  # force beam chunks
 FLAG_BLEND_TC = 1 << 11  # opt-in tensor-core blend (tolerance path)
 FLAG_BLEND_LISTS = 1 << 12  # force the list form of the FP32 blend (default from 148 x 64 probes per shard)
 FLAG_BLEND_TILES = 1 << 13  # force the tiled form
+FLAG_BLEND_TC_MMA_SYNC = 1 << 14  # with FLAG_BLEND_TC: mma.sync kernels instead of tcgen05 / TMA
 FLAG_MARCH_PROBE_MAJOR = 1 << 8  # A/B: the round-1 march work order
 BUF_RADIANCE, BUF_DIRECTION_DISTANCE, BUF_IRRADIANCE, BUF_DEPTH, BUF_IRRADIANCE_PREV, BUF_DEPTH_PREV, BUF_GLOBAL_SDF, BUF_GLOBAL_SDF_MIP = range(8)
 

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libluxddgi.so")
 SOURCES = ["ddgi_kernels.cu", "ddgi_engine.cpp"]
-HEADERS = ["ddgi_kernels.h", "ddgi_math.cuh", "march_kernel.inc", "blend_tc.inc", "blend_lists.inc", os.path.join("..", "..", "include", "luxddgi.h")]
+HEADERS = ["ddgi_kernels.h", "ddgi_math.cuh", "march_kernel.inc", "blend_tc.inc", "blend_lists.inc", "blend_umma.inc", os.path.join("..", "..", "include", "luxddgi.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

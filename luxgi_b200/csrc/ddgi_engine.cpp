@@ -94,6 +94,7 @@ struct LuxDDGIContext
     DeviceBuffer dirsHalf;                                       // [R] fp16 directions for the blend weights (pipelined update)
     DeviceBuffer blendLists;                                     // live-ray lists of the list blend (lux::BlendLists layout)
     bool         useBlendLists = false;
+    DeviceBuffer ummaW[2];                                       // tcgen05 irradiance GEMM: B' hi / lo [192][kPad] fp16
     DeviceBuffer tcW[4];                                         // LUX_DDGI_FLAG_BLEND_TC: irradiance hi / lo [64][kPad], depth hi / lo [256][kPad] fp16
     DeviceBuffer unitOrder, unitIndex, rayOrder, raySlot;        // march order tables (init::marchOrder)
     int          probeUnits = 0, rayClusters = 0;
@@ -423,6 +424,9 @@ static int initializeProbeGrid(LuxDDGIContext& c)
         const size_t kPad = (size_t)lux::blend_tc_kpad(u.raysPerProbe);
         for (int i = 0; i < 4; i++)
             if ((rc = allocZero(c, c.tcW[i], (i < 2 ? 64 : 256) * kPad * sizeof(uint16_t))) != LUX_OK) return rc;
+        if (!(c.flags & LUX_DDGI_FLAG_BLEND_TC_MMA_SYNC))
+            for (int i = 0; i < 2; i++)
+                if ((rc = allocZero(c, c.ummaW[i], (size_t)192 * lux::blend_umma_irr_kpad(u.raysPerProbe) * sizeof(uint16_t))) != LUX_OK) return rc;
     }
     c.frames      = 0;
     c.pingPong    = 0;
@@ -630,6 +634,11 @@ static void weights(LuxDDGIContext& c, const uint2* dirsHalf, cudaStream_t s)
         lux::launch_blend_tc_weights((const float*)c.wIrr.ptr, (const float*)c.wDepth.ptr, c.raysPadded, lux::blend_tc_kpad(u.raysPerProbe), (uint16_t*)c.tcW[0].ptr,
                                      (uint16_t*)c.tcW[1].ptr, (uint16_t*)c.tcW[2].ptr, (uint16_t*)c.tcW[3].ptr, s);
         c.launches += 2;
+        if (c.ummaW[0].ptr)
+        {
+            lux::launch_blend_umma_irr_weights((const float*)c.wIrr.ptr, u.raysPerProbe, (uint16_t*)c.ummaW[0].ptr, (uint16_t*)c.ummaW[1].ptr, s);
+            c.launches += 1;
+        }
     }
 }
 
@@ -668,7 +677,10 @@ static void launch(LuxDDGIContext& c, cudaStream_t s, cudaEvent_t evIrr, cudaEve
     const int  kPad = lux::blend_tc_kpad(u.raysPerProbe);
     const lux::BlendLists lists = c.useBlendLists ? lux::blend_lists_layout(c.blendLists.ptr, u.raysPerProbe, c.raysPadded) : lux::BlendLists{};
     if (tc)
-        lux::launch_blend_irradiance_tc(p, (const uint16_t*)c.tcW[0].ptr, (const uint16_t*)c.tcW[1].ptr, kPad, s);
+    {
+        if (!c.ummaW[0].ptr || !lux::launch_blend_irradiance_umma(p, (const uint16_t*)c.ummaW[0].ptr, (const uint16_t*)c.ummaW[1].ptr, s))
+            lux::launch_blend_irradiance_tc(p, (const uint16_t*)c.tcW[0].ptr, (const uint16_t*)c.tcW[1].ptr, kPad, s);
+    }
     else if (c.useBlendLists)
         lux::launch_blend_irradiance_lists(p, lists, s);
     else
@@ -904,7 +916,7 @@ int lux_ddgi_destroy(LuxDDGIContext* c)
     if (c->auxStream)
         cudaStreamSynchronize(c->auxStream);
     DeviceBuffer* all[] = {&c->radiance, &c->directionDepth, &c->irradiance[0], &c->irradiance[1], &c->depth[0], &c->depth[1],
-                           &c->dirs, &c->blendLists, &c->wIrr, &c->wDepth, &c->scaleIrr, &c->scaleDepth, &c->nzIrr, &c->nzDepth, &c->origins, &c->records, &c->meta, &c->chunkCounter, &c->sortTicket, &c->binCounts, &c->binBlockSums, &c->sortedIdx, &c->dirsHalf, &c->sdf, &c->mip, &c->chunks, &c->cull,
+                           &c->dirs, &c->blendLists, &c->ummaW[0], &c->ummaW[1], &c->wIrr, &c->wDepth, &c->scaleIrr, &c->scaleDepth, &c->nzIrr, &c->nzDepth, &c->origins, &c->records, &c->meta, &c->chunkCounter, &c->sortTicket, &c->binCounts, &c->binBlockSums, &c->sortedIdx, &c->dirsHalf, &c->sdf, &c->mip, &c->chunks, &c->cull,
                            &c->objects, &c->objectInverse, &c->chunkMasks, &c->tiles, &c->tileZRow, &c->light, &c->atlasDepth, &c->sky,
                            &c->unitOrder, &c->unitIndex, &c->rayOrder, &c->raySlot, &c->mipScratch, &c->probeTaps, &c->tcW[0], &c->tcW[1], &c->tcW[2], &c->tcW[3]};
     for (DeviceBuffer* b : all)

@@ -13,6 +13,8 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <cuda.h> // CUtensorMap (the encoder is fetched through cudaGetDriverEntryPoint: libcuda is not linked)
+
 #include "ddgi_kernels.h"
 #include "ddgi_math.cuh"
 
@@ -1852,6 +1854,7 @@ __global__ void __launch_bounds__(512) blend_depth_kernel(const __grid_constant_
 
 #include "blend_lists.inc"
 #include "blend_tc.inc"
+#include "blend_umma.inc"
 
 // Standalone border pass (BorderUpdate.glsl:136-156): one warp-sized group of threads per probe and atlas.
 template <typename T, int SIDE>
@@ -3128,6 +3131,51 @@ bool launch_blend_depth_tc(const BlendParams& p, const uint16_t* hi, const uint1
     const size_t smem = (size_t)(2 * 64 + 2 * 256) * TC_LD * sizeof(uint16_t);
     cudaFuncSetAttribute(blend_depth_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     blend_depth_tc_kernel<<<(p.probeCount + 31) / 32, 256, smem, s>>>(p, hi, lo, kPad);
+    return true;
+}
+
+// ---- tcgen05 / TMA form of the tensor-core blend (blend_umma.inc) ----
+typedef CUresult (*TensorMapEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                           const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TensorMapEncodeTiledFn tensor_map_encoder()
+{
+    static TensorMapEncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<TensorMapEncodeTiledFn>(p);
+    }();
+    return fn;
+}
+// fp16 matrix [outer][inner] with a row pitch in bytes, boxes of boxOuter x boxInner elements, 128-byte swizzle, zero fill outside
+static bool make_tensor_map_f16(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, uint64_t pitchBytes, uint32_t boxInner, uint32_t boxOuter)
+{
+    TensorMapEncodeTiledFn enc = tensor_map_encoder();
+    if (!enc || (reinterpret_cast<uintptr_t>(base) & 15) || (pitchBytes & 15))
+        return false;
+    const cuuint64_t dims[2] = {inner, outer}, strides[1] = {pitchBytes};
+    const cuuint32_t box[2] = {boxInner, boxOuter}, estr[2] = {1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+int blend_umma_irr_kpad(int raysPerProbe) { return (raysPerProbe * 4 + umma::BK - 1) / umma::BK * umma::BK; }
+void launch_blend_umma_irr_weights(const float* wIrr, int raysPerProbe, uint16_t* hi, uint16_t* lo, cudaStream_t s)
+{
+    const int kPad = blend_umma_irr_kpad(raysPerProbe);
+    umma::blend_umma_irr_weights_kernel<<<(umma::IRR_BN * kPad + 255) / 256, 256, 0, s>>>(wIrr, raysPerProbe, kPad, hi, lo);
+}
+bool launch_blend_irradiance_umma(const BlendParams& p, const uint16_t* hi, const uint16_t* lo, cudaStream_t s)
+{
+    const int kPad = blend_umma_irr_kpad(p.raysPerProbe);
+    CUtensorMap mapA, mapBhi, mapBlo;
+    if (!make_tensor_map_f16(&mapA, p.radiance, (uint64_t)p.raysPerProbe * 4, (uint64_t)p.probeCount, (uint64_t)p.raysPerProbe * 8, umma::BK, umma::BM) ||
+        !make_tensor_map_f16(&mapBhi, hi, (uint64_t)kPad, umma::IRR_BN, (uint64_t)kPad * 2, umma::BK, umma::IRR_BN) ||
+        !make_tensor_map_f16(&mapBlo, lo, (uint64_t)kPad, umma::IRR_BN, (uint64_t)kPad * 2, umma::BK, umma::IRR_BN))
+        return false; // odd ray count (row pitch not a multiple of 16 bytes) or no encoder: the mma.sync kernel takes over
+    const size_t smem = (size_t)umma::STAGES * umma::IRR_STAGE_BYTES + 1024 + 256;
+    cudaFuncSetAttribute(umma::blend_irradiance_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    umma::blend_irradiance_umma_kernel<<<(p.probeCount + umma::BM - 1) / umma::BM, 256, smem, s>>>(mapA, mapBhi, mapBlo, p, kPad / umma::BK);
     return true;
 }
 
