@@ -689,6 +689,8 @@ static void launch(LuxDDGIContext& c, cudaStream_t s, cudaEvent_t evIrr, cudaEve
         cudaEventRecord(evIrr, s);
     if (c.useBlendLists)
         lux::launch_blend_depth_lists(p, lists, s);
+    else if (tc && c.ummaW[0].ptr && lux::launch_blend_depth_umma(p, (const uint16_t*)c.tcW[2].ptr, (const uint16_t*)c.tcW[3].ptr, kPad, s))
+        ;
     else if (!tc || !lux::launch_blend_depth_tc(p, (const uint16_t*)c.tcW[2].ptr, (const uint16_t*)c.tcW[3].ptr, kPad, s))
         launch_blend_depth(p, s);
     if (evDepth)

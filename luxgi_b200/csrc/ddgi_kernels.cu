@@ -3179,6 +3179,20 @@ bool launch_blend_irradiance_umma(const BlendParams& p, const uint16_t* hi, cons
     return true;
 }
 
+bool launch_blend_depth_umma(const BlendParams& p, const uint16_t* hi, const uint16_t* lo, int kPad, cudaStream_t s)
+{
+    if (!(p.maxDistance * p.maxDistance < 60000.0f) || (p.raysPerProbe & 1)) // d * d must stay inside fp16; rays are loaded in pairs
+        return false;
+    CUtensorMap mapBhi, mapBlo;
+    if (!make_tensor_map_f16(&mapBhi, hi, (uint64_t)kPad, umma::DEP_BN, (uint64_t)kPad * 2, umma::BK, umma::DEP_BN) ||
+        !make_tensor_map_f16(&mapBlo, lo, (uint64_t)kPad, umma::DEP_BN, (uint64_t)kPad * 2, umma::BK, umma::DEP_BN))
+        return false;
+    const size_t smem = (size_t)umma::DEP_STAGES * umma::DEP_STAGE_BYTES + 1024 + 256;
+    cudaFuncSetAttribute(umma::blend_depth_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    umma::blend_depth_umma_kernel<<<(p.probeCount + umma::DEP_PROBES - 1) / umma::DEP_PROBES, 320, smem, s>>>(mapBhi, mapBlo, p, kPad / umma::BK);
+    return true;
+}
+
 void launch_border(uint2* irr, int irrWidth, uint32_t* depth, int depthWidth, int probesPerRow, int probeBegin, int probeCount,
                    cudaStream_t s)
 {

@@ -161,6 +161,7 @@ bool launch_blend_depth_tc(const BlendParams& p, const uint16_t* hi, const uint1
 int  blend_umma_irr_kpad(int raysPerProbe);
 void launch_blend_umma_irr_weights(const float* wIrr, int raysPerProbe, uint16_t* hi, uint16_t* lo, cudaStream_t s); // [192][kPad] each
 bool launch_blend_irradiance_umma(const BlendParams& p, const uint16_t* hi, const uint16_t* lo, cudaStream_t s);
+bool launch_blend_depth_umma(const BlendParams& p, const uint16_t* hi, const uint16_t* lo, int kPad, cudaStream_t s); // hi / lo: the [256][kPad] matrices of blend_tc.inc
 void launch_blend_depth(const BlendParams& p, cudaStream_t s);
 void launch_border(uint2* irr, int irrWidth, uint32_t* depth, int depthWidth, int probesPerRow, int probeBegin, int probeCount,
                    cudaStream_t s);
