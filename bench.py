@@ -480,6 +480,23 @@ def run_lux(args):
         per_rank = [[round(float(x) / args.steps, 4) for x in t.tolist()[1:3]] for t in allr]
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
     ms_total, trace_ms, blend_ms, setup_ms, march_ms, shade_ms = [float(x) for x in tm.tolist()]
+    # ---- opt-in tensor-core blend (LUX_DDGI_FLAG_BLEND_TC, tolerance path): its stage time on the same workload, reported beside the line ------
+    blend_tc = None
+    if world == 1 and not args.no_tc_ab and not (flags & abi.FLAG_BLEND_TC):
+        pipe.close()
+        pipe = ddgi.DDGIPipeline(u, device=local, rank=shard_rank, world=shard_world, flags=flags | abi.FLAG_BLEND_TC | abi.FLAG_STAGE_TIMERS,
+                                 stream=stream.cuda_stream)
+        pipe.set_scene(sc)
+        n_tc, tc_blend, tc_total = min(args.steps, 4), 0.0, 0.0
+        for i in range(2 + n_tc):
+            pipe.update(rot_of(f)); f += 1
+            if i >= 2:
+                pipe.synchronize()
+                t = pipe.stage_ms()
+                tc_blend += t.blend_ms; tc_total += t.setup_ms + t.trace_ms + t.blend_ms
+        blend_tc = {"blend_ms": tc_blend / n_tc, "update_ms_stage_sum": tc_total / n_tc, "steps": n_tc,
+                    "kernels": "umma::blend_irradiance_umma_kernel+umma::blend_depth_umma_kernel (tcgen05.mma, TMEM accumulators, TMA operands)",
+                    "note": "NOT part of value / e2e: opt-in path held to the north-star tolerance (1e-3 rel / 1e-4 abs), the default blend is the bit-exact FP32 one"}
     parity = None
     if world > 1 and args.emulate_shard is None and not args.no_parity:
         pipe.close()
@@ -548,6 +565,7 @@ def run_lux(args):
                     "sdf_region_update_ms": region_ms,
                     "sdf_region_update_note": "not part of the timed steps: one dirty 32^3 chunk (64 KiB from host memory) patched into the bound global SDF + that cascade's mip rebuilt on device (lux_ddgi_update_global_sdf_region), the per-frame call of a renderer whose scene changed; a full lux_ddgi_set_global_sdf re-upload is the alternative it replaces",
                     "note": "per rank and per step: light cache H2D from pinned memory (N > 1: own 1/N of its rows, all-gathered over NVLink by the library), own atlas rows D2H into pinned memory; the host waits for frame f-1's rows while frame f computes (every frame delivered, one frame late), all copies complete inside the timed region"},
+            "blend_tc": blend_tc,
             "gpu_launches": int(launches),
             "multi_gpu_parity": parity,
             "wall_s_timed_region": t_wall,
@@ -594,6 +612,7 @@ def main():
     ap.add_argument("--trace", default="texture", choices=["texture", "loads", "simple"],
                     help="SDF read path / trace kernel variant: wavefront + tld4 gathers (default), wavefront + fp16 loads, thread-per-ray")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-tc-ab", action="store_true", help="skip the short extra pass that times the opt-in tensor-core blend (N = 1 only)")
     ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the post-run parity pass (atlas checksums across ranks + oracle subsample on rank 0)")
     ap.add_argument("--e2e-skip-h2d", action="store_true", help="diagnosis only: e2e leg without the light-cache upload (the printed e2e is then NOT an end-to-end number)")
     ap.add_argument("--e2e-skip-d2h", action="store_true", help="diagnosis only: e2e leg without the atlas downloads")

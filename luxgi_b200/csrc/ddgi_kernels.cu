@@ -1269,8 +1269,10 @@ __global__ void __launch_bounds__(256) classify_kernel(const __grid_constant__ T
 
 // The same pass for ROW chunks (TraceParams::beam == 0): there the 32 lanes of a record row are 32 x-adjacent probes of one ray, so a block takes
 // 32 probes x 16 consecutive ray ids, reads whole 512-byte record rows and transposes through shared memory to write 128-byte row segments.
-constexpr int CLASSIFY_ROW_RAYS = 16;
-__global__ void __launch_bounds__(128, 12) classify_rows_kernel(const __grid_constant__ TraceParams P, int rayGroups)
+constexpr int CLASSIFY_ROW_RAYS    = 64;  // ray ids per block: a probe's output is one 512-byte segment per buffer (16 rays = 128-byte bursts ran at 62 % of the copy bandwidth)
+constexpr int CLASSIFY_ROW_WARPS   = 8;
+constexpr int CLASSIFY_ROW_RPT     = CLASSIFY_ROW_RAYS / CLASSIFY_ROW_WARPS; // record rows per warp
+__global__ void __launch_bounds__(32 * CLASSIFY_ROW_WARPS, 4) classify_rows_kernel(const __grid_constant__ TraceParams P, int rayGroups)
 {
     __shared__ uint2 sRad[32][CLASSIFY_ROW_RAYS + 1];
     __shared__ uint2 sDir[32][CLASSIFY_ROW_RAYS + 1];
@@ -1283,28 +1285,27 @@ __global__ void __launch_bounds__(128, 12) classify_rows_kernel(const __grid_con
     const LuxGlobalSDFData& data = P.sdf;
     const bool probeValid = probeLocal < P.probeCount;
 
-    float4   rec[CLASSIFY_RPT];
-    uint32_t meta[CLASSIFY_RPT];
-    float4   d4[CLASSIFY_RPT];
-    bool     valid[CLASSIFY_RPT];
+    float4   rec[CLASSIFY_ROW_RPT];
+    uint32_t meta[CLASSIFY_ROW_RPT];
+    bool     valid[CLASSIFY_ROW_RPT];
 #pragma unroll
-    for (int k = 0; k < CLASSIFY_RPT; k++)
+    for (int k = 0; k < CLASSIFY_ROW_RPT; k++)
     {
-        const int rayId = rayBase + warp + k * 4;
+        const int rayId = rayBase + warp + k * CLASSIFY_ROW_WARPS;
         valid[k] = probeValid && rayId < P.raysPerProbe;
         const uint32_t g = valid[k] ? march_record(P, (uint32_t)probeLocal, (uint32_t)rayId) : 0u;
         rec[k]   = valid[k] ? __ldcs(P.records + g) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         meta[k]  = valid[k] ? __ldcs(P.meta + g) : 0u;
-        d4[k]    = valid[k] ? __ldg(P.dirs + rayId) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
 #pragma unroll
-    for (int k = 0; k < CLASSIFY_RPT; k++)
+    for (int k = 0; k < CLASSIFY_ROW_RPT; k++)
     {
-        const int rayInUnit = warp + k * 4;
+        const int rayInUnit = warp + k * CLASSIFY_ROW_WARPS;
         if (valid[k])
         {
             const uint32_t hc = meta[k] & 3u, kind = (meta[k] >> 2) & 3u;
-            f3 d = {d4[k].x, d4[k].y, d4[k].z};
+            const float4 d4 = __ldg(P.dirs + rayBase + rayInUnit); // the frame's directions: 16 KB, cache resident
+            f3 d = {d4.x, d4.y, d4.z};
             f4 radiance;
             if (kind == RAY_HIT) // rgb comes from the shade kernel (zero without a surface cache)
                 radiance = {0.0f, 0.0f, 0.0f, gmax(rec[k].x + data.cascadeVoxelSize[hc] * 0.5f, 0.0f)};
@@ -1325,19 +1326,19 @@ __global__ void __launch_bounds__(128, 12) classify_rows_kernel(const __grid_con
         }
     }
     __syncthreads();
-    // transposed write-out: 16 consecutive rays (128 bytes) per probe
+    // transposed write-out: 64 consecutive rays (512 bytes) per probe and buffer
 #pragma unroll
-    for (int k = 0; k < CLASSIFY_RPT; k++)
+    for (int k = 0; k < CLASSIFY_ROW_RPT; k++)
     {
-        const int idx = threadIdx.x + k * 128;
+        const int idx = threadIdx.x + k * (32 * CLASSIFY_ROW_WARPS);
         const int pl = idx / CLASSIFY_ROW_RAYS, rl = idx % CLASSIFY_ROW_RAYS;
         const int oProbe = (int)probeGroup * 32 + pl;
         const int oRay   = rayBase + rl;
         if (oProbe < P.probeCount && oRay < P.raysPerProbe)
         {
             size_t o = (size_t)oProbe * P.raysPerProbe + oRay;
-            P.radiance[o] = sRad[pl][rl];
-            P.dirDist[o]  = sDir[pl][rl];
+            __stcs(P.radiance + o, sRad[pl][rl]);
+            __stcs(P.dirDist + o, sDir[pl][rl]);
         }
     }
 }
@@ -1415,26 +1416,35 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(uint4* __restr
     counts[i]  = make_uint4(b, b + v.x, b + v.x + v.y, b + v.x + v.y + v.z);
 }
 
-constexpr int SCATTER_RPT = 4; // records per thread: the pass is a chain ticket -> prefix -> store per record, so loads are batched
+constexpr int SCATTER_RPT = 8; // records per thread (four 16-byte loads of two tickets each): the pass is a chain ticket -> prefix -> store per record, so loads are batched
 __global__ void __launch_bounds__(256) scatter_kernel(const uint2* __restrict__ ticket, const uint32_t* __restrict__ prefix,
                                                       uint32_t* __restrict__ sortedIdx, size_t records)
 {
-    const size_t g0 = (size_t)blockIdx.x * (256 * SCATTER_RPT) + threadIdx.x;
-    uint2    t[SCATTER_RPT];
+    // thread -> records g0 + k * 512, g0 + k * 512 + 1 (k = 0..3); the record capacity is a multiple of 64, so a pair never straddles the end
+    const size_t g0 = (size_t)blockIdx.x * (256 * SCATTER_RPT) + (size_t)threadIdx.x * 2;
+    uint4    t[SCATTER_RPT / 2];
     uint32_t base[SCATTER_RPT];
 #pragma unroll
-    for (int k = 0; k < SCATTER_RPT; k++)
+    for (int k = 0; k < SCATTER_RPT / 2; k++)
     {
-        const size_t g = g0 + (size_t)k * 256;
-        t[k] = g < records ? __ldcs(ticket + g) : make_uint2(0xffffffffu, 0u);
+        const size_t g = g0 + (size_t)k * 512;
+        t[k] = g + 1 < records ? __ldcs(reinterpret_cast<const uint4*>(ticket + g)) : make_uint4(0xffffffffu, 0u, 0xffffffffu, 0u);
     }
 #pragma unroll
-    for (int k = 0; k < SCATTER_RPT; k++)
-        base[k] = t[k].x != 0xffffffffu ? __ldg(prefix + t[k].x) : 0u;
+    for (int k = 0; k < SCATTER_RPT / 2; k++)
+    {
+        base[2 * k]     = t[k].x != 0xffffffffu ? __ldg(prefix + t[k].x) : 0u;
+        base[2 * k + 1] = t[k].z != 0xffffffffu ? __ldg(prefix + t[k].z) : 0u;
+    }
 #pragma unroll
-    for (int k = 0; k < SCATTER_RPT; k++)
+    for (int k = 0; k < SCATTER_RPT / 2; k++)
+    {
+        const uint32_t g = (uint32_t)(g0 + (size_t)k * 512);
         if (t[k].x != 0xffffffffu)
-            sortedIdx[base[k] + (t[k].y & 0x3fffffffu)] = (uint32_t)(g0 + (size_t)k * 256) | (t[k].y & 0xc0000000u);
+            sortedIdx[base[2 * k] + (t[k].y & 0x3fffffffu)] = g | (t[k].y & 0xc0000000u);
+        if (t[k].z != 0xffffffffu)
+            sortedIdx[base[2 * k + 1] + (t[k].w & 0x3fffffffu)] = (g + 1u) | (t[k].w & 0xc0000000u);
+    }
 }
 
 template <bool TEX>
@@ -2914,7 +2924,7 @@ static int launch_shade_sorted(const TraceParams& p, cudaStream_t s)
     else
     {
         const int rayGroups = (p.raysPerProbe + CLASSIFY_ROW_RAYS - 1) / CLASSIFY_ROW_RAYS;
-        classify_rows_kernel<<<(unsigned)((size_t)rayGroups * ((p.probeCount + 31) / 32)), 128, 0, s>>>(p, rayGroups);
+        classify_rows_kernel<<<(unsigned)((size_t)rayGroups * ((p.probeCount + 31) / 32)), 32 * CLASSIFY_ROW_WARPS, 0, s>>>(p, rayGroups);
     }
     if (!p.hasAtlas)
         return 1; // hits carry no radiance without a surface cache: classify wrote the final values
