@@ -271,6 +271,37 @@ def test_tensor_core_blend_stays_inside_the_north_star_tolerance(oracle, cfg, fr
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("counts,rays", [((3, 5, 2), 50), ((5, 4, 7), 300), ((4, 4, 4), 96)])
+def test_tensor_core_blend_ragged_shapes(oracle, counts, rays):
+    """The tcgen05 / TMA blend on shapes that do not fill its tiles: probe counts below and between multiples of the 64- / 128-probe CTAs (the TMA box
+    reaches past the end of the ray buffer: zero fill), ray counts that are no multiple of the 16-ray (irradiance) / 64-ray (depth) stages (the operand
+    rows end inside a box; the weights beyond the last ray are zero).  Same tolerance as above, three frames."""
+    from luxgi_b200 import abi, ddgi
+
+    sc = scenes.cornell_scene(res=32, counts=counts, rays=rays, atlas_res=256)
+    orc = oracle.OraclePipeline(sc)
+    pipe = ddgi.DDGIPipeline(sc.uniform, flags=abi.FLAG_BLEND_TC)
+    pipe.set_scene(sc)
+    for f in range(3):
+        rot = scenes.frame_rotation(f)
+        orc.update(rot)
+        pipe.update(rot)
+    assert np.array_equal(pipe.radiance, orc.rad) and np.array_equal(pipe.direction_distance, orc.dd)
+    for name, got, want in (("irradiance", pipe.irradiance, orc.irradiance), ("depth", pipe.depth, orc.depth)):
+        g, w = f16(got), f16(want)
+        assert np.isfinite(g).all()
+        err = np.abs(g - w)
+        assert np.all(err <= 1e-4 + 1e-3 * np.abs(w)), (name, float(err.max()), int((err > 1e-4 + 1e-3 * np.abs(w)).sum()))
+        ulp = np.abs(got.astype(np.int32) - want.astype(np.int32))
+        print(counts, rays, name, "differing fp16 values", int((ulp > 0).sum()), "of", ulp.size, "max ulp", int(ulp.max()))
+        assert int(ulp.max()) <= 2
+    # outer pad rows / columns of the atlases stay untouched
+    irr = pipe.irradiance
+    assert not irr[0].any() and not irr[-1].any() and not irr[:, 0].any() and not irr[:, -1].any()
+    pipe.close()
+
+
+@pytest.mark.gpu
 def test_c3_infinite_bounce_on_the_dark_room(oracle):
     """BASELINE configs[2] at its specified length: 32x16x32 probes, 256 rays, 64 frames, the previous frame's irradiance fed into
     the surface-cache lighting every 16 frames (GI_FRAMES cadence; refreshes at frames 16, 32, 48 and 64, the last one traced by a 65th frame).
