@@ -300,6 +300,8 @@ def run_lux(args):
     if args.unsorted:
         flags |= abi.FLAG_SHADE_UNSORTED
     flags |= args.extra_flags
+    if args.shards == "interleaved" and args.allgather == "lib":
+        flags |= abi.FLAG_SHARD_INTERLEAVED  # rank g owns z-layers g, g + N, ...: evenly loaded shards (no effect at N = 1)
     shard_rank, shard_world = (rank, world) if args.emulate_shard is None else tuple(int(x) for x in args.emulate_shard.split('/'))
     # The measured pipe runs lux_ddgi_update as shipped (blend weights on a second stream during the march, no stage events); the per-stage
     # times and the kernel roofline come from a second, serialized pass below (LUX_DDGI_FLAG_STAGE_TIMERS = one batch, one stream).
@@ -414,8 +416,8 @@ def run_lux(args):
             step(f)
             k = f & 1
             if not args.e2e_skip_d2h:
-                pipe.download_rows_async_ptr(abi.BUF_IRRADIANCE, st.irradianceRowBegin, st.irradianceRowCount, pin_irr[k].data_ptr())
-                pipe.download_rows_async_ptr(abi.BUF_DEPTH, st.depthRowBegin, st.depthRowCount, pin_dep[k].data_ptr())
+                pipe.download_shard_async_ptr(abi.BUF_IRRADIANCE, pin_irr[k].data_ptr())  # the shard's own rows, packed (one strided copy)
+                pipe.download_shard_async_ptr(abi.BUF_DEPTH, pin_dep[k].data_ptr())
             fences.append(pipe.download_fence())
             if len(fences) > 1:
                 pipe.wait_fence(fences.pop(0))  # frame f-1 is on the host now
@@ -546,8 +548,8 @@ def run_lux(args):
             "ms_per_step": ms_per_step, "ms_per_update": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": workload_desc(args.workload, sc),
-            "parallelism": {"layout": f"zslab{world}",
-                            "sharding": "probe z-slabs, SDF + surface cache replicated, in-place NCCL all-gather of atlas rows per step"
+            "parallelism": {"layout": (f"zlayers-interleaved{world}" if flags & abi.FLAG_SHARD_INTERLEAVED and world > 1 else f"zslab{world}"),
+                            "sharding": ("probe z-layers dealt out round-robin (rank g owns layers g, g + N, ...: evenly loaded), " if flags & abi.FLAG_SHARD_INTERLEAVED and world > 1 else "probe z-slabs, ") + "SDF + surface cache replicated, in-place NCCL all-gather of atlas rows per step"
                             + ("" if world == 1 else ((" issued by lux_ddgi_update on the library's gather stream" if args.allgather == "lib" else " issued by the host (torch.distributed)")
                                                       + (" on the compute stream" if args.sync_allgather else ", overlapped with the next step's trace")))},
             "stage_ms": {"setup": setup_ms / args.steps, "trace": trace_launch_ms, "march": march_launch_ms, "shade": shade_launch_ms,
@@ -619,6 +621,9 @@ def main():
     ap.add_argument("--emulate-shard", default=None, help="r/w: run shard r of w on one GPU without any collective (profiling aid)")
     ap.add_argument("--allgather", default="lib", choices=["lib", "torch"],
                     help="N > 1: exchange inside lux_ddgi_update (ncclComm bound through the C ABI, default) or issued by this script through torch.distributed")
+    ap.add_argument("--shards", default="slabs", choices=["interleaved", "slabs"],
+                    help="N > 1: which probe z-layers a rank owns - one contiguous z-slab (default) or every N-th layer (LUX_DDGI_FLAG_SHARD_INTERLEAVED: "
+                         "evenly loaded ranks, but measured slower on C5: 18.5 ms against 17.7 ms at N = 8, the sparser shards reuse less of the SDF)")
     ap.add_argument("--sync-allgather", action="store_true", help="all-gather on the compute stream (no overlap with the next trace)")
     ap.add_argument("--no-pipeline", action="store_true", help="A/B: one batch on one stream instead of two-stream probe batches")
     ap.add_argument("--extra-flags", type=lambda v: int(v, 0), default=0, help="A/B: LUX_DDGI_FLAG_* bits OR-ed into the context flags")

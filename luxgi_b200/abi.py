@@ -150,7 +150,20 @@ class State(C.Structure):
         ("depthRowBegin", C.c_int32),
         ("depthRowCount", C.c_int32),
         ("kernelLaunches", C.c_uint64),
+        ("layerProbes", C.c_int32),
+        ("layerStride", C.c_int32),
     ]
+
+    def own_rows(self, side):
+        """Atlas rows owned by the shard (side = 8 | 16), in shard-local layer order: what lux_ddgi_download_shard_async packs."""
+        S, begin = side + 2, (self.irradianceRowBegin if side == 8 else self.depthRowBegin)
+        layers = self.probeCount // self.layerProbes
+        return [begin + k * self.layerStride * S + r for k in range(layers) for r in range(S)]
+
+    def own_probes(self):
+        """Probe ids of the shard in shard-local order."""
+        L = self.layerProbes
+        return [self.probeBegin + (l // L) * self.layerStride * L + l % L for l in range(self.probeCount)]
 
 
 class StageTimes(C.Structure):
@@ -202,6 +215,7 @@ FLAG_BLEND_TC = 1 << 11  # opt-in tensor-core blend (tolerance path)
 FLAG_BLEND_LISTS = 1 << 12  # force the list form of the FP32 blend (default from 148 x 64 probes per shard)
 FLAG_BLEND_TILES = 1 << 13  # force the tiled form
 FLAG_BLEND_TC_MMA_SYNC = 1 << 14  # with FLAG_BLEND_TC: mma.sync kernels instead of tcgen05 / TMA
+FLAG_SHARD_INTERLEAVED = 1 << 15  # multi-GPU: rank g owns z-layers g, g + world, ... (balanced) instead of one z-slab
 FLAG_MARCH_PROBE_MAJOR = 1 << 8  # A/B: the round-1 march work order
 BUF_RADIANCE, BUF_DIRECTION_DISTANCE, BUF_IRRADIANCE, BUF_DEPTH, BUF_IRRADIANCE_PREV, BUF_DEPTH_PREV, BUF_GLOBAL_SDF, BUF_GLOBAL_SDF_MIP = range(8)
 

@@ -22,6 +22,14 @@ namespace lux {
 
 struct RotationArg { float m[16]; };
 
+// probe id of shard-local probe `local` (LuxDDGIState::layerStride): a z-slab, or every world-th z-layer
+__device__ __forceinline__ int shard_probe(int probeBegin, int layerProbes, int layerStride, int local)
+{
+    return layerStride == 1 ? probeBegin + local : probeBegin + (local / layerProbes) * layerStride * layerProbes + local % layerProbes;
+}
+template <class Params>
+__device__ __forceinline__ int shard_probe(const Params& P, int local) { return shard_probe(P.probeBegin, P.layerProbes, P.layerStride, local); }
+
 // =====================================================================================================================
 // Per-frame setup
 // =====================================================================================================================
@@ -634,7 +642,7 @@ __global__ void __launch_bounds__(32 * TRACE_RAYS_PER_BLOCK) trace_kernel(const 
 
     if (active)
     {
-        const int probeId = P.probeBegin + probeLocal;
+        const int probeId = shard_probe(P, probeLocal);
         // probeLocation, DDGICommon.glsl:101-114
         int cx = probeId % P.countX;
         int cy = (probeId % (P.countX * P.countY)) / P.countX;
@@ -1486,7 +1494,7 @@ __global__ void probe_origins_kernel(const TraceParams P, float4* __restrict__ o
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.probeCount)
         return;
-    f3 o = probe_origin(P, P.probeBegin + i);
+    f3 o = probe_origin(P, shard_probe(P, i));
     origins[i] = make_float4(o.x, o.y, o.z, 0.0f);
 }
 
@@ -1585,7 +1593,7 @@ __device__ __forceinline__ void irradiance_epilogue(const BlendParams& P, const 
         int probeLocal = probe0 + p;
         if (probeLocal >= P.probeCount)
             continue;
-        int   probe = P.probeBegin + probeLocal;
+        int   probe = shard_probe(P, probeLocal);
         float s = __ldg(P.scaleIrr + t);
         float r = Cs[(p * 3 + 0) * N + t] * s, g = Cs[(p * 3 + 1) * N + t] * s, b = Cs[(p * 3 + 2) * N + t] * s;
         r = pow_rn(r, P.invGamma);
@@ -1724,7 +1732,7 @@ __device__ __forceinline__ void depth_epilogue(const BlendParams& P, const float
         int probeLocal = probe0 + p;
         if (probeLocal >= P.probeCount)
             continue;
-        int   probe = P.probeBegin + probeLocal;
+        int   probe = shard_probe(P, probeLocal);
         int i, j; // column t of the weight matrix -> texel (i, j)
         depth_texel_of_column(t, i, j);
         float s = __ldg(P.scaleDepth + (j * 16 + i));
@@ -1868,14 +1876,14 @@ __global__ void __launch_bounds__(512) blend_depth_kernel(const __grid_constant_
 
 // Standalone border pass (BorderUpdate.glsl:136-156): one warp-sized group of threads per probe and atlas.
 template <typename T, int SIDE>
-__global__ void border_kernel(T* __restrict__ img, int W, int probesPerRow, int probeBegin, int probeCount)
+__global__ void border_kernel(T* __restrict__ img, int W, int probesPerRow, int probeBegin, int probeCount, int layerProbes, int layerStride)
 {
     constexpr int NB = 4 * SIDE + 4; // 36 / 68 copies
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     int p = idx / NB, e = idx % NB;
     if (p >= probeCount)
         return;
-    int probe = probeBegin + p;
+    int probe = shard_probe(probeBegin, layerProbes, layerStride, p);
     int bx = (probe % probesPerRow) * (SIDE + 2) + 1, by = (probe / probesPerRow) * (SIDE + 2) + 1;
     int sx, sy, dx, dy;
     if (e < SIDE)            { int x = e + 1;            sx = SIDE + 1 - x; sy = 1;    dx = x; dy = 0; }
@@ -3203,7 +3211,7 @@ bool launch_blend_depth_umma(const BlendParams& p, const uint16_t* hi, const uin
     return true;
 }
 
-void launch_border(uint2* irr, int irrWidth, uint32_t* depth, int depthWidth, int probesPerRow, int probeBegin, int probeCount,
+void launch_border(uint2* irr, int irrWidth, uint32_t* depth, int depthWidth, int probesPerRow, int probeBegin, int probeCount, int layerProbes, int layerStride,
                    cudaStream_t s)
 {
     if (probeCount <= 0)
@@ -3211,12 +3219,12 @@ void launch_border(uint2* irr, int irrWidth, uint32_t* depth, int depthWidth, in
     if (irr)
     {
         long long n = (long long)probeCount * 36;
-        border_kernel<uint2, 8><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(irr, irrWidth, probesPerRow, probeBegin, probeCount);
+        border_kernel<uint2, 8><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(irr, irrWidth, probesPerRow, probeBegin, probeCount, layerProbes, layerStride);
     }
     if (depth)
     {
         long long n = (long long)probeCount * 68;
-        border_kernel<uint32_t, 16><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(depth, depthWidth, probesPerRow, probeBegin, probeCount);
+        border_kernel<uint32_t, 16><<<(unsigned)((n + 255) / 256), 256, 0, s>>>(depth, depthWidth, probesPerRow, probeBegin, probeCount, layerProbes, layerStride);
     }
 }
 

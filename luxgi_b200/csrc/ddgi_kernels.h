@@ -15,7 +15,8 @@ struct TraceParams
     float step[3];
     int   countX, countY;
     int   raysPerProbe;
-    int   probeBegin, probeCount; // z-slab shard: probes [probeBegin, probeBegin + probeCount)
+    int   probeBegin, probeCount; // shard: probeCount probes from probeBegin on, see shard_probe()
+    int   layerProbes, layerStride; // probes per z-layer; 1 = one z-slab, world = interleaved layers (LuxDDGIState)
     // global SDF
     LuxGlobalSDFData sdf;
     const uint16_t*  tex; // R16F [res][res][res*cascades]
@@ -84,6 +85,7 @@ struct TraceParams
 struct BlendParams
 {
     int   probeBegin, probeCount;
+    int   layerProbes, layerStride; // see shard_probe()
     int   raysPerProbe, raysPadded; // raysPadded = round_up(R, 32): weight rows beyond R are zero
     int   probesPerRow;             // X*Y
     int   irrWidth, depthWidth;     // atlas widths in texels
@@ -163,7 +165,7 @@ void launch_blend_umma_irr_weights(const float* wIrr, int raysPerProbe, uint16_t
 bool launch_blend_irradiance_umma(const BlendParams& p, const uint16_t* hi, const uint16_t* lo, cudaStream_t s);
 bool launch_blend_depth_umma(const BlendParams& p, const uint16_t* hi, const uint16_t* lo, int kPad, cudaStream_t s); // hi / lo: the [256][kPad] matrices of blend_tc.inc
 void launch_blend_depth(const BlendParams& p, cudaStream_t s);
-void launch_border(uint2* irr, int irrWidth, uint32_t* depth, int depthWidth, int probesPerRow, int probeBegin, int probeCount,
+void launch_border(uint2* irr, int irrWidth, uint32_t* depth, int depthWidth, int probesPerRow, int probeBegin, int probeCount, int layerProbes, int layerStride,
                    cudaStream_t s);
 
 

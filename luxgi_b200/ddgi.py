@@ -23,7 +23,7 @@ EXPORTS = [
     "lux_ddgi_destroy", "lux_ddgi_set_uniform", "lux_ddgi_set_global_sdf", "lux_ddgi_set_surface_atlas",
     "lux_ddgi_update_surface_light_cache", "lux_ddgi_set_skybox", "lux_ddgi_trace_rays", "lux_ddgi_probe_update",
     "lux_ddgi_border_update", "lux_ddgi_end_frame", "lux_ddgi_update", "lux_ddgi_synchronize", "lux_ddgi_get_buffer",
-    "lux_ddgi_download", "lux_ddgi_download_async", "lux_ddgi_download_rows_async", "lux_ddgi_set_ray_buffers", "lux_ddgi_restore", "lux_ddgi_get_state", "lux_ddgi_shard_layout",
+    "lux_ddgi_download", "lux_ddgi_download_async", "lux_ddgi_download_rows_async", "lux_ddgi_set_ray_buffers", "lux_ddgi_restore", "lux_ddgi_get_state", "lux_ddgi_shard_layout", "lux_ddgi_shard_layout_ex", "lux_ddgi_download_shard_async",
     "lux_ddgi_get_stage_ms", "lux_ddgi_sample_irradiance", "lux_ddgi_sample_probe", "lux_ddgi_indirect_light",
     "lux_ddgi_get_surface_light_cache", "lux_ddgi_build_global_sdf", "lux_ddgi_build_sdf_mip", "lux_ddgi_sdf_file_read", "lux_ddgi_download_fence", "lux_ddgi_wait_fence", "lux_ddgi_set_nccl_comm", "lux_ddgi_update_surface_light_cache_rows", "lux_ddgi_cull_surface_objects",
     "lux_ddgi_get_surface_cull_lists", "lux_ddgi_trace_global_sdf", "lux_ddgi_surface_direct_light",
@@ -73,6 +73,8 @@ def load():
         "lux_ddgi_restore": [vp, vp, vp, i32, i32],
         "lux_ddgi_get_state": [vp, C.POINTER(abi.State)],
         "lux_ddgi_shard_layout": [C.POINTER(abi.DDGIUniform), i32, i32, C.POINTER(abi.State)],
+        "lux_ddgi_shard_layout_ex": [C.POINTER(abi.DDGIUniform), i32, i32, C.c_uint32, C.POINTER(abi.State)],
+        "lux_ddgi_download_shard_async": [vp, i32, vp],
         "lux_ddgi_get_stage_ms": [vp, C.POINTER(abi.StageTimes)],
         "lux_ddgi_sample_irradiance": [vp, i32, vp, vp, vp, vp, i32],
         "lux_ddgi_sample_probe": [vp, i32, i32, vp, vp, vp, vp, vp, i32],
@@ -143,10 +145,11 @@ def uniform_from_volume(volume: abi.IrradianceVolume, aabb_min, aabb_max) -> abi
     return u
 
 
-def shard_layout(uniform: abi.DDGIUniform, rank: int, world: int) -> abi.State:
-    """z-slab probe range and atlas row ranges of one shard (host arithmetic only; works without a GPU)."""
+def shard_layout(uniform: abi.DDGIUniform, rank: int, world: int, flags: int = 0) -> abi.State:
+    """Probe range and atlas row ranges of one shard - a z-slab, or interleaved z-layers with abi.FLAG_SHARD_INTERLEAVED (host arithmetic only;
+    works without a GPU)."""
     st = abi.State()
-    _check(load().lux_ddgi_shard_layout(C.byref(uniform), int(rank), int(world), C.byref(st)))
+    _check(load().lux_ddgi_shard_layout_ex(C.byref(uniform), int(rank), int(world), int(flags), C.byref(st)))
     return st
 
 
@@ -330,6 +333,10 @@ class DDGIPipeline:
 
     def download_rows_async_ptr(self, buf, row_begin, row_count, host_ptr):
         _check(self._lib.lux_ddgi_download_rows_async(self._h, buf, int(row_begin), int(row_count), C.c_void_p(host_ptr)))
+
+    def download_shard_async_ptr(self, buf, host_ptr):
+        """The shard's own rows of an atlas, packed in shard-local layer order, to pinned host memory (see State.own_rows)."""
+        _check(self._lib.lux_ddgi_download_shard_async(self._h, buf, C.c_void_p(host_ptr)))
 
     def trace_global_sdf(self, traces, start_bias=0.0) -> np.ndarray:
         """tracyGlobalSDF for arbitrary rays: traces = abi.SDF_TRACE_DTYPE records -> abi.SDF_HIT_DTYPE records."""

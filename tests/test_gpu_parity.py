@@ -223,6 +223,37 @@ def test_z_slab_shards_reassemble_the_full_volume(oracle):
         p.close()
 
 
+def test_interleaved_layer_shards_reassemble_the_full_volume(oracle):
+    """LUX_DDGI_FLAG_SHARD_INTERLEAVED: four shards on one GPU, rank g owning the z-layers g, g + 4, ... (the balanced multi-GPU layout), write
+    disjoint atlas rows whose union is the single-context result; the packed own-row download returns exactly those rows; both blend forms."""
+    sc = scenes.cornell_scene(res=32, counts=(5, 3, 8), rays=96, atlas_res=256)
+    rots = [scenes.frame_rotation(f) for f in range(2)]
+    full = run_engine(sc, rots)
+    for blend in (abi.FLAG_BLEND_LISTS, abi.FLAG_BLEND_TILES):
+        parts = [run_engine(sc, rots, flags=abi.FLAG_SHARD_INTERLEAVED | blend, rank=r, world=4) for r in range(4)]
+        irr, dep = np.zeros_like(full.irradiance), np.zeros_like(full.depth)
+        rad = np.zeros_like(full.radiance)
+        for p in parts:
+            st = p.state()
+            assert st.layerStride == 4 and st.probeCount == full.probe_count // 4
+            ri, rd = st.own_rows(8), st.own_rows(16)
+            irr[ri], dep[rd] = p.irradiance[ri], p.depth[rd]
+            other = np.ones(irr.shape[0], dtype=bool)
+            other[ri] = False
+            assert not p.irradiance[other].any()  # a shard never touches rows it does not own
+            rad[st.own_probes()] = p.radiance
+            import torch
+            pin = torch.empty(len(ri) * irr.shape[1] * irr.shape[2] * 2, dtype=torch.uint8).pin_memory()
+            p.download_shard_async_ptr(abi.BUF_IRRADIANCE, pin.data_ptr())
+            p.wait_fence(p.download_fence())
+            assert np.array_equal(pin.numpy().view(np.uint16).reshape(len(ri), irr.shape[1], irr.shape[2]), p.irradiance[ri])
+        assert np.array_equal(irr, full.irradiance) and np.array_equal(dep, full.depth)
+        assert np.array_equal(rad, full.radiance)
+        for p in parts:
+            p.close()
+    full.close()
+
+
 def test_restore_resumes_bit_identically():
     sc = scenes.cornell_scene(res=32, counts=(4, 4, 4), rays=64, atlas_res=256)
     rots = [scenes.frame_rotation(f) for f in range(4)]

@@ -32,6 +32,28 @@ def test_shard_layout_partitions_probes_and_rows(engine_lib):
         ddgi.shard_layout(u, 0, 3)  # 3 does not divide Z = 8
 
 
+def test_interleaved_shard_layout_partitions_probes_and_rows(engine_lib):
+    """LUX_DDGI_FLAG_SHARD_INTERLEAVED: rank g owns the z-layers g, g + world, ...; the shards still partition probes and rows, and round k of the
+    exchange (layers k * world .. k * world + world - 1) is a contiguous block of rows to which rank g contributes the g-th part."""
+    u = abi.make_uniform((0, 0, 0), (1, 1, 1), (4, 3, 8), 32)
+    P, xy = abi.probe_count(u), 12
+    for world in (1, 2, 4, 8):
+        probes, irr_rows, dep_rows = [], [], []
+        for r in range(world):
+            st = ddgi.shard_layout(u, r, world, abi.FLAG_SHARD_INTERLEAVED)
+            assert st.probeCount == P // world and st.layerProbes == xy and st.layerStride == (world if world > 1 else 1)
+            own = st.own_probes()
+            assert all((p // xy) % world == r for p in own) and len(own) == st.probeCount
+            probes += own
+            irr_rows += st.own_rows(8)
+            dep_rows += st.own_rows(16)
+            for k in range(st.probeCount // xy):  # the rank's part of round k sits at offset r inside the round's block
+                assert st.own_rows(8)[k * 10] == 1 + (k * world + r) * 10 and st.own_rows(16)[k * 18] == 1 + (k * world + r) * 18
+        assert sorted(probes) == list(range(P))
+        assert sorted(irr_rows) == list(range(1, u.irradianceTextureHeight - 1))
+        assert sorted(dep_rows) == list(range(1, u.depthTextureHeight - 1))
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
