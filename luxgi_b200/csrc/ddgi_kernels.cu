@@ -1081,7 +1081,10 @@ constexpr int MARCH_WARPS = MARCH_WARPS_N;
 #endif
 constexpr int MARCH_CHUNK_RAYS  = 64;                                      // rays per pool fetch (2 probes x 32 directions): small, so
                                                                            // that shards with few rays per warp still balance
-constexpr int MARCH_REFILL_MIN  = 8;                                       // refill when this many lanes are idle
+// refill when this many lanes are idle.  Measured on B200 (profiles/r2_experiments.md): rows (C5) 6 / 8 / 12 / 16 / 20 / 24 idle lanes = 82.3 / 81.4 / 80.4 /
+// 79.8 / 82.7 / 86.2 ms, beams (C4) 3.26 / 3.21 / 3.17 / 3.18 / 3.30 / 3.60 ms: a refill (flush of the parked records, tickets, pool bookkeeping) costs
+// about as many instructions as a step, so fewer and fuller refills win until the idle lanes outweigh them
+constexpr int MARCH_REFILL_MIN_ROWS = 16, MARCH_REFILL_MIN_BEAMS = 12;
 constexpr unsigned int MARCH_BATCH       = MARCH_BATCH_N;                             // consecutive chunks a block draws at a time (rows: one unit x one cluster)
 constexpr unsigned int MARCH_BATCH_SLOTS = 32;                             // published batch ids kept per block (a waiter reads its slot at once)
 
@@ -1277,10 +1280,15 @@ __global__ void __launch_bounds__(256) classify_kernel(const __grid_constant__ T
 
 // The same pass for ROW chunks (TraceParams::beam == 0): there the 32 lanes of a record row are 32 x-adjacent probes of one ray, so a block takes
 // 32 probes x 16 consecutive ray ids, reads whole 512-byte record rows and transposes through shared memory to write 128-byte row segments.
-constexpr int CLASSIFY_ROW_RAYS    = 64;  // ray ids per block: a probe's output is one 512-byte segment per buffer (16 rays = 128-byte bursts ran at 62 % of the copy bandwidth)
-constexpr int CLASSIFY_ROW_WARPS   = 8;
+#ifndef CLASSIFY_ROW_RAYS_N
+#define CLASSIFY_ROW_RAYS_N 64
+#define CLASSIFY_ROW_WARPS_N 8
+#define CLASSIFY_ROW_BLOCKS_N 4
+#endif
+constexpr int CLASSIFY_ROW_RAYS    = CLASSIFY_ROW_RAYS_N;  // ray ids per block: a probe's output is one 512-byte segment per buffer (16 rays = 128-byte bursts ran at 62 % of the copy bandwidth)
+constexpr int CLASSIFY_ROW_WARPS   = CLASSIFY_ROW_WARPS_N;
 constexpr int CLASSIFY_ROW_RPT     = CLASSIFY_ROW_RAYS / CLASSIFY_ROW_WARPS; // record rows per warp
-__global__ void __launch_bounds__(32 * CLASSIFY_ROW_WARPS, 4) classify_rows_kernel(const __grid_constant__ TraceParams P, int rayGroups)
+__global__ void __launch_bounds__(32 * CLASSIFY_ROW_WARPS, CLASSIFY_ROW_BLOCKS_N) classify_rows_kernel(const __grid_constant__ TraceParams P, int rayGroups)
 {
     __shared__ uint2 sRad[32][CLASSIFY_ROW_RAYS + 1];
     __shared__ uint2 sDir[32][CLASSIFY_ROW_RAYS + 1];
