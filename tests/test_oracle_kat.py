@@ -414,3 +414,13 @@ def test_fma_blend_stays_within_one_fp16_ulp_of_the_literal_blend_over_64_frames
         oracle.set_unfused(False)
     assert worst_ulp <= 1, worst_ulp
     assert differing > 0  # the two readings are really different arithmetic (otherwise this test pins nothing)
+
+
+def test_depth_minus_one_quirk_is_unreachable_from_fp16():
+    """ProbeUpdate.glsl:75-77 replaces a ray distance of exactly -1 by maxDistance (`if (d == -1.0f)` after d = min(maxDistance, dist - 0.01)).  The
+    distances come from an RGBA16F image, and no fp16 value gives dist - 0.01f == -1.0f in binary32, so the branch is dead for every input the path
+    can see (unless maxDistance itself is -1).  The bit-exact kernels keep the statement; the tensor-core producer (blend_umma.inc) relies on this."""
+    with np.errstate(invalid="ignore"):
+        h = np.arange(65536, dtype=np.uint16).view(np.float16).astype(np.float32)
+        d = h - np.float32(0.01)
+    assert int((d == np.float32(-1.0)).sum()) == 0
