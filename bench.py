@@ -300,8 +300,11 @@ def run_lux(args):
     if args.unsorted:
         flags |= abi.FLAG_SHADE_UNSORTED
     flags |= args.extra_flags
-    if args.shards == "interleaved" and args.allgather == "lib":
-        flags |= abi.FLAG_SHARD_INTERLEAVED  # rank g owns z-layers g, g + N, ...: evenly loaded shards (no effect at N = 1)
+    shards = args.shards
+    if shards == "auto":  # blocks of 8 z-layers dealt out round-robin from 4 GPUs on (measured on C5: 33.9 -> 33.2 ms at N = 4, 17.7 -> 17.3 ms at N = 8; at
+        shards = "blocks8" if world >= 4 and u.probeCounts[2] % (world * 8) == 0 else "slabs"  # N = 2 the two slabs are evenly loaded already)
+    if shards != "slabs" and args.allgather == "lib":  # z-layers dealt out in blocks (no effect at N = 1)
+        flags |= abi.flag_shard_blocks({"interleaved": 0, "blocks2": 1, "blocks4": 2, "blocks8": 3}[shards])
     shard_rank, shard_world = (rank, world) if args.emulate_shard is None else tuple(int(x) for x in args.emulate_shard.split('/'))
     # The measured pipe runs lux_ddgi_update as shipped (blend weights on a second stream during the march, no stage events); the per-stage
     # times and the kernel roofline come from a second, serialized pass below (LUX_DDGI_FLAG_STAGE_TIMERS = one batch, one stream).
@@ -548,8 +551,8 @@ def run_lux(args):
             "ms_per_step": ms_per_step, "ms_per_update": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": workload_desc(args.workload, sc),
-            "parallelism": {"layout": (f"zlayers-interleaved{world}" if flags & abi.FLAG_SHARD_INTERLEAVED and world > 1 else f"zslab{world}"),
-                            "sharding": ("probe z-layers dealt out round-robin (rank g owns layers g, g + N, ...: evenly loaded), " if flags & abi.FLAG_SHARD_INTERLEAVED and world > 1 else "probe z-slabs, ") + "SDF + surface cache replicated, in-place NCCL all-gather of atlas rows per step"
+            "parallelism": {"layout": (f"zlayers-{shards}-{world}" if flags & abi.FLAG_SHARD_INTERLEAVED and world > 1 else f"zslab{world}"),
+                            "sharding": (f"probe z-layers dealt out round-robin in blocks ({shards}: rank g owns blocks g, g + N, ...: evenly loaded), " if flags & abi.FLAG_SHARD_INTERLEAVED and world > 1 else "probe z-slabs, ") + "SDF + surface cache replicated, in-place NCCL all-gather of atlas rows per step"
                             + ("" if world == 1 else ((" issued by lux_ddgi_update on the library's gather stream" if args.allgather == "lib" else " issued by the host (torch.distributed)")
                                                       + (" on the compute stream" if args.sync_allgather else ", overlapped with the next step's trace")))},
             "stage_ms": {"setup": setup_ms / args.steps, "trace": trace_launch_ms, "march": march_launch_ms, "shade": shade_launch_ms,
@@ -621,9 +624,9 @@ def main():
     ap.add_argument("--emulate-shard", default=None, help="r/w: run shard r of w on one GPU without any collective (profiling aid)")
     ap.add_argument("--allgather", default="lib", choices=["lib", "torch"],
                     help="N > 1: exchange inside lux_ddgi_update (ncclComm bound through the C ABI, default) or issued by this script through torch.distributed")
-    ap.add_argument("--shards", default="slabs", choices=["interleaved", "slabs"],
-                    help="N > 1: which probe z-layers a rank owns - one contiguous z-slab (default) or every N-th layer (LUX_DDGI_FLAG_SHARD_INTERLEAVED: "
-                         "evenly loaded ranks, but measured slower on C5: 18.5 ms against 17.7 ms at N = 8, the sparser shards reuse less of the SDF)")
+    ap.add_argument("--shards", default="auto", choices=["auto", "interleaved", "blocks2", "blocks4", "blocks8", "slabs"],
+                    help="N > 1: which probe z-layers a rank owns - one contiguous z-slab, or blocks of 1 / 2 / 4 / 8 layers dealt out round-robin "
+                         "(LUX_DDGI_FLAG_SHARD_INTERLEAVED: evenly loaded ranks; single layers cost locality, blocks of 8 keep it). auto = blocks8 from 4 GPUs on")
     ap.add_argument("--sync-allgather", action="store_true", help="all-gather on the compute stream (no overlap with the next trace)")
     ap.add_argument("--no-pipeline", action="store_true", help="A/B: one batch on one stream instead of two-stream probe batches")
     ap.add_argument("--extra-flags", type=lambda v: int(v, 0), default=0, help="A/B: LUX_DDGI_FLAG_* bits OR-ed into the context flags")

@@ -257,16 +257,20 @@ enum {
                                             * the tiled form).  Default: by probe count (>= 148 x 64 probes in the shard)                               */
     LUX_DDGI_FLAG_BLEND_TILES   = 1u << 13,/* force the tiled form (32-ray chunks, zero skipping per 8-texel group), for A/B                            */
     LUX_DDGI_FLAG_BLEND_TC_MMA_SYNC = 1u << 14,/* with BLEND_TC: the mma.sync kernels instead of the tcgen05 / TMA ones, for A/B                   */
-    LUX_DDGI_FLAG_SHARD_INTERLEAVED = 1u << 15,/* multi-GPU: rank g owns the probe z-layers g, g + world, g + 2 world, ... instead of one contiguous z-slab.  The cost of a
-                                            * probe layer depends on its height in the scene (layers that look at open sky or ground march shorter rays), so slabs are
-                                            * unevenly loaded; interleaved layers are not.  The exchange stays contiguous: round k all-gathers layers k world .. k world +
-                                            * world - 1, rank g contributing the g-th.  Results are identical.  Measured on C5 at 8 GPUs the balance (16.0 - 16.2 ms
-                                            * per rank instead of 13.2 - 15.7) is paid for by locality - a shard's probes are 8 x sparser in space and reuse less of the
-                                            * SDF they pull through L2 -: 18.5 ms per update against 17.7 ms with slabs.  For volumes whose layers differ more (half of
-                                            * them inside geometry) the trade goes the other way                                                                     */
+    LUX_DDGI_FLAG_SHARD_INTERLEAVED = 1u << 15,/* multi-GPU: the probe z-layers are dealt out to the ranks in blocks of B = LUX_DDGI_SHARD_BLOCK_LAYERS(flags) layers - rank g
+                                            * owns the blocks g, g + world, g + 2 world, ... - instead of one contiguous z-slab per rank.  The cost of a probe layer
+                                            * depends on its height in the scene (layers that look at open sky or ground march shorter rays), so slabs are unevenly
+                                            * loaded: C5 at 8 GPUs 13.2 - 15.7 ms of march per rank.  The exchange stays contiguous: round k all-gathers the blocks
+                                            * k world .. k world + world - 1, rank g contributing the g-th.  Results are identical.  B = 1 balances perfectly (16.0 -
+                                            * 16.2 ms) but a shard's probes are then 8 x sparser in space and reuse less of the SDF they pull through L2: 18.5 ms per
+                                            * update against 17.7 ms with slabs; larger blocks keep the locality                                     */
+    LUX_DDGI_FLAG_SHARD_BLOCK_SHIFT = 16,      /* bits 16..19: log2 of the layers per interleaved block (0 = single layers)                                            */
     LUX_DDGI_FLAG_MARCH_PROBE_MAJOR = 1u << 8 /* wavefront march in the round-1 work order (probe groups outermost, ray ids as they come) instead of direction
                                             * clusters outermost over spatially tiled probe groups; same results, for A/B of the DRAM traffic */
 };
+
+#define LUX_DDGI_SHARD_BLOCK_LAYERS(flags) (1 << (((flags) >> 16) & 0xF))
+#define LUX_DDGI_FLAG_SHARD_BLOCKS(log2Layers) (LUX_DDGI_FLAG_SHARD_INTERLEAVED | ((uint32_t)(log2Layers) << 16))
 
 typedef struct LuxDDGICreateInfo {
     int32_t  device;  /* CUDA device ordinal                                                              */
@@ -295,10 +299,11 @@ typedef struct LuxDDGIState {
     int32_t  irradianceRowBegin, irradianceRowCount; /* atlas rows owned by this shard (all-gather unit)  */
     int32_t  depthRowBegin, depthRowCount;
     uint64_t kernelLaunches;  /* kernels launched by this context since creation                          */
-    int32_t  layerProbes;     /* probes per z-layer (X * Y)                                                 */
-    int32_t  layerStride;     /* 1: the shard is one z-slab.  world (LUX_DDGI_FLAG_SHARD_INTERLEAVED): its k-th layer is layer rank + k * world, i.e.
+    int32_t  layerProbes;     /* probes per interleave unit: B z-layers of X * Y probes (B = 1 for a z-slab)   */
+    int32_t  layerStride;     /* 1: the shard is one z-slab.  world (LUX_DDGI_FLAG_SHARD_INTERLEAVED): its k-th unit is unit rank + k * world, i.e.
                                * shard-local probe l is probe probeBegin + (l / layerProbes) * layerStride * layerProbes + l % layerProbes and the
-                               * atlas rows of its k-th layer start at *RowBegin + k * layerStride * (10 | 18); *RowCount is the total of own rows */
+                               * atlas rows of its k-th unit start at *RowBegin + k * layerStride * unitLayers * (10 | 18); *RowCount = all own rows */
+    int32_t  unitLayers;      /* B: z-layers per interleave unit                                             */
 } LuxDDGIState;
 
 typedef struct LuxStageTimes { /* milliseconds of the last lux_ddgi_update, needs FLAG_STAGE_TIMERS */

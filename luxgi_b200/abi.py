@@ -152,13 +152,14 @@ class State(C.Structure):
         ("kernelLaunches", C.c_uint64),
         ("layerProbes", C.c_int32),
         ("layerStride", C.c_int32),
+        ("unitLayers", C.c_int32),
     ]
 
     def own_rows(self, side):
-        """Atlas rows owned by the shard (side = 8 | 16), in shard-local layer order: what lux_ddgi_download_shard_async packs."""
-        S, begin = side + 2, (self.irradianceRowBegin if side == 8 else self.depthRowBegin)
-        layers = self.probeCount // self.layerProbes
-        return [begin + k * self.layerStride * S + r for k in range(layers) for r in range(S)]
+        """Atlas rows owned by the shard (side = 8 | 16), in shard-local order: what lux_ddgi_download_shard_async packs."""
+        S, begin = (side + 2) * self.unitLayers, (self.irradianceRowBegin if side == 8 else self.depthRowBegin)  # rows per interleave unit
+        units = self.probeCount // self.layerProbes
+        return [begin + k * self.layerStride * S + r for k in range(units) for r in range(S)]
 
     def own_probes(self):
         """Probe ids of the shard in shard-local order."""
@@ -216,6 +217,13 @@ FLAG_BLEND_LISTS = 1 << 12  # force the list form of the FP32 blend (default fro
 FLAG_BLEND_TILES = 1 << 13  # force the tiled form
 FLAG_BLEND_TC_MMA_SYNC = 1 << 14  # with FLAG_BLEND_TC: mma.sync kernels instead of tcgen05 / TMA
 FLAG_SHARD_INTERLEAVED = 1 << 15  # multi-GPU: rank g owns z-layers g, g + world, ... (balanced) instead of one z-slab
+
+
+def flag_shard_blocks(log2_layers):
+    """LUX_DDGI_FLAG_SHARD_BLOCKS: interleave blocks of 2**log2_layers z-layers (0 = single layers)."""
+    return FLAG_SHARD_INTERLEAVED | (int(log2_layers) << 16)
+
+
 FLAG_MARCH_PROBE_MAJOR = 1 << 8  # A/B: the round-1 march work order
 BUF_RADIANCE, BUF_DIRECTION_DISTANCE, BUF_IRRADIANCE, BUF_DEPTH, BUF_IRRADIANCE_PREV, BUF_DEPTH_PREV, BUF_GLOBAL_SDF, BUF_GLOBAL_SDF_MIP = range(8)
 

@@ -327,7 +327,8 @@ static int marchOrder(LuxDDGIContext& c, bool beam)
         const int id = g * unit, x = id % X, y = (id / X) % Y, z = id / (X * Y); // first probe of the unit, shard-local
         // interleaved shards (LuxDDGIState::layerStride = world): consecutive LOCAL layers are `world` layers apart, so a tile takes fewer of them to
         // stay as compact in the scene (measured at N = 2: 16 local layers per tile made the march 2.7 % slower than z-slabs)
-        const int tz = c.layerStride > 1 ? std::max(1, 16 / c.layerStride) : 16;
+        const int B  = c.layerStride > 1 ? c.layerProbes / (X * Y) : 16; // layers per interleaved block
+        const int tz = c.layerStride > 1 ? (B >= 2 ? std::min(16, B) : std::max(1, 16 / c.layerStride)) : 16;
         const uint64_t tile = spread3((uint32_t)(x / 32)) | (spread3((uint32_t)(y / 16)) << 1) | ((uint64_t)spread3((uint32_t)(z / tz)) << 2);
         const uint64_t in = ((uint64_t)(z % tz) << 16) | ((uint64_t)(y % 16) << 8) | (uint64_t)(x % 32);
         keyed[g] = {identity ? (uint64_t)g : ((tile << 24) | in), (uint32_t)g};
@@ -763,15 +764,23 @@ static void shardLayout(const LuxDDGIUniform& u, int rank, int world, uint32_t f
     const int  xy     = u.probeCounts[0] * u.probeCounts[1];
     const int  zCount = u.probeCounts[2] / world;
     const bool inter  = (flags & LUX_DDGI_FLAG_SHARD_INTERLEAVED) != 0 && world > 1;
-    const int  zBegin = inter ? rank : zCount * rank;
+    const int  B      = inter ? LUX_DDGI_SHARD_BLOCK_LAYERS(flags) : 1; // layers per interleave unit (validated by the callers: world * B divides Z)
+    const int  zBegin = inter ? rank * B : zCount * rank;
     out->probeBegin         = zBegin * xy;
     out->probeCount         = zCount * xy;
     out->irradianceRowBegin = 1 + zBegin * (LUX_IRRADIANCE_OCT_SIZE + 2);
     out->irradianceRowCount = zCount * (LUX_IRRADIANCE_OCT_SIZE + 2);
     out->depthRowBegin      = 1 + zBegin * (LUX_DEPTH_OCT_SIZE + 2);
     out->depthRowCount      = zCount * (LUX_DEPTH_OCT_SIZE + 2);
-    out->layerProbes        = xy;
+    out->layerProbes        = B * xy;
     out->layerStride        = inter ? world : 1;
+    out->unitLayers         = B;
+}
+static bool shardFlagsValid(const LuxDDGIUniform& u, int world, uint32_t flags)
+{
+    if (!(flags & LUX_DDGI_FLAG_SHARD_INTERLEAVED) || world <= 1)
+        return true;
+    return u.probeCounts[2] % (world * LUX_DDGI_SHARD_BLOCK_LAYERS(flags)) == 0;
 }
 // does this shard own every row of [rowBegin, rowBegin + rowCount) of an atlas with `side` + 2 rows per z-layer?
 static bool ownsRows(const LuxDDGIContext* c, int side, int rowBegin, int rowCount)
@@ -783,11 +792,15 @@ static bool ownsRows(const LuxDDGIContext* c, int side, int rowBegin, int rowCou
         return true;
     if (rowBegin < 1)
         return false; // the outer pad row belongs to nobody
-    const int first = (rowBegin - 1) / S, last = (rowBegin + rowCount - 2) / S, zBegin = st.probeBegin / st.layerProbes, zCount = st.probeCount / st.layerProbes;
+    const int xy = c->uniform.probeCounts[0] * c->uniform.probeCounts[1];
+    const int first = (rowBegin - 1) / S, last = (rowBegin + rowCount - 2) / S, zBegin = st.probeBegin / xy, zCount = st.probeCount / xy;
     for (int z = first; z <= last; z++)
     {
-        const int k = z - zBegin;
-        if (k < 0 || k % st.layerStride != 0 || k / st.layerStride >= zCount)
+        const int k = z - zBegin; // layers past the shard's first one
+        if (k < 0)
+            return false;
+        const int unit = k / st.unitLayers; // in units of B layers: own units are every layerStride-th
+        if (unit % st.layerStride != 0 || (unit / st.layerStride) * st.unitLayers + k % st.unitLayers >= zCount)
             return false;
     }
     return true;
@@ -874,6 +887,9 @@ int lux_ddgi_create(const LuxDDGIUniform* uniform, const LuxDDGICreateInfo* info
         return fail(LUX_ERR_INVALID_ARG, "rank %d outside world %d", ci.rank, ci.world);
     if (uniform->probeCounts[2] % ci.world != 0)
         return fail(LUX_ERR_INVALID_ARG, "world %d must divide probeCounts.z %d (z-slab sharding)", ci.world, uniform->probeCounts[2]);
+    if (!shardFlagsValid(*uniform, ci.world, ci.flags))
+        return fail(LUX_ERR_INVALID_ARG, "world %d x %d layers per interleaved block must divide probeCounts.z %d", ci.world, LUX_DDGI_SHARD_BLOCK_LAYERS(ci.flags),
+                    uniform->probeCounts[2]);
 
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -1771,10 +1787,10 @@ static int enqueueAllGather(LuxDDGIContext* c)
     LUX_CUDA(cudaEventRecord(c->evBlendDone, c->stream));
     LUX_CUDA(cudaStreamWaitEvent(c->gatherStream, c->evBlendDone, 0));
     int rc = n->groupStart();
-    // z-slabs: one all-gather per atlas.  Interleaved layers: round k gathers the layers k * world .. k * world + world - 1 (contiguous rows), this rank
-    // contributing its k-th layer; all rounds of both atlases in one group.
+    // z-slabs: one all-gather per atlas.  Interleaved blocks: round k gathers the blocks k * world .. k * world + world - 1 (contiguous rows), this rank
+    // contributing its k-th block; all rounds of both atlases in one group.
     const int rounds = st.layerStride == 1 ? 1 : st.probeCount / st.layerProbes;
-    const int irrS = LUX_IRRADIANCE_OCT_SIZE + 2, depS = LUX_DEPTH_OCT_SIZE + 2;
+    const int irrS = (LUX_IRRADIANCE_OCT_SIZE + 2) * st.unitLayers, depS = (LUX_DEPTH_OCT_SIZE + 2) * st.unitLayers; // rows per interleave unit
     for (int k = 0; k < rounds && rc == 0; k++)
     {
         const size_t irrOwn = st.layerStride == 1 ? (size_t)st.irradianceRowBegin : (size_t)st.irradianceRowBegin + (size_t)k * st.layerStride * irrS;
@@ -2010,10 +2026,10 @@ int lux_ddgi_download_shard_async(LuxDDGIContext* c, LuxBufferId id, void* pinne
     LuxDDGIState st{};
     shardLayout(c->uniform, c->rank, c->world, c->flags, &st);
     const size_t rowBytes = isIrr ? (size_t)c->uniform.irradianceTextureWidth * 8 : (size_t)c->uniform.depthTextureWidth * 4;
-    const int    S = (isIrr ? LUX_IRRADIANCE_OCT_SIZE : LUX_DEPTH_OCT_SIZE) + 2, layers = st.probeCount / st.layerProbes;
+    const int    S = ((isIrr ? LUX_IRRADIANCE_OCT_SIZE : LUX_DEPTH_OCT_SIZE) + 2) * st.unitLayers, layers = st.probeCount / st.layerProbes; // rows per unit, units
     const int    rowBegin = isIrr ? st.irradianceRowBegin : st.depthRowBegin;
     LUX_CUDA(cudaStreamWaitEvent(c->downStream, isIrr ? c->evIrrDone : c->evDepthDone, 0));
-    // `layers` blocks of S rows each, layerStride * S rows apart in the atlas, packed on the host: one strided copy
+    // `layers` units of S rows each, layerStride * S rows apart in the atlas, packed on the host: one strided copy
     LUX_CUDA(cudaMemcpy2DAsync(pinnedHost, (size_t)S * rowBytes, (const char*)b->ptr + (size_t)rowBegin * rowBytes, (size_t)st.layerStride * S * rowBytes,
                                (size_t)S * rowBytes, (size_t)layers, cudaMemcpyDeviceToHost, c->downStream));
     LUX_CUDA(cudaEventRecord(c->evCopyDone, c->downStream));
@@ -2070,6 +2086,8 @@ int lux_ddgi_shard_layout_ex(const LuxDDGIUniform* u, int32_t rank, int32_t worl
         return fail(LUX_ERR_INVALID_ARG, "rank %d outside world %d", rank, world);
     if (u->probeCounts[2] <= 0 || u->probeCounts[2] % world != 0)
         return fail(LUX_ERR_INVALID_ARG, "world %d must divide probeCounts.z %d (z-slab sharding)", world, u->probeCounts[2]);
+    if (!shardFlagsValid(*u, world, flags))
+        return fail(LUX_ERR_INVALID_ARG, "world %d x %d layers per interleaved block must divide probeCounts.z %d", world, LUX_DDGI_SHARD_BLOCK_LAYERS(flags), u->probeCounts[2]);
     *out = LuxDDGIState{};
     shardLayout(*u, rank, world, flags, out);
     return LUX_OK;

@@ -229,13 +229,13 @@ def test_interleaved_layer_shards_reassemble_the_full_volume(oracle):
     sc = scenes.cornell_scene(res=32, counts=(5, 3, 8), rays=96, atlas_res=256)
     rots = [scenes.frame_rotation(f) for f in range(2)]
     full = run_engine(sc, rots)
-    for blend in (abi.FLAG_BLEND_LISTS, abi.FLAG_BLEND_TILES):
-        parts = [run_engine(sc, rots, flags=abi.FLAG_SHARD_INTERLEAVED | blend, rank=r, world=4) for r in range(4)]
+    for blend, log2b in ((abi.FLAG_BLEND_LISTS, 0), (abi.FLAG_BLEND_TILES, 0), (abi.FLAG_BLEND_LISTS, 1)):  # single layers, blocks of 2 layers
+        parts = [run_engine(sc, rots, flags=abi.flag_shard_blocks(log2b) | blend, rank=r, world=4) for r in range(4)]
         irr, dep = np.zeros_like(full.irradiance), np.zeros_like(full.depth)
         rad = np.zeros_like(full.radiance)
         for p in parts:
             st = p.state()
-            assert st.layerStride == 4 and st.probeCount == full.probe_count // 4
+            assert st.layerStride == 4 and st.unitLayers == 1 << log2b and st.probeCount == full.probe_count // 4
             ri, rd = st.own_rows(8), st.own_rows(16)
             irr[ri], dep[rd] = p.irradiance[ri], p.depth[rd]
             other = np.ones(irr.shape[0], dtype=bool)

@@ -33,25 +33,33 @@ def test_shard_layout_partitions_probes_and_rows(engine_lib):
 
 
 def test_interleaved_shard_layout_partitions_probes_and_rows(engine_lib):
-    """LUX_DDGI_FLAG_SHARD_INTERLEAVED: rank g owns the z-layers g, g + world, ...; the shards still partition probes and rows, and round k of the
-    exchange (layers k * world .. k * world + world - 1) is a contiguous block of rows to which rank g contributes the g-th part."""
-    u = abi.make_uniform((0, 0, 0), (1, 1, 1), (4, 3, 8), 32)
+    """LUX_DDGI_FLAG_SHARD_INTERLEAVED: the z-layers are dealt out in blocks of B layers, rank g owning the blocks g, g + world, ...; the shards still
+    partition probes and rows, and round k of the exchange (blocks k * world .. k * world + world - 1) is a contiguous range of rows to which rank g
+    contributes the g-th part."""
+    u = abi.make_uniform((0, 0, 0), (1, 1, 1), (4, 3, 16), 32)
     P, xy = abi.probe_count(u), 12
-    for world in (1, 2, 4, 8):
-        probes, irr_rows, dep_rows = [], [], []
-        for r in range(world):
-            st = ddgi.shard_layout(u, r, world, abi.FLAG_SHARD_INTERLEAVED)
-            assert st.probeCount == P // world and st.layerProbes == xy and st.layerStride == (world if world > 1 else 1)
-            own = st.own_probes()
-            assert all((p // xy) % world == r for p in own) and len(own) == st.probeCount
-            probes += own
-            irr_rows += st.own_rows(8)
-            dep_rows += st.own_rows(16)
-            for k in range(st.probeCount // xy):  # the rank's part of round k sits at offset r inside the round's block
-                assert st.own_rows(8)[k * 10] == 1 + (k * world + r) * 10 and st.own_rows(16)[k * 18] == 1 + (k * world + r) * 18
-        assert sorted(probes) == list(range(P))
-        assert sorted(irr_rows) == list(range(1, u.irradianceTextureHeight - 1))
-        assert sorted(dep_rows) == list(range(1, u.depthTextureHeight - 1))
+    for log2b in (0, 1, 2):
+        B = 1 << log2b
+        for world in (1, 2, 4):
+            probes, irr_rows, dep_rows = [], [], []
+            for r in range(world):
+                st = ddgi.shard_layout(u, r, world, abi.flag_shard_blocks(log2b))
+                inter = world > 1
+                assert st.probeCount == P // world and st.layerStride == (world if inter else 1)
+                assert st.unitLayers == (B if inter else 1) and st.layerProbes == st.unitLayers * xy
+                own = st.own_probes()
+                assert len(own) == st.probeCount and (not inter or all(((p // xy) // B) % world == r for p in own))
+                probes += own
+                irr_rows += st.own_rows(8)
+                dep_rows += st.own_rows(16)
+                for k in range(st.probeCount // st.layerProbes):  # the rank's part of round k sits at offset r inside the round's block of rows
+                    if inter:
+                        assert st.own_rows(8)[k * 10 * B] == 1 + (k * world + r) * 10 * B and st.own_rows(16)[k * 18 * B] == 1 + (k * world + r) * 18 * B
+            assert sorted(probes) == list(range(P))
+            assert sorted(irr_rows) == list(range(1, u.irradianceTextureHeight - 1))
+            assert sorted(dep_rows) == list(range(1, u.depthTextureHeight - 1))
+    with pytest.raises(ddgi.LuxError):
+        ddgi.shard_layout(u, 0, 4, abi.flag_shard_blocks(3))  # 4 ranks x 8 layers do not divide Z = 16
 
 
 def _free_port():
