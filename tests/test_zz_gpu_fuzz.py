@@ -2,7 +2,8 @@
 
 The same scene families the oracle is fuzzed on against the reference's shipped SPIR-V (tests/golden/fuzz_oracle_vs_spirv.py: the Cornell room
 with 1-4 cascades, open cities with random probe placement under a 2x2-texel sky, probe grids pushed into geometry and onto cascade faces), with
-fixed seeds, two frames each, texture and load SDF paths.  Ray buffers and atlases must be bit-identical to the oracle's."""
+fixed seeds, two frames each, texture and load SDF paths, tiled and list form of the FP32 blend, row and beam shape of the march.  Ray buffers and
+atlases must be bit-identical to the oracle's."""
 import numpy as np
 import pytest
 
@@ -22,7 +23,7 @@ def test_fuzz_engine_vs_oracle(oracle, seed):
         orc = oracle.OraclePipeline(sc)
         for r in rots:
             orc.update(r)
-        for flags in (0, abi.FLAG_SDF_LOADS):
+        for flags in (0, abi.FLAG_SDF_LOADS, abi.FLAG_BLEND_LISTS | abi.FLAG_MARCH_ROWS, abi.FLAG_BLEND_LISTS | abi.FLAG_MARCH_BEAMS | abi.FLAG_SDF_LOADS):
             pipe = ddgi.DDGIPipeline(sc.uniform, flags=flags)
             pipe.set_scene(sc)
             for r in rots:
