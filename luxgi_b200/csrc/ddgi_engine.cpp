@@ -405,7 +405,7 @@ static int initializeProbeGrid(LuxDDGIContext& c)
     if ((rc = allocZero(c, c.nzIrr, (size_t)c.raysPadded * sizeof(uint32_t))) != LUX_OK) return rc;
     if ((rc = allocZero(c, c.nzDepth, (size_t)c.raysPadded * sizeof(uint32_t))) != LUX_OK) return rc;
     if ((rc = allocZero(c, c.origins, (size_t)c.probeCount * sizeof(float4))) != LUX_OK) return rc;
-    if ((rc = allocZero(c, c.chunkCounter, 64)) != LUX_OK) return rc;
+    if ((rc = allocZero(c, c.chunkCounter, 64 + lux::trace_shade_pool_bytes())) != LUX_OK) return rc; // 16 counters + the shade's per-SM pools
     if (!(c.flags & LUX_DDGI_FLAG_TRACE_SIMPLE))
     {
         const size_t nrec = lux::trace_record_capacity(c.probeCount, u.raysPerProbe);
@@ -600,6 +600,8 @@ static int launch(LuxDDGIContext& c, cudaStream_t s, bool timers)
         p.binCounts    = (uint32_t*)c.binCounts.ptr;
         p.binBlockSums = (uint32_t*)c.binBlockSums.ptr;
         p.hitCount     = counters + 1;
+        p.shadeCounter = counters + 3;
+        p.shadePools   = reinterpret_cast<unsigned long long*>(counters + 16);
         p.sortedIdx    = (uint32_t*)c.sortedIdx.ptr;
     }
     const int variant = (c.flags & LUX_DDGI_FLAG_TRACE_SIMPLE) ? 0 : (c.sdfTex ? 2 : 1);

@@ -1091,6 +1091,7 @@ constexpr unsigned int MARCH_BATCH_SLOTS = 32;                             // pu
 enum RayKind : uint32_t { RAY_MISS = 0, RAY_INSIDE = 1, RAY_HIT = 2 };
 
 constexpr int SORT_CELLS_PER_CHUNK = 64;
+constexpr unsigned int SHADE_SM_GROUP = 8, SHADE_POOL_SLOTS = 32, SHADE_POOL_SMS = 256; // see shade_sorted_kernel
 // Bin of a hit position.  Only groups work, never enters a result: plain (approximate) arithmetic is fine.
 __device__ __forceinline__ uint32_t shade_bin(const TraceParams& P, f3 pos)
 {
@@ -1471,8 +1472,41 @@ __global__ void __launch_bounds__(256, SHADE_BLOCKS_PER_SM) shade_sorted_kernel(
     const LuxGlobalSDFData& data = P.sdf;
     const uint32_t hits = *P.hitCount;
     const float texelOffset = __fdiv_rn(1.0f, data.resolution);
-    for (uint32_t t = blockIdx.x * 256u + threadIdx.x; t < hits; t += gridDim.x * 256u)
+    // Segments of 256 consecutive hits are handed out per SM: the blocks resident on one SM draw tickets from that SM's counter (in global memory, indexed
+    // by %smid) and every SHADE_SM_GROUP consecutive tickets share one group of adjacent segments fetched from the global counter, so co-resident blocks
+    // shade neighbouring hits - same bins, same objects, tiles and SDF neighbourhood in L1 - instead of segments 148 x 256 hits apart (static striding).
+    __shared__ uint32_t sSegment;
+    unsigned int smid;
+    asm("mov.u32 %0, %%smid;" : "=r"(smid));
+    unsigned long long* pool = P.shadePools + (size_t)(smid % SHADE_POOL_SMS) * (1 + SHADE_POOL_SLOTS);
+    while (true)
     {
+        if (threadIdx.x == 0)
+        {
+            const unsigned int tk = (unsigned int)atomicAdd(pool, 1ull), seq = tk / SHADE_SM_GROUP, slot = seq % SHADE_POOL_SLOTS;
+            unsigned int grp;
+            if (tk % SHADE_SM_GROUP == 0)
+            {
+                grp = atomicAdd(P.shadeCounter, 1u);
+                atomicExch(pool + 1 + slot, ((unsigned long long)(seq + 1u) << 32) | grp);
+            }
+            else
+            {
+                unsigned long long v;
+                while ((unsigned int)((v = atomicAdd(pool + 1 + slot, 0ull)) >> 32) != seq + 1u)
+                    __nanosleep(40);
+                grp = (unsigned int)v;
+            }
+            sSegment = grp * SHADE_SM_GROUP + tk % SHADE_SM_GROUP;
+        }
+        __syncthreads();
+        const unsigned long long t64 = (unsigned long long)sSegment * 256ull + threadIdx.x;
+        __syncthreads();
+        if (t64 - threadIdx.x >= hits)
+            break;
+        if (t64 >= hits)
+            continue;
+        const uint32_t t = (uint32_t)t64;
         const uint32_t gi   = __ldg(P.sortedIdx + t);
         const uint32_t g    = gi & 0x3fffffffu, hc = gi >> 30;
         const RayOfRecord rr = march_ray(P, g);
@@ -2919,6 +2953,7 @@ size_t trace_record_count(int probeCount, int raysPerProbe, bool beam)
     return ((size_t)probeCount + unit - 1) / unit * unit * slots; // chunks x 64
 }
 size_t trace_record_capacity(int probeCount, int raysPerProbe) { return trace_record_count(probeCount, raysPerProbe, false); }
+size_t trace_shade_pool_bytes() { return (size_t)SHADE_POOL_SMS * (1 + SHADE_POOL_SLOTS) * sizeof(unsigned long long); }
 
 void launch_probe_origins(const TraceParams& p, cudaStream_t s)
 {
@@ -2951,6 +2986,8 @@ static int launch_shade_sorted(const TraceParams& p, cudaStream_t s)
     long long blocks = (long long)(records + 255) / 256;
     if (blocks > 148ll * SHADE_BLOCKS_PER_SM)
         blocks = 148ll * SHADE_BLOCKS_PER_SM;
+    cudaMemsetAsync(p.shadePools, 0, trace_shade_pool_bytes(), s);
+    cudaMemsetAsync(p.shadeCounter, 0, sizeof(unsigned int), s);
     shade_sorted_kernel<TEX><<<(unsigned)blocks, 256, 0, s>>>(p);
     return 6;
 }

@@ -80,6 +80,8 @@ struct TraceParams
     uint32_t* binBlockSums; // [trace_sort_blocks]
     uint32_t* hitCount;     // [1] number of hits = length of sortedIdx in use
     uint32_t* sortedIdx;    // [records] record indices in bin order
+    unsigned long long* shadePools; // [256][1 + 32] per-SM segment tickets of shade_sorted_kernel (zeroed per launch)
+    unsigned int*       shadeCounter; // [1] next group of segments
 };
 
 struct BlendParams
@@ -148,6 +150,7 @@ int    launch_trace(const TraceParams& p, int variant, unsigned int* chunkCounte
 constexpr int MARCH_CLUSTER_RAYS = 32; // directions per cluster = lanes of a warp
 size_t trace_record_count(int probeCount, int raysPerProbe, bool beam);
 size_t trace_record_capacity(int probeCount, int raysPerProbe); // enough for either chunk shape
+size_t trace_shade_pool_bytes();
 size_t trace_sort_bins();   // bins of the sorted shade's counting sort (culling chunks x octants, padded to the scan's block size)
 size_t trace_sort_blocks(); // scan blocks over those bins
 void   launch_probe_origins(const TraceParams& p, cudaStream_t s);
