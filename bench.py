@@ -546,6 +546,21 @@ def run_lux(args):
                                     "blend_irradiance_lists_kernel+blend_depth_lists_kernel" if probes_rank >= 148 * 64 and not flags & abi.FLAG_BLEND_TILES
                                     else "blend_irradiance_kernel+blend_depth_kernel")
         roofs["blend"]["fp32_tfma_per_s_dense_equivalent"] = probes_rank * R * 704 / (blend_launch_ms * 1e-3) / 1e12
+        # Issue-slot roofline of the march (what actually binds it): warp instructions per launch from the committed ncu capture of this
+        # configuration, divided by the launch time measured here, against 4 schedulers x SMs x the SM clock sampled during the timed region.
+        issue_roof = None
+        try:
+            inst = traffic.get("march_kernel_warp_instructions")
+            mhz = (clocks or {}).get("sm_mhz")
+            if inst and mhz and march_launch_ms > 0 and probes_rank == sc.probes:
+                sms = torch.cuda.get_device_properties(dev).multi_processor_count
+                peak = 4.0 * sms * mhz * 1e6
+                ach = inst / (march_launch_ms * 1e-3)
+                issue_roof = {"bound": "issue", "kernel": "march_kernel", "achieved": ach / 1e9, "peak": peak / 1e9, "unit": "G warp instructions/s",
+                              "frac": ach / peak, "warp_instructions_per_launch": inst,
+                              "source": "profiles/traffic.json (smsp__inst_executed.sum of the ncu capture of this configuration) / launch time measured live"}
+        except Exception:
+            issue_roof = None
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "ms_per_update": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -563,6 +578,7 @@ def run_lux(args):
             "trace_rays_per_s": probes_rank * world * R / (trace_launch_ms * 1e-3),
             "per_rank_trace_blend_ms": per_rank,
             "roofline": roofs[dominant],
+            "roofline_issue": issue_roof,
             "roofline_stages": {k: v for k, v in roofs.items() if k != dominant and v["ms_per_launch"] > 0},
             "clocks": clocks,
             "e2e": None if e2e_value is None else {"value": e2e_value, "unit": UNIT, "ms_per_update": e2e_s / args.steps * 1e3,
